@@ -1,0 +1,53 @@
+// Shared helpers for the dl4ds_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/dl4ds_b200.h"
+
+namespace dl4ds {
+
+// thread-local last-error text behind dl4ds_last_error()
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define DL4DS_REQUIRE(cond, code, ...)                 \
+    do {                                               \
+        if (!(cond)) {                                 \
+            ::dl4ds::set_error(__VA_ARGS__);           \
+            return (code);                             \
+        }                                              \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case DL4DS_ACT_RELU: return fmaxf(v, 0.0f);
+        case DL4DS_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+        case DL4DS_ACT_TANH: return tanhf(v);
+        default: return v;
+    }
+}
+
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+    switch (act) {
+        case DL4DS_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
+        case DL4DS_ACT_SIGMOID: return y * (1.0f - y);
+        case DL4DS_ACT_TANH: return 1.0f - y * y;
+        default: return 1.0f;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dl4ds

@@ -1,0 +1,208 @@
+/*
+ * dl4ds_b200 -- C ABI of the B200-native DL4DS convolutional super-resolution hot path.
+ *
+ * The reference (carlos-gg/dl4ds @ 232ae49) has no FFI: its hot path is whatever TensorFlow/Keras
+ * executes for the graphs built in dl4ds/models/ and the step logic in dl4ds/training/.  This
+ * library is the NEW lower boundary that replaces that runtime.  Every
+ * entry point below names the reference call site(s) whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - plain C, no torch types; pointers are DEVICE pointers unless stated otherwise;
+ *  - every function returns int: 0 = OK, negative = DL4DS_E_*; dl4ds_last_error() gives text;
+ *  - no allocation inside: the caller owns every buffer, including workspaces;
+ *  - every launch is asynchronous on the cudaStream_t passed as `void* stream`;
+ *  - tensors are dense fp32 NHWC.  `*_ld` arguments are the channel pitch (elements between
+ *    consecutive pixels) so a tensor may live inside a wider concat buffer; the pointer already
+ *    includes the channel offset;
+ *  - weights use the Keras layouts: Conv2D (kh,kw,Cin,Cout); Conv2DTranspose (kh,kw,Cout,Cin);
+ *    ConvLSTM2D (kh,kw,Cin,4F)/(kh,kw,F,4F) gate order i,f,c,o; LocallyConnected2D 1x1
+ *    W[H,W,Cin,F], b[H,W,F]; Dense (in,out);
+ *  - parameter-gradient outputs ACCUMULATE (+=) into their destination (the flat gradient arena is
+ *    zeroed once per step); this is what makes shared-weight layers (SubpixelConvolutionBlock
+ *    conv2x, DeconvolutionBlock T2 -- blocks.py:415,421-422,528-531) sum over applications.
+ */
+#ifndef DL4DS_B200_H
+#define DL4DS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DL4DS_OK             0
+#define DL4DS_E_BADARG      -1
+#define DL4DS_E_SHAPE       -2
+#define DL4DS_E_UNSUPPORTED -3
+#define DL4DS_E_CUDA        -4
+#define DL4DS_E_NCCL        -5
+
+/* activation codes (tf.keras.layers.Activation, blocks.py:75) */
+#define DL4DS_ACT_NONE    0
+#define DL4DS_ACT_RELU    1
+#define DL4DS_ACT_SIGMOID 2
+#define DL4DS_ACT_TANH    3
+
+/* math modes for the convolution kernels */
+#define DL4DS_MATH_FP32    0   /* CUDA-core fp32 FMA (exact fp32 semantics)                     */
+#define DL4DS_MATH_TF32X3  1   /* tcgen05 kind::tf32, 3-term split (hi*hi+hi*lo+lo*hi), ~fp32   */
+#define DL4DS_MATH_TF32    2   /* tcgen05 kind::tf32, single pass (10-bit mantissa operands)    */
+
+/* weight indexing modes of dl4ds_conv2d_fwd */
+#define DL4DS_W_HWIO        0  /* B[(tap,c),n] = w[tap][c][n]            (Conv2D forward)          */
+#define DL4DS_W_FLIP_T      1  /* B[(tap,c),n] = w[flip(tap)][n][c]      (Conv2D dgrad, ConvT fwd) */
+
+const char* dl4ds_last_error(void);
+int dl4ds_version(void);
+/* 1 if the device behind the current context is sm_100 (tcgen05 paths usable). */
+int dl4ds_device_is_sm100(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution family.  One generalized implicit-GEMM entry point covers:
+ *   Conv2D forward                       blocks.py:49-61,91,97,208,299; sp_postups.py:134,156
+ *   Conv2D input gradient (dgrad)        what TF's GradientTape derives for the same layers
+ *   Conv2DTranspose forward              blocks.py:508-516 (DeconvolutionBlock)
+ *   Conv2DTranspose input gradient       = strided Conv2D forward
+ *
+ * y[n,oy,ox,co] = act( sum_{kh,kw,c} x[n,(oy*stride+kh-pad_t)/up,(ox*stride+kw-pad_l)/up,c] * B[(kh,kw,c),co]
+ *                      + bias[co] + res[n,oy,ox,co] )
+ * where a tap only contributes if the numerator is divisible by `up` and the source pixel is in
+ * range (zero padding).  `up`>1 is the fractional stride used by Conv2DTranspose forward / strided
+ * dgrad.  If d2s_r>1 the result is stored through tf.nn.depth_to_space(., r) (NHWC DCR order,
+ * blocks.py:427): y has shape (N, Ho*r, Wo*r, Cout/(r*r)) and `res` must be NULL.
+ * bias and res may be NULL.  beta=1 accumulates into y (y += result; only with act NONE, no d2s).
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias,
+                     const float* res, int res_ld, float* y, int y_ld,
+                     int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
+                     int KH, int KW, int stride, int up, int pad_t, int pad_l,
+                     int wmode, int act, int d2s_r, int beta, int math_mode, void* stream);
+
+/* Weight gradient of the same family (accumulating):
+ *   dw[kh][kw][a][b] += sum_{n,oy,ox} P[n,oy*stride+kh-pad_t,ox*stride+kw-pad_l,a] * Q[n,oy,ox,b]
+ * Conv2D: P = layer input (Ca=Cin), Q = dZ (Cb=Cout).  Conv2DTranspose (kernel (kh,kw,Cout,Cin)):
+ * P = dY (Ca=Cout), Q = layer input (Cb=Cin).  (Hp,Wp) is P's grid, (Hq,Wq) is Q's grid.
+ * `ws` is a caller-owned workspace of dl4ds_conv2d_wgrad_workspace_bytes() bytes (may be NULL if 0). */
+int64_t dl4ds_conv2d_wgrad_workspace_bytes(int N, int Hq, int Wq, int Ca, int Cb, int KH, int KW,
+                                           int math_mode);
+int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float* dw,
+                       int N, int Hp, int Wp, int Ca, int Hq, int Wq, int Cb,
+                       int KH, int KW, int stride, int pad_t, int pad_l,
+                       void* ws, int math_mode, void* stream);
+
+/* Backward of the fused bias+activation(+depth_to_space) epilogue:
+ *   dz = dy * act'(y)   (act' expressed through the stored output y; NONE: dz = dy)
+ *   dbias[c] += sum_pixels dz[.,c]          (dbias may be NULL)
+ * With d2s_r>1 (y unused, act must be NONE) dy is the HR-layout gradient (N,Ho*r,Wo*r,C/(r*r)) and
+ * dz is written un-shuffled (N,Ho,Wo,C) -- the space_to_depth adjoint of blocks.py:427.
+ * dz may alias dy when d2s_r==1.  n_pix = N*Ho*Wo. */
+int dl4ds_bias_act_bwd(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld,
+                       float* dbias, int N, int Ho, int Wo, int C, int act, int d2s_r, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Element-wise helpers (Add -- sp_postups.py:164; Concatenate -- blocks.py:276, sp_postups.py:186,201)
+ * out[p,c] = a[p,c] + b[p,c]  (act applied after the sum);   copy/accumulate of channel slices.
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_add(const float* a, int a_ld, const float* b, int b_ld, float* out, int out_ld,
+              int64_t n_pix, int C, int act, void* stream);
+/* dst[p, 0:C] (= or +=) src[p, 0:C] with independent pitches. */
+int dl4ds_copy_channels(const float* src, int src_ld, float* dst, int dst_ld,
+                        int64_t n_pix, int C, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ChannelAttention2D -- blocks.py:537-593.  y = x * sigmoid(W2 relu(W1 mean_HW(x) + b1) + b2).
+ *  fwd : pooled[N,C] (sum over H*W, workspace, zeroed by the call), hidden[N,Cr], scale[N,C] are
+ *        saved for backward.  w1 (C,Cr), w2 (Cr,C) are the 1x1 Conv2D kernels.
+ *  bwd : dx = dy*scale + dmean/(H*W); parameter gradients accumulate.  dsum[N,C] is workspace.
+ *  groups_hw: number of pixels pooled per attention vector and n_groups vectors (4-D tensors:
+ *  n_groups = N, pix_per_group = H*W).
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_channel_attention_fwd(const float* x, int x_ld, float* y, int y_ld,
+                                const float* w1, const float* b1, const float* w2, const float* b2,
+                                float* pooled, float* hidden, float* scale,
+                                int n_groups, int64_t pix_per_group, int C, int Cr, void* stream);
+int dl4ds_channel_attention_bwd(const float* x, int x_ld, const float* dy, int dy_ld,
+                                float* dx, int dx_ld,
+                                const float* w1, const float* w2,
+                                const float* pooled, const float* hidden, const float* scale,
+                                float* dsum, float* dw1, float* db1, float* dw2, float* db2,
+                                int n_groups, int64_t pix_per_group, int C, int Cr, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pixel losses -- losses.py:5-20 (Keras MeanAbsoluteError / MeanSquaredError = global mean).
+ * kind 0 = MAE, 1 = MSE.  loss_out[0] += scale * mean(...) (caller zeroes it); if dy != NULL,
+ * dy = scale * d(mean)/d(y_pred).  n = total element count.
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_pixel_loss(const float* y_pred, const float* y_true, float* loss_out, float* dy,
+                     int64_t n, int kind, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * tf.keras.optimizers.Adam step on a flat arena -- supervised.py:353, cgan.py:277-278.
+ *   g = grad * grad_scale (grad_scale = 1/world_size folds Horovod's allreduce-average,
+ *   supervised.py:365);  m,v updated;  theta -= lr_t * m / (sqrt(v) + eps)
+ *   with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller-independent formula inside.
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n,
+                    float lr, float beta1, float beta2, float eps, int t, float grad_scale,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Data path: HR -> LR coarsening by s x s block mean == cv2.resize(INTER_AREA) at an integer
+ * factor -- utils.py:376-384 as called from dataloader.py:204,208.  (N,H,W,C) -> (N,H/s,W/s,C).
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_avgpool_coarsen(const float* x, float* y, int N, int H, int W, int C, int s, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Remaining graph ops for the dense / U-Net / recurrent / cGAN configurations.
+ * ------------------------------------------------------------------------------------------- */
+/* Resizing(h, w, 'bilinear') half-pixel centers -- blocks.py:489, discriminator.py:62.
+ * bwd accumulates into dx (caller zeroes). */
+int dl4ds_resize_bilinear_fwd(const float* x, int x_ld, float* y, int y_ld,
+                              int N, int H, int W, int C, int Ho, int Wo, void* stream);
+int dl4ds_resize_bilinear_bwd(const float* dy, int dy_ld, float* dx, int dx_ld,
+                              int N, int H, int W, int C, int Ho, int Wo, void* stream);
+/* MaxPooling2D((2,2)) -- blocks.py:613.  bwd routes dy to the first max of each window and
+ * WRITES dx fully (zeros elsewhere, including odd trailing rows/cols). */
+int dl4ds_maxpool2_fwd(const float* x, int x_ld, float* y, int y_ld,
+                       int N, int H, int W, int C, void* stream);
+int dl4ds_maxpool2_bwd(const float* x, int x_ld, const float* dy, int dy_ld, float* dx, int dx_ld,
+                       int N, int H, int W, int C, void* stream);
+/* LocallyConnected2D(f,(1,1),implementation=3) -- blocks.py:322-328.  Parameter grads accumulate. */
+int dl4ds_local_conv1x1_fwd(const float* x, int x_ld, const float* w, const float* b,
+                            float* y, int y_ld, int N, int H, int W, int Cin, int F, void* stream);
+int dl4ds_local_conv1x1_bwd(const float* x, int x_ld, const float* dy, int dy_ld, const float* w,
+                            float* dx, int dx_ld, float* dw, float* db,
+                            int N, int H, int W, int Cin, int F, void* stream);
+/* ConvLSTM2D cell pointwise part -- blocks.py:350-355 (Keras 2.x: tanh / hard_sigmoid, gates
+ * i,f,c,o).  z (n_pix,4F) = conv(x_t,Wx)+b+conv(h_{t-1},Wh) computed with dl4ds_conv2d_fwd.
+ * fwd: c = f*c_prev + i*tanh(zc); h = o*tanh(c).  gates (n_pix,4F) saves i,f,g,o for backward.
+ * bwd: given dh (total gradient wrt h_t) and dc_next (gradient flowing into c_t from t+1, may be
+ * NULL), writes dz (n_pix,4F) and dc_prev. */
+int dl4ds_convlstm_gates_fwd(const float* z, const float* c_prev, float* c, float* h, int h_ld,
+                             float* gates, int64_t n_pix, int F, void* stream);
+int dl4ds_convlstm_gates_bwd(const float* gates, const float* c_prev, const float* c,
+                             const float* dh, int dh_ld, const float* dc_next,
+                             float* dz, float* dc_prev, int64_t n_pix, int F, void* stream);
+/* Standalone activation (RecurrentConvBlock act on h, blocks.py:391,397): y = act(x);
+ * bwd: dx = dy*act'(y). */
+int dl4ds_act_fwd(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, int C, int act,
+                  void* stream);
+/* Mean over `pix_per_group` pixels: GlobalAveragePooling2D -- discriminator.py:76.
+ * out[g,c] = mean; bwd: dx[g,p,c] = dout[g,c]/pix_per_group (written, not accumulated). */
+int dl4ds_group_mean_fwd(const float* x, int x_ld, float* out, int n_groups, int64_t pix_per_group,
+                         int C, void* stream);
+int dl4ds_group_mean_bwd(const float* dout, float* dx, int dx_ld, int n_groups,
+                         int64_t pix_per_group, int C, void* stream);
+/* out[p,c] = a[p,c] * b[p,c]  (Dropout mask multiply, discriminator.py:77). */
+int dl4ds_mul(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* BinaryCrossentropy(from_logits=False) -- cgan.py:546-552,567-571 (Keras eps 1e-7 clipping).
+ * loss_out[0] += scale * bce(target, p);  dp (+)= scale * d bce / d p  (accumulate flag). */
+int dl4ds_bce_loss(const float* p, float target, float* loss_out, float* dp, int64_t n,
+                   float scale, int accumulate, void* stream);
+/* y = a*x + b*y element-wise (gradient combination for the two-seed cGAN backward). */
+int dl4ds_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DL4DS_B200_H */
