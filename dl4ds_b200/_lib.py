@@ -1,0 +1,90 @@
+"""ctypes binding of ``libdl4ds_b200.so`` (C ABI declared in ``include/dl4ds_b200.h``).
+
+The library is built in-tree by ``dl4ds_b200/csrc/Makefile`` (``__graft_entry__.build()``).  There is
+no CPU fallback: if the shared object is missing, or a call returns a negative status, a
+``RuntimeError`` carrying ``dl4ds_last_error()`` is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libdl4ds_b200.so')
+
+ACT = {None: 0, 'linear': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
+MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2
+MATH = {'fp32': MATH_FP32, 'tf32x3': MATH_TF32X3, 'tf32': MATH_TF32}
+W_HWIO, W_FLIP_T = 0, 1
+
+_P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+_CODES = {'p': _P, 'i': _I, 'l': _L, 'f': _F}
+
+# name -> (restype code, argument codes); order follows include/dl4ds_b200.h
+SIGNATURES = {
+    'dl4ds_last_error': ('s', ''),
+    'dl4ds_version': ('i', ''),
+    'dl4ds_device_is_sm100': ('i', ''),
+    'dl4ds_conv2d_fwd': ('i', 'pipppipiiiiiiiiiiiiiiiiiiip'),
+    'dl4ds_conv2d_wgrad_workspace_bytes': ('l', 'iiiiiiii'),
+    'dl4ds_conv2d_wgrad': ('i', 'pipipiiiiiiiiiiiipip'),
+    'dl4ds_bias_act_bwd': ('i', 'pipipipiiiiiip'),
+    'dl4ds_add': ('i', 'pipipiliip'),
+    'dl4ds_copy_channels': ('i', 'pipiliip'),
+    'dl4ds_channel_attention_fwd': ('i', 'pipipppppppiliiip'),
+    'dl4ds_channel_attention_bwd': ('i', 'pipipippppppppppiliiip'),
+    'dl4ds_pixel_loss': ('i', 'pppplifp'),
+    'dl4ds_adam_step': ('i', 'pppplffffifp'),
+    'dl4ds_adam_step_dev': ('i', 'pppplpffffp'),
+    'dl4ds_avgpool_coarsen': ('i', 'ppiiiiip'),
+    'dl4ds_resize_bilinear_fwd': ('i', 'pipiiiiiiip'),
+    'dl4ds_resize_bilinear_bwd': ('i', 'pipiiiiiiip'),
+    'dl4ds_maxpool2_fwd': ('i', 'pipiiiiip'),
+    'dl4ds_maxpool2_bwd': ('i', 'pipipiiiiip'),
+    'dl4ds_local_conv1x1_fwd': ('i', 'pipppiiiiiip'),
+    'dl4ds_local_conv1x1_bwd': ('i', 'pipippippiiiiip'),
+    'dl4ds_convlstm_gates_fwd': ('i', 'ppppiplip'),
+    'dl4ds_convlstm_gates_bwd': ('i', 'ppppippplip'),
+    'dl4ds_act_fwd': ('i', 'pipiliip'),
+    'dl4ds_group_mean_fwd': ('i', 'pipilip'),
+    'dl4ds_group_mean_bwd': ('i', 'ppiilip'),
+    'dl4ds_mul': ('i', 'ppplp'),
+    'dl4ds_bce_loss': ('i', 'pfpplfip'),
+    'dl4ds_permute_frames': ('i', 'ppiilp'),
+    'dl4ds_pad_bottom_right': ('i', 'pipiiiiiiip'),
+    'dl4ds_axpby': ('i', 'fpfplp'),
+}
+
+_lib = None
+
+
+class Dl4dsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Dl4dsError(
+            'libdl4ds_b200.so not found at %s -- build it with `python -c "import __graft_entry__ as g; '
+            'g.build()"` or `make -C dl4ds_b200/csrc`; there is no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_char_p if res == 's' else _CODES[res]
+        fn.argtypes = [_CODES[c] for c in args]
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().dl4ds_last_error().decode('utf-8', 'replace')
+
+
+def call(name, *args):
+    """Call a status-returning entry point; raise on a negative status."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise Dl4dsError('%s failed (%d): %s' % (name, rc, last_error()))
+    return rc

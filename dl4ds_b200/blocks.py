@@ -1,0 +1,100 @@
+"""Graph blocks of the DL4DS hot path as functions over an engine context (``Ctx`` or ``SpecCtx``).
+
+Mirrors the layer classes of the reference's ``dl4ds/models/blocks.py`` (cited per function) for the
+configurations on the north-star path: ``normalization=None`` and ``dropout_rate=0`` (the model
+defaults, sp_postups.py:26-28).  Parameter names follow ``<layer>/<sublayer>/{kernel,bias}``.
+Where the reference fuses nothing, the CUDA path fuses bias + activation (+ residual add)
+(+ depth_to_space) into the convolution epilogue.
+"""
+
+SUPPORTED_ACTIVATIONS = (None, 'linear', 'relu', 'sigmoid', 'tanh')
+
+
+def conv_block(c, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3):
+    """ConvBlock.call -- blocks.py:87-103."""
+    y = c.conv(x, name + '/conv1', filters, k=ks1, act=activation)
+    y = c.conv(y, name + '/conv2', filters, k=ks2, act=activation)
+    if attention:
+        y = c.channel_attention(y, name + '/att')
+    return y
+
+
+def residual_block(c, name, x, filters, activation='relu', attention=False, use_1x1conv=False):
+    """ResidualBlock.call -- blocks.py:210-230: act(conv2(act(conv1(X))) [*att] + [conv1x1](X))."""
+    y = c.conv(x, name + '/conv1', filters, act=activation)
+    skip = c.conv(x, name + '/conv1x1', filters, k=1) if use_1x1conv else x
+    if attention:
+        y = c.conv(y, name + '/conv2', filters)
+        y = c.channel_attention(y, name + '/att')
+        return c.add(y, skip, act=activation)
+    # residual add + activation fused into conv2's epilogue
+    return c.conv(y, name + '/conv2', filters, act=activation, res=skip)
+
+
+def dense_block(c, name, x, filters, activation='relu', attention=False):
+    """DenseBlock.call -- blocks.py:262-277.  The pre-activation of X is computed and discarded by
+    the reference (:263-267): Y = conv3x3(act(conv1x1(X))) [*att]; out = concat([Y, X])."""
+    y = c.conv(x, name + '/conv1', 4 * filters, k=1, act=activation)
+    y = c.conv(y, name + '/conv2', filters, k=3)
+    if attention:
+        y = c.channel_attention(y, name + '/att')
+    return c.concat([y, x])
+
+
+def transition_block(c, name, x, filters, activation='relu'):
+    """TransitionBlock.call without BN: 1x1 conv then activation -- blocks.py:306-308."""
+    return c.conv(x, name + '/conv', filters, k=1, act=activation)
+
+
+def localized_conv_block(c, name, x, filters=2):
+    """LocalizedConvBlock.call -- blocks.py:330-333."""
+    y = transition_block(c, name + '/transition', x, filters)
+    return c.local_conv(y, name + '/localconv', filters)
+
+
+def subpixel_block(c, name, x, scale, n_filters):
+    """SubpixelConvolutionBlock.call -- blocks.py:433-454.  One shared ``conv2x`` layer serves every
+    x2 stage (:415,421-422); depth_to_space is fused into the convolution's store."""
+    plan = {2: [2], 4: [2, 2], 8: [2, 2, 2], 10: [2, 5], 20: [2, 2, 5]}.get(scale, [scale])
+    for f in plan:
+        lname = {2: 'conv2x', 5: 'conv5x'}.get(f, 'conv')
+        x = c.conv(x, name + '/' + lname, n_filters * f * f, d2s=f)
+    return x
+
+
+def resize_conv_block(c, name, x, scale, n_filters):
+    """ResizeConvolutionBlock.call (bilinear) -- blocks.py:485-491."""
+    y = c.resize_bilinear(x, int(x.H * scale), int(x.W * scale))
+    return c.conv(y, name + '/conv', n_filters)
+
+
+def deconv_block(c, name, x, scale, n_filters, output_activation=None):
+    """DeconvolutionBlock.call -- blocks.py:522-534, reproducing its if/if/else fall-through:
+    scale 8 = T1, T2, T2 (T2 shared); scale 4 additionally runs the stride-4 transpose (x16 total);
+    any other scale is a single stride-`scale` transpose."""
+    def t(lname, v, stride, a):
+        return c.conv_transpose(v, name + '/' + lname, n_filters, 9, stride, act=a)
+    if scale == 4:
+        x = t('deconv_1of2_scale_x2', x, 2, None)
+        x = t('deconv_2of2_scale_x2', x, 2, output_activation)
+    if scale == 8:
+        x = t('deconv_1of2_scale_x2', x, 2, None)
+        x = t('deconv_2of2_scale_x2', x, 2, output_activation)
+        x = t('deconv_2of2_scale_x2', x, 2, output_activation)
+    else:
+        x = t('deconv_scale_x' + str(scale), x, scale, output_activation)
+    return x
+
+
+def recurrent_conv_block(c, name, x, filters, T, activation='relu'):
+    """RecurrentConvBlock.call -- blocks.py:380-398: ConvLSTM2D 5x5 -> act -> ConvLSTM2D 3x3 -> act.
+    ``x`` holds time-major frames (T*B, H, W, C)."""
+    y = c.act(c.convlstm(x, name + '/convlstm1', filters, 5, T), activation)
+    y = c.act(c.convlstm(y, name + '/convlstm2', filters, 3, T), activation)
+    return y
+
+
+def pad_concat(c, t1, t2):
+    """PadConcat.call -- blocks.py:629-656 (zero-pad the smaller one at the bottom / right)."""
+    H, W = max(t1.H, t2.H), max(t1.W, t2.W)
+    return c.concat([c.pad_to(t1, H, W), c.pad_to(t2, H, W)])

@@ -25,6 +25,30 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
+// argument blocks shared by api.cu / conv_simt.cu / conv_tc.cu
+struct ConvArgs {
+    const float* x; const float* w; const float* bias; const float* res; float* y;
+    int x_ld, res_ld, y_ld;
+    int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, up, pad_t, pad_l, wmode, act, d2s_r, beta;
+    int M, HoWo, vec;
+};
+struct WgradArgs {
+    const float* P; const float* Q; float* dw;
+    int p_ld, q_ld;
+    int N, Hp, Wp, Ca, Hq, Wq, Cb, KH, KW, stride, pad_t, pad_l;
+    int Mw;            // KH*KW*Ca
+    int64_t NQ;        // N*Hq*Wq
+    int chunks_per_split;
+};
+int conv2d_fwd_simt(const ConvArgs& a, cudaStream_t st);
+int conv2d_wgrad_simt(const WgradArgs& a, cudaStream_t st);
+// conv_tc.cu: DL4DS_E_UNSUPPORTED when the shape is outside the tensor-core kernels' domain
+int conv2d_fwd_tc(const ConvArgs& a, int math_mode, cudaStream_t st);
+int conv2d_wgrad_tc(const WgradArgs& a, void* ws, int math_mode, cudaStream_t st);
+int64_t conv2d_wgrad_tc_workspace(int N, int Hq, int Wq, int Ca, int Cb, int KH, int KW);
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
         case DL4DS_ACT_RELU: return fmaxf(v, 0.0f);

@@ -13,13 +13,6 @@
 
 namespace dl4ds {
 
-struct ConvArgs {
-    const float* x; const float* w; const float* bias; const float* res; float* y;
-    int x_ld, res_ld, y_ld;
-    int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, up, pad_t, pad_l, wmode, act, d2s_r, beta;
-    int M, HoWo, vec;
-};
-
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvArgs p) {
     constexpr int BK = 8;
@@ -206,15 +199,6 @@ int conv2d_fwd_simt(const ConvArgs& a, cudaStream_t st) {
 // weight gradient: dw[(tap,a)][b] += sum_q P[shift_tap(q)][a] * Q[q][b]
 // GEMM view: M = KH*KW*Ca, N = Cb, K = N*Hq*Wq pixels (split across gridDim.z, fp32 atomics).
 // -------------------------------------------------------------------------------------------------
-struct WgradArgs {
-    const float* P; const float* Q; float* dw;
-    int p_ld, q_ld;
-    int N, Hp, Wp, Ca, Hq, Wq, Cb, KH, KW, stride, pad_t, pad_l;
-    int Mw;            // KH*KW*Ca
-    int64_t NQ;        // N*Hq*Wq
-    int chunks_per_split;
-};
-
 template <int TMW, int TBW, int RA, int RB>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs p) {
     constexpr int BP = 32;

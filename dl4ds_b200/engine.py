@@ -1,0 +1,701 @@
+"""Define-by-run graph engine over the C ABI (``include/dl4ds_b200.h``).
+
+The reference hands its graphs (dl4ds/models/*.py) to Keras, which executes and differentiates
+them.  Here a model is a Python function over a :class:`Ctx`; every op launches hand-written CUDA
+kernels through ctypes and records its backward closure on a tape.  PyTorch supplies device
+storage and the stream only -- no torch operator touches activations or weights on this path.
+
+Storage conventions
+  * activations: fp32 NHWC, possibly a channel slice of a wider buffer (:class:`Var` keeps the base
+    buffer, channel offset and pitch) so Concatenate never needs a transposition;
+  * parameters: one flat fp32 arena (:class:`Arena`) holding theta / grad / Adam m / v; parameter
+    gradients ACCUMULATE into ``grad`` (zeroed once per step) which is what sums the gradient of
+    shared layers (blocks.py:415,421-422,528-531) over their applications and lets the
+    data-parallel all-reduce be a single collective on one buffer.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, MATH, W_FLIP_T, W_HWIO, call
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def same_pads(n, k, s):
+    """TF 'SAME' padding: out = ceil(n/s); total = max((out-1)*s + k - n, 0); before = total//2."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return out, total // 2
+
+
+class Arena:
+    """Flat fp32 parameter arena: theta, grad and the two Adam slots, with named views."""
+
+    def __init__(self, spec, device):
+        self.spec = OrderedDict((k, tuple(int(s) for s in v)) for k, v in spec.items())
+        self.offsets = OrderedDict()
+        n = 0
+        for name, shape in self.spec.items():
+            self.offsets[name] = n
+            n += int(np.prod(shape))
+            n = (n + 3) // 4 * 4            # keep every tensor 16-byte aligned
+        self.n = max(n, 4)
+        self.device = torch.device(device)
+        self.theta = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros_like(self.theta)
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.t = 0                          # optimizer iterations
+
+    def n_params(self):
+        return sum(int(np.prod(s)) for s in self.spec.values())
+
+    def _view(self, flat, name):
+        shape = self.spec[name]
+        o = self.offsets[name]
+        return flat[o:o + int(np.prod(shape))].view(shape)
+
+    def param(self, name):
+        return self._view(self.theta, name)
+
+    def gradient(self, name):
+        return self._view(self.grad, name)
+
+    def load(self, weights):
+        """Copy a {name: array-like} dict (Keras layouts) into theta."""
+        for name in self.spec:
+            w = weights[name]
+            w = torch.as_tensor(np.asarray(w, dtype=np.float32) if not torch.is_tensor(w) else w)
+            assert tuple(w.shape) == self.spec[name], (name, tuple(w.shape), self.spec[name])
+            self.param(name).copy_(w.to(torch.float32))
+
+    def state_dict(self):
+        return OrderedDict((n, self.param(n).detach().cpu().numpy().copy()) for n in self.spec)
+
+    def grads(self):
+        return OrderedDict((n, self.gradient(n).detach().cpu().numpy().copy()) for n in self.spec)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+class Var:
+    """fp32 NHWC activation: channels [off, off+C) of ``buf`` (N,H,W,ld)."""
+    __slots__ = ('buf', 'off', 'C', 'grad', 'requires_grad')
+
+    def __init__(self, buf, off=0, C=None, requires_grad=True):
+        assert buf.dim() == 4 and buf.is_contiguous() and buf.dtype == torch.float32
+        self.buf = buf
+        self.off = off
+        self.C = buf.shape[3] - off if C is None else C
+        self.grad = None
+        self.requires_grad = requires_grad
+
+    @property
+    def N(self):
+        return self.buf.shape[0]
+
+    @property
+    def H(self):
+        return self.buf.shape[1]
+
+    @property
+    def W(self):
+        return self.buf.shape[2]
+
+    @property
+    def ld(self):
+        return self.buf.shape[3]
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 4 * self.off
+
+    @property
+    def npix(self):
+        return self.N * self.H * self.W
+
+    @property
+    def t(self):
+        return self.buf[..., self.off:self.off + self.C]
+
+    def slice(self, off, C):
+        return Var(self.buf, self.off + off, C, self.requires_grad)
+
+    def like(self, C=None):
+        C = self.C if C is None else C
+        return Var(torch.empty((self.N, self.H, self.W, C), dtype=torch.float32, device=self.buf.device))
+
+
+def new_var(N, H, W, C, device, zero=False):
+    f = torch.zeros if zero else torch.empty
+    return Var(f((N, H, W, C), dtype=torch.float32, device=device))
+
+
+class Ctx:
+    """One recorded forward pass (and its backward)."""
+
+    def __init__(self, arena, math='fp32', training=True):
+        self.arena = arena
+        self.math = MATH[math] if isinstance(math, str) else math
+        self.training = training
+        self.tape = []
+        self.device = arena.device
+        self.names_used = []
+        self.launches = 0
+
+    # ---------------------------------------------------------------- helpers
+    def _call(self, name, *args):
+        self.launches += 1
+        return call(name, *args)
+
+    def input(self, tensor, requires_grad=False):
+        """Wrap an NHWC fp32 CUDA tensor as a graph input."""
+        assert tensor.is_cuda and tensor.dtype == torch.float32 and tensor.dim() == 4
+        return Var(tensor.contiguous(), requires_grad=requires_grad)
+
+    def _p(self, name):
+        self.names_used.append(name)
+        return self.arena.param(name)
+
+    def _g(self, name):
+        return self.arena.gradient(name)
+
+    def _record(self, fn):
+        if self.training:
+            self.tape.append(fn)
+
+    def _acc(self, var, writer):
+        """Accumulate a gradient into ``var``.  writer(dst_var, beta) must write (beta=0) or
+        add (beta=1) the gradient; ops that cannot accumulate are wrapped by ``_acc_via_tmp``."""
+        if not var.requires_grad:
+            return
+        if var.grad is None:
+            var.grad = var.like()
+            writer(var.grad, 0)
+        else:
+            writer(var.grad, 1)
+
+    def _acc_via_tmp(self, var, writer):
+        """writer(dst_var) writes the full gradient; summed into var.grad if one exists."""
+        if not var.requires_grad:
+            return
+        if var.grad is None:
+            var.grad = var.like()
+            writer(var.grad)
+        else:
+            tmp = var.like()
+            writer(tmp)
+            self._copy(tmp, var.grad, accumulate=1)
+
+    def _copy(self, src, dst, accumulate=0):
+        assert src.C == dst.C and src.npix == dst.npix
+        self._call('dl4ds_copy_channels', src.ptr, src.ld, dst.ptr, dst.ld, src.npix, src.C, accumulate,
+                   _stream())
+
+    def _give_grad(self, var, gvar, adopt=True):
+        """Hand ``gvar`` (a Var holding d loss / d var) to ``var``.  A gradient buffer has exactly one
+        owner (backward closures scale and accumulate in place): ``adopt`` transfers ownership when
+        ``var`` has no gradient yet; otherwise the values are copied / added.  Returns True if the
+        buffer was adopted."""
+        if not var.requires_grad:
+            return False
+        if var.grad is None:
+            if adopt:
+                var.grad = gvar
+                return True
+            var.grad = var.like()
+            self._copy(gvar, var.grad, accumulate=0)
+        else:
+            self._copy(gvar, var.grad, accumulate=1)
+        return False
+
+    # ---------------------------------------------------------------- convolution family
+    def conv(self, x, name, cout, k=3, act=None, bias=True, stride=1, padding='same', res=None,
+             d2s=1, out=None, dense=False):
+        """Keras Conv2D (+bias +activation [+residual add before the activation] [+depth_to_space])
+        -- blocks.py:49-61,91,97,208,299,427; sp_postups.py:134,156."""
+        w = self._p(name + '/kernel')
+        wshape = (x.C, cout) if dense else (k, k, x.C, cout)
+        assert tuple(w.shape) == wshape, (name, tuple(w.shape), wshape)
+        b = self._p(name + '/bias') if bias else None
+        if padding == 'same':
+            Ho, pt = same_pads(x.H, k, stride)
+            Wo, pl = same_pads(x.W, k, stride)
+        else:
+            Ho, pt = (x.H - k) // stride + 1, 0
+            Wo, pl = (x.W - k) // stride + 1, 0
+        r = d2s if d2s > 1 else 1
+        if out is None:
+            out = new_var(x.N, Ho * r, Wo * r, cout // (r * r), self.device)
+        else:
+            assert (out.N, out.H, out.W, out.C) == (x.N, Ho * r, Wo * r, cout // (r * r))
+        if res is not None:
+            assert (res.N, res.H, res.W, res.C) == (x.N, Ho, Wo, cout)
+        a = ACT[act]
+        self._call('dl4ds_conv2d_fwd', x.ptr, x.ld, w.data_ptr(), b.data_ptr() if bias else None,
+                   res.ptr if res is not None else None, res.ld if res is not None else 0,
+                   out.ptr, out.ld, x.N, x.H, x.W, x.C, Ho, Wo, cout, k, k, stride, 1, pt, pl,
+                   W_HWIO, a, r, 0, self.math, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            # epilogue backward: dz = dy * act'(y) (un-shuffled if d2s), dbias += sum dz
+            if a == 0 and r == 1:
+                dz = dy
+                if bias:
+                    self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, None, 0, None, 0,
+                               self._g(name + '/bias').data_ptr(), x.N, Ho, Wo, cout, 0, 1, _stream())
+            else:
+                dz = new_var(x.N, Ho, Wo, cout, self.device) if r > 1 else dy
+                self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dz.ptr, dz.ld,
+                           self._g(name + '/bias').data_ptr() if bias else None,
+                           x.N, Ho, Wo, cout, a, r, _stream())
+            # weight gradient (accumulating)
+            self._wgrad(x, dz, self._g(name + '/kernel'), k, stride, pt, pl)
+            # input gradient
+            if x.requires_grad:
+                def wr(dst, beta):
+                    self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
+                               dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1, stride,
+                               k - 1 - pt, k - 1 - pl, W_FLIP_T, 0, 1, beta, self.math, _stream())
+                self._acc(x, wr)
+            if res is not None:     # d(res) = dz; handed over last (stream order keeps reads before
+                self._give_grad(res, dz)   # any later in-place update by the new owner)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def _wgrad(self, P, Q, dw, k, stride, pt, pl):
+        ws_bytes = _lib.load().dl4ds_conv2d_wgrad_workspace_bytes(P.N, Q.H, Q.W, P.C, Q.C, k, k, self.math)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device) if ws_bytes > 0 else None
+        self._call('dl4ds_conv2d_wgrad', P.ptr, P.ld, Q.ptr, Q.ld, dw.data_ptr(),
+                   P.N, P.H, P.W, P.C, Q.H, Q.W, Q.C, k, k, stride, pt, pl,
+                   ws.data_ptr() if ws is not None else None, self.math, _stream())
+
+    def conv_transpose(self, x, name, cout, k, stride, act=None):
+        """Keras Conv2DTranspose(cout, k, strides=stride, padding='same', use_bias=False)
+        -- blocks.py:508-516.  out = stride * in; kernel layout (kh,kw,Cout,Cin)."""
+        w = self._p(name + '/kernel')
+        assert tuple(w.shape) == (k, k, cout, x.C), (name, tuple(w.shape))
+        Ho, Wo = x.H * stride, x.W * stride
+        _, pt = same_pads(Ho, k, stride)
+        _, pl = same_pads(Wo, k, stride)
+        out = new_var(x.N, Ho, Wo, cout, self.device)
+        a = ACT[act]
+        self._call('dl4ds_conv2d_fwd', x.ptr, x.ld, w.data_ptr(), None, None, 0, out.ptr, out.ld,
+                   x.N, x.H, x.W, x.C, Ho, Wo, cout, k, k, 1, stride, k - 1 - pt, k - 1 - pl,
+                   W_FLIP_T, a, 1, 0, self.math, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dz = dy
+            if a != 0:
+                self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dz.ptr, dz.ld, None,
+                           x.N, Ho, Wo, cout, a, 1, _stream())
+            # dw[k][cout][cin] += sum dz[s*i + k - p][cout] * x[i][cin]
+            self._wgrad(dz, x, self._g(name + '/kernel'), k, stride, pt, pl)
+            if x.requires_grad:
+                def wr(dst, beta):
+                    self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
+                               dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, stride, 1,
+                               pt, pl, W_HWIO, 0, 1, beta, self.math, _stream())
+                self._acc(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def dense(self, x, name, cout, act=None):
+        """Keras Dense on (B,1,1,Cin) -- discriminator.py:78-79 (a 1x1 convolution on a 1x1 map)."""
+        assert x.H == 1 and x.W == 1
+        return self.conv(x, name, cout, k=1, act=act, dense=True)
+
+    # ---------------------------------------------------------------- element-wise / structural
+    def add(self, a, b, act=None):
+        """Add (+ optional activation) -- sp_postups.py:164, blocks.py:228-229."""
+        assert (a.N, a.H, a.W, a.C) == (b.N, b.H, b.W, b.C)
+        out = a.like()
+        code = ACT[act]
+        self._call('dl4ds_add', a.ptr, a.ld, b.ptr, b.ld, out.ptr, out.ld, a.npix, a.C, code, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            if code != 0:
+                self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dy.ptr, dy.ld, None,
+                           a.N, a.H, a.W, a.C, code, 1, _stream())
+            adopted = self._give_grad(a, dy)
+            self._give_grad(b, dy, adopt=not adopted)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def concat(self, parts):
+        """Concatenate along channels -- blocks.py:276, sp_postups.py:186,201."""
+        p0 = parts[0]
+        ctot = sum(p.C for p in parts)
+        out = new_var(p0.N, p0.H, p0.W, ctot, self.device)
+        offs = []
+        o = 0
+        for p in parts:
+            assert (p.N, p.H, p.W) == (p0.N, p0.H, p0.W)
+            self._copy(p, out.slice(o, p.C))
+            offs.append(o)
+            o += p.C
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            for p, o in zip(parts, offs):
+                self._give_grad(p, dy.slice(o, p.C))
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def act(self, x, act):
+        """Standalone activation -- blocks.py:391,397."""
+        code = ACT[act]
+        if code == 0:
+            return x
+        out = x.like()
+        self._call('dl4ds_act_fwd', x.ptr, x.ld, out.ptr, out.ld, x.npix, x.C, code, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dy.ptr, dy.ld, None,
+                       x.N, x.H, x.W, x.C, code, 1, _stream())
+            self._give_grad(x, dy)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def channel_attention(self, x, name, r=4, groups=None):
+        """ChannelAttention2D -- blocks.py:537-593.  ``groups`` = (n_groups, pix_per_group, inner)
+        overrides the default per-image pooling (used for the 5-D (T,H) pooling quirk)."""
+        C = x.C
+        Cr = int(C / r)
+        w1, b1 = self._p(name + '/conv1/kernel'), self._p(name + '/conv1/bias')
+        w2, b2 = self._p(name + '/conv2/kernel'), self._p(name + '/conv2/bias')
+        ng, ppg, inner = groups if groups is not None else (x.N, x.H * x.W, 1)
+        assert ng * ppg == x.npix
+        dev = self.device
+        pooled = torch.empty(ng * C, dtype=torch.float32, device=dev)
+        hidden = torch.empty(ng * Cr, dtype=torch.float32, device=dev)
+        scale = torch.empty(ng * C, dtype=torch.float32, device=dev)
+        out = x.like()
+        self.launches += 3
+        self._call('dl4ds_channel_attention_fwd', x.ptr, x.ld, out.ptr, out.ld, w1.data_ptr(),
+                   b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), pooled.data_ptr(), hidden.data_ptr(),
+                   scale.data_ptr(), ng, ppg, inner, C, Cr, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dsum = torch.empty(ng * C, dtype=torch.float32, device=dev)
+
+            def wr(dst):
+                self.launches += 3
+                self._call('dl4ds_channel_attention_bwd', x.ptr, x.ld, dy.ptr, dy.ld, dst.ptr, dst.ld,
+                           w1.data_ptr(), w2.data_ptr(), pooled.data_ptr(), hidden.data_ptr(),
+                           scale.data_ptr(), dsum.data_ptr(),
+                           self._g(name + '/conv1/kernel').data_ptr(), self._g(name + '/conv1/bias').data_ptr(),
+                           self._g(name + '/conv2/kernel').data_ptr(), self._g(name + '/conv2/bias').data_ptr(),
+                           ng, ppg, inner, C, Cr, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def local_conv(self, x, name, filters):
+        """LocallyConnected2D(filters, (1,1), implementation=3) -- blocks.py:322-328."""
+        w, b = self._p(name + '/kernel'), self._p(name + '/bias')
+        assert tuple(w.shape) == (x.H, x.W, x.C, filters)
+        out = x.like(filters)
+        self._call('dl4ds_local_conv1x1_fwd', x.ptr, x.ld, w.data_ptr(), b.data_ptr(), out.ptr, out.ld,
+                   x.N, x.H, x.W, x.C, filters, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+
+            def wr(dst):
+                self._call('dl4ds_local_conv1x1_bwd', x.ptr, x.ld, dy.ptr, dy.ld, w.data_ptr(),
+                           dst.ptr, dst.ld, self._g(name + '/kernel').data_ptr(),
+                           self._g(name + '/bias').data_ptr(), x.N, x.H, x.W, x.C, filters, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def resize_bilinear(self, x, Ho, Wo):
+        """keras Resizing(Ho, Wo, 'bilinear') -- blocks.py:489, discriminator.py:62."""
+        out = new_var(x.N, Ho, Wo, x.C, self.device)
+        self._call('dl4ds_resize_bilinear_fwd', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, x.C, Ho, Wo,
+                   _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None or not x.requires_grad:
+                return
+            if x.grad is None:
+                x.grad = Var(torch.zeros((x.N, x.H, x.W, x.C), dtype=torch.float32, device=self.device))
+            self._call('dl4ds_resize_bilinear_bwd', dy.ptr, dy.ld, x.grad.ptr, x.grad.ld, x.N, x.H, x.W,
+                       x.C, Ho, Wo, _stream())
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def maxpool2(self, x):
+        """MaxPooling2D((2,2)) -- blocks.py:613."""
+        out = new_var(x.N, x.H // 2, x.W // 2, x.C, self.device)
+        self._call('dl4ds_maxpool2_fwd', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, x.C, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+
+            def wr(dst):
+                self._call('dl4ds_maxpool2_bwd', x.ptr, x.ld, dy.ptr, dy.ld, dst.ptr, dst.ld, x.N, x.H,
+                           x.W, x.C, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def pad_to(self, x, H, W):
+        """ZeroPadding2D bottom/right to (H, W) -- PadConcat, blocks.py:639-655."""
+        if (x.H, x.W) == (H, W):
+            return x
+        out = new_var(x.N, H, W, x.C, self.device)
+        self._call('dl4ds_pad_bottom_right', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, H, W, x.C,
+                   _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+
+            def wr(dst):   # adjoint = crop
+                self._call('dl4ds_pad_bottom_right', dy.ptr, dy.ld, dst.ptr, dst.ld, x.N, H, W, x.H, x.W,
+                           x.C, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def permute_frames(self, x, A, B):
+        """(A,B,frame) -> (B,A,frame) over the leading (frame) dimension of a (A*B,H,W,C) Var."""
+        assert x.N == A * B and x.ld == x.C
+        out = x.like()
+        fe = x.H * x.W * x.C
+        self._call('dl4ds_permute_frames', x.ptr, out.ptr, A, B, fe, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            assert dy.ld == dy.C
+
+            def wr(dst):
+                self._call('dl4ds_permute_frames', dy.ptr, dst.ptr, B, A, fe, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def group_mean(self, x):
+        """GlobalAveragePooling2D -- discriminator.py:76.  (N,H,W,C) -> (N,1,1,C)."""
+        out = new_var(x.N, 1, 1, x.C, self.device)
+        self.launches += 1
+        self._call('dl4ds_group_mean_fwd', x.ptr, x.ld, out.ptr, x.N, x.H * x.W, x.C, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            assert dy.ld == dy.C
+
+            def wr(dst):
+                self._call('dl4ds_group_mean_bwd', dy.ptr, dst.ptr, dst.ld, x.N, x.H * x.W, x.C, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def repeat_frames(self, x, T):
+        """tf.repeat(tf.expand_dims(s, 1), T, axis=1) (spt_postups.py:139-140) in the time-major
+        frame layout: (B,H,W,C) -> (T*B,H,W,C), T stacked copies."""
+        B_ = x.N
+        out = new_var(T * B_, x.H, x.W, x.C, self.device)
+        for t in range(T):
+            self._copy(x, Var(out.buf[t * B_:(t + 1) * B_]))
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            assert dy.off == 0 and dy.ld == dy.C
+            for t in range(T):
+                self._give_grad(x, Var(dy.buf[t * B_:(t + 1) * B_]), adopt=False)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def mul_mask(self, x, mask):
+        """x * mask (inverted-dropout keep mask, discriminator.py:77).  mask: Var/tensor (N,1,1,C)."""
+        if isinstance(mask, Var):
+            assert mask.off == 0 and mask.ld == mask.C
+            mask = mask.buf
+        assert x.ld == x.C and mask.numel() == x.npix * x.C
+        out = x.like()
+        self._call('dl4ds_mul', x.ptr, mask.data_ptr(), out.ptr, x.npix * x.C, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            assert dy.ld == dy.C
+
+            def wr(dst):
+                self._call('dl4ds_mul', dy.ptr, mask.data_ptr(), dst.ptr, x.npix * x.C, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def convlstm(self, x, name, filters, k, T):
+        """ConvLSTM2D(filters, k, return_sequences=True, padding='same') -- blocks.py:350-355
+        (Keras 2.x: tanh / hard_sigmoid, gates i,f,c,o, zero initial state, recurrent conv 'same'
+        without bias).  ``x``: TIME-MAJOR frames (T*B, H, W, C); returns (T*B, H, W, filters)."""
+        TB, H, W, C = x.N, x.H, x.W, x.C
+        B = TB // T
+        F4 = 4 * filters
+        wx, wh, bias = self._p(name + '/kernel'), self._p(name + '/recurrent_kernel'), self._p(name + '/bias')
+        assert tuple(wx.shape) == (k, k, C, F4) and tuple(wh.shape) == (k, k, filters, F4)
+        dev = self.device
+        pad = k // 2
+        npx = B * H * W
+        # input convolution for all T at once (one GEMM): z (T*B, H, W, 4F)
+        z = new_var(TB, H, W, F4, dev)
+        self._call('dl4ds_conv2d_fwd', x.ptr, x.ld, wx.data_ptr(), bias.data_ptr(), None, 0, z.ptr, z.ld,
+                   TB, H, W, C, H, W, F4, k, k, 1, 1, pad, pad, W_HWIO, 0, 1, 0, self.math, _stream())
+        out = new_var(TB, H, W, filters, dev)
+        cs = torch.empty((TB, H, W, filters), dtype=torch.float32, device=dev)
+        gates = torch.empty((TB, H, W, F4), dtype=torch.float32, device=dev)
+
+        def step(buf, t):
+            return buf[t * B:(t + 1) * B]
+
+        for t in range(T):
+            zt = step(z.buf, t)
+            if t > 0:   # z_t += conv(h_{t-1}, Wh)
+                self._call('dl4ds_conv2d_fwd', step(out.buf, t - 1).data_ptr(), filters, wh.data_ptr(), None,
+                           None, 0, zt.data_ptr(), F4, B, H, W, filters, H, W, F4, k, k, 1, 1, pad, pad,
+                           W_HWIO, 0, 1, 1, self.math, _stream())
+            self._call('dl4ds_convlstm_gates_fwd', zt.data_ptr(), step(cs, t - 1).data_ptr() if t > 0 else None,
+                       step(cs, t).data_ptr(), step(out.buf, t).data_ptr(), filters,
+                       step(gates, t).data_ptr(), npx, filters, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            assert dy.ld == dy.C and dy.off == 0
+            dh = dy.buf      # owned; dh_{t-1} is accumulated in place
+            dz = new_var(TB, H, W, F4, dev)
+            dc = [torch.empty((B, H, W, filters), dtype=torch.float32, device=dev) for _ in range(2)]
+            gwh = self._g(name + '/recurrent_kernel')
+            for t in range(T - 1, -1, -1):
+                dzt = step(dz.buf, t)
+                self._call('dl4ds_convlstm_gates_bwd', step(gates, t).data_ptr(),
+                           step(cs, t - 1).data_ptr() if t > 0 else None, step(cs, t).data_ptr(),
+                           step(dh, t).data_ptr(), filters,
+                           dc[(t + 1) % 2].data_ptr() if t < T - 1 else None,
+                           dzt.data_ptr(), dc[t % 2].data_ptr(), npx, filters, _stream())
+                if t > 0:
+                    # dh_{t-1} += dgrad(dz_t, Wh);  dWh += wgrad(h_{t-1}, dz_t)
+                    self._call('dl4ds_conv2d_fwd', dzt.data_ptr(), F4, wh.data_ptr(), None, None, 0,
+                               step(dh, t - 1).data_ptr(), filters, B, H, W, F4, H, W, filters, k, k, 1, 1,
+                               k - 1 - pad, k - 1 - pad, W_FLIP_T, 0, 1, 1, self.math, _stream())
+                    self._wgrad(Var(step(out.buf, t - 1)), Var(dzt), gwh, k, 1, pad, pad)
+            # the input convolution's bias / weight / input gradients, all T in one shot
+            self._call('dl4ds_bias_act_bwd', dz.ptr, dz.ld, None, 0, None, 0,
+                       self._g(name + '/bias').data_ptr(), TB, H, W, F4, 0, 1, _stream())
+            self._wgrad(x, dz, self._g(name + '/kernel'), k, 1, pad, pad)
+            if x.requires_grad:
+                def wr(dst, beta):
+                    self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, wx.data_ptr(), None, None, 0, dst.ptr,
+                               dst.ld, TB, H, W, F4, H, W, C, k, k, 1, 1, k - 1 - pad, k - 1 - pad,
+                               W_FLIP_T, 0, 1, beta, self.math, _stream())
+                self._acc(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    # ---------------------------------------------------------------- losses
+    def pixel_loss(self, y_pred, y_true, kind='mae', scale=1.0, loss_buf=None):
+        """losses.mae / losses.mse (losses.py:5-20): loss_buf[0] += scale*mean; seeds y_pred.grad."""
+        assert y_pred.ld == y_pred.C and y_true.ld == y_true.C
+        n = y_pred.npix * y_pred.C
+        if loss_buf is None:
+            loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+        dy = y_pred.like() if self.training else None
+        self._call('dl4ds_pixel_loss', y_pred.ptr, y_true.ptr, loss_buf.data_ptr(),
+                   dy.ptr if dy is not None else None, n, {'mae': 0, 'mse': 1}[kind], float(scale),
+                   _stream())
+        if dy is not None:
+            self._give_grad(y_pred, dy)
+        return loss_buf
+
+    def bce_loss(self, p, target, scale=1.0, loss_buf=None, seed=True):
+        """BinaryCrossentropy(from_logits=False) vs a constant target -- cgan.py:546-552,567-571."""
+        assert p.ld == p.C
+        n = p.npix * p.C
+        if loss_buf is None:
+            loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+        dp = None
+        acc = 0
+        if self.training and seed:
+            if p.grad is None:
+                p.grad = p.like()
+            else:
+                acc = 1
+            dp = p.grad
+        self._call('dl4ds_bce_loss', p.ptr, float(target), loss_buf.data_ptr(),
+                   dp.ptr if dp is not None else None, n, float(scale), acc, _stream())
+        return loss_buf
+
+    # ---------------------------------------------------------------- backward
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+
+def adam_step(arena, lr, beta_1=0.9, beta_2=0.999, eps=1e-7, grad_scale=1.0, lr_t_dev=None):
+    """tf.keras Adam on the whole arena (supervised.py:353, cgan.py:277-278)."""
+    arena.t += 1
+    if lr_t_dev is not None:
+        call('dl4ds_adam_step_dev', arena.theta.data_ptr(), arena.grad.data_ptr(), arena.m.data_ptr(),
+             arena.v.data_ptr(), arena.n, lr_t_dev.data_ptr(), float(beta_1), float(beta_2), float(eps),
+             float(grad_scale), _stream())
+    else:
+        call('dl4ds_adam_step', arena.theta.data_ptr(), arena.grad.data_ptr(), arena.m.data_ptr(),
+             arena.v.data_ptr(), arena.n, float(lr), float(beta_1), float(beta_2), float(eps), arena.t,
+             float(grad_scale), _stream())

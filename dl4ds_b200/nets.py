@@ -1,0 +1,456 @@
+"""Network graph builders + the ``Model`` object the trainers / ``Predictor`` hold.
+
+Each builder keeps the signature and the model naming (``<backbone>_<upsampling>``,
+``rec<backbone>_<upsampling>``, ``discriminator``) of its reference counterpart in
+``dl4ds/models/`` and returns a :class:`Model` whose graph function runs over the CUDA engine
+(``engine.Ctx``) or, for shape/parameter inference, over ``spec.SpecCtx``.
+
+Scope: ``normalization=None``, ``dropout_rate=0`` (model defaults),
+activations in {None, relu, sigmoid, tanh}, bilinear resize-convolution; backbones
+convnet / resnet / densenet / unet.  Anything else raises ``NotImplementedError`` -- there is no
+fallback path.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import blocks as B
+from .engine import Arena, Ctx
+from .spec import SpecCtx
+
+BACKBONES = ('convnet', 'resnet', 'densenet', 'unet')
+POSTUPSAMPLING_METHODS = ('spc', 'rc', 'dc')
+
+
+def _check_common(activation, output_activation, normalization, dropout_rate, backbone_block=None):
+    for a in (activation, output_activation):
+        if a not in B.SUPPORTED_ACTIVATIONS:
+            raise NotImplementedError('activation %r is outside the B200 hot path' % (a,))
+    if normalization is not None:
+        raise NotImplementedError('normalization=%r is outside the B200 hot path' % (normalization,))
+    if dropout_rate:
+        raise NotImplementedError('dropout_rate>0 is outside the B200 hot path (model default is 0)')
+    if backbone_block is not None and backbone_block not in BACKBONES:
+        raise NotImplementedError('backbone %r is outside the B200 hot path' % (backbone_block,))
+
+
+class _InputSpec:
+    """Stand-in for ``keras.Model.input``: ``Predictor`` only reads ``.shape`` (inference.py:173)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
+class Model:
+    """A built network: graph function + flat parameter arena.
+
+    Exposes what the reference's callers use on a ``tf.keras.Model``: ``name``, ``input.shape``,
+    ``predict(inputs, batch_size, verbose)``, ``count_params()``, ``summary()``, ``get_weights`` /
+    ``set_weights`` by name, ``save_weights`` / ``load_weights`` (npz).
+    """
+
+    def __init__(self, name, fn, input_shapes, time_window=None, math='fp32'):
+        self.name = name
+        self.fn = fn                                # fn(ctx, [Var...]) -> Var
+        self.input_shapes = [tuple(s) for s in input_shapes]   # without batch dim, None allowed
+        self.time_window = time_window
+        self.math = math
+        self.input = _InputSpec((None,) + self.input_shapes[0])
+        sc = SpecCtx()
+        ins = [sc.input(self._spec_shape(s)) for s in self.input_shapes]
+        out = fn(sc, ins)
+        self.spec = sc.spec
+        self.macs_per_sample = sc.macs
+        self.output_shape = out.shape[1:]
+        self.arena = None
+
+    def _spec_shape(self, s):
+        """Concrete (N,H,W,C) used for tracing; spatio-temporal inputs (T,H,W,C) fold T into N."""
+        if len(s) == 4:
+            t, h, w, ch = s
+            return ((t or self.time_window or 1), h or 32, w or 32, ch)
+        h, w, ch = s
+        return (1, h or 32, w or 32, ch)
+
+    # -- parameters -------------------------------------------------------------------------
+    def count_params(self):
+        return sum(int(np.prod(s)) for s in self.spec.values())
+
+    def summary(self, print_fn=print):
+        print_fn('Model: "%s"' % self.name)
+        groups = OrderedDict()
+        for n, s in self.spec.items():
+            groups.setdefault(n.split('/')[0], 0)
+            groups[n.split('/')[0]] += int(np.prod(s))
+        for g, n in groups.items():
+            print_fn('  %-40s %12d' % (g, n))
+        print_fn('Total params: %d' % self.count_params())
+
+    def to(self, device='cuda'):
+        if self.arena is None or self.arena.device != torch.device(device):
+            old = self.arena
+            self.arena = Arena(self.spec, device)
+            if old is not None:
+                self.arena.theta.copy_(old.theta)
+        return self
+
+    def init_weights(self, seed=0):
+        """Keras default initialisers from a seeded numpy generator: glorot_uniform kernels
+        (fans include the receptive field), zero biases, ConvLSTM forget-gate bias 1
+        (unit_forget_bias), orthogonal-free: recurrent kernels also glorot (seeded synthetic runs;
+        trained weights are loaded by name)."""
+        rng = np.random.default_rng(seed)
+        w = OrderedDict()
+        for name, shape in self.spec.items():
+            if name.endswith('/bias'):
+                a = np.zeros(shape, np.float32)
+                if 'convlstm' in name:
+                    f = shape[0] // 4
+                    a[f:2 * f] = 1.0
+                w[name] = a
+            elif name.endswith('localconv/kernel'):
+                h, wd, cin, f = shape
+                lim = math.sqrt(6.0 / (h * wd * cin + h * wd * f))
+                w[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+            else:
+                rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+                lim = math.sqrt(6.0 / (shape[-2] * rf + shape[-1] * rf))
+                w[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        self.set_weights(w)
+        return self
+
+    def set_weights(self, weights):
+        self.to(self.arena.device if self.arena is not None else 'cuda')
+        self.arena.load(weights)
+
+    def get_weights(self):
+        return self.arena.state_dict()
+
+    def save_weights(self, path):
+        np.savez(path, **{k.replace('/', '|'): v for k, v in self.get_weights().items()})
+
+    def load_weights(self, path):
+        with np.load(path) as z:
+            self.set_weights({k.replace('|', '/'): z[k] for k in z.files})
+
+    save = save_weights
+
+    # -- execution --------------------------------------------------------------------------
+    def _prep_inputs(self, inputs, device):
+        """numpy / torch NHWC (or NTHWC) -> list of CUDA fp32 tensors; returns (tensors, B, T)."""
+        if not isinstance(inputs, (list, tuple)):
+            inputs = [inputs]
+        out = []
+        bsz, T = None, None
+        for i, (x, s) in enumerate(zip(inputs, self.input_shapes)):
+            x = torch.as_tensor(x)
+            x = x.to(device=device, dtype=torch.float32)
+            if len(s) == 4:                       # (B,T,H,W,C) -> time-major frames (T*B,H,W,C)
+                assert x.dim() == 5, 'expected a 5-D spatio-temporal input'
+                bsz, T = x.shape[0], x.shape[1]
+                x = x.transpose(0, 1).reshape(T * bsz, *x.shape[2:])
+            else:
+                assert x.dim() == 4, 'expected a 4-D NHWC input'
+                if bsz is None:
+                    bsz = x.shape[0]
+            out.append(x.contiguous())
+        return out, bsz, T
+
+    def forward(self, inputs, training=False, math=None):
+        """Run the graph on CUDA tensors prepared by ``_prep_inputs``.  Returns (ctx, out Var)."""
+        ctx = Ctx(self.arena, math or self.math, training=training)
+        vs = [ctx.input(x) for x in inputs]
+        out = self.fn(ctx, vs)
+        return ctx, out
+
+    def _finish_output(self, out_t, bsz, T):
+        """(T*B,H,W,C) time-major frames -> (B,T,H,W,C) for spatio-temporal models."""
+        if T is None:
+            return out_t
+        return out_t.reshape(T, bsz, *out_t.shape[1:]).transpose(0, 1).contiguous()
+
+    def __call__(self, inputs, training=False):
+        dev = self.arena.device
+        ins, bsz, T = self._prep_inputs(inputs, dev)
+        _, out = self.forward(ins, training=False)
+        return self._finish_output(out.t.contiguous(), bsz, T)
+
+    def predict(self, inputs, batch_size=32, verbose=0):
+        """keras ``Model.predict`` (inference.py:238): forward in chunks of ``batch_size``."""
+        self.to('cuda')
+        if not isinstance(inputs, (list, tuple)):
+            inputs = [inputs]
+        n = len(inputs[0])
+        outs = []
+        for s in range(0, n, batch_size):
+            chunk = [x[s:s + batch_size] for x in inputs]
+            y = self(chunk)
+            outs.append(y.cpu().numpy())
+            if verbose:
+                print('%d/%d' % (min(s + batch_size, n), n))
+        return np.concatenate(outs, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# shared sections
+# ---------------------------------------------------------------------------------------------
+def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activation):
+    """Stem + N blocks + last conv + long skip -- sp_postups.py:132-168, sp_preups.py:116-151."""
+    init_n_filters = n_filters
+    x = b = c.conv(x_in, 'stem', n_filters)
+    for i in range(n_blocks):
+        n_filters = init_n_filters * (i + 1)
+        if backbone_block == 'convnet':
+            b = B.conv_block(c, 'ConvBlock%d' % (i + 1), b, n_filters, activation, attention)
+        elif backbone_block == 'resnet':
+            b = B.residual_block(c, 'ResidualBlock%d' % (i + 1), b, n_filters, activation, attention,
+                                 use_1x1conv=(i != 0))
+        elif backbone_block == 'densenet':
+            b = B.dense_block(c, 'DenseBlock%d' % (i + 1), b, n_filters, activation, attention)
+            b = B.transition_block(c, 'Transition%d' % (i + 1), b, b.C // 2)
+    b = c.conv(b, 'backbone_last', n_filters, act=activation)
+    if backbone_block == 'convnet':
+        x = b
+    elif backbone_block == 'resnet':
+        x = B.transition_block(c, 'TransitionSkip', x, n_filters, activation)
+        x = c.add(x, b)
+    elif backbone_block == 'densenet':
+        x = c.concat([x, b])
+        x = B.transition_block(c, 'TransitionBackboneLast', x, n_filters, activation)
+    return x, n_filters
+
+
+def _tail(c, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation, output_activation,
+          localcon_layer):
+    """LCB, HR aux branch, TransitionLast, ConvBlock(att), ConvBlock(out)
+    -- sp_postups.py:184-212, sp_preups.py:155-183,291-309."""
+    if localcon_layer:
+        lws = B.localized_conv_block(c, 'LocalizedConvBlock', x, 2)
+        x = c.concat([x, lws])
+    if s_in is not None:
+        s = B.conv_block(c, 'ConvBlock_aux', s_in, n_filters_aux, activation=activation)
+        x = c.concat([x, s])
+    x = B.transition_block(c, 'TransitionLast', x, init_n_filters)      # default relu
+    x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True)
+    x = B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation)
+    return x
+
+
+# ---------------------------------------------------------------------------------------------
+# builders (signatures follow dl4ds/models/*.py)
+# ---------------------------------------------------------------------------------------------
+def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_channels, lr_size,
+                       n_channels_out=1, n_filters=8, n_blocks=6, dropout_rate=0,
+                       dropout_variant=None, normalization=None, attention=False, activation='relu',
+                       output_activation=None, rc_interpolation='bilinear', localcon_layer=False,
+                       math='fp32'):
+    """net_postupsampling -- sp_postups.py:14-217."""
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    if upsampling not in POSTUPSAMPLING_METHODS:
+        raise ValueError('`upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
+    if upsampling == 'rc' and rc_interpolation != 'bilinear':
+        raise NotImplementedError('rc_interpolation=%r is outside the B200 hot path' % rc_interpolation)
+    h_lr, w_lr = lr_size
+    aux = n_aux_channels > 0
+
+    def fn(c, inputs):
+        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation)
+        if upsampling == 'spc':
+            x = B.subpixel_block(c, 'SubpixelConvolution', x, scale, nf)
+        elif upsampling == 'rc':
+            x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf)
+        else:
+            x = B.transition_block(c, 'TransitionDC', x, n_filters, activation)
+            x = B.deconv_block(c, 'Deconvolution', x, scale, nf, activation)
+        return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
+                     output_activation, localcon_layer)
+
+    ups_total = scale
+    if upsampling == 'dc' and scale == 4:
+        ups_total = 16          # reference fall-through, blocks.py:525-533
+    shapes = [(h_lr, w_lr, n_channels)]
+    if aux:
+        shapes.append((int(h_lr * ups_total), int(w_lr * ups_total), n_aux_channels))
+    return Model(backbone_block + '_' + upsampling, fn, shapes, math=math)
+
+
+def net_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out=1, n_filters=8,
+            n_blocks=6, dropout_rate=0, dropout_variant=None, normalization=None, attention=False,
+            activation='relu', output_activation=None, localcon_layer=False, math='fp32'):
+    """net_pin -- sp_preups.py:13-189."""
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    aux = n_aux_channels > 0
+
+    def fn(c, inputs):
+        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation)
+        return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
+                     output_activation, localcon_layer)
+
+    shapes = [(hr_size[0], hr_size[1], n_channels)]
+    if aux:
+        shapes.append((hr_size[0], hr_size[1], n_aux_channels))
+    return Model(backbone_block + '_pin', fn, shapes, math=math)
+
+
+def _check_nblocks(shape, power):
+    """_check_nblocks -- sp_preups.py:318-324."""
+    while shape[0] // 2 ** power < 2 or shape[1] // 2 ** power < 2:
+        print('`n_blocks` is too large, cannot downsample %d times given the input grid size. '
+              'Setting `n_blocks` to %d' % (power, power - 1))
+        power -= 1
+    return power
+
+
+def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out, n_filters, n_blocks,
+             activation='relu', dropout_rate=0, dropout_variant=None, normalization=None,
+             attention=False, decoder_upsampling='rc', rc_interpolation='bilinear',
+             output_activation=None, width_cap=256, localcon_layer=False, math='fp32'):
+    """unet_pin -- sp_preups.py:192-315."""
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    if decoder_upsampling not in POSTUPSAMPLING_METHODS:
+        raise ValueError('`decoder_upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
+    if decoder_upsampling == 'rc' and rc_interpolation != 'bilinear':
+        raise NotImplementedError('rc_interpolation=%r is outside the B200 hot path' % rc_interpolation)
+    n_blocks = _check_nblocks(hr_size, n_blocks)
+    aux = n_aux_channels > 0
+
+    def fn(c, inputs):
+        x = inputs[0]
+        nf = n_filters
+        skips, flist = [], []
+        for i in range(n_blocks):       # EncoderBlock: ConvBlock then 2x2 max-pool (blocks.py:602-618)
+            y = B.conv_block(c, 'EncoderBlock%d' % (i + 1), x, nf, activation, attention)
+            skips.append(y)
+            x = c.maxpool2(y)
+            flist.append(nf)
+            nf = min(width_cap, nf * 2)
+        x = B.conv_block(c, 'Bottleneck', x, nf, activation)
+        for j, skip in enumerate(reversed(skips)):
+            nf = flist[::-1][j]
+            if decoder_upsampling == 'spc':
+                x = B.subpixel_block(c, 'SubpixelConvolution%d' % (j + 1), x, 2, nf)
+            elif decoder_upsampling == 'rc':
+                x = B.resize_conv_block(c, 'ResizeConvolution%d' % (j + 1), x, 2, nf)
+            else:
+                x = B.deconv_block(c, 'Deconvolution%d' % (j + 1), x, 2, nf, activation)
+            x = B.pad_concat(c, x, skip)
+            x = B.conv_block(c, 'DecoderConvBlock%d' % (j + 1), x, nf, activation, attention)
+        return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
+                     output_activation, localcon_layer)
+
+    shapes = [(hr_size[0], hr_size[1], n_channels)]
+    if aux:
+        shapes.append((hr_size[0], hr_size[1], n_aux_channels))
+    return Model(backbone_block + '_pin', fn, shapes, math=math)
+
+
+def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_channels, lr_size,
+                          time_window, n_channels_out=1, n_filters=8, n_blocks=4, dropout_rate=0,
+                          dropout_variant=None, normalization=None, attention=False,
+                          activation='relu', output_activation=None, rc_interpolation='bilinear',
+                          localcon_layer=False, math='fp32'):
+    """recnet_postupsampling -- spt_postups.py:12-163.  Inputs (B,T,h,w,C) [+ (B,H,W,n_aux)];
+    output (B,T,H,W,n_channels_out).  Internally frames are time-major (T*B,H,W,C)."""
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    if backbone_block == 'unet':
+        raise ValueError('unet backbone is not compatible with post-upsampling')
+    if upsampling not in POSTUPSAMPLING_METHODS:
+        raise ValueError('`upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
+    T = int(time_window)
+    aux = n_aux_channels > 0
+    h_lr, w_lr = lr_size
+
+    def fn(c, inputs):
+        x_in = inputs[0]
+        bsz = x_in.N // T
+        x = b = B.recurrent_conv_block(c, 'RecurrentConvBlock1', x_in, n_filters, T, activation)
+        for i in range(n_blocks):
+            b = B.recurrent_conv_block(c, 'RecurrentConvBlock%d' % (i + 2), b, n_filters, T, activation)
+        if backbone_block == 'convnet':
+            x = b
+        elif backbone_block == 'resnet':
+            x = c.add(x, b)
+        else:
+            x = c.concat([x, b])
+        nf_ups = x.C
+        # TimeDistributed(upsampler): frames are independent images
+        if upsampling == 'spc':
+            x = B.subpixel_block(c, 'SubpixelConvolution', x, scale, nf_ups)
+        elif upsampling == 'rc':
+            x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf_ups)
+        else:
+            x = B.deconv_block(c, 'Deconvolution', x, scale, nf_ups, None)    # no activation passed
+        if aux:
+            # ConvBlock on the static HR field, then tf.repeat over time (spt_postups.py:135-141):
+            # the static branch is time- and (per-sample) batch-dependent only through s_in
+            s = B.conv_block(c, 'ConvBlock_aux', inputs[1], n_filters, activation, attention)
+            s = c.repeat_frames(s, T)
+            x = c.concat([x, s])
+        if localcon_layer:
+            lws = B.localized_conv_block(c, 'LocalizedConvBlock', x, 2)
+            x = c.concat([x, lws])
+        x = B.transition_block(c, 'TransitionLast', x, x.C // 2)
+        # ConvBlock(n_filters, activation=None, attention=True) on the 5-D tensor: the attention's
+        # reduce_mean over axes [1,2] pools (T,H) and keeps W (blocks.py:587)
+        y = c.conv(x, 'ConvBlock_tail/conv1', n_filters)
+        y = c.conv(y, 'ConvBlock_tail/conv2', n_filters)
+        yb = c.permute_frames(y, T, bsz)                       # batch-major (B*T,H,W,C)
+        yb = c.channel_attention(yb, 'ConvBlock_tail/att', groups=(bsz * y.W, T * y.H, y.W))
+        y = c.permute_frames(yb, bsz, T)                       # back to time-major
+        return B.conv_block(c, 'ConvBlock_out', y, n_channels_out, activation=output_activation)
+
+    shapes = [(T, h_lr, w_lr, n_channels)]
+    if aux:
+        shapes.append((int(h_lr * scale), int(w_lr * scale), n_aux_channels))
+    return Model('rec' + backbone_block + '_' + upsampling, fn, shapes, time_window=T, math=math)
+
+
+def residual_discriminator(n_channels, upsampling, is_spatiotemporal, scale, lr_size, n_filters=8,
+                           n_res_blocks=4, normalization=None, activation='relu', attention=False,
+                           math='fp32'):
+    """residual_discriminator -- discriminator.py:11-81 (spatial variant).  ResidualBlocks always
+    use relu (the ``activation`` argument is ignored there, :36-38).  Dropout(0.4) on the pooled
+    features is applied with a caller-supplied keep mask as third input (training) or skipped."""
+    if is_spatiotemporal:
+        raise NotImplementedError('spatio-temporal discriminator is outside the B200 hot path')
+    if normalization is not None:
+        raise NotImplementedError('normalization=%r is outside the B200 hot path' % (normalization,))
+
+    def fn(c, inputs):
+        x_in, x_ref = inputs[0], inputs[1]
+        mask = inputs[2] if len(inputs) > 2 else None
+        x1 = b = c.conv(x_in, 'branch1_stem', n_filters)
+        for i in range(n_res_blocks):
+            b = B.residual_block(c, 'ResidualBlock%d_branch1' % (i + 1), b, n_filters, 'relu', attention)
+        x1 = c.conv(b, 'branch1_last', n_filters, res=x1)
+        x2 = cc = c.conv(x_ref, 'branch2_stem', n_filters)
+        for i in range(n_res_blocks):
+            cc = B.residual_block(c, 'ResidualBlock%d_branch2' % (i + 1), cc, n_filters, 'relu', attention)
+        if upsampling in POSTUPSAMPLING_METHODS:
+            if scale == 5:
+                cc = c.conv(cc, 'branch2_down1', n_filters, stride=2, padding='valid')
+                x2 = c.conv(cc, 'branch2_down2', n_filters, stride=2, padding='valid')
+                x2 = c.pad_to(x2, x2.H - 1, x2.W - 1)            # Cropping2D(((0,1),(0,1)))
+            elif scale == 4:
+                cc = c.conv(cc, 'branch2_down1', n_filters, stride=2)
+                x2 = c.conv(cc, 'branch2_down2', n_filters, stride=2)
+            else:
+                x2 = c.resize_bilinear(cc, lr_size[0], lr_size[1])
+        else:
+            x2 = c.conv(cc, 'branch2_last', n_filters, res=x2)
+        x = c.concat([x1, x2])
+        x = B.residual_block(c, 'ResidualBlock_merged', x, x.C, 'relu', attention)
+        x = c.group_mean(x)
+        if mask is not None:
+            x = c.mul_mask(x, mask)
+        x = c.dense(x, 'dense1', 32, act='sigmoid')
+        return c.dense(x, 'dense2', 1, act='sigmoid')
+
+    if upsampling in POSTUPSAMPLING_METHODS:
+        in_hw = (lr_size[0], lr_size[1])
+        ref_hw = (int(lr_size[0] * scale), int(lr_size[1] * scale))
+    else:
+        in_hw = ref_hw = (lr_size[0], lr_size[1])
+    return Model('discriminator', fn, [in_hw + (n_channels,), ref_hw + (1,)], math=math)

@@ -114,19 +114,23 @@ int dl4ds_copy_channels(const float* src, int src_ld, float* dst, int dst_ld,
  *  fwd : pooled[N,C] (sum over H*W, workspace, zeroed by the call), hidden[N,Cr], scale[N,C] are
  *        saved for backward.  w1 (C,Cr), w2 (Cr,C) are the 1x1 Conv2D kernels.
  *  bwd : dx = dy*scale + dmean/(H*W); parameter gradients accumulate.  dsum[N,C] is workspace.
- *  groups_hw: number of pixels pooled per attention vector and n_groups vectors (4-D tensors:
- *  n_groups = N, pix_per_group = H*W).
+ *  n_groups attention vectors, each pooled over pix_per_group pixels.  Pixel p belongs to group
+ *  (p / (pix_per_group*inner))*inner + p % inner.  4-D tensors: n_groups = N, pix_per_group = H*W,
+ *  inner = 1.  5-D (B,T,H,W,C) tensors pooled over axes [1,2] = (T,H) as blocks.py:587 does when
+ *  called from spt_postups.py:153-154: n_groups = B*W, pix_per_group = T*H, inner = W.
  * ------------------------------------------------------------------------------------------- */
 int dl4ds_channel_attention_fwd(const float* x, int x_ld, float* y, int y_ld,
                                 const float* w1, const float* b1, const float* w2, const float* b2,
                                 float* pooled, float* hidden, float* scale,
-                                int n_groups, int64_t pix_per_group, int C, int Cr, void* stream);
+                                int n_groups, int64_t pix_per_group, int inner, int C, int Cr,
+                                void* stream);
 int dl4ds_channel_attention_bwd(const float* x, int x_ld, const float* dy, int dy_ld,
                                 float* dx, int dx_ld,
                                 const float* w1, const float* w2,
                                 const float* pooled, const float* hidden, const float* scale,
                                 float* dsum, float* dw1, float* db1, float* dw2, float* db2,
-                                int n_groups, int64_t pix_per_group, int C, int Cr, void* stream);
+                                int n_groups, int64_t pix_per_group, int inner, int C, int Cr,
+                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pixel losses -- losses.py:5-20 (Keras MeanAbsoluteError / MeanSquaredError = global mean).
@@ -145,6 +149,13 @@ int dl4ds_pixel_loss(const float* y_pred, const float* y_true, float* loss_out, 
 int dl4ds_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n,
                     float lr, float beta1, float beta2, float eps, int t, float grad_scale,
                     void* stream);
+
+/* Same update with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) read from DEVICE memory (one float), so that a
+ * captured CUDA graph of the whole step can be replayed while the host advances t / the
+ * PiecewiseConstantDecay schedule (supervised.py:336-353). */
+int dl4ds_adam_step_dev(float* theta, const float* grad, float* m, float* v, int64_t n,
+                        const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Data path: HR -> LR coarsening by s x s block mean == cv2.resize(INTER_AREA) at an integer
@@ -199,6 +210,14 @@ int dl4ds_mul(const float* a, const float* b, float* out, int64_t n, void* strea
  * loss_out[0] += scale * bce(target, p);  dp (+)= scale * d bce / d p  (accumulate flag). */
 int dl4ds_bce_loss(const float* p, float target, float* loss_out, float* dp, int64_t n,
                    float scale, int accumulate, void* stream);
+/* dst[b][a][:] = src[a][b][:] over frames of `frame_elems` floats: (B,T,...) <-> (T,B,...) layout
+ * change around the ConvLSTM recurrence (spt_postups.py:96-163 keeps NTHWC; the recurrence here runs
+ * time-major so each step is one dense tensor). */
+int dl4ds_permute_frames(const float* src, float* dst, int A, int B, int64_t frame_elems, void* stream);
+/* ZeroPadding2D(((0,dh),(0,dw))) of PadConcat -- blocks.py:639-655: dst (N,Hd,Wd,C) <- src (N,Hs,Ws,C)
+ * zero-filled where src has no pixel.  With Hd<=Hs, Wd<=Ws it is the adjoint crop. */
+int dl4ds_pad_bottom_right(const float* src, int src_ld, float* dst, int dst_ld,
+                           int N, int Hs, int Ws, int Hd, int Wd, int C, void* stream);
 /* y = a*x + b*y element-wise (gradient combination for the two-seed cGAN backward). */
 int dl4ds_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream);
 

@@ -1,0 +1,238 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): every engine op and every network graph,
+forward AND backward, through the C ABI (libdl4ds_b200.so) against the oracle
+(oracle/torch_ref.py -- torch-CPU fp32 restatement of the reference's Keras graphs; parity
+unpinned by the reference, see oracle/__init__.py).
+
+Tolerances (fp32 CUDA-core math mode, the exact-fp32 anchor): forward <= 2e-5 * max|y|,
+gradients <= 2e-4 * max|g| (fp32 summation-order noise of split-K atomics over up to 1e6 pixels).
+"""
+import numpy as np
+import pytest
+import torch
+
+from dl4ds_b200 import blocks as B
+from dl4ds_b200 import nets
+from dl4ds_b200.spec import SpecCtx
+from oracle import torch_ref as R
+from tests.util import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def _o(fn):
+    """Wrap an oracle NCHW block function into NHWC-in / NHWC-out."""
+    def w(p, xs):
+        return R._nhwc(fn(p, [R._nchw(x) for x in xs]))
+    return w
+
+
+# ------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize('shape,cout,k,act,stride,padding', [
+    ((2, 8, 8, 1), 8, 3, None, 1, 'same'),
+    ((2, 9, 7, 3), 5, 3, 'relu', 1, 'same'),
+    ((1, 16, 16, 8), 16, 3, 'relu', 1, 'same'),
+    ((2, 12, 12, 24), 40, 3, None, 1, 'same'),
+    ((2, 10, 10, 48), 48, 3, 'tanh', 1, 'same'),
+    ((2, 6, 6, 16), 64, 1, 'sigmoid', 1, 'same'),
+    ((2, 11, 11, 4), 6, 5, None, 1, 'same'),
+    ((2, 16, 16, 8), 8, 3, None, 2, 'same'),
+    ((2, 15, 13, 8), 8, 3, 'relu', 2, 'same'),
+    ((2, 17, 17, 8), 8, 3, None, 2, 'valid'),
+    ((1, 20, 20, 2), 3, 7, None, 1, 'same'),
+    ((3, 1, 1, 16), 32, 1, 'sigmoid', 1, 'same'),
+])
+def test_conv(cuda, shape, cout, k, act, stride, padding):
+    fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=k, act=act, stride=stride, padding=padding)
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=k, stride=stride, padding=padding), act))
+    compare(fn, ofn, [shape], cuda)
+
+
+def test_conv_residual_epilogue(cuda):
+    def fn(c, xs):
+        return c.conv(xs[0], 'cv', 12, act='relu', res=xs[1])
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], 12) + xs[1], 'relu'))
+    compare(fn, ofn, [(2, 9, 10, 7), (2, 9, 10, 12)], cuda)
+
+
+@pytest.mark.parametrize('r,c', [(2, 12), (2, 48), (5, 2), (3, 4)])
+def test_conv_depth_to_space(cuda, r, c):
+    fn = lambda cx, xs: cx.conv(xs[0], 'cv', c * r * r, d2s=r)
+    ofn = _o(lambda p, xs: R.depth_to_space(R._conv(p, 'cv', xs[0], c * r * r), r))
+    compare(fn, ofn, [(2, 6, 5, 8)], cuda)
+
+
+@pytest.mark.parametrize('shape,cout,stride', [((2, 4, 4, 8), 6, 2), ((1, 5, 3, 4), 4, 2),
+                                               ((1, 3, 3, 4), 5, 4), ((2, 8, 8, 48), 48, 2)])
+def test_conv_transpose(cuda, shape, cout, stride):
+    fn = lambda c, xs: c.conv_transpose(xs[0], 'ct', cout, 9, stride, act='relu')
+
+    def ofn_(p, xs):
+        w = p.get('ct/kernel', (9, 9, cout, xs[0].shape[1]))
+        return R.act(R.conv2d_transpose_same(xs[0], w, stride), 'relu')
+    compare(fn, _o(ofn_), [shape], cuda)
+
+
+def test_shared_conv_accumulates(cuda):
+    """SubpixelConvolutionBlock applies ONE conv2x at every x2 stage (blocks.py:415,421-422)."""
+    fn = lambda c, xs: B.subpixel_block(c, 'spc', xs[0], 4, 8)
+    ofn = _o(lambda p, xs: R.subpixel_block(p, 'spc', xs[0], 4, 8))
+    compare(fn, ofn, [(2, 5, 6, 8)], cuda)
+
+
+# ------------------------------------------------------------------------------------------ blocks
+@pytest.mark.parametrize('att,proj', [(False, False), (False, True), (True, True)])
+def test_residual_block(cuda, att, proj):
+    cin = 16 if not proj else 8
+    fn = lambda c, xs: B.residual_block(c, 'rb', xs[0], 16, 'relu', att, proj)
+    ofn = _o(lambda p, xs: R.residual_block(p, 'rb', xs[0], 16, 'relu', att, proj))
+    compare(fn, ofn, [(2, 8, 8, cin)], cuda)
+
+
+@pytest.mark.parametrize('att', [False, True])
+def test_dense_block(cuda, att):
+    fn = lambda c, xs: B.dense_block(c, 'db', xs[0], 8, 'relu', att)
+    ofn = _o(lambda p, xs: R.dense_block(p, 'db', xs[0], 8, 'relu', att))
+    compare(fn, ofn, [(2, 7, 9, 12)], cuda)
+
+
+def test_conv_block_attention(cuda):
+    fn = lambda c, xs: B.conv_block(c, 'cb', xs[0], 8, None, True)
+    ofn = _o(lambda p, xs: R.conv_block(p, 'cb', xs[0], 8, None, True))
+    compare(fn, ofn, [(3, 16, 16, 8)], cuda)
+
+
+def test_channel_attention_wide(cuda):
+    fn = lambda c, xs: c.channel_attention(xs[0], 'att')
+    ofn = _o(lambda p, xs: R.channel_attention(p, 'att', xs[0], 80))
+    compare(fn, ofn, [(2, 6, 6, 80)], cuda)
+
+
+def test_localized_conv_block(cuda):
+    fn = lambda c, xs: B.localized_conv_block(c, 'lcb', xs[0], 2)
+    ofn = _o(lambda p, xs: R.localized_conv_block(p, 'lcb', xs[0], 2))
+    compare(fn, ofn, [(3, 8, 6, 10)], cuda)
+
+
+def test_resize_conv_block(cuda):
+    fn = lambda c, xs: B.resize_conv_block(c, 'rc', xs[0], 4, 8)
+    ofn = _o(lambda p, xs: R.resize_conv_block(p, 'rc', xs[0], 4, 8))
+    compare(fn, ofn, [(2, 5, 7, 8)], cuda)
+
+
+def test_resize_bilinear_down(cuda):
+    fn = lambda c, xs: c.conv(c.resize_bilinear(xs[0], 4, 5), 'cv', 3, k=1)
+    ofn = _o(lambda p, xs: R._conv(p, 'cv', R.resize_bilinear(xs[0], 4, 5), 3, k=1))
+    compare(fn, ofn, [(2, 12, 15, 3)], cuda)
+
+
+def test_maxpool_padconcat(cuda):
+    def fn(c, xs):
+        y = c.conv(xs[0], 'cv', 6)
+        d = c.maxpool2(y)
+        u = c.resize_bilinear(d, d.H * 2, d.W * 2)
+        return c.conv(B.pad_concat(c, u, y), 'cv2', 4)
+
+    def ofn_(p, xs):
+        y = R._conv(p, 'cv', xs[0], 6)
+        d = R.maxpool2(y)
+        u = R.resize_bilinear(d, d.shape[2] * 2, d.shape[3] * 2)
+        return R._conv(p, 'cv2', R.pad_concat(u, y), 4)
+    compare(fn, _o(ofn_), [(2, 9, 11, 3)], cuda)
+
+
+def test_deconv_block_x8(cuda):
+    fn = lambda c, xs: B.deconv_block(c, 'dc', xs[0], 8, 6, 'relu')
+    ofn = _o(lambda p, xs: R.deconv_block(p, 'dc', xs[0], 8, 6, 'relu'))
+    compare(fn, ofn, [(1, 3, 4, 4)], cuda)
+
+
+def test_convlstm_block(cuda):
+    T, Bz = 3, 2
+
+    def fn(c, xs):
+        return B.recurrent_conv_block(c, 'rcb', xs[0], 4, T, 'relu')
+
+    def ofn(p, xs):     # xs[0]: time-major frames (T*B,H,W,C) NHWC
+        x = xs[0]
+        x5 = x.reshape(T, Bz, *x.shape[1:]).permute(1, 0, 4, 2, 3)      # (B,T,C,H,W)
+        y5 = R.recurrent_conv_block(p, 'rcb', x5, 4, 'relu')            # (B,T,F,H,W)
+        return y5.permute(1, 0, 3, 4, 2).reshape(T * Bz, y5.shape[3], y5.shape[4], y5.shape[2])
+    compare(fn, ofn, [(T * Bz, 6, 5, 3)], cuda, gtol=5e-4)
+
+
+# ------------------------------------------------------------------------------------------ nets
+def _net_case(cuda, model, ofn, batch, tol=5e-5, gtol=5e-4):
+    shapes = []
+    for s in model.input_shapes:
+        if len(s) == 4:
+            shapes.append((batch * s[0],) + tuple(s[1:]))
+        else:
+            shapes.append((batch,) + tuple(s))
+    compare(model.fn, ofn, shapes, cuda, tol=tol, gtol=gtol, input_grads=False)
+
+
+def test_net_resnet_spc_cfg1(cuda):
+    """BASELINE config 1/2 graph: resnet + 4x SPC, 32->128, 1 channel (batch 4)."""
+    m = nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (32, 32))
+    assert m.count_params() == 204405
+    ofn = lambda p, xs: R.net_postupsampling(p, xs, 'resnet', 'spc', 4)
+    _net_case(cuda, m, ofn, 4)
+
+
+def test_net_densenet_dc_lcb_cfg3(cuda):
+    """BASELINE config 3 graph: densenet + attention + LCB, 8x deconv, 5 LR ch + 1 HR aux."""
+    m = nets.net_postupsampling('densenet', 'dc', 8, 5, 1, (8, 8), attention=True, localcon_layer=True)
+    ofn = lambda p, xs: R.net_postupsampling(p, xs, 'densenet', 'dc', 8, attention=True, localcon_layer=True)
+    _net_case(cuda, m, ofn, 3)
+
+
+def test_net_convnet_rc(cuda):
+    m = nets.net_postupsampling('convnet', 'rc', 2, 2, 0, (10, 12), n_blocks=2)
+    ofn = lambda p, xs: R.net_postupsampling(p, xs, 'convnet', 'rc', 2, n_blocks=2)
+    _net_case(cuda, m, ofn, 2)
+
+
+def test_net_pin(cuda):
+    m = nets.net_pin('resnet', 2, 1, (16, 16), n_blocks=3)
+    ofn = lambda p, xs: R.net_pin(p, xs, 'resnet', n_blocks=3)
+    _net_case(cuda, m, ofn, 2)
+
+
+def test_net_unet_pin_cfg5(cuda):
+    """BASELINE config 5 generator graph (reduced grid): unet / pin, 2 in ch + 1 aux."""
+    m = nets.unet_pin('unet', 2, 1, (32, 32), 1, 8, 6)
+    ofn = lambda p, xs: R.unet_pin(p, xs, 8, 6)
+    _net_case(cuda, m, ofn, 2)
+
+
+def test_net_recnet_cfg4(cuda):
+    """BASELINE config 4 graph (reduced): recurrent resnet + 4x resize-conv, T=3; includes the
+    5-D channel-attention (T,H)-pooling quirk (blocks.py:587)."""
+    T, Bz = 3, 2
+    m = nets.recnet_postupsampling('resnet', 'rc', 4, 1, 1, (8, 8), T, n_blocks=1)
+
+    def ofn(p, xs):
+        x = xs[0]
+        x5 = x.reshape(T, Bz, *x.shape[1:]).permute(1, 0, 2, 3, 4)      # (B,T,h,w,C)
+        y5 = R.recnet_postupsampling(p, [x5, xs[1]], 'resnet', 'rc', 4, T, n_blocks=1)
+        return y5.permute(1, 0, 2, 3, 4).reshape(T * Bz, *y5.shape[2:])
+    shapes = [(T * Bz, 8, 8, 1), (Bz, 32, 32, 1)]
+    compare(m.fn, ofn, shapes, cuda, tol=5e-5, gtol=1e-3, input_grads=False)
+
+
+@pytest.mark.parametrize('ups,scale', [('pin', 4), ('spc', 4), ('spc', 2)])
+def test_discriminator(cuda, ups, scale):
+    lr = (20, 20) if ups == 'pin' else (5, 5)
+    m = nets.residual_discriminator(2, ups, False, scale, lr, n_res_blocks=2)
+    mask = (np.random.default_rng(5).random((3, 1, 1, 16)) > 0.4).astype(np.float32) / 0.6
+
+    def fn(c, xs):
+        mk = c.input((3, 1, 1, 16)) if isinstance(c, SpecCtx) else c.input(torch.as_tensor(mask).cuda())
+        return m.fn(c, [xs[0], xs[1], mk])
+
+    def ofn(p, xs):
+        y = R.residual_discriminator(p, xs, ups, scale, lr, n_res_blocks=2,
+                                     dropout_mask=torch.as_tensor(mask.reshape(3, 16)))
+        return y.reshape(3, 1, 1, 1)
+    shapes = [(3,) + s for s in m.input_shapes]
+    compare(fn, ofn, shapes, cuda, tol=5e-5, gtol=1e-3)
