@@ -148,6 +148,7 @@ class Ctx:
         self.device = arena.device
         self.names_used = []
         self.launches = 0
+        self.param_grads = True     # False: backward propagates to inputs only (cGAN G-through-D pass)
 
     # ---------------------------------------------------------------- helpers
     def _call(self, name, *args):
@@ -197,6 +198,15 @@ class Ctx:
         assert src.C == dst.C and src.npix == dst.npix
         self._call('dl4ds_copy_channels', src.ptr, src.ld, dst.ptr, dst.ld, src.npix, src.C, accumulate,
                    _stream())
+
+    def _dense(self, gvar):
+        """Return ``gvar`` itself if it is a dense tensor, else a dense copy (ops whose kernels
+        take no pitch use this on incoming gradients that are channel slices of a concat)."""
+        if gvar.off == 0 and gvar.ld == gvar.C:
+            return gvar
+        d = gvar.like()
+        self._copy(gvar, d)
+        return d
 
     def _give_grad(self, var, gvar, adopt=True):
         """Hand ``gvar`` (a Var holding d loss / d var) to ``var``.  A gradient buffer has exactly one
@@ -248,18 +258,20 @@ class Ctx:
             if dy is None:
                 return
             # epilogue backward: dz = dy * act'(y) (un-shuffled if d2s), dbias += sum dz
+            pg = self.param_grads
             if a == 0 and r == 1:
                 dz = dy
-                if bias:
+                if bias and pg:
                     self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, None, 0, None, 0,
                                self._g(name + '/bias').data_ptr(), x.N, Ho, Wo, cout, 0, 1, _stream())
             else:
                 dz = new_var(x.N, Ho, Wo, cout, self.device) if r > 1 else dy
                 self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dz.ptr, dz.ld,
-                           self._g(name + '/bias').data_ptr() if bias else None,
+                           self._g(name + '/bias').data_ptr() if (bias and pg) else None,
                            x.N, Ho, Wo, cout, a, r, _stream())
             # weight gradient (accumulating)
-            self._wgrad(x, dz, self._g(name + '/kernel'), k, stride, pt, pl)
+            if pg:
+                self._wgrad(x, dz, self._g(name + '/kernel'), k, stride, pt, pl)
             # input gradient
             if x.requires_grad:
                 def wr(dst, beta):
@@ -303,7 +315,8 @@ class Ctx:
                 self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dz.ptr, dz.ld, None,
                            x.N, Ho, Wo, cout, a, 1, _stream())
             # dw[k][cout][cin] += sum dz[s*i + k - p][cout] * x[i][cin]
-            self._wgrad(dz, x, self._g(name + '/kernel'), k, stride, pt, pl)
+            if self.param_grads:
+                self._wgrad(dz, x, self._g(name + '/kernel'), k, stride, pt, pl)
             if x.requires_grad:
                 def wr(dst, beta):
                     self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
@@ -406,14 +419,17 @@ class Ctx:
             if dy is None:
                 return
             dsum = torch.empty(ng * C, dtype=torch.float32, device=dev)
+            if self.param_grads:
+                gp = [self._g(name + s) for s in ('/conv1/kernel', '/conv1/bias', '/conv2/kernel', '/conv2/bias')]
+            else:       # parameter gradients go to scratch
+                gp = [torch.zeros(n_, dtype=torch.float32, device=dev) for n_ in (C * Cr, Cr, Cr * C, C)]
 
             def wr(dst):
                 self.launches += 3
                 self._call('dl4ds_channel_attention_bwd', x.ptr, x.ld, dy.ptr, dy.ld, dst.ptr, dst.ld,
                            w1.data_ptr(), w2.data_ptr(), pooled.data_ptr(), hidden.data_ptr(),
                            scale.data_ptr(), dsum.data_ptr(),
-                           self._g(name + '/conv1/kernel').data_ptr(), self._g(name + '/conv1/bias').data_ptr(),
-                           self._g(name + '/conv2/kernel').data_ptr(), self._g(name + '/conv2/bias').data_ptr(),
+                           gp[0].data_ptr(), gp[1].data_ptr(), gp[2].data_ptr(), gp[3].data_ptr(),
                            ng, ppg, inner, C, Cr, _stream())
             self._acc_via_tmp(x, wr)
             out.grad = None
@@ -433,10 +449,15 @@ class Ctx:
             if dy is None:
                 return
 
+            if self.param_grads:
+                gk, gb = self._g(name + '/kernel'), self._g(name + '/bias')
+            else:
+                gk, gb = torch.zeros_like(w), torch.zeros_like(b)
+
             def wr(dst):
                 self._call('dl4ds_local_conv1x1_bwd', x.ptr, x.ld, dy.ptr, dy.ld, w.data_ptr(),
-                           dst.ptr, dst.ld, self._g(name + '/kernel').data_ptr(),
-                           self._g(name + '/bias').data_ptr(), x.N, x.H, x.W, x.C, filters, _stream())
+                           dst.ptr, dst.ld, gk.data_ptr(), gb.data_ptr(), x.N, x.H, x.W, x.C, filters,
+                           _stream())
             self._acc_via_tmp(x, wr)
             out.grad = None
         self._record(bwd)
@@ -510,7 +531,7 @@ class Ctx:
             dy = out.grad
             if dy is None:
                 return
-            assert dy.ld == dy.C
+            dy = self._dense(dy)
 
             def wr(dst):
                 self._call('dl4ds_permute_frames', dy.ptr, dst.ptr, B, A, fe, _stream())
@@ -529,7 +550,7 @@ class Ctx:
             dy = out.grad
             if dy is None:
                 return
-            assert dy.ld == dy.C
+            dy = self._dense(dy)
 
             def wr(dst):
                 self._call('dl4ds_group_mean_bwd', dy.ptr, dst.ptr, dst.ld, x.N, x.H * x.W, x.C, _stream())
@@ -550,9 +571,8 @@ class Ctx:
             dy = out.grad
             if dy is None:
                 return
-            assert dy.off == 0 and dy.ld == dy.C
             for t in range(T):
-                self._give_grad(x, Var(dy.buf[t * B_:(t + 1) * B_]), adopt=False)
+                self._give_grad(x, Var(dy.buf[t * B_:(t + 1) * B_], dy.off, dy.C), adopt=False)
             out.grad = None
         self._record(bwd)
         return out
@@ -570,7 +590,7 @@ class Ctx:
             dy = out.grad
             if dy is None:
                 return
-            assert dy.ld == dy.C
+            dy = self._dense(dy)
 
             def wr(dst):
                 self._call('dl4ds_mul', dy.ptr, mask.data_ptr(), dst.ptr, x.npix * x.C, _stream())
@@ -616,7 +636,7 @@ class Ctx:
             dy = out.grad
             if dy is None:
                 return
-            assert dy.ld == dy.C and dy.off == 0
+            dy = self._dense(dy)
             dh = dy.buf      # owned; dh_{t-1} is accumulated in place
             dz = new_var(TB, H, W, F4, dev)
             dc = [torch.empty((B, H, W, filters), dtype=torch.float32, device=dev) for _ in range(2)]
@@ -682,10 +702,13 @@ class Ctx:
         return loss_buf
 
     # ---------------------------------------------------------------- backward
-    def backward(self):
+    def backward(self, keep_tape=False):
+        """Run the recorded backward closures.  ``keep_tape`` allows a second pass with other seeds
+        (cGAN: D(fake) is differentiated once for the discriminator weights, once for the generator)."""
         for fn in reversed(self.tape):
             fn()
-        self.tape = []
+        if not keep_tape:
+            self.tape = []
 
 
 def adam_step(arena, lr, beta_1=0.9, beta_2=0.999, eps=1e-7, grad_scale=1.0, lr_t_dev=None):

@@ -1,0 +1,184 @@
+"""Device-side training / evaluation steps: what Keras' ``train_function`` + Horovod's
+``DistributedOptimizer`` do per batch in the reference (supervised.py:363-369,396-406), as ONE
+replayable CUDA graph of hand-written kernels:
+
+    zero grad arena -> forward -> pixel loss (+ gradient seed) -> backward -> [all-reduce] -> Adam
+
+Static shapes (fixed per-rank batch) make the whole step capturable; the host only refreshes the
+input buffers and the scalar ``lr_t`` (Adam bias correction x PiecewiseConstantDecay) between
+replays.  Data parallelism shards the batch only: every rank runs the same graph on its own
+samples; the flat gradient arena is summed over ranks with a single NCCL all-reduce and the
+1/world_size of Horovod's average is folded into the Adam kernel's ``grad_scale``.
+"""
+import math
+
+import torch
+
+from . import _lib
+from .engine import Ctx, Var, _stream, adam_step
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class LRSchedule:
+    """float, or PiecewiseConstantDecay([boundary], [v0, v1]) (supervised.py:336-353): v0 while the
+    optimizer iteration count <= boundary, else v1."""
+
+    def __init__(self, learning_rate, lr_decay_after=1e5, scale=1.0):
+        if isinstance(learning_rate, (tuple, list)) and len(learning_rate) > 1:
+            self.values = (float(learning_rate[0]) * scale, float(learning_rate[1]) * scale)
+            self.boundary = lr_decay_after
+        else:
+            if isinstance(learning_rate, (tuple, list)):
+                learning_rate = learning_rate[0]
+            self.values = (float(learning_rate) * scale,) * 2
+            self.boundary = float('inf')
+
+    def __call__(self, iterations):
+        return self.values[0] if iterations <= self.boundary else self.values[1]
+
+
+class SupervisedStep:
+    """One optimizer step of ``model`` on fixed-shape device batches."""
+
+    def __init__(self, model, batch_shapes, target_shape, loss='mae', lr=1e-3, lr_decay_after=1e5,
+                 beta_1=0.9, beta_2=0.999, eps=1e-7, math=None, use_graph=True, lr_scale=1.0):
+        self.model = model
+        self.arena = model.arena
+        dev = self.arena.device
+        self.loss_kind = loss
+        self.schedule = lr if isinstance(lr, LRSchedule) else LRSchedule(lr, lr_decay_after, lr_scale)
+        self.b1, self.b2, self.eps = beta_1, beta_2, eps
+        self.math = math or model.math
+        self.inputs = [torch.zeros(s, dtype=torch.float32, device=dev) for s in batch_shapes]
+        self.target = torch.zeros(target_shape, dtype=torch.float32, device=dev)
+        self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else None
+        self.use_graph = use_graph
+        self.graph_fb = None        # zero-grad + forward + loss + backward
+        self.graph_opt = None       # adam
+        self.launches_per_step = 0
+        self.world = 1
+        d = _dist()
+        if d is not None:
+            self.world = d.get_world_size()
+
+    # the recorded work -------------------------------------------------------------------------
+    def _fwd_bwd(self):
+        self.arena.grad.zero_()
+        self.loss_buf.zero_()
+        ctx, out = self.model.forward(self.inputs, training=True, math=self.math)
+        ctx.pixel_loss(out, ctx.input(self.target), self.loss_kind, loss_buf=self.loss_buf)
+        ctx.backward()
+        return ctx.launches + 2     # + the two memsets
+
+    def _opt(self):
+        _lib.call('dl4ds_adam_step_dev', self.arena.theta.data_ptr(), self.arena.grad.data_ptr(),
+                  self.arena.m.data_ptr(), self.arena.v.data_ptr(), self.arena.n,
+                  self.lr_t_dev.data_ptr(), float(self.b1), float(self.b2), float(self.eps),
+                  1.0 / self.world, _stream())
+        return 1
+
+    def _allreduce(self):
+        d = _dist()
+        if d is not None:
+            d.all_reduce(self.arena.grad, op=d.ReduceOp.SUM)
+
+    def _set_lr_t(self):
+        self.arena.t += 1
+        t = self.arena.t
+        lr = self.schedule(t - 1)     # Keras evaluates the schedule at `iterations` before increment
+        lr_t = lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+        if self._lr_host is not None:
+            self._lr_host[0] = lr_t
+            self.lr_t_dev.copy_(self._lr_host, non_blocking=True)
+        else:
+            self.lr_t_dev.fill_(lr_t)
+
+    def capture(self):
+        """Warm up eagerly (module load, allocator), restore the optimizer state, then capture."""
+        a = self.arena
+        snap = (a.theta.clone(), a.m.clone(), a.v.clone(), a.t)
+        self._set_lr_t()
+        n1 = self._fwd_bwd()
+        self._allreduce()
+        n2 = self._opt()
+        self.launches_per_step = n1 + n2
+        torch.cuda.synchronize()
+        a.theta.copy_(snap[0]); a.m.copy_(snap[1]); a.v.copy_(snap[2]); a.t = snap[3]
+        if not self.use_graph:
+            return self
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.graph_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fb, stream=s):
+                self._fwd_bwd()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, stream=s):
+                self._opt()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        return self
+
+    # per-batch entry points --------------------------------------------------------------------
+    def load_batch(self, inputs, target):
+        """Copy a batch (CUDA tensors, or pinned host tensors -> async H2D) into the static buffers."""
+        for dst, src in zip(self.inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+
+    def run(self):
+        """One optimizer step on the batch in the static buffers.  Returns the device loss scalar
+        (valid after the stream is synchronised / ``.item()``)."""
+        self._set_lr_t()
+        if self.graph_fb is not None:
+            self.graph_fb.replay()
+            self._allreduce()
+            self.graph_opt.replay()
+        else:
+            self._fwd_bwd()
+            self._allreduce()
+            self._opt()
+        return self.loss_buf
+
+    def broadcast_from_rank0(self):
+        """hvd BroadcastGlobalVariablesCallback(0) (supervised.py:369) + optimizer slots."""
+        d = _dist()
+        if d is not None:
+            for t in (self.arena.theta, self.arena.m, self.arena.v):
+                d.broadcast(t, src=0)
+
+
+class EvalStep:
+    """Forward + loss on fixed-shape device batches (Keras ``evaluate`` / validation)."""
+
+    def __init__(self, model, loss='mae', math=None):
+        self.model = model
+        self.loss_kind = loss
+        self.math = math or model.math
+
+    def run(self, inputs, target):
+        dev = self.model.arena.device
+        ctx = Ctx(self.model.arena, self.math, training=False)
+        vs = [ctx.input(x) for x in inputs]
+        out = self.model.fn(ctx, vs)
+        buf = torch.zeros(1, dtype=torch.float32, device=dev)
+        ctx.pixel_loss(out, ctx.input(target), self.loss_kind, loss_buf=buf)
+        return buf
+
+
+def coarsen_on_device(hr, scale):
+    """(N,H,W,C) CUDA fp32 -> (N,H/s,W/s,C): exact s x s block mean == cv2 INTER_AREA at an integer
+    factor (utils.py:376-384), the HR->LR step of dataloader.py:204-208 done on the device."""
+    assert hr.is_cuda and hr.dtype == torch.float32 and hr.is_contiguous()
+    n, h, w, c = hr.shape
+    lr = torch.empty((n, h // scale, w // scale, c), dtype=torch.float32, device=hr.device)
+    _lib.call('dl4ds_avgpool_coarsen', hr.data_ptr(), lr.data_ptr(), n, h, w, c, int(scale), _stream())
+    return lr
