@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Headline benchmark: HR pixels per second of one SUPERVISED TRAINING STEP (forward + MAE +
+backward + [gradient all-reduce] + Adam) of the residual-backbone 4x sub-pixel model on synthetic
+32 -> 128 single-channel tiles, batch 64 per GPU (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--math fp32|tf32x3|tf32]
+
+N > 1 is launched by ``python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N``:
+one rank per GPU, batch sharded (weak scaling, per-GPU batch fixed as in the reference,
+training/base.py:115-116), ONE gradient all-reduce per step.  Rank 0 prints ONE JSON line.
+
+  value      device-resident inputs (a pool of pre-staged batches in HBM), the captured CUDA graph
+             of the whole step replayed K times, CUDA-event timed, max over ranks.
+  e2e        the same step driven through the public trainer API (`SupervisedTrainer.train_on_batch`)
+             with HOST numpy batches: pinned staging + H2D of LR/HR every step and a D2H read of
+             the loss inside the timed region.
+  roofline   the dominant kernel of the step (largest summed duration), timed with CUDA events
+             around its launches on the launching stream in extra eager steps right after the
+             timed region; algorithmic FLOPs = 2*MACs of those launches.
+  cpu_baseline / --impl reference
+             the oracle (oracle/torch_ref.py: torch-CPU fp32 restatement of the reference's TF/Keras
+             graph + Keras Adam) on the host cores.  TF itself is not installable offline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'HR-pixels/sec, supervised training step (4x residual SPC, 32->128)'
+UNIT = 'HR-px/s'
+LR_HW, SCALE, BATCH = 32, 4, 64
+HR_HW = LR_HW * SCALE
+WORKLOAD = ('SupervisedTrainer step: resnet backbone (n_filters=8, n_blocks=6), 4x SPC, 32->128, '
+            '1 channel, batch 64 per GPU, MAE, Adam(1e-3)')
+
+
+def _config(n_gpus, extra=None):
+    cfg = {'workload': WORKLOAD, 'global_batch': BATCH * n_gpus, 'per_gpu_batch': BATCH,
+           'lr_hw': LR_HW, 'hr_hw': HR_HW, 'scale': SCALE, 'parallelism': 'dp%d' % n_gpus,
+           'l2_policy': 'working set >> L2: ~1 GB of activations per step and 4 rotating device '
+                        'batches; no explicit flush'}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+# CPU leg (oracle): used for cpu_baseline and for --impl reference
+# --------------------------------------------------------------------------------------------
+def cpu_oracle_rate(batch, steps, warmup, threads):
+    import numpy as np
+    import torch
+    from oracle import torch_ref as R
+    from dl4ds_b200 import nets
+    torch.set_num_threads(threads)
+    m = nets.net_postupsampling('resnet', 'spc', SCALE, 1, 0, (LR_HW, LR_HW))
+    w = R.init_weights(m.spec, seed=0)
+    opt = R.TFAdam(list(w), lr=1e-3)
+    fwd = lambda p, xs: R.net_postupsampling(p, xs, 'resnet', 'spc', SCALE)
+    rng = np.random.default_rng(1234)
+    hr = rng.standard_normal((batch, HR_HW, HR_HW, 1), dtype=np.float32)
+    lr = hr.reshape(batch, LR_HW, SCALE, LR_HW, SCALE, 1).mean(axis=(2, 4)).astype(np.float32)
+    hr_t, lr_t = torch.from_numpy(hr), torch.from_numpy(lr)
+    for _ in range(warmup):
+        R.supervised_step(fwd, w, opt, [lr_t], hr_t)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        R.supervised_step(fwd, w, opt, [lr_t], hr_t)
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch * HR_HW * HR_HW / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = 16
+    rate, sec = cpu_oracle_rate(sample_b, args.steps, args.warmup, threads)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': _config(args.gpus),
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': 'full training step (fwd+MAE+bwd+Adam) on a %d-sample slice of the '
+                                   'batch-64 workload per step; torch-CPU fp32 restatement of the '
+                                   'reference graph (TF/Keras not installable offline)' % sample_b},
+        'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return self
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        for _, line in rows:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU leg
+# --------------------------------------------------------------------------------------------
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dl4ds_b200 import _lib, training
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback on the product path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()
+
+    # the reference's public entry point; data_* are only used for shapes here (bench drives the
+    # step directly so that the timed region is exactly K steps)
+    rng = np.random.default_rng(1234 + rank)
+    n_pool = 4
+    hr_host = rng.standard_normal((n_pool * BATCH, HR_HW, HR_HW, 1), dtype=np.float32)
+    trainer = training.SupervisedTrainer(
+        'resnet', 'spc', hr_host, hr_host[:BATCH], hr_host[:BATCH], scale=SCALE, batch_size=BATCH,
+        loss='mae', epochs=1, learning_rate=1e-3, device='GPU', verbose=False, save=False,
+        show_plot=False, math=args.math, seed=0)
+    trainer.setup_model()
+    step = trainer.train_step          # SupervisedStep (captured CUDA graph)
+    model = trainer.model
+
+    # ---------------- device-resident pool (value) ----------------
+    hr_dev = torch.from_numpy(hr_host).to(dev)
+    from dl4ds_b200.step import coarsen_on_device
+    lr_dev = coarsen_on_device(hr_dev, SCALE)
+    pool = [(lr_dev[i * BATCH:(i + 1) * BATCH], hr_dev[i * BATCH:(i + 1) * BATCH]) for i in range(n_pool)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i):
+        lr_b, hr_b = pool[i % n_pool]
+        step.load_batch([lr_b], hr_b)      # D2D into the graph's static buffers
+        return step.run()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    time.sleep(0.25)
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = one_step(i)
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    final_loss = float(loss.item())
+
+    # ---------------- e2e through the trainer API with host batches ----------------
+    lr_host = lr_dev.cpu().numpy()
+    host_pool = [(lr_host[i * BATCH:(i + 1) * BATCH], hr_host[i * BATCH:(i + 1) * BATCH]) for i in range(n_pool)]
+    for i in range(max(3, args.warmup)):
+        trainer.train_on_batch([host_pool[i % n_pool][0]], host_pool[i % n_pool][1])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        lval = trainer.train_on_batch([host_pool[i % n_pool][0]], host_pool[i % n_pool][1])   # float (D2H)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t_wall2 = time.perf_counter()
+    if sampler is not None:
+        sampler.stop()
+
+    # ---------------- per-kernel durations (roofline) ----------------
+    timers = {}
+    n_prof = 3
+    for i in range(n_prof):
+        step.load_batch([pool[i % n_pool][0]], pool[i % n_pool][1])
+        step.run_profiled(timers)
+    torch.cuda.synchronize()
+    per_label = {k: (sum(a.elapsed_time(b) for a, b in v) / n_prof, len(v) // n_prof) for k, v in timers.items()}
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        peaks_src = 'fallback'
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peaks = json.load(f)
+            peaks_src = 'measured'
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        bf16_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
+        tf32_peak = bf16_peak / 2.0         # kind::tf32 issues at half the kind::f16 rate
+
+        px_per_step = BATCH * HR_HW * HR_HW * world
+        value = px_per_step * args.steps / (ms * 1e-3)
+        e2e = px_per_step * args.steps / (ms_e2e * 1e-3)
+
+        # dominant conv-family kernel group: label = '<layer>:<pass>@HxW'
+        macs = trainer.layer_macs(BATCH)            # {label: MACs of ONE launch}
+        top = max(per_label.items(), key=lambda kv: kv[1][0])
+        label, (ms_lab, n_launch) = top
+        flops_launch = 2.0 * macs.get(label, 0)
+        avg_ms = ms_lab / max(n_launch, 1)
+        achieved = flops_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        conv_ms = sum(v[0] for v in per_label.values())
+        step_ms = ms / args.steps
+        algo_flops_step = 2.0 * trainer.train_macs_per_sample() * BATCH
+        roofline = {
+            'bound': 'tensor', 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+            'frac': achieved / tf32_peak, 'traffic': None,
+            'kernel': label, 'avg_launch_ms': avg_ms, 'launches_per_step': n_launch,
+            'share_of_step': ms_lab / max(sum(v[0] for v in per_label.values()), 1e-9),
+            'peak_source': '%s: bf16_tflops_sustained/2 (tcgen05 kind::tf32 issue rate)' % peaks_src,
+            'math': args.math,
+            'step_conv_roofline_frac': (algo_flops_step / (step_ms * 1e-3) / 1e12) / tf32_peak,
+            'step_algorithmic_tflops': algo_flops_step / (step_ms * 1e-3) / 1e12,
+            'conv_family_ms_per_step_eager': conv_ms,
+            'hbm_peak_gbs': hbm_peak,
+        }
+
+        # bounded CPU sample: 10-30 s of host work
+        threads = os.cpu_count() or 1
+        cpu_rate, cpu_sec = cpu_oracle_rate(4, 8, 2, threads) if not args.no_cpu else (None, None)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': _config(world, {'math': args.math}),
+            'e2e': {'value': e2e, 'unit': UNIT,
+                    'h2d_bytes_per_step': int(BATCH * (LR_HW * LR_HW + HR_HW * HR_HW) * 4),
+                    'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps,
+                    'api': 'SupervisedTrainer.train_on_batch(host numpy LR, HR) -> float loss'},
+            'gpu_launches': int(step.launches_per_step * args.steps),
+            'launches_per_step': int(step.launches_per_step),
+            'roofline': roofline,
+            'cpu_baseline': None if cpu_rate is None else {
+                'value': cpu_rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                'sample': '8 timed training steps at batch 4 (configs[0]) of the torch-CPU fp32 '
+                          'restatement of the reference graph; TF/Keras not installable offline'},
+            'clocks': sampler.summary(t_wall0, t_wall2) if sampler is not None else None,
+            'final_loss': final_loss,
+            'top_kernels_ms_per_step': dict(sorted(((k, round(v[0], 4)) for k, v in per_label.items()),
+                                                   key=lambda kv: -kv[1])[:8]),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--math', default=os.environ.get('DL4DS_MATH', 'auto'),
+                    choices=['auto', 'fp32', 'tf32x3', 'tf32'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline sample')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if args.math == 'auto':
+            args.math = 'fp32'
+        run_native(args)
+
+
+if __name__ == '__main__':
+    main()

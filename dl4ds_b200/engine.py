@@ -149,11 +149,24 @@ class Ctx:
         self.names_used = []
         self.launches = 0
         self.param_grads = True     # False: backward propagates to inputs only (cGAN G-through-D pass)
+        self.timers = None          # {label: [(start_event, end_event), ...]} when profiling (bench.py)
 
     # ---------------------------------------------------------------- helpers
     def _call(self, name, *args):
         self.launches += 1
         return call(name, *args)
+
+    def _timed(self, label, name, *args):
+        """``_call`` bracketed by CUDA events on the launching stream when ``self.timers`` is set
+        (per-kernel durations for bench.py's roofline line; never active inside graph capture)."""
+        if self.timers is None:
+            return self._call(name, *args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = self._call(name, *args)
+        e1.record()
+        self.timers.setdefault(label, []).append((e0, e1))
+        return rc
 
     def input(self, tensor, requires_grad=False):
         """Wrap an NHWC fp32 CUDA tensor as a graph input."""
@@ -248,7 +261,8 @@ class Ctx:
         if res is not None:
             assert (res.N, res.H, res.W, res.C) == (x.N, Ho, Wo, cout)
         a = ACT[act]
-        self._call('dl4ds_conv2d_fwd', x.ptr, x.ld, w.data_ptr(), b.data_ptr() if bias else None,
+        self._timed('%s:fwd@%dx%d' % (name, x.H, x.W),
+                    'dl4ds_conv2d_fwd', x.ptr, x.ld, w.data_ptr(), b.data_ptr() if bias else None,
                    res.ptr if res is not None else None, res.ld if res is not None else 0,
                    out.ptr, out.ld, x.N, x.H, x.W, x.C, Ho, Wo, cout, k, k, stride, 1, pt, pl,
                    W_HWIO, a, r, 0, self.math, _stream())
@@ -271,11 +285,13 @@ class Ctx:
                            x.N, Ho, Wo, cout, a, r, _stream())
             # weight gradient (accumulating)
             if pg:
-                self._wgrad(x, dz, self._g(name + '/kernel'), k, stride, pt, pl)
+                self._wgrad(x, dz, self._g(name + '/kernel'), k, stride, pt, pl,
+                            label='%s:wgrad@%dx%d' % (name, x.H, x.W))
             # input gradient
             if x.requires_grad:
                 def wr(dst, beta):
-                    self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
+                    self._timed('%s:dgrad@%dx%d' % (name, x.H, x.W),
+                               'dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
                                dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1, stride,
                                k - 1 - pt, k - 1 - pl, W_FLIP_T, 0, 1, beta, self.math, _stream())
                 self._acc(x, wr)
@@ -285,10 +301,10 @@ class Ctx:
         self._record(bwd)
         return out
 
-    def _wgrad(self, P, Q, dw, k, stride, pt, pl):
+    def _wgrad(self, P, Q, dw, k, stride, pt, pl, label='wgrad'):
         ws_bytes = _lib.load().dl4ds_conv2d_wgrad_workspace_bytes(P.N, Q.H, Q.W, P.C, Q.C, k, k, self.math)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device) if ws_bytes > 0 else None
-        self._call('dl4ds_conv2d_wgrad', P.ptr, P.ld, Q.ptr, Q.ld, dw.data_ptr(),
+        self._timed(label, 'dl4ds_conv2d_wgrad', P.ptr, P.ld, Q.ptr, Q.ld, dw.data_ptr(),
                    P.N, P.H, P.W, P.C, Q.H, Q.W, Q.C, k, k, stride, pt, pl,
                    ws.data_ptr() if ws is not None else None, self.math, _stream())
 

@@ -62,7 +62,10 @@ class Model:
         ins = [sc.input(self._spec_shape(s)) for s in self.input_shapes]
         out = fn(sc, ins)
         self.spec = sc.spec
-        self.macs_per_sample = sc.macs
+        n0 = ins[0].N if len(self.input_shapes[0]) == 3 else 1    # traced batch (T folded into N)
+        self.macs_per_sample = sc.macs // n0 if len(self.input_shapes[0]) == 3 else sc.macs
+        self.macs_dgrad_per_sample = sc.macs_dgrad
+        self.layer_macs_per_sample = dict(sc.layer_macs)
         self.output_shape = out.shape[1:]
         self.arena = None
 
@@ -158,9 +161,10 @@ class Model:
             out.append(x.contiguous())
         return out, bsz, T
 
-    def forward(self, inputs, training=False, math=None):
+    def forward(self, inputs, training=False, math=None, timers=None):
         """Run the graph on CUDA tensors prepared by ``_prep_inputs``.  Returns (ctx, out Var)."""
         ctx = Ctx(self.arena, math or self.math, training=training)
+        ctx.timers = timers
         vs = [ctx.input(x) for x in inputs]
         out = self.fn(ctx, vs)
         return ctx, out

@@ -10,10 +10,11 @@ from .engine import same_pads
 
 
 class SVar:
-    __slots__ = ('N', 'H', 'W', 'C')
+    __slots__ = ('N', 'H', 'W', 'C', 'requires_grad')
 
-    def __init__(self, N, H, W, C):
+    def __init__(self, N, H, W, C, requires_grad=True):
         self.N, self.H, self.W, self.C = int(N), int(H), int(W), int(C)
+        self.requires_grad = requires_grad
 
     @property
     def shape(self):
@@ -24,6 +25,8 @@ class SpecCtx:
     def __init__(self):
         self.spec = OrderedDict()
         self.macs = 0            # multiply-accumulates of one forward pass (conv / dense / local)
+        self.macs_dgrad = 0      # ... of the input-gradient passes backward actually runs
+        self.layer_macs = {}     # '<layer>@HxW' -> MACs of that convolution application
         self.training = False
 
     def _reg(self, name, shape):
@@ -34,7 +37,13 @@ class SpecCtx:
             self.spec[name] = shape
 
     def input(self, shape, requires_grad=False):
-        return SVar(*shape)
+        return SVar(*shape, requires_grad=requires_grad)
+
+    def _count(self, name, x, macs):
+        self.macs += macs
+        if x.requires_grad:
+            self.macs_dgrad += macs
+        self.layer_macs['%s@%dx%d' % (name, x.H, x.W)] = macs
 
     def conv(self, x, name, cout, k=3, act=None, bias=True, stride=1, padding='same', res=None,
              d2s=1, out=None, dense=False):
@@ -46,13 +55,13 @@ class SpecCtx:
             Wo, _ = same_pads(x.W, k, stride)
         else:
             Ho, Wo = (x.H - k) // stride + 1, (x.W - k) // stride + 1
-        self.macs += x.N * Ho * Wo * k * k * x.C * cout
+        self._count(name, x, x.N * Ho * Wo * k * k * x.C * cout)
         r = d2s if d2s > 1 else 1
         return SVar(x.N, Ho * r, Wo * r, cout // (r * r))
 
     def conv_transpose(self, x, name, cout, k, stride, act=None):
         self._reg(name + '/kernel', (k, k, cout, x.C))
-        self.macs += x.N * x.H * x.W * k * k * x.C * cout
+        self._count(name, x, x.N * x.H * x.W * k * k * x.C * cout)
         return SVar(x.N, x.H * stride, x.W * stride, cout)
 
     def dense(self, x, name, cout, act=None):

@@ -70,10 +70,10 @@ class SupervisedStep:
             self.world = d.get_world_size()
 
     # the recorded work -------------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd(self, timers=None):
         self.arena.grad.zero_()
         self.loss_buf.zero_()
-        ctx, out = self.model.forward(self.inputs, training=True, math=self.math)
+        ctx, out = self.model.forward(self.inputs, training=True, math=self.math, timers=timers)
         ctx.pixel_loss(out, ctx.input(self.target), self.loss_kind, loss_buf=self.loss_buf)
         ctx.backward()
         return ctx.launches + 2     # + the two memsets
@@ -146,6 +146,15 @@ class SupervisedStep:
             self._fwd_bwd()
             self._allreduce()
             self._opt()
+        return self.loss_buf
+
+    def run_profiled(self, timers):
+        """One eager (un-graphed) optimizer step with CUDA events around every convolution-family
+        launch; ``timers`` collects {label: [(start, end)]}.  Used by bench.py's roofline line."""
+        self._set_lr_t()
+        self._fwd_bwd(timers)
+        self._allreduce()
+        self._opt()
         return self.loss_buf
 
     def broadcast_from_rank0(self):
