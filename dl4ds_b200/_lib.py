@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libdl4ds_b200.so')
 ACT = {None: 0, 'linear': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
 MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2
 MATH = {'fp32': MATH_FP32, 'tf32x3': MATH_TF32X3, 'tf32': MATH_TF32}
-W_HWIO, W_FLIP_T = 0, 1
+W_HWIO, W_FLIP_T, W_PREPACKED = 0, 1, 4
 
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _CODES = {'p': _P, 'i': _I, 'l': _L, 'f': _F}
@@ -23,7 +23,10 @@ SIGNATURES = {
     'dl4ds_last_error': ('s', ''),
     'dl4ds_version': ('i', ''),
     'dl4ds_device_is_sm100': ('i', ''),
-    'dl4ds_conv2d_fwd': ('i', 'pipppipiiiiiiiiiiiiiiiiiiip'),
+    'dl4ds_tc_launch_count': ('l', ''),
+    'dl4ds_conv2d_fwd_workspace_bytes': ('l', 'iiiiiiiiiiiii'),
+    'dl4ds_conv2d_pack': ('i', 'piiiiiipp'),
+    'dl4ds_conv2d_fwd': ('i', 'pipppipiiiiiiiiiiiiiiiiiiipp'),
     'dl4ds_conv2d_wgrad_workspace_bytes': ('l', 'iiiiiiii'),
     'dl4ds_conv2d_wgrad': ('i', 'pipipiiiiiiiiiiiipip'),
     'dl4ds_bias_act_bwd': ('i', 'pipipipiiiiiip'),

@@ -34,6 +34,8 @@ extern "C" {
 const char* dl4ds_last_error(void) { return g_err; }
 int dl4ds_version(void) { return 100; }
 
+int64_t dl4ds_tc_launch_count(void) { return g_tc_launches.load(); }
+
 int dl4ds_device_is_sm100(void) {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -45,8 +47,10 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
                      const float* res, int res_ld, float* y, int y_ld,
                      int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
                      int KH, int KW, int stride, int up, int pad_t, int pad_l,
-                     int wmode, int act, int d2s_r, int beta, int math_mode, void* stream) {
+                     int wmode, int act, int d2s_r, int beta, int math_mode, void* ws, void* stream) {
     DL4DS_REQUIRE(x && w && y, DL4DS_E_BADARG, "conv2d_fwd: null pointer");
+    const int prepacked = (wmode & DL4DS_W_PREPACKED) ? 1 : 0;
+    wmode &= ~DL4DS_W_PREPACKED;
     DL4DS_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Ho > 0 && Wo > 0 && Cout > 0,
                   DL4DS_E_SHAPE, "conv2d_fwd: non-positive dimension");
     DL4DS_REQUIRE(KH > 0 && KW > 0 && stride > 0 && up > 0, DL4DS_E_SHAPE, "conv2d_fwd: bad kernel/stride");
@@ -74,10 +78,29 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
     a.vec = (Cin % 4 == 0) && (x_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (math_mode != DL4DS_MATH_FP32) {
-        int rc = conv2d_fwd_tc(a, math_mode, st);
+        int rc = conv2d_fwd_tc(a, math_mode, ws, prepacked, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
     }
     return conv2d_fwd_simt(a, st);
+}
+
+int64_t dl4ds_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
+                                         int KH, int KW, int stride, int up, int d2s_r, int math_mode) {
+    if (math_mode == DL4DS_MATH_FP32) return 0;
+    ConvArgs a = {};
+    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Ho = Ho; a.Wo = Wo; a.Cout = Cout;
+    a.KH = KH; a.KW = KW; a.stride = stride; a.up = up; a.d2s_r = d2s_r > 1 ? d2s_r : 1;
+    return conv2d_fwd_tc_workspace(a, math_mode);
+}
+
+int dl4ds_conv2d_pack(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode,
+                      void* ws, void* stream) {
+    DL4DS_REQUIRE(w && ws, DL4DS_E_BADARG, "conv2d_pack: null pointer");
+    DL4DS_REQUIRE(math_mode == DL4DS_MATH_TF32 || math_mode == DL4DS_MATH_TF32X3, DL4DS_E_BADARG,
+                  "conv2d_pack: math_mode must be a tensor-core mode");
+    DL4DS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, DL4DS_E_SHAPE, "conv2d_pack: channels must be multiples of 8");
+    return conv2d_pack_tc(w, wmode & ~DL4DS_W_PREPACKED, KH, KW, Cin, Cout, math_mode, ws,
+                          reinterpret_cast<cudaStream_t>(stream));
 }
 
 int64_t dl4ds_conv2d_wgrad_workspace_bytes(int N, int Hq, int Wq, int Ca, int Cb, int KH, int KW,

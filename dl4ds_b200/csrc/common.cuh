@@ -43,9 +43,17 @@ struct WgradArgs {
 int conv2d_fwd_simt(const ConvArgs& a, cudaStream_t st);
 int conv2d_wgrad_simt(const WgradArgs& a, cudaStream_t st);
 // conv_tc.cu: DL4DS_E_UNSUPPORTED when the shape is outside the tensor-core kernels' domain
-int conv2d_fwd_tc(const ConvArgs& a, int math_mode, cudaStream_t st);
+int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cudaStream_t st);
+int64_t conv2d_fwd_tc_workspace(const ConvArgs& a, int math_mode);
+int conv2d_pack_tc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws,
+                   cudaStream_t st);
 int conv2d_wgrad_tc(const WgradArgs& a, void* ws, int math_mode, cudaStream_t st);
 int64_t conv2d_wgrad_tc_workspace(int N, int Hq, int Wq, int Ca, int Cb, int KH, int KW);
+
+}  // namespace dl4ds
+#include <atomic>
+namespace dl4ds {
+extern std::atomic<long long> g_tc_launches;   // tensor-core kernel launches issued by this process
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -1,11 +1,769 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM convolution kernels -- placeholder dispatch until the
-// kernels land: every shape reports DL4DS_E_UNSUPPORTED so api.cu routes to the CUDA-core fp32 path.
-#include "common.cuh"
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution kernels for sm_100a.
+//
+// Forward / input-gradient (stride-1 'same'-grid convolutions -- blocks.py:49-61,208,299,414-416;
+// sp_postups.py:134,156 -- and their dgrads, which are the same op with flipped/transposed weights):
+//   GEMM M = 128 output pixels (a BH x BW patch of one image), N = Cout (padded to 16), K = taps x Cin.
+//   A (activations): one TMA 4-D box {KC ch, BW, BH, 1} per (tap, channel chunk), shifted by the
+//     tap offset, out-of-bounds rows/cols/channels zero-filled by TMA = the convolution's zero padding;
+//     lands K-major in the hardware 32/64/128-byte swizzle.
+//   B (weights): pre-packed once per optimizer step by pack_weights_kernel into the exact swizzled
+//     shared-memory image ([tap][chunk][Npad][KC]), fetched with one cp.async.bulk per stage.
+//   D: fp32 accumulator in TMEM (Npad columns x 128 lanes), tcgen05.mma kind::tf32 issued by one thread.
+//   Epilogue (4 warps): tcgen05.ld -> +bias (+residual) -> activation -> vectorised NHWC store, or the
+//     depth_to_space (tf.nn.depth_to_space, DCR order, blocks.py:427) permuted store.
+// Math modes: DL4DS_MATH_TF32 feeds raw fp32 (the tensor core reads the top 19 bits);
+// DL4DS_MATH_TF32X3 splits both operands into tf32 hi + lo and issues hi*lo + lo*hi + hi*hi
+// (fp32 accumulate) -- error ~2^-21 per product, i.e. fp32-level parity.  The activation split runs
+// in-kernel on the (otherwise idle) epilogue warps; the weight split is done by the pack kernel.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = operand splitter (x3 mode) during the main loop, then epilogue.
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "tc_common.cuh"
 
 namespace dl4ds {
 
-int conv2d_fwd_tc(const ConvArgs&, int, cudaStream_t) { return DL4DS_E_UNSUPPORTED; }
-int conv2d_wgrad_tc(const WgradArgs&, void*, int, cudaStream_t) { return DL4DS_E_UNSUPPORTED; }
+using namespace tc;
+
+// -------------------------------------------------------------------------------------------------
+// host: tensor-map cache
+// -------------------------------------------------------------------------------------------------
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+const CUtensorMap* get_tensor_map_nhwc(const float* base, int ld, int N, int H, int W, int C,
+                                       int box_c, int box_w, int box_h, int swizzle) {
+    typedef std::tuple<const void*, int, int, int, int, int, int, int, int, int> Key;
+    static std::map<Key, CUtensorMap*> cache;
+    static std::mutex mu;
+    Key key(base, ld, N, H, W, C, box_c, box_w, box_h, swizzle);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return nullptr;
+    }
+    CUtensorMap* m = new CUtensorMap;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for C=%d W=%d H=%d N=%d ld=%d box=%d,%d,%d", (int)r, C, W, H, N,
+                  ld, box_c, box_w, box_h);
+        delete m;
+        return nullptr;
+    }
+    if (cache.size() > 4096) {          // unbounded growth guard (addresses are stable under CUDA graphs)
+        for (auto& kv : cache) delete kv.second;
+        cache.clear();
+    }
+    cache[key] = m;
+    return m;
+}
+
+}  // namespace tc
+
+// -------------------------------------------------------------------------------------------------
+// weight packing: Keras-layout weights -> [tap][chunk][Npad][KC] swizzled smem images (hi and lo)
+// -------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                    int taps, int Cin, int Cout, int Npad, int kc, int nchunks, int wmode,
+                                    int x3) {
+    const int upr = kc / 4;                                  // 16-byte units per row
+    const int64_t total = (int64_t)taps * nchunks * Npad * upr;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int u = (int)(idx % upr);
+        const int n = (int)((idx / upr) % Npad);
+        const int blk = (int)(idx / ((int64_t)upr * Npad));
+        const int tap = blk / nchunks, ch = blk - tap * nchunks;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = ch * kc + u * 4 + j;
+            float x = 0.0f;
+            if (n < Cout && c < Cin) {
+                if (wmode == DL4DS_W_HWIO)
+                    x = __ldg(w + ((int64_t)tap * Cin + c) * Cout + n);
+                else
+                    x = __ldg(w + ((int64_t)(taps - 1 - tap) * Cout + n) * Cin + c);
+            }
+            v[j] = x;
+        }
+        const int us = swizzle_unit(u, n, kc * 4);
+        const int64_t dst = ((int64_t)blk * Npad + n) * kc + us * 4;
+        if (x3) {
+            float h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[j] = tf32_rna(v[j]);
+                l[j] = tf32_rna(v[j] - h[j]);
+            }
+            *reinterpret_cast<float4*>(hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+            *reinterpret_cast<float4*>(hi + dst) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// -------------------------------------------------------------------------------------------------
+struct TcFwdParams {
+    const float* wp_hi;
+    const float* wp_lo;
+    const float* bias;
+    const float* res;
+    float* y;
+    int res_ld, y_ld;
+    int H, W, Cin, Cout, Npad;
+    int KW, ntaps, pad_t, pad_l;
+    int BW, BH, tiles_x, tiles_per_img;
+    int kc, span, nchunks;
+    uint32_t layout;
+    int act, d2s_r, beta;
+    int stages, stage_bytes, a_bytes, b_bytes, tmem_cols;
+};
+
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+
+template <bool X3>
+__global__ void __launch_bounds__(kTcThreads) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                const TcFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_conv[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_accum;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+    // tile coordinates
+    const int tile = blockIdx.x;
+    const int img = tile / p.tiles_per_img;
+    const int trem = tile - img * p.tiles_per_img;
+    const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+    const int y0 = ty * p.BH, x0 = tx * p.BW;
+    const int nit = p.ntaps * p.nchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_conv[s]), 128);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_accum), 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(p.a_bytes + p.b_bytes * (X3 ? 2 : 1));
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_arrive_expect_tx(full, tx_bytes);
+                const int tap = it / p.nchunks, ch = it - tap * p.nchunks;
+                const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                tma_load_4d(sa, &tmap_x, full, ch * p.kc, x0 + kw - p.pad_l, y0 + kh - p.pad_t, img);
+                const uint32_t sb = sa + (uint32_t)p.a_bytes * (X3 ? 2u : 1u);
+                const size_t woff = (size_t)it * p.Npad * p.kc;
+                bulk_load(sb, p.wp_hi + woff, (uint32_t)p.b_bytes, full);
+                if (X3) bulk_load(sb + (uint32_t)p.b_bytes, p.wp_lo + woff, (uint32_t)p.b_bytes, full);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, p.Npad, 0, 0);
+            const uint32_t sbo = 8u * (uint32_t)p.span;
+            uint32_t accumulate = 0;
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+                mbar_wait(smem_u32(X3 ? &bar_conv[s] : &bar_full[s]), ph);
+                tc_fence_after();
+                const int ch = it % p.nchunks;
+                int ksteps = (p.Cin - ch * p.kc);
+                ksteps = (ksteps > p.kc ? p.kc : ksteps) >> 3;
+                const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                const uint32_t sb = sa + (uint32_t)p.a_bytes * (X3 ? 2u : 1u);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t ko = (uint32_t)k * 32u;
+                    const uint64_t da = make_smem_desc(sa + ko, 16, sbo, p.layout);
+                    const uint64_t db = make_smem_desc(sb + ko, 16, sbo, p.layout);
+                    if (X3) {
+                        const uint64_t dal = make_smem_desc(sa + (uint32_t)p.a_bytes + ko, 16, sbo, p.layout);
+                        const uint64_t dbl = make_smem_desc(sb + (uint32_t)p.b_bytes + ko, 16, sbo, p.layout);
+                        umma_tf32(tmem_d, dal, db, idesc, accumulate);
+                        umma_tf32(tmem_d, da, dbl, idesc, 1u);
+                        umma_tf32(tmem_d, da, db, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_d, da, db, idesc, accumulate);
+                    }
+                    accumulate = 1u;
+                }
+                umma_commit(smem_u32(&bar_empty[s]));
+            }
+            umma_commit(smem_u32(&bar_accum));
+        }
+    } else {
+        // ===================== operand splitter (x3) + epilogue =====================
+        const int et = threadIdx.x - 64;           // 0..127
+        if (X3) {
+            const int units = p.kc / 4;            // float4 per thread per stage (A tile = 128 rows x span)
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                uint8_t* a_hi = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)s * p.stage_bytes;
+                uint8_t* a_lo = a_hi + p.a_bytes;
+                for (int u = 0; u < units; ++u) {
+                    const int off = (et + u * 128) * 16;
+                    const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+                    float4 h, l;
+                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    *reinterpret_cast<float4*>(a_hi + off) = h;
+                    *reinterpret_cast<float4*>(a_lo + off) = l;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(smem_u32(&bar_conv[s]));
+            }
+        }
+        mbar_wait(smem_u32(&bar_accum), 0);
+        tc_fence_after();
+
+        const int q = warp & 3;                     // TMEM lane quadrant this warp may read
+        const int row = q * 32 + lane;
+        const int ry = row / p.BW, rx = row - ry * p.BW;
+        const int oy = y0 + ry, ox = x0 + rx;
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+        const int r = p.d2s_r;
+        const int64_t pix = ((int64_t)img * p.H + oy) * p.W + ox;
+        const float* resp = p.res ? p.res + pix * p.res_ld : nullptr;
+        float* yp = p.y + pix * p.y_ld;
+        const int Cd = p.Cout / (r * r);
+        for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const int co = c0 + j;
+                if (co >= p.Cout) continue;
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                if (resp) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(resp + co));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
+                o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
+                if (r == 1) {
+                    float4* dst = reinterpret_cast<float4*>(yp + co);
+                    if (p.beta) {
+                        const float4 old = *dst;
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    *dst = o;
+                } else {
+                    const int g = co / Cd, c = co - g * Cd;
+                    const int di = g / r, dj = g - di * r;
+                    const int64_t hp = ((int64_t)img * p.H * r + (oy * r + di)) * ((int64_t)p.W * r) + ox * r + dj;
+                    *reinterpret_cast<float4*>(p.y + hp * p.y_ld + c) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host dispatch
+// -------------------------------------------------------------------------------------------------
+std::atomic<long long> g_tc_launches{0};
+
+static bool is_sm100() {
+    static int v = -1;
+    if (v < 0) v = dl4ds_device_is_sm100();
+    return v == 1;
+}
+
+static bool tile_geometry(int H, int W, int tile_pix, int* BW, int* BH) {
+    int bw;
+    if (W >= tile_pix) {
+        if (W % tile_pix) return false;
+        bw = tile_pix;
+    } else {
+        if (W < 8 || tile_pix % W) return false;
+        bw = W;
+    }
+    const int bh = tile_pix / bw;
+    if (bh > 256 || H % bh) return false;
+    *BW = bw;
+    *BH = bh;
+    return true;
+}
+
+// shape-only part of the eligibility test (what the workspace query can see)
+static bool fwd_shape_supported(const ConvArgs& a, int math_mode) {
+    if (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3) return false;
+    if (!is_sm100()) return false;
+    if (a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W) return false;
+    if (a.Cin % 8 || a.Cout % 8 || a.Cout > 256) return false;
+    if (a.d2s_r != 1 && (a.d2s_r != 2 || (a.Cout / 4) % 4)) return false;
+    if (a.KH * a.KW > 81) return false;
+    int bw, bh;
+    return tile_geometry(a.H, a.W, 128, &bw, &bh);
+}
+
+static bool fwd_supported(const ConvArgs& a, int math_mode) {
+    if (!fwd_shape_supported(a, math_mode)) return false;
+    if (a.x_ld % 4 || (reinterpret_cast<uintptr_t>(a.x) & 15)) return false;
+    if (a.y_ld % 4 || (reinterpret_cast<uintptr_t>(a.y) & 15)) return false;
+    if (a.res && (a.res_ld % 4 || (reinterpret_cast<uintptr_t>(a.res) & 15))) return false;
+    if (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)) return false;
+    return true;
+}
+
+static int64_t pack_floats(int taps, int Cin, int Cout) {
+    const Chunk c = pick_chunk(Cin);
+    const int nchunks = (Cin + c.kc - 1) / c.kc;
+    const int npad = (Cout + 15) / 16 * 16;
+    return (int64_t)taps * nchunks * npad * c.kc;
+}
+
+int64_t conv2d_fwd_tc_workspace(const ConvArgs& a, int math_mode) {
+    if (!fwd_shape_supported(a, math_mode)) return 0;
+    const int64_t n = pack_floats(a.KH * a.KW, a.Cin, a.Cout);
+    return n * 4 * (math_mode == DL4DS_MATH_TF32X3 ? 2 : 1);
+}
+
+int conv2d_pack_tc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws,
+                   cudaStream_t st) {
+    const Chunk c = pick_chunk(Cin);
+    const int nchunks = (Cin + c.kc - 1) / c.kc;
+    const int npad = (Cout + 15) / 16 * 16;
+    const int64_t n = pack_floats(KH * KW, Cin, Cout);
+    float* hi = reinterpret_cast<float*>(ws);
+    float* lo = hi + n;
+    const int64_t units = n / 4;
+    const int blocks = (int)((units + 255) / 256 > 1184 ? 1184 : (units + 255) / 256);
+    pack_weights_kernel<<<blocks, 256, 0, st>>>(w, hi, lo, KH * KW, Cin, Cout, npad, c.kc, nchunks, wmode,
+                                                math_mode == DL4DS_MATH_TF32X3 ? 1 : 0);
+    return check_launch("pack_weights_kernel");
+}
+
+int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cudaStream_t st) {
+    if (!fwd_supported(a, math_mode)) return DL4DS_E_UNSUPPORTED;
+    DL4DS_REQUIRE(ws != nullptr, DL4DS_E_BADARG,
+                  "conv2d_fwd: tensor-core math needs the packed-weight workspace "
+                  "(dl4ds_conv2d_fwd_workspace_bytes)");
+    DL4DS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 127) == 0, DL4DS_E_BADARG, "conv2d_fwd: ws must be 128-byte aligned");
+    const bool x3 = math_mode == DL4DS_MATH_TF32X3;
+    if (!prepacked) {
+        int rc = conv2d_pack_tc(a.w, a.wmode, a.KH, a.KW, a.Cin, a.Cout, math_mode, ws, st);
+        if (rc) return rc;
+    }
+    const Chunk c = pick_chunk(a.Cin);
+    TcFwdParams p;
+    p.Npad = (a.Cout + 15) / 16 * 16;
+    p.nchunks = (a.Cin + c.kc - 1) / c.kc;
+    const int64_t n = pack_floats(a.KH * a.KW, a.Cin, a.Cout);
+    p.wp_hi = reinterpret_cast<const float*>(ws);
+    p.wp_lo = p.wp_hi + n;
+    p.bias = a.bias; p.res = a.res; p.y = a.y; p.res_ld = a.res_ld; p.y_ld = a.y_ld;
+    p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout;
+    p.KW = a.KW; p.ntaps = a.KH * a.KW; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
+    tile_geometry(a.H, a.W, 128, &p.BW, &p.BH);
+    p.tiles_x = a.W / p.BW;
+    p.tiles_per_img = p.tiles_x * (a.H / p.BH);
+    p.kc = c.kc; p.span = c.span; p.layout = c.layout;
+    p.act = a.act; p.d2s_r = a.d2s_r; p.beta = a.beta;
+    p.a_bytes = 128 * c.span;
+    p.b_bytes = p.Npad * c.span;
+    p.stage_bytes = (p.a_bytes + p.b_bytes) * (x3 ? 2 : 1);
+    int stages = (100 * 1024) / p.stage_bytes;             // <= ~100 KB so that two CTAs share an SM
+    if (stages < 2) stages = 2;
+    if (stages > kMaxStages) stages = kMaxStages;
+    const int nit = p.ntaps * p.nchunks;
+    if (stages > nit) stages = nit;
+    p.stages = stages;
+    int cols = 32;
+    while (cols < p.Npad) cols *= 2;
+    p.tmem_cols = cols;
+    const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+    DL4DS_REQUIRE(smem <= 220 * 1024, DL4DS_E_UNSUPPORTED, "conv2d_fwd_tc: stage too large");
+    const CUtensorMap* tm = get_tensor_map_nhwc(a.x, a.x_ld, a.N, a.H, a.W, a.Cin, c.kc, p.BW, p.BH, c.swz);
+    if (!tm) return DL4DS_E_CUDA;
+    const int grid = a.N * p.tiles_per_img;
+    static size_t attr_set[2] = {0, 0};
+    if (x3) {
+        if (smem > attr_set[1]) {
+            cudaFuncSetAttribute(conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+            attr_set[1] = 221 * 1024;
+        }
+        conv_tc_fwd_kernel<true><<<grid, kTcThreads, smem, st>>>(*tm, p);
+    } else {
+        if (smem > attr_set[0]) {
+            cudaFuncSetAttribute(conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+            attr_set[0] = 221 * 1024;
+        }
+        conv_tc_fwd_kernel<false><<<grid, kTcThreads, smem, st>>>(*tm, p);
+    }
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch("conv_tc_fwd_kernel");
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight-gradient kernel:  dw[kh][kw][ca][cb] += sum_{n,y,x} P[n, y+kh-pad_t, x+kw-pad_l, ca] * Q[n,y,x,cb]
+//
+// Per kernel tap a GEMM whose reduction dimension is the PIXELS: D (Ca x Cb) += P_tap^T (Ca x pix) *
+// Q (pix x Cb).  kind::tf32 only accepts K-major operands (measured: the MN-major bits of the
+// instruction descriptor yield zeros for tf32), i.e. rows = channels, 32 consecutive pixels per
+// 128-byte row -- the transpose of what NHWC delivers.  So each stage is:
+//   TMA: NHWC boxes {KC ch, BW, BH, 1} of 32 pixels (P shifted by the tap, Q unshifted) -> raw region
+//   4 transposer warps: swizzle-aware conflict-free LDS.128 of (pixel, 4 channels), tf32 hi/lo split
+//     in registers (x3 mode), STS.32 into the channel-major SWIZZLE_128B operand tiles
+//   1 thread: tcgen05.mma M=64 (<= 64 input channels; rows past Ca hold stale data whose D rows are
+//     never read), N = block of <= 128 output channels, 4 K-steps of 8 pixels per stage and tap.
+// CTA role (blockIdx.y) = (kernel row kh, Ca group, Cb block): it owns the KW accumulators of that
+// kernel row in TMEM (KW x Nmma columns) so one Q tile feeds KW taps.  blockIdx.x splits the pixel
+// tiles (split-K); partial sums are merged with fp32 atomics.
+// -------------------------------------------------------------------------------------------------
+constexpr int kWgKT = 32;             // pixels per stage = one 128-byte K-major row
+
+struct TcWgradParams {
+    float* dw;
+    int H, W, Ca, Cb;
+    int KH, KW, pad_t, pad_l;
+    int BW, BH, tiles_x, tiles_per_img, ntiles, tiles_per_split;
+    int kc_p, span_p, kc_q, span_q;
+    int ncig, ncob, Nb;
+    int nblk_p_max, nblk_q_max;       // raw boxes per tap (P) / per tile (Q) the smem layout is sized for
+    int box_p, box_q;                 // bytes per raw TMA box (32 pixels x span)
+    int raw_bytes;                    // raw region per stage
+    int pt_bytes, qt_bytes;           // transposed operand tiles: P^T per tap (64 rows x 128 B), Q^T (Nmma rows x 128 B)
+    int op_bytes;                     // KW*pt_bytes + qt_bytes: one (hi) operand set
+    int stage_bytes, stages, tmem_cols;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p,
+                                                                  const __grid_constant__ CUtensorMap tmap_q,
+                                                                  const TcWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_conv[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_accum;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    // role
+    const int role = blockIdx.y;
+    const int cob = role % p.ncob;
+    const int cig = (role / p.ncob) % p.ncig;
+    const int kh = role / (p.ncob * p.ncig);
+    const int ca0 = cig * 64;
+    const int ca_n = min(64, p.Ca - ca0);
+    const int nblk_p = ca_n / p.kc_p;
+    const int cb0 = cob * p.Nb;
+    const int cb_n = min(p.Nb, p.Cb - cb0);
+    const int nblk_q = cb_n / p.kc_q;
+    const int Nmma = (cb_n + 15) & ~15;
+    // pixel-tile range of this split
+    const int t_begin = blockIdx.x * p.tiles_per_split;
+    const int t_end = min(p.ntiles, t_begin + p.tiles_per_split);
+    const int my_tiles = t_end - t_begin;
+    if (my_tiles <= 0) return;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_conv[s]), 128);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_accum), 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_p);
+        tma_prefetch_desc(&tmap_q);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+    const uint32_t rawq_off = (uint32_t)(p.KW * p.nblk_p_max * p.box_p);     // Q boxes inside the raw region
+    const uint32_t op_off = (uint32_t)p.raw_bytes;                          // operand tiles follow the raw region
+    const uint32_t qt_off = (uint32_t)(p.KW * p.pt_bytes);                  // Q^T inside an operand set
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(p.KW * nblk_p * p.box_p + nblk_q * p.box_q);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_arrive_expect_tx(full, tx_bytes);
+                const int tile = t_begin + it;
+                const int img = tile / p.tiles_per_img;
+                const int trem = tile - img * p.tiles_per_img;
+                const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+                const int y0 = ty * p.BH, x0 = tx * p.BW;
+                const uint32_t sp = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                for (int kw = 0; kw < p.KW; ++kw)
+                    for (int b = 0; b < nblk_p; ++b)
+                        tma_load_4d(sp + (uint32_t)((kw * p.nblk_p_max + b) * p.box_p), &tmap_p, full,
+                                    ca0 + b * p.kc_p, x0 + kw - p.pad_l, y0 + kh - p.pad_t, img);
+                for (int b = 0; b < nblk_q; ++b)
+                    tma_load_4d(sp + rawq_off + (uint32_t)(b * p.box_q), &tmap_q, full, cb0 + b * p.kc_q, x0, y0, img);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(64, Nmma, 0, 0);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+                mbar_wait(smem_u32(&bar_conv[s]), ph);
+                tc_fence_after();
+                const uint32_t so = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes + op_off;
+                for (int kw = 0; kw < p.KW; ++kw) {
+                    const uint32_t pa = so + (uint32_t)(kw * p.pt_bytes);
+                    const uint32_t qb = so + qt_off;
+                    const uint32_t td = tmem_d + (uint32_t)(kw * Nmma);
+#pragma unroll
+                    for (int k = 0; k < kWgKT / 8; ++k) {
+                        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+                        const uint32_t ko = (uint32_t)k * 32u;
+                        const uint64_t da = make_smem_desc(pa + ko, 16, 1024, kLayoutSw128);
+                        const uint64_t db = make_smem_desc(qb + ko, 16, 1024, kLayoutSw128);
+                        if (X3) {
+                            const uint32_t h = (uint32_t)p.op_bytes;
+                            const uint64_t dal = make_smem_desc(pa + h + ko, 16, 1024, kLayoutSw128);
+                            const uint64_t dbl = make_smem_desc(qb + h + ko, 16, 1024, kLayoutSw128);
+                            umma_tf32(td, dal, db, idesc, acc);
+                            umma_tf32(td, da, dbl, idesc, 1u);
+                            umma_tf32(td, da, db, idesc, 1u);
+                        } else {
+                            umma_tf32(td, da, db, idesc, acc);
+                        }
+                    }
+                }
+                umma_commit(smem_u32(&bar_empty[s]));
+            }
+            umma_commit(smem_u32(&bar_accum));
+        }
+    } else {
+        // ===================== transposer (+ tf32 split) and epilogue =====================
+        const int ew = warp - 2;                       // 0..3
+        const int gp = p.kc_p / 4, gq = p.kc_q / 4;     // float4 groups per raw row
+        const int items_p = p.KW * nblk_p * gp;         // (tap, block, group) triples of P
+        const int items = items_p + nblk_q * gq;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+            mbar_wait(smem_u32(&bar_full[s]), ph);
+            uint8_t* raw = smem_al + (size_t)s * p.stage_bytes;
+            uint8_t* ops = raw + p.raw_bytes;
+            for (int i = ew; i < items; i += 4) {
+                const uint8_t* src;
+                uint8_t* dst;
+                int ch;                                 // first of the 4 channel rows this item writes
+                if (i < items_p) {
+                    const int g = i % gp, tb = i / gp;              // tb = tap * nblk_p + block
+                    const int kw = tb / nblk_p, b = tb - kw * nblk_p;
+                    src = raw + (size_t)(kw * p.nblk_p_max + b) * p.box_p + lane * p.span_p +
+                          (swizzle_unit(g, lane, p.span_p) << 4);
+                    ch = b * p.kc_p + g * 4;
+                    dst = ops + (size_t)kw * p.pt_bytes;
+                } else {
+                    const int j = i - items_p;
+                    const int g = j % gq, b = j / gq;
+                    src = raw + rawq_off + (size_t)b * p.box_q + lane * p.span_q + (swizzle_unit(g, lane, p.span_q) << 4);
+                    ch = b * p.kc_q + g * 4;
+                    dst = ops + qt_off;
+                }
+                const float4 v = *reinterpret_cast<const float4*>(src);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = ch + j;
+                    const int off = row * 128 + ((((lane >> 2) ^ (row & 7)) << 4) | ((lane & 3) << 2));
+                    if (X3) {
+                        const float h = tf32_rna(vv[j]);
+                        *reinterpret_cast<float*>(dst + off) = h;
+                        *reinterpret_cast<float*>(dst + p.op_bytes + off) = tf32_rna(vv[j] - h);
+                    } else {
+                        *reinterpret_cast<float*>(dst + off) = vv[j];
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(smem_u32(&bar_conv[s]));
+        }
+        mbar_wait(smem_u32(&bar_accum), 0);
+        tc_fence_after();
+        // M = 64 accumulator layout: row r lives in TMEM lane 32*(r/16) + r%16
+        const int q = warp & 3;
+        const int ci = ca0 + q * 16 + lane;                 // valid for lane < 16
+        const bool row_ok = lane < 16 && (q * 16 + lane) < ca_n;
+        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+        for (int kw = 0; kw < p.KW; ++kw) {
+            float* dst_row = p.dw + ((int64_t)((kh * p.KW + kw) * p.Ca + ci)) * p.Cb + cb0;
+            for (int c0 = 0; c0 < Nmma; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)(kw * Nmma + c0), v);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < cb_n) atomicAdd(dst_row + c0 + j, v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+}
+
+static bool wgrad_supported(const WgradArgs& a, int math_mode, int* BW, int* BH) {
+    if (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3) return false;
+    if (!is_sm100()) return false;
+    if (a.stride != 1 || a.Hp != a.Hq || a.Wp != a.Wq) return false;
+    if (a.Ca % 8 || a.Cb % 8) return false;
+    if (a.p_ld % 4 || a.q_ld % 4) return false;
+    if ((reinterpret_cast<uintptr_t>(a.P) & 15) || (reinterpret_cast<uintptr_t>(a.Q) & 15)) return false;
+    if (a.KW > 5 || a.KH > 9) return false;
+    return tile_geometry(a.Hq, a.Wq, kWgKT, BW, BH);
+}
+
 int64_t conv2d_wgrad_tc_workspace(int, int, int, int, int, int, int) { return 0; }
+
+int conv2d_wgrad_tc(const WgradArgs& a, void*, int math_mode, cudaStream_t st) {
+    int BW, BH;
+    if (!wgrad_supported(a, math_mode, &BW, &BH)) return DL4DS_E_UNSUPPORTED;
+    const bool x3 = math_mode == DL4DS_MATH_TF32X3;
+    const Chunk cp = pick_chunk(a.Ca), cq = pick_chunk(a.Cb);
+    TcWgradParams p;
+    p.dw = a.dw;
+    p.H = a.Hq; p.W = a.Wq; p.Ca = a.Ca; p.Cb = a.Cb;
+    p.KH = a.KH; p.KW = a.KW; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
+    p.BW = BW; p.BH = BH;
+    p.tiles_x = a.Wq / BW;
+    p.tiles_per_img = p.tiles_x * (a.Hq / BH);
+    p.ntiles = a.N * p.tiles_per_img;
+    p.kc_p = cp.kc; p.span_p = cp.span;
+    p.kc_q = cq.kc; p.span_q = cq.span;
+    p.ncig = (a.Ca + 63) / 64;
+    // output-channel block: <= 128 (<= 96 for KW = 5 so that KW*Nmma <= 512 TMEM columns), a multiple of
+    // lcm(16, kc_q), balanced over the blocks
+    const int nb_cap = a.KW > 3 ? 96 : 128;
+    const int unit = cq.kc > 16 ? cq.kc : 16;
+    int ncob = (a.Cb + nb_cap - 1) / nb_cap;
+    int nb = ((a.Cb + ncob - 1) / ncob + unit - 1) / unit * unit;
+    if (nb > nb_cap) { nb = nb_cap / unit * unit; ncob = (a.Cb + nb - 1) / nb; }
+    p.Nb = nb; p.ncob = ncob;
+    const int ca_first = a.Ca < 64 ? a.Ca : 64;
+    p.nblk_p_max = ca_first / cp.kc;
+    const int cb_first = a.Cb < nb ? a.Cb : nb;
+    p.nblk_q_max = cb_first / cq.kc;
+    p.box_p = kWgKT * cp.span;
+    p.box_q = kWgKT * cq.span;
+    p.raw_bytes = a.KW * p.nblk_p_max * p.box_p + p.nblk_q_max * p.box_q;       // multiples of 1024
+    const int nmma_max = (cb_first + 15) & ~15;
+    p.pt_bytes = 64 * 128;
+    p.qt_bytes = ((nmma_max * 128) + 1023) & ~1023;
+    p.op_bytes = a.KW * p.pt_bytes + p.qt_bytes;
+    p.stage_bytes = p.raw_bytes + p.op_bytes * (x3 ? 2 : 1);
+    int stages = (218 * 1024) / p.stage_bytes;
+    if (stages < 1) return DL4DS_E_UNSUPPORTED;
+    if (stages > kMaxStages) stages = kMaxStages;
+    int cols = 32;
+    while (cols < a.KW * nmma_max) cols *= 2;
+    if (cols > 512) return DL4DS_E_UNSUPPORTED;
+    p.tmem_cols = cols;
+    const int nroles = a.KH * p.ncig * p.ncob;
+    int splits = kNumSMs / nroles;
+    if (cols <= 256 && 3 * p.stage_bytes <= 100 * 1024) {  // two CTAs per SM hide each other's epilogue
+        splits = (2 * kNumSMs) / nroles;
+        if (stages > 3) stages = 3;
+    }
+    if (splits < 1) splits = 1;
+    if (splits > p.ntiles) splits = p.ntiles;
+    p.tiles_per_split = (p.ntiles + splits - 1) / splits;
+    splits = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    if (stages > p.tiles_per_split) stages = p.tiles_per_split;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+    const CUtensorMap* tp = get_tensor_map_nhwc(a.P, a.p_ld, a.N, a.Hp, a.Wp, a.Ca, cp.kc, BW, BH, cp.swz);
+    const CUtensorMap* tq = get_tensor_map_nhwc(a.Q, a.q_ld, a.N, a.Hq, a.Wq, a.Cb, cq.kc, BW, BH, cq.swz);
+    if (!tp || !tq) return DL4DS_E_CUDA;
+    dim3 grid((unsigned)splits, (unsigned)nroles);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv_tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        cudaFuncSetAttribute(conv_tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        attr_done = true;
+    }
+    if (x3)
+        conv_tc_wgrad_kernel<true><<<grid, kTcThreads, smem, st>>>(*tp, *tq, p);
+    else
+        conv_tc_wgrad_kernel<false><<<grid, kTcThreads, smem, st>>>(*tp, *tq, p);
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch("conv_tc_wgrad_kernel");
+}
 
 }  // namespace dl4ds

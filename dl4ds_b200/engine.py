@@ -173,6 +173,23 @@ class Ctx:
         assert tensor.is_cuda and tensor.dtype == torch.float32 and tensor.dim() == 4
         return Var(tensor.contiguous(), requires_grad=requires_grad)
 
+    def _conv_ws(self, N, H, W, Cin, Ho, Wo, Cout, k, stride, up, r):
+        """Packed-weight workspace for the tensor-core convolution path (None when not needed)."""
+        if self.math == 0:
+            return None
+        nb = _lib.load().dl4ds_conv2d_fwd_workspace_bytes(N, H, W, Cin, Ho, Wo, Cout, k, k, stride, up, r, self.math)
+        if nb <= 0:
+            return None
+        return torch.empty(nb, dtype=torch.uint8, device=self.device)
+
+    def _conv_raw(self, xptr, xld, wptr, bptr, resptr, resld, yptr, yld, N, H, W, Cin, Ho, Wo, Cout,
+                  k, stride, up, pt, pl, wmode, act, r, beta):
+        """dl4ds_conv2d_fwd on raw pointers (ConvLSTM time slices), workspace handled here."""
+        ws = self._conv_ws(N, H, W, Cin, Ho, Wo, Cout, k, stride, up, r)
+        self._call('dl4ds_conv2d_fwd', xptr, xld, wptr, bptr, resptr, resld, yptr, yld, N, H, W, Cin, Ho, Wo,
+                   Cout, k, k, stride, up, pt, pl, wmode, act, r, beta, self.math,
+                   ws.data_ptr() if ws is not None else None, _stream())
+
     def _p(self, name):
         self.names_used.append(name)
         return self.arena.param(name)
@@ -261,11 +278,12 @@ class Ctx:
         if res is not None:
             assert (res.N, res.H, res.W, res.C) == (x.N, Ho, Wo, cout)
         a = ACT[act]
+        ws = self._conv_ws(x.N, x.H, x.W, x.C, Ho, Wo, cout, k, stride, 1, r)
         self._timed('%s:fwd@%dx%d' % (name, x.H, x.W),
                     'dl4ds_conv2d_fwd', x.ptr, x.ld, w.data_ptr(), b.data_ptr() if bias else None,
                    res.ptr if res is not None else None, res.ld if res is not None else 0,
                    out.ptr, out.ld, x.N, x.H, x.W, x.C, Ho, Wo, cout, k, k, stride, 1, pt, pl,
-                   W_HWIO, a, r, 0, self.math, _stream())
+                   W_HWIO, a, r, 0, self.math, ws.data_ptr() if ws is not None else None, _stream())
 
         def bwd():
             dy = out.grad
@@ -290,10 +308,12 @@ class Ctx:
             # input gradient
             if x.requires_grad:
                 def wr(dst, beta):
+                    ws2 = self._conv_ws(x.N, Ho, Wo, cout, x.H, x.W, x.C, k, 1, stride, 1)
                     self._timed('%s:dgrad@%dx%d' % (name, x.H, x.W),
                                'dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
                                dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1, stride,
-                               k - 1 - pt, k - 1 - pl, W_FLIP_T, 0, 1, beta, self.math, _stream())
+                               k - 1 - pt, k - 1 - pl, W_FLIP_T, 0, 1, beta, self.math,
+                               ws2.data_ptr() if ws2 is not None else None, _stream())
                 self._acc(x, wr)
             if res is not None:     # d(res) = dz; handed over last (stream order keeps reads before
                 self._give_grad(res, dz)   # any later in-place update by the new owner)
@@ -320,7 +340,7 @@ class Ctx:
         a = ACT[act]
         self._call('dl4ds_conv2d_fwd', x.ptr, x.ld, w.data_ptr(), None, None, 0, out.ptr, out.ld,
                    x.N, x.H, x.W, x.C, Ho, Wo, cout, k, k, 1, stride, k - 1 - pt, k - 1 - pl,
-                   W_FLIP_T, a, 1, 0, self.math, _stream())
+                   W_FLIP_T, a, 1, 0, self.math, None, _stream())
 
         def bwd():
             dy = out.grad
@@ -337,7 +357,7 @@ class Ctx:
                 def wr(dst, beta):
                     self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
                                dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, stride, 1,
-                               pt, pl, W_HWIO, 0, 1, beta, self.math, _stream())
+                               pt, pl, W_HWIO, 0, 1, beta, self.math, None, _stream())
                 self._acc(x, wr)
             out.grad = None
         self._record(bwd)
@@ -629,8 +649,8 @@ class Ctx:
         npx = B * H * W
         # input convolution for all T at once (one GEMM): z (T*B, H, W, 4F)
         z = new_var(TB, H, W, F4, dev)
-        self._call('dl4ds_conv2d_fwd', x.ptr, x.ld, wx.data_ptr(), bias.data_ptr(), None, 0, z.ptr, z.ld,
-                   TB, H, W, C, H, W, F4, k, k, 1, 1, pad, pad, W_HWIO, 0, 1, 0, self.math, _stream())
+        self._conv_raw(x.ptr, x.ld, wx.data_ptr(), bias.data_ptr(), None, 0, z.ptr, z.ld,
+                       TB, H, W, C, H, W, F4, k, 1, 1, pad, pad, W_HWIO, 0, 1, 0)
         out = new_var(TB, H, W, filters, dev)
         cs = torch.empty((TB, H, W, filters), dtype=torch.float32, device=dev)
         gates = torch.empty((TB, H, W, F4), dtype=torch.float32, device=dev)
@@ -641,9 +661,9 @@ class Ctx:
         for t in range(T):
             zt = step(z.buf, t)
             if t > 0:   # z_t += conv(h_{t-1}, Wh)
-                self._call('dl4ds_conv2d_fwd', step(out.buf, t - 1).data_ptr(), filters, wh.data_ptr(), None,
-                           None, 0, zt.data_ptr(), F4, B, H, W, filters, H, W, F4, k, k, 1, 1, pad, pad,
-                           W_HWIO, 0, 1, 1, self.math, _stream())
+                self._conv_raw(step(out.buf, t - 1).data_ptr(), filters, wh.data_ptr(), None,
+                               None, 0, zt.data_ptr(), F4, B, H, W, filters, H, W, F4, k, 1, 1, pad, pad,
+                               W_HWIO, 0, 1, 1)
             self._call('dl4ds_convlstm_gates_fwd', zt.data_ptr(), step(cs, t - 1).data_ptr() if t > 0 else None,
                        step(cs, t).data_ptr(), step(out.buf, t).data_ptr(), filters,
                        step(gates, t).data_ptr(), npx, filters, _stream())
@@ -666,9 +686,9 @@ class Ctx:
                            dzt.data_ptr(), dc[t % 2].data_ptr(), npx, filters, _stream())
                 if t > 0:
                     # dh_{t-1} += dgrad(dz_t, Wh);  dWh += wgrad(h_{t-1}, dz_t)
-                    self._call('dl4ds_conv2d_fwd', dzt.data_ptr(), F4, wh.data_ptr(), None, None, 0,
-                               step(dh, t - 1).data_ptr(), filters, B, H, W, F4, H, W, filters, k, k, 1, 1,
-                               k - 1 - pad, k - 1 - pad, W_FLIP_T, 0, 1, 1, self.math, _stream())
+                    self._conv_raw(dzt.data_ptr(), F4, wh.data_ptr(), None, None, 0,
+                                   step(dh, t - 1).data_ptr(), filters, B, H, W, F4, H, W, filters, k, 1, 1,
+                                   k - 1 - pad, k - 1 - pad, W_FLIP_T, 0, 1, 1)
                     self._wgrad(Var(step(out.buf, t - 1)), Var(dzt), gwh, k, 1, pad, pad)
             # the input convolution's bias / weight / input gradients, all T in one shot
             self._call('dl4ds_bias_act_bwd', dz.ptr, dz.ld, None, 0, None, 0,
@@ -676,9 +696,9 @@ class Ctx:
             self._wgrad(x, dz, self._g(name + '/kernel'), k, 1, pad, pad)
             if x.requires_grad:
                 def wr(dst, beta):
-                    self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, wx.data_ptr(), None, None, 0, dst.ptr,
-                               dst.ld, TB, H, W, F4, H, W, C, k, k, 1, 1, k - 1 - pad, k - 1 - pad,
-                               W_FLIP_T, 0, 1, beta, self.math, _stream())
+                    self._conv_raw(dz.ptr, dz.ld, wx.data_ptr(), None, None, 0, dst.ptr,
+                                   dst.ld, TB, H, W, F4, H, W, C, k, 1, 1, k - 1 - pad, k - 1 - pad,
+                                   W_FLIP_T, 0, 1, beta)
                 self._acc(x, wr)
             out.grad = None
         self._record(bwd)

@@ -51,11 +51,15 @@ extern "C" {
 /* weight indexing modes of dl4ds_conv2d_fwd */
 #define DL4DS_W_HWIO        0  /* B[(tap,c),n] = w[tap][c][n]            (Conv2D forward)          */
 #define DL4DS_W_FLIP_T      1  /* B[(tap,c),n] = w[flip(tap)][n][c]      (Conv2D dgrad, ConvT fwd) */
+#define DL4DS_W_PREPACKED   4  /* OR-ed into wmode: `ws` already holds dl4ds_conv2d_pack(w, wmode) */
 
 const char* dl4ds_last_error(void);
 int dl4ds_version(void);
 /* 1 if the device behind the current context is sm_100 (tcgen05 paths usable). */
 int dl4ds_device_is_sm100(void);
+/* Number of tcgen05 (tensor-core) kernel launches issued by this process so far: lets callers and
+ * tests verify that a tensor-core math mode did not silently take the CUDA-core path. */
+int64_t dl4ds_tc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution family.  One generalized implicit-GEMM entry point covers:
@@ -71,12 +75,24 @@ int dl4ds_device_is_sm100(void);
  * dgrad.  If d2s_r>1 the result is stored through tf.nn.depth_to_space(., r) (NHWC DCR order,
  * blocks.py:427): y has shape (N, Ho*r, Wo*r, Cout/(r*r)) and `res` must be NULL.
  * bias and res may be NULL.  beta=1 accumulates into y (y += result; only with act NONE, no d2s).
+ *
+ * Tensor-core math modes (TF32 / TF32X3) run the tcgen05 implicit-GEMM kernel when the shape is in
+ * its domain (stride 1, up 1, 'same' grid, Cin and Cout multiples of 8, Cout <= 256, W a power of two
+ * in [8,128] or a multiple of 128, 16-byte aligned tensors); otherwise the call runs the CUDA-core
+ * fp32 kernel.  They need `ws`: dl4ds_conv2d_fwd_workspace_bytes() bytes, 128-byte aligned, into which
+ * the call packs the weights (tf32 hi/lo split, swizzled shared-memory image) -- or, with
+ * DL4DS_W_PREPACKED in wmode, which already holds dl4ds_conv2d_pack() of the same (w, wmode), so one
+ * pack per optimizer step serves every application of a layer.  ws may be NULL when the query is 0.
  * ------------------------------------------------------------------------------------------- */
+int64_t dl4ds_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
+                                         int KH, int KW, int stride, int up, int d2s_r, int math_mode);
+int dl4ds_conv2d_pack(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode,
+                      void* ws, void* stream);
 int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias,
                      const float* res, int res_ld, float* y, int y_ld,
                      int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
                      int KH, int KW, int stride, int up, int pad_t, int pad_l,
-                     int wmode, int act, int d2s_r, int beta, int math_mode, void* stream);
+                     int wmode, int act, int d2s_r, int beta, int math_mode, void* ws, void* stream);
 
 /* Weight gradient of the same family (accumulating):
  *   dw[kh][kw][a][b] += sum_{n,oy,ox} P[n,oy*stride+kh-pad_t,ox*stride+kw-pad_l,a] * Q[n,oy,ox,b]

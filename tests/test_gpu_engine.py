@@ -236,3 +236,65 @@ def test_discriminator(cuda, ups, scale):
         return y.reshape(3, 1, 1, 1)
     shapes = [(3,) + s for s in m.input_shapes]
     compare(fn, ofn, shapes, cuda, tol=5e-5, gtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------ tcgen05
+TC_TOL = {'tf32x3': dict(tol=2e-5, gtol=2e-4), 'tf32': dict(tol=5e-3, gtol=2e-2)}
+
+
+def _tc_count():
+    from dl4ds_b200 import _lib
+    return _lib.load().dl4ds_tc_launch_count()
+
+
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('shape,cout,k,act', [
+    ((2, 16, 16, 8), 16, 3, 'relu'),        # SW32 chunks, BW=16 BH=8
+    ((2, 8, 16, 24), 40, 3, None),          # Cin 24 -> three 8-channel chunks; Cout 40 -> Npad 48
+    ((1, 32, 32, 48), 48, 3, 'tanh'),       # SW64 chunks
+    ((1, 64, 64, 16), 48, 1, 'relu'),       # 1x1
+    ((1, 128, 128, 8), 8, 3, None),         # HR tail shape: one row per tile, Npad 16 > Cout 8
+    ((2, 16, 8, 32), 64, 5, 'sigmoid'),     # SW128 chunks, 5x5, BW=8 BH=16
+    ((1, 2, 256, 8), 8, 3, 'relu'),         # W > 128: two tiles per row
+])
+def test_conv_tc(cuda, math, shape, cout, k, act):
+    """tcgen05 implicit-GEMM forward + dgrad against the oracle; asserts the tensor-core kernel ran."""
+    if math == 'tf32' and act == 'relu':
+        act = 'tanh'    # single-pass tf32 flips relu masks where |y| ~ 1e-3: compare smooth graphs only
+    fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=k, act=act)
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=k), act))
+    n0 = _tc_count()
+    compare(fn, ofn, [shape], cuda, math=math, **TC_TOL[math])
+    assert _tc_count() >= n0 + 2, 'tensor-core path did not run (fwd + dgrad expected)'
+
+
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+def test_conv_tc_residual_and_d2s(cuda, math):
+    a = 'relu' if math == 'tf32x3' else 'tanh'
+
+    def fn(c, xs):
+        y = c.conv(xs[0], 'cv', 16, act=a, res=xs[1])
+        return c.conv(y, 'up', 64, d2s=2)
+    ofn = _o(lambda p, xs: R.depth_to_space(R._conv(p, 'up', R.act(R._conv(p, 'cv', xs[0], 16) + xs[1], a), 64), 2))
+    n0 = _tc_count()
+    compare(fn, ofn, [(2, 16, 32, 8), (2, 16, 32, 16)], cuda, math=math, **TC_TOL[math])
+    assert _tc_count() >= n0 + 4
+
+
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+def test_spc_block_tc(cuda, math):
+    """The headline layer: shared 48 -> 192 3x3 conv + depth_to_space applied at 32^2 and 64^2."""
+    fn = lambda c, xs: B.subpixel_block(c, 'spc', xs[0], 4, 48)
+    ofn = _o(lambda p, xs: R.subpixel_block(p, 'spc', xs[0], 4, 48))
+    compare(fn, ofn, [(1, 32, 32, 48)], cuda, math=math, **TC_TOL[math])
+
+
+@pytest.mark.parametrize('math', ['tf32x3'])
+def test_net_resnet_spc_tc(cuda, math):
+    m = nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (32, 32), n_blocks=3)
+    ofn = lambda p, xs: R.net_postupsampling(p, xs, 'resnet', 'spc', 4, n_blocks=3)
+    n0 = _tc_count()
+    # gtol: a relu mask that flips on a ~1e-6 pre-activation difference moves a 2048-pixel weight
+    # gradient by ~1e-3 of its max; the per-op tests above (smooth graphs) hold 2e-4
+    compare(m.fn, ofn, [(2, 32, 32, 1)], cuda, math=math, tol=5e-5, gtol=3e-3, input_grads=False)
+    assert _tc_count() > n0 + 10
