@@ -125,6 +125,10 @@ int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float
     a.NQ = (int64_t)N * Hq * Wq;
     a.chunks_per_split = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {   // narrow layers (Ca, Cb in {1, 8}, 3x3): exact-fp32 sliding-window kernel in every math mode
+        int rc = conv2d_wgrad_thin(a, st);
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+    }
     if (math_mode != DL4DS_MATH_FP32) {
         int rc = conv2d_wgrad_tc(a, ws, math_mode, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;

@@ -476,25 +476,32 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
 // kernel row in TMEM (KW x Nmma columns) so one Q tile feeds KW taps.  blockIdx.x splits the pixel
 // tiles (split-K); partial sums are merged with fp32 atomics.
 // -------------------------------------------------------------------------------------------------
-constexpr int kWgKT = 32;             // pixels per stage = one 128-byte K-major row
+constexpr int kWgThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 transposers (2-5 also epilogue)
+constexpr int kWgMaxUnits = 128;      // (raw box, 4-channel group) pairs per stage
 
 struct TcWgradParams {
     float* dw;
     int H, W, Ca, Cb;
     int KH, KW, pad_t, pad_l;
+    int nk;                           // 32-pixel chunks per stage (KT = 32*nk pixels)
     int BW, BH, tiles_x, tiles_per_img, ntiles, tiles_per_split;
     int kc_p, span_p, kc_q, span_q;
     int ncig, ncob, Nb;
     int nblk_p_max, nblk_q_max;       // raw boxes per tap (P) / per tile (Q) the smem layout is sized for
-    int box_p, box_q;                 // bytes per raw TMA box (32 pixels x span)
+    int box_p, box_q;                 // bytes per raw TMA box (KT pixels x span)
     int raw_bytes;                    // raw region per stage
-    int pt_bytes, qt_bytes;           // transposed operand tiles: P^T per tap (64 rows x 128 B), Q^T (Nmma rows x 128 B)
-    int op_bytes;                     // KW*pt_bytes + qt_bytes: one (hi) operand set
+    int pt_bytes, qt_bytes;           // transposed tiles per 32-pixel chunk: P^T per tap, Q^T
+    int chunk_bytes;                  // KW*pt_bytes + qt_bytes: operand tiles of one 32-pixel chunk
+    int op_bytes;                     // nk*chunk_bytes: one (hi) operand set
     int stage_bytes, stages, tmem_cols;
 };
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <bool X3>
-__global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p,
+__global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p,
                                                                   const __grid_constant__ CUtensorMap tmap_q,
                                                                   const TcWgradParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -503,6 +510,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_
     __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
     __shared__ __align__(8) uint64_t bar_accum;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ uint4 unit_tab[kWgMaxUnits];     // {raw box offset, group, dst tile offset in a chunk, first row | isQ<<16}
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -526,10 +534,16 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_
     const int my_tiles = t_end - t_begin;
     if (my_tiles <= 0) return;
 
+    const uint32_t rawq_off = (uint32_t)(p.KW * p.nblk_p_max * p.box_p);     // Q boxes inside the raw region
+    const uint32_t qt_off = (uint32_t)(p.KW * p.pt_bytes);                  // Q^T inside a chunk's operand tiles
+    const int gp = p.kc_p / 4, gq = p.kc_q / 4;
+    const int units_p = p.KW * nblk_p * gp;
+    const int nunits = units_p + nblk_q * gq;
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_conv[s]), 128);
+            mbar_init(smem_u32(&bar_conv[s]), 256);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         mbar_init(smem_u32(&bar_accum), 1);
@@ -537,14 +551,31 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_
         tma_prefetch_desc(&tmap_p);
         tma_prefetch_desc(&tmap_q);
     }
+    for (int u = threadIdx.x; u < nunits; u += blockDim.x) {
+        uint4 e;
+        if (u < units_p) {
+            const int g = u % gp, tb = u / gp;
+            const int kw = tb / nblk_p, b = tb - kw * nblk_p;
+            e.x = (uint32_t)((kw * p.nblk_p_max + b) * p.box_p);
+            e.y = (uint32_t)g;
+            e.z = (uint32_t)(kw * p.pt_bytes);
+            e.w = (uint32_t)(b * p.kc_p + g * 4);
+        } else {
+            const int j = u - units_p;
+            const int g = j % gq, b = j / gq;
+            e.x = rawq_off + (uint32_t)(b * p.box_q);
+            e.y = (uint32_t)g;
+            e.z = qt_off;
+            e.w = (uint32_t)(b * p.kc_q + g * 4) | (1u << 16);
+        }
+        unit_tab[u] = e;
+    }
     if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
-    const uint32_t rawq_off = (uint32_t)(p.KW * p.nblk_p_max * p.box_p);     // Q boxes inside the raw region
     const uint32_t op_off = (uint32_t)p.raw_bytes;                          // operand tiles follow the raw region
-    const uint32_t qt_off = (uint32_t)(p.KW * p.pt_bytes);                  // Q^T inside an operand set
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -580,25 +611,28 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_
                 mbar_wait(smem_u32(&bar_conv[s]), ph);
                 tc_fence_after();
                 const uint32_t so = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes + op_off;
-                for (int kw = 0; kw < p.KW; ++kw) {
-                    const uint32_t pa = so + (uint32_t)(kw * p.pt_bytes);
-                    const uint32_t qb = so + qt_off;
-                    const uint32_t td = tmem_d + (uint32_t)(kw * Nmma);
+                for (int j = 0; j < p.nk; ++j) {
+                    const uint32_t sc = so + (uint32_t)(j * p.chunk_bytes);
+                    const uint32_t qb = sc + qt_off;
+                    for (int kw = 0; kw < p.KW; ++kw) {
+                        const uint32_t pa = sc + (uint32_t)(kw * p.pt_bytes);
+                        const uint32_t td = tmem_d + (uint32_t)(kw * Nmma);
 #pragma unroll
-                    for (int k = 0; k < kWgKT / 8; ++k) {
-                        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-                        const uint32_t ko = (uint32_t)k * 32u;
-                        const uint64_t da = make_smem_desc(pa + ko, 16, 1024, kLayoutSw128);
-                        const uint64_t db = make_smem_desc(qb + ko, 16, 1024, kLayoutSw128);
-                        if (X3) {
-                            const uint32_t h = (uint32_t)p.op_bytes;
-                            const uint64_t dal = make_smem_desc(pa + h + ko, 16, 1024, kLayoutSw128);
-                            const uint64_t dbl = make_smem_desc(qb + h + ko, 16, 1024, kLayoutSw128);
-                            umma_tf32(td, dal, db, idesc, acc);
-                            umma_tf32(td, da, dbl, idesc, 1u);
-                            umma_tf32(td, da, db, idesc, 1u);
-                        } else {
-                            umma_tf32(td, da, db, idesc, acc);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t acc = (it > 0 || j > 0 || k > 0) ? 1u : 0u;
+                            const uint32_t ko = (uint32_t)k * 32u;
+                            const uint64_t da = make_smem_desc(pa + ko, 16, 1024, kLayoutSw128);
+                            const uint64_t db = make_smem_desc(qb + ko, 16, 1024, kLayoutSw128);
+                            if (X3) {
+                                const uint32_t h = (uint32_t)p.op_bytes;
+                                const uint64_t dal = make_smem_desc(pa + h + ko, 16, 1024, kLayoutSw128);
+                                const uint64_t dbl = make_smem_desc(qb + h + ko, 16, 1024, kLayoutSw128);
+                                umma_tf32(td, dal, db, idesc, acc);
+                                umma_tf32(td, da, dbl, idesc, 1u);
+                                umma_tf32(td, da, db, idesc, 1u);
+                            } else {
+                                umma_tf32(td, da, db, idesc, acc);
+                            }
                         }
                     }
                 }
@@ -607,69 +641,64 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_
             umma_commit(smem_u32(&bar_accum));
         }
     } else {
-        // ===================== transposer (+ tf32 split) and epilogue =====================
-        const int ew = warp - 2;                       // 0..3
-        const int gp = p.kc_p / 4, gq = p.kc_q / 4;     // float4 groups per raw row
-        const int items_p = p.KW * nblk_p * gp;         // (tap, block, group) triples of P
-        const int items = items_p + nblk_q * gq;
+        // ===================== transposers (+ tf32 split), then epilogue on warps 2-5 =====================
+        const int tw = warp - 2;                       // 0..7
+        // lane-dependent parts of the swizzled addresses (this thread always handles pixel row `lane` of a chunk)
+        const uint32_t src_lane_p = (uint32_t)(lane * p.span_p), src_lane_q = (uint32_t)(lane * p.span_q);
+        const uint32_t dst_lane = (uint32_t)((lane & 3) << 2);
+        const uint32_t lane_unit = (uint32_t)(lane >> 2);
         for (int it = 0; it < my_tiles; ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)((it / p.stages) & 1);
             mbar_wait(smem_u32(&bar_full[s]), ph);
             uint8_t* raw = smem_al + (size_t)s * p.stage_bytes;
             uint8_t* ops = raw + p.raw_bytes;
-            for (int i = ew; i < items; i += 4) {
-                const uint8_t* src;
-                uint8_t* dst;
-                int ch;                                 // first of the 4 channel rows this item writes
-                if (i < items_p) {
-                    const int g = i % gp, tb = i / gp;              // tb = tap * nblk_p + block
-                    const int kw = tb / nblk_p, b = tb - kw * nblk_p;
-                    src = raw + (size_t)(kw * p.nblk_p_max + b) * p.box_p + lane * p.span_p +
-                          (swizzle_unit(g, lane, p.span_p) << 4);
-                    ch = b * p.kc_p + g * 4;
-                    dst = ops + (size_t)kw * p.pt_bytes;
-                } else {
-                    const int j = i - items_p;
-                    const int g = j % gq, b = j / gq;
-                    src = raw + rawq_off + (size_t)b * p.box_q + lane * p.span_q + (swizzle_unit(g, lane, p.span_q) << 4);
-                    ch = b * p.kc_q + g * 4;
-                    dst = ops + qt_off;
-                }
+            for (int j = 0; j < p.nk; ++j)
+            for (int u = tw; u < nunits; u += 8) {
+                const uint4 e = unit_tab[u];
+                const bool isq = (e.w >> 16) != 0;
+                const int span = isq ? p.span_q : p.span_p;
+                const uint32_t chunk_rows = (uint32_t)(j * 32) * (uint32_t)span;
+                const uint8_t* src = raw + e.x + chunk_rows + (isq ? src_lane_q : src_lane_p) +
+                                     ((uint32_t)swizzle_unit((int)e.y, lane, span) << 4);
                 const float4 v = *reinterpret_cast<const float4*>(src);
+                uint8_t* dst = ops + (size_t)j * p.chunk_bytes + e.z;
+                const uint32_t row0 = e.w & 0xffffu;
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int row = ch + j;
-                    const int off = row * 128 + ((((lane >> 2) ^ (row & 7)) << 4) | ((lane & 3) << 2));
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t row = row0 + r;
+                    const uint32_t off = row * 128u + (((lane_unit ^ (row & 7u)) << 4) | dst_lane);
                     if (X3) {
-                        const float h = tf32_rna(vv[j]);
+                        const float h = tf32_rna(vv[r]);
                         *reinterpret_cast<float*>(dst + off) = h;
-                        *reinterpret_cast<float*>(dst + p.op_bytes + off) = tf32_rna(vv[j] - h);
+                        *reinterpret_cast<float*>(dst + p.op_bytes + off) = tf32_rna(vv[r] - h);
                     } else {
-                        *reinterpret_cast<float*>(dst + off) = vv[j];
+                        *reinterpret_cast<float*>(dst + off) = vv[r];
                     }
                 }
             }
             fence_proxy_async_smem();
             mbar_arrive(smem_u32(&bar_conv[s]));
         }
-        mbar_wait(smem_u32(&bar_accum), 0);
-        tc_fence_after();
-        // M = 64 accumulator layout: row r lives in TMEM lane 32*(r/16) + r%16
-        const int q = warp & 3;
-        const int ci = ca0 + q * 16 + lane;                 // valid for lane < 16
-        const bool row_ok = lane < 16 && (q * 16 + lane) < ca_n;
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
-        for (int kw = 0; kw < p.KW; ++kw) {
-            float* dst_row = p.dw + ((int64_t)((kh * p.KW + kw) * p.Ca + ci)) * p.Cb + cb0;
-            for (int c0 = 0; c0 < Nmma; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)(kw * Nmma + c0), v);
-                if (row_ok) {
+        if (tw < 4) {
+            mbar_wait(smem_u32(&bar_accum), 0);
+            tc_fence_after();
+            // M = 64 accumulator layout: row r lives in TMEM lane 32*(r/16) + r%16
+            const int q = warp & 3;
+            const int ci = ca0 + q * 16 + lane;                 // valid for lane < 16
+            const bool row_ok = lane < 16 && (q * 16 + lane) < ca_n;
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
+            for (int kw = 0; kw < p.KW; ++kw) {
+                float* dst_row = p.dw + ((int64_t)((kh * p.KW + kw) * p.Ca + ci)) * p.Cb + cb0;
+                for (int c0 = 0; c0 < Nmma; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)(kw * Nmma + c0), v);
+                    if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < cb_n) atomicAdd(dst_row + c0 + j, v[j]);
+                        for (int j = 0; j < 16; j += 4)
+                            if (c0 + j < cb_n) red_add_v4(dst_row + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
                 }
             }
         }
@@ -679,7 +708,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_wgrad_kernel(const __grid_
     if (warp == 1) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
 }
 
-static bool wgrad_supported(const WgradArgs& a, int math_mode, int* BW, int* BH) {
+static bool wgrad_supported(const WgradArgs& a, int math_mode) {
     if (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3) return false;
     if (!is_sm100()) return false;
     if (a.stride != 1 || a.Hp != a.Hq || a.Wp != a.Wq) return false;
@@ -687,17 +716,27 @@ static bool wgrad_supported(const WgradArgs& a, int math_mode, int* BW, int* BH)
     if (a.p_ld % 4 || a.q_ld % 4) return false;
     if ((reinterpret_cast<uintptr_t>(a.P) & 15) || (reinterpret_cast<uintptr_t>(a.Q) & 15)) return false;
     if (a.KW > 5 || a.KH > 9) return false;
-    return tile_geometry(a.Hq, a.Wq, kWgKT, BW, BH);
+    if ((reinterpret_cast<uintptr_t>(a.dw) & 15)) return false;
+    int bw, bh;
+    return tile_geometry(a.Hq, a.Wq, 32, &bw, &bh);
 }
 
 int64_t conv2d_wgrad_tc_workspace(int, int, int, int, int, int, int) { return 0; }
 
 int conv2d_wgrad_tc(const WgradArgs& a, void*, int math_mode, cudaStream_t st) {
-    int BW, BH;
-    if (!wgrad_supported(a, math_mode, &BW, &BH)) return DL4DS_E_UNSUPPORTED;
+    if (!wgrad_supported(a, math_mode)) return DL4DS_E_UNSUPPORTED;
     const bool x3 = math_mode == DL4DS_MATH_TF32X3;
     const Chunk cp = pick_chunk(a.Ca), cq = pick_chunk(a.Cb);
     TcWgradParams p;
+    // pixels per stage: 32*nk, aiming at >= 16 KB of raw TMA traffic per stage (latency amortisation)
+    const int ca_f = a.Ca < 64 ? a.Ca : 64;
+    const int raw32 = 32 * 4 * (a.KW * ca_f + (a.Cb < 128 ? a.Cb : 128));
+    int nk = (16 * 1024 + raw32 - 1) / raw32;
+    if (nk > 8) nk = 8;
+    int BW = 0, BH = 0;
+    while (nk > 1 && !tile_geometry(a.Hq, a.Wq, 32 * nk, &BW, &BH)) --nk;
+    tile_geometry(a.Hq, a.Wq, 32 * nk, &BW, &BH);
+    p.nk = nk;
     p.dw = a.dw;
     p.H = a.Hq; p.W = a.Wq; p.Ca = a.Ca; p.Cb = a.Cb;
     p.KH = a.KH; p.KW = a.KW; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
@@ -720,15 +759,18 @@ int conv2d_wgrad_tc(const WgradArgs& a, void*, int math_mode, cudaStream_t st) {
     p.nblk_p_max = ca_first / cp.kc;
     const int cb_first = a.Cb < nb ? a.Cb : nb;
     p.nblk_q_max = cb_first / cq.kc;
-    p.box_p = kWgKT * cp.span;
-    p.box_q = kWgKT * cq.span;
+    p.box_p = 32 * nk * cp.span;
+    p.box_q = 32 * nk * cq.span;
     p.raw_bytes = a.KW * p.nblk_p_max * p.box_p + p.nblk_q_max * p.box_q;       // multiples of 1024
     const int nmma_max = (cb_first + 15) & ~15;
-    p.pt_bytes = 64 * 128;
-    p.qt_bytes = ((nmma_max * 128) + 1023) & ~1023;
-    p.op_bytes = a.KW * p.pt_bytes + p.qt_bytes;
+    p.pt_bytes = ((ca_first + 7) & ~7) * 128;              // rows past Ca alias whatever follows (never read back)
+    p.qt_bytes = nmma_max * 128;
+    p.chunk_bytes = a.KW * p.pt_bytes + p.qt_bytes;
+    p.op_bytes = nk * p.chunk_bytes;
     p.stage_bytes = p.raw_bytes + p.op_bytes * (x3 ? 2 : 1);
-    int stages = (218 * 1024) / p.stage_bytes;
+    if (a.KW * (ca_first / cp.kc) * (cp.kc / 4) + (cb_first / cq.kc) * (cq.kc / 4) > kWgMaxUnits) return DL4DS_E_UNSUPPORTED;
+    const int slack = 64 * 128;                            // the M=64 operand window of the last tile stays in-bounds
+    int stages = (218 * 1024 - slack) / p.stage_bytes;
     if (stages < 1) return DL4DS_E_UNSUPPORTED;
     if (stages > kMaxStages) stages = kMaxStages;
     int cols = 32;
@@ -747,7 +789,7 @@ int conv2d_wgrad_tc(const WgradArgs& a, void*, int math_mode, cudaStream_t st) {
     splits = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
     if (stages > p.tiles_per_split) stages = p.tiles_per_split;
     p.stages = stages;
-    const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+    const size_t smem = (size_t)stages * p.stage_bytes + slack + 1024;
     const CUtensorMap* tp = get_tensor_map_nhwc(a.P, a.p_ld, a.N, a.Hp, a.Wp, a.Ca, cp.kc, BW, BH, cp.swz);
     const CUtensorMap* tq = get_tensor_map_nhwc(a.Q, a.q_ld, a.N, a.Hq, a.Wq, a.Cb, cq.kc, BW, BH, cq.swz);
     if (!tp || !tq) return DL4DS_E_CUDA;
@@ -759,9 +801,9 @@ int conv2d_wgrad_tc(const WgradArgs& a, void*, int math_mode, cudaStream_t st) {
         attr_done = true;
     }
     if (x3)
-        conv_tc_wgrad_kernel<true><<<grid, kTcThreads, smem, st>>>(*tp, *tq, p);
+        conv_tc_wgrad_kernel<true><<<grid, kWgThreads, smem, st>>>(*tp, *tq, p);
     else
-        conv_tc_wgrad_kernel<false><<<grid, kTcThreads, smem, st>>>(*tp, *tq, p);
+        conv_tc_wgrad_kernel<false><<<grid, kWgThreads, smem, st>>>(*tp, *tq, p);
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     return check_launch("conv_tc_wgrad_kernel");
 }

@@ -708,13 +708,17 @@ int dl4ds_bias_act_bwd(const float* dy, int dy_ld, const float* y, int y_ld, flo
         DL4DS_REQUIRE(act == DL4DS_ACT_NONE || y != nullptr, DL4DS_E_BADARG, "bias_act_bwd: y needed");
     }
     int TX, KS;
+    const int64_t n_pix = (int64_t)N * Ho * Wo;
+    cudaStream_t st = as_stream(stream);
+    {
+        int rc = bias_act_bwd_vec4(dy, dy_ld, y, y_ld, dz, dz_ld, dbias, n_pix, Ho, Wo, C, act, d2s_r, st);
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+    }
     pick_xy(C, TX, KS);
     DL4DS_REQUIRE(KS <= 8, DL4DS_E_UNSUPPORTED, "bias_act_bwd: C > 512 unsupported");
     const int PY = 256 / TX;
-    const int64_t n_pix = (int64_t)N * Ho * Wo;
     dim3 block(TX, PY);
     const int grid = grid_for(n_pix, PY * 8, 4 * kNumSMs);
-    cudaStream_t st = as_stream(stream);
 #define LAUNCH_BAB(K) bias_act_bwd_kernel<K><<<grid, block, 0, st>>>(dy, dy_ld, y, y_ld, dz, dz_ld, dbias, n_pix, Ho, Wo, C, act, d2s_r)
     if (KS == 1) LAUNCH_BAB(1);
     else if (KS == 2) LAUNCH_BAB(2);

@@ -1,0 +1,325 @@
+// HBM-bound kernels for the NARROW layers of the DL4DS graphs (the HR tail: 8 / 1 channels at
+// 128 x 128 -- sp_postups.py:205-212 -- and the 1-channel stem, sp_postups.py:134).  These layers
+// cannot feed a 128 x N tensor-core tile (Cout 1 / 8) and are bandwidth-bound anyway, so they get
+// CUDA-core kernels built around data reuse in shared memory and registers:
+//
+//   thin_wgrad_kernel<CA,CB>  3x3 stride-1 weight gradient for Ca, Cb in {1, 8}: an (rows x cols)
+//       tile of P (with halo) and Q lives in shared memory; a thread owns a TA x TB block of
+//       (ca, cb) pairs for ALL nine taps (9*TA*TB accumulators) and walks 32 pixels of one row with
+//       a 3x3 sliding register window, i.e. 4 shared loads per 72 FMAs for Ca = Cb = 8.
+//   bias_act_bwd_vec4_kernel  dz = dy * act'(y) (+ space_to_depth un-shuffle), dbias += sum dz with
+//       16-byte accesses.
+#include "common.cuh"
+
+namespace dl4ds {
+
+// -------------------------------------------------------------------------------------------------
+// thin 3x3 wgrad
+// -------------------------------------------------------------------------------------------------
+template <int CA, int CB>
+struct ThinCfg {
+    static constexpr int TA = CA >= 2 ? 2 : 1;
+    static constexpr int TB = CB >= 4 ? 4 : 1;
+    static constexpr int TPS = (CA / TA) * (CB / TB);      // threads per pixel stream
+    static constexpr int STREAMS = 256 / TPS;
+    static constexpr int SEG = 32;                          // pixels per stream per tile
+};
+
+struct ThinWgradArgs {
+    const float* P; const float* Q; float* dw;
+    int p_ld, q_ld;
+    int N, H, W, pad_t, pad_l;
+    int TW, TH, tiles_x, tiles_y, ntiles;
+    int p_pitch, q_pitch;       // shared-memory row pitches in floats
+};
+
+template <int CA, int CB>
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWgradArgs a) {
+    using C = ThinCfg<CA, CB>;
+    constexpr int TA = C::TA, TB = C::TB, TPS = C::TPS, SEG = C::SEG;
+    extern __shared__ float sm[];
+    float* Ps = sm;                                          // (TH+2) rows x p_pitch
+    float* Qs = sm + (((size_t)(a.TH + 2) * a.p_pitch + 3) & ~(size_t)3);   // TH rows x q_pitch (16-byte aligned)
+    __shared__ float red[9 * CA * CB];
+
+    const int tid = threadIdx.x;
+    const int stream = tid / TPS, sub = tid % TPS;
+    const int ca0 = (sub / (CB / TB)) * TA, cb0 = (sub % (CB / TB)) * TB;
+    const int segs = a.TW / SEG;
+    // consecutive streams = consecutive rows (row pitches are chosen so that they hit distinct banks)
+    const int srow = stream % a.TH, sseg = stream / a.TH;
+    const bool active = sseg < segs;
+
+    float acc[3][3][TA][TB];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int u = 0; u < TA; ++u)
+#pragma unroll
+                for (int v = 0; v < TB; ++v) acc[i][j][u][v] = 0.0f;
+    for (int i = tid; i < 9 * CA * CB; i += 256) red[i] = 0.0f;
+
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int img = tile / (a.tiles_x * a.tiles_y);
+        const int trem = tile - img * a.tiles_x * a.tiles_y;
+        const int ty = trem / a.tiles_x, tx = trem - ty * a.tiles_x;
+        const int y0 = ty * a.TH, x0 = tx * a.TW;
+        __syncthreads();       // previous tile fully consumed
+        // ---- P tile with halo: rows y0-pad_t .. +TH+2, cols x0-pad_l .. +TW+2, CA channels
+        {
+            const int cols = a.TW + 2, rows = a.TH + 2;
+            if constexpr (CA % 4 == 0) {
+                const int v4 = CA / 4, total = rows * cols * v4;
+                for (int i = tid; i < total; i += 256) {
+                    const int c4 = i % v4, px = (i / v4) % cols, r = i / (v4 * cols);
+                    const int gy = y0 + r - a.pad_t, gx = x0 + px - a.pad_l;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W)
+                        v = __ldg(reinterpret_cast<const float4*>(a.P + ((int64_t)(img * a.H + gy) * a.W + gx) * a.p_ld) + c4);
+                    *reinterpret_cast<float4*>(Ps + (size_t)r * a.p_pitch + px * CA + c4 * 4) = v;
+                }
+            } else {
+                const int total = rows * cols * CA;
+                for (int i = tid; i < total; i += 256) {
+                    const int c = i % CA, px = (i / CA) % cols, r = i / (CA * cols);
+                    const int gy = y0 + r - a.pad_t, gx = x0 + px - a.pad_l;
+                    float v = 0.f;
+                    if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W)
+                        v = __ldg(a.P + ((int64_t)(img * a.H + gy) * a.W + gx) * a.p_ld + c);
+                    Ps[(size_t)r * a.p_pitch + px * CA + c] = v;
+                }
+            }
+        }
+        // ---- Q tile
+        if constexpr (CB % 4 == 0) {
+            const int v4 = CB / 4, total = a.TH * a.TW * v4;
+            for (int i = tid; i < total; i += 256) {
+                const int c4 = i % v4, px = (i / v4) % a.TW, r = i / (v4 * a.TW);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(
+                                           a.Q + ((int64_t)(img * a.H + y0 + r) * a.W + x0 + px) * a.q_ld) + c4);
+                *reinterpret_cast<float4*>(Qs + (size_t)r * a.q_pitch + px * CB + c4 * 4) = v;
+            }
+        } else {
+            const int total = a.TH * a.TW * CB;
+            for (int i = tid; i < total; i += 256) {
+                const int c = i % CB, px = (i / CB) % a.TW, r = i / (CB * a.TW);
+                Qs[(size_t)r * a.q_pitch + px * CB + c] =
+                    __ldg(a.Q + ((int64_t)(img * a.H + y0 + r) * a.W + x0 + px) * a.q_ld + c);
+            }
+        }
+        __syncthreads();
+        if (active) {
+            // window win[kh][kw][ta] = P at (row srow+kh, col x+kw) in halo coordinates
+            float win[3][3][TA];
+            const int xs = sseg * SEG;
+            const float* prow[3];
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) prow[kh] = Ps + (size_t)(srow + kh) * a.p_pitch + ca0;
+            const float* qrow = Qs + (size_t)srow * a.q_pitch + cb0;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 1; kw < 3; ++kw)
+#pragma unroll
+                    for (int u = 0; u < TA; ++u) win[kh][kw][u] = prow[kh][(xs + kw - 1) * CA + u];
+#pragma unroll 4
+            for (int x = xs; x < xs + SEG; ++x) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int u = 0; u < TA; ++u) {
+                        win[kh][0][u] = win[kh][1][u];
+                        win[kh][1][u] = win[kh][2][u];
+                    }
+                    if (TA == 2) {
+                        const float2 v = *reinterpret_cast<const float2*>(prow[kh] + (x + 2) * CA);
+                        win[kh][2][0] = v.x;
+                        win[kh][2][TA - 1] = v.y;
+                    } else {
+                        win[kh][2][0] = prow[kh][(x + 2) * CA];
+                    }
+                }
+                float q[TB];
+                if (TB == 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(qrow + x * CB);
+                    q[0] = v.x; q[TB > 1 ? 1 : 0] = v.y; q[TB > 2 ? 2 : 0] = v.z; q[TB > 3 ? 3 : 0] = v.w;
+                } else {
+                    q[0] = qrow[x * CB];
+                }
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                        for (int u = 0; u < TA; ++u)
+#pragma unroll
+                            for (int v = 0; v < TB; ++v)
+                                acc[kh][kw][u][v] = fmaf(win[kh][kw][u], q[v], acc[kh][kw][u][v]);
+            }
+        }
+    }
+    // ---- block reduction (shared atomics) then one global atomic per weight
+    __syncthreads();
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int u = 0; u < TA; ++u)
+#pragma unroll
+                for (int v = 0; v < TB; ++v)
+                    atomicAdd(&red[((kh * 3 + kw) * CA + ca0 + u) * CB + cb0 + v], acc[kh][kw][u][v]);
+    __syncthreads();
+    for (int i = tid; i < 9 * CA * CB; i += 256) atomicAdd(a.dw + i, red[i]);
+}
+
+template <int CA, int CB>
+static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
+    using C = ThinCfg<CA, CB>;
+    const int segs = a.TW / C::SEG;
+    int th = C::STREAMS / segs;
+    if (th > a.H) th = a.H;
+    while (th > 1 && a.H % th) --th;
+    // shared-memory budget: shrink the tile height until both tiles fit in ~96 KB
+    auto bytes = [&](int t) {
+        const int pp = ((a.TW + 2) * CA + 31) / 32 * 32 + CA, qp = (a.TW * CB + 31) / 32 * 32 + CB;
+        return (size_t)((((t + 2) * pp + 3) & ~3) + t * qp) * 4;
+    };
+    while (th > 1 && bytes(th) > 96 * 1024) { --th; while (th > 1 && a.H % th) --th; }
+    a.TH = th;
+    a.tiles_x = a.W / a.TW;
+    a.tiles_y = a.H / th;
+    a.ntiles = a.N * a.tiles_x * a.tiles_y;
+    // row pitch = CA (mod 32) floats: consecutive rows land on consecutive bank groups
+    a.p_pitch = ((a.TW + 2) * CA + 31) / 32 * 32 + CA;
+    a.q_pitch = (a.TW * CB + 31) / 32 * 32 + CB;
+    const size_t smem = bytes(th);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(thin_wgrad_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr = true;
+    }
+    int blocks_per_sm = (int)((200 * 1024) / (smem + 4096));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    if (blocks_per_sm > 4) blocks_per_sm = 4;
+    int grid = kNumSMs * blocks_per_sm;
+    if (grid > a.ntiles) grid = a.ntiles;
+    thin_wgrad_kernel<CA, CB><<<grid, 256, smem, st>>>(a);
+    return check_launch("thin_wgrad_kernel");
+}
+
+// DL4DS_E_UNSUPPORTED when the shape is outside this kernel's domain
+int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
+    if (w.KH != 3 || w.KW != 3 || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
+    if (!((w.Ca == 1 || w.Ca == 8) && (w.Cb == 1 || w.Cb == 8))) return DL4DS_E_UNSUPPORTED;
+    if (w.Wq % 32 || (w.Wq > 128 && w.Wq % 128)) return DL4DS_E_UNSUPPORTED;
+    if (w.Ca == 8 && (w.p_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15))) return DL4DS_E_UNSUPPORTED;
+    if (w.Cb == 8 && (w.q_ld % 4 || (reinterpret_cast<uintptr_t>(w.Q) & 15))) return DL4DS_E_UNSUPPORTED;
+    if (w.NQ < 16384) return DL4DS_E_UNSUPPORTED;          // tiny problems: the generic kernel is fine
+    ThinWgradArgs a;
+    a.P = w.P; a.Q = w.Q; a.dw = w.dw; a.p_ld = w.p_ld; a.q_ld = w.q_ld;
+    a.N = w.N; a.H = w.Hq; a.W = w.Wq; a.pad_t = w.pad_t; a.pad_l = w.pad_l;
+    a.TW = w.Wq > 128 ? 128 : w.Wq;
+    if (w.Ca == 8 && w.Cb == 8) return launch_thin<8, 8>(a, st);
+    if (w.Ca == 8 && w.Cb == 1) return launch_thin<8, 1>(a, st);
+    if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8>(a, st);
+    return launch_thin<1, 1>(a, st);
+}
+
+// -------------------------------------------------------------------------------------------------
+// vectorised bias / activation backward (+ space_to_depth un-shuffle)
+// -------------------------------------------------------------------------------------------------
+// block = (TX, PY): thread (tx, ty) owns float4 channel groups g = tx + k*TX (k < KS), pixels ty, ty+PY, ...
+template <int KS>
+__global__ void __launch_bounds__(256) bias_act_bwd_vec4_kernel(
+    const float* __restrict__ dy, int dy_ld, const float* __restrict__ y, int y_ld,
+    float* __restrict__ dz, int dz_ld, float* __restrict__ dbias,
+    int64_t n_pix, int Ho, int Wo, int C, int act, int r) {
+    __shared__ float4 red[256];
+    const int TX = blockDim.x, PY = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int G = C / 4;
+    float4 acc[KS];
+#pragma unroll
+    for (int k = 0; k < KS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int Cd = (r > 1) ? C / (r * r) : C;
+    for (int64_t p = (int64_t)blockIdx.x * PY + ty; p < n_pix; p += (int64_t)gridDim.x * PY) {
+        int n = 0, oy = 0, ox = 0;
+        if (r > 1) {
+            const int hw = Ho * Wo;
+            n = (int)(p / hw);
+            const int rem = (int)(p - (int64_t)n * hw);
+            oy = rem / Wo; ox = rem - oy * Wo;
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const int g = tx + k * TX;
+            if (g < G) {
+                const int c = g * 4;
+                float4 v;
+                if (r > 1) {
+                    const int grp = c / Cd, cc = c - grp * Cd;
+                    const int di = grp / r, dj = grp - di * r;
+                    const int64_t hp = ((int64_t)(n * Ho * r + oy * r + di)) * (Wo * r) + ox * r + dj;
+                    v = __ldg(reinterpret_cast<const float4*>(dy + hp * dy_ld + cc));
+                } else {
+                    v = __ldg(reinterpret_cast<const float4*>(dy + p * dy_ld + c));
+                    if (act != DL4DS_ACT_NONE) {
+                        const float4 o = __ldg(reinterpret_cast<const float4*>(y + p * y_ld + c));
+                        v.x *= act_grad_from_out(o.x, act); v.y *= act_grad_from_out(o.y, act);
+                        v.z *= act_grad_from_out(o.z, act); v.w *= act_grad_from_out(o.w, act);
+                    }
+                }
+                if (dz) *reinterpret_cast<float4*>(dz + p * dz_ld + c) = v;
+                acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+            }
+        }
+    }
+    if (dbias == nullptr) return;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        red[ty * TX + tx] = acc[k];
+        __syncthreads();
+        if (ty == 0) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < PY; ++j) {
+                const float4 t = red[j * TX + tx];
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
+            const int g = tx + k * TX;
+            if (g < G) {
+                atomicAdd(dbias + g * 4 + 0, s.x); atomicAdd(dbias + g * 4 + 1, s.y);
+                atomicAdd(dbias + g * 4 + 2, s.z); atomicAdd(dbias + g * 4 + 3, s.w);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int bias_act_bwd_vec4(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld, float* dbias,
+                      int64_t n_pix, int Ho, int Wo, int C, int act, int r, cudaStream_t st) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const int Cd = r > 1 ? C / (r * r) : C;
+    if (C % 4 || Cd % 4 || dy_ld % 4 || !al(dy)) return DL4DS_E_UNSUPPORTED;
+    if (dz && (dz_ld % 4 || !al(dz))) return DL4DS_E_UNSUPPORTED;
+    if (act != DL4DS_ACT_NONE && r == 1 && (y_ld % 4 || !al(y))) return DL4DS_E_UNSUPPORTED;
+    const int G = C / 4;
+    int TX = 1;
+    while (TX < G && TX < 64) TX <<= 1;
+    const int KS = (G + TX - 1) / TX;
+    if (KS > 4) return DL4DS_E_UNSUPPORTED;
+    const int PY = 256 / TX;
+    dim3 block(TX, PY);
+    int64_t want = (n_pix + PY * 4 - 1) / (PY * 4);
+    int grid = (int)(want > 8 * kNumSMs ? 8 * kNumSMs : (want < 1 ? 1 : want));
+#define LAUNCH_V4(K) bias_act_bwd_vec4_kernel<K><<<grid, block, 0, st>>>(dy, dy_ld, y, y_ld, dz, dz_ld, dbias, n_pix, Ho, Wo, C, act, r)
+    if (KS == 1) LAUNCH_V4(1);
+    else if (KS == 2) LAUNCH_V4(2);
+    else LAUNCH_V4(4);
+#undef LAUNCH_V4
+    return check_launch("bias_act_bwd_vec4");
+}
+
+}  // namespace dl4ds

@@ -298,3 +298,20 @@ def test_net_resnet_spc_tc(cuda, math):
     # gradient by ~1e-3 of its max; the per-op tests above (smooth graphs) hold 2e-4
     compare(m.fn, ofn, [(2, 32, 32, 1)], cuda, math=math, tol=5e-5, gtol=3e-3, input_grads=False)
     assert _tc_count() > n0 + 10
+
+
+# ------------------------------------------------------------------------------------------ narrow layers
+@pytest.mark.parametrize('cin,cout', [(8, 8), (8, 1), (1, 8), (1, 1)])
+@pytest.mark.parametrize('hw', [(128, 128), (64, 32), (16, 256)])
+def test_thin_wgrad(cuda, cin, cout, hw):
+    """Sliding-window CUDA-core wgrad of the HR-tail / stem layers (thin.cu) in every math mode."""
+    fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=3, act='tanh')
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=3), 'tanh'))
+    n = max(1, 16384 // (hw[0] * hw[1])) + 1
+    compare(fn, ofn, [(n, hw[0], hw[1], cin)], cuda)
+
+
+def test_bias_act_bwd_vec4_d2s(cuda):
+    fn = lambda cx, xs: cx.conv(xs[0], 'cv', 48 * 4, d2s=2)
+    ofn = _o(lambda p, xs: R.depth_to_space(R._conv(p, 'cv', xs[0], 48 * 4), 2))
+    compare(fn, ofn, [(2, 8, 8, 16)], cuda)
