@@ -342,7 +342,7 @@ def main():
         run_reference(args)
     else:
         if args.math == 'auto':
-            args.math = 'fp32'
+            args.math = 'tf32x3'       # tensor cores with the 3-term split: fp32-level parity
         run_native(args)
 
 

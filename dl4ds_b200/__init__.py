@@ -8,4 +8,5 @@ from .utils import (BACKBONE_BLOCKS, DROPOUT_VARIANTS, INTERPOLATION_METHODS, LO
 from .dataloader import DataGenerator, create_batch_hr_lr, create_pair_hr_lr  # noqa: F401
 from .nets import (net_pin, net_postupsampling, recnet_postupsampling, residual_discriminator,  # noqa: F401
                    unet_pin)
-from .training import SupervisedTrainer, Trainer  # noqa: F401
+from .training import CGANTrainer, SupervisedTrainer, Trainer  # noqa: F401
+from .inference import Predictor, predict  # noqa: F401

@@ -25,6 +25,22 @@ def _dist():
     return None
 
 
+def allreduce_sum_(flat, dist=None):
+    """In-place sum of a flat gradient buffer over the data-parallel group (the exchange step of
+    hvd.DistributedOptimizer / DistributedGradientTape, supervised.py:365, cgan.py:610-611).  The
+    average's 1/world is NOT applied here: it is folded into the Adam kernel's ``grad_scale``
+    (``world_grad_scale``).  NCCL for CUDA buffers, gloo for the CPU tests."""
+    d = dist if dist is not None else _dist()
+    if d is not None and d.get_world_size() > 1:
+        d.all_reduce(flat, op=d.ReduceOp.SUM)
+    return flat
+
+
+def world_grad_scale(dist=None):
+    d = dist if dist is not None else _dist()
+    return 1.0 / d.get_world_size() if d is not None else 1.0
+
+
 class LRSchedule:
     """float, or PiecewiseConstantDecay([boundary], [v0, v1]) (supervised.py:336-353): v0 while the
     optimizer iteration count <= boundary, else v1."""
@@ -86,9 +102,7 @@ class SupervisedStep:
         return 1
 
     def _allreduce(self):
-        d = _dist()
-        if d is not None:
-            d.all_reduce(self.arena.grad, op=d.ReduceOp.SUM)
+        allreduce_sum_(self.arena.grad)
 
     def _set_lr_t(self):
         self.arena.t += 1

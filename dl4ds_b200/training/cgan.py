@@ -1,0 +1,307 @@
+"""CGANTrainer, train_step, generator_loss, discriminator_loss -- dl4ds/training/cgan.py:30-639 on
+the CUDA engine.
+
+One ``train_step`` (cgan.py:575-639) = generator forward, discriminator on (LR, HR) and on
+(LR, generated), the four losses, two gradient computations and two Adam(beta_1=0.5) updates.  The
+reference differentiates D(fake) twice with its two tapes (once for the discriminator weights, once
+through to the generator); here the recorded D(fake) tape is replayed with the two seeds:
+    pass 1 (D loss):  seed dBCE(0,p_fake)/dp -> discriminator weight gradients (input gradient dropped)
+    pass 2 (G loss):  seed dBCE(1,p_fake)/dp -> input gradient only (``param_grads=False``) -> generator
+which is mathematically identical.  Dropout(0.4) inside the discriminator is active during training
+(``training=True``); its keep masks are drawn per call, as Keras does, and applied by ``dl4ds_mul``.
+Data parallelism: both gradient arenas are all-reduced (sum) and averaged inside Adam
+(``hvd.DistributedGradientTape``, cgan.py:608-611); after the first step theta/m/v of both models
+are broadcast from rank 0 (cgan.py:626-637).  The cGAN learning rate is NOT scaled by world size.
+
+Reference bug fixed: ``run`` passes an undefined ``aux_hr`` to ``train_step`` when
+``static_vars`` is None (cgan.py:346); here ``static_array=None`` is passed.
+"""
+import os
+
+import numpy as np
+
+from .. import nets
+from ..dataloader import create_batch_hr_lr
+from ..utils import POSTUPSAMPLING_METHODS, Timing
+from .base import Trainer
+
+DROPOUT_RATE = 0.4      # discriminator.py:77
+LAMBDA = 100.0          # cgan.py:526
+
+
+class Adam:
+    """tf.keras.optimizers.Adam(lr, beta_1) bound to a model's flat arena (theta / m / v / t)."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = learning_rate, beta_1, beta_2, epsilon
+
+    def apply(self, model, grad_scale=1.0):
+        from ..engine import adam_step
+        adam_step(model.arena, self.learning_rate, self.beta_1, self.beta_2, self.epsilon, grad_scale)
+
+
+def _bce_np(target, p, eps=1e-7):
+    p = np.clip(np.asarray(p, np.float64), eps, 1.0 - eps)
+    return float(-np.mean(target * np.log(p + eps) + (1.0 - target) * np.log(1.0 - p + eps)))
+
+
+def generator_loss(disc_generated_output, gen_output, target, gen_pxloss_function, lambda_scaling_factor=100):
+    """cgan.py:525-553 on host arrays (API parity; the training step computes these on the device)."""
+    gan = _bce_np(1.0, disc_generated_output)
+    d = np.asarray(target, np.float64) - np.asarray(gen_output, np.float64)
+    px = float(np.mean(np.abs(d))) if gen_pxloss_function in ('mae', None) else float(np.mean(d * d))
+    return gan + lambda_scaling_factor * px, gan, px
+
+
+def discriminator_loss(disc_real_output, disc_generated_output):
+    """cgan.py:556-572 on host arrays."""
+    return _bce_np(1.0, disc_real_output) + _bce_np(0.0, disc_generated_output)
+
+
+def _dev_inputs(model, arrays, dev):
+    ins, _, _ = model._prep_inputs(arrays, dev)
+    return ins
+
+
+def train_step(lr_array, hr_array, generator, discriminator, generator_optimizer, discriminator_optimizer,
+               epoch=0, gen_pxloss_function='mae', summary_writer=None, first_batch=False, static_array=None,
+               dropout_masks=None, dist=None):
+    """One cGAN optimisation step (cgan.py:575-639).  Arrays are host numpy / CUDA tensors (NHWC).
+    ``dropout_masks`` = (mask_real, mask_fake) of shape (B,1,1,F) overrides the random keep masks
+    (tests).  Returns (gen_total_loss, gen_gan_loss, gen_px_loss, disc_loss) as floats."""
+    import torch
+    from ..engine import Ctx, Var
+    G, D = generator, discriminator
+    G.to('cuda'); D.to('cuda')
+    dev = G.arena.device
+    f32 = lambda a: torch.as_tensor(np.asarray(a, np.float32) if not torch.is_tensor(a) else a).to(dev, torch.float32).contiguous()
+    lr_t, hr_t = f32(lr_array), f32(hr_array)
+    if lr_t.dim() != 4:
+        raise NotImplementedError('the spatio-temporal cGAN step is outside the B200 hot path')
+    st_t = f32(static_array) if static_array is not None else None
+    B = lr_t.shape[0]
+    nfeat = D.spec['dense1/kernel'][0]
+    if dropout_masks is None:
+        keep = 1.0 - DROPOUT_RATE
+        mk = [(torch.rand((B, 1, 1, nfeat), device=dev) < keep).to(torch.float32) / keep for _ in range(2)]
+    else:
+        mk = [f32(m) for m in dropout_masks]
+    world = dist.get_world_size() if dist is not None else 1
+
+    G.arena.zero_grad(); D.arena.zero_grad()
+    losses = torch.zeros(4, dtype=torch.float32, device=dev)        # gan, px, d_real, d_fake
+
+    # ---- forward: generator, D(real), D(fake)
+    cg = Ctx(G.arena, G.math, training=True)
+    gin = [cg.input(lr_t)] + ([cg.input(st_t)] if st_t is not None else [])
+    gen = G.fn(cg, gin)
+    cr = Ctx(D.arena, D.math, training=True)
+    p_real = D.fn(cr, [cr.input(lr_t), cr.input(hr_t), cr.input(mk[0])])
+    cf = Ctx(D.arena, D.math, training=True)
+    gen_in = Var(gen.buf, gen.off, gen.C, requires_grad=True)
+    p_fake = D.fn(cf, [cf.input(lr_t), gen_in, cf.input(mk[1])])
+
+    # ---- discriminator loss and weight gradients
+    cr.bce_loss(p_real, 1.0, loss_buf=losses[2:3])
+    cr.backward()
+    cf.bce_loss(p_fake, 0.0, loss_buf=losses[3:4])
+    cf.backward(keep_tape=True)
+    gen_in.grad = None                      # d(D loss)/d(gen) is not used by either optimizer
+    # ---- generator loss: through D(fake) to the generated field, then through G
+    cf.param_grads = False
+    cf.bce_loss(p_fake, 1.0, loss_buf=losses[0:1])
+    cf.backward()
+    if gen_in.grad is not None:
+        cg._give_grad(gen, gen_in.grad)
+    cg.pixel_loss(gen, cg.input(hr_t), gen_pxloss_function or 'mae', scale=LAMBDA, loss_buf=losses[1:2])
+    cg.backward()
+
+    # ---- exchange + Adam
+    if dist is not None and world > 1:
+        dist.all_reduce(G.arena.grad, op=dist.ReduceOp.SUM)
+        dist.all_reduce(D.arena.grad, op=dist.ReduceOp.SUM)
+    generator_optimizer.apply(G, 1.0 / world)
+    discriminator_optimizer.apply(D, 1.0 / world)
+    if dist is not None and world > 1 and first_batch:
+        for m in (G, D):
+            for t in (m.arena.theta, m.arena.m, m.arena.v):
+                dist.broadcast(t, src=0)
+    gan, pxs, dr, df = [float(v) for v in losses.cpu().numpy()]
+    px = pxs / LAMBDA
+    return gan + pxs, gan, px, dr + df
+
+
+class CGANTrainer(Trainer):
+    """Procedure for training the conditional adversarial models (same signature as cgan.py:33-64;
+    ``math`` and ``seed`` are additions)."""
+
+    def __init__(self, backbone, upsampling, data_train, data_test, data_train_lr=None, data_test_lr=None,
+                 predictors_train=None, predictors_test=None, scale=5, patch_size=None, time_window=True,
+                 loss='mae', epochs=60, batch_size=16, learning_rates=(2e-4, 2e-4), device='GPU',
+                 gpu_memory_growth=True, model_list=None, steps_per_epoch=None, interpolation='inter_area',
+                 static_vars=None, checkpoints_frequency=0, save=False, save_path=None, save_logs=False,
+                 save_loss_history=True, generator_params={}, discriminator_params={}, verbose=True,
+                 math='tf32x3', seed=None):
+        # `time_window=True` is the reference's default (sic); True is not > 1, i.e. a spatial model
+        super().__init__(backbone=backbone, upsampling=upsampling, data_train=data_train,
+                         data_train_lr=data_train_lr, time_window=time_window, loss=loss, batch_size=batch_size,
+                         patch_size=patch_size, scale=scale, device=device, gpu_memory_growth=gpu_memory_growth,
+                         verbose=verbose, model_list=model_list, save=save, save_path=save_path, show_plot=False)
+        self.data_test = data_test
+        self.data_test_lr = data_test_lr
+        self.predictors_train = predictors_train
+        if self.predictors_train is not None and not isinstance(self.predictors_train, list):
+            raise TypeError('`predictors_train` must be a list of ndarrays')
+        self.predictors_test = predictors_test
+        if self.predictors_test is not None and not isinstance(self.predictors_test, list):
+            raise TypeError('`predictors_test` must be a list of ndarrays')
+        self.epochs = epochs
+        self.learning_rates = learning_rates
+        self.steps_per_epoch = steps_per_epoch
+        self.interpolation = interpolation
+        self.static_vars = static_vars
+        if self.static_vars is not None:
+            for i in range(len(self.static_vars)):
+                self.static_vars[i] = getattr(self.static_vars[i], 'values', self.static_vars[i])
+        self.checkpoints_frequency = checkpoints_frequency
+        self.save_loss_history = save_loss_history
+        self.save_logs = save_logs
+        self.generator_params = dict(generator_params)
+        self.discriminator_params = dict(discriminator_params)
+        self.gentotal, self.gengan, self.gen_pxloss, self.disc = [], [], [], []
+        if self.time_window is not None and not self.model_is_spatiotemporal:
+            self.time_window = None
+        if self.model_is_spatiotemporal and self.time_window is None:
+            raise ValueError('The argument `time_window` must be a postive integer for spatio-temporal models')
+        self.math = math
+        self.seed = seed
+
+    def setup_model(self):
+        """cgan.py:173-262."""
+        n_channels = self.data_train.shape[-1]
+        n_aux_channels = 0
+        if self.model_is_spatiotemporal:
+            raise NotImplementedError('the spatio-temporal cGAN is outside the B200 hot path')
+        if self.static_vars is not None:
+            n_channels += len(self.static_vars)
+            n_aux_channels = len(self.static_vars)
+        if self.predictors_train is not None:
+            n_channels += len(self.predictors_train)
+        if self.patch_size is None:
+            lr_h, lr_w = int(self.data_train.shape[1] / self.scale), int(self.data_train.shape[2] / self.scale)
+            hr_h, hr_w = int(self.data_train.shape[1]), int(self.data_train.shape[2])
+        else:
+            lr_h = lr_w = int(self.patch_size / self.scale)
+            hr_h = hr_w = int(self.patch_size)
+        gp = self.generator_params
+        if self.upsampling in POSTUPSAMPLING_METHODS:
+            self.generator = nets.net_postupsampling(
+                backbone_block=self.backbone, upsampling=self.upsampling, scale=self.scale,
+                n_channels=n_channels, n_aux_channels=n_aux_channels, lr_size=(lr_h, lr_w), math=self.math, **gp)
+            d_size = (lr_h, lr_w)
+        elif self.backbone == 'unet':
+            self.generator = nets.unet_pin(backbone_block=self.backbone, n_channels=n_channels,
+                                           n_aux_channels=n_aux_channels, hr_size=(hr_h, hr_w),
+                                           math=self.math, **gp)
+            d_size = (hr_h, hr_w)
+        else:
+            self.generator = nets.net_pin(backbone_block=self.backbone, n_channels=n_channels,
+                                          n_aux_channels=n_aux_channels, hr_size=(hr_h, hr_w),
+                                          math=self.math, **gp)
+            d_size = (hr_h, hr_w)
+        # the reference passes lr_size=(lr_height, lr_width) also for 'pin', where the discriminator
+        # inputs live on the HR grid (the Keras Input shapes are then only nominal); here the grid
+        # the tensors really have is passed so that shape inference is exact
+        self.discriminator = nets.residual_discriminator(
+            n_channels=n_channels, scale=self.scale, upsampling=self.upsampling,
+            is_spatiotemporal=self.model_is_spatiotemporal, lr_size=d_size, math=self.math,
+            **self.discriminator_params)
+        seed = self.seed if self.seed is not None else int(np.random.randint(0, 2 ** 31 - 2))
+        dev = self.dp.torch_device
+        self.generator.to(dev).init_weights(seed)
+        self.discriminator.to(dev).init_weights(seed + 1)
+        if self.verbose == 1 and self.running_on_first_worker:
+            self.generator.summary()
+            self.discriminator.summary()
+
+    def run(self):
+        """cgan.py:264-444."""
+        self.timing = Timing(self.verbose)
+        self.setup_model()
+        if isinstance(self.learning_rates, (tuple, list)) and len(self.learning_rates) > 1:
+            genlr, dislr = self.learning_rates
+        else:
+            if isinstance(self.learning_rates, (tuple, list)):
+                self.learning_rates = self.learning_rates[0]
+            genlr = dislr = self.learning_rates
+        self.generator_optimizer = Adam(genlr, beta_1=0.5)
+        self.discriminator_optimizer = Adam(dislr, beta_1=0.5)
+        if self.predictors_train is not None:
+            self.predictors_train = np.concatenate([getattr(p, 'values', p) for p in self.predictors_train], axis=-1)
+        self.n = self.data_train.shape[0] - (self.time_window or 0)
+        self.indices_train = np.random.permutation(np.arange(self.n))
+        if self.steps_per_epoch is None:
+            self.steps_per_epoch = int(self.n / self.batch_size)
+        self.data_train = getattr(self.data_train, 'values', self.data_train)
+        self.data_train_lr = getattr(self.data_train_lr, 'values', self.data_train_lr)
+        chatty = bool(self.verbose) and self.running_on_first_worker
+        losses = (float('nan'),) * 4
+        for epoch in range(self.epochs):
+            for i in range(self.steps_per_epoch):
+                res = create_batch_hr_lr(
+                    self.indices_train, i, self.data_train, self.data_train_lr, upsampling=self.upsampling,
+                    scale=self.scale, batch_size=self.batch_size, patch_size=self.patch_size,
+                    time_window=self.time_window, static_vars=self.static_vars,
+                    predictors=self.predictors_train, interpolation=self.interpolation, time_metadata=None)
+                if self.static_vars is not None:
+                    [lr_array, aux_hr], [hr_array] = res
+                else:
+                    [lr_array], [hr_array] = res
+                    aux_hr = None
+                losses = train_step(
+                    lr_array, hr_array, generator=self.generator, discriminator=self.discriminator,
+                    generator_optimizer=self.generator_optimizer,
+                    discriminator_optimizer=self.discriminator_optimizer, epoch=epoch,
+                    gen_pxloss_function=self.lossf, summary_writer=None,
+                    first_batch=(epoch == 0 and i == 0), static_array=aux_hr, dist=self.dp.dist)
+            self.gentotal.append(losses[0]); self.gengan.append(losses[1])
+            self.gen_pxloss.append(losses[2]); self.disc.append(losses[3])
+            if chatty:
+                print('Epoch %d/%d - gen_total_loss: %.4f - gen_crosentr_loss: %.4f - gen_px_loss: %.4f - '
+                      'disc_loss: %.4f' % ((epoch + 1, self.epochs) + tuple(losses)))
+            if self.checkpoints_frequency > 0 and self.running_on_first_worker and \
+                    (epoch + 1) % self.checkpoints_frequency == 0:
+                ck = os.path.join(self.savecheckpoint_path, 'checkpoints')
+                os.makedirs(ck, exist_ok=True)
+                self.generator.save(os.path.join(ck, 'generator_epoch%d.npz' % (epoch + 1)))
+                self.discriminator.save(os.path.join(ck, 'discriminator_epoch%d.npz' % (epoch + 1)))
+        if self.save_loss_history and self.running_on_first_worker:
+            np.save(self.save_path + './losses.npy',
+                    np.array((self.gentotal, self.gengan, self.gen_pxloss, self.disc)))
+        self.timing.checktime()
+        # ---- loss on the test set (first worker)
+        if self.predictors_test is not None:
+            self.predictors_test = np.concatenate([getattr(p, 'values', p) for p in self.predictors_test], axis=-1)
+        self.data_test = getattr(self.data_test, 'values', self.data_test)
+        self.data_test_lr = getattr(self.data_test_lr, 'values', self.data_test_lr)
+        self.n_test = self.data_test.shape[0] - (self.time_window or 0)
+        self.indices_test = np.random.permutation(np.arange(self.n_test))
+        if self.running_on_first_worker:
+            res = create_batch_hr_lr(
+                self.indices_test, 0, self.data_test, self.data_test_lr, upsampling=self.upsampling,
+                scale=self.scale, batch_size=self.n_test, patch_size=self.patch_size,
+                time_window=self.time_window, static_vars=self.static_vars, predictors=self.predictors_test,
+                interpolation=self.interpolation, time_metadata=None)
+            if self.static_vars is not None:
+                [lr_array, aux_hr], [hr_array] = res
+                input_test = [lr_array, aux_hr]
+            else:
+                [lr_array], [hr_array] = res
+                input_test = [lr_array]
+            y_pred = self.generator.predict(input_test, batch_size=self.batch_size)
+            d = np.asarray(hr_array, np.float64) - y_pred
+            self.test_loss = float(np.mean(np.abs(d))) if self.lossf == 'mae' else float(np.mean(d * d))
+            if self.verbose:
+                print('\n%s on the test set: %s' % (self.lossf, self.test_loss))
+        self.timing.runtime()
+        self.save_results(self.generator, folder_prefix='cgan_')

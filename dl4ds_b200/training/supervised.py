@@ -43,7 +43,7 @@ class SupervisedTrainer(Trainer):
                  gpu_memory_growth=True, use_multiprocessing=False, model_list=None,
                  learning_rate=(1e-3, 1e-4), lr_decay_after=1e5, early_stopping=False, patience=6,
                  min_delta=0, show_plot=True, save=False, save_path=None, save_bestmodel=False,
-                 trained_model=None, trained_epochs=0, verbose=True, math='fp32', seed=None,
+                 trained_model=None, trained_epochs=0, verbose=True, math='tf32x3', seed=None,
                  **architecture_params):
         super().__init__(backbone=backbone, upsampling=upsampling, data_train=data_train,
                          data_train_lr=data_train_lr, time_window=time_window, loss=loss,

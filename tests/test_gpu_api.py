@@ -1,0 +1,104 @@
+"""GPU tests of the reference-facing API (SupervisedTrainer / CGANTrainer / Predictor) and of the
+training steps against the oracle (oracle/torch_ref.py)."""
+import numpy as np
+import pytest
+import torch
+
+from dl4ds_b200 import CGANTrainer, Predictor, SupervisedTrainer, nets
+from dl4ds_b200.training import cgan
+from oracle import torch_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, hw, seed=0):
+    return np.random.default_rng(seed).standard_normal((n, hw, hw, 1)).astype(np.float32)
+
+
+@pytest.mark.parametrize('math', ['fp32', 'tf32x3'])
+def test_supervised_step_sequence_matches_oracle(cuda, math):
+    """Five optimizer steps (fwd + MAE + bwd + Keras-Adam with PiecewiseConstantDecay) through
+    SupervisedTrainer.train_on_batch == the oracle's supervised_step, loss by loss."""
+    hr = _data(24, 64)
+    tr = SupervisedTrainer('resnet', 'spc', hr, hr[:8], hr[:8], scale=4, batch_size=8, epochs=1,
+                           learning_rate=(1e-3, 1e-4), lr_decay_after=3, verbose=False, math=math, seed=7,
+                           n_blocks=2)
+    tr.setup_datagen()
+    tr.setup_model()
+    w = {k: torch.from_numpy(v.copy()) for k, v in tr.model.get_weights().items()}
+    opt = R.TFAdam(list(w), lr=R.piecewise_constant(3, 1e-3, 1e-4))
+    fwd = lambda p, xs: R.net_postupsampling(p, xs, 'resnet', 'spc', 4, n_blocks=2)
+    for i in range(5):
+        (lr,), (y,) = tr.ds_train[i % len(tr.ds_train)]
+        loss = tr.train_on_batch([lr], y)
+        ref, _ = R.supervised_step(fwd, w, opt, [torch.from_numpy(lr)], torch.from_numpy(y))
+        assert abs(loss - ref) <= 2e-4 * max(1.0, abs(ref)), (i, loss, ref)
+    new = tr.model.get_weights()
+    worst = max(float(np.abs(new[k] - w[k].numpy()).max()) for k in w)
+    # Adam's first steps move a weight by ~lr*sign(g): a gradient whose sign is decided by rounding noise
+    # shifts that weight by up to 2*lr per step, so the bound scales with lr (1e-3), not with eps
+    assert worst <= (2e-4 if math == 'fp32' else 2e-3), worst
+
+
+def test_supervised_run_and_predictor(cuda, tmp_path):
+    hr = _data(40, 32, 1)
+    tr = SupervisedTrainer('resnet', 'spc', hr[:24], hr[24:32], hr[32:], scale=4, batch_size=8, epochs=3,
+                           learning_rate=1e-3, verbose=False, seed=3, n_blocks=2, save=True,
+                           save_path=str(tmp_path))
+    tr.run()
+    h = tr.fithist.history
+    assert len(h['loss']) == 3 and len(h['val_loss']) == 3 and np.isfinite(tr.test_loss)
+    assert h['loss'][-1] < h['loss'][0]                       # it learns
+    assert tr.model.name == 'resnet_spc'
+    out = Predictor(tr, hr[32:], scale=4, array_in_hr=True, batch_size=3).run()
+    assert out.shape == (8, 32, 32, 1) and out.dtype == np.float32
+    # same result as one big forward
+    lr = hr[32:].reshape(8, 8, 4, 8, 4, 1).mean(axis=(2, 4)).astype(np.float32)
+    full = tr.model.predict([lr], batch_size=8)
+    assert np.abs(out - full).max() <= 1e-6
+    out2, lr2 = Predictor(tr, lr, scale=4, array_in_hr=False, return_lr=True).run()
+    assert out2.shape == (8, 32, 32, 1) and lr2.shape == (8, 8, 8, 1)
+
+
+def test_cgan_step_matches_oracle(cuda):
+    """train_step (cgan.py:575-639): losses and BOTH weight updates after one step == oracle."""
+    rng = np.random.default_rng(11)
+    B, hw = 3, 16
+    G = nets.unet_pin('unet', 2, 1, (hw, hw), 1, 4, 2, math='fp32').to(cuda)
+    D = nets.residual_discriminator(2, 'pin', False, 4, (hw, hw), n_filters=4, n_res_blocks=1, math='fp32').to(cuda)
+    gw = R.init_weights(G.spec, seed=1, bias_scale=0.05)
+    dw = R.init_weights(D.spec, seed=2, bias_scale=0.05)
+    G.set_weights({k: v.numpy() for k, v in gw.items()})
+    D.set_weights({k: v.numpy() for k, v in dw.items()})
+    lr = rng.standard_normal((B, hw, hw, 2)).astype(np.float32)
+    hr = rng.standard_normal((B, hw, hw, 1)).astype(np.float32)
+    st = rng.standard_normal((B, hw, hw, 1)).astype(np.float32)
+    nfeat = D.spec['dense1/kernel'][0]
+    masks = [(rng.random((B, 1, 1, nfeat)) < 0.6).astype(np.float32) / 0.6 for _ in range(2)]
+    losses = cgan.train_step(lr, hr, G, D, cgan.Adam(2e-4, beta_1=0.5), cgan.Adam(2e-4, beta_1=0.5),
+                             gen_pxloss_function='mae', static_array=st, dropout_masks=masks)
+    gen_fn = lambda p, xs: R.unet_pin(p, xs, 4, 2)
+    disc_fn = lambda p, xs, m: R.residual_discriminator(p, xs, 'pin', 4, (hw, hw), n_filters=4, n_res_blocks=1,
+                                                        dropout_mask=m)
+    gopt, dopt = R.TFAdam(list(gw), lr=2e-4, beta_1=0.5), R.TFAdam(list(dw), lr=2e-4, beta_1=0.5)
+    ref, _, _ = R.cgan_step(gen_fn, disc_fn, gw, dw, gopt, dopt, torch.from_numpy(lr), torch.from_numpy(hr),
+                            torch.from_numpy(st), mask_real=torch.from_numpy(masks[0].reshape(B, nfeat)),
+                            mask_fake=torch.from_numpy(masks[1].reshape(B, nfeat)))
+    for a, b in zip(losses, ref):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (losses, ref)
+    for model, w in ((G, gw), (D, dw)):
+        new = model.get_weights()
+        worst = max(float(np.abs(new[k] - w[k].numpy()).max()) for k in w)
+        assert worst <= 5e-5, worst
+
+
+def test_cgan_trainer_runs(cuda, tmp_path):
+    hr = _data(12, 32, 5)
+    static = np.random.default_rng(6).standard_normal((32, 32)).astype(np.float32)
+    tr = CGANTrainer('unet', 'pin', hr[:8], hr[8:], scale=4, batch_size=4, epochs=2, static_vars=[static],
+                     generator_params=dict(n_filters=4, n_blocks=2, n_channels_out=1),
+                     discriminator_params=dict(n_filters=4, n_res_blocks=1), verbose=False, seed=2, time_window=None,
+                     save_loss_history=False, save_path=str(tmp_path))
+    tr.run()
+    assert len(tr.gentotal) == 2 and all(np.isfinite(v) for v in tr.gentotal + tr.disc)
+    assert np.isfinite(tr.test_loss) and tr.generator.name == 'unet_pin'
