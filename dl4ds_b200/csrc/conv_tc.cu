@@ -149,40 +149,42 @@ struct TcFwdParams {
     int kc, span, nchunks;
     uint32_t layout;
     int act, d2s_r, beta;
-    int stages, stage_bytes, a_bytes, b_bytes, tmem_cols;
+    int stages, stage_bytes, a_bytes, b_bytes, tmem_cols, ntiles;
+    int group, ngroups;     // kernel-tap / channel-chunk iterations per smem stage, stages per tile
 };
 
-constexpr int kTcThreads = 192;
-constexpr int kMaxStages = 8;
+constexpr int kTcThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kTcThreadsX3 = 448;     // + warps 6-13: tf32 hi/lo splitter
+constexpr int kMaxStages = 16;
 
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The smem
+// stage ring runs continuously across tiles and the accumulator is double-buffered in TMEM
+// (2 x Npad columns), so the epilogue of tile i overlaps the TMA / MMA work of tile i+1.
 template <bool X3>
-__global__ void __launch_bounds__(kTcThreads) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                                                                const TcFwdParams p) {
+__global__ void __launch_bounds__(X3 ? kTcThreadsX3 : kTcThreads, 2)
+conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[kMaxStages];
     __shared__ __align__(8) uint64_t bar_conv[kMaxStages];
     __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
-    __shared__ __align__(8) uint64_t bar_accum;
+    __shared__ __align__(8) uint64_t bar_tfull[2];
+    __shared__ __align__(8) uint64_t bar_tempty[2];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-
-    // tile coordinates
-    const int tile = blockIdx.x;
-    const int img = tile / p.tiles_per_img;
-    const int trem = tile - img * p.tiles_per_img;
-    const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-    const int y0 = ty * p.BH, x0 = tx * p.BW;
     const int nit = p.ntaps * p.nchunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_conv[s]), 128);
+            mbar_init(smem_u32(&bar_conv[s]), 256);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
-        mbar_init(smem_u32(&bar_accum), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bar_tfull[b]), 1);
+            mbar_init(smem_u32(&bar_tempty[b]), 128);
+        }
         fence_barrier_init();
         tma_prefetch_desc(&tmap_x);
     }
@@ -195,21 +197,35 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_fwd_kernel(const __grid_co
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t tx_bytes = (uint32_t)(p.a_bytes + p.b_bytes * (X3 ? 2 : 1));
-            for (int it = 0; it < nit; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-                const uint32_t full = smem_u32(&bar_full[s]);
-                mbar_arrive_expect_tx(full, tx_bytes);
-                const int tap = it / p.nchunks, ch = it - tap * p.nchunks;
-                const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
-                tma_load_4d(sa, &tmap_x, full, ch * p.kc, x0 + kw - p.pad_l, y0 + kh - p.pad_t, img);
-                const uint32_t sb = sa + (uint32_t)p.a_bytes * (X3 ? 2u : 1u);
-                const size_t woff = (size_t)it * p.Npad * p.kc;
-                bulk_load(sb, p.wp_hi + woff, (uint32_t)p.b_bytes, full);
-                if (X3) bulk_load(sb + (uint32_t)p.b_bytes, p.wp_lo + woff, (uint32_t)p.b_bytes, full);
+            const uint32_t it_bytes = (uint32_t)(p.a_bytes + p.b_bytes * (X3 ? 2 : 1));
+            const uint32_t a_lo_off = (uint32_t)(p.group * p.a_bytes);
+            const uint32_t b_off = a_lo_off * (X3 ? 2u : 1u);
+            const uint32_t b_lo_off = (uint32_t)(p.group * p.b_bytes);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int img = tile / p.tiles_per_img;
+                const int trem = tile - img * p.tiles_per_img;
+                const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+                const int y0 = ty * p.BH, x0 = tx * p.BW;
+                int ch = 0, kh = 0, kw = 0;
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const int it0 = g * p.group;
+                    const int n = min(p.group, nit - it0);
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_arrive_expect_tx(full, (uint32_t)n * it_bytes);
+                    const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                    for (int j = 0; j < n; ++j) {
+                        tma_load_4d(sa + (uint32_t)(j * p.a_bytes), &tmap_x, full, ch * p.kc, x0 + kw - p.pad_l,
+                                    y0 + kh - p.pad_t, img);
+                        if (++ch == p.nchunks) { ch = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+                    }
+                    const size_t woff = (size_t)it0 * p.Npad * p.kc;
+                    bulk_load(sa + b_off, p.wp_hi + woff, (uint32_t)(n * p.b_bytes), full);
+                    if (X3) bulk_load(sa + b_off + b_lo_off, p.wp_lo + woff, (uint32_t)(n * p.b_bytes), full);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -217,104 +233,136 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_fwd_kernel(const __grid_co
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(128, p.Npad, 0, 0);
             const uint32_t sbo = 8u * (uint32_t)p.span;
-            uint32_t accumulate = 0;
-            for (int it = 0; it < nit; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-                mbar_wait(smem_u32(X3 ? &bar_conv[s] : &bar_full[s]), ph);
+            int s = 0;
+            uint32_t ph = 0;
+            int tcount = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+                const int ab = tcount & 1;
+                mbar_wait(smem_u32(&bar_tempty[ab]), (uint32_t)(((tcount >> 1) & 1) ^ 1));
                 tc_fence_after();
-                const int ch = it % p.nchunks;
-                int ksteps = (p.Cin - ch * p.kc);
-                ksteps = (ksteps > p.kc ? p.kc : ksteps) >> 3;
-                const uint32_t sa = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
-                const uint32_t sb = sa + (uint32_t)p.a_bytes * (X3 ? 2u : 1u);
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t ko = (uint32_t)k * 32u;
-                    const uint64_t da = make_smem_desc(sa + ko, 16, sbo, p.layout);
-                    const uint64_t db = make_smem_desc(sb + ko, 16, sbo, p.layout);
-                    if (X3) {
-                        const uint64_t dal = make_smem_desc(sa + (uint32_t)p.a_bytes + ko, 16, sbo, p.layout);
-                        const uint64_t dbl = make_smem_desc(sb + (uint32_t)p.b_bytes + ko, 16, sbo, p.layout);
-                        umma_tf32(tmem_d, dal, db, idesc, accumulate);
-                        umma_tf32(tmem_d, da, dbl, idesc, 1u);
-                        umma_tf32(tmem_d, da, db, idesc, 1u);
-                    } else {
-                        umma_tf32(tmem_d, da, db, idesc, accumulate);
+                const uint32_t td = tmem_d + (uint32_t)(ab * p.Npad);
+                uint32_t accumulate = 0;
+                int ch = 0;
+                const uint32_t a_lo_off = (uint32_t)(p.group * p.a_bytes);
+                const uint32_t b_off = a_lo_off * (X3 ? 2u : 1u);
+                const uint32_t b_lo_off = (uint32_t)(p.group * p.b_bytes);
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const int n = min(p.group, nit - g * p.group);
+                    mbar_wait(smem_u32(X3 ? &bar_conv[s] : &bar_full[s]), ph);
+                    tc_fence_after();
+                    const uint32_t st0 = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                    for (int j = 0; j < n; ++j) {
+                        int ksteps = (p.Cin - ch * p.kc);
+                        ksteps = (ksteps > p.kc ? p.kc : ksteps) >> 3;
+                        const uint32_t sa = st0 + (uint32_t)(j * p.a_bytes);
+                        const uint32_t sb = st0 + b_off + (uint32_t)(j * p.b_bytes);
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint32_t ko = (uint32_t)k * 32u;
+                            const uint64_t da = make_smem_desc(sa + ko, 16, sbo, p.layout);
+                            const uint64_t db = make_smem_desc(sb + ko, 16, sbo, p.layout);
+                            if (X3) {
+                                const uint64_t dal = make_smem_desc(sa + a_lo_off + ko, 16, sbo, p.layout);
+                                const uint64_t dbl = make_smem_desc(sb + b_lo_off + ko, 16, sbo, p.layout);
+                                umma_tf32(td, dal, db, idesc, accumulate);
+                                umma_tf32(td, da, dbl, idesc, 1u);
+                                umma_tf32(td, da, db, idesc, 1u);
+                            } else {
+                                umma_tf32(td, da, db, idesc, accumulate);
+                            }
+                            accumulate = 1u;
+                        }
+                        if (++ch == p.nchunks) ch = 0;
                     }
-                    accumulate = 1u;
+                    umma_commit(smem_u32(&bar_empty[s]));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(smem_u32(&bar_empty[s]));
-            }
-            umma_commit(smem_u32(&bar_accum));
-        }
-    } else {
-        // ===================== operand splitter (x3) + epilogue =====================
-        const int et = threadIdx.x - 64;           // 0..127
-        if (X3) {
-            const int units = p.kc / 4;            // float4 per thread per stage (A tile = 128 rows x span)
-            for (int it = 0; it < nit; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-                mbar_wait(smem_u32(&bar_full[s]), ph);
-                uint8_t* a_hi = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)s * p.stage_bytes;
-                uint8_t* a_lo = a_hi + p.a_bytes;
-                for (int u = 0; u < units; ++u) {
-                    const int off = (et + u * 128) * 16;
-                    const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
-                    float4 h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                    *reinterpret_cast<float4*>(a_hi + off) = h;
-                    *reinterpret_cast<float4*>(a_lo + off) = l;
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(smem_u32(&bar_conv[s]));
+                umma_commit(smem_u32(&bar_tfull[ab]));
             }
         }
-        mbar_wait(smem_u32(&bar_accum), 0);
-        tc_fence_after();
-
+    } else if (warp < 6) {
+        // ===================== epilogue (warps 2-5) =====================
         const int q = warp & 3;                     // TMEM lane quadrant this warp may read
         const int row = q * 32 + lane;
         const int ry = row / p.BW, rx = row - ry * p.BW;
-        const int oy = y0 + ry, ox = x0 + rx;
-        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16);
         const int r = p.d2s_r;
-        const int64_t pix = ((int64_t)img * p.H + oy) * p.W + ox;
-        const float* resp = p.res ? p.res + pix * p.res_ld : nullptr;
-        float* yp = p.y + pix * p.y_ld;
         const int Cd = p.Cout / (r * r);
-        for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + (uint32_t)c0, v);
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+            const int ab = tcount & 1;
+            const int img = tile / p.tiles_per_img;
+            const int trem = tile - img * p.tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int oy = ty * p.BH + ry, ox = tx * p.BW + rx;
+            const int64_t pix = ((int64_t)img * p.H + oy) * p.W + ox;
+            const float* resp = p.res ? p.res + pix * p.res_ld : nullptr;
+            float* yp = p.y + pix * p.y_ld;
+            mbar_wait(smem_u32(&bar_tfull[ab]), (uint32_t)((tcount >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.Npad);
+            for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const int co = c0 + j;
-                if (co >= p.Cout) continue;
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                if (resp) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(resp + co));
-                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
-                o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
-                if (r == 1) {
-                    float4* dst = reinterpret_cast<float4*>(yp + co);
-                    if (p.beta) {
-                        const float4 old = *dst;
-                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                for (int j = 0; j < 16; j += 4) {
+                    const int co = c0 + j;
+                    if (co >= p.Cout) continue;
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
-                    *dst = o;
-                } else {
-                    const int g = co / Cd, c = co - g * Cd;
-                    const int di = g / r, dj = g - di * r;
-                    const int64_t hp = ((int64_t)img * p.H * r + (oy * r + di)) * ((int64_t)p.W * r) + ox * r + dj;
-                    *reinterpret_cast<float4*>(p.y + hp * p.y_ld + c) = o;
+                    if (resp) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(resp + co));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
+                    o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
+                    if (r == 1) {
+                        float4* dst = reinterpret_cast<float4*>(yp + co);
+                        if (p.beta) {
+                            const float4 old = *dst;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *dst = o;
+                    } else {
+                        const int g = co / Cd, c = co - g * Cd;
+                        const int di = g / r, dj = g - di * r;
+                        const int64_t hp = ((int64_t)img * p.H * r + (oy * r + di)) * ((int64_t)p.W * r) + ox * r + dj;
+                        *reinterpret_cast<float4*>(p.y + hp * p.y_ld + c) = o;
+                    }
                 }
+            }
+            // accumulator buffer drained: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bar_tempty[ab]));
+        }
+    } else if (X3) {
+        // ===================== operand splitter (warps 6-13, x3 mode) =====================
+        const int et = threadIdx.x - 192;          // 0..255
+        int s = 0;
+        uint32_t ph = 0;
+        uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+        const int a_lo_off = p.group * p.a_bytes;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            for (int g = 0; g < p.ngroups; ++g) {
+                const int n = min(p.group, nit - g * p.group);
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                uint8_t* a_hi = smem_al + (size_t)s * p.stage_bytes;
+                uint8_t* a_lo = a_hi + a_lo_off;
+                const int units = n * (p.a_bytes >> 4);
+#pragma unroll 2
+                for (int u = et; u < units; u += 256) {
+                    const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 16);
+                    float4 h, l;
+                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y);
+                    l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    *reinterpret_cast<float4*>(a_hi + u * 16) = h;
+                    *reinterpret_cast<float4*>(a_lo + u * 16) = l;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(smem_u32(&bar_conv[s]));
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     }
@@ -427,28 +475,36 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     p.act = a.act; p.d2s_r = a.d2s_r; p.beta = a.beta;
     p.a_bytes = 128 * c.span;
     p.b_bytes = p.Npad * c.span;
-    p.stage_bytes = (p.a_bytes + p.b_bytes) * (x3 ? 2 : 1);
-    int stages = (100 * 1024) / p.stage_bytes;             // <= ~100 KB so that two CTAs share an SM
+    const int nit = p.ntaps * p.nchunks;
+    const int it_bytes = (p.a_bytes + p.b_bytes) * (x3 ? 2 : 1);
+    int group = (32 * 1024) / it_bytes;                    // ~32 KB per stage: few barrier round trips per tile
+    if (group < 1) group = 1;
+    if (group > nit) group = nit;
+    p.group = group;
+    p.ngroups = (nit + group - 1) / group;
+    p.stage_bytes = group * it_bytes;
+    int cols = 32;
+    while (cols < 2 * p.Npad) cols *= 2;                   // double-buffered accumulator
+    p.tmem_cols = cols;
+    // persistent CTAs: two per SM when TMEM (<= 256 columns each) allows, else one with all the smem
+    const int ctas_per_sm = cols <= 256 ? 2 : 1;
+    int stages = ((ctas_per_sm == 2 ? 104 : 208) * 1024) / p.stage_bytes;
     if (stages < 2) stages = 2;
     if (stages > kMaxStages) stages = kMaxStages;
-    const int nit = p.ntaps * p.nchunks;
-    if (stages > nit) stages = nit;
     p.stages = stages;
-    int cols = 32;
-    while (cols < p.Npad) cols *= 2;
-    p.tmem_cols = cols;
     const size_t smem = (size_t)stages * p.stage_bytes + 1024;
     DL4DS_REQUIRE(smem <= 220 * 1024, DL4DS_E_UNSUPPORTED, "conv2d_fwd_tc: stage too large");
     const CUtensorMap* tm = get_tensor_map_nhwc(a.x, a.x_ld, a.N, a.H, a.W, a.Cin, c.kc, p.BW, p.BH, c.swz);
     if (!tm) return DL4DS_E_CUDA;
-    const int grid = a.N * p.tiles_per_img;
+    p.ntiles = a.N * p.tiles_per_img;
+    const int grid = p.ntiles < ctas_per_sm * kNumSMs ? p.ntiles : ctas_per_sm * kNumSMs;
     static size_t attr_set[2] = {0, 0};
     if (x3) {
         if (smem > attr_set[1]) {
             cudaFuncSetAttribute(conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
             attr_set[1] = 221 * 1024;
         }
-        conv_tc_fwd_kernel<true><<<grid, kTcThreads, smem, st>>>(*tm, p);
+        conv_tc_fwd_kernel<true><<<grid, kTcThreadsX3, smem, st>>>(*tm, p);
     } else {
         if (smem > attr_set[0]) {
             cudaFuncSetAttribute(conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
