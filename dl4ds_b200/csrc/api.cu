@@ -77,6 +77,10 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
     a.M = N * Ho * Wo; a.HoWo = Ho * Wo;
     a.vec = (Cin % 4 == 0) && (x_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {   // narrow 3x3 layers (Cin, Cout in {1, 8}): HBM-bound, exact-fp32 direct kernel in every math mode
+        int rc = conv2d_fwd_thin(a, st);
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+    }
     if (math_mode != DL4DS_MATH_FP32) {
         int rc = conv2d_fwd_tc(a, math_mode, ws, prepacked, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;

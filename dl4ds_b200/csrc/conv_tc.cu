@@ -123,7 +123,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 h[j] = tf32_rna(v[j]);
-                l[j] = tf32_rna(v[j] - h[j]);
+                l[j] = v[j] - h[j];
             }
             *reinterpret_cast<float4*>(hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
@@ -355,8 +355,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                     const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 16);
                     float4 h, l;
                     h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y);
-                    l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
                     *reinterpret_cast<float4*>(a_hi + u * 16) = h;
                     *reinterpret_cast<float4*>(a_lo + u * 16) = l;
                 }
@@ -728,7 +727,7 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
                     if (X3) {
                         const float h = tf32_rna(vv[r]);
                         *reinterpret_cast<float*>(dst + off) = h;
-                        *reinterpret_cast<float*>(dst + p.op_bytes + off) = tf32_rna(vv[r] - h);
+                        *reinterpret_cast<float*>(dst + p.op_bytes + off) = vv[r] - h;
                     } else {
                         *reinterpret_cast<float*>(dst + off) = vv[r];
                     }

@@ -138,10 +138,18 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a
     return d;
 }
 
+// round-to-nearest (ties away from zero in magnitude) onto the tf32 grid with two integer ops: add half
+// an ulp of the 10-bit mantissa, clear the 13 low bits.  (cvt.rna.tf32.f32 expands to ~8 SASS
+// instructions with Inf/NaN handling; the operand splitters run this per element.)  Inf/NaN inputs
+// are not expected on this path.
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+// hi/lo split for the 3xTF32 scheme: x = hi + lo exactly; the tensor core truncates lo to tf32
+// (|lo| <= 2^-12 |x|, so the truncation error is <= 2^-22 |x|).
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+    hi = tf32_rna(x);
+    lo = x - hi;
 }
 
 // channel-chunk geometry shared by the pack kernel, the tensor maps and the UMMA descriptors:

@@ -229,6 +229,141 @@ int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// thin 3x3 direct convolution (forward, and input gradient = same op with flipped/transposed weights)
+// for Cin, Cout in {1, 8}: one warp per output row, lane t owns pixels t, t+32, ... of the row (so every
+// shared-memory access of a warp touches 32 consecutive pixels: conflict-free), all Cout outputs in
+// registers; the weights sit in shared memory and are read as warp-uniform broadcasts.
+// -------------------------------------------------------------------------------------------------
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) thin_conv_kernel(const ConvArgs p, int TW, int tiles_x, int tiles_y) {
+    constexpr int TH = 8;
+    extern __shared__ float sm[];
+    __shared__ __align__(16) float ws[9 * CI * CO];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pitch = (TW + 2) * CI + (CI == 8 ? 8 : 1);      // row pitch (floats), rows land on distinct banks
+    for (int i = tid; i < 9 * CI * CO; i += 256) {
+        const int co = i % CO, ci = (i / CO) % CI, tap = i / (CO * CI);
+        ws[i] = (p.wmode == DL4DS_W_HWIO) ? __ldg(p.w + (tap * CI + ci) * CO + co)
+                                           : __ldg(p.w + ((8 - tap) * CO + co) * CI + ci);
+    }
+    const int tile = blockIdx.x;
+    const int img = tile / (tiles_x * tiles_y);
+    const int trem = tile - img * tiles_x * tiles_y;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    // ---- input tile with halo
+    {
+        const int cols = TW + 2, rows = TH + 2;
+        if constexpr (CI % 4 == 0) {
+            const int v4 = CI / 4, total = rows * cols * v4;
+            for (int i = tid; i < total; i += 256) {
+                const int c4 = i % v4, px = (i / v4) % cols, r = i / (v4 * cols);
+                const int gy = y0 + r - p.pad_t, gx = x0 + px - p.pad_l;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+                    v = __ldg(reinterpret_cast<const float4*>(p.x + ((int64_t)(img * p.H + gy) * p.W + gx) * p.x_ld) + c4);
+                *reinterpret_cast<float4*>(sm + (size_t)r * pitch + px * CI + c4 * 4) = v;
+            }
+        } else {
+            const int total = rows * cols * CI;
+            for (int i = tid; i < total; i += 256) {
+                const int c = i % CI, px = (i / CI) % cols, r = i / (CI * cols);
+                const int gy = y0 + r - p.pad_t, gx = x0 + px - p.pad_l;
+                float v = 0.f;
+                if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+                    v = __ldg(p.x + ((int64_t)(img * p.H + gy) * p.W + gx) * p.x_ld + c);
+                sm[(size_t)r * pitch + px * CI + c] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int oy = y0 + warp;
+    if (oy >= p.H) return;
+    const int npx = TW / 32;                                 // pixels per lane (1..4)
+    for (int j = 0; j < npx; ++j) {
+        const int xl = lane + 32 * j;
+        float acc[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const float* row = sm + (size_t)(warp + kh) * pitch + xl * CI;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                float in[CI];
+                if constexpr (CI == 8) {
+                    const float4 a = *reinterpret_cast<const float4*>(row + kw * CI);
+                    const float4 b = *reinterpret_cast<const float4*>(row + kw * CI + 4);
+                    in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w;
+                    in[4] = b.x; in[5] = b.y; in[6] = b.z; in[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CI; ++c) in[c] = row[kw * CI + c];
+                }
+                const float* wt = ws + (kh * 3 + kw) * CI * CO;
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) {
+                    if constexpr (CO == 8) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wt + ci * CO);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wt + ci * CO + 4);
+                        acc[0] = fmaf(in[ci], w0.x, acc[0]); acc[1] = fmaf(in[ci], w0.y, acc[1]);
+                        acc[2] = fmaf(in[ci], w0.z, acc[2]); acc[3] = fmaf(in[ci], w0.w, acc[3]);
+                        acc[4] = fmaf(in[ci], w1.x, acc[4]); acc[5] = fmaf(in[ci], w1.y, acc[5]);
+                        acc[6] = fmaf(in[ci], w1.z, acc[6]); acc[7] = fmaf(in[ci], w1.w, acc[7]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CO; ++c) acc[c] = fmaf(in[ci], wt[ci * CO + c], acc[c]);
+                    }
+                }
+            }
+        }
+        // ---- epilogue: bias, residual, activation, (accumulating) store
+        const int64_t pix = ((int64_t)img * p.H + oy) * p.W + x0 + xl;
+        float* yp = p.y + pix * p.y_ld;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+            float v = acc[c];
+            if (p.bias) v += __ldg(p.bias + c);
+            if (p.res) v += __ldg(p.res + pix * p.res_ld + c);
+            v = apply_act(v, p.act);
+            if (p.beta) v += yp[c];
+            acc[c] = v;
+        }
+        if (CO == 8 && (p.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0)) {
+            *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(yp + 4) = make_float4(acc[4 % CO], acc[5 % CO], acc[6 % CO], acc[7 % CO]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CO; ++c) yp[c] = acc[c];
+        }
+    }
+}
+
+template <int CI, int CO>
+static int launch_thin_conv(const ConvArgs& a, cudaStream_t st) {
+    const int TW = a.W > 128 ? 128 : a.W;
+    const int tiles_x = a.W / TW, tiles_y = (a.H + 7) / 8;
+    const int pitch = (TW + 2) * CI + (CI == 8 ? 8 : 1);
+    const size_t smem = (size_t)10 * pitch * 4;
+    thin_conv_kernel<CI, CO><<<a.N * tiles_x * tiles_y, 256, smem, st>>>(a, TW, tiles_x, tiles_y);
+    return check_launch("thin_conv_kernel");
+}
+
+// DL4DS_E_UNSUPPORTED when the shape is outside this kernel's domain
+int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
+    if (a.KH != 3 || a.KW != 3 || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
+        return DL4DS_E_UNSUPPORTED;
+    if (!((a.Cin == 1 || a.Cin == 8) && (a.Cout == 1 || a.Cout == 8))) return DL4DS_E_UNSUPPORTED;
+    if (a.W % 32 || (a.W > 128 && a.W % 128)) return DL4DS_E_UNSUPPORTED;
+    if (a.Cin == 8 && !a.vec) return DL4DS_E_UNSUPPORTED;
+    if ((int64_t)a.N * a.H * a.W < 16384) return DL4DS_E_UNSUPPORTED;
+    if (a.Cin == 8 && a.Cout == 8) return launch_thin_conv<8, 8>(a, st);
+    if (a.Cin == 8 && a.Cout == 1) return launch_thin_conv<8, 1>(a, st);
+    if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8>(a, st);
+    return launch_thin_conv<1, 1>(a, st);
+}
+
+// -------------------------------------------------------------------------------------------------
 // vectorised bias / activation backward (+ space_to_depth un-shuffle)
 // -------------------------------------------------------------------------------------------------
 // block = (TX, PY): thread (tx, ty) owns float4 channel groups g = tx + k*TX (k < KS), pixels ty, ty+PY, ...

@@ -253,7 +253,7 @@ def _tc_count():
     ((2, 8, 16, 24), 40, 3, None),          # Cin 24 -> three 8-channel chunks; Cout 40 -> Npad 48
     ((1, 32, 32, 48), 48, 3, 'tanh'),       # SW64 chunks
     ((1, 64, 64, 16), 48, 1, 'relu'),       # 1x1
-    ((1, 128, 128, 8), 8, 3, None),         # HR tail shape: one row per tile, Npad 16 > Cout 8
+    ((1, 128, 128, 16), 8, 3, None),        # one row per tile, Npad 16 > Cout 8
     ((2, 16, 8, 32), 64, 5, 'sigmoid'),     # SW128 chunks, 5x5, BW=8 BH=16
     ((1, 2, 256, 8), 8, 3, 'relu'),         # W > 128: two tiles per row
 ])
@@ -304,7 +304,7 @@ def test_net_resnet_spc_tc(cuda, math):
 @pytest.mark.parametrize('cin,cout', [(8, 8), (8, 1), (1, 8), (1, 1)])
 @pytest.mark.parametrize('hw', [(128, 128), (64, 32), (16, 256)])
 def test_thin_wgrad(cuda, cin, cout, hw):
-    """Sliding-window CUDA-core wgrad of the HR-tail / stem layers (thin.cu) in every math mode."""
+    """Direct conv (fwd + dgrad) and sliding-window wgrad of the HR-tail / stem layers (thin.cu)."""
     fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=3, act='tanh')
     ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=3), 'tanh'))
     n = max(1, 16384 // (hw[0] * hw[1])) + 1
@@ -315,3 +315,10 @@ def test_bias_act_bwd_vec4_d2s(cuda):
     fn = lambda cx, xs: cx.conv(xs[0], 'cv', 48 * 4, d2s=2)
     ofn = _o(lambda p, xs: R.depth_to_space(R._conv(p, 'cv', xs[0], 48 * 4), 2))
     compare(fn, ofn, [(2, 8, 8, 16)], cuda)
+
+
+def test_thin_conv_residual_bias_relu(cuda):
+    def fn(c, xs):
+        return c.conv(xs[0], 'cv', 8, act='relu', res=xs[1])
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], 8) + xs[1], 'relu'))
+    compare(fn, ofn, [(2, 96, 128, 8), (2, 96, 128, 8)], cuda)
