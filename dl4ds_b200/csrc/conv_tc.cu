@@ -18,6 +18,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = operand splitter (x3 mode) during the main loop, then epilogue.
+#include <stdlib.h>
+
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -151,10 +153,12 @@ struct TcFwdParams {
     int act, d2s_r, beta;
     int stages, stage_bytes, a_bytes, b_bytes, tmem_cols, ntiles;
     int group, ngroups;     // kernel-tap / channel-chunk iterations per smem stage, stages per tile
+    int a_tmem;             // x3: split activations go to TMEM (A operand from TMEM), not back to smem
+    int tmem_a_off;         // first TMEM column of the A ring (stage s, iteration j: + (s*group+j)*2*kc)
 };
 
-constexpr int kTcThreads = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kTcThreadsX3 = 448;     // + warps 6-13: tf32 hi/lo splitter
+constexpr int kTcThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kTcThreadsX3 = 448;     // + warps 10-13: tf32 hi/lo splitter
 constexpr int kMaxStages = 16;
 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The smem
@@ -170,20 +174,22 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
     __shared__ __align__(8) uint64_t bar_tfull[2];
     __shared__ __align__(8) uint64_t bar_tempty[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int nit = p.ntaps * p.nchunks;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_conv[s]), 256);
+            mbar_init(smem_u32(&bar_conv[s]), 128);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bar_tfull[b]), 1);
-            mbar_init(smem_u32(&bar_tempty[b]), 128);
+            mbar_init(smem_u32(&bar_tempty[b]), 256);
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmap_x);
@@ -199,7 +205,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
         if (lane == 0) {
             const uint32_t it_bytes = (uint32_t)(p.a_bytes + p.b_bytes * (X3 ? 2 : 1));
             const uint32_t a_lo_off = (uint32_t)(p.group * p.a_bytes);
-            const uint32_t b_off = a_lo_off * (X3 ? 2u : 1u);
+            const uint32_t b_off = a_lo_off * ((X3 && !p.a_tmem) ? 2u : 1u);
             const uint32_t b_lo_off = (uint32_t)(p.group * p.b_bytes);
             int s = 0;
             uint32_t ph = 0;
@@ -244,7 +250,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 uint32_t accumulate = 0;
                 int ch = 0;
                 const uint32_t a_lo_off = (uint32_t)(p.group * p.a_bytes);
-                const uint32_t b_off = a_lo_off * (X3 ? 2u : 1u);
+                const uint32_t b_off = a_lo_off * ((X3 && !p.a_tmem) ? 2u : 1u);
                 const uint32_t b_lo_off = (uint32_t)(p.group * p.b_bytes);
                 for (int g = 0; g < p.ngroups; ++g) {
                     const int n = min(p.group, nit - g * p.group);
@@ -256,11 +262,18 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                         ksteps = (ksteps > p.kc ? p.kc : ksteps) >> 3;
                         const uint32_t sa = st0 + (uint32_t)(j * p.a_bytes);
                         const uint32_t sb = st0 + b_off + (uint32_t)(j * p.b_bytes);
+                        const uint32_t ta = tmem_d + (uint32_t)(p.tmem_a_off + (s * p.group + j) * 2 * p.kc);
                         for (int k = 0; k < ksteps; ++k) {
                             const uint32_t ko = (uint32_t)k * 32u;
                             const uint64_t da = make_smem_desc(sa + ko, 16, sbo, p.layout);
                             const uint64_t db = make_smem_desc(sb + ko, 16, sbo, p.layout);
-                            if (X3) {
+                            if (X3 && p.a_tmem) {
+                                const uint64_t dbl = make_smem_desc(sb + b_lo_off + ko, 16, sbo, p.layout);
+                                const uint32_t ah = ta + (uint32_t)(k * 8), al = ah + (uint32_t)p.kc;
+                                umma_tf32_ts(td, al, db, idesc, accumulate);
+                                umma_tf32_ts(td, ah, dbl, idesc, 1u);
+                                umma_tf32_ts(td, ah, db, idesc, 1u);
+                            } else if (X3) {
                                 const uint64_t dal = make_smem_desc(sa + a_lo_off + ko, 16, sbo, p.layout);
                                 const uint64_t dbl = make_smem_desc(sb + b_lo_off + ko, 16, sbo, p.layout);
                                 umma_tf32(td, dal, db, idesc, accumulate);
@@ -279,9 +292,12 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 umma_commit(smem_u32(&bar_tfull[ab]));
             }
         }
-    } else if (warp < 6) {
-        // ===================== epilogue (warps 2-5) =====================
-        const int q = warp & 3;                     // TMEM lane quadrant this warp may read
+    } else if (warp < 10) {
+        // ===================== epilogue (warps 2-9) =====================
+        // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant take alternate
+        // 16-column blocks.  Thread = one output pixel (TMEM lane), 16 consecutive channels per block.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int ry = row / p.BW, rx = row - ry * p.BW;
         const int r = p.d2s_r;
@@ -294,27 +310,33 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int oy = ty * p.BH + ry, ox = tx * p.BW + rx;
             const int64_t pix = ((int64_t)img * p.H + oy) * p.W + ox;
-            const float* resp = p.res ? p.res + pix * p.res_ld : nullptr;
-            float* yp = p.y + pix * p.y_ld;
+            const float* __restrict__ resp = p.res ? p.res + pix * p.res_ld : nullptr;
+            float* __restrict__ yp = p.y + pix * p.y_ld;
+            // depth_to_space: HR pixel (oy*r+di, ox*r+dj) receives channels [g*Cd, (g+1)*Cd), g = di*r+dj
+            const int64_t hr_row0 = ((int64_t)img * p.H * r + (int64_t)oy * r) * ((int64_t)p.W * r) + (int64_t)ox * r;
             mbar_wait(smem_u32(&bar_tfull[ab]), (uint32_t)((tcount >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.Npad);
-            for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+            for (int c0 = half * 16; c0 < p.Npad; c0 += 32) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)c0, v);
+                if (c0 >= p.Cout) continue;
+                float4 rs[4];
+                if (resp) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const int co = c0 + j;
-                    if (co >= p.Cout) continue;
-                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + co));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
-                    if (resp) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(resp + co));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        rs[j] = (c0 + 4 * j < p.Cout) ? __ldg(reinterpret_cast<const float4*>(resp + c0) + j)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                int g = 0, cg = c0;
+                if (r > 1) { g = c0 / Cd; cg = c0 - g * Cd; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int co = c0 + 4 * j;
+                    if (co >= p.Cout) break;
+                    const float4 b = *reinterpret_cast<const float4*>(&bias_s[co]);
+                    float4 o = make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+                    if (resp) { o.x += rs[j].x; o.y += rs[j].y; o.z += rs[j].z; o.w += rs[j].w; }
                     o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
                     o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
                     if (r == 1) {
@@ -325,10 +347,11 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                         }
                         *dst = o;
                     } else {
-                        const int g = co / Cd, c = co - g * Cd;
+                        if (cg >= Cd) { cg -= Cd; ++g; }
                         const int di = g / r, dj = g - di * r;
-                        const int64_t hp = ((int64_t)img * p.H * r + (oy * r + di)) * ((int64_t)p.W * r) + ox * r + dj;
-                        *reinterpret_cast<float4*>(p.y + hp * p.y_ld + c) = o;
+                        const int64_t hp = hr_row0 + (int64_t)di * p.W * r + dj;
+                        *reinterpret_cast<float4*>(p.y + hp * p.y_ld + cg) = o;
+                        cg += 4;
                     }
                 }
             }
@@ -337,21 +360,63 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
             mbar_arrive(smem_u32(&bar_tempty[ab]));
         }
     } else if (X3) {
-        // ===================== operand splitter (warps 6-13, x3 mode) =====================
-        const int et = threadIdx.x - 192;          // 0..255
+        // ===================== operand splitter (warps 10-13, x3 mode) =====================
+        const int et = threadIdx.x - 320;          // 0..127
         int s = 0;
         uint32_t ph = 0;
         uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
         const int a_lo_off = p.group * p.a_bytes;
+        int pending = -1;                          // TS mode: stage whose TMEM stores are issued but not yet published
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             for (int g = 0; g < p.ngroups; ++g) {
                 const int n = min(p.group, nit - g * p.group);
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 uint8_t* a_hi = smem_al + (size_t)s * p.stage_bytes;
                 uint8_t* a_lo = a_hi + a_lo_off;
+                if (p.a_tmem) {
+                    // thread = A row (TMEM lane): read the row's channels of the stage (<= 32 floats = 4 octets)
+                    // through the TMA swizzle, then -- only now -- wait for the PREVIOUS stage's TMEM stores
+                    // and publish that stage, then split and store this stage (asynchronously).  The deferred
+                    // arrive keeps the tcgen05.st latency off the critical path.
+                    const int q = warp & 3;
+                    const int row = q * 32 + lane;
+                    const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+                    const int noct = (n * p.kc) >> 3;
+                    float4 v0[4], v1[4];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (o < noct) {
+                            const int e0 = o * 8, j = e0 / p.kc, c = e0 - j * p.kc;
+                            const uint8_t* arow = a_hi + (size_t)j * p.a_bytes + (size_t)row * p.span;
+                            v0[o] = *reinterpret_cast<const float4*>(arow + (swizzle_unit(c >> 2, row, p.span) << 4));
+                            v1[o] = *reinterpret_cast<const float4*>(arow + (swizzle_unit((c >> 2) + 1, row, p.span) << 4));
+                        }
+                    }
+                    if (pending >= 0) {
+                        tmem_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(smem_u32(&bar_conv[pending]));
+                    }
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (o < noct) {
+                            const int e0 = o * 8, j = e0 / p.kc, c = e0 - j * p.kc;
+                            const uint32_t ta = trow + (uint32_t)(p.tmem_a_off + (s * p.group + j) * 2 * p.kc);
+                            const float vv[8] = {v0[o].x, v0[o].y, v0[o].z, v0[o].w, v1[o].x, v1[o].y, v1[o].z, v1[o].w};
+                            float h[8], l[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) tf32_split(vv[e], h[e], l[e]);
+                            tmem_st8(ta + (uint32_t)c, h);
+                            tmem_st8(ta + (uint32_t)(p.kc + c), l);
+                        }
+                    }
+                    pending = s;
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    continue;
+                }
                 const int units = n * (p.a_bytes >> 4);
 #pragma unroll 2
-                for (int u = et; u < units; u += 256) {
+                for (int u = et; u < units; u += 128) {
                     const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 16);
                     float4 h, l;
                     h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
@@ -363,6 +428,11 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 mbar_arrive(smem_u32(&bar_conv[s]));
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
+        }
+        if (pending >= 0) {
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bar_conv[pending]));
         }
     }
     tc_fence_before();
@@ -475,22 +545,45 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     p.a_bytes = 128 * c.span;
     p.b_bytes = p.Npad * c.span;
     const int nit = p.ntaps * p.nchunks;
-    const int it_bytes = (p.a_bytes + p.b_bytes) * (x3 ? 2 : 1);
+    // x3: the split activations live in TMEM when 2 accumulators + an A ring fit in 512 columns; that
+    // removes the A_lo smem copy and all A-operand smem reads of the 3 MMAs (the kernel is otherwise
+    // shared-memory-bandwidth bound for narrow N)
+    // MEASURED (round 1): correct but slower than the smem path on B200 (SPC dgrad 0.80 vs 0.45 ms), so it is
+    // opt-in (DL4DS_TC_A_TMEM=1) until the TMEM-store latency is understood.
+    static const bool want_a_tmem = [] { const char* e = getenv("DL4DS_TC_A_TMEM"); return e && e[0] == '1'; }();
+    p.a_tmem = (want_a_tmem && x3 && 2 * p.Npad + 2 * 2 * c.kc <= 512) ? 1 : 0;
+    const int it_bytes = p.a_tmem ? (p.a_bytes + 2 * p.b_bytes) : (p.a_bytes + p.b_bytes) * (x3 ? 2 : 1);
     int group = (32 * 1024) / it_bytes;                    // ~32 KB per stage: few barrier round trips per tile
     if (group < 1) group = 1;
     if (group > nit) group = nit;
+    if (p.a_tmem && group * c.kc > 32) group = 32 / c.kc;  // the splitter holds one stage row (<= 32 floats) in registers
     p.group = group;
     p.ngroups = (nit + group - 1) / group;
     p.stage_bytes = group * it_bytes;
-    int cols = 32;
-    while (cols < 2 * p.Npad) cols *= 2;                   // double-buffered accumulator
-    p.tmem_cols = cols;
+    p.tmem_a_off = 2 * p.Npad;
+    int acc_cols = 32;
+    while (acc_cols < 2 * p.Npad) acc_cols *= 2;           // double-buffered accumulator alone
     // persistent CTAs: two per SM when TMEM (<= 256 columns each) allows, else one with all the smem
-    const int ctas_per_sm = cols <= 256 ? 2 : 1;
-    int stages = ((ctas_per_sm == 2 ? 104 : 208) * 1024) / p.stage_bytes;
+    int ctas_per_sm = acc_cols <= 256 ? 2 : 1;
+    int stages;
+    int cols;
+    for (;;) {
+        stages = ((ctas_per_sm == 2 ? 104 : 208) * 1024) / p.stage_bytes;
+        if (stages > kMaxStages) stages = kMaxStages;
+        const int budget = (ctas_per_sm == 2 ? 256 : 512) - 2 * p.Npad;
+        if (p.a_tmem) {
+            const int by_tmem = budget / (group * 2 * c.kc);
+            if (stages > by_tmem) stages = by_tmem;
+        }
+        if (stages >= 3 || ctas_per_sm == 1) break;         // a 2-stage ring cannot hide the TMA latency
+        ctas_per_sm = 1;
+    }
     if (stages < 2) stages = 2;
-    if (stages > kMaxStages) stages = kMaxStages;
     p.stages = stages;
+    cols = 32;
+    while (cols < 2 * p.Npad + (p.a_tmem ? stages * group * 2 * c.kc : 0)) cols *= 2;
+    if (cols > (ctas_per_sm == 2 ? 256 : 512)) { p.a_tmem = 0; return DL4DS_E_UNSUPPORTED; }
+    p.tmem_cols = cols;
     const size_t smem = (size_t)stages * p.stage_bytes + 1024;
     DL4DS_REQUIRE(smem <= 220 * 1024, DL4DS_E_UNSUPPORTED, "conv2d_fwd_tc: stage too large");
     const CUtensorMap* tm = get_tensor_map_nhwc(a.x, a.x_ld, a.N, a.H, a.W, a.Cin, c.kc, p.BW, p.BH, c.swz);
