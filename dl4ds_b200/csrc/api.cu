@@ -80,6 +80,8 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
     {   // narrow 3x3 layers (Cin, Cout in {1, 8}): HBM-bound, exact-fp32 direct kernel in every math mode
         int rc = conv2d_fwd_thin(a, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
+        rc = conv2d_fwd_pointwise(a, st);
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
     }
     if (math_mode != DL4DS_MATH_FP32) {
         int rc = conv2d_fwd_tc(a, math_mode, ws, prepacked, st);

@@ -575,7 +575,7 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
             const int by_tmem = budget / (group * 2 * c.kc);
             if (stages > by_tmem) stages = by_tmem;
         }
-        if (stages >= 3 || ctas_per_sm == 1) break;         // a 2-stage ring cannot hide the TMA latency
+        if (stages >= 2 || ctas_per_sm == 1) break;         // measured: 2 CTAs x 2 stages beat 1 CTA x 4 stages
         ctas_per_sm = 1;
     }
     if (stages < 2) stages = 2;
@@ -641,7 +641,10 @@ struct TcWgradParams {
     int pt_bytes, qt_bytes;           // transposed tiles per 32-pixel chunk: P^T per tap, Q^T
     int chunk_bytes;                  // KW*pt_bytes + qt_bytes: operand tiles of one 32-pixel chunk
     int op_bytes;                     // nk*chunk_bytes: one (hi) operand set
-    int stage_bytes, stages, tmem_cols;
+    int rstages, ostages;             // raw (TMA) ring depth, operand-tile ring depth
+    int ops_set_bytes;                // op_bytes * (1 or 2): operand bytes of one ring slot
+    int ops_base;                     // byte offset of the operand ring (after the raw ring)
+    int tmem_cols;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -653,7 +656,9 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
                                                                   const __grid_constant__ CUtensorMap tmap_q,
                                                                   const TcWgradParams p) {
     extern __shared__ uint8_t smem_raw[];
+    // raw ring: TMA -> transposers (full) and back (rfree); operand ring: transposers -> MMA (conv) and back (empty)
     __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_rfree[kMaxStages];
     __shared__ __align__(8) uint64_t bar_conv[kMaxStages];
     __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
     __shared__ __align__(8) uint64_t bar_accum;
@@ -689,8 +694,11 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
     const int nunits = units_p + nblk_q * gq;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) {
+        for (int s = 0; s < p.rstages; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_rfree[s]), 256);
+        }
+        for (int s = 0; s < p.ostages; ++s) {
             mbar_init(smem_u32(&bar_conv[s]), 256);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
@@ -723,16 +731,15 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
-    const uint32_t op_off = (uint32_t)p.raw_bytes;                          // operand tiles follow the raw region
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             const uint32_t tx_bytes = (uint32_t)(p.KW * nblk_p * p.box_p + nblk_q * p.box_q);
             for (int it = 0; it < my_tiles; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                const int s = it % p.rstages;
+                const uint32_t ph = (uint32_t)((it / p.rstages) & 1);
+                mbar_wait(smem_u32(&bar_rfree[s]), ph ^ 1u);
                 const uint32_t full = smem_u32(&bar_full[s]);
                 mbar_arrive_expect_tx(full, tx_bytes);
                 const int tile = t_begin + it;
@@ -740,7 +747,7 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
                 const int trem = tile - img * p.tiles_per_img;
                 const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
                 const int y0 = ty * p.BH, x0 = tx * p.BW;
-                const uint32_t sp = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                const uint32_t sp = smem_base + (uint32_t)s * (uint32_t)p.raw_bytes;
                 for (int kw = 0; kw < p.KW; ++kw)
                     for (int b = 0; b < nblk_p; ++b)
                         tma_load_4d(sp + (uint32_t)((kw * p.nblk_p_max + b) * p.box_p), &tmap_p, full,
@@ -754,11 +761,11 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(64, Nmma, 0, 0);
             for (int it = 0; it < my_tiles; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+                const int s = it % p.ostages;
+                const uint32_t ph = (uint32_t)((it / p.ostages) & 1);
                 mbar_wait(smem_u32(&bar_conv[s]), ph);
                 tc_fence_after();
-                const uint32_t so = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes + op_off;
+                const uint32_t so = smem_base + (uint32_t)p.ops_base + (uint32_t)s * (uint32_t)p.ops_set_bytes;
                 for (int j = 0; j < p.nk; ++j) {
                     const uint32_t sc = so + (uint32_t)(j * p.chunk_bytes);
                     const uint32_t qb = sc + qt_off;
@@ -796,11 +803,11 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
         const uint32_t dst_lane = (uint32_t)((lane & 3) << 2);
         const uint32_t lane_unit = (uint32_t)(lane >> 2);
         for (int it = 0; it < my_tiles; ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-            mbar_wait(smem_u32(&bar_full[s]), ph);
-            uint8_t* raw = smem_al + (size_t)s * p.stage_bytes;
-            uint8_t* ops = raw + p.raw_bytes;
+            const int rs = it % p.rstages, os = it % p.ostages;
+            mbar_wait(smem_u32(&bar_full[rs]), (uint32_t)((it / p.rstages) & 1));
+            mbar_wait(smem_u32(&bar_empty[os]), (uint32_t)(((it / p.ostages) & 1) ^ 1));
+            uint8_t* raw = smem_al + (size_t)rs * p.raw_bytes;
+            uint8_t* ops = smem_al + p.ops_base + (size_t)os * p.ops_set_bytes;
             for (int j = 0; j < p.nk; ++j)
             for (int u = tw; u < nunits; u += 8) {
                 const uint4 e = unit_tab[u];
@@ -826,8 +833,9 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
                     }
                 }
             }
+            mbar_arrive(smem_u32(&bar_rfree[rs]));           // raw slot read: the next TMA may overwrite it
             fence_proxy_async_smem();
-            mbar_arrive(smem_u32(&bar_conv[s]));
+            mbar_arrive(smem_u32(&bar_conv[os]));
         }
         if (tw < 4) {
             mbar_wait(smem_u32(&bar_accum), 0);
@@ -915,29 +923,35 @@ int conv2d_wgrad_tc(const WgradArgs& a, void*, int math_mode, cudaStream_t st) {
     p.qt_bytes = nmma_max * 128;
     p.chunk_bytes = a.KW * p.pt_bytes + p.qt_bytes;
     p.op_bytes = nk * p.chunk_bytes;
-    p.stage_bytes = p.raw_bytes + p.op_bytes * (x3 ? 2 : 1);
+    p.ops_set_bytes = p.op_bytes * (x3 ? 2 : 1);
     if (a.KW * (ca_first / cp.kc) * (cp.kc / 4) + (cb_first / cq.kc) * (cq.kc / 4) > kWgMaxUnits) return DL4DS_E_UNSUPPORTED;
     const int slack = 64 * 128;                            // the M=64 operand window of the last tile stays in-bounds
-    int stages = (218 * 1024 - slack) / p.stage_bytes;
-    if (stages < 1) return DL4DS_E_UNSUPPORTED;
-    if (stages > kMaxStages) stages = kMaxStages;
     int cols = 32;
     while (cols < a.KW * nmma_max) cols *= 2;
     if (cols > 512) return DL4DS_E_UNSUPPORTED;
     p.tmem_cols = cols;
     const int nroles = a.KH * p.ncig * p.ncob;
+    // ring depths: operand ring 2 deep (transpose of tile i+1 overlaps the MMAs of tile i), the rest of the
+    // budget goes to the raw TMA ring (up to 4) to cover the global-load latency
+    int budget = 218 * 1024 - slack;
     int splits = kNumSMs / nroles;
-    if (cols <= 256 && 3 * p.stage_bytes <= 100 * 1024) {  // two CTAs per SM hide each other's epilogue
+    if (cols <= 256 && 2 * p.ops_set_bytes + 3 * p.raw_bytes <= 100 * 1024) {   // two CTAs per SM
+        budget = 100 * 1024;
         splits = (2 * kNumSMs) / nroles;
-        if (stages > 3) stages = 3;
     }
+    int ostages = 2;
+    if (budget < ostages * p.ops_set_bytes + p.raw_bytes) ostages = 1;
+    if (budget < ostages * p.ops_set_bytes + p.raw_bytes) return DL4DS_E_UNSUPPORTED;
+    int rstages = (budget - ostages * p.ops_set_bytes) / p.raw_bytes;
+    if (rstages > 4) rstages = 4;
     if (splits < 1) splits = 1;
     if (splits > p.ntiles) splits = p.ntiles;
     p.tiles_per_split = (p.ntiles + splits - 1) / splits;
     splits = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
-    if (stages > p.tiles_per_split) stages = p.tiles_per_split;
-    p.stages = stages;
-    const size_t smem = (size_t)stages * p.stage_bytes + slack + 1024;
+    p.rstages = rstages;
+    p.ostages = ostages;
+    p.ops_base = rstages * p.raw_bytes;
+    const size_t smem = (size_t)p.ops_base + (size_t)ostages * p.ops_set_bytes + slack + 1024;
     const CUtensorMap* tp = get_tensor_map_nhwc(a.P, a.p_ld, a.N, a.Hp, a.Wp, a.Ca, cp.kc, BW, BH, cp.swz);
     const CUtensorMap* tq = get_tensor_map_nhwc(a.Q, a.q_ld, a.N, a.Hq, a.Wq, a.Cb, cq.kc, BW, BH, cq.swz);
     if (!tp || !tq) return DL4DS_E_CUDA;

@@ -364,6 +364,122 @@ int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
 }
 
 // -------------------------------------------------------------------------------------------------
+// pointwise (1x1) convolution for narrow layers (TransitionLast 48 -> 8 at 128 x 128 and its input
+// gradient 8 -> 48, sp_postups.py:205): pure streaming.  A block handles 256 consecutive pixels: the
+// input rows are staged in shared memory with coalesced 16-byte loads (pixel pitch Cin+4 floats so that
+// per-thread row reads are conflict-free), each thread computes all COUT outputs of its pixel from
+// broadcast weight reads, the outputs go back through shared memory so that global stores are fully
+// coalesced 512-byte runs.
+// -------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) pointwise_conv_kernel(const ConvArgs p, int64_t n_pix) {
+    extern __shared__ __align__(16) float psm[];
+    const int Cin = p.Cin;
+    const int ips = Cin + 4, ops = COUT + 4;                 // padded pixel pitches (floats)
+    float* wsm = psm;                                        // Cin x COUT
+    float* bsm = wsm + Cin * COUT;                           // COUT
+    float* xin = bsm + ((COUT + 3) & ~3);                    // 256 x ips
+    float* yout = xin + 256 * ips;                           // 256 x ops
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Cin * COUT; i += 256) {
+        const int co = i % COUT, ci = i / COUT;
+        wsm[i] = (p.wmode == DL4DS_W_HWIO) ? __ldg(p.w + ci * COUT + co) : __ldg(p.w + co * Cin + ci);
+    }
+    for (int i = tid; i < COUT; i += 256) bsm[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
+    const int v4in = Cin / 4, v4out = COUT / 4;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n_pix; base += (int64_t)gridDim.x * 256) {
+        const int npx = (int)min((int64_t)256, n_pix - base);
+        __syncthreads();
+        for (int i = tid; i < npx * v4in; i += 256) {
+            const int px = i / v4in, c4 = i - px * v4in;
+            *reinterpret_cast<float4*>(xin + px * ips + c4 * 4) =
+                __ldg(reinterpret_cast<const float4*>(p.x + (base + px) * p.x_ld) + c4);
+        }
+        __syncthreads();
+        if (tid < npx) {
+            float acc[COUT];
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[c] = bsm[c];
+            const float* xr = xin + tid * ips;
+            for (int c4 = 0; c4 < v4in; ++c4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xr + c4 * 4);
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float* wr = wsm + (c4 * 4 + u) * COUT;
+#pragma unroll
+                    for (int c = 0; c < COUT; c += 4) {
+                        const float4 wv = *reinterpret_cast<const float4*>(wr + c);
+                        acc[c] = fmaf(xs[u], wv.x, acc[c]);
+                        acc[c + 1] = fmaf(xs[u], wv.y, acc[c + 1]);
+                        acc[c + 2] = fmaf(xs[u], wv.z, acc[c + 2]);
+                        acc[c + 3] = fmaf(xs[u], wv.w, acc[c + 3]);
+                    }
+                }
+            }
+            float* yr = yout + tid * ops;
+#pragma unroll
+            for (int c = 0; c < COUT; c += 4)
+                *reinterpret_cast<float4*>(yr + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        }
+        __syncthreads();
+        for (int i = tid; i < npx * v4out; i += 256) {
+            const int px = i / v4out, c4 = i - px * v4out;
+            float4 v = *reinterpret_cast<const float4*>(yout + px * ops + c4 * 4);
+            const int64_t pix = base + px;
+            if (p.res) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + pix * p.res_ld) + c4);
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+            v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+            float4* dst = reinterpret_cast<float4*>(p.y + pix * p.y_ld) + c4;
+            if (p.beta) {
+                const float4 o = *dst;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *dst = v;
+        }
+    }
+}
+
+template <int COUT>
+static int launch_pointwise(const ConvArgs& a, cudaStream_t st) {
+    const int64_t n_pix = (int64_t)a.N * a.H * a.W;
+    const size_t smem = (size_t)(a.Cin * COUT + ((COUT + 3) & ~3) + 256 * (a.Cin + 4) + 256 * (COUT + 4)) * 4;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(pointwise_conv_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr = true;
+    }
+    if (smem > 100 * 1024) return DL4DS_E_UNSUPPORTED;
+    int64_t blocks = (n_pix + 255) / 256;
+    if (blocks > 3 * kNumSMs) blocks = 3 * kNumSMs;
+    pointwise_conv_kernel<COUT><<<(int)blocks, 256, smem, st>>>(a, n_pix);
+    return check_launch("pointwise_conv_kernel");
+}
+
+// DL4DS_E_UNSUPPORTED when the shape is outside this kernel's domain
+int conv2d_fwd_pointwise(const ConvArgs& a, cudaStream_t st) {
+    if (a.KH != 1 || a.KW != 1 || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
+        return DL4DS_E_UNSUPPORTED;
+    if (a.Cin % 4 || a.Cin > 64 || !a.vec) return DL4DS_E_UNSUPPORTED;
+    if (a.Cin > 8 && a.Cout > 8) return DL4DS_E_UNSUPPORTED;          // wide x wide goes to the tensor cores
+    if (a.y_ld % 4 || (reinterpret_cast<uintptr_t>(a.y) & 15)) return DL4DS_E_UNSUPPORTED;
+    if (a.res && (a.res_ld % 4 || (reinterpret_cast<uintptr_t>(a.res) & 15))) return DL4DS_E_UNSUPPORTED;
+    if ((int64_t)a.N * a.H * a.W < 65536) return DL4DS_E_UNSUPPORTED;
+    switch (a.Cout) {
+        case 8: return launch_pointwise<8>(a, st);
+        case 16: return launch_pointwise<16>(a, st);
+        case 24: return launch_pointwise<24>(a, st);
+        case 32: return launch_pointwise<32>(a, st);
+        case 40: return launch_pointwise<40>(a, st);
+        case 48: return launch_pointwise<48>(a, st);
+        default: return DL4DS_E_UNSUPPORTED;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // vectorised bias / activation backward (+ space_to_depth un-shuffle)
 // -------------------------------------------------------------------------------------------------
 // block = (TX, PY): thread (tx, ty) owns float4 channel groups g = tx + k*TX (k < KS), pixels ty, ty+PY, ...

@@ -322,3 +322,12 @@ def test_thin_conv_residual_bias_relu(cuda):
         return c.conv(xs[0], 'cv', 8, act='relu', res=xs[1])
     ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], 8) + xs[1], 'relu'))
     compare(fn, ofn, [(2, 96, 128, 8), (2, 96, 128, 8)], cuda)
+
+
+@pytest.mark.parametrize('cin,cout', [(48, 8), (8, 48), (8, 8), (16, 8)])
+def test_pointwise_conv(cuda, cin, cout):
+    """Streaming 1x1 kernel of the narrow layers (TransitionLast and its dgrad), bias + relu + residual."""
+    def fn(c, xs):
+        return c.conv(xs[0], 'cv', cout, k=1, act='relu', res=xs[1])
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=1) + xs[1], 'relu'))
+    compare(fn, ofn, [(5, 128, 128, cin), (5, 128, 128, cout)], cuda)
