@@ -24,6 +24,7 @@ SIGNATURES = {
     'dl4ds_version': ('i', ''),
     'dl4ds_device_is_sm100': ('i', ''),
     'dl4ds_tc_launch_count': ('l', ''),
+    'dl4ds_debug_set_buffer': ('i', 'p'),
     'dl4ds_conv2d_fwd_workspace_bytes': ('l', 'iiiiiiiiiiiii'),
     'dl4ds_conv2d_pack': ('i', 'piiiiiipp'),
     'dl4ds_conv2d_fwd': ('i', 'pipppipiiiiiiiiiiiiiiiiiiipp'),

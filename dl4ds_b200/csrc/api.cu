@@ -36,6 +36,11 @@ int dl4ds_version(void) { return 100; }
 
 int64_t dl4ds_tc_launch_count(void) { return g_tc_launches.load(); }
 
+int dl4ds_debug_set_buffer(void* dev_i64) {
+    wgrad2_set_debug_buffer(reinterpret_cast<long long*>(dev_i64));
+    return DL4DS_OK;
+}
+
 int dl4ds_device_is_sm100(void) {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -136,7 +141,9 @@ int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
     }
     if (math_mode != DL4DS_MATH_FP32) {
-        int rc = conv2d_wgrad_tc(a, ws, math_mode, st);
+        int rc = conv2d_wgrad_tc2(a, math_mode, st);
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+        rc = conv2d_wgrad_tc(a, ws, math_mode, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
     }
     return conv2d_wgrad_simt(a, st);

@@ -184,12 +184,12 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_conv[s]), 128);
+            mbar_init(smem_u32(&bar_conv[s]), 4);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bar_tfull[b]), 1);
-            mbar_init(smem_u32(&bar_tempty[b]), 256);
+            mbar_init(smem_u32(&bar_tempty[b]), 8);
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmap_x);
@@ -357,7 +357,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
             }
             // accumulator buffer drained: hand it back to the MMA warp
             tc_fence_before();
-            mbar_arrive(smem_u32(&bar_tempty[ab]));
+            mbar_arrive_warp(smem_u32(&bar_tempty[ab]));
         }
     } else if (X3) {
         // ===================== operand splitter (warps 10-13, x3 mode) =====================
@@ -395,7 +395,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                     if (pending >= 0) {
                         tmem_wait_st();
                         tc_fence_before();
-                        mbar_arrive(smem_u32(&bar_conv[pending]));
+                        mbar_arrive_warp(smem_u32(&bar_conv[pending]));
                     }
 #pragma unroll
                     for (int o = 0; o < 4; ++o) {
@@ -425,14 +425,14 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                     *reinterpret_cast<float4*>(a_lo + u * 16) = l;
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(smem_u32(&bar_conv[s]));
+                mbar_arrive_warp(smem_u32(&bar_conv[s]));
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
         if (pending >= 0) {
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(smem_u32(&bar_conv[pending]));
+            mbar_arrive_warp(smem_u32(&bar_conv[pending]));
         }
     }
     tc_fence_before();
@@ -696,10 +696,10 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.rstages; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_rfree[s]), 256);
+            mbar_init(smem_u32(&bar_rfree[s]), 8);
         }
         for (int s = 0; s < p.ostages; ++s) {
-            mbar_init(smem_u32(&bar_conv[s]), 256);
+            mbar_init(smem_u32(&bar_conv[s]), 8);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         mbar_init(smem_u32(&bar_accum), 1);
@@ -833,9 +833,9 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
                     }
                 }
             }
-            mbar_arrive(smem_u32(&bar_rfree[rs]));           // raw slot read: the next TMA may overwrite it
+            mbar_arrive_warp(smem_u32(&bar_rfree[rs]));      // raw slot read: the next TMA may overwrite it
             fence_proxy_async_smem();
-            mbar_arrive(smem_u32(&bar_conv[os]));
+            mbar_arrive_warp(smem_u32(&bar_conv[os]));
         }
         if (tw < 4) {
             mbar_wait(smem_u32(&bar_accum), 0);

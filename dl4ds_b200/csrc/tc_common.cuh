@@ -29,6 +29,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// one arrival per WARP: every lane's prior shared-memory accesses are ordered before lane 0's
+// (release) arrive by the __syncwarp.  512 per-thread arrivals on one mbarrier serialise in the
+// shared-memory atomic unit (measured ~1-2k cycles per phase); barriers fed by whole warps are
+// initialised with the warp count and use this.
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {

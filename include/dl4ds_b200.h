@@ -60,6 +60,9 @@ int dl4ds_device_is_sm100(void);
 /* Number of tcgen05 (tensor-core) kernel launches issued by this process so far: lets callers and
  * tests verify that a tensor-core math mode did not silently take the CUDA-core path. */
 int64_t dl4ds_tc_launch_count(void);
+/* Developer aid: a device buffer of >= 1024 int64 that CTA (0,0) of the weight-gradient tensor-core kernel
+ * fills with clock64() stamps of its pipeline stages (scratch/wg2_stamps.py); NULL (default) disables it. */
+int dl4ds_debug_set_buffer(void* dev_i64);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution family.  One generalized implicit-GEMM entry point covers:

@@ -331,3 +331,37 @@ def test_pointwise_conv(cuda, cin, cout):
         return c.conv(xs[0], 'cv', cout, k=1, act='relu', res=xs[1])
     ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=1) + xs[1], 'relu'))
     compare(fn, ofn, [(5, 128, 128, cin), (5, 128, 128, cout)], cuda)
+
+
+# ------------------------------------------------------------------------------------------ stacked-taps wgrad
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('shape,cout,k', [
+    ((3, 32, 32, 48), 48, 3),       # backbone layer: 432 stacked rows -> 4 M-blocks, one role
+    ((2, 64, 64, 48), 192, 3),      # SPC layer: two output-channel roles of 96, two chunks per image row
+    ((2, 16, 16, 24), 8, 3),        # 2 rows per chunk (BW=16), 216 rows -> 2 blocks, Nmma 16 > Cb 8
+    ((2, 8, 8, 64), 16, 3),         # 4 rows per chunk (BW=8); 576 rows -> two input-channel groups of 32
+    ((1, 128, 128, 48), 8, 1),      # TransitionLast: 1x1, long pixel stream, narrow N
+    ((2, 32, 32, 8), 48, 1),        # 1x1 projection, 8 stacked rows
+    ((2, 16, 32, 16), 40, 5),       # 5x5: 400 stacked rows, halo 36 x 5
+    ((5, 32, 32, 40), 56, 3),       # 360 rows (3 blocks, last one partial), Cb 56 -> Nmma 64
+])
+def test_wgrad_stacked_taps(cuda, math, shape, cout, k):
+    """conv_tc_wgrad2_kernel (conv_tc_wgrad.cu) through Ctx.conv's backward, against the oracle."""
+    fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=k, act='tanh')
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=k), 'tanh'))
+    compare(fn, ofn, [shape], cuda, math=math, **TC_TOL[math])
+
+
+def test_wgrad_stacked_taps_on_concat_slices(cuda):
+    """Q (dz) as a channel slice of a wider gradient buffer (pitch 24, 16 channels): the gradient of a
+    Concatenate input is a slice of the concat's gradient (dense-block wiring, blocks.py:276)."""
+    def fn(c, xs):
+        a = c.conv(xs[0], 'a', 16, act='tanh')
+        cat = c.concat([a, xs[0]])                       # 16 + 8 channels
+        return c.conv(cat, 'b', 24, act='tanh')
+
+    def ofn(p, xs):
+        x = R._nchw(xs[0])
+        a = R.act(R._conv(p, 'a', x, 16), 'tanh')
+        return R._nhwc(R.act(R._conv(p, 'b', torch.cat([a, x], 1), 24), 'tanh'))
+    compare(fn, ofn, [(2, 32, 32, 8)], cuda, math='tf32x3', **TC_TOL['tf32x3'])
