@@ -30,6 +30,8 @@ SIGNATURES = {
     'dl4ds_conv2d_fwd': ('i', 'pipppipiiiiiiiiiiiiiiiiiiipp'),
     'dl4ds_conv2d_wgrad_workspace_bytes': ('l', 'iiiiiiii'),
     'dl4ds_conv2d_wgrad': ('i', 'pipipiiiiiiiiiiiipip'),
+    'dl4ds_spc_pointwise_compose': ('i', 'ppppppiiiip'),
+    'dl4ds_spc_pointwise_chain': ('i', 'pppppppppiiiip'),
     'dl4ds_bias_act_bwd': ('i', 'pipipipiiiiiip'),
     'dl4ds_add': ('i', 'pipipiliip'),
     'dl4ds_copy_channels': ('i', 'pipiliip'),

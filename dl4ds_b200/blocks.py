@@ -62,6 +62,20 @@ def subpixel_block(c, name, x, scale, n_filters):
     return x
 
 
+def subpixel_transition(c, name, x, scale, n_filters, tname, t_filters, activation='relu'):
+    """SubpixelConvolutionBlock (blocks.py:433-454) followed directly by a TransitionBlock (blocks.py:306-308):
+    every x2 stage but the last runs as in :func:`subpixel_block`; the last one is composed with the
+    transition's 1x1 convolution (``Ctx.conv_d2s_pointwise``), which removes the widest HR tensor of the graph.
+    Falls back to the two separate blocks when the last stage is not x2."""
+    plan = {2: [2], 4: [2, 2], 8: [2, 2, 2], 10: [2, 5], 20: [2, 2, 5]}.get(scale, [scale])
+    if plan[-1] != 2 or n_filters % 4 or t_filters % 4:
+        return transition_block(c, tname, subpixel_block(c, name, x, scale, n_filters), t_filters, activation)
+    for f in plan[:-1]:
+        lname = {2: 'conv2x', 5: 'conv5x'}.get(f, 'conv')
+        x = c.conv(x, name + '/' + lname, n_filters * f * f, d2s=f)
+    return c.conv_d2s_pointwise(x, name + '/conv2x', n_filters, tname + '/conv', t_filters, act=activation, r=2)
+
+
 def resize_conv_block(c, name, x, scale, n_filters):
     """ResizeConvolutionBlock.call (bilinear) -- blocks.py:485-491."""
     y = c.resize_bilinear(x, int(x.H * scale), int(x.W * scale))

@@ -139,6 +139,8 @@ int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float
     {   // narrow layers (Ca, Cb in {1, 8}, 3x3): exact-fp32 sliding-window kernel in every math mode
         int rc = conv2d_wgrad_thin(a, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
+        rc = conv2d_wgrad_pointwise(a, st);        // 1x1, Ca*Cb <= 1024: streaming CUDA-core kernel
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
     }
     if (math_mode != DL4DS_MATH_FP32) {
         int rc = conv2d_wgrad_tc2(a, math_mode, st);

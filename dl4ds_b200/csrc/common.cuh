@@ -44,6 +44,7 @@ int conv2d_fwd_simt(const ConvArgs& a, cudaStream_t st);
 int conv2d_wgrad_simt(const WgradArgs& a, cudaStream_t st);
 // thin.cu: DL4DS_E_UNSUPPORTED outside their domains
 int conv2d_wgrad_thin(const WgradArgs& a, cudaStream_t st);
+int conv2d_wgrad_pointwise(const WgradArgs& a, cudaStream_t st);
 int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st);
 int conv2d_fwd_pointwise(const ConvArgs& a, cudaStream_t st);
 int bias_act_bwd_vec4(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld, float* dbias,

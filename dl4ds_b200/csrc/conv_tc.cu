@@ -153,6 +153,8 @@ struct TcFwdParams {
     int act, d2s_r, beta;
     int stages, stage_bytes, a_bytes, b_bytes, tmem_cols, ntiles;
     int group, ngroups;     // kernel-tap / channel-chunk iterations per smem stage, stages per tile
+    int stackn;             // x3, Npad <= 64: B = [W_hi ; W_lo] stacked on N -> 2 MMAs per K-step (see the issuer)
+    int acc_stride;         // TMEM columns per accumulator buffer: Npad, or 2*Npad when stackn
     int a_tmem;             // x3: split activations go to TMEM (A operand from TMEM), not back to smem
     int tmem_a_off;         // first TMEM column of the A ring (stage s, iteration j: + (s*group+j)*2*kc)
 };
@@ -228,8 +230,17 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                         if (++ch == p.nchunks) { ch = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
                     }
                     const size_t woff = (size_t)it0 * p.Npad * p.kc;
-                    bulk_load(sa + b_off, p.wp_hi + woff, (uint32_t)(n * p.b_bytes), full);
-                    if (X3) bulk_load(sa + b_off + b_lo_off, p.wp_lo + woff, (uint32_t)(n * p.b_bytes), full);
+                    if (X3 && p.stackn) {
+                        // hi and lo tiles of one iteration adjacent in shared memory: one B operand of 2*Npad rows
+                        for (int j = 0; j < n; ++j) {
+                            const size_t wj = woff + (size_t)j * p.Npad * p.kc;
+                            bulk_load(sa + b_off + (uint32_t)(2 * j * p.b_bytes), p.wp_hi + wj, (uint32_t)p.b_bytes, full);
+                            bulk_load(sa + b_off + (uint32_t)((2 * j + 1) * p.b_bytes), p.wp_lo + wj, (uint32_t)p.b_bytes, full);
+                        }
+                    } else {
+                        bulk_load(sa + b_off, p.wp_hi + woff, (uint32_t)(n * p.b_bytes), full);
+                        if (X3) bulk_load(sa + b_off + b_lo_off, p.wp_lo + woff, (uint32_t)(n * p.b_bytes), full);
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -238,6 +249,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(128, p.Npad, 0, 0);
+            const uint32_t idesc2 = make_idesc_tf32(128, 2 * p.Npad, 0, 0);
             const uint32_t sbo = 8u * (uint32_t)p.span;
             int s = 0;
             uint32_t ph = 0;
@@ -246,7 +258,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 const int ab = tcount & 1;
                 mbar_wait(smem_u32(&bar_tempty[ab]), (uint32_t)(((tcount >> 1) & 1) ^ 1));
                 tc_fence_after();
-                const uint32_t td = tmem_d + (uint32_t)(ab * p.Npad);
+                const uint32_t td = tmem_d + (uint32_t)(ab * p.acc_stride);
                 uint32_t accumulate = 0;
                 int ch = 0;
                 const uint32_t a_lo_off = (uint32_t)(p.group * p.a_bytes);
@@ -261,7 +273,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                         int ksteps = (p.Cin - ch * p.kc);
                         ksteps = (ksteps > p.kc ? p.kc : ksteps) >> 3;
                         const uint32_t sa = st0 + (uint32_t)(j * p.a_bytes);
-                        const uint32_t sb = st0 + b_off + (uint32_t)(j * p.b_bytes);
+                        const uint32_t sb = st0 + b_off + (uint32_t)(j * p.b_bytes * (p.stackn ? 2 : 1));
                         const uint32_t ta = tmem_d + (uint32_t)(p.tmem_a_off + (s * p.group + j) * 2 * p.kc);
                         for (int k = 0; k < ksteps; ++k) {
                             const uint32_t ko = (uint32_t)k * 32u;
@@ -273,6 +285,13 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                                 umma_tf32_ts(td, al, db, idesc, accumulate);
                                 umma_tf32_ts(td, ah, dbl, idesc, 1u);
                                 umma_tf32_ts(td, ah, db, idesc, 1u);
+                            } else if (X3 && p.stackn) {
+                                // A_hi x [W_hi ; W_lo] -> columns [0,Npad) and [Npad,2Npad); A_lo x W_hi -> columns
+                                // [0,Npad).  One MMA costs ~119 cycles for any N <= 128 (scratch/umma_rate.cu), so
+                                // 2 instead of 3 per K-step; the epilogue adds the two column groups.
+                                const uint64_t dal = make_smem_desc(sa + a_lo_off + ko, 16, sbo, p.layout);
+                                umma_tf32(td, da, db, idesc2, accumulate);
+                                umma_tf32(td, dal, db, idesc, 1u);
                             } else if (X3) {
                                 const uint64_t dal = make_smem_desc(sa + a_lo_off + ko, 16, sbo, p.layout);
                                 const uint64_t dbl = make_smem_desc(sb + b_lo_off + ko, 16, sbo, p.layout);
@@ -316,10 +335,16 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
             const int64_t hr_row0 = ((int64_t)img * p.H * r + (int64_t)oy * r) * ((int64_t)p.W * r) + (int64_t)ox * r;
             mbar_wait(smem_u32(&bar_tfull[ab]), (uint32_t)((tcount >> 1) & 1));
             tc_fence_after();
-            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.Npad);
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.acc_stride);
             for (int c0 = half * 16; c0 < p.Npad; c0 += 32) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)c0, v);
+                if (X3 && p.stackn) {
+                    float v2[16];
+                    tmem_ld16(taddr + (uint32_t)(p.Npad + c0), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                }
                 if (c0 >= p.Cout) continue;
                 float4 rs[4];
                 if (resp) {
@@ -561,8 +586,11 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     p.ngroups = (nit + group - 1) / group;
     p.stage_bytes = group * it_bytes;
     p.tmem_a_off = 2 * p.Npad;
+    static const bool no_stack = [] { const char* e = getenv("DL4DS_TC_NO_STACKN"); return e && e[0] == '1'; }();
+    p.stackn = (x3 && !p.a_tmem && p.Npad <= 64 && !no_stack) ? 1 : 0;
+    p.acc_stride = p.stackn ? 2 * p.Npad : p.Npad;
     int acc_cols = 32;
-    while (acc_cols < 2 * p.Npad) acc_cols *= 2;           // double-buffered accumulator alone
+    while (acc_cols < 2 * p.acc_stride) acc_cols *= 2;     // double-buffered accumulator alone
     // persistent CTAs: two per SM when TMEM (<= 256 columns each) allows, else one with all the smem
     int ctas_per_sm = acc_cols <= 256 ? 2 : 1;
     int stages;
@@ -570,7 +598,7 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     for (;;) {
         stages = ((ctas_per_sm == 2 ? 104 : 208) * 1024) / p.stage_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
-        const int budget = (ctas_per_sm == 2 ? 256 : 512) - 2 * p.Npad;
+        const int budget = (ctas_per_sm == 2 ? 256 : 512) - 2 * p.acc_stride;
         if (p.a_tmem) {
             const int by_tmem = budget / (group * 2 * c.kc);
             if (stages > by_tmem) stages = by_tmem;
@@ -581,7 +609,7 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     if (stages < 2) stages = 2;
     p.stages = stages;
     cols = 32;
-    while (cols < 2 * p.Npad + (p.a_tmem ? stages * group * 2 * c.kc : 0)) cols *= 2;
+    while (cols < 2 * p.acc_stride + (p.a_tmem ? stages * group * 2 * c.kc : 0)) cols *= 2;
     if (cols > (ctas_per_sm == 2 ? 256 : 512)) { p.a_tmem = 0; return DL4DS_E_UNSUPPORTED; }
     p.tmem_cols = cols;
     const size_t smem = (size_t)stages * p.stage_bytes + 1024;

@@ -19,6 +19,15 @@
 //     layouts -- all warps sharing a block with one unit in flight each, and one private slot per
 //     warp group -- showed the transposers latency-bound resp. in lock-step with the MMA warp).
 //
+// Operand orientation.  scratch/umma_rate.cu measured the cost of one kind::tf32 M=128 K=8 MMA with both
+// operands in shared memory: ~119 cycles for ANY N <= 128, 139 at N=192, 171 at N=256 -- a per-instruction
+// floor, so the instruction count is what matters and N should be as large as TMEM allows:
+//   * Cb <= 128 ("swap"): A = Q^T (one M tile, rows past Cb are never read back), B = a block of up to 256
+//     stacked P^T rows; 432 stacked rows -> 2 blocks of 224/208 -> 24 MMAs per 32-pixel chunk (x3) instead
+//     of 48 with the stacked rows on M;
+//   * Cb > 128 (the 48 -> 192 sub-pixel layer): A = 128-row block of stacked P^T, B = Q^T with N = Cb (<= 256);
+//     the blocks are spread over `nrg` CTA roles because bpr * N accumulator columns must fit TMEM.
+//
 // Warp roles (kWg2Threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = Q
 // group (transposes the Q^T tile of every chunk), warps 6-17 = A group (every block of the stacked
 // P^T, 3 units in flight per warp).  A transposer unit = swizzle-aware LDS.128 of (pixel, 4
@@ -34,9 +43,7 @@ namespace dl4ds {
 
 using namespace tc;
 
-constexpr int kWg2QWarps = 4;
-constexpr int kWg2AWarps = 12;
-constexpr int kWg2TransWarps = kWg2QWarps + kWg2AWarps;
+constexpr int kWg2TransWarps = 16;     // split into a Q group (qwarps) and an A group (the rest) per launch
 constexpr int kWg2Threads = (2 + kWg2TransWarps) * 32;
 constexpr int kWg2MaxAUnits = 128;     // 512 stacked rows / 4
 constexpr int kWg2MaxQUnits = 64;      // 256 output channels / 4
@@ -49,6 +56,12 @@ struct Wg2Params {
     int tiles_x, tiles_per_img, ntiles, tiles_per_split;
     int kc_p, span_p, kc_q, span_q;
     int CaG, ncig, Nb, ncob;
+    int swap;                         // 1: A = Q^T, B = stacked-row block (N = BR); 0: A = stacked-row block, B = Q^T
+    int BR;                           // stacked rows per block (128 when !swap, <= 256 when swap)
+    int bpr, nrg;                     // blocks per CTA role, row-group roles
+    int qwarps, qstages;
+    int stackm;                       // swap, x3, 2*q_rows <= 128: A = [Q_hi ; Q_lo] stacked on M -> 2 MMAs per K-step
+    int q_rows;                       // rows of one Q^T half in its slot
     int box_p, box_q;                 // smem bytes reserved per raw box (multiples of 1024)
     int tx_p, tx_q;                   // bytes one TMA box transfers
     int nbox_p_max;                   // P boxes of a full input-channel group (Q boxes follow them)
@@ -56,7 +69,8 @@ struct Wg2Params {
     int a_half, q_half;               // bytes of the hi half of an A / Q slot (lo follows in x3 mode)
     int a_slot, q_slot;
     int rstages, astages;             // raw (TMA) ring depth, A-slot ring depth
-    int a_base, q_base;               // smem byte offsets of the A-slot ring and the two Q slots
+    int q_base, raw_base, a_base;     // smem byte offsets: Q slots first (an A-operand read of a short Q^T tile
+                                      // runs on into the raw ring, never out of bounds), raw ring, A-slot ring
     int tmem_cols;
     long long* dbg;                   // optional: clock64 stamps of CTA (0,0) (dl4ds_debug_set_buffer), else NULL
 };
@@ -66,6 +80,13 @@ struct Wg2Params {
     do {                                                                                        \
         if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && lane == 0)     \
             p.dbg[it * 16 + (id)] = clock64();                                                  \
+    } while (0)
+
+// whole-kernel stamps of CTA (0,0): slot 1024 + id (0 entry, 1 setup done, 2 main loop drained, 3 epilogue done)
+#define WG2_KSTAMP(id)                                                                          \
+    do {                                                                                        \
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64)        \
+            p.dbg[1024 + (id)] = clock64();                                                     \
     } while (0)
 
 __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
@@ -153,18 +174,24 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    WG2_KSTAMP(0);
 
-    // role: input-channel group x output-channel block
-    const int cob = blockIdx.y % p.ncob;
-    const int cig = blockIdx.y / p.ncob;
+    // role: input-channel group x output-channel block x row group
+    const int rg = blockIdx.y % p.nrg;
+    const int cob = (blockIdx.y / p.nrg) % p.ncob;
+    const int cig = blockIdx.y / (p.nrg * p.ncob);
+    const int qwarps = p.qwarps, awarps = kWg2TransWarps - p.qwarps;
     const int ca0 = cig * p.CaG;
     const int ca_n = min(p.CaG, p.Ca - ca0);
     const int cb0 = cob * p.Nb;
     const int cb_n = min(p.Nb, p.Cb - cb0);
     const int Nmma = (cb_n + 15) & ~15;
     const int taps = p.KH * p.KW;
-    const int rows = taps * ca_n;                 // stacked A rows
-    const int nblk = (rows + 127) >> 7;
+    const int rows = taps * ca_n;                 // stacked P^T rows of this input-channel group
+    const int blk0 = rg * p.bpr;                  // first block of this role
+    const int nblk = min(p.bpr, (rows + p.BR - 1) / p.BR - blk0);
+    if (nblk <= 0) return;
+    const int upb = p.BR >> 2;                    // units per block
     const int n_aunits = rows >> 2;
     const int n_qunits = cb_n >> 2;
     const int nbox_p = ca_n / p.kc_p;
@@ -179,11 +206,11 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
             mbar_init(smem_u32(&bar_rfree[s]), kWg2TransWarps);
         }
         for (int s = 0; s < p.astages; ++s) {
-            mbar_init(smem_u32(&bar_afull[s]), kWg2AWarps);
+            mbar_init(smem_u32(&bar_afull[s]), awarps);
             mbar_init(smem_u32(&bar_aempty[s]), 1);
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(smem_u32(&bar_qfull[s]), kWg2QWarps);
+            mbar_init(smem_u32(&bar_qfull[s]), qwarps);
             mbar_init(smem_u32(&bar_qempty[s]), 1);
         }
         mbar_init(smem_u32(&bar_accum), 1);
@@ -196,7 +223,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
         const int tap = r0 / ca_n, ca = r0 - tap * ca_n;
         const int kh = tap / p.KW, kw = tap - kh * p.KW;
         const int b = ca / p.kc_p;
-        a_tab[u] = make_int4(b * p.box_p, (ca - b * p.kc_p) >> 2, kh * p.PW + kw, r0 & 127);
+        a_tab[u] = make_int4(b * p.box_p, (ca - b * p.kc_p) >> 2, kh * p.PW + kw, r0 % p.BR);
     }
     for (int u = threadIdx.x; u < n_qunits; u += blockDim.x) {
         const int cb = u << 2;
@@ -208,6 +235,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
+    WG2_KSTAMP(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -225,7 +253,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
                 const int trem = tile - img * p.tiles_per_img;
                 const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
                 const int y0 = ty * p.BH, x0 = tx * p.BW;
-                const uint32_t sp = smem_base + (uint32_t)s * (uint32_t)p.raw_bytes;
+                const uint32_t sp = smem_base + (uint32_t)p.raw_base + (uint32_t)s * (uint32_t)p.raw_bytes;
                 for (int b = 0; b < nbox_p; ++b)
                     tma_load_4d(sp + (uint32_t)(b * p.box_p), &tmap_p, full, ca0 + b * p.kc_p, x0 - p.pad_l,
                                 y0 - p.pad_t, img);
@@ -236,11 +264,10 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, Nmma, 0, 0);
             int item = 0;
             for (int it = 0; it < my_tiles; ++it) {
-                const int qs = it & 1;
-                mbar_wait(smem_u32(&bar_qfull[qs]), (uint32_t)((it >> 1) & 1));
+                const int qs = it % p.qstages;
+                mbar_wait(smem_u32(&bar_qfull[qs]), (uint32_t)((it / p.qstages) & 1));
                 WG2_STAMP(1);
                 const uint32_t qb = smem_base + (uint32_t)p.q_base + (uint32_t)(qs * p.q_slot);
                 for (int b = 0; b < nblk; ++b, ++item) {
@@ -249,16 +276,28 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
                     if (b == 0) WG2_STAMP(2);
                     tc_fence_after();
                     const uint32_t ab = smem_base + (uint32_t)p.a_base + (uint32_t)(as * p.a_slot);
-                    const uint32_t td = tmem_d + (uint32_t)(b * Nmma);
+                    // swap: D[cb][stacked row] with N = rows of this block; else D[stacked row][cb] with N = Nmma
+                    const int nb_rows = min(p.BR, rows - (blk0 + b) * p.BR);
+                    const uint32_t idesc = make_idesc_tf32(128, p.swap ? ((nb_rows + 15) & ~15) : Nmma, 0, 0);
+                    const uint32_t td = tmem_d + (uint32_t)(b * (p.swap ? p.BR : Nmma));
+                    const uint32_t sa = p.swap ? qb : ab, sb = p.swap ? ab : qb;
+                    const uint32_t la = (uint32_t)(p.swap ? p.q_half : p.a_half), lb = (uint32_t)(p.swap ? p.a_half : p.q_half);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
                         const uint32_t ko = (uint32_t)k * 32u;
-                        const uint64_t da = make_smem_desc(ab + ko, 16, 1024, kLayoutSw128);
-                        const uint64_t db = make_smem_desc(qb + ko, 16, 1024, kLayoutSw128);
-                        if (X3) {
-                            const uint64_t dal = make_smem_desc(ab + (uint32_t)p.a_half + ko, 16, 1024, kLayoutSw128);
-                            const uint64_t dbl = make_smem_desc(qb + (uint32_t)p.q_half + ko, 16, 1024, kLayoutSw128);
+                        const uint64_t da = make_smem_desc(sa + ko, 16, 1024, kLayoutSw128);
+                        const uint64_t db = make_smem_desc(sb + ko, 16, 1024, kLayoutSw128);
+                        if (X3 && p.stackm) {
+                            // the 128 A rows starting at the slot hold [Q_hi ; Q_lo]: rows [0,q_rows) of D collect
+                            // hi*hi + hi*lo, rows [q_rows, 2 q_rows) lo*hi + lo*lo; the epilogue adds both row groups
+                            // to the same dw element.  2 MMAs (~137 cycles each) instead of 3 per K-step.
+                            const uint64_t dbl = make_smem_desc(sb + lb + ko, 16, 1024, kLayoutSw128);
+                            umma_tf32(td, da, db, idesc, acc);
+                            umma_tf32(td, da, dbl, idesc, 1u);
+                        } else if (X3) {
+                            const uint64_t dal = make_smem_desc(sa + la + ko, 16, 1024, kLayoutSw128);
+                            const uint64_t dbl = make_smem_desc(sb + lb + ko, 16, 1024, kLayoutSw128);
                             umma_tf32(td, dal, db, idesc, acc);
                             umma_tf32(td, da, dbl, idesc, 1u);
                             umma_tf32(td, da, db, idesc, 1u);
@@ -276,17 +315,17 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
     } else {
         // ===================== transposers (+ tf32 split), then the epilogue =====================
         const int tw = warp - 2;
-        if (tw < kWg2QWarps) {
-            // ---- Q group: Q^T of every chunk into the two Q slots
+        if (tw < qwarps) {
+            // ---- Q group: Q^T of every chunk into the Q slot ring
             for (int it = 0; it < my_tiles; ++it) {
                 const int rs = it % p.rstages;
-                const int qs = it & 1;
+                const int qs = it % p.qstages;
                 mbar_wait(smem_u32(&bar_rfull[rs]), (uint32_t)((it / p.rstages) & 1));
                 if (tw == 0) WG2_STAMP(4);
-                mbar_wait(smem_u32(&bar_qempty[qs]), (uint32_t)(((it >> 1) & 1) ^ 1));
+                mbar_wait(smem_u32(&bar_qempty[qs]), (uint32_t)(((it / p.qstages) & 1) ^ 1));
                 if (tw == 0) WG2_STAMP(5);
-                transpose_units<X3, 4>(q_tab, tw, n_qunits, kWg2QWarps, smem_al + (size_t)rs * p.raw_bytes, p.span_q, lane,
-                                       smem_al + p.q_base + (size_t)qs * p.q_slot, p.q_half, lane);
+                transpose_units<X3, 3>(q_tab, tw, n_qunits, qwarps, smem_al + p.raw_base + (size_t)rs * p.raw_bytes, p.span_q,
+                                       lane, smem_al + p.q_base + (size_t)qs * p.q_slot, p.q_half, lane);
                 if (tw == 0) WG2_STAMP(6);
                 fence_proxy_async_smem();
                 mbar_arrive_warp(smem_u32(&bar_qfull[qs]));
@@ -294,21 +333,21 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
                 if (tw == 0) WG2_STAMP(7);
             }
         } else {
-            // ---- A group: every 128-row block of the stacked P^T, through the ring of operand slots
-            const int gw = tw - kWg2QWarps;
+            // ---- A group: every block of the stacked P^T of this role, through the ring of operand slots
+            const int gw = tw - qwarps;
             const int ry = lane / p.BW, rx = lane - ry * p.BW;
             const int lane_row_p = ry * p.PW + rx;          // this lane's pixel inside the halo box (before the tap shift)
             int item = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int rs = it % p.rstages;
                 mbar_wait(smem_u32(&bar_rfull[rs]), (uint32_t)((it / p.rstages) & 1));
-                const uint8_t* raw = smem_al + (size_t)rs * p.raw_bytes;
+                const uint8_t* raw = smem_al + p.raw_base + (size_t)rs * p.raw_bytes;
                 for (int b = 0; b < nblk; ++b, ++item) {
                     const int as = item % p.astages;
                     mbar_wait(smem_u32(&bar_aempty[as]), (uint32_t)(((item / p.astages) & 1) ^ 1));
                     if (gw == 0 && b == 0) WG2_STAMP(8);
-                    transpose_units<X3, 3>(a_tab, (b << 5) + gw, min(n_aunits, (b + 1) << 5), kWg2AWarps, raw, p.span_p,
-                                           lane_row_p, smem_al + p.a_base + (size_t)as * p.a_slot, p.a_half, lane);
+                    transpose_units<X3, 3>(a_tab, (blk0 + b) * upb + gw, min(n_aunits, (blk0 + b + 1) * upb), awarps, raw,
+                                           p.span_p, lane_row_p, smem_al + p.a_base + (size_t)as * p.a_slot, p.a_half, lane);
                     if (gw == 0 && b == 0) WG2_STAMP(9);
                     fence_proxy_async_smem();
                     mbar_arrive_warp(smem_u32(&bar_afull[as]));
@@ -322,28 +361,72 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
             // ---- epilogue: TMEM lane quadrant = warp % 4; the 4 warps of a quadrant take alternate 16-column groups
             mbar_wait(smem_u32(&bar_accum), 0);
             tc_fence_after();
+            WG2_KSTAMP(2);
             const int q = warp & 3;
             const int cphase = tw >> 2;
-            for (int b = 0; b < nblk; ++b) {
-                const int row = (b << 7) + q * 32 + lane;   // stacked row = accumulator lane
-                const bool row_ok = row < rows;
-                const int tap = row / ca_n, ca = row - tap * ca_n;
-                float* dst_row = p.dw + ((int64_t)tap * p.Ca + ca0 + ca) * p.Cb + cb0;
-                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Nmma);
-                for (int c0 = cphase * 16; c0 < Nmma; c0 += 64) {
-                    float v[16];
-                    tmem_ld16(taddr + (uint32_t)c0, v);
-                    if (row_ok) {
+            if (!p.swap) {
+                for (int b = 0; b < nblk; ++b) {
+                    const int row = ((blk0 + b) << 7) + q * 32 + lane;   // stacked row = accumulator lane
+                    const bool row_ok = row < rows;
+                    const int tap = row / ca_n, ca = row - tap * ca_n;
+                    float* dst_row = p.dw + ((int64_t)tap * p.Ca + ca0 + ca) * p.Cb + cb0;
+                    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Nmma);
+                    for (int c0 = cphase * 16; c0 < Nmma; c0 += 64) {
+                        float v[16];
+                        tmem_ld16(taddr + (uint32_t)c0, v);
+                        if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            if (c0 + j < cb_n) red_add_v4_f32(dst_row + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            for (int j = 0; j < 16; j += 4)
+                                if (c0 + j < cb_n) red_add_v4_f32(dst_row + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
                     }
+                }
+            } else {
+                // accumulator lane = output channel (stackm: a second group of lanes holds the lo-half products of
+                // the same channels), column = stacked row.  Staged through shared memory (free now: every TMA box
+                // is consumed and every MMA retired) so that the hi/lo lane groups are summed on chip and dw gets
+                // 16-byte vector reductions along cb -- per-lane scalar reductions of both groups were ~40 % of
+                // this kernel's time on the backbone layers (L2 atomic throughput, 148 partial tiles).
+                float* const T = reinterpret_cast<float*>(smem_al);
+                const int tp = p.stackm ? 2 * p.q_rows : p.q_rows;       // tile pitch (floats), multiple of 8
+                const int r = q * 32 + lane;
+                const int cb4n = cb_n >> 2;
+                const int et = threadIdx.x - 64;                          // 0..511
+                for (int b = 0; b < nblk; ++b) {
+                    const int r_base = (blk0 + b) * p.BR;
+                    const int nb_rows = min(p.BR, rows - r_base);
+                    if (q * 32 < tp) {
+                        const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.BR);
+                        for (int c0 = cphase * 16; c0 < nb_rows; c0 += 64) {
+                            float v[16];
+                            tmem_ld16(taddr + (uint32_t)c0, v);
+                            if (r < tp) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (c0 + j < nb_rows) T[(c0 + j) * tp + r] = v[j];
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(kWg2TransWarps * 32) : "memory");
+                    for (int idx = et; idx < nb_rows * cb4n; idx += kWg2TransWarps * 32) {
+                        const int j = idx / cb4n, c4 = (idx - j * cb4n) << 2;
+                        float4 sum = *reinterpret_cast<const float4*>(T + j * tp + c4);
+                        if (p.stackm) {
+                            const float4 lo = *reinterpret_cast<const float4*>(T + j * tp + p.q_rows + c4);
+                            sum.x += lo.x; sum.y += lo.y; sum.z += lo.z; sum.w += lo.w;
+                        }
+                        const int row = r_base + j;
+                        const int tap = row / ca_n, ca = row - tap * ca_n;
+                        red_add_v4_f32(p.dw + ((int64_t)tap * p.Ca + ca0 + ca) * p.Cb + cb0 + c4, sum.x, sum.y, sum.z, sum.w);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(kWg2TransWarps * 32) : "memory");
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    WG2_KSTAMP(3);
     if (warp == 1) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
 }
 
@@ -397,54 +480,85 @@ int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st) {
     p.ntiles = a.N * p.tiles_per_img;
     p.kc_p = cp.kc; p.span_p = cp.span;
     p.kc_q = cq.kc; p.span_q = cq.span;
-    // input-channel group: all of Ca when the stacked rows fit 4 M-blocks, else the largest multiple of kc that does
+    // input-channel group: all of Ca when the stacked rows fit 512 accumulator rows/columns, else the largest
+    // multiple of kc that does
     int CaG = a.Ca;
     if (taps * CaG > 512) CaG = (512 / taps) / cp.kc * cp.kc;
     if (CaG < cp.kc) return DL4DS_E_UNSUPPORTED;
     p.CaG = CaG;
     p.ncig = (a.Ca + CaG - 1) / CaG;
-    const int nblk = (taps * CaG + 127) / 128;
-    // output-channel block: nblk accumulators of Nmma columns share the 512 TMEM columns
+    const int rows_g = taps * CaG;
     const int unit = cq.kc > 16 ? cq.kc : 16;
-    int nb_cap = (512 / nblk) / unit * unit;
-    if (nb_cap > 256) nb_cap = 256 / unit * unit;
-    if (nb_cap < unit) return DL4DS_E_UNSUPPORTED;
-    int ncob = (a.Cb + nb_cap - 1) / nb_cap;
-    int nb = ((a.Cb + ncob - 1) / ncob + unit - 1) / unit * unit;
-    if (nb > nb_cap) { nb = nb_cap; ncob = (a.Cb + nb - 1) / nb; }
-    p.Nb = nb; p.ncob = ncob;
-    const int cb_first = a.Cb < nb ? a.Cb : nb;
-    const int nmma_max = (cb_first + 15) & ~15;
-    if (CaG * taps / 4 > kWg2MaxAUnits || cb_first / 4 > kWg2MaxQUnits) return DL4DS_E_UNSUPPORTED;
+    p.swap = a.Cb <= 128 ? 1 : 0;
+    int nmma_max, cb_first, tmem_need;
+    if (p.swap) {
+        // A = Q^T (all of Cb, one M tile), B = blocks of <= 256 stacked rows, all blocks in one role
+        p.Nb = a.Cb; p.ncob = 1;
+        cb_first = a.Cb;
+        nmma_max = (a.Cb + 15) & ~15;
+        const int nnb = (rows_g + 255) / 256;
+        p.BR = ((rows_g + nnb - 1) / nnb + 15) & ~15;
+        p.bpr = nnb; p.nrg = 1;
+        tmem_need = nnb * p.BR;
+    } else {
+        // A = 128-row blocks of stacked rows, B = Q^T with N = Cb (<= 256 per output-channel role); as many blocks
+        // per role as accumulators fit TMEM, the rest goes to further row-group roles
+        int ncob = (a.Cb + 255) / 256;
+        int nb = ((a.Cb + ncob - 1) / ncob + unit - 1) / unit * unit;
+        if (nb > 256) { nb = 256 / unit * unit; ncob = (a.Cb + nb - 1) / nb; }
+        p.Nb = nb; p.ncob = ncob;
+        cb_first = a.Cb < nb ? a.Cb : nb;
+        nmma_max = (cb_first + 15) & ~15;
+        p.BR = 128;
+        const int nblk_total = (rows_g + 127) / 128;
+        int bpr = 512 / nmma_max;
+        if (bpr > nblk_total) bpr = nblk_total;
+        p.bpr = bpr;
+        p.nrg = (nblk_total + bpr - 1) / bpr;
+        tmem_need = bpr * nmma_max;
+    }
+    if (rows_g / 4 > kWg2MaxAUnits || cb_first / 4 > kWg2MaxQUnits) return DL4DS_E_UNSUPPORTED;
     p.tx_p = cp.span * p.PW * PH;
     p.tx_q = cq.span * 32;
     p.box_p = (p.tx_p + 1023) & ~1023;
     p.box_q = (p.tx_q + 1023) & ~1023;
     p.nbox_p_max = CaG / cp.kc;
     p.raw_bytes = p.nbox_p_max * p.box_p + (cb_first / cq.kc) * p.box_q;
-    p.a_half = 128 * 128;
-    p.q_half = nmma_max * 128;
+    p.a_half = p.BR * 128;
+    p.q_rows = p.swap ? ((cb_first + 7) & ~7) : nmma_max;
+    p.q_half = p.q_rows * 128;
+    static const bool no_stack = [] { const char* e = getenv("DL4DS_TC_NO_STACKM"); return e && e[0] == '1'; }();
+    p.stackm = (p.swap && x3 && 2 * p.q_rows <= 128 && !no_stack) ? 1 : 0;
     p.a_slot = p.a_half * (x3 ? 2 : 1);
     p.q_slot = p.q_half * (x3 ? 2 : 1);
     int cols = 32;
-    while (cols < nblk * nmma_max) cols *= 2;
+    while (cols < tmem_need) cols *= 2;
     if (cols > 512) return DL4DS_E_UNSUPPORTED;
     p.tmem_cols = cols;
-    // shared-memory plan: 2 Q slots, A-slot ring (3 when it fits: the transposers run up to two blocks ahead of the
-    // MMA warp), raw TMA ring of 2..6 stages (latency cover); a 4th A slot if there is still room
+    // transposer warps: the Q group gets a share proportional to its units per chunk (4 or 8 of the 16 warps)
+    const int a_units_chunk = (p.bpr * p.BR < rows_g ? p.bpr * p.BR : rows_g) / 4;
+    p.qwarps = (cb_first / 4) * 3 >= a_units_chunk * 2 ? 8 : 4;
+    // shared-memory plan: [Q slots][raw TMA ring][A-slot ring].  Minimum 1 Q slot, 2 raw stages, 2 A slots; spare
+    // capacity goes to a 2nd Q slot, a 3rd raw stage, a 3rd A slot, then raw stages up to 6.  (swap: an A-operand
+    // read of the short Q^T tile covers 128 rows = 16 KB from the slot start and runs on into the raw ring.)
     const int budget = 220 * 1024;
-    auto need = [&](int r, int s) { return r * p.raw_bytes + s * p.a_slot + 2 * p.q_slot; };
-    int ast = 3, rst = 2;
-    while (ast > 2 && need(rst, ast) > budget) --ast;
-    if (need(rst, ast) > budget) return DL4DS_E_UNSUPPORTED;
-    while (rst < 4 && need(rst + 1, ast) <= budget) ++rst;
-    if (ast == 3 && need(rst, 4) <= budget) ast = 4;
-    while (rst < 6 && need(rst + 1, ast) <= budget) ++rst;
-    p.rstages = rst; p.astages = ast;
-    p.a_base = rst * p.raw_bytes;
-    p.q_base = p.a_base + ast * p.a_slot;
-    const size_t smem = (size_t)need(rst, ast) + 1024;
-    const int nroles = p.ncig * p.ncob;
+    auto need = [&](int qn, int r, int s) { return qn * p.q_slot + r * p.raw_bytes + s * p.a_slot; };
+    int qst = 1, rst = 2, ast = 2;
+    if (need(qst, rst, ast) > budget) return DL4DS_E_UNSUPPORTED;
+    if (need(2, rst, ast) <= budget) qst = 2;
+    if (need(qst, 3, ast) <= budget) rst = 3;
+    if (need(qst, rst, 3) <= budget) ast = 3;
+    while (rst < 6 && need(qst, rst + 1, ast) <= budget) ++rst;
+    p.qstages = qst; p.rstages = rst; p.astages = ast;
+    p.q_base = 0;
+    p.raw_base = qst * p.q_slot;
+    p.a_base = p.raw_base + rst * p.raw_bytes;
+    size_t smem = (size_t)need(qst, rst, ast) + 1024;
+    if (p.swap && smem < (size_t)(p.q_slot * qst + 33 * 1024)) smem = (size_t)(p.q_slot * qst + 33 * 1024);
+    const size_t epi_tile = (size_t)p.BR * (p.stackm ? 2 * p.q_rows : p.q_rows) * 4 + 1024;   // swap epilogue staging
+    if (p.swap && smem < epi_tile) smem = epi_tile;
+    if (smem > 221 * 1024) return DL4DS_E_UNSUPPORTED;
+    const int nroles = p.ncig * p.ncob * p.nrg;
     int splits = kNumSMs / nroles;
     if (splits < 1) splits = 1;
     if (splits > p.ntiles) splits = p.ntiles;

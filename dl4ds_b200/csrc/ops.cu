@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(
                     const int di = grp / r, dj = grp - di * r;
                     const int64_t hp = ((int64_t)(n * Ho * r + oy * r + di)) * (Wo * r) + ox * r + dj;
                     g = __ldg(dy + hp * dy_ld + cc);
+                    if (act != DL4DS_ACT_NONE) g *= act_grad_from_out(__ldg(y + hp * y_ld + cc), act);
                 } else {
                     g = __ldg(dy + src_base * dy_ld + c);
                     if (act != DL4DS_ACT_NONE) g *= act_grad_from_out(__ldg(y + p * y_ld + c), act);
@@ -221,6 +222,83 @@ __global__ void group_scale_kernel(const float* __restrict__ x, int x_ld, float*
         else if (mode == 1) v = __ldg(x + p * x_ld + c) * __ldg(s + g * C + c) + __ldg(dm + g * C + c) * inv;
         else v = __ldg(dm + g * C + c) * inv;
         y[p * y_ld + c] = v;
+    }
+}
+
+// 16-byte variant (C % 4 == 0, pitches % 4 == 0, 16-byte aligned, < 2^31 float4 items): 32-bit index math, one
+// float4 per thread and iteration (the scalar kernel above spends its time in 64-bit divisions: 55 us for the
+// 33.5 MB HR tensor of the headline model, 5x the HBM roofline)
+__global__ void __launch_bounds__(256) group_scale_vec4_kernel(
+    const float* __restrict__ x, int x_ld, float* __restrict__ y, int y_ld, const float* __restrict__ s,
+    const float* __restrict__ dm, float inv, int n_items, int ppg, int inner, int C, int mode) {
+    const int G = C >> 2;
+    const int span = ppg * inner;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n_items; i += gridDim.x * 256) {
+        const int p = i / G, c = (i - p * G) << 2;
+        const int g = inner == 1 ? p / ppg : (p / span) * inner + (p % inner);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mode != 2) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + (int64_t)p * x_ld + c));
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(s + (int64_t)g * C + c));
+            v = make_float4(a.x * sc.x, a.y * sc.y, a.z * sc.z, a.w * sc.w);
+        }
+        if (mode != 0) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(dm + (int64_t)g * C + c));
+            v.x += d.x * inv; v.y += d.y * inv; v.z += d.z * inv; v.w += d.w * inv;
+        }
+        *reinterpret_cast<float4*>(y + (int64_t)p * y_ld + c) = v;
+    }
+}
+
+// 16-byte variant of group_sum_kernel for C % 4 == 0, C <= 64, inner == 1: block = (C/4, 256/(C/4)), 4 pixels in flight
+template <bool kMulB>
+__global__ void __launch_bounds__(256) group_sum_vec4_kernel(
+    const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
+    float* __restrict__ out, int ppg, int C) {
+    __shared__ float4 red[256];
+    const int TX = blockDim.x, PY = blockDim.y;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int g = blockIdx.y;
+    const int64_t p0 = (int64_t)g * ppg;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int step = gridDim.x * PY;
+    int q = blockIdx.x * PY + ty;
+    for (; q + 3 * step < ppg; q += 4 * step) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(a + (p0 + q + u * step) * a_ld) + tx);
+        if (kMulB) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(b + (p0 + q + u * step) * b_ld) + tx);
+                v[u].x *= w.x; v[u].y *= w.y; v[u].z *= w.z; v[u].w *= w.w;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; q < ppg; q += step) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(a + (p0 + q) * a_ld) + tx);
+        if (kMulB) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(b + (p0 + q) * b_ld) + tx);
+            v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w;
+        }
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    red[ty * TX + tx] = acc;
+    __syncthreads();
+    for (int h = PY >> 1; h > 0; h >>= 1) {
+        if (ty < h) {
+            const float4 t = red[(ty + h) * TX + tx];
+            float4& r = red[ty * TX + tx];
+            r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+        }
+        __syncthreads();
+    }
+    if (ty == 0) {
+        const float4 r = red[tx];
+        float* o = out + (int64_t)g * C + tx * 4;
+        atomicAdd(o + 0, r.x); atomicAdd(o + 1, r.y); atomicAdd(o + 2, r.z); atomicAdd(o + 3, r.w);
     }
 }
 
@@ -688,11 +766,109 @@ static void pick_xy(int C, int& TX, int& KS) {
     KS = (int)cdiv(C, TX);
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Composition of a linear convolution + depth_to_space(r) with the 1x1 convolution that follows it
+// (the last x2 stage of SubpixelConvolutionBlock, blocks.py:421-427, feeding TransitionLast,
+// sp_postups.py:205 / blocks.py:299): a 1x1 conv after depth_to_space applies the same Cm x Co matrix
+// to each of the r*r sub-pixel channel groups, so
+//   W_eff[row][d*Co + co] = sum_c W1[row][d*Cm + c] * W2[c][co]          row = (tap, ci), d < r*r
+//   b_eff[d*Co + co]      = sum_c b1[d*Cm + c] * W2[c][co] + b2[co]
+// and the Cm-channel HR tensor (201 MB per step for the headline model) never exists.  The backward
+// kernel is the exact chain rule from (dW_eff, db_eff) to the four original parameter gradients.
+// -------------------------------------------------------------------------------------------------
+__global__ void spc_compose_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                   const float* __restrict__ w2, const float* __restrict__ b2,
+                                   float* __restrict__ weff, float* __restrict__ beff, int rows, int Cm, int Co, int R2) {
+    const int ne = R2 * Co;
+    const int total = (rows + 1) * ne;                       // row == rows: the bias row
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int row = i / ne, e = i - row * ne;
+        const int d = e / Co, co = e - d * Co;
+        const float* src = (row < rows ? w1 + (int64_t)row * R2 * Cm : b1) + d * Cm;
+        float acc = 0.0f;
+        for (int c = 0; c < Cm; ++c) acc = fmaf(__ldg(src + c), __ldg(w2 + c * Co + co), acc);
+        if (row < rows) weff[(int64_t)row * ne + e] = acc;
+        else beff[e] = acc + (b2 ? __ldg(b2 + co) : 0.0f);
+    }
+}
+
+// gW1[row][d*Cm + c] += sum_co dWeff[row][d*Co + co] * W2[c][co]   (row == rows: gb1 from dbeff)
+__global__ void spc_chain_w1_kernel(const float* __restrict__ dweff, const float* __restrict__ dbeff,
+                                    const float* __restrict__ w2, float* __restrict__ gw1, float* __restrict__ gb1,
+                                    int rows, int Cm, int Co, int R2) {
+    const int n1 = R2 * Cm, ne = R2 * Co;
+    const int total = (rows + 1) * n1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int row = i / n1, e = i - row * n1;
+        const int d = e / Cm, c = e - d * Cm;
+        const float* src = (row < rows ? dweff + (int64_t)row * ne : dbeff) + d * Co;
+        float acc = 0.0f;
+        for (int co = 0; co < Co; ++co) acc = fmaf(__ldg(src + co), __ldg(w2 + c * Co + co), acc);
+        if (row < rows) gw1[(int64_t)row * n1 + e] += acc;
+        else if (gb1) gb1[e] += acc;
+    }
+}
+
+// gW2[c][co] += sum_{row,d} W1[row][d*Cm+c] * dWeff[row][d*Co+co] + sum_d b1[d*Cm+c] * dbeff[d*Co+co]
+// gb2[co]    += sum_d dbeff[d*Co+co]                     one block per (c, co): warp-shuffle + smem reduction
+__global__ void __launch_bounds__(256) spc_chain_w2_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
+                                                           const float* __restrict__ dweff, const float* __restrict__ dbeff,
+                                                           float* __restrict__ gw2, float* __restrict__ gb2,
+                                                           int rows, int Cm, int Co, int R2) {
+    __shared__ float red[8];
+    const int c = blockIdx.x / Co, co = blockIdx.x - c * Co;
+    const int n1 = R2 * Cm, ne = R2 * Co;
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < (rows + 1) * R2; i += 256) {
+        const int row = i / R2, d = i - row * R2;
+        const float a = row < rows ? __ldg(w1 + (int64_t)row * n1 + d * Cm + c) : (b1 ? __ldg(b1 + d * Cm + c) : 0.0f);
+        const float g = row < rows ? __ldg(dweff + (int64_t)row * ne + d * Co + co) : __ldg(dbeff + d * Co + co);
+        acc = fmaf(a, g, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        gw2[c * Co + co] += t;
+        if (c == 0 && gb2) {
+            float sb = 0.0f;
+            for (int d = 0; d < R2; ++d) sb += __ldg(dbeff + d * Co + co);
+            gb2[co] += sb;
+        }
+    }
+}
+
 }  // namespace dl4ds
 
 using namespace dl4ds;
 
 extern "C" {
+
+int dl4ds_spc_pointwise_compose(const float* w1, const float* b1, const float* w2, const float* b2,
+                                float* weff, float* beff, int rows, int Cm, int Co, int r, void* stream) {
+    DL4DS_REQUIRE(w1 && b1 && w2 && weff && beff, DL4DS_E_BADARG, "spc_pointwise_compose: null pointer");
+    DL4DS_REQUIRE(rows > 0 && Cm > 0 && Co > 0 && r > 1, DL4DS_E_SHAPE, "spc_pointwise_compose: bad shape");
+    const int total = (rows + 1) * r * r * Co;
+    spc_compose_kernel<<<(unsigned)cdiv(total, 256), 256, 0, as_stream(stream)>>>(w1, b1, w2, b2, weff, beff, rows, Cm, Co, r * r);
+    return check_launch("spc_compose");
+}
+
+int dl4ds_spc_pointwise_chain(const float* w1, const float* b1, const float* w2, const float* dweff, const float* dbeff,
+                              float* gw1, float* gb1, float* gw2, float* gb2, int rows, int Cm, int Co, int r,
+                              void* stream) {
+    DL4DS_REQUIRE(w1 && w2 && dweff && dbeff && gw1 && gw2, DL4DS_E_BADARG, "spc_pointwise_chain: null pointer");
+    DL4DS_REQUIRE(rows > 0 && Cm > 0 && Co > 0 && r > 1, DL4DS_E_SHAPE, "spc_pointwise_chain: bad shape");
+    cudaStream_t st = as_stream(stream);
+    const int total = (rows + 1) * r * r * Cm;
+    spc_chain_w1_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(dweff, dbeff, w2, gw1, gb1, rows, Cm, Co, r * r);
+    int rc = check_launch("spc_chain_w1");
+    if (rc) return rc;
+    spc_chain_w2_kernel<<<(unsigned)(Cm * Co), 256, 0, st>>>(w1, b1, dweff, dbeff, gw2, gb2, rows, Cm, Co, r * r);
+    return check_launch("spc_chain_w2");
+}
 
 int dl4ds_bias_act_bwd(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld,
                        float* dbias, int N, int Ho, int Wo, int C, int act, int d2s_r, void* stream) {
@@ -701,8 +877,8 @@ int dl4ds_bias_act_bwd(const float* dy, int dy_ld, const float* y, int y_ld, flo
     DL4DS_REQUIRE(act >= 0 && act <= 3, DL4DS_E_BADARG, "bias_act_bwd: act");
     if (d2s_r <= 1) d2s_r = 1;
     if (d2s_r > 1) {
-        DL4DS_REQUIRE(act == DL4DS_ACT_NONE && C % (d2s_r * d2s_r) == 0, DL4DS_E_BADARG,
-                      "bias_act_bwd: d2s needs act NONE and C %% r^2 == 0");
+        DL4DS_REQUIRE(C % (d2s_r * d2s_r) == 0, DL4DS_E_BADARG, "bias_act_bwd: d2s needs C %% r^2 == 0");
+        DL4DS_REQUIRE(act == DL4DS_ACT_NONE || y != nullptr, DL4DS_E_BADARG, "bias_act_bwd: y needed");
         DL4DS_REQUIRE(dz != nullptr && dz != dy, DL4DS_E_BADARG, "bias_act_bwd: d2s needs distinct dz");
     } else {
         DL4DS_REQUIRE(act == DL4DS_ACT_NONE || y != nullptr, DL4DS_E_BADARG, "bias_act_bwd: y needed");
@@ -770,6 +946,19 @@ int dl4ds_axpby(float a, const float* x, float b, float* y, int64_t n, void* str
     return launch1d("axpby", axpby_kernel, n, as_stream(stream), a, x, b, y, n);
 }
 
+static int group_scale(const char* what, const float* x, int x_ld, float* y, int y_ld, const float* s, const float* dm,
+                       float inv, int64_t n_pix, int64_t ppg, int inner, int C, int mode, cudaStream_t st) {
+    const int64_t n4 = n_pix * (C / 4);
+    if (C % 4 == 0 && y_ld % 4 == 0 && aligned16(y) && (mode == 2 || (x_ld % 4 == 0 && aligned16(x) && aligned16(s))) &&
+        (mode == 0 || aligned16(dm)) && n4 < (1ll << 31) && ppg * inner < (1ll << 31)) {
+        int64_t blocks = (n4 + 255) / 256;
+        if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+        group_scale_vec4_kernel<<<(int)blocks, 256, 0, st>>>(x, x_ld, y, y_ld, s, dm, inv, (int)n4, (int)ppg, inner, C, mode);
+        return check_launch(what);
+    }
+    return launch1d(what, group_scale_kernel, n_pix * C, st, x, x_ld, y, y_ld, s, dm, inv, n_pix, ppg, inner, C, mode);
+}
+
 static int group_sum(const float* a, int a_ld, const float* b, int b_ld, float* out, int n_groups,
                      int64_t ppg, int inner, int C, cudaStream_t st) {
     int TX, KS;
@@ -783,6 +972,22 @@ static int group_sum(const float* a, int a_ld, const float* b, int b_ld, float* 
     dim3 grid(chunks, n_groups), block(TX, PY);
     if (cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_groups * C, st) != cudaSuccess)
         return check_launch("group_sum memset");
+    {
+        const int G4 = C / 4;
+        const bool pow2 = G4 > 0 && (G4 & (G4 - 1)) == 0;
+        if (inner == 1 && C % 4 == 0 && pow2 && G4 <= 16 && a_ld % 4 == 0 && aligned16(a) && ppg < (1ll << 30) &&
+            (!b || (b_ld % 4 == 0 && aligned16(b)))) {
+            const int py = 256 / G4;
+            int ch = (int)cdiv(ppg, (int64_t)py * 8);
+            const int mc = (int)cdiv(8 * kNumSMs, n_groups);
+            if (ch > mc) ch = mc;
+            if (ch < 1) ch = 1;
+            dim3 g2(ch, n_groups), b2(G4, py);
+            if (b) group_sum_vec4_kernel<true><<<g2, b2, 0, st>>>(a, a_ld, b, b_ld, out, (int)ppg, C);
+            else group_sum_vec4_kernel<false><<<g2, b2, 0, st>>>(a, a_ld, b, b_ld, out, (int)ppg, C);
+            return check_launch("group_sum_vec4");
+        }
+    }
 #define LAUNCH_GS(K)                                                                              \
     do {                                                                                          \
         if (b) group_sum_kernel<K, true><<<grid, block, 0, st>>>(a, a_ld, b, b_ld, out, ppg, inner, C); \
@@ -814,8 +1019,7 @@ int dl4ds_channel_attention_fwd(const float* x, int x_ld, float* y, int y_ld,
     rc = check_launch("attention_mlp_fwd");
     if (rc) return rc;
     const int64_t n_pix = (int64_t)n_groups * pix_per_group;
-    return launch1d("attention_scale", group_scale_kernel, n_pix * C, st, x, x_ld, y, y_ld, scale,
-                    (const float*)nullptr, 0.0f, n_pix, pix_per_group, inner, C, 0);
+    return group_scale("attention_scale", x, x_ld, y, y_ld, scale, nullptr, 0.0f, n_pix, pix_per_group, inner, C, 0, st);
 }
 
 int dl4ds_channel_attention_bwd(const float* x, int x_ld, const float* dy, int dy_ld,
@@ -840,8 +1044,7 @@ int dl4ds_channel_attention_bwd(const float* x, int x_ld, const float* dy, int d
     rc = check_launch("attention_mlp_bwd");
     if (rc) return rc;
     const int64_t n_pix = (int64_t)n_groups * pix_per_group;
-    return launch1d("attention_bwd_scale", group_scale_kernel, n_pix * C, st, dy, dy_ld, dx, dx_ld, scale,
-                    (const float*)dsum, inv, n_pix, pix_per_group, inner, C, 1);
+    return group_scale("attention_bwd_scale", dy, dy_ld, dx, dx_ld, scale, dsum, inv, n_pix, pix_per_group, inner, C, 1, st);
 }
 
 int dl4ds_group_mean_fwd(const float* x, int x_ld, float* out, int n_groups, int64_t pix_per_group,
@@ -859,9 +1062,8 @@ int dl4ds_group_mean_bwd(const float* dout, float* dx, int dx_ld, int n_groups, 
                          int C, void* stream) {
     DL4DS_REQUIRE(dout && dx, DL4DS_E_BADARG, "group_mean_bwd: null pointer");
     const int64_t n_pix = (int64_t)n_groups * pix_per_group;
-    return launch1d("group_mean_bwd", group_scale_kernel, n_pix * C, as_stream(stream),
-                    (const float*)nullptr, 0, dx, dx_ld, (const float*)nullptr, dout,
-                    1.0f / (float)pix_per_group, n_pix, pix_per_group, 1, C, 2);
+    return group_scale("group_mean_bwd", nullptr, 0, dx, dx_ld, nullptr, dout, 1.0f / (float)pix_per_group, n_pix,
+                       pix_per_group, 1, C, 2, as_stream(stream));
 }
 
 int dl4ds_pixel_loss(const float* y_pred, const float* y_true, float* loss_out, float* dy,

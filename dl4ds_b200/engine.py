@@ -321,6 +321,66 @@ class Ctx:
         self._record(bwd)
         return out
 
+    def conv_d2s_pointwise(self, x, name1, cm, name2, co, act=None, r=2, k=3):
+        """The last x`r` stage of SubpixelConvolutionBlock -- Conv2D(r*r*cm, k, linear) + depth_to_space(r),
+        blocks.py:421-427 -- COMPOSED with the 1x1 convolution (+bias +activation) that consumes it
+        (TransitionLast, sp_postups.py:205 / blocks.py:299).  Both maps are linear, so the pair equals one
+        k x k convolution to r*r*co channels + depth_to_space whose weights are W1 (x) W2
+        (``dl4ds_spc_pointwise_compose``); the cm-channel HR tensor is never written.  The backward pass
+        differentiates the composed layer and maps (dW_eff, db_eff) back onto the four original parameter
+        gradients with the exact chain rule (``dl4ds_spc_pointwise_chain``).  Results equal the unfused
+        graph up to fp32 re-association."""
+        w1, b1 = self._p(name1 + '/kernel'), self._p(name1 + '/bias')
+        w2, b2 = self._p(name2 + '/kernel'), self._p(name2 + '/bias')
+        R2 = r * r
+        assert tuple(w1.shape) == (k, k, x.C, R2 * cm) and tuple(w2.shape) == (1, 1, cm, co), (w1.shape, w2.shape)
+        dev = self.device
+        rows, ce = k * k * x.C, R2 * co
+        weff = torch.empty((k, k, x.C, ce), dtype=torch.float32, device=dev)
+        beff = torch.empty(ce, dtype=torch.float32, device=dev)
+        self._call('dl4ds_spc_pointwise_compose', w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                   weff.data_ptr(), beff.data_ptr(), rows, cm, co, r, _stream())
+        Ho, pt = same_pads(x.H, k, 1)
+        Wo, pl = same_pads(x.W, k, 1)
+        out = new_var(x.N, Ho * r, Wo * r, co, dev)
+        a = ACT[act]
+        label = '%s*%s' % (name1, name2)
+        ws = self._conv_ws(x.N, x.H, x.W, x.C, Ho, Wo, ce, k, 1, 1, r)
+        self._timed('%s:fwd@%dx%d' % (label, x.H, x.W),
+                    'dl4ds_conv2d_fwd', x.ptr, x.ld, weff.data_ptr(), beff.data_ptr(), None, 0, out.ptr, out.ld,
+                    x.N, x.H, x.W, x.C, Ho, Wo, ce, k, k, 1, 1, pt, pl, W_HWIO, a, r, 0, self.math,
+                    ws.data_ptr() if ws is not None else None, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            pg = self.param_grads
+            dz = new_var(x.N, Ho, Wo, ce, dev)
+            dbeff = torch.zeros(ce, dtype=torch.float32, device=dev)
+            self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dz.ptr, dz.ld,
+                       dbeff.data_ptr() if pg else None, x.N, Ho, Wo, ce, a, r, _stream())
+            if pg:
+                dweff = torch.zeros_like(weff)
+                self._wgrad(x, dz, dweff, k, 1, pt, pl, label='%s:wgrad@%dx%d' % (label, x.H, x.W))
+                self.launches += 1
+                self._call('dl4ds_spc_pointwise_chain', w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                           dweff.data_ptr(), dbeff.data_ptr(), self._g(name1 + '/kernel').data_ptr(),
+                           self._g(name1 + '/bias').data_ptr(), self._g(name2 + '/kernel').data_ptr(),
+                           self._g(name2 + '/bias').data_ptr(), rows, cm, co, r, _stream())
+            if x.requires_grad:
+                def wr(dst, beta):
+                    ws2 = self._conv_ws(x.N, Ho, Wo, ce, x.H, x.W, x.C, k, 1, 1, 1)
+                    self._timed('%s:dgrad@%dx%d' % (label, x.H, x.W),
+                                'dl4ds_conv2d_fwd', dz.ptr, dz.ld, weff.data_ptr(), None, None, 0,
+                                dst.ptr, dst.ld, x.N, Ho, Wo, ce, x.H, x.W, x.C, k, k, 1, 1,
+                                k - 1 - pt, k - 1 - pl, W_FLIP_T, 0, 1, beta, self.math,
+                                ws2.data_ptr() if ws2 is not None else None, _stream())
+                self._acc(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
     def _wgrad(self, P, Q, dw, k, stride, pt, pl, label='wgrad'):
         ws_bytes = _lib.load().dl4ds_conv2d_wgrad_workspace_bytes(P.N, Q.H, Q.W, P.C, Q.C, k, k, self.math)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device) if ws_bytes > 0 else None

@@ -66,6 +66,7 @@ class Model:
         self.macs_per_sample = sc.macs // n0 if len(self.input_shapes[0]) == 3 else sc.macs
         self.macs_dgrad_per_sample = sc.macs_dgrad
         self.layer_macs_per_sample = dict(sc.layer_macs)
+        self.macs_saved_per_sample = sc.macs_saved       # forward MACs of the reference graph removed by composition
         self.output_shape = out.shape[1:]
         self.arena = None
 
@@ -227,9 +228,13 @@ def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activatio
 
 
 def _tail(c, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation, output_activation,
-          localcon_layer):
+          localcon_layer, transition_done=False):
     """LCB, HR aux branch, TransitionLast, ConvBlock(att), ConvBlock(out)
-    -- sp_postups.py:184-212, sp_preups.py:155-183,291-309."""
+    -- sp_postups.py:184-212, sp_preups.py:155-183,291-309.  ``transition_done``: TransitionLast was already
+    applied by the caller (composed with the last sub-pixel stage)."""
+    if transition_done:
+        x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True)
+        return B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation)
     if localcon_layer:
         lws = B.localized_conv_block(c, 'LocalizedConvBlock', x, 2)
         x = c.concat([x, lws])
@@ -249,8 +254,9 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
                        n_channels_out=1, n_filters=8, n_blocks=6, dropout_rate=0,
                        dropout_variant=None, normalization=None, attention=False, activation='relu',
                        output_activation=None, rc_interpolation='bilinear', localcon_layer=False,
-                       math='fp32'):
-    """net_postupsampling -- sp_postups.py:14-217."""
+                       math='fp32', fuse_spc_transition=True):
+    """net_postupsampling -- sp_postups.py:14-217.  ``fuse_spc_transition`` (an addition): compose the last
+    sub-pixel stage with TransitionLast when nothing sits between them (same function, same parameters)."""
     _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
     if upsampling not in POSTUPSAMPLING_METHODS:
         raise ValueError('`upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
@@ -261,15 +267,22 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
 
     def fn(c, inputs):
         x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation)
+        fused = False
         if upsampling == 'spc':
-            x = B.subpixel_block(c, 'SubpixelConvolution', x, scale, nf)
+            if fuse_spc_transition and not aux and not localcon_layer:
+                # nothing sits between the sub-pixel block and TransitionLast (sp_postups.py:172-205):
+                # compose the last x2 stage with the 1x1 convolution
+                x = B.subpixel_transition(c, 'SubpixelConvolution', x, scale, nf, 'TransitionLast', n_filters)
+                fused = True
+            else:
+                x = B.subpixel_block(c, 'SubpixelConvolution', x, scale, nf)
         elif upsampling == 'rc':
             x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf)
         else:
             x = B.transition_block(c, 'TransitionDC', x, n_filters, activation)
             x = B.deconv_block(c, 'Deconvolution', x, scale, nf, activation)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
-                     output_activation, localcon_layer)
+                     output_activation, localcon_layer, transition_done=fused)
 
     ups_total = scale
     if upsampling == 'dc' and scale == 4:

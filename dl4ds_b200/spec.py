@@ -26,7 +26,8 @@ class SpecCtx:
         self.spec = OrderedDict()
         self.macs = 0            # multiply-accumulates of one forward pass (conv / dense / local)
         self.macs_dgrad = 0      # ... of the input-gradient passes backward actually runs
-        self.layer_macs = {}     # '<layer>@HxW' -> MACs of that convolution application
+        self.layer_macs = {}     # '<layer>@HxW' -> MACs of that convolution application (as executed)
+        self.macs_saved = 0      # reference-graph MACs (fwd) that operator composition does not execute
         self.training = False
 
     def _reg(self, name, shape):
@@ -58,6 +59,23 @@ class SpecCtx:
         self._count(name, x, x.N * Ho * Wo * k * k * x.C * cout)
         r = d2s if d2s > 1 else 1
         return SVar(x.N, Ho * r, Wo * r, cout // (r * r))
+
+    def conv_d2s_pointwise(self, x, name1, cm, name2, co, act=None, r=2, k=3):
+        """Shape / parameter / MAC accounting of the composed SubpixelConvolution stage + 1x1 conv.  ``macs``
+        keeps counting the REFERENCE graph (both layers, what Keras executes); ``layer_macs`` and
+        ``macs_saved`` record what the composed kernel really executes."""
+        self._reg(name1 + '/kernel', (k, k, x.C, r * r * cm))
+        self._reg(name1 + '/bias', (r * r * cm,))
+        self._reg(name2 + '/kernel', (1, 1, cm, co))
+        self._reg(name2 + '/bias', (co,))
+        m_conv = x.N * x.H * x.W * k * k * x.C * r * r * cm
+        m_pw = x.N * x.H * r * x.W * r * cm * co
+        m_exec = x.N * x.H * x.W * k * k * x.C * r * r * co
+        self.macs += m_conv + m_pw
+        self.macs_dgrad += (m_conv if x.requires_grad else 0) + m_pw
+        self.macs_saved += m_conv + m_pw - m_exec
+        self.layer_macs['%s*%s@%dx%d' % (name1, name2, x.H, x.W)] = m_exec
+        return SVar(x.N, x.H * r, x.W * r, co)
 
     def conv_transpose(self, x, name, cout, k, stride, act=None):
         self._reg(name + '/kernel', (k, k, cout, x.C))

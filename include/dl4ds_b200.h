@@ -60,7 +60,7 @@ int dl4ds_device_is_sm100(void);
 /* Number of tcgen05 (tensor-core) kernel launches issued by this process so far: lets callers and
  * tests verify that a tensor-core math mode did not silently take the CUDA-core path. */
 int64_t dl4ds_tc_launch_count(void);
-/* Developer aid: a device buffer of >= 1024 int64 that CTA (0,0) of the weight-gradient tensor-core kernel
+/* Developer aid: a device buffer of >= 1088 int64 that CTA (0,0) of the weight-gradient tensor-core kernel
  * fills with clock64() stamps of its pipeline stages (scratch/wg2_stamps.py); NULL (default) disables it. */
 int dl4ds_debug_set_buffer(void* dev_i64);
 
@@ -109,10 +109,23 @@ int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float
                        int KH, int KW, int stride, int pad_t, int pad_l,
                        void* ws, int math_mode, void* stream);
 
+/* SubpixelConvolutionBlock's last x2 stage (linear Conv2D + depth_to_space(r), blocks.py:421-427) composed with
+ * the 1x1 convolution that consumes it (TransitionLast, sp_postups.py:205 / blocks.py:299):
+ *   weff[row][d*Co+co] = sum_c w1[row][d*Cm+c] * w2[c][co],  beff[d*Co+co] = sum_c b1[d*Cm+c]*w2[c][co] + b2[co]
+ * (row = (tap, ci) < rows, d < r*r).  conv2d_fwd(x, weff, beff, act, d2s_r=r) then equals
+ * act(conv1x1(depth_to_space(conv(x, w1) + b1), w2) + b2) up to fp32 re-association, and the Cm-channel HR tensor is
+ * never materialised.  _chain is the exact chain rule from (dweff, dbeff) to the original parameter gradients
+ * (all four accumulate; gb1 / gb2 may be NULL). */
+int dl4ds_spc_pointwise_compose(const float* w1, const float* b1, const float* w2, const float* b2,
+                                float* weff, float* beff, int rows, int Cm, int Co, int r, void* stream);
+int dl4ds_spc_pointwise_chain(const float* w1, const float* b1, const float* w2, const float* dweff, const float* dbeff,
+                              float* gw1, float* gb1, float* gw2, float* gb2, int rows, int Cm, int Co, int r,
+                              void* stream);
+
 /* Backward of the fused bias+activation(+depth_to_space) epilogue:
  *   dz = dy * act'(y)   (act' expressed through the stored output y; NONE: dz = dy)
  *   dbias[c] += sum_pixels dz[.,c]          (dbias may be NULL)
- * With d2s_r>1 (y unused, act must be NONE) dy is the HR-layout gradient (N,Ho*r,Wo*r,C/(r*r)) and
+ * With d2s_r>1 dy (and y, read only when act != NONE) are in the HR layout (N,Ho*r,Wo*r,C/(r*r)) and
  * dz is written un-shuffled (N,Ho,Wo,C) -- the space_to_depth adjoint of blocks.py:427.
  * dz may alias dy when d2s_r==1.  n_pix = N*Ho*Wo. */
 int dl4ds_bias_act_bwd(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld,

@@ -13,7 +13,7 @@ lib = _lib.load()
 P = torch.randn(N, H, W, Ca, device=dev)
 Q = torch.randn(N, H, W, Cb, device=dev)
 dw = torch.zeros(k, k, Ca, Cb, device=dev)
-dbg = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+dbg = torch.zeros(64 * 16 + 64, dtype=torch.int64, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 names = ['tma:rfree', 'mma:qfull', 'mma:afull0', 'mma:issued', 'q:rfull', 'q:qempty', 'q:done', 'q:arrived',
          'a:b0-go', 'a:b0-done', 'a:b0-arr', 'a:rfree']
@@ -24,7 +24,9 @@ for rep in range(3):
               k // 2, k // 2, None, MATH[math], st)
     torch.cuda.synchronize()
 lib.dl4ds_debug_set_buffer(None)
-t = dbg.cpu().view(64, 16)
+k = dbg.cpu()[1024:1028]
+print('kernel stamps (clk): setup %d, main loop %d, epilogue %d' % (int(k[1] - k[0]), int(k[2] - k[1]), int(k[3] - k[2])))
+t = dbg.cpu()[:1024].view(64, 16)
 t0 = int(t[0][t[0] > 0].min())
 print('chunk ' + ' '.join('%10s' % n for n in names))
 for it in range(64):

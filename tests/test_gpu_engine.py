@@ -365,3 +365,23 @@ def test_wgrad_stacked_taps_on_concat_slices(cuda):
         a = R.act(R._conv(p, 'a', x, 16), 'tanh')
         return R._nhwc(R.act(R._conv(p, 'b', torch.cat([a, x], 1), 24), 'tanh'))
     compare(fn, ofn, [(2, 32, 32, 8)], cuda, math='tf32x3', **TC_TOL['tf32x3'])
+
+
+# ------------------------------------------------------------------------------------------ composed SPC stage + 1x1
+@pytest.mark.parametrize('math', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('scale,cin,hw', [(4, 48, 16), (2, 16, 32), (4, 8, 32)])
+def test_subpixel_transition_composed(cuda, math, scale, cin, hw):
+    """SubpixelConvolutionBlock + TransitionLast with the last x2 stage composed with the 1x1 convolution
+    (Ctx.conv_d2s_pointwise) against the oracle's two separate blocks: forward, input gradient and all four
+    parameter gradients (chain rule back onto conv2x / TransitionLast, shared conv2x summed over stages)."""
+    fn = lambda c, xs: B.subpixel_transition(c, 'spc', xs[0], scale, cin, 'tl', 8, 'tanh')
+    ofn = _o(lambda p, xs: R.transition_block(p, 'tl', R.subpixel_block(p, 'spc', xs[0], scale, cin), 8, 'tanh'))
+    tol = dict(tol=2e-5, gtol=2e-4) if math == 'fp32' else TC_TOL[math]
+    compare(fn, ofn, [(2, hw, hw, cin)], cuda, math=math, **tol)
+
+
+def test_subpixel_transition_fallback_x5(cuda):
+    """scale 10 = x2 then x5: the last stage is not x2, the two blocks run unfused."""
+    fn = lambda c, xs: B.subpixel_transition(c, 'spc', xs[0], 10, 4, 'tl', 8, 'relu')
+    ofn = _o(lambda p, xs: R.transition_block(p, 'tl', R.subpixel_block(p, 'spc', xs[0], 10, 4), 8, 'relu'))
+    compare(fn, ofn, [(1, 6, 6, 4)], cuda)
