@@ -86,12 +86,14 @@ class SupervisedStep:
             self.world = d.get_world_size()
 
     # the recorded work -------------------------------------------------------------------------
-    def _fwd_bwd(self, timers=None):
+    def _fwd_bwd(self, timers=None, pack_stream=None):
         self.arena.grad.zero_()
         self.loss_buf.zero_()
-        ctx, out = self.model.forward(self.inputs, training=True, math=self.math, timers=timers)
+        ctx, out = self.model.forward(self.inputs, training=True, math=self.math, timers=timers,
+                                      pack_stream=pack_stream)
         ctx.pixel_loss(out, ctx.input(self.target), self.loss_kind, loss_buf=self.loss_buf)
         ctx.backward()
+        ctx.join_pack_stream()
         return ctx.launches + 2     # + the two memsets
 
     def _opt(self):
@@ -132,8 +134,9 @@ class SupervisedStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self.graph_fb = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()          # weight-image packs: a parallel branch of the captured graph
             with torch.cuda.graph(self.graph_fb, stream=s):
-                self._fwd_bwd()
+                self._fwd_bwd(pack_stream=side)
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, stream=s):
                 self._opt()
@@ -163,12 +166,12 @@ class SupervisedStep:
         return self.loss_buf
 
     def run_profiled(self, timers):
-        """One eager (un-graphed) optimizer step with CUDA events around every convolution-family
-        launch; ``timers`` collects {label: [(start, end)]}.  Used by bench.py's roofline line."""
-        self._set_lr_t()
+        """One eager (un-graphed) forward + backward with CUDA events around ``Ctx.TIMER_REPS`` repeats of every
+        convolution-family launch; ``timers`` collects {label: [(start, end)]} (elapsed / TIMER_REPS = one
+        launch).  The repeated launches over-accumulate gradients, so no optimizer step is taken and the state is
+        left untouched.  Used by bench.py's roofline line."""
         self._fwd_bwd(timers)
-        self._allreduce()
-        self._opt()
+        torch.cuda.synchronize()
         return self.loss_buf
 
     def broadcast_from_rank0(self):

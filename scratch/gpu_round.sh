@@ -9,5 +9,5 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --steps 30 --warmup 5 --math tf32 --no-cpu > gpurun_out/${TAG}_bench_tf32.json 2> gpurun_out/${TAG}_bench_tf32.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_tc" -c 12 -o gpurun_out/${TAG}_layers -f python scratch/prof_layers.py tf32x3 > gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|thin_" -c 18 -o gpurun_out/${TAG}_layers -f python scratch/prof_layers.py tf32x3 > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json

@@ -27,7 +27,8 @@ def run(shape, cout, d2s, reps):
     torch.cuda.synchronize()
 
 
-run((64, 64, 64, 48), 192, 2, 2)
-run((64, 32, 32, 48), 48, 1, 2)
-run((64, 128, 128, 8), 8, 1, 2)
+run((64, 64, 64, 48), 32, 2, 2)       # composed last sub-pixel stage x TransitionLast (48 -> 4*8, depth_to_space)
+run((64, 32, 32, 48), 192, 2, 2)      # first sub-pixel stage
+run((64, 32, 32, 48), 48, 1, 2)       # widest backbone layer
+run((64, 128, 128, 8), 8, 1, 2)       # HR tail
 print('done')
