@@ -209,6 +209,75 @@ class SupervisedTrainer(Trainer):
         self._stage(inputs, target)
         return float(self.train_step.run().item())
 
+    def train_on_batches(self, batches):
+        """Pipelined ``fit`` loop body: iterate ``batches`` (host ``([lr(, aux)], hr)`` pairs) and yield one
+        float loss per batch, in order.  While the GPU runs step i the host already converts batch i+1 into the
+        second pinned staging set and enqueues its H2D copy on a copy stream; the loss of step i is read back
+        (async D2H + event) after step i+1 has been queued.  Every batch still crosses PCIe and every loss still
+        comes back to the host -- only the waiting overlaps.  (Keras ``fit`` overlaps the same way through its
+        ``Sequence`` worker, supervised.py:397-409.)"""
+        import torch
+        st = self.train_step
+        dev = self.dp.torch_device
+        T = self.time_window if self.model_is_spatiotemporal else None
+        if getattr(self, '_pipe', None) is None:
+            mk = lambda t: torch.empty(t.shape, dtype=torch.float32)
+            self._pipe = {
+                'pin': [([mk(t).pin_memory() for t in st.inputs], mk(st.target).pin_memory()) for _ in range(2)],
+                'dev': [([torch.empty_like(t) for t in st.inputs], torch.empty_like(st.target)) for _ in range(2)],
+                'loss': [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
+                'h2d': [torch.cuda.Event() for _ in range(2)],
+                'done': [torch.cuda.Event() for _ in range(2)],
+                'copy': torch.cuda.Stream(device=dev),
+            }
+        P = self._pipe
+        main = torch.cuda.current_stream(dev)
+
+        def put(dst, src, fold):
+            a = np.asarray(src, dtype=np.float32)
+            if fold:
+                a = np.swapaxes(a, 0, 1)
+            dst.numpy()[...] = a.reshape(dst.shape)
+
+        def stage(i, inputs, target):
+            k = i & 1
+            P['h2d'][k].synchronize()                       # the slot's previous H2D copy has left the pinned buffers
+            pins, ptgt = P['pin'][k]
+            for dst, src, shp in zip(pins, inputs, self.model.input_shapes):
+                put(dst, src, len(shp) == 4)
+            put(ptgt, target, T is not None)
+            devs, dtgt = P['dev'][k]
+            with torch.cuda.stream(P['copy']):
+                P['copy'].wait_event(P['done'][k])          # step i-2 no longer reads this device slot
+                for d, s_ in zip(devs, pins):
+                    d.copy_(s_, non_blocking=True)
+                dtgt.copy_(ptgt, non_blocking=True)
+                P['h2d'][k].record(P['copy'])
+
+        def launch(i):
+            k = i & 1
+            main.wait_event(P['h2d'][k])
+            devs, dtgt = P['dev'][k]
+            st.load_batch(devs, dtgt)                        # D2D into the captured graph's static buffers
+            loss = st.run()
+            P['loss'][k].copy_(loss, non_blocking=True)
+            P['done'][k].record(main)
+
+        it = iter(batches)
+        i = 0
+        pending = None
+        for inputs, target in it:
+            stage(i, inputs, target)
+            launch(i)
+            if pending is not None:
+                P['done'][pending & 1].synchronize()
+                yield float(P['loss'][pending & 1][0])
+            pending = i
+            i += 1
+        if pending is not None:
+            P['done'][pending & 1].synchronize()
+            yield float(P['loss'][pending & 1][0])
+
     def test_on_batch(self, inputs, target):
         import torch
         dev = self.dp.torch_device
@@ -243,10 +312,13 @@ class SupervisedTrainer(Trainer):
         chatty = bool(self.verbose) and self.running_on_first_worker
         for epoch in range(self.trained_epochs, self.epochs):
             order = np.random.permutation(len(self.ds_train))      # Keras fit(shuffle=True) on a Sequence
+            def epoch_batches():
+                for s in range(n_train):
+                    x, y = self.ds_train[int(order[s % len(order)])]
+                    yield x, y[0]
             tot = 0.0
-            for s in range(n_train):
-                x, y = self.ds_train[int(order[s % len(order)])]
-                tot += self.train_on_batch(x, y[0])
+            for lval in self.train_on_batches(epoch_batches()):
+                tot += lval
             loss = tot / max(n_train, 1)
             val = self.evaluate(self.ds_val, self.validation_steps)
             self.fithist.history['loss'].append(loss)
