@@ -841,6 +841,27 @@ __global__ void __launch_bounds__(256) spc_chain_w2_kernel(const float* __restri
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// device-resident batch assembly (dataloader.py:297-360 without the per-sample host loop): sample
+// picks[b] of the resident array, cropped at (y0[b], x0[b]) to (ph, pw), written into channels
+// [dst_coff, dst_coff + C) of the batch tensor.  idx / y0 / x0 are DEVICE int32 arrays (y0, x0 may be NULL).
+// -------------------------------------------------------------------------------------------------
+__global__ void gather_crop_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                   const int* __restrict__ y0, const int* __restrict__ x0, float* __restrict__ dst,
+                                   int n, int H, int W, int C, int ph, int pw, int dst_ld, int dst_coff) {
+    const int64_t total = (int64_t)n * ph * pw * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        int64_t t = i / C;
+        const int x = (int)(t % pw); t /= pw;
+        const int y = (int)(t % ph);
+        const int b = (int)(t / ph);
+        const int sy = y + (y0 ? __ldg(y0 + b) : 0), sx = x + (x0 ? __ldg(x0 + b) : 0);
+        dst[(((int64_t)b * ph + y) * pw + x) * dst_ld + dst_coff + c] =
+            __ldg(src + (((int64_t)__ldg(idx + b) * H + sy) * W + sx) * C + c);
+    }
+}
 }  // namespace dl4ds
 
 using namespace dl4ds;
@@ -1117,6 +1138,16 @@ int dl4ds_pad_bottom_right(const float* src, int src_ld, float* dst, int dst_ld,
                   "pad_bottom_right: bad shape");
     return launch1d("pad_bottom_right", pad_br_kernel, (int64_t)N * Hd * Wd * C, as_stream(stream), src,
                     src_ld, dst, dst_ld, N, Hs, Ws, Hd, Wd, C);
+}
+
+int dl4ds_gather_crop(const float* src, const int* idx, const int* y0, const int* x0, float* dst,
+                      int n, int H, int W, int C, int ph, int pw, int dst_ld, int dst_coff, void* stream) {
+    DL4DS_REQUIRE(src && idx && dst, DL4DS_E_BADARG, "gather_crop: null pointer");
+    DL4DS_REQUIRE(n > 0 && H > 0 && W > 0 && C > 0 && ph > 0 && pw > 0 && ph <= H && pw <= W, DL4DS_E_SHAPE,
+                  "gather_crop: bad shape");
+    DL4DS_REQUIRE(dst_ld >= dst_coff + C && dst_coff >= 0, DL4DS_E_SHAPE, "gather_crop: channel slice outside dst_ld");
+    return launch1d("gather_crop", gather_crop_kernel, (int64_t)n * ph * pw * C, as_stream(stream), src, idx, y0, x0, dst,
+                    n, H, W, C, ph, pw, dst_ld, dst_coff);
 }
 
 int dl4ds_avgpool_coarsen(const float* x, float* y, int N, int H, int W, int C, int s, void* stream) {

@@ -44,7 +44,7 @@ class SupervisedTrainer(Trainer):
                  learning_rate=(1e-3, 1e-4), lr_decay_after=1e5, early_stopping=False, patience=6,
                  min_delta=0, show_plot=True, save=False, save_path=None, save_bestmodel=False,
                  trained_model=None, trained_epochs=0, verbose=True, math='tf32x3', seed=None,
-                 **architecture_params):
+                 data_on_device=False, **architecture_params):
         super().__init__(backbone=backbone, upsampling=upsampling, data_train=data_train,
                          data_train_lr=data_train_lr, time_window=time_window, loss=loss,
                          batch_size=batch_size, patch_size=patch_size, scale=scale, device=device,
@@ -84,6 +84,7 @@ class SupervisedTrainer(Trainer):
         self.save_bestmodel = save_bestmodel
         self.math = math
         self.seed = seed
+        self.data_on_device = data_on_device    # addition: keep the training array in HBM (DeviceDataGenerator)
         self.model = None
         self.train_step = None
         self._pinned = None
@@ -95,7 +96,13 @@ class SupervisedTrainer(Trainer):
                  batch_size=self.global_batch_size, static_vars=self.static_vars,
                  patch_size=self.patch_size, interpolation=self.interpolation,
                  time_window=self.time_window)
-        self.ds_train = DataGenerator(self.data_train, self.data_train_lr, predictors=self.predictors_train, **p)
+        from ..dataloader import DeviceDataGenerator
+        if self.data_on_device and DeviceDataGenerator.supported(
+                getattr(self.data_train, 'values', self.data_train), self.data_train_lr, self.upsampling, self.scale,
+                self.patch_size, self.time_window, self.static_vars, self.predictors_train, self.interpolation):
+            self.ds_train = DeviceDataGenerator(self.data_train, None, device=self.dp.torch_device, **p)
+        else:
+            self.ds_train = DataGenerator(self.data_train, self.data_train_lr, predictors=self.predictors_train, **p)
         self.ds_val = DataGenerator(self.data_val, self.data_val_lr, predictors=self.predictors_val, **p)
         self.ds_test = DataGenerator(self.data_test, self.data_test_lr, predictors=self.predictors_test, **p)
 
@@ -278,6 +285,27 @@ class SupervisedTrainer(Trainer):
             P['done'][pending & 1].synchronize()
             yield float(P['loss'][pending & 1][0])
 
+    def train_on_device_batches(self, gen, order):
+        """The fit loop over a :class:`DeviceDataGenerator`: batch ``order[s]`` is gathered / coarsened on the
+        GPU straight into the step's static buffers; yields one float loss per step (read back one step late)."""
+        import torch
+        st = self.train_step
+        slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        evs = [torch.cuda.Event() for _ in range(2)]
+        pending = None
+        for i, idx in enumerate(order):
+            gen.fill(int(idx), st.inputs[0], st.target)
+            loss = st.run()
+            slots[i & 1].copy_(loss, non_blocking=True)
+            evs[i & 1].record()
+            if pending is not None:
+                evs[pending & 1].synchronize()
+                yield float(slots[pending & 1][0])
+            pending = i
+        if pending is not None:
+            evs[pending & 1].synchronize()
+            yield float(slots[pending & 1][0])
+
     def test_on_batch(self, inputs, target):
         import torch
         dev = self.dp.torch_device
@@ -317,7 +345,12 @@ class SupervisedTrainer(Trainer):
                     x, y = self.ds_train[int(order[s % len(order)])]
                     yield x, y[0]
             tot = 0.0
-            for lval in self.train_on_batches(epoch_batches()):
+            from ..dataloader import DeviceDataGenerator
+            if isinstance(self.ds_train, DeviceDataGenerator):
+                losses = self.train_on_device_batches(self.ds_train, [order[s % len(order)] for s in range(n_train)])
+            else:
+                losses = self.train_on_batches(epoch_batches())
+            for lval in losses:
                 tot += lval
             loss = tot / max(n_train, 1)
             val = self.evaluate(self.ds_val, self.validation_steps)

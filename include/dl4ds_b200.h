@@ -189,6 +189,12 @@ int dl4ds_adam_step_dev(float* theta, const float* grad, float* m, float* v, int
                         const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
                         void* stream);
 
+/* Device-resident batch assembly (create_batch_hr_lr, dataloader.py:297-360, without the per-sample host loop):
+ * dst[b, y, x, dst_coff + c] = src[idx[b], y0[b] + y, x0[b] + x, c] for b < n, y < ph, x < pw, c < C.  src is the
+ * whole (Ns, H, W, C) array resident in HBM; idx, y0, x0 are DEVICE int32 arrays (y0 / x0 NULL = no crop offset). */
+int dl4ds_gather_crop(const float* src, const int* idx, const int* y0, const int* x0, float* dst,
+                      int n, int H, int W, int C, int ph, int pw, int dst_ld, int dst_coff, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Data path: HR -> LR coarsening by s x s block mean == cv2.resize(INTER_AREA) at an integer
  * factor -- utils.py:376-384 as called from dataloader.py:204,208.  (N,H,W,C) -> (N,H/s,W/s,C).

@@ -89,3 +89,13 @@ def test_argument_checks():
         utils.crop_array(np.zeros((4, 4)), 5)
     with pytest.raises(ValueError):
         utils.resize_array(np.zeros((4, 4), np.float32), (2, 2), 'cubic')
+
+
+def test_device_data_generator_rejects_out_of_domain():
+    from dl4ds_b200.dataloader import DeviceDataGenerator
+    a = np.zeros((4, 30, 30, 1), np.float32)
+    assert not DeviceDataGenerator.supported(a, None, 'spc', 4, None, None, None, None, 'inter_area')   # 30 % 4
+    assert not DeviceDataGenerator.supported(a, a, 'spc', 2, None, None, None, None, 'inter_area')      # explicit LR
+    assert not DeviceDataGenerator.supported(a, None, 'pin', 2, None, None, None, None, 'inter_area')
+    assert not DeviceDataGenerator.supported(a, None, 'spc', 2, None, None, None, None, 'bicubic')
+    assert DeviceDataGenerator.supported(a, None, 'spc', 2, None, None, None, None, 'inter_area')

@@ -102,3 +102,41 @@ def test_cgan_trainer_runs(cuda, tmp_path):
     tr.run()
     assert len(tr.gentotal) == 2 and all(np.isfinite(v) for v in tr.gentotal + tr.disc)
     assert np.isfinite(tr.test_loss) and tr.generator.name == 'unet_pin'
+
+
+# ------------------------------------------------------------------------------------------ device-resident data path
+@pytest.mark.parametrize('patch', [None, 32])
+def test_device_data_generator_matches_host(cuda, patch):
+    """DeviceDataGenerator (gather/crop + block-mean coarsening on the GPU) == the host DataGenerator (numpy
+    slicing + cv2 INTER_AREA, itself pinned bit-for-bit to the reference by tests/test_datapath.py) for the same
+    numpy RNG state: same permutation, same crops, same batches."""
+    from dl4ds_b200.dataloader import DataGenerator, DeviceDataGenerator
+    hr = np.random.default_rng(5).standard_normal((20, 48, 64, 2)).astype(np.float32)
+    kw = dict(backbone='resnet', upsampling='spc', scale=4, batch_size=6, patch_size=patch)
+    np.random.seed(11)
+    host = DataGenerator(hr, None, **kw)
+    hb = [host[i] for i in range(len(host))]
+    np.random.seed(11)
+    dev = DeviceDataGenerator(hr, None, device=cuda, **kw)
+    assert len(dev) == len(host) == 3
+    for i in range(len(dev)):
+        (lr_d,), (hr_d,) = dev[i]
+        (lr_h,), (hr_h,) = hb[i]
+        assert hr_d.shape == hr_h.shape and lr_d.shape == lr_h.shape
+        assert np.array_equal(hr_d, hr_h)
+        assert np.abs(lr_d - lr_h).max() <= 1e-6 * max(1.0, np.abs(lr_h).max())
+
+
+def test_supervised_run_data_on_device(cuda):
+    """SupervisedTrainer(data_on_device=True): the same losses as the host data path, epoch by epoch."""
+    hr = _data(40, 32, 2)
+    hist = []
+    for on_dev in (False, True):
+        np.random.seed(4)
+        tr = SupervisedTrainer('resnet', 'spc', hr[:24], hr[24:32], hr[32:], scale=4, batch_size=8, epochs=2,
+                               learning_rate=1e-3, verbose=False, seed=3, n_blocks=2, data_on_device=on_dev)
+        tr.run()
+        from dl4ds_b200.dataloader import DeviceDataGenerator
+        assert isinstance(tr.ds_train, DeviceDataGenerator) == on_dev
+        hist.append(tr.fithist.history['loss'])
+    assert np.allclose(hist[0], hist[1], rtol=2e-4), hist
