@@ -141,6 +141,38 @@ class Model:
 
     save = save_weights
 
+    def save_checkpoint(self, path):
+        """Weights AND optimizer state of the flat arena (theta, Adam m / v per parameter, iteration count) in one
+        ``.npz`` -- what ``tf.train.Checkpoint(generator=..., generator_optimizer=...)`` stores in the reference
+        (cgan.py:288-292,375): resuming from it continues the Adam trajectory exactly."""
+        a = self.arena
+        out = {'__iterations__': np.asarray(a.t, np.int64), '__model_name__': np.asarray(self.name)}
+        for n in a.spec:
+            key = n.replace('/', '|')
+            out[key] = a.param(n).detach().cpu().numpy()
+            out['__adam_m__' + key] = a._view(a.m, n).detach().cpu().numpy()
+            out['__adam_v__' + key] = a._view(a.v, n).detach().cpu().numpy()
+        np.savez(path, **out)
+
+    def load_checkpoint(self, path):
+        """Restore ``save_checkpoint`` output (a weights-only ``save_weights`` file also loads: slots reset)."""
+        import torch
+        with np.load(path) as z:
+            files = set(z.files)
+            self.set_weights({n: z[n.replace('/', '|')] for n in self.spec})
+            a = self.arena
+            full = '__iterations__' in files
+            a.t = int(z['__iterations__']) if full else 0
+            for n in a.spec:
+                key = n.replace('/', '|')
+                for flat, tag in ((a.m, '__adam_m__'), (a.v, '__adam_v__')):
+                    view = a._view(flat, n)
+                    if full and tag + key in files:
+                        view.copy_(torch.as_tensor(z[tag + key]).to(view.device))
+                    else:
+                        view.zero_()
+        return self
+
     # -- execution --------------------------------------------------------------------------
     def _prep_inputs(self, inputs, device):
         """numpy / torch NHWC (or NTHWC) -> list of CUDA fp32 tensors; returns (tensors, B, T)."""

@@ -273,8 +273,9 @@ class CGANTrainer(Trainer):
                     (epoch + 1) % self.checkpoints_frequency == 0:
                 ck = os.path.join(self.savecheckpoint_path, 'checkpoints')
                 os.makedirs(ck, exist_ok=True)
-                self.generator.save(os.path.join(ck, 'generator_epoch%d.npz' % (epoch + 1)))
-                self.discriminator.save(os.path.join(ck, 'discriminator_epoch%d.npz' % (epoch + 1)))
+                # tf.train.Checkpoint(generator, discriminator, both optimizers), cgan.py:288-292,375: weights + Adam slots
+                self.generator.save_checkpoint(os.path.join(ck, 'generator_epoch%d.npz' % (epoch + 1)))
+                self.discriminator.save_checkpoint(os.path.join(ck, 'discriminator_epoch%d.npz' % (epoch + 1)))
         if self.save_loss_history and self.running_on_first_worker:
             np.save(self.save_path + './losses.npy',
                     np.array((self.gentotal, self.gengan, self.gen_pxloss, self.disc)))
@@ -305,3 +306,48 @@ class CGANTrainer(Trainer):
                 print('\n%s on the test set: %s' % (self.lossf, self.test_loss))
         self.timing.runtime()
         self.save_results(self.generator, folder_prefix='cgan_')
+
+
+def load_checkpoint(checkpoint_dir, checkpoint_number, backbone, upsampling, scale, input_height_width,
+                    n_static_vars=0, n_predictors=0, time_window=None, n_blocks=(20, 4), n_filters=(8, 32),
+                    attention=False, localcon_layer=False, math='tf32x3', device='cuda'):
+    """load_checkpoint -- cgan.py:447-522 (same arguments): rebuild generator and discriminator and restore the
+    epoch-``checkpoint_number`` files written by ``CGANTrainer(checkpoints_frequency=...)``, optimizer slots
+    included.  Returns ``(generator, generator_optimizer, discriminator, discriminator_optimizer)``; the Adam
+    objects are bound to the restored arenas (theta / m / v / iteration count)."""
+    n_channels, n_aux = 1, 0
+    if n_static_vars > 0:
+        n_channels += n_static_vars
+        n_aux += n_static_vars
+    if n_predictors > 0:
+        n_channels += n_predictors
+    st = time_window is not None and time_window > 1
+    if upsampling in POSTUPSAMPLING_METHODS:
+        if st:
+            generator = nets.recnet_postupsampling(
+                backbone_block=backbone, upsampling=upsampling, scale=scale, n_channels=n_channels,
+                n_aux_channels=n_aux, n_filters=n_filters[0], n_blocks=n_blocks[0], lr_size=input_height_width,
+                n_channels_out=1, time_window=time_window, attention=attention, localcon_layer=localcon_layer, math=math)
+        else:
+            generator = nets.net_postupsampling(
+                backbone_block=backbone, upsampling=upsampling, scale=scale, n_channels=n_channels,
+                n_aux_channels=n_aux, n_filters=n_filters[0], n_blocks=n_blocks[0], lr_size=input_height_width,
+                n_channels_out=1, attention=attention, localcon_layer=localcon_layer, math=math)
+    elif upsampling == 'pin':
+        if st:
+            raise NotImplementedError('recnet_pin is outside the B200 hot path (no BASELINE config)')
+        build = nets.unet_pin if backbone == 'unet' else nets.net_pin
+        generator = build(backbone_block=backbone, n_channels=n_channels, n_aux_channels=n_aux,
+                          hr_size=input_height_width, n_filters=n_filters[0], n_blocks=n_blocks[0], n_channels_out=1,
+                          attention=attention, localcon_layer=localcon_layer, math=math)
+    else:
+        raise ValueError('`upsampling` not recognized')
+    discriminator = nets.residual_discriminator(
+        n_channels=n_channels, upsampling=upsampling, is_spatiotemporal=st, scale=scale, lr_size=input_height_width,
+        n_filters=n_filters[1], n_res_blocks=n_blocks[1], attention=attention, math=math)
+    ck = os.path.join(checkpoint_dir, 'checkpoints')
+    if not os.path.isdir(ck):
+        ck = checkpoint_dir
+    generator.to(device).load_checkpoint(os.path.join(ck, 'generator_epoch%d.npz' % checkpoint_number))
+    discriminator.to(device).load_checkpoint(os.path.join(ck, 'discriminator_epoch%d.npz' % checkpoint_number))
+    return generator, Adam(2e-4, beta_1=0.5), discriminator, Adam(2e-4, beta_1=0.5)

@@ -359,9 +359,11 @@ class SupervisedTrainer(Trainer):
             self.fithist.epoch.append(epoch)
             if chatty:
                 print('Epoch %d/%d - loss: %.4f - val_loss: %.4f' % (epoch + 1, self.epochs, loss, val))
-            if self.save_bestmodel and self.running_on_first_worker:
+            if self.save_bestmodel and self.running_on_first_worker and val <= min(self.fithist.history['val_loss']):
+                # ModelCheckpoint(save_best_only=True, monitor='val_loss'), supervised.py:380-390 -- with the
+                # optimizer slots, so that `trained_model` + `trained_epochs` resume the same Adam trajectory
                 os.makedirs(self.savecheckpoint_path, exist_ok=True)
-                self.model.save(os.path.join(self.savecheckpoint_path, 'best_model.npz'))
+                self.model.save_checkpoint(os.path.join(self.savecheckpoint_path, 'best_model.npz'))
             if self.early_stopping:
                 if val < best - self.min_delta:
                     best, wait = val, 0
