@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWgradArgs a) 
                 } else {
                     q[0] = qrow[x * CB];
                 }
+                // (packed FFMA2 was tried here: 74 -> 102 us, the register pairs cost more moves than they save)
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -317,8 +318,20 @@ __global__ void __launch_bounds__(256) thin_conv_kernel(const ConvArgs p, int TW
                         for (int j = 0; j < 4; ++j) {
                             if (j < npx) {
                                 const float x = u == 0 ? in[j].x : (u == 1 ? in[j].y : (u == 2 ? in[j].z : in[j].w));
+                                if constexpr (CO == 8) {
+                                    // packed fp32 FMA (FFMA2): 4 instructions + 1 pair setup for the 8 outputs
+                                    const float2 xx = make_float2(x, x);
 #pragma unroll
-                                for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(x, wv[c], acc[j][c]);
+                                    for (int c = 0; c < CO; c += 2) {
+                                        const float2 r = __ffma2_rn(xx, make_float2(wv[c], wv[c + 1 < CO ? c + 1 : c]),
+                                                                    make_float2(acc[j][c], acc[j][c + 1 < CO ? c + 1 : c]));
+                                        acc[j][c] = r.x;
+                                        acc[j][c + 1 < CO ? c + 1 : c] = r.y;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(x, wv[c], acc[j][c]);
+                                }
                             }
                         }
                     }
