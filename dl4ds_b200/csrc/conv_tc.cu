@@ -441,12 +441,15 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 }
                 const int units = n * (p.a_bytes >> 4);
 #pragma unroll 2
+                // The raw fp32 tile stays where TMA put it and serves as the hi operand: kind::tf32 reads the top 19
+                // bits of each element, i.e. hi = trunc(v).  Only lo = v - trunc(v) (exact: <= 13 significant bits) is
+                // written -- one 16-byte store per unit instead of two; these kernels are bound by shared-memory
+                // bandwidth (~57 KB per 256 pixels and K slice, measured ~92 B/cycle/SM), not by the tensor pipe.
                 for (int u = et; u < units; u += 128) {
                     const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 16);
-                    float4 h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                    *reinterpret_cast<float4*>(a_hi + u * 16) = h;
+                    float4 l;
+                    l.x = v.x - tf32_trunc(v.x); l.y = v.y - tf32_trunc(v.y);
+                    l.z = v.z - tf32_trunc(v.z); l.w = v.w - tf32_trunc(v.w);
                     *reinterpret_cast<float4*>(a_lo + u * 16) = l;
                 }
                 fence_proxy_async_smem();

@@ -173,6 +173,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a
 __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+// what the tensor core itself does with an fp32 operand of kind::tf32: keep sign, exponent and 10 mantissa bits
+__device__ __forceinline__ float tf32_trunc(float x) {
+    return __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+}
 // hi/lo split for the 3xTF32 scheme: x = hi + lo exactly; the tensor core truncates lo to tf32
 // (|lo| <= 2^-12 |x|, so the truncation error is <= 2^-22 |x|).
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
