@@ -83,7 +83,9 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
     a.vec = (Cin % 4 == 0) && (x_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     {   // narrow 3x3 layers (Cin, Cout in {1, 8}): HBM-bound, exact-fp32 direct kernel in every math mode
-        int rc = conv2d_fwd_thin(a, st);
+        int rc = conv2d_fwd_thin_mma(a, math_mode, st);    // 8 -> 8, tensor-core math modes: warp-level mma.sync
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+        rc = conv2d_fwd_thin(a, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
         rc = conv2d_fwd_pointwise(a, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
@@ -137,7 +139,9 @@ int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float
     a.chunks_per_split = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     {   // narrow layers (Ca, Cb in {1, 8}, 3x3): exact-fp32 sliding-window kernel in every math mode
-        int rc = conv2d_wgrad_thin(a, st);
+        int rc = conv2d_wgrad_thin_mma(a, math_mode, st);   // 8 x 8, tensor-core math modes: warp-level mma.sync
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+        rc = conv2d_wgrad_thin(a, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
         rc = conv2d_wgrad_pointwise(a, st);        // 1x1, Ca*Cb <= 1024: streaming CUDA-core kernel
         if (rc != DL4DS_E_UNSUPPORTED) return rc;

@@ -46,6 +46,9 @@ int conv2d_wgrad_simt(const WgradArgs& a, cudaStream_t st);
 int conv2d_wgrad_thin(const WgradArgs& a, cudaStream_t st);
 int conv2d_wgrad_pointwise(const WgradArgs& a, cudaStream_t st);
 int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st);
+// thin_mma.cu: mma.sync (register-operand) kernels of the 8-channel HR tail, tensor-core math modes only
+int conv2d_fwd_thin_mma(const ConvArgs& a, int math_mode, cudaStream_t st);
+int conv2d_wgrad_thin_mma(const WgradArgs& a, int math_mode, cudaStream_t st);
 int conv2d_fwd_pointwise(const ConvArgs& a, cudaStream_t st);
 int bias_act_bwd_vec4(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld, float* dbias,
                       int64_t n_pix, int Ho, int Wo, int C, int act, int r, cudaStream_t st);
