@@ -40,6 +40,7 @@ SIGNATURES = {
     'dl4ds_pixel_loss': ('i', 'pppplifp'),
     'dl4ds_adam_step': ('i', 'pppplffffifp'),
     'dl4ds_adam_step_dev': ('i', 'pppplpffffp'),
+    'dl4ds_convt_rearrange': ('i', 'ppiiiiiiiip'),
     'dl4ds_gather_crop': ('i', 'pppppiiiiiiiip'),
     'dl4ds_avgpool_coarsen': ('i', 'ppiiiiip'),
     'dl4ds_resize_bilinear_fwd': ('i', 'pipiiiiiiip'),

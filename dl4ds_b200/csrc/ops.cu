@@ -862,6 +862,38 @@ __global__ void gather_crop_kernel(const float* __restrict__ src, const int* __r
             __ldg(src + (((int64_t)__ldg(idx + b) * H + sy) * W + sx) * C + c);
     }
 }
+
+// -------------------------------------------------------------------------------------------------
+// Conv2DTranspose(k, strides=s, 'same') (DeconvolutionBlock, blocks.py:508-516) as a stride-1 convolution on the
+// input grid followed by depth_to_space(s): output pixel (s*a + dy, s*b + dx) only sees the kernel taps kh with
+// (dy + kh - pad) % s == 0, at input row a + (dy + kh - pad) / s.  Collecting the s*s phases as output-channel
+// groups gives a Kp x Kp convolution (Kp = ceil-ish(k/s): 5 for k=9, s=2) to s*s*Co channels in HWIO layout:
+//   wp[my][mx][ci][(dy*s + dx)*Co + co] = w[k-1-kh][k-1-kw][co][ci]   (Keras layout (kh,kw,Co,Ci), flipped), or 0
+// with kh = s*(my + off_min) - dy + pad, kw likewise -- which runs on the tensor-core kernels with the fused
+// depth_to_space store instead of the CUDA-core fractional-stride path.  backward != 0 scatters dwp back: dw += .
+// -------------------------------------------------------------------------------------------------
+__global__ void convt_rearrange_kernel(float* __restrict__ w, float* __restrict__ wp, int k, int s, int pad, int off_min,
+                                       int Kp, int Co, int Ci, int backward) {
+    const int ne = s * s * Co;
+    const int64_t total = (int64_t)Kp * Kp * Ci * ne;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % ne);
+        int64_t r = i / ne;
+        const int ci = (int)(r % Ci); r /= Ci;
+        const int mx = (int)(r % Kp);
+        const int my = (int)(r / Kp);
+        const int d = e / Co, co = e - d * Co;
+        const int dy = d / s, dx = d - dy * s;
+        const int kh = s * (my + off_min) - dy + pad, kw = s * (mx + off_min) - dx + pad;
+        const bool ok = kh >= 0 && kh < k && kw >= 0 && kw < k;
+        const int64_t wi = ok ? ((int64_t)((k - 1 - kh) * k + (k - 1 - kw)) * Co + co) * Ci + ci : 0;
+        if (backward) {
+            if (ok) w[wi] += wp[i];          // every (kh, kw, co, ci) has exactly one image: no atomics needed
+        } else {
+            wp[i] = ok ? w[wi] : 0.0f;
+        }
+    }
+}
 }  // namespace dl4ds
 
 using namespace dl4ds;
@@ -1148,6 +1180,15 @@ int dl4ds_gather_crop(const float* src, const int* idx, const int* y0, const int
     DL4DS_REQUIRE(dst_ld >= dst_coff + C && dst_coff >= 0, DL4DS_E_SHAPE, "gather_crop: channel slice outside dst_ld");
     return launch1d("gather_crop", gather_crop_kernel, (int64_t)n * ph * pw * C, as_stream(stream), src, idx, y0, x0, dst,
                     n, H, W, C, ph, pw, dst_ld, dst_coff);
+}
+
+int dl4ds_convt_rearrange(float* w, float* wp, int k, int stride, int pad, int off_min, int Kp, int Co, int Ci,
+                          int backward, void* stream) {
+    DL4DS_REQUIRE(w && wp, DL4DS_E_BADARG, "convt_rearrange: null pointer");
+    DL4DS_REQUIRE(k > 0 && stride > 1 && Kp > 0 && Co > 0 && Ci > 0, DL4DS_E_SHAPE, "convt_rearrange: bad shape");
+    const int64_t total = (int64_t)Kp * Kp * Ci * stride * stride * Co;
+    return launch1d("convt_rearrange", convt_rearrange_kernel, total, as_stream(stream), w, wp, k, stride, pad, off_min, Kp,
+                    Co, Ci, backward);
 }
 
 int dl4ds_avgpool_coarsen(const float* x, float* y, int N, int H, int W, int C, int s, void* stream) {

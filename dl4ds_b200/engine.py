@@ -13,6 +13,7 @@ Storage conventions
     shared layers (blocks.py:415,421-422,528-531) over their applications and lets the
     data-parallel all-reduce be a single collective on one buffer.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -456,6 +457,8 @@ class Ctx:
         Ho, Wo = x.H * stride, x.W * stride
         _, pt = same_pads(Ho, k, stride)
         _, pl = same_pads(Wo, k, stride)
+        if stride > 1 and pt == pl and os.environ.get('DL4DS_CONVT_DIRECT', '0') != '1':
+            return self._conv_transpose_d2s(x, name, w, cout, k, stride, pt, act)
         out = new_var(x.N, Ho, Wo, cout, self.device)
         a = ACT[act]
         self._call('dl4ds_conv2d_fwd', x.ptr, x.ld, w.data_ptr(), None, None, 0, out.ptr, out.ld,
@@ -478,6 +481,53 @@ class Ctx:
                     self._call('dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
                                dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, stride, 1,
                                pt, pl, W_HWIO, 0, 1, beta, self.math, None, _stream())
+                self._acc(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def _conv_transpose_d2s(self, x, name, w, cout, k, s, pt, act):
+        """Conv2DTranspose as a stride-1 Kp x Kp convolution to s*s*cout channels + depth_to_space(s)
+        (``dl4ds_convt_rearrange``): every output phase (dy, dx) of a fractionally strided convolution is an
+        ordinary convolution on the input grid, so the layer runs on the tensor-core kernels (forward with the
+        fused depth_to_space store, dgrad, stacked-taps wgrad) instead of the CUDA-core fractional-stride path.
+        The weight gradient of the rearranged image is scattered back onto the Keras-layout kernel (each element
+        has exactly one image).  Same function; only the summation order differs."""
+        dev = self.device
+        pad = k - 1 - pt
+        offs = sorted({(d + kh - pad) // s for d in range(s) for kh in range(k) if (d + kh - pad) % s == 0})
+        off_min, Kp = offs[0], offs[-1] - offs[0] + 1
+        ce = s * s * cout
+        wp = torch.empty((Kp, Kp, x.C, ce), dtype=torch.float32, device=dev)
+        self._call('dl4ds_convt_rearrange', w.data_ptr(), wp.data_ptr(), k, s, pad, off_min, Kp, cout, x.C, 0, _stream())
+        out = new_var(x.N, x.H * s, x.W * s, cout, dev)
+        a = ACT[act]
+        pp = -off_min                                       # top / left padding of the equivalent convolution
+        ws = self._conv_ws(x.N, x.H, x.W, x.C, x.H, x.W, ce, Kp, 1, 1, s)
+        self._timed('%s:fwd@%dx%d' % (name, x.H, x.W),
+                    'dl4ds_conv2d_fwd', x.ptr, x.ld, wp.data_ptr(), None, None, 0, out.ptr, out.ld,
+                    x.N, x.H, x.W, x.C, x.H, x.W, ce, Kp, Kp, 1, 1, pp, pp, W_HWIO, a, s, 0, self.math,
+                    ws.data_ptr() if ws is not None else None, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dz = new_var(x.N, x.H, x.W, ce, dev)
+            self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dz.ptr, dz.ld, None,
+                       x.N, x.H, x.W, ce, a, s, _stream())
+            if self.param_grads:
+                dwp = torch.zeros_like(wp)
+                self._wgrad(x, dz, dwp, Kp, 1, pp, pp, label='%s:wgrad@%dx%d' % (name, x.H, x.W))
+                self._call('dl4ds_convt_rearrange', self._g(name + '/kernel').data_ptr(), dwp.data_ptr(), k, s, pad,
+                           off_min, Kp, cout, x.C, 1, _stream())
+            if x.requires_grad:
+                def wr(dst, beta):
+                    ws2 = self._conv_ws(x.N, x.H, x.W, ce, x.H, x.W, x.C, Kp, 1, 1, 1)
+                    self._timed('%s:dgrad@%dx%d' % (name, x.H, x.W),
+                                'dl4ds_conv2d_fwd', dz.ptr, dz.ld, wp.data_ptr(), None, None, 0, dst.ptr, dst.ld,
+                                x.N, x.H, x.W, ce, x.H, x.W, x.C, Kp, Kp, 1, 1, Kp - 1 - pp, Kp - 1 - pp,
+                                W_FLIP_T, 0, 1, beta, self.math, ws2.data_ptr() if ws2 is not None else None, _stream())
                 self._acc(x, wr)
             out.grad = None
         self._record(bwd)

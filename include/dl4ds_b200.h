@@ -189,6 +189,14 @@ int dl4ds_adam_step_dev(float* theta, const float* grad, float* m, float* v, int
                         const float* lr_t_dev, float beta1, float beta2, float eps, float grad_scale,
                         void* stream);
 
+/* Conv2DTranspose(k, strides=stride, padding='same', use_bias=False) (blocks.py:508-516) re-expressed as a stride-1
+ * Kp x Kp convolution to stride^2*Co channels + depth_to_space(stride):  backward == 0 builds the HWIO weight image
+ *   wp[my][mx][ci][(dy*stride+dx)*Co+co] = w[k-1-kh][k-1-kw][co][ci]  (w in the Keras layout (kh,kw,Co,Ci)), kh = stride*(my+off_min)-dy+pad
+ * (0 where kh / kw fall outside the kernel); backward != 0 adds dwp back onto dw (= `w` argument) through the same map.
+ * pad = k-1-pad_before of the transpose, off_min = smallest input offset any phase reads, Kp = number of offsets. */
+int dl4ds_convt_rearrange(float* w, float* wp, int k, int stride, int pad, int off_min, int Kp, int Co, int Ci,
+                          int backward, void* stream);
+
 /* Device-resident batch assembly (create_batch_hr_lr, dataloader.py:297-360, without the per-sample host loop):
  * dst[b, y, x, dst_coff + c] = src[idx[b], y0[b] + y, x0[b] + x, c] for b < n, y < ph, x < pw, c < C.  src is the
  * whole (Ns, H, W, C) array resident in HBM; idx, y0, x0 are DEVICE int32 arrays (y0 / x0 NULL = no crop offset). */

@@ -385,3 +385,26 @@ def test_subpixel_transition_fallback_x5(cuda):
     fn = lambda c, xs: B.subpixel_transition(c, 'spc', xs[0], 10, 4, 'tl', 8, 'relu')
     ofn = _o(lambda p, xs: R.transition_block(p, 'tl', R.subpixel_block(p, 'spc', xs[0], 10, 4), 8, 'relu'))
     compare(fn, ofn, [(1, 6, 6, 4)], cuda)
+
+
+# ------------------------------------------------------------------------------------------ Conv2DTranspose on tensor cores
+@pytest.mark.parametrize('math', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('shape,cout,k,stride,act', [
+    ((2, 16, 16, 8), 48, 9, 2, None),        # DeconvolutionBlock T1 (blocks.py:508-516): 8 -> 48, 9x9, s=2
+    ((2, 32, 32, 48), 48, 9, 2, 'tanh'),     # T2: 48 -> 48 with the block's activation
+    ((1, 16, 16, 16), 8, 5, 2, None),        # another odd kernel
+    ((1, 8, 8, 8), 8, 9, 4, None),           # stride 4 (scale-4 fall-through): depth_to_space(4) -> CUDA-core store path
+])
+def test_conv_transpose_as_conv_d2s(cuda, math, shape, cout, k, stride, act):
+    """Ctx.conv_transpose = rearranged stride-1 convolution + depth_to_space (dl4ds_convt_rearrange) against the
+    oracle's conv_transpose: forward, input gradient and the gradient scattered back onto the Keras kernel."""
+    fn = lambda c, xs: c.conv_transpose(xs[0], 'ct', cout, k, stride, act=act)
+
+    def ofn_(p, xs):
+        w = p.get('ct/kernel', (k, k, cout, xs[0].shape[1]))
+        return R.act(R.conv2d_transpose_same(xs[0], w, stride), act)
+    tol = dict(tol=2e-5, gtol=2e-4) if math == 'fp32' else TC_TOL[math]
+    n0 = _tc_count()
+    compare(fn, _o(ofn_), [shape], cuda, math=math, **tol)
+    if math != 'fp32' and stride == 2 and shape[2] >= 16:
+        assert _tc_count() > n0, 'tensor-core path did not run'
