@@ -63,6 +63,132 @@ def _dev_inputs(model, arrays, dev):
     return ins
 
 
+def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function):
+    """Device work of one cGAN step up to the gradients (cgan.py:587-611): zero both gradient arenas, generator
+    forward, D(real), D(fake), the four loss terms into ``losses`` (gan, lambda*px, d_real, d_fake) and the two
+    backward passes.  Pure kernel launches on the current stream: ``train_step`` runs it eagerly, ``CGANStep``
+    captures it into a CUDA graph."""
+    from ..engine import Ctx, Var
+    G.arena.zero_grad(); D.arena.zero_grad()
+    losses.zero_()
+    # ---- forward: generator, D(real), D(fake)
+    cg = Ctx(G.arena, G.math, training=True)
+    gin = [cg.input(lr_t)] + ([cg.input(st_t)] if st_t is not None else [])
+    gen = G.fn(cg, gin)
+    cr = Ctx(D.arena, D.math, training=True)
+    p_real = D.fn(cr, [cr.input(lr_t), cr.input(hr_t), cr.input(mk[0])])
+    cf = Ctx(D.arena, D.math, training=True)
+    gen_in = Var(gen.buf, gen.off, gen.C, requires_grad=True)
+    p_fake = D.fn(cf, [cf.input(lr_t), gen_in, cf.input(mk[1])])
+
+    # ---- discriminator loss and weight gradients
+    cr.bce_loss(p_real, 1.0, loss_buf=losses[2:3])
+    cr.backward()
+    cf.bce_loss(p_fake, 0.0, loss_buf=losses[3:4])
+    cf.backward(keep_tape=True)
+    gen_in.grad = None                      # d(D loss)/d(gen) is not used by either optimizer
+    # ---- generator loss: through D(fake) to the generated field, then through G
+    cf.param_grads = False
+    cf.bce_loss(p_fake, 1.0, loss_buf=losses[0:1])
+    cf.backward()
+    if gen_in.grad is not None:
+        cg._give_grad(gen, gen_in.grad)
+    cg.pixel_loss(gen, cg.input(hr_t), gen_pxloss_function or 'mae', scale=LAMBDA, loss_buf=losses[1:2])
+    cg.backward()
+
+
+class CGANStep:
+    """One cGAN optimisation step on fixed-shape device batches as replayable CUDA graphs (what ``train_step``
+    does eagerly, ~450 launches whose Python/ctypes issue cost exceeds the GPU time at small per-GPU batches):
+    graph 1 = ``_fwd_bwd``; [NCCL all-reduce of both gradient arenas]; graph 2 = the two Adam(beta_1=0.5) updates
+    with the bias-corrected step sizes read from device scalars.  The host refreshes the static input buffers, the
+    two dropout keep masks (drawn per step, discriminator.py:77 with ``training=True``) and the step sizes."""
+
+    def __init__(self, generator, discriminator, lr_shape, hr_shape, static_shape=None, gen_pxloss_function='mae',
+                 learning_rates=(2e-4, 2e-4), beta_1=0.5, beta_2=0.999, eps=1e-7, dist=None):
+        import torch
+        self.G, self.D = generator, discriminator
+        dev = self.G.arena.device
+        z = lambda shp: torch.zeros(tuple(shp), dtype=torch.float32, device=dev)
+        self.lr, self.hr = z(lr_shape), z(hr_shape)
+        self.st = z(static_shape) if static_shape is not None else None
+        nfeat = self.D.spec['dense1/kernel'][0]
+        self.masks = [z((lr_shape[0], 1, 1, nfeat)) for _ in range(2)]
+        self.losses = z((4,))
+        self.pxloss = gen_pxloss_function
+        self.lrs = learning_rates
+        self.b1, self.b2, self.eps = beta_1, beta_2, eps
+        self.dist = dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.lr_t = [z((1,)), z((1,))]
+        self._lr_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.graph_fb = self.graph_opt = None
+
+    def _opt(self):
+        import torch
+        from .. import _lib
+        st = torch.cuda.current_stream().cuda_stream
+        for m, lr_t in ((self.G, self.lr_t[0]), (self.D, self.lr_t[1])):
+            a = m.arena
+            _lib.call('dl4ds_adam_step_dev', a.theta.data_ptr(), a.grad.data_ptr(), a.m.data_ptr(), a.v.data_ptr(), a.n,
+                      lr_t.data_ptr(), float(self.b1), float(self.b2), float(self.eps), 1.0 / self.world, st)
+
+    def capture(self):
+        import torch
+        snap = [(m.arena.theta.clone(), m.arena.m.clone(), m.arena.v.clone(), m.arena.t) for m in (self.G, self.D)]
+        _fwd_bwd(self.G, self.D, self.lr, self.hr, self.st, self.masks, self.losses, self.pxloss)   # warm-up (eager)
+        self._opt()
+        torch.cuda.synchronize()
+        for m, (th, mm, vv, t) in zip((self.G, self.D), snap):
+            m.arena.theta.copy_(th); m.arena.m.copy_(mm); m.arena.v.copy_(vv); m.arena.t = t
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.graph_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fb, stream=s):
+                _fwd_bwd(self.G, self.D, self.lr, self.hr, self.st, self.masks, self.losses, self.pxloss)
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, stream=s):
+                self._opt()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        return self
+
+    def run(self, lr_array, hr_array, static_array=None, dropout_masks=None, first_batch=False):
+        """One step on host (or device) arrays; returns (gen_total, gen_gan, gen_px, disc) floats like ``train_step``."""
+        import math
+        import torch
+        f32 = lambda a: torch.as_tensor(np.asarray(a, np.float32) if not torch.is_tensor(a) else a)
+        self.lr.copy_(f32(lr_array), non_blocking=True)
+        self.hr.copy_(f32(hr_array), non_blocking=True)
+        if self.st is not None:
+            self.st.copy_(f32(static_array), non_blocking=True)
+        keep = 1.0 - DROPOUT_RATE
+        for i, m in enumerate(self.masks):
+            if dropout_masks is not None:
+                m.copy_(f32(dropout_masks[i]).reshape(m.shape))
+            else:
+                m.copy_((torch.rand(m.shape, device=m.device) < keep).to(torch.float32) / keep)
+        for i, mdl in enumerate((self.G, self.D)):
+            mdl.arena.t += 1
+            t = mdl.arena.t
+            self._lr_host[i] = self.lrs[i] * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+        self.lr_t[0].copy_(self._lr_host[0:1], non_blocking=True)
+        self.lr_t[1].copy_(self._lr_host[1:2], non_blocking=True)
+        self.graph_fb.replay()
+        d = self.dist
+        if d is not None and self.world > 1:
+            d.all_reduce(self.G.arena.grad, op=d.ReduceOp.SUM)
+            d.all_reduce(self.D.arena.grad, op=d.ReduceOp.SUM)
+        self.graph_opt.replay()
+        if d is not None and self.world > 1 and first_batch:
+            for mdl in (self.G, self.D):
+                for t in (mdl.arena.theta, mdl.arena.m, mdl.arena.v):
+                    d.broadcast(t, src=0)
+        gan, pxs, dr, df = [float(v) for v in self.losses.cpu().numpy()]
+        return gan + pxs, gan, pxs / LAMBDA, dr + df
+
+
 def train_step(lr_array, hr_array, generator, discriminator, generator_optimizer, discriminator_optimizer,
                epoch=0, gen_pxloss_function='mae', summary_writer=None, first_batch=False, static_array=None,
                dropout_masks=None, dist=None):
@@ -88,33 +214,8 @@ def train_step(lr_array, hr_array, generator, discriminator, generator_optimizer
         mk = [f32(m) for m in dropout_masks]
     world = dist.get_world_size() if dist is not None else 1
 
-    G.arena.zero_grad(); D.arena.zero_grad()
     losses = torch.zeros(4, dtype=torch.float32, device=dev)        # gan, px, d_real, d_fake
-
-    # ---- forward: generator, D(real), D(fake)
-    cg = Ctx(G.arena, G.math, training=True)
-    gin = [cg.input(lr_t)] + ([cg.input(st_t)] if st_t is not None else [])
-    gen = G.fn(cg, gin)
-    cr = Ctx(D.arena, D.math, training=True)
-    p_real = D.fn(cr, [cr.input(lr_t), cr.input(hr_t), cr.input(mk[0])])
-    cf = Ctx(D.arena, D.math, training=True)
-    gen_in = Var(gen.buf, gen.off, gen.C, requires_grad=True)
-    p_fake = D.fn(cf, [cf.input(lr_t), gen_in, cf.input(mk[1])])
-
-    # ---- discriminator loss and weight gradients
-    cr.bce_loss(p_real, 1.0, loss_buf=losses[2:3])
-    cr.backward()
-    cf.bce_loss(p_fake, 0.0, loss_buf=losses[3:4])
-    cf.backward(keep_tape=True)
-    gen_in.grad = None                      # d(D loss)/d(gen) is not used by either optimizer
-    # ---- generator loss: through D(fake) to the generated field, then through G
-    cf.param_grads = False
-    cf.bce_loss(p_fake, 1.0, loss_buf=losses[0:1])
-    cf.backward()
-    if gen_in.grad is not None:
-        cg._give_grad(gen, gen_in.grad)
-    cg.pixel_loss(gen, cg.input(hr_t), gen_pxloss_function or 'mae', scale=LAMBDA, loss_buf=losses[1:2])
-    cg.backward()
+    _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function)
 
     # ---- exchange + Adam
     if dist is not None and world > 1:
@@ -175,6 +276,8 @@ class CGANTrainer(Trainer):
             raise ValueError('The argument `time_window` must be a postive integer for spatio-temporal models')
         self.math = math
         self.seed = seed
+        self.use_graph = True        # replay the step as CUDA graphs (CGANStep); False = eager train_step per batch
+        self._step = None
 
     def setup_model(self):
         """cgan.py:173-262."""
@@ -258,12 +361,22 @@ class CGANTrainer(Trainer):
                 else:
                     [lr_array], [hr_array] = res
                     aux_hr = None
-                losses = train_step(
-                    lr_array, hr_array, generator=self.generator, discriminator=self.discriminator,
-                    generator_optimizer=self.generator_optimizer,
-                    discriminator_optimizer=self.discriminator_optimizer, epoch=epoch,
-                    gen_pxloss_function=self.lossf, summary_writer=None,
-                    first_batch=(epoch == 0 and i == 0), static_array=aux_hr, dist=self.dp.dist)
+                if self._step is None and self.use_graph:
+                    # static shapes (fixed batch / patch size): capture the step once, replay it per batch
+                    self._step = CGANStep(
+                        self.generator, self.discriminator, np.shape(lr_array), np.shape(hr_array),
+                        np.shape(aux_hr) if aux_hr is not None else None, gen_pxloss_function=self.lossf,
+                        learning_rates=(self.generator_optimizer.learning_rate,
+                                        self.discriminator_optimizer.learning_rate), dist=self.dp.dist).capture()
+                if self._step is not None:
+                    losses = self._step.run(lr_array, hr_array, aux_hr, first_batch=(epoch == 0 and i == 0))
+                else:
+                    losses = train_step(
+                        lr_array, hr_array, generator=self.generator, discriminator=self.discriminator,
+                        generator_optimizer=self.generator_optimizer,
+                        discriminator_optimizer=self.discriminator_optimizer, epoch=epoch,
+                        gen_pxloss_function=self.lossf, summary_writer=None,
+                        first_batch=(epoch == 0 and i == 0), static_array=aux_hr, dist=self.dp.dist)
             self.gentotal.append(losses[0]); self.gengan.append(losses[1])
             self.gen_pxloss.append(losses[2]); self.disc.append(losses[3])
             if chatty:

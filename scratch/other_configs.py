@@ -70,4 +70,7 @@ go, do = cgan.Adam(2e-4, beta_1=0.5), cgan.Adam(2e-4, beta_1=0.5)
 ms = timed(lambda: cgan.train_step(lr, hr[:B], G, D, go, do, gen_pxloss_function='mae', static_array=st), n=4, warm=2)
 out['cfg5 cGAN unet pin 256x256, batch 4/GPU (eager step)'] = dict(ms_per_step=ms, hr_px_per_s=B * 256 * 256 / ms * 1e3,
                                                                     params=G.count_params() + D.count_params())
+step = cgan.CGANStep(G, D, lr.shape, hr[:B].shape, st.shape).capture()
+ms = timed(lambda: step.run(lr, hr[:B], st), n=6, warm=2)
+out['cfg5 cGAN unet pin 256x256, batch 4/GPU (CUDA-graph step)'] = dict(ms_per_step=ms, hr_px_per_s=B * 256 * 256 / ms * 1e3)
 print(json.dumps(out, indent=1), flush=True)

@@ -140,3 +140,35 @@ def test_supervised_run_data_on_device(cuda):
         assert isinstance(tr.ds_train, DeviceDataGenerator) == on_dev
         hist.append(tr.fithist.history['loss'])
     assert np.allclose(hist[0], hist[1], rtol=2e-4), hist
+
+
+def test_cgan_graph_step_equals_eager_step(cuda):
+    """CGANStep (captured CUDA graphs, device-side Adam step sizes) == train_step (eager launches) over three steps
+    with the same dropout masks: same four losses, same generator and discriminator weights."""
+    rng = np.random.default_rng(21)
+    B, hw = 4, 32
+    lr = rng.standard_normal((B, hw, hw, 2)).astype(np.float32)
+    hr = rng.standard_normal((B, hw, hw, 1)).astype(np.float32)
+    st = rng.standard_normal((B, hw, hw, 1)).astype(np.float32)
+    results = []
+    for graph in (False, True):
+        G = nets.unet_pin('unet', 2, 1, (hw, hw), 1, 8, 2, math='tf32x3').to(cuda).init_weights(3)
+        D = nets.residual_discriminator(2, 'pin', False, 4, (hw, hw), n_filters=8, n_res_blocks=1, math='tf32x3').to(cuda).init_weights(4)
+        nfeat = D.spec['dense1/kernel'][0]
+        mrng = np.random.default_rng(5)
+        step = cgan.CGANStep(G, D, lr.shape, hr.shape, st.shape).capture() if graph else None
+        go, do = cgan.Adam(2e-4, beta_1=0.5), cgan.Adam(2e-4, beta_1=0.5)
+        hist = []
+        for i in range(3):
+            masks = [(mrng.random((B, 1, 1, nfeat)) < 0.6).astype(np.float32) / 0.6 for _ in range(2)]
+            if graph:
+                hist.append(step.run(lr, hr, st, dropout_masks=masks))
+            else:
+                hist.append(cgan.train_step(lr, hr, G, D, go, do, gen_pxloss_function='mae', static_array=st,
+                                            dropout_masks=masks))
+        results.append((np.array(hist), G.get_weights(), D.get_weights()))
+    (h0, g0, d0), (h1, g1, d1) = results
+    assert np.allclose(h0, h1, rtol=2e-4, atol=1e-6), (h0, h1)
+    for a, b in ((g0, g1), (d0, d1)):
+        worst = max(float(np.abs(a[k] - b[k]).max()) for k in a)
+        assert worst <= 1e-3, worst      # Adam's first steps move weights by ~lr per step; sign flips of ~0 gradients
