@@ -13,8 +13,12 @@
 
 namespace dl4ds {
 
+// `splits` > 1 (split-K): blockIdx.z takes a contiguous range of the (tap, channel-chunk) loop and ADDS its raw partial
+// sums into y (zeroed by the launcher); bias / residual / activation are applied afterwards by conv_finish_kernel.
+// Used when M x Cout yields only a handful of CTAs but K is long (the 4x4 / 8x8 levels of the U-Net, sp_preups.py:
+// 230-315: 256 pixels x 256 channels x K=2304 ran on 4-16 CTAs for 340 us).
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvArgs p) {
+__global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvArgs p, int splits) {
     constexpr int BK = 8;
     constexpr int APT = BM * BK / 256;   // A floats per thread per chunk (4 or 8)
     constexpr int TPP = BK / APT;        // threads per pixel (2 or 1)
@@ -41,8 +45,12 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvArgs p) {
         base_x = ox * p.stride - p.pad_l;
     }
     const int cpt = (p.Cin + BK - 1) / BK;
-    const int nchunks = p.KH * p.KW * cpt;
+    const int nchunks_all = p.KH * p.KW * cpt;
     const int ntaps = p.KH * p.KW;
+    const int per = (nchunks_all + splits - 1) / splits;
+    const int chunk0 = blockIdx.z * per;
+    const int nchunks = min(per, nchunks_all - chunk0);
+    if (nchunks <= 0) return;
 
     float ra[APT];
     float rb[BPT];
@@ -115,11 +123,11 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvArgs p) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-    load_chunk(0);
+    load_chunk(chunk0);
     store_chunk();
     __syncthreads();
     for (int chunk = 0; chunk < nchunks; ++chunk) {
-        if (chunk + 1 < nchunks) load_chunk(chunk + 1);
+        if (chunk + 1 < nchunks) load_chunk(chunk0 + chunk + 1);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[TM], b[TN];
@@ -160,6 +168,10 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvArgs p) {
             const int co = n0 + tx * TN + j;
             if (co >= p.Cout) continue;
             float v = acc[i][j];
+            if (splits > 1) {
+                atomicAdd(p.y + (int64_t)m * p.y_ld + co, v);
+                continue;
+            }
             if (p.bias) v += __ldg(p.bias + co);
             if (p.res) v += __ldg(p.res + (int64_t)m * p.res_ld + co);
             v = apply_act(v, p.act);
@@ -176,10 +188,43 @@ __global__ void __launch_bounds__(256) conv_fwd_kernel(const ConvArgs p) {
     }
 }
 
+// y = act(y + bias + res) over (M, Cout) with pitch: second pass of the split-K path
+__global__ void conv_finish_kernel(float* __restrict__ y, int y_ld, const float* __restrict__ bias,
+                                   const float* __restrict__ res, int res_ld, int64_t M, int Cout, int act) {
+    const int64_t total = M * Cout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / Cout;
+        const int co = (int)(i - m * Cout);
+        float v = y[m * y_ld + co];
+        if (bias) v += __ldg(bias + co);
+        if (res) v += __ldg(res + m * res_ld + co);
+        y[m * y_ld + co] = apply_act(v, act);
+    }
+}
+
 template <int BM, int BN, int TM, int TN>
 static int launch_conv(const ConvArgs& a, cudaStream_t st) {
     dim3 grid((unsigned)cdiv(a.M, BM), (unsigned)cdiv(a.Cout, BN));
-    conv_fwd_kernel<BM, BN, TM, TN><<<grid, 256, 0, st>>>(a);
+    const int nchunks = a.KH * a.KW * ((a.Cin + 7) / 8);
+    const int ctas = (int)(grid.x * grid.y);
+    int splits = 1;
+    if (ctas * 4 <= kNumSMs && nchunks >= 32 && a.d2s_r <= 1 && !a.beta) {
+        splits = (2 * kNumSMs) / ctas;
+        if (splits > nchunks / 8) splits = nchunks / 8;      // >= 8 chunks (64 K rows) per split
+    }
+    if (splits > 1) {
+        grid.z = (unsigned)splits;
+        if (cudaMemset2DAsync(a.y, (size_t)a.y_ld * 4, 0, (size_t)a.Cout * 4, (size_t)a.M, st) != cudaSuccess)
+            return check_launch("conv_fwd split-K memset");
+        conv_fwd_kernel<BM, BN, TM, TN><<<grid, 256, 0, st>>>(a, splits);
+        int rc = check_launch("conv_fwd_kernel");
+        if (rc) return rc;
+        const int64_t total = (int64_t)a.M * a.Cout;
+        const int blocks = (int)((total + 255) / 256 > 8 * kNumSMs ? 8 * kNumSMs : (total + 255) / 256);
+        conv_finish_kernel<<<blocks, 256, 0, st>>>(a.y, a.y_ld, a.bias, a.res, a.res_ld, a.M, a.Cout, a.act);
+        return check_launch("conv_finish_kernel");
+    }
+    conv_fwd_kernel<BM, BN, TM, TN><<<grid, 256, 0, st>>>(a, 1);
     return check_launch("conv_fwd_kernel");
 }
 

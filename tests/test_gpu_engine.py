@@ -408,3 +408,20 @@ def test_conv_transpose_as_conv_d2s(cuda, math, shape, cout, k, stride, act):
     compare(fn, _o(ofn_), [shape], cuda, math=math, **tol)
     if math != 'fp32' and stride == 2 and shape[2] >= 16:
         assert _tc_count() > n0, 'tensor-core path did not run'
+
+
+@pytest.mark.parametrize('shape,cout,act,with_res', [((4, 8, 8, 256), 256, 'relu', False),
+                                                      ((4, 4, 4, 256), 256, 'tanh', True),
+                                                      ((3, 8, 8, 128), 64, None, False)])
+def test_conv_small_map_split_k(cuda, shape, cout, act, with_res):
+    """Deep U-Net levels (4x4 / 8x8 maps, 128-256 channels): the CUDA-core kernel splits the (tap, channel) loop over
+    blockIdx.z and finishes bias / residual / activation in a second pass (conv_finish_kernel)."""
+    if with_res:
+        fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=3, act=act, res=xs[1])
+        ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=3) + xs[1], act))
+        shapes = [shape, shape[:3] + (cout,)]
+    else:
+        fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=3, act=act)
+        ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=3), act))
+        shapes = [shape]
+    compare(fn, ofn, shapes, cuda, math='tf32x3', tol=2e-5, gtol=2e-4)
