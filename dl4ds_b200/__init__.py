@@ -6,7 +6,7 @@ __version__ = '0.1.0'
 from .utils import (BACKBONE_BLOCKS, DROPOUT_VARIANTS, INTERPOLATION_METHODS, LOSS_FUNCTIONS,  # noqa: F401
                     POSTUPSAMPLING_METHODS, UPSAMPLING_METHODS)
 from .dataloader import DataGenerator, create_batch_hr_lr, create_pair_hr_lr  # noqa: F401
-from .nets import (net_pin, net_postupsampling, recnet_postupsampling, residual_discriminator,  # noqa: F401
-                   unet_pin)
+from .nets import (net_pin, net_postupsampling, recnet_pin, recnet_postupsampling,  # noqa: F401
+                   residual_discriminator, unet_pin)
 from .training import CGANTrainer, SupervisedTrainer, Trainer  # noqa: F401
 from .inference import Predictor, predict  # noqa: F401

@@ -409,7 +409,7 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
     _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
     if backbone_block == 'unet':
         raise ValueError('unet backbone is not compatible with post-upsampling')
-    if upsampling not in POSTUPSAMPLING_METHODS:
+    if upsampling not in POSTUPSAMPLING_METHODS + ('pin',):
         raise ValueError('`upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
     T = int(time_window)
     aux = n_aux_channels > 0
@@ -433,8 +433,9 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
             x = B.subpixel_block(c, 'SubpixelConvolution', x, scale, nf_ups)
         elif upsampling == 'rc':
             x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf_ups)
-        else:
+        elif upsampling == 'dc':
             x = B.deconv_block(c, 'Deconvolution', x, scale, nf_ups, None)    # no activation passed
+        # ('pin': the samples already live on the HR grid, spt_preups.py:100-118)
         if aux:
             # ConvBlock on the static HR field, then tf.repeat over time (spt_postups.py:135-141):
             # the static branch is time- and (per-sample) batch-dependent only through s_in
@@ -444,7 +445,8 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
         if localcon_layer:
             lws = B.localized_conv_block(c, 'LocalizedConvBlock', x, 2)
             x = c.concat([x, lws])
-        x = B.transition_block(c, 'TransitionLast', x, x.C // 2)
+        # spt_postups.py:150 halves the channels; spt_preups.py:133 goes straight to n_filters
+        x = B.transition_block(c, 'TransitionLast', x, n_filters if upsampling == 'pin' else x.C // 2)
         # ConvBlock(n_filters, activation=None, attention=True) on the 5-D tensor: the attention's
         # reduce_mean over axes [1,2] pools (T,H) and keeps W (blocks.py:587)
         y = c.conv(x, 'ConvBlock_tail/conv1', n_filters)
@@ -458,6 +460,20 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
     if aux:
         shapes.append((int(h_lr * scale), int(w_lr * scale), n_aux_channels))
     return Model('rec' + backbone_block + '_' + upsampling, fn, shapes, time_window=T, math=math)
+
+
+def recnet_pin(backbone_block, n_channels, n_aux_channels, hr_size, time_window, n_channels_out=1, n_filters=8,
+               n_blocks=6, normalization=None, dropout_rate=0, dropout_variant=None, attention=False,
+               activation='relu', output_activation=None, localcon_layer=False, math='fp32'):
+    """recnet_pin -- spt_preups.py:12-163: the recurrent (ConvLSTM) network on samples that were interpolated to
+    the HR grid beforehand.  Same graph as ``recnet_postupsampling`` without the upsampler; TransitionLast maps to
+    ``n_filters``.  Inputs (B,T,H,W,C) [+ (B,H,W,n_aux)]; output (B,T,H,W,n_channels_out)."""
+    m = recnet_postupsampling(backbone_block, 'pin', 1, n_channels, n_aux_channels, hr_size, time_window,
+                              n_channels_out=n_channels_out, n_filters=n_filters, n_blocks=n_blocks,
+                              dropout_rate=dropout_rate, dropout_variant=dropout_variant, normalization=normalization,
+                              attention=attention, activation=activation, output_activation=output_activation,
+                              localcon_layer=localcon_layer, math=math)
+    return m
 
 
 def residual_discriminator(n_channels, upsampling, is_spatiotemporal, scale, lr_size, n_filters=8,

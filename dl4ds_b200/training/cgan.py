@@ -448,11 +448,15 @@ def load_checkpoint(checkpoint_dir, checkpoint_number, backbone, upsampling, sca
                 n_channels_out=1, attention=attention, localcon_layer=localcon_layer, math=math)
     elif upsampling == 'pin':
         if st:
-            raise NotImplementedError('recnet_pin is outside the B200 hot path (no BASELINE config)')
-        build = nets.unet_pin if backbone == 'unet' else nets.net_pin
-        generator = build(backbone_block=backbone, n_channels=n_channels, n_aux_channels=n_aux,
-                          hr_size=input_height_width, n_filters=n_filters[0], n_blocks=n_blocks[0], n_channels_out=1,
-                          attention=attention, localcon_layer=localcon_layer, math=math)
+            generator = nets.recnet_pin(backbone_block=backbone, n_channels=n_channels, n_aux_channels=n_aux,
+                                        hr_size=input_height_width, time_window=time_window, n_filters=n_filters[0],
+                                        n_blocks=n_blocks[0], n_channels_out=1, attention=attention,
+                                        localcon_layer=localcon_layer, math=math)
+        else:
+            build = nets.unet_pin if backbone == 'unet' else nets.net_pin
+            generator = build(backbone_block=backbone, n_channels=n_channels, n_aux_channels=n_aux,
+                              hr_size=input_height_width, n_filters=n_filters[0], n_blocks=n_blocks[0], n_channels_out=1,
+                              attention=attention, localcon_layer=localcon_layer, math=math)
     else:
         raise ValueError('`upsampling` not recognized')
     discriminator = nets.residual_discriminator(

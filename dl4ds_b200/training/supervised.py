@@ -143,9 +143,11 @@ class SupervisedTrainer(Trainer):
                         lr_size=(lr_h, lr_w), n_channels=n_channels, n_aux_channels=n_aux_channels,
                         math=self.math, **ap)
             elif self.upsampling == 'pin':
-                if self.model_is_spatiotemporal:
-                    raise NotImplementedError('recnet_pin is outside the B200 hot path (no BASELINE config)')
-                if self.backbone == 'unet':
+                if self.model_is_spatiotemporal:          # supervised.py:300-307
+                    self.model = nets.recnet_pin(
+                        backbone_block=self.backbone, n_channels=n_channels, n_aux_channels=n_aux_channels,
+                        hr_size=(hr_h, hr_w), time_window=self.time_window, math=self.math, **ap)
+                elif self.backbone == 'unet':
                     self.model = nets.unet_pin(
                         backbone_block=self.backbone, n_channels=n_channels, n_aux_channels=n_aux_channels,
                         hr_size=(hr_h, hr_w), math=self.math, **ap)

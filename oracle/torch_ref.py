@@ -443,6 +443,7 @@ def recnet_postupsampling(p, inputs, backbone_block, upsampling, scale, time_win
         xf = resize_conv_block(p, 'ResizeConvolution', xf, scale, n_filters_ups)
     elif upsampling == 'dc':
         xf = deconv_block(p, 'Deconvolution', xf, scale, n_filters_ups, None)   # App. B #8
+    # upsampling == 'pin' (recnet_pin, spt_preups.py:100-118): no upsampler
     if len(inputs) > 1:
         s = conv_block(p, 'ConvBlock_aux', _nchw(inputs[1]), n_filters, activation, attention)
         s = s.unsqueeze(1).expand(bsz, t, *s.shape[1:]).reshape(bsz * t, *s.shape[1:])
@@ -450,7 +451,8 @@ def recnet_postupsampling(p, inputs, backbone_block, upsampling, scale, time_win
     if localcon_layer:
         lws = localized_conv_block(p, 'LocalizedConvBlock', xf, 2)
         xf = torch.cat([xf, lws], dim=1)
-    xf = transition_block(p, 'TransitionLast', xf, xf.shape[1] // 2)
+    # spt_postups.py:150 halves the channel count; spt_preups.py:133 maps to n_filters
+    xf = transition_block(p, 'TransitionLast', xf, n_filters if upsampling == 'pin' else xf.shape[1] // 2)
     # ConvBlock(n_filters, activation=None, attention=True) on a 5-D tensor (App. B #6)
     y = _conv(p, 'ConvBlock_tail/conv1', xf, n_filters)
     y = _conv(p, 'ConvBlock_tail/conv2', y, n_filters)
@@ -460,6 +462,15 @@ def recnet_postupsampling(p, inputs, backbone_block, upsampling, scale, time_win
     y = conv_block(p, 'ConvBlock_out', y, n_channels_out, activation=output_activation)
     y5 = y.reshape(bsz, t, *y.shape[1:])
     return y5.permute(0, 1, 3, 4, 2).contiguous()
+
+
+def recnet_pin(p, inputs, backbone_block, time_window, n_channels_out=1, n_filters=8, n_blocks=6, attention=False,
+               activation='relu', output_activation=None, localcon_layer=False):
+    """recnet_pin -- spt_preups.py:12-163: recnet_postupsampling's graph without the upsampler (inputs already on
+    the HR grid) and with TransitionLast -> n_filters (:133)."""
+    return recnet_postupsampling(p, inputs, backbone_block, 'pin', 1, time_window, n_channels_out=n_channels_out,
+                                 n_filters=n_filters, n_blocks=n_blocks, attention=attention, activation=activation,
+                                 output_activation=output_activation, localcon_layer=localcon_layer)
 
 
 def residual_discriminator(p, inputs, upsampling, scale, lr_size, n_filters=8, n_res_blocks=4,

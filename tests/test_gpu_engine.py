@@ -425,3 +425,18 @@ def test_conv_small_map_split_k(cuda, shape, cout, act, with_res):
         ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=3), act))
         shapes = [shape]
     compare(fn, ofn, shapes, cuda, math='tf32x3', tol=2e-5, gtol=2e-4)
+
+
+def test_net_recnet_pin(cuda):
+    """recnet_pin (spt_preups.py:12-163): ConvLSTM backbone on pre-upsampled samples, static HR branch, T=3."""
+    T, Bz = 3, 2
+    m = nets.recnet_pin('resnet', 2, 1, (16, 16), T, n_blocks=1)
+    assert m.name == 'recresnet_pin'
+
+    def ofn(p, xs):
+        x = xs[0]
+        x5 = x.reshape(T, Bz, *x.shape[1:]).permute(1, 0, 2, 3, 4)      # (B,T,H,W,C)
+        y5 = R.recnet_pin(p, [x5, xs[1]], 'resnet', T, n_blocks=1)
+        return y5.permute(1, 0, 2, 3, 4).reshape(T * Bz, *y5.shape[2:])
+    shapes = [(T * Bz, 16, 16, 2), (Bz, 16, 16, 1)]
+    compare(m.fn, ofn, shapes, cuda, tol=5e-5, gtol=1e-3, input_grads=False)

@@ -192,3 +192,15 @@ def test_model_names_and_unsupported():
         nets.net_postupsampling('convnext', 'spc', 4, 1, 0, (8, 8))
     with pytest.raises(NotImplementedError):
         nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), activation='gelu')
+
+
+def test_recnet_pin_structure():
+    """recnet_pin: same parameters as recnet_postupsampling minus the upsampler; TransitionLast -> n_filters
+    (spt_preups.py:133)."""
+    from dl4ds_b200 import nets
+    m = nets.recnet_pin('resnet', 1, 0, (16, 16), 4, n_filters=8, n_blocks=2)
+    assert m.name == 'recresnet_pin' and m.input.shape == (None, 4, 16, 16, 1)
+    assert m.spec['TransitionLast/conv/kernel'] == (1, 1, 8, 8)
+    assert not any(k.startswith(('SubpixelConvolution', 'ResizeConvolution', 'Deconvolution')) for k in m.spec)
+    md = nets.recnet_pin('densenet', 1, 0, (16, 16), 4, n_filters=8, n_blocks=2)
+    assert md.spec['TransitionLast/conv/kernel'] == (1, 1, 16, 8)
