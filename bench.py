@@ -248,6 +248,18 @@ def run_native(args):
     if sampler is not None:
         sampler.stop()
 
+    # ---------------- forward only: Predictor path (host LR in, host HR out) ----------------
+    lr_all = np.concatenate([hp[0] for hp in host_pool], axis=0)          # n_pool batches of LR tiles
+    model.predict([lr_all], batch_size=BATCH)                              # warm-up + graph capture
+    barrier()
+    t_p0 = time.perf_counter()
+    n_pred_rounds = 4
+    for _ in range(n_pred_rounds):
+        y_pred = model.predict([lr_all], batch_size=BATCH)
+    torch.cuda.synchronize()
+    pred_s = (time.perf_counter() - t_p0) / n_pred_rounds
+    pred_px = y_pred.shape[0] * HR_HW * HR_HW
+
     # ---------------- per-kernel durations (roofline) ----------------
     timers = {}
     n_prof = 3
@@ -331,6 +343,9 @@ def run_native(args):
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps,
                     'api': 'SupervisedTrainer.train_on_batches(host numpy (LR, HR) batches) -> one float loss per step '
                            '(the fit loop of SupervisedTrainer.run: pinned staging + H2D of batch i+1 overlap step i)'},
+            'predict': {'value': pred_px * world / pred_s, 'unit': UNIT, 'ms_per_batch': pred_s / n_pool * 1e3,
+                        'api': 'Model.predict(host LR array, batch_size=64) -> host HR array (forward only, captured '
+                               'graph per chunk, H2D + D2H included; what Predictor.run calls, inference.py:238)'},
             'gpu_launches': int(step.launches_per_step * args.steps),
             'launches_per_step': int(step.launches_per_step),
             'roofline': roofline,

@@ -219,19 +219,72 @@ class Model:
         return self._finish_output(out.t.contiguous(), bsz, T)
 
     def predict(self, inputs, batch_size=32, verbose=0):
-        """keras ``Model.predict`` (inference.py:238): forward in chunks of ``batch_size``."""
+        """keras ``Model.predict`` (inference.py:238): forward in chunks of ``batch_size``.  Spatial models run every
+        full chunk through ONE captured CUDA graph of the forward pass (static input buffers, weight images re-packed
+        from the live parameters inside the graph), with pinned staging: the host converts chunk i+1 and copies chunk
+        i-1's result out while chunk i computes.  A trailing partial chunk (and spatio-temporal models) run eagerly."""
         self.to('cuda')
         if not isinstance(inputs, (list, tuple)):
             inputs = [inputs]
         n = len(inputs[0])
         outs = []
-        for s in range(0, n, batch_size):
+        start = 0
+        spatial = all(len(s_) == 3 for s_ in self.input_shapes) and all(np.ndim(x) == 4 for x in inputs)
+        if spatial and n >= batch_size and self.arena.device.type == 'cuda':
+            outs, start = self._predict_graphed(inputs, batch_size, verbose)
+        for s in range(start, n, batch_size):
             chunk = [x[s:s + batch_size] for x in inputs]
             y = self(chunk)
             outs.append(y.cpu().numpy())
             if verbose:
                 print('%d/%d' % (min(s + batch_size, n), n))
         return np.concatenate(outs, axis=0)
+
+    def _predict_graphed(self, inputs, batch_size, verbose):
+        """All full chunks through a captured forward graph; returns (list of output arrays, samples consumed)."""
+        dev = self.arena.device
+        shapes = tuple((batch_size,) + tuple(np.shape(x)[1:]) for x in inputs)
+        cache = self.__dict__.setdefault('_predict_graphs', {})
+        key = (shapes, self.math)
+        if key not in cache:
+            xin = [torch.zeros(shp, dtype=torch.float32, device=dev) for shp in shapes]
+            _, o = self.forward(xin, training=False)                     # warm-up (module load, allocator)
+            torch.cuda.synchronize()
+            stream = torch.cuda.Stream()
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                with torch.cuda.graph(g, stream=stream):
+                    ctx, o = self.forward(xin, training=False, pack_stream=side)
+                    ctx.join_pack_stream()
+                    y = o.t.contiguous()
+            torch.cuda.current_stream().wait_stream(stream)
+            pin_in = [[torch.empty(shp, dtype=torch.float32).pin_memory() for shp in shapes] for _ in range(2)]
+            pin_out = [torch.empty(tuple(y.shape), dtype=torch.float32).pin_memory() for _ in range(2)]
+            cache[key] = (g, xin, y, pin_in, pin_out, [torch.cuda.Event() for _ in range(2)])
+        g, xin, y, pin_in, pin_out, evs = cache[key]
+        n_full = (len(inputs[0]) // batch_size) * batch_size
+        outs = []
+        for i, s in enumerate(range(0, n_full, batch_size)):
+            k = i & 1
+            if i >= 2:
+                evs[k].synchronize()                                     # slot k's previous result has landed
+                outs.append(pin_out[k].numpy().copy())
+            for dst, x in zip(pin_in[k], inputs):
+                dst.numpy()[...] = np.asarray(x[s:s + batch_size], dtype=np.float32)
+            for d, src in zip(xin, pin_in[k]):
+                d.copy_(src, non_blocking=True)
+            g.replay()
+            pin_out[k].copy_(y, non_blocking=True)
+            evs[k].record()
+            if verbose:
+                print('%d/%d' % (s + batch_size, len(inputs[0])))
+        nchunks = n_full // batch_size
+        for i in range(max(0, nchunks - 2), nchunks):                    # drain the last (up to) two slots in order
+            evs[i & 1].synchronize()
+            outs.append(pin_out[i & 1].numpy().copy())
+        return outs, n_full
 
 
 # ---------------------------------------------------------------------------------------------

@@ -172,3 +172,16 @@ def test_cgan_graph_step_equals_eager_step(cuda):
     for a, b in ((g0, g1), (d0, d1)):
         worst = max(float(np.abs(a[k] - b[k]).max()) for k in a)
         assert worst <= 1e-3, worst      # Adam's first steps move weights by ~lr per step; sign flips of ~0 gradients
+
+
+def test_predict_graphed_equals_eager(cuda):
+    """Model.predict: full chunks through the captured forward graph (+ an eager trailing chunk) == one eager
+    forward over everything; still correct after the weights change (the graph re-packs the weight images)."""
+    m = nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (16, 16), n_blocks=2, math='tf32x3').to(cuda).init_weights(5)
+    lr = np.random.default_rng(9).standard_normal((22, 16, 16, 1)).astype(np.float32)
+    for rnd in range(2):
+        ref = m([lr]).cpu().numpy()                       # eager, one batch of 22
+        out = m.predict([lr], batch_size=4)               # 5 graphed chunks + 1 eager chunk of 2
+        assert out.shape == (22, 64, 64, 1)
+        assert np.abs(out - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+        m.arena.theta.mul_(1.5)                           # change the parameters, predict again
