@@ -616,6 +616,35 @@ __global__ void __launch_bounds__(256) bias_act_bwd_vec4_kernel(
             }
         }
         acc[0] = a0;
+    } else if (KS == 1 && r == 1 && tx < G) {
+        // same-layout case (every backbone layer): 4 pixels in flight per thread, loads of dy and y issued together
+        const int c = tx * 4;
+        const int64_t step = (int64_t)gridDim.x * PY;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t p0 = (int64_t)blockIdx.x * PY + ty; p0 < n_pix; p0 += 4 * step) {
+            float4 v[4], o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = p0 + u * step;
+                if (p < n_pix) {
+                    v[u] = __ldg(reinterpret_cast<const float4*>(dy + p * dy_ld + c));
+                    if (act != DL4DS_ACT_NONE) o[u] = __ldg(reinterpret_cast<const float4*>(y + p * y_ld + c));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = p0 + u * step;
+                if (p < n_pix) {
+                    if (act != DL4DS_ACT_NONE) {
+                        v[u].x *= act_grad_from_out(o[u].x, act); v[u].y *= act_grad_from_out(o[u].y, act);
+                        v[u].z *= act_grad_from_out(o[u].z, act); v[u].w *= act_grad_from_out(o[u].w, act);
+                    }
+                    if (dz) *reinterpret_cast<float4*>(dz + p * dz_ld + c) = v[u];
+                    a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w;
+                }
+            }
+        }
+        acc[0] = a0;
     } else
     for (int64_t p = (int64_t)blockIdx.x * PY + ty; p < n_pix; p += (int64_t)gridDim.x * PY) {
         int n = 0, oy = 0, ox = 0;
@@ -685,7 +714,7 @@ int bias_act_bwd_vec4(const float* dy, int dy_ld, const float* y, int y_ld, floa
     const int G = C / 4;
     int TX = 1;
     while (TX < G && TX < 64) TX <<= 1;
-    if (G <= 64 && G > 32) TX = G;                          // e.g. 48 float4 groups: no idle lanes
+    if (G <= 64 && (G & (G - 1)) != 0) TX = G;              // e.g. 48, 12, 10 or 6 float4 groups: no idle lanes
     const int KS = (G + TX - 1) / TX;
     if (KS > 4) return DL4DS_E_UNSUPPORTED;
     const int PY = 256 / TX;
