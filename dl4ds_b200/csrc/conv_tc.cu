@@ -155,6 +155,8 @@ struct TcFwdParams {
     int group, ngroups;     // kernel-tap / channel-chunk iterations per smem stage, stages per tile
     int stackn;             // x3, Npad <= 64: B = [W_hi ; W_lo] stacked on N -> 2 MMAs per K-step (see the issuer)
     int acc_stride;         // TMEM columns per accumulator buffer: Npad, or 2*Npad when stackn
+    int lo_tmem;            // x3 + stackn: the lo halves of the activation tile go to TMEM (A operand of the second MMA
+                            // from TMEM), the raw tile in smem is the hi operand: no A_lo write / read in shared memory
     int a_tmem;             // x3: split activations go to TMEM (A operand from TMEM), not back to smem
     int tmem_a_off;         // first TMEM column of the A ring (stage s, iteration j: + (s*group+j)*2*kc)
 };
@@ -207,7 +209,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
         if (lane == 0) {
             const uint32_t it_bytes = (uint32_t)(p.a_bytes + p.b_bytes * (X3 ? 2 : 1));
             const uint32_t a_lo_off = (uint32_t)(p.group * p.a_bytes);
-            const uint32_t b_off = a_lo_off * ((X3 && !p.a_tmem) ? 2u : 1u);
+            const uint32_t b_off = a_lo_off * ((X3 && !p.a_tmem && !p.lo_tmem) ? 2u : 1u);
             const uint32_t b_lo_off = (uint32_t)(p.group * p.b_bytes);
             int s = 0;
             uint32_t ph = 0;
@@ -262,7 +264,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 uint32_t accumulate = 0;
                 int ch = 0;
                 const uint32_t a_lo_off = (uint32_t)(p.group * p.a_bytes);
-                const uint32_t b_off = a_lo_off * ((X3 && !p.a_tmem) ? 2u : 1u);
+                const uint32_t b_off = a_lo_off * ((X3 && !p.a_tmem && !p.lo_tmem) ? 2u : 1u);
                 const uint32_t b_lo_off = (uint32_t)(p.group * p.b_bytes);
                 for (int g = 0; g < p.ngroups; ++g) {
                     const int n = min(p.group, nit - g * p.group);
@@ -285,6 +287,12 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                                 umma_tf32_ts(td, al, db, idesc, accumulate);
                                 umma_tf32_ts(td, ah, dbl, idesc, 1u);
                                 umma_tf32_ts(td, ah, db, idesc, 1u);
+                            } else if (X3 && p.lo_tmem) {
+                                // as the stacked-N scheme below, with A_lo read from TMEM (lane = pixel row, one
+                                // column per channel of the chunk) instead of shared memory
+                                const uint32_t tl = tmem_d + (uint32_t)(p.tmem_a_off + (s * p.group + j) * p.kc + k * 8);
+                                umma_tf32(td, da, db, idesc2, accumulate);
+                                umma_tf32_ts(td, tl, db, idesc, 1u);
                             } else if (X3 && p.stackn) {
                                 // A_hi x [W_hi ; W_lo] -> columns [0,Npad) and [Npad,2Npad); A_lo x W_hi -> columns
                                 // [0,Npad).  One MMA costs ~119 cycles for any N <= 128 (scratch/umma_rate.cu), so
@@ -398,6 +406,43 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 uint8_t* a_hi = smem_al + (size_t)s * p.stage_bytes;
                 uint8_t* a_lo = a_hi + a_lo_off;
+                if (p.lo_tmem) {
+                    // thread = pixel row of the tile = TMEM lane: read the row's channels of every chunk of the stage
+                    // through the TMA swizzle (a quarter-warp = 8 consecutive rows hits 8 distinct 16-byte slots),
+                    // keep the raw tile untouched (it is the hi operand) and store lo = v - trunc(v) to TMEM.  The
+                    // arrival for stage s is deferred until stage s+1's shared-memory reads are issued, which
+                    // keeps the tcgen05.st latency off the critical path.
+                    const int q = warp & 3;
+                    const int row = q * 32 + lane;
+                    const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)p.tmem_a_off;
+                    const int noct = (n * p.kc) >> 3;                     // <= 4 (group * kc <= 32)
+                    float4 v0[4], v1[4];
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (o < noct) {
+                            const int e0 = o * 8, j = e0 / p.kc, c = e0 - j * p.kc;
+                            const uint8_t* arow = a_hi + (size_t)j * p.a_bytes + (size_t)row * p.span;
+                            v0[o] = *reinterpret_cast<const float4*>(arow + (swizzle_unit(c >> 2, row, p.span) << 4));
+                            v1[o] = *reinterpret_cast<const float4*>(arow + (swizzle_unit((c >> 2) + 1, row, p.span) << 4));
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (o < noct) {
+                            const int e0 = o * 8, j = e0 / p.kc, c = e0 - j * p.kc;
+                            const float vv[8] = {v0[o].x, v0[o].y, v0[o].z, v0[o].w, v1[o].x, v1[o].y, v1[o].z, v1[o].w};
+                            float l[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) l[e] = vv[e] - tf32_trunc(vv[e]);
+                            tmem_st8(trow + (uint32_t)((s * p.group + j) * p.kc + c), l);
+                        }
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive_warp(smem_u32(&bar_conv[s]));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    continue;
+                }
                 if (p.a_tmem) {
                     // thread = A row (TMEM lane): read the row's channels of the stage (<= 32 floats = 4 octets)
                     // through the TMA swizzle, then -- only now -- wait for the PREVIOUS stage's TMEM stores
@@ -580,18 +625,24 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     // opt-in (DL4DS_TC_A_TMEM=1) until the TMEM-store latency is understood.
     static const bool want_a_tmem = [] { const char* e = getenv("DL4DS_TC_A_TMEM"); return e && e[0] == '1'; }();
     p.a_tmem = (want_a_tmem && x3 && 2 * p.Npad + 2 * 2 * c.kc <= 512) ? 1 : 0;
-    const int it_bytes = p.a_tmem ? (p.a_bytes + 2 * p.b_bytes) : (p.a_bytes + p.b_bytes) * (x3 ? 2 : 1);
+    static const bool no_stack = [] { const char* e = getenv("DL4DS_TC_NO_STACKN"); return e && e[0] == '1'; }();
+    // MEASURED (round 1f): correct (131/131 parity tests) but slower -- 3.47 vs 2.77 ms/step, SPC dgrad 287 vs 116 us: the
+    // four row-per-thread splitter warps run one LDS -> split -> tcgen05.st -> wait::st chain per stage, which is longer
+    // than the stage's MMAs.  Opt-in (DL4DS_TC_LO_TMEM=1) until the stores are spread over two warps per lane quadrant.
+    static const bool want_lo_tmem = [] { const char* e = getenv("DL4DS_TC_LO_TMEM"); return e && e[0] == '1'; }();
+    p.stackn = (x3 && !p.a_tmem && p.Npad <= 64 && !no_stack) ? 1 : 0;
+    p.lo_tmem = (p.stackn && want_lo_tmem) ? 1 : 0;
+    const int it_bytes = (p.a_tmem || p.lo_tmem) ? (p.a_bytes + 2 * p.b_bytes) : (p.a_bytes + p.b_bytes) * (x3 ? 2 : 1);
     int group = (32 * 1024) / it_bytes;                    // ~32 KB per stage: few barrier round trips per tile
     if (group < 1) group = 1;
     if (group > nit) group = nit;
     if (p.a_tmem && group * c.kc > 32) group = 32 / c.kc;  // the splitter holds one stage row (<= 32 floats) in registers
+    if (p.lo_tmem) group = 1;                              // one chunk per stage: TMEM columns (kc per stage) decide the ring depth
     p.group = group;
     p.ngroups = (nit + group - 1) / group;
     p.stage_bytes = group * it_bytes;
-    p.tmem_a_off = 2 * p.Npad;
-    static const bool no_stack = [] { const char* e = getenv("DL4DS_TC_NO_STACKN"); return e && e[0] == '1'; }();
-    p.stackn = (x3 && !p.a_tmem && p.Npad <= 64 && !no_stack) ? 1 : 0;
     p.acc_stride = p.stackn ? 2 * p.Npad : p.Npad;
+    p.tmem_a_off = 2 * p.acc_stride;                       // the A ring follows the two accumulator buffers
     int acc_cols = 32;
     while (acc_cols < 2 * p.acc_stride) acc_cols *= 2;     // double-buffered accumulator alone
     // persistent CTAs: two per SM when TMEM (<= 256 columns each) allows, else one with all the smem
@@ -602,17 +653,17 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
         stages = ((ctas_per_sm == 2 ? 104 : 208) * 1024) / p.stage_bytes;
         if (stages > kMaxStages) stages = kMaxStages;
         const int budget = (ctas_per_sm == 2 ? 256 : 512) - 2 * p.acc_stride;
-        if (p.a_tmem) {
-            const int by_tmem = budget / (group * 2 * c.kc);
+        if (p.a_tmem || p.lo_tmem) {
+            const int by_tmem = budget / (group * (p.a_tmem ? 2 : 1) * c.kc);
             if (stages > by_tmem) stages = by_tmem;
         }
-        if (stages >= 2 || ctas_per_sm == 1) break;         // measured: 2 CTAs x 2 stages beat 1 CTA x 4 stages
+        if (stages >= (p.lo_tmem ? 3 : 2) || ctas_per_sm == 1) break;   // measured: 2 CTAs x 2 stages beat 1 CTA x 4 stages
         ctas_per_sm = 1;
     }
     if (stages < 2) stages = 2;
     p.stages = stages;
     cols = 32;
-    while (cols < 2 * p.acc_stride + (p.a_tmem ? stages * group * 2 * c.kc : 0)) cols *= 2;
+    while (cols < 2 * p.acc_stride + (p.a_tmem ? stages * group * 2 * c.kc : (p.lo_tmem ? stages * group * c.kc : 0))) cols *= 2;
     if (cols > (ctas_per_sm == 2 ? 256 : 512)) { p.a_tmem = 0; return DL4DS_E_UNSUPPORTED; }
     p.tmem_cols = cols;
     const size_t smem = (size_t)stages * p.stage_bytes + 1024;
