@@ -168,7 +168,9 @@ constexpr int kMaxStages = 16;
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  The smem
 // stage ring runs continuously across tiles and the accumulator is double-buffered in TMEM
 // (2 x Npad columns), so the epilogue of tile i overlaps the TMA / MMA work of tile i+1.
-template <bool X3>
+// AT: compile the two experimental A-operand-in-TMEM paths (p.a_tmem / p.lo_tmem) -- kept out of the default
+// instantiation, where their splitter code cost the hot kernel 84 bytes of register spills
+template <bool X3, bool AT>
 __global__ void __launch_bounds__(X3 ? kTcThreadsX3 : kTcThreads, 2)
 conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -281,13 +283,13 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                             const uint32_t ko = (uint32_t)k * 32u;
                             const uint64_t da = make_smem_desc(sa + ko, 16, sbo, p.layout);
                             const uint64_t db = make_smem_desc(sb + ko, 16, sbo, p.layout);
-                            if (X3 && p.a_tmem) {
+                            if (X3 && AT && p.a_tmem) {
                                 const uint64_t dbl = make_smem_desc(sb + b_lo_off + ko, 16, sbo, p.layout);
                                 const uint32_t ah = ta + (uint32_t)(k * 8), al = ah + (uint32_t)p.kc;
                                 umma_tf32_ts(td, al, db, idesc, accumulate);
                                 umma_tf32_ts(td, ah, dbl, idesc, 1u);
                                 umma_tf32_ts(td, ah, db, idesc, 1u);
-                            } else if (X3 && p.lo_tmem) {
+                            } else if (X3 && AT && p.lo_tmem) {
                                 // as the stacked-N scheme below, with A_lo read from TMEM (lane = pixel row, one
                                 // column per channel of the chunk) instead of shared memory
                                 const uint32_t tl = tmem_d + (uint32_t)(p.tmem_a_off + (s * p.group + j) * p.kc + k * 8);
@@ -406,7 +408,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 uint8_t* a_hi = smem_al + (size_t)s * p.stage_bytes;
                 uint8_t* a_lo = a_hi + a_lo_off;
-                if (p.lo_tmem) {
+                if (AT && p.lo_tmem) {
                     // thread = pixel row of the tile = TMEM lane: read the row's channels of every chunk of the stage
                     // through the TMA swizzle (a quarter-warp = 8 consecutive rows hits 8 distinct 16-byte slots),
                     // keep the raw tile untouched (it is the hi operand) and store lo = v - trunc(v) to TMEM.  The
@@ -443,7 +445,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                     continue;
                 }
-                if (p.a_tmem) {
+                if (AT && p.a_tmem) {
                     // thread = A row (TMEM lane): read the row's channels of the stage (<= 32 floats = 4 octets)
                     // through the TMA swizzle, then -- only now -- wait for the PREVIOUS stage's TMEM stores
                     // and publish that stage, then split and store this stage (asynchronously).  The deferred
@@ -672,20 +674,19 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     if (!tm) return DL4DS_E_CUDA;
     p.ntiles = a.N * p.tiles_per_img;
     const int grid = p.ntiles < ctas_per_sm * kNumSMs ? p.ntiles : ctas_per_sm * kNumSMs;
-    static size_t attr_set[2] = {0, 0};
-    if (x3) {
-        if (smem > attr_set[1]) {
-            cudaFuncSetAttribute(conv_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
-            attr_set[1] = 221 * 1024;
-        }
-        conv_tc_fwd_kernel<true><<<grid, kTcThreadsX3, smem, st>>>(*tm, p);
-    } else {
-        if (smem > attr_set[0]) {
-            cudaFuncSetAttribute(conv_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
-            attr_set[0] = 221 * 1024;
-        }
-        conv_tc_fwd_kernel<false><<<grid, kTcThreads, smem, st>>>(*tm, p);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv_tc_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        cudaFuncSetAttribute(conv_tc_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        cudaFuncSetAttribute(conv_tc_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        attr_done = true;
     }
+    if (x3 && (p.a_tmem || p.lo_tmem))
+        conv_tc_fwd_kernel<true, true><<<grid, kTcThreadsX3, smem, st>>>(*tm, p);
+    else if (x3)
+        conv_tc_fwd_kernel<true, false><<<grid, kTcThreadsX3, smem, st>>>(*tm, p);
+    else
+        conv_tc_fwd_kernel<false, false><<<grid, kTcThreads, smem, st>>>(*tm, p);
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     return check_launch("conv_tc_fwd_kernel");
 }

@@ -19,6 +19,7 @@ def _data(n, hw, seed=0):
 def test_supervised_step_sequence_matches_oracle(cuda, math):
     """Five optimizer steps (fwd + MAE + bwd + Keras-Adam with PiecewiseConstantDecay) through
     SupervisedTrainer.train_on_batch == the oracle's supervised_step, loss by loss."""
+    np.random.seed(0)                      # the DataGenerator permutation is drawn from numpy's global RNG
     hr = _data(24, 64)
     tr = SupervisedTrainer('resnet', 'spc', hr, hr[:8], hr[:8], scale=4, batch_size=8, epochs=1,
                            learning_rate=(1e-3, 1e-4), lr_decay_after=3, verbose=False, math=math, seed=7,
@@ -33,11 +34,10 @@ def test_supervised_step_sequence_matches_oracle(cuda, math):
         loss = tr.train_on_batch([lr], y)
         ref, _ = R.supervised_step(fwd, w, opt, [torch.from_numpy(lr)], torch.from_numpy(y))
         assert abs(loss - ref) <= 2e-4 * max(1.0, abs(ref)), (i, loss, ref)
-    new = tr.model.get_weights()
-    worst = max(float(np.abs(new[k] - w[k].numpy()).max()) for k in w)
-    # Adam's first steps move a weight by ~lr*sign(g): a gradient whose sign is decided by rounding noise
-    # shifts that weight by up to 2*lr per step, so the bound scales with lr (1e-3), not with eps
-    assert worst <= (2e-4 if math == 'fp32' else 2e-3), worst
+    from tests.util import assert_adam_weights_close
+    # (in the tensor-core mode ReLU masks flip on ~1e-6 pre-activation differences: a looser agreement bound)
+    assert_adam_weights_close(tr.model.get_weights(), {k: v.numpy() for k, v in w.items()}, lr=1e-3, steps=5,
+                              tight=5e-5 if math == 'fp32' else 5e-4, frac=5e-3 if math == 'fp32' else 5e-2)
 
 
 def test_supervised_run_and_predictor(cuda, tmp_path):
@@ -86,10 +86,10 @@ def test_cgan_step_matches_oracle(cuda):
                             mask_fake=torch.from_numpy(masks[1].reshape(B, nfeat)))
     for a, b in zip(losses, ref):
         assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (losses, ref)
+    from tests.util import assert_adam_weights_close
     for model, w in ((G, gw), (D, dw)):
-        new = model.get_weights()
-        worst = max(float(np.abs(new[k] - w[k].numpy()).max()) for k in w)
-        assert worst <= 5e-5, worst
+        assert_adam_weights_close(model.get_weights(), {k: v.numpy() for k, v in w.items()}, lr=2e-4, steps=1,
+                                  tight=2e-5)
 
 
 def test_cgan_trainer_runs(cuda, tmp_path):

@@ -59,5 +59,6 @@ def test_two_ranks_equal_one_rank(tmp_path):
             p.join(timeout=300)
             assert p.exitcode == 0
         outs.append(dict(np.load(out)))
-    worst = max(float(np.abs(outs[0][k] - outs[1][k]).max()) for k in outs[0])
-    assert worst <= 2e-5, worst
+    from tests.util import assert_adam_weights_close
+    # 2 ranks x batch b vs 1 rank x batch 2b: same gradients up to summation order (see assert_adam_weights_close)
+    assert_adam_weights_close(outs[0], outs[1], lr=1e-3, steps=3, tight=2e-5)
