@@ -142,9 +142,9 @@ __device__ __forceinline__ void transpose_units(const int4* tab, int u_begin, in
                     const uint32_t row = (uint32_t)(e[i].w + r);
                     const uint32_t off = row * 128u + (((lu ^ (row & 7u)) << 4) | lb);
                     if (X3) {
-                        const float h = tf32_rna(vv[r]);
-                        *reinterpret_cast<float*>(tile + off) = h;
-                        *reinterpret_cast<float*>(tile + lo_off + off) = vv[r] - h;
+                        // hi = the raw value (kind::tf32 reads its top 19 bits), lo = v - trunc(v): exact, 2 ALU ops
+                        *reinterpret_cast<float*>(tile + off) = vv[r];
+                        *reinterpret_cast<float*>(tile + lo_off + off) = vv[r] - tf32_trunc(vv[r]);
                     } else {
                         *reinterpret_cast<float*>(tile + off) = vv[r];
                     }
