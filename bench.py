@@ -98,7 +98,7 @@ def run_reference(args):
         'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -358,10 +358,28 @@ def run_native(args):
             'top_kernels_ms_per_step': dict(sorted(((k, round(v[0], 4)) for k, v in per_label.items()),
                                                    key=lambda kv: -kv[1])[:8]),
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _stdout_to_stderr():
+    """Keep stdout for the ONE JSON line: anything a library writes to fd 1 during the run (NCCL prints its
+    version banner there under torchrun) goes to stderr instead."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
@@ -375,6 +393,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline sample')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    _stdout_to_stderr()
     if args.impl == 'reference':
         run_reference(args)
     else:
