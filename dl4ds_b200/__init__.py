@@ -10,3 +10,4 @@ from .nets import (net_pin, net_postupsampling, recnet_pin, recnet_postupsamplin
                    residual_discriminator, unet_pin)
 from .training import CGANTrainer, SupervisedTrainer, Trainer  # noqa: F401
 from .inference import Predictor, predict  # noqa: F401
+from . import losses  # noqa: F401

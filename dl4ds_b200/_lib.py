@@ -38,6 +38,8 @@ SIGNATURES = {
     'dl4ds_channel_attention_fwd': ('i', 'pipipppppppiliiip'),
     'dl4ds_channel_attention_bwd': ('i', 'pipipippppppppppiliiip'),
     'dl4ds_pixel_loss': ('i', 'pppplifp'),
+    'dl4ds_ssim_loss_workspace_floats': ('l', 'iiiii'),
+    'dl4ds_ssim_loss': ('i', 'ppiiiiipfppipp'),
     'dl4ds_adam_step': ('i', 'pppplffffifp'),
     'dl4ds_adam_step_dev': ('i', 'pppplpffffp'),
     'dl4ds_convt_rearrange': ('i', 'ppiiiiiiiip'),

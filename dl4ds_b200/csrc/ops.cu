@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const float* __restrict
                                                          const float* __restrict__ yt,
                                                          float* __restrict__ loss_out,
                                                          float* __restrict__ dy, int64_t n, int kind,
-                                                         float scale) {
+                                                         float scale, int accumulate) {
     __shared__ float red[8];
     const float invn = 1.0f / (float)n;
     float acc = 0.0f;
@@ -387,10 +387,16 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const float* __restrict
         const float d = __ldg(yp + i) - __ldg(yt + i);
         if (kind == 0) {
             acc += fabsf(d);
-            if (dy) dy[i] = (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * (scale * invn);
+            if (dy) {
+                const float g = (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * (scale * invn);
+                dy[i] = accumulate ? dy[i] + g : g;
+            }
         } else {
             acc += d * d;
-            if (dy) dy[i] = 2.0f * d * (scale * invn);
+            if (dy) {
+                const float g = 2.0f * d * (scale * invn);
+                dy[i] = accumulate ? dy[i] + g : g;
+            }
         }
     }
     acc = warp_sum(acc);
@@ -1122,9 +1128,11 @@ int dl4ds_group_mean_bwd(const float* dout, float* dx, int dx_ld, int n_groups, 
 int dl4ds_pixel_loss(const float* y_pred, const float* y_true, float* loss_out, float* dy,
                      int64_t n, int kind, float scale, void* stream) {
     DL4DS_REQUIRE(y_pred && y_true && loss_out, DL4DS_E_BADARG, "pixel_loss: null pointer");
+    const int accumulate = (kind & DL4DS_LOSS_ACCUMULATE) ? 1 : 0;
+    kind &= ~DL4DS_LOSS_ACCUMULATE;
     DL4DS_REQUIRE(n > 0 && (kind == 0 || kind == 1), DL4DS_E_BADARG, "pixel_loss: bad n/kind");
     pixel_loss_kernel<<<grid_for(n, 256 * 4, 2 * kNumSMs), 256, 0, as_stream(stream)>>>(
-        y_pred, y_true, loss_out, dy, n, kind, scale);
+        y_pred, y_true, loss_out, dy, n, kind, scale, accumulate);
     return check_launch("pixel_loss");
 }
 

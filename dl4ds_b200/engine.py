@@ -13,6 +13,7 @@ Storage conventions
     shared layers (blocks.py:415,421-422,528-531) over their applications and lets the
     data-parallel all-reduce be a single collective on one buffer.
 """
+import ctypes
 import os
 from collections import OrderedDict
 
@@ -21,6 +22,21 @@ import torch
 
 from . import _lib
 from ._lib import ACT, MATH, W_FLIP_T, W_HWIO, W_PREPACKED, call
+
+# losses.py:5-151: every entry of LOSS_FUNCTIONS as a weighted sum of kernel terms (pixel terms first)
+LOSS_TERMS = {
+    'mae': (('mae', 1.0),), 'mse': (('mse', 1.0),),
+    'dssim': (('dssim', 1.0),),
+    'dssim_mae': (('mae', 0.2), ('dssim', 0.8)),
+    'dssim_mse': (('mse', 0.2), ('dssim', 0.8)),
+    'dssim_mae_mse': (('mae', 0.2), ('mse', 0.2), ('dssim', 0.6)),
+    'msdssim': (('msdssim', 1.0),),
+    'msdssim_mae': (('mae', 0.2), ('msdssim', 0.8)),
+    'msdssim_mae_mse': (('mae', 0.2), ('mse', 0.2), ('msdssim', 0.6)),
+}
+MSSSIM_POWER_FACTORS = (0.0448, 0.2856, 0.3001, 0.2363)      # losses.py:128
+LOSS_ACCUMULATE = 16                                          # DL4DS_LOSS_ACCUMULATE, OR-ed into `kind`
+_PF_HOST = (ctypes.c_float * len(MSSSIM_POWER_FACTORS))(*MSSSIM_POWER_FACTORS)
 
 
 def _stream():
@@ -877,14 +893,40 @@ class Ctx:
     # ---------------------------------------------------------------- losses
     def pixel_loss(self, y_pred, y_true, kind='mae', scale=1.0, loss_buf=None):
         """losses.mae / losses.mse (losses.py:5-20): loss_buf[0] += scale*mean; seeds y_pred.grad."""
+        return self.loss(y_pred, y_true, kind, scale=scale, loss_buf=loss_buf)
+
+    def loss(self, y_pred, y_true, name='mae', scale=1.0, loss_buf=None):
+        """Any of LOSS_FUNCTIONS (losses.py:5-151, looked up by utils.checkarg_loss, utils.py:139-171):
+        loss_buf[0] += scale * loss(y_true, y_pred); in training mode seeds y_pred.grad with scale * d loss / d y_pred.
+        The weighted mixes (losses.py:62-93,134-151) run their pixel terms first, then the SSIM term accumulates
+        into the same gradient buffer."""
         assert y_pred.ld == y_pred.C and y_true.ld == y_true.C
+        if name not in LOSS_TERMS:
+            raise ValueError('unknown loss %r' % (name,))
         n = y_pred.npix * y_pred.C
         if loss_buf is None:
             loss_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
         dy = y_pred.like() if self.training else None
-        self._call('dl4ds_pixel_loss', y_pred.ptr, y_true.ptr, loss_buf.data_ptr(),
-                   dy.ptr if dy is not None else None, n, {'mae': 0, 'mse': 1}[kind], float(scale),
-                   _stream())
+        dyp = dy.ptr if dy is not None else None
+        acc = 0
+        for term, weight in LOSS_TERMS[name]:
+            if term in ('mae', 'mse'):
+                self._call('dl4ds_pixel_loss', y_pred.ptr, y_true.ptr, loss_buf.data_ptr(), dyp, n,
+                           {'mae': 0, 'mse': 1}[term] | (LOSS_ACCUMULATE if acc else 0), float(scale * weight),
+                           _stream())
+            else:
+                n_scales = 1 if term == 'dssim' else len(MSSSIM_POWER_FACTORS)
+                nws = _lib.load().dl4ds_ssim_loss_workspace_floats(y_pred.N, y_pred.H, y_pred.W, y_pred.C, n_scales)
+                if nws < 0:
+                    raise _lib.Dl4dsError('ssim_loss: %s' % _lib.last_error())
+                ws = torch.empty(nws, dtype=torch.float32, device=self.device)
+                # several kernels behind one entry point: range (2), per scale maps (+2 poolings), combine,
+                # per scale backward, fixup
+                self.launches += 2 + n_scales + 2 * (n_scales - 1) + 1 + ((n_scales + 1) if dy is not None else 0) - 1
+                self._call('dl4ds_ssim_loss', y_pred.ptr, y_true.ptr, y_pred.N, y_pred.H, y_pred.W, y_pred.C,
+                           n_scales, _PF_HOST, float(scale * weight), loss_buf.data_ptr(), dyp, acc, ws.data_ptr(),
+                           _stream())
+            acc = 1
         if dy is not None:
             self._give_grad(y_pred, dy)
         return loss_buf

@@ -45,11 +45,20 @@ def _bce_np(target, p, eps=1e-7):
     return float(-np.mean(target * np.log(p + eps) + (1.0 - target) * np.log(1.0 - p + eps)))
 
 
+def _host_loss(name, y_true, y_pred):
+    """Pixel losses in numpy fp64; the SSIM family (losses.py:23-151) through the device kernels."""
+    name = getattr(name, '__name__', name)
+    if name in ('mae', 'mse'):
+        d = np.asarray(y_true, np.float64) - np.asarray(y_pred, np.float64)
+        return float(np.mean(np.abs(d))) if name == 'mae' else float(np.mean(d * d))
+    from .. import losses
+    return losses._value(name, y_true, y_pred)
+
+
 def generator_loss(disc_generated_output, gen_output, target, gen_pxloss_function, lambda_scaling_factor=100):
     """cgan.py:525-553 on host arrays (API parity; the training step computes these on the device)."""
     gan = _bce_np(1.0, disc_generated_output)
-    d = np.asarray(target, np.float64) - np.asarray(gen_output, np.float64)
-    px = float(np.mean(np.abs(d))) if gen_pxloss_function in ('mae', None) else float(np.mean(d * d))
+    px = _host_loss(gen_pxloss_function or 'mae', target, gen_output)
     return gan + lambda_scaling_factor * px, gan, px
 
 
@@ -413,8 +422,7 @@ class CGANTrainer(Trainer):
                 [lr_array], [hr_array] = res
                 input_test = [lr_array]
             y_pred = self.generator.predict(input_test, batch_size=self.batch_size)
-            d = np.asarray(hr_array, np.float64) - y_pred
-            self.test_loss = float(np.mean(np.abs(d))) if self.lossf == 'mae' else float(np.mean(d * d))
+            self.test_loss = _host_loss(self.lossf, hr_array, y_pred)
             if self.verbose:
                 print('\n%s on the test set: %s' % (self.lossf, self.test_loss))
         self.timing.runtime()

@@ -167,10 +167,27 @@ int dl4ds_channel_attention_bwd(const float* x, int x_ld, const float* dy, int d
 /* ---------------------------------------------------------------------------------------------
  * Pixel losses -- losses.py:5-20 (Keras MeanAbsoluteError / MeanSquaredError = global mean).
  * kind 0 = MAE, 1 = MSE.  loss_out[0] += scale * mean(...) (caller zeroes it); if dy != NULL,
- * dy = scale * d(mean)/d(y_pred).  n = total element count.
+ * dy = scale * d(mean)/d(y_pred) (dy += ... when DL4DS_LOSS_ACCUMULATE is OR-ed into kind: the second
+ * pixel term of the weighted mixes, losses.py:71-84,143-151).  n = total element count.
  * ------------------------------------------------------------------------------------------- */
+#define DL4DS_LOSS_ACCUMULATE 16
 int dl4ds_pixel_loss(const float* y_pred, const float* y_true, float* loss_out, float* dy,
                      int64_t n, int kind, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SSIM-family losses -- losses.dssim / losses.msdssim, losses.py:27-59,96-131 (and the weighted mixes
+ * :62-93,134-151, which add dl4ds_pixel_loss terms).  tf.image.ssim / tf.image.ssim_multiscale semantics:
+ * 11x11 gaussian (sigma 1.5), k1 0.01, k2 0.03, VALID filtering, max_val = max(both) - min(both), each tensor
+ * shifted by its own minimum when negative.  n_scales 1 = SSIM; > 1 = MS-SSIM with `power_factors` (HOST
+ * array, n_scales entries; the reference passes 4: losses.py:128), 2x2 average pooling between scales (even
+ * sizes only).  loss_out[0] += scale * mean_b((1 - ssim_b) / 2); if dy != NULL, dy (+)= scale * d/d y_pred,
+ * including the gradient through the dynamic range and the shift (arg-max / arg-min elements of y_pred).
+ * `ws`: dl4ds_ssim_loss_workspace_floats(...) floats of device scratch, 16-byte aligned (no allocation inside).
+ * ------------------------------------------------------------------------------------------- */
+int64_t dl4ds_ssim_loss_workspace_floats(int B, int H, int W, int C, int n_scales);
+int dl4ds_ssim_loss(const float* y_pred, const float* y_true, int B, int H, int W, int C, int n_scales,
+                    const float* power_factors, float scale, float* loss_out, float* dy, int accumulate,
+                    float* ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * tf.keras.optimizers.Adam step on a flat arena -- supervised.py:353, cgan.py:277-278.

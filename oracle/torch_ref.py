@@ -526,6 +526,119 @@ def mse(y_true, y_pred):
     return ((y_true - y_pred) ** 2).mean()
 
 
+# SSIM family -- losses.py:23-147.  The arithmetic is TensorFlow's `tf.image.ssim` / `tf.image.ssim_multiscale`
+# (tensorflow/python/ops/image_ops_impl.py, TF 2.6-2.15: `_fspecial_gauss`, `_ssim_helper`, `_ssim_per_channel`,
+# `ssim`, `ssim_multiscale`; third-party, not under /root/reference, unpinned -- restated from the published source).
+_MSSSIM_POWER_FACTORS = (0.0448, 0.2856, 0.3001, 0.2363)        # losses.py:128 (4 scales, not TF's 5)
+
+
+def _fspecial_gauss(size=11, sigma=1.5, dtype=torch.float32):
+    """softmax over the flattened 2-D grid of -(x^2+y^2)/(2 sigma^2): `_fspecial_gauss`."""
+    coords = torch.arange(size, dtype=dtype) - (size - 1) / 2.0
+    g = coords ** 2 * (-0.5 / sigma ** 2)
+    g = (g[None, :] + g[:, None]).reshape(1, -1)
+    return torch.softmax(g, dim=-1).reshape(size, size)
+
+
+def _ssim_per_channel(img1, img2, max_val, filter_size=11, filter_sigma=1.5, k1=0.01, k2=0.03):
+    """`_ssim_per_channel` + `_ssim_helper` on NHWC tensors: depthwise VALID gaussian filtering of x, y, x*y and
+    x^2+y^2; returns (mean over H,W of luminance*cs, mean over H,W of cs), each (B, C)."""
+    c = img1.shape[-1]
+    kern = _fspecial_gauss(filter_size, filter_sigma, img1.dtype).reshape(1, 1, filter_size, filter_size)
+    kern = kern.repeat(c, 1, 1, 1)
+    red = lambda t: F.conv2d(_nchw(t), kern, groups=c)
+    c1 = (k1 * max_val) ** 2
+    c2 = (k2 * max_val) ** 2
+    mean0, mean1 = red(img1), red(img2)
+    num0 = mean0 * mean1 * 2.0
+    den0 = mean0 ** 2 + mean1 ** 2
+    luminance = (num0 + c1) / (den0 + c1)
+    num1 = red(img1 * img2) * 2.0
+    den1 = red(img1 ** 2 + img2 ** 2)
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    return (luminance * cs).mean(dim=(2, 3)), cs.mean(dim=(2, 3))
+
+
+def tf_image_ssim(img1, img2, max_val, **kw):
+    """tf.image.ssim: mean over channels of the per-channel SSIM -> (B,)."""
+    return _ssim_per_channel(img1, img2, max_val, **kw)[0].mean(dim=-1)
+
+
+def tf_image_ssim_multiscale(img1, img2, max_val, power_factors=_MSSSIM_POWER_FACTORS, **kw):
+    """tf.image.ssim_multiscale: per scale relu(cs) (relu(ssim) at the last), 2x2 average pooling between scales
+    (SYMMETRIC padding of odd sizes), weighted geometric mean over scales, mean over channels -> (B,)."""
+    imgs = [img1, img2]
+    mcs = []
+    for k in range(len(power_factors)):
+        if k > 0:
+            nxt = []
+            for t in imgs:
+                t = _nchw(t)
+                ph, pw = t.shape[2] % 2, t.shape[3] % 2
+                if ph or pw:
+                    t = F.pad(t, (0, pw, 0, ph), mode='replicate')   # SYMMETRIC pad by one == edge replicate
+                nxt.append(_nhwc(F.avg_pool2d(t, 2, 2)))
+            imgs = nxt
+        ssim_pc, cs = _ssim_per_channel(imgs[0], imgs[1], max_val, **kw)
+        mcs.append(torch.relu(cs))
+    mcs.pop()
+    stack = torch.stack(mcs + [torch.relu(ssim_pc)], dim=-1)
+    pf = torch.tensor(power_factors, dtype=img1.dtype)
+    return torch.prod(stack ** pf, dim=-1).mean(dim=-1)
+
+
+def _positive_pair(y_true, y_pred):
+    """losses.py:44-54 / 118-128: dynamic range over both tensors, each shifted by its own minimum if negative."""
+    maxv = torch.maximum(y_true.max(), y_pred.max())
+    minv = torch.minimum(y_true.min(), y_pred.min())
+    drange = maxv - minv
+    yt = y_true - y_true.min() if y_true.min() < 0 else y_true
+    yp = y_pred - y_pred.min() if y_pred.min() < 0 else y_pred
+    return yt, yp, drange
+
+
+def dssim(y_true, y_pred):
+    """losses.dssim -- losses.py:27-59."""
+    yt, yp, drange = _positive_pair(y_true, y_pred)
+    return ((1.0 - tf_image_ssim(yt, yp, drange)) / 2.0).mean()
+
+
+def msdssim(y_true, y_pred):
+    """losses.msdssim -- losses.py:96-131."""
+    yt, yp, drange = _positive_pair(y_true, y_pred)
+    return ((1.0 - tf_image_ssim_multiscale(yt, yp, drange)) / 2.0).mean()
+
+
+def dssim_mae(y_true, y_pred):
+    """losses.py:62-68."""
+    return 0.8 * dssim(y_true, y_pred) + 0.2 * mae(y_true, y_pred)
+
+
+def dssim_mae_mse(y_true, y_pred):
+    """losses.py:71-84."""
+    return 0.6 * dssim(y_true, y_pred) + 0.2 * mae(y_true, y_pred) + 0.2 * mse(y_true, y_pred)
+
+
+def dssim_mse(y_true, y_pred):
+    """losses.py:87-93."""
+    return 0.8 * dssim(y_true, y_pred) + 0.2 * mse(y_true, y_pred)
+
+
+def msdssim_mae(y_true, y_pred):
+    """losses.py:134-140."""
+    return 0.8 * msdssim(y_true, y_pred) + 0.2 * mae(y_true, y_pred)
+
+
+def msdssim_mae_mse(y_true, y_pred):
+    """losses.py:143-151."""
+    return 0.6 * msdssim(y_true, y_pred) + 0.2 * mae(y_true, y_pred) + 0.2 * mse(y_true, y_pred)
+
+
+LOSSES = {'mae': mae, 'mse': mse, 'dssim': dssim, 'dssim_mae': dssim_mae, 'dssim_mse': dssim_mse,
+          'dssim_mae_mse': dssim_mae_mse, 'msdssim': msdssim, 'msdssim_mae': msdssim_mae,
+          'msdssim_mae_mse': msdssim_mae_mse}
+
+
 def bce(y_true, p):
     """tf.keras.losses.BinaryCrossentropy(from_logits=False) -- cgan.py:546,567.
     Keras backend: p = clip(p, eps, 1-eps); -mean(y log(p+eps) + (1-y) log(1-p+eps)), eps=1e-7."""
@@ -578,7 +691,7 @@ def supervised_step(forward_fn, weights, opt, inputs, target, loss='mae'):
         w.requires_grad_(True)
         w.grad = None
     y = forward_fn(Params(weights), inputs)
-    lossv = {'mae': mae, 'mse': mse}[loss](target, y)
+    lossv = LOSSES[loss](target, y)
     lossv.backward()
     grads = {n: w.grad.detach().clone() for n, w in weights.items()}
     for w in weights.values():
@@ -600,7 +713,7 @@ def cgan_step(gen_fn, disc_fn, gw, dw, gopt, dopt, lr_array, hr_array, static_ar
     d_real = disc_fn(Params(dw), [lr_array, hr_array], mask_real)
     d_fake = disc_fn(Params(dw), [lr_array, gen], mask_fake)
     gan = bce(torch.ones_like(d_fake), d_fake)
-    px = {'mae': mae, 'mse': mse}[loss](hr_array, gen)
+    px = LOSSES[loss](hr_array, gen)
     g_total = gan + lam * px
     d_loss = bce(torch.ones_like(d_real), d_real) + bce(torch.zeros_like(d_fake), d_fake)
     g_grads = torch.autograd.grad(g_total, list(gw.values()), retain_graph=True)
