@@ -40,6 +40,11 @@ SIGNATURES = {
     'dl4ds_pixel_loss': ('i', 'pppplifp'),
     'dl4ds_ssim_loss_workspace_floats': ('l', 'iiiii'),
     'dl4ds_ssim_loss': ('i', 'ppiiiiipfppipp'),
+    'dl4ds_batchnorm_stats': ('i', 'pilippppfpp'),
+    'dl4ds_norm_apply': ('i', 'pippppfpiliip'),
+    'dl4ds_batchnorm_bwd': ('i', 'pipipipppfpipppliip'),
+    'dl4ds_layernorm_fwd': ('i', 'pippfpiliip'),
+    'dl4ds_layernorm_bwd': ('i', 'pipipipfpippliip'),
     'dl4ds_adam_step': ('i', 'pppplffffifp'),
     'dl4ds_adam_step_dev': ('i', 'pppplpffffp'),
     'dl4ds_convt_rearrange': ('i', 'ppiiiiiiiip'),

@@ -617,6 +617,65 @@ class Ctx:
         self._record(bwd)
         return out
 
+    def norm(self, x, name, kind, act=None, eps=1e-3):
+        """BatchNormalization() / LayerNormalization() followed by the activation, fused -- blocks.py:63-71 and
+        their uses :92-101,216-224,263-272.  Keras defaults (axis -1, epsilon 1e-3, BN momentum 0.99).  BN in
+        training mode normalises with the batch statistics and updates ``moving_mean`` / ``moving_variance`` (they
+        live in the parameter arena with a gradient that stays zero, so Adam leaves them alone); in inference mode
+        it uses the moving ones."""
+        if kind not in ('bn', 'ln'):
+            raise ValueError('Normalization not supported, got %s' % (kind,))           # blocks.py:64-65
+        code, C, n_pix = ACT[act], x.C, x.npix
+        gamma, beta = self._p(name + '/gamma'), self._p(name + '/beta')
+        out = x.like()
+        if kind == 'ln':
+            self._call('dl4ds_layernorm_fwd', x.ptr, x.ld, gamma.data_ptr(), beta.data_ptr(), float(eps), out.ptr,
+                       out.ld, n_pix, C, code, _stream())
+            stats = None
+        else:
+            mm, mv = self._p(name + '/moving_mean'), self._p(name + '/moving_variance')
+            if self.training:
+                stats = torch.empty(4 * C, dtype=torch.float32, device=self.device)   # mean | var | scratch (2C)
+                mean_p, var_p = stats.data_ptr(), stats.data_ptr() + 4 * C
+                self._call('dl4ds_batchnorm_stats', x.ptr, x.ld, n_pix, C, mean_p, var_p, mm.data_ptr(),
+                           mv.data_ptr(), 0.99, stats.data_ptr() + 8 * C, _stream())
+                self.launches += 3
+            else:
+                stats = None
+                mean_p, var_p = mm.data_ptr(), mv.data_ptr()
+            self._call('dl4ds_norm_apply', x.ptr, x.ld, mean_p, var_p, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                       out.ptr, out.ld, n_pix, C, code, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            pg = self.param_grads
+            dg = self._g(name + '/gamma').data_ptr() if pg else None
+            db = self._g(name + '/beta').data_ptr() if pg else None
+            if kind == 'ln':
+                def wr(dst):
+                    self._call('dl4ds_layernorm_bwd', dy.ptr, dy.ld, x.ptr, x.ld, out.ptr, out.ld, gamma.data_ptr(),
+                               float(eps), dst.ptr if dst is not None else None, dst.ld if dst is not None else 0,
+                               dg, db, n_pix, C, code, _stream())
+                if x.requires_grad:
+                    self._acc_via_tmp(x, wr)
+                elif pg:
+                    wr(None)
+            else:
+                def wr(dst):
+                    self._call('dl4ds_batchnorm_bwd', dy.ptr, dy.ld, x.ptr, x.ld, out.ptr, out.ld, stats.data_ptr(),
+                               stats.data_ptr() + 4 * C, gamma.data_ptr(), float(eps), dst.ptr, dst.ld, dg, db,
+                               stats.data_ptr() + 8 * C, n_pix, C, code, _stream())
+                    self.launches += 2
+                if x.requires_grad:
+                    self._acc_via_tmp(x, wr)
+                elif pg:
+                    wr(x.like())
+            out.grad = None
+        self._record(bwd)
+        return out
+
     def channel_attention(self, x, name, r=4, groups=None):
         """ChannelAttention2D -- blocks.py:537-593.  ``groups`` = (n_groups, pix_per_group, inner)
         overrides the default per-image pooling (used for the 5-D (T,H) pooling quirk)."""

@@ -28,8 +28,8 @@ def _check_common(activation, output_activation, normalization, dropout_rate, ba
     for a in (activation, output_activation):
         if a not in B.SUPPORTED_ACTIVATIONS:
             raise NotImplementedError('activation %r is outside the B200 hot path' % (a,))
-    if normalization is not None:
-        raise NotImplementedError('normalization=%r is outside the B200 hot path' % (normalization,))
+    if normalization not in (None, 'bn', 'ln'):
+        raise ValueError('Normalization not supported, got %s' % (normalization,))      # blocks.py:64-65
     if dropout_rate:
         raise NotImplementedError('dropout_rate>0 is outside the B200 hot path (model default is 0)')
     if backbone_block is not None and backbone_block not in BACKBONES:
@@ -108,7 +108,11 @@ class Model:
         rng = np.random.default_rng(seed)
         w = OrderedDict()
         for name, shape in self.spec.items():
-            if name.endswith('/bias'):
+            if name.endswith(('/gamma', '/moving_variance')):        # BatchNormalization / LayerNormalization: ones
+                w[name] = np.ones(shape, np.float32)
+            elif name.endswith(('/beta', '/moving_mean')):
+                w[name] = np.zeros(shape, np.float32)
+            elif name.endswith('/bias'):
                 a = np.zeros(shape, np.float32)
                 if 'convlstm' in name:
                     f = shape[0] // 4
@@ -290,19 +294,21 @@ class Model:
 # ---------------------------------------------------------------------------------------------
 # shared sections
 # ---------------------------------------------------------------------------------------------
-def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activation):
+def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization=None):
     """Stem + N blocks + last conv + long skip -- sp_postups.py:132-168, sp_preups.py:116-151."""
     init_n_filters = n_filters
     x = b = c.conv(x_in, 'stem', n_filters)
     for i in range(n_blocks):
         n_filters = init_n_filters * (i + 1)
         if backbone_block == 'convnet':
-            b = B.conv_block(c, 'ConvBlock%d' % (i + 1), b, n_filters, activation, attention)
+            b = B.conv_block(c, 'ConvBlock%d' % (i + 1), b, n_filters, activation, attention,
+                             normalization=normalization)
         elif backbone_block == 'resnet':
             b = B.residual_block(c, 'ResidualBlock%d' % (i + 1), b, n_filters, activation, attention,
-                                 use_1x1conv=(i != 0))
+                                 use_1x1conv=(i != 0), normalization=normalization)
         elif backbone_block == 'densenet':
-            b = B.dense_block(c, 'DenseBlock%d' % (i + 1), b, n_filters, activation, attention)
+            b = B.dense_block(c, 'DenseBlock%d' % (i + 1), b, n_filters, activation, attention,
+                              normalization=normalization)
             b = B.transition_block(c, 'Transition%d' % (i + 1), b, b.C // 2)
     b = c.conv(b, 'backbone_last', n_filters, act=activation)
     if backbone_block == 'convnet':
@@ -317,22 +323,23 @@ def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activatio
 
 
 def _tail(c, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation, output_activation,
-          localcon_layer, transition_done=False):
+          localcon_layer, transition_done=False, normalization=None):
     """LCB, HR aux branch, TransitionLast, ConvBlock(att), ConvBlock(out)
     -- sp_postups.py:184-212, sp_preups.py:155-183,291-309.  ``transition_done``: TransitionLast was already
     applied by the caller (composed with the last sub-pixel stage)."""
+    nz = normalization
     if transition_done:
-        x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True)
-        return B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation)
+        x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz)
+        return B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz)
     if localcon_layer:
         lws = B.localized_conv_block(c, 'LocalizedConvBlock', x, 2)
         x = c.concat([x, lws])
     if s_in is not None:
-        s = B.conv_block(c, 'ConvBlock_aux', s_in, n_filters_aux, activation=activation)
+        s = B.conv_block(c, 'ConvBlock_aux', s_in, n_filters_aux, activation=activation, normalization=nz)
         x = c.concat([x, s])
     x = B.transition_block(c, 'TransitionLast', x, init_n_filters)      # default relu
-    x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True)
-    x = B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation)
+    x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz)
+    x = B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz)
     return x
 
 
@@ -355,7 +362,7 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
     aux = n_aux_channels > 0
 
     def fn(c, inputs):
-        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation)
+        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation, normalization)
         fused = False
         if upsampling == 'spc':
             if fuse_spc_transition and not aux and not localcon_layer:
@@ -371,7 +378,7 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
             x = B.transition_block(c, 'TransitionDC', x, n_filters, activation)
             x = B.deconv_block(c, 'Deconvolution', x, scale, nf, activation)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
-                     output_activation, localcon_layer, transition_done=fused)
+                     output_activation, localcon_layer, transition_done=fused, normalization=normalization)
 
     ups_total = scale
     if upsampling == 'dc' and scale == 4:
@@ -390,9 +397,9 @@ def net_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out=
     aux = n_aux_channels > 0
 
     def fn(c, inputs):
-        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation)
+        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation, normalization)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
-                     output_activation, localcon_layer)
+                     output_activation, localcon_layer, normalization=normalization)
 
     shapes = [(hr_size[0], hr_size[1], n_channels)]
     if aux:
@@ -427,7 +434,7 @@ def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out
         nf = n_filters
         skips, flist = [], []
         for i in range(n_blocks):       # EncoderBlock: ConvBlock then 2x2 max-pool (blocks.py:602-618)
-            y = B.conv_block(c, 'EncoderBlock%d' % (i + 1), x, nf, activation, attention)
+            y = B.conv_block(c, 'EncoderBlock%d' % (i + 1), x, nf, activation, attention, normalization=normalization)
             skips.append(y)
             x = c.maxpool2(y)
             flist.append(nf)
@@ -442,9 +449,10 @@ def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out
             else:
                 x = B.deconv_block(c, 'Deconvolution%d' % (j + 1), x, 2, nf, activation)
             x = B.pad_concat(c, x, skip)
-            x = B.conv_block(c, 'DecoderConvBlock%d' % (j + 1), x, nf, activation, attention)
+            x = B.conv_block(c, 'DecoderConvBlock%d' % (j + 1), x, nf, activation, attention,
+                             normalization=normalization)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
-                     output_activation, localcon_layer)
+                     output_activation, localcon_layer, normalization=normalization)
 
     shapes = [(hr_size[0], hr_size[1], n_channels)]
     if aux:
@@ -460,6 +468,8 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
     """recnet_postupsampling -- spt_postups.py:12-163.  Inputs (B,T,h,w,C) [+ (B,H,W,n_aux)];
     output (B,T,H,W,n_channels_out).  Internally frames are time-major (T*B,H,W,C)."""
     _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    if normalization is not None:
+        raise NotImplementedError('normalization in the recurrent (ConvLSTM) networks is not built')
     if backbone_block == 'unet':
         raise ValueError('unet backbone is not compatible with post-upsampling')
     if upsampling not in POSTUPSAMPLING_METHODS + ('pin',):
@@ -537,19 +547,23 @@ def residual_discriminator(n_channels, upsampling, is_spatiotemporal, scale, lr_
     features is applied with a caller-supplied keep mask as third input (training) or skipped."""
     if is_spatiotemporal:
         raise NotImplementedError('spatio-temporal discriminator is outside the B200 hot path')
-    if normalization is not None:
-        raise NotImplementedError('normalization=%r is outside the B200 hot path' % (normalization,))
+    if normalization not in (None, 'bn', 'ln'):
+        raise ValueError('Normalization not supported, got %s' % (normalization,))
+    if normalization is not None and is_spatiotemporal:
+        raise NotImplementedError('normalization in the spatio-temporal discriminator is not built')
 
     def fn(c, inputs):
         x_in, x_ref = inputs[0], inputs[1]
         mask = inputs[2] if len(inputs) > 2 else None
         x1 = b = c.conv(x_in, 'branch1_stem', n_filters)
         for i in range(n_res_blocks):
-            b = B.residual_block(c, 'ResidualBlock%d_branch1' % (i + 1), b, n_filters, 'relu', attention)
+            b = B.residual_block(c, 'ResidualBlock%d_branch1' % (i + 1), b, n_filters, 'relu', attention,
+                                 normalization=normalization)
         x1 = c.conv(b, 'branch1_last', n_filters, res=x1)
         x2 = cc = c.conv(x_ref, 'branch2_stem', n_filters)
         for i in range(n_res_blocks):
-            cc = B.residual_block(c, 'ResidualBlock%d_branch2' % (i + 1), cc, n_filters, 'relu', attention)
+            cc = B.residual_block(c, 'ResidualBlock%d_branch2' % (i + 1), cc, n_filters, 'relu', attention,
+                                  normalization=normalization)
         if upsampling in POSTUPSAMPLING_METHODS:
             if scale == 5:
                 cc = c.conv(cc, 'branch2_down1', n_filters, stride=2, padding='valid')
@@ -563,7 +577,7 @@ def residual_discriminator(n_channels, upsampling, is_spatiotemporal, scale, lr_
         else:
             x2 = c.conv(cc, 'branch2_last', n_filters, res=x2)
         x = c.concat([x1, x2])
-        x = B.residual_block(c, 'ResidualBlock_merged', x, x.C, 'relu', attention)
+        x = B.residual_block(c, 'ResidualBlock_merged', x, x.C, 'relu', attention, normalization=normalization)
         x = c.group_mean(x)
         if mask is not None:
             x = c.mul_mask(x, mask)

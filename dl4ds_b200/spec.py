@@ -98,6 +98,16 @@ class SpecCtx:
     def act(self, x, act):
         return x
 
+    def norm(self, x, name, kind, act=None, eps=1e-3):
+        if kind not in ('bn', 'ln'):
+            raise ValueError('Normalization not supported, got %s' % (kind,))
+        self._reg(name + '/gamma', (x.C,))
+        self._reg(name + '/beta', (x.C,))
+        if kind == 'bn':
+            self._reg(name + '/moving_mean', (x.C,))
+            self._reg(name + '/moving_variance', (x.C,))
+        return SVar(*x.shape)
+
     def channel_attention(self, x, name, r=4, groups=None):
         cr = int(x.C / r)
         self._reg(name + '/conv1/kernel', (1, 1, x.C, cr))

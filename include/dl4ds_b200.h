@@ -190,6 +190,36 @@ int dl4ds_ssim_loss(const float* y_pred, const float* y_true, int B, int H, int 
                     float* ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Normalisation layers of the conv blocks (`normalization='bn' | 'ln'`) with the following activation fused --
+ * blocks.py:63-71 (construction), :94-101 ConvBlock, :216-224 ResidualBlock, :263-272 DenseBlock, :298-305
+ * TransitionBlock, :160-164,178 ConvNextBlock.  Keras defaults: axis -1, epsilon 1e-3 (1e-6 in ConvNext's LN),
+ * BatchNormalization momentum 0.99.  NHWC tensors with a channel pitch (`*_ld`), C <= 256.
+ *
+ * dl4ds_batchnorm_stats: training-mode statistics over all n_pix pixels: mean[c], var[c] (biased, what the layer
+ *   normalises with) and, if moving_mean/moving_var != NULL, the moving averages updated in place
+ *   (moving = moving * momentum + batch * (1 - momentum); the moving variance takes the unbiased batch variance,
+ *   as Keras' fused path does).  ws: 2*C floats of device scratch.
+ * dl4ds_norm_apply: y = act(gamma * (x - mean) / sqrt(var + eps) + beta) -- batch statistics in training,
+ *   the moving ones in inference (Predictor / validation).
+ * dl4ds_batchnorm_bwd: dz = dy * act'(y); dgamma += sum dz*xhat; dbeta += sum dz (NULL = not wanted);
+ *   dx = gamma/sqrt(var+eps) * (dz - mean(dz) - xhat * mean(dz*xhat)).  ws: 2*C floats.
+ * dl4ds_layernorm_fwd / _bwd: the same per pixel over the channel axis (dx may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_batchnorm_stats(const float* x, int x_ld, int64_t n_pix, int C, float* mean, float* var,
+                          float* moving_mean, float* moving_var, float momentum, float* ws, void* stream);
+int dl4ds_norm_apply(const float* x, int x_ld, const float* mean, const float* var, const float* gamma,
+                     const float* beta, float eps, float* y, int y_ld, int64_t n_pix, int C, int act,
+                     void* stream);
+int dl4ds_batchnorm_bwd(const float* dy, int dy_ld, const float* x, int x_ld, const float* y, int y_ld,
+                        const float* mean, const float* var, const float* gamma, float eps, float* dx, int dx_ld,
+                        float* dgamma, float* dbeta, float* ws, int64_t n_pix, int C, int act, void* stream);
+int dl4ds_layernorm_fwd(const float* x, int x_ld, const float* gamma, const float* beta, float eps, float* y,
+                        int y_ld, int64_t n_pix, int C, int act, void* stream);
+int dl4ds_layernorm_bwd(const float* dy, int dy_ld, const float* x, int x_ld, const float* y, int y_ld,
+                        const float* gamma, float eps, float* dx, int dx_ld, float* dgamma, float* dbeta,
+                        int64_t n_pix, int C, int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * tf.keras.optimizers.Adam step on a flat arena -- supervised.py:353, cgan.py:277-278.
  *   g = grad * grad_scale (grad_scale = 1/world_size folds Horovod's allreduce-average,
  *   supervised.py:365);  m,v updated;  theta -= lr_t * m / (sqrt(v) + eps)

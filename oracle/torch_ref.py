@@ -31,10 +31,11 @@ class Params:
     """Name -> tensor store.  ``Params()`` = spec mode (records shapes, hands out zeros);
     ``Params(weights)`` = run mode (hands out the given tensors, checks shapes)."""
 
-    def __init__(self, weights=None, dtype=torch.float32):
+    def __init__(self, weights=None, dtype=torch.float32, training=True):
         self.spec = OrderedDict()
         self.weights = weights
         self.dtype = dtype
+        self.training = training        # Keras `training` flag: BatchNormalization batch vs moving statistics
 
     def get(self, name, shape):
         shape = tuple(int(s) for s in shape)
@@ -168,19 +169,64 @@ def channel_attention_5d(p, name, x5, nf, r=4):
     return x5 * y.unsqueeze(1)              # broadcast over T and H
 
 
-def conv_block(p, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3):
-    """ConvBlock.call -- blocks.py:87-103 (normalization=None, dropout_rate=0)."""
-    y = act(_conv(p, name + '/conv1', x, filters, k=ks1), activation)
-    y = act(_conv(p, name + '/conv2', y, filters, k=ks2), activation)
+def normalize(p, name, x, kind, eps=1e-3):
+    """tf.keras.layers.BatchNormalization() / LayerNormalization() on NCHW ``x`` -- blocks.py:63-71.
+    Keras defaults: axis=-1 (channels), epsilon=1e-3, BN momentum 0.99, gamma ones / beta zeros.
+    BN, training: normalise with the batch mean / biased variance over (N,H,W); moving statistics updated in
+    place (moving = moving*0.99 + batch*0.01, the moving variance with the unbiased batch variance, as the fused
+    Keras path does).  BN, inference: moving statistics.  LN: per pixel over the channel axis."""
+    c = x.shape[1]
+    gamma = p.get(name + '/gamma', (c,)).view(1, c, 1, 1)
+    beta = p.get(name + '/beta', (c,)).view(1, c, 1, 1)
+    if kind == 'ln':
+        mu = x.mean(dim=1, keepdim=True)
+        var = ((x - mu) ** 2).mean(dim=1, keepdim=True)
+        return (x - mu) / torch.sqrt(var + eps) * gamma + beta
+    if kind != 'bn':
+        raise ValueError('Normalization not supported, got %s' % kind)        # blocks.py:64-65
+    mm = p.get(name + '/moving_mean', (c,))
+    mv = p.get(name + '/moving_variance', (c,))
+    if p.training:
+        mu = x.mean(dim=(0, 2, 3))
+        var = ((x - mu.view(1, c, 1, 1)) ** 2).mean(dim=(0, 2, 3))
+        if p.weights is not None:
+            m = x.numel() // c
+            with torch.no_grad():
+                mm.data.mul_(0.99).add_(0.01 * mu.detach())
+                mv.data.mul_(0.99).add_(0.01 * var.detach() * (m / max(m - 1, 1)))
+    else:
+        mu, var = mm, mv
+    return (x - mu.view(1, c, 1, 1)) / torch.sqrt(var.view(1, c, 1, 1) + eps) * gamma + beta
+
+
+def conv_block(p, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3, normalization=None):
+    """ConvBlock.call -- blocks.py:87-103 (dropout_rate=0).  With a normalisation the convolutions carry no
+    bias (blocks.py:37,44,52,58)."""
+    nb = normalization is None
+    y = _conv(p, name + '/conv1', x, filters, k=ks1, bias=nb)
+    if not nb:
+        y = normalize(p, name + '/norm1', y, normalization)
+    y = act(y, activation)
+    y = _conv(p, name + '/conv2', y, filters, k=ks2, bias=nb)
+    if not nb:
+        y = normalize(p, name + '/norm2', y, normalization)
+    y = act(y, activation)
     if attention:
         y = channel_attention(p, name + '/att', y, filters)
     return y
 
 
-def residual_block(p, name, x, filters, activation='relu', attention=False, use_1x1conv=False):
+def residual_block(p, name, x, filters, activation='relu', attention=False, use_1x1conv=False,
+                   normalization=None):
     """ResidualBlock.call -- blocks.py:210-230."""
-    y = act(_conv(p, name + '/conv1', x, filters), activation)
-    y = _conv(p, name + '/conv2', y, filters)
+    nb = normalization is None
+    y = _conv(p, name + '/conv1', x, filters, bias=nb)
+    if not nb:
+        y = normalize(p, name + '/norm1', y, normalization)
+    y = act(y, activation)
+    y = _conv(p, name + '/conv2', y, filters, bias=nb)
+    if not nb:
+        y = normalize(p, name + '/norm2', y, normalization)
     if attention:
         y = channel_attention(p, name + '/att', y, filters)
     if use_1x1conv:
@@ -188,10 +234,17 @@ def residual_block(p, name, x, filters, activation='relu', attention=False, use_
     return act(y + x, activation)
 
 
-def dense_block(p, name, x, filters, activation='relu', attention=False):
+def dense_block(p, name, x, filters, activation='relu', attention=False, normalization=None):
     """DenseBlock.call -- blocks.py:262-277.  The pre-activation of X is discarded (:263-267,
-    App. B #5): Y = conv3x3(act(conv1x1(X))); out = concat([Y, X])."""
-    y = act(_conv(p, name + '/conv1', x, 4 * filters, k=1), activation)
+    App. B #5): Y = conv3x3(act([norm2](conv1x1(X)))); out = concat([Y, X]).  DenseBlock re-creates conv1 / conv2
+    WITH bias (:249-259); norm1 is applied to X and its result dropped, so its gamma / beta exist without a
+    gradient and, for BN, its moving statistics still follow X."""
+    if normalization is not None:
+        normalize(p, name + '/norm1', x, normalization)
+    y = _conv(p, name + '/conv1', x, 4 * filters, k=1)
+    if normalization is not None:
+        y = normalize(p, name + '/norm2', y, normalization)
+    y = act(y, activation)
     y = _conv(p, name + '/conv2', y, filters, k=3)
     if attention:
         y = channel_attention(p, name + '/att', y, filters)
@@ -304,22 +357,24 @@ def _nhwc(x):
 
 
 def _tail(p, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation,
-          output_activation, localcon_layer, aux_name='ConvBlock_aux'):
+          output_activation, localcon_layer, aux_name='ConvBlock_aux', normalization=None):
     """Shared output module: LCB, aux branch, TransitionLast, two ConvBlocks
     -- sp_postups.py:184-212, sp_preups.py:155-183,291-309."""
     if localcon_layer:
         lws = localized_conv_block(p, 'LocalizedConvBlock', x, 2)
         x = torch.cat([x, lws], dim=1)
     if s_in is not None:
-        s = conv_block(p, aux_name, s_in, n_filters_aux, activation=activation)
+        s = conv_block(p, aux_name, s_in, n_filters_aux, activation=activation, normalization=normalization)
         x = torch.cat([x, s], dim=1)
     x = transition_block(p, 'TransitionLast', x, init_n_filters)   # default relu (App. B #9)
-    x = conv_block(p, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True)
-    x = conv_block(p, 'ConvBlock_out', x, n_channels_out, activation=output_activation)
+    x = conv_block(p, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True,
+                   normalization=normalization)
+    x = conv_block(p, 'ConvBlock_out', x, n_channels_out, activation=output_activation,
+                   normalization=normalization)
     return x
 
 
-def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation):
+def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization=None):
     """Backbone section shared by net_postupsampling / net_pin -- sp_postups.py:132-168,
     sp_preups.py:116-151."""
     init_n_filters = n_filters
@@ -327,12 +382,14 @@ def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activatio
     for i in range(n_blocks):
         n_filters = init_n_filters * (i + 1)
         if backbone_block == 'convnet':
-            b = conv_block(p, 'ConvBlock' + str(i + 1), b, n_filters, activation, attention)
+            b = conv_block(p, 'ConvBlock' + str(i + 1), b, n_filters, activation, attention,
+                           normalization=normalization)
         elif backbone_block == 'resnet':
             b = residual_block(p, 'ResidualBlock' + str(i + 1), b, n_filters, activation,
-                               attention, use_1x1conv=(i != 0))
+                               attention, use_1x1conv=(i != 0), normalization=normalization)
         elif backbone_block == 'densenet':
-            b = dense_block(p, 'DenseBlock' + str(i + 1), b, n_filters, activation, attention)
+            b = dense_block(p, 'DenseBlock' + str(i + 1), b, n_filters, activation, attention,
+                            normalization=normalization)
             b = transition_block(p, 'Transition' + str(i + 1), b, b.shape[1] // 2)
         else:
             raise NotImplementedError(backbone_block)
@@ -350,12 +407,12 @@ def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activatio
 
 def net_postupsampling(p, inputs, backbone_block, upsampling, scale, n_channels_out=1,
                        n_filters=8, n_blocks=6, attention=False, activation='relu',
-                       output_activation=None, localcon_layer=False):
+                       output_activation=None, localcon_layer=False, normalization=None):
     """net_postupsampling -- sp_postups.py:14-217.  inputs: [x_lr NHWC] or [x_lr, s_hr]."""
     x_in = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
     init_n_filters = n_filters
-    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation)
+    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization)
     if upsampling == 'spc':
         x = subpixel_block(p, 'SubpixelConvolution', x, scale, n_filters)
     elif upsampling == 'rc':
@@ -364,19 +421,20 @@ def net_postupsampling(p, inputs, backbone_block, upsampling, scale, n_channels_
         x = transition_block(p, 'TransitionDC', x, init_n_filters, activation)
         x = deconv_block(p, 'Deconvolution', x, scale, n_filters, activation)
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
-              output_activation, localcon_layer)
+              output_activation, localcon_layer, normalization=normalization)
     return _nhwc(x)
 
 
 def net_pin(p, inputs, backbone_block, n_channels_out=1, n_filters=8, n_blocks=6,
-            attention=False, activation='relu', output_activation=None, localcon_layer=False):
+            attention=False, activation='relu', output_activation=None, localcon_layer=False,
+            normalization=None):
     """net_pin -- sp_preups.py:13-189."""
     x_in = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
     init_n_filters = n_filters
-    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation)
+    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization)
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
-              output_activation, localcon_layer)
+              output_activation, localcon_layer, normalization=normalization)
     return _nhwc(x)
 
 
@@ -389,15 +447,16 @@ def check_nblocks(shape, power):
 
 def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu',
              attention=False, decoder_upsampling='rc', output_activation=None, width_cap=256,
-             localcon_layer=False):
-    """unet_pin -- sp_preups.py:192-315."""
+             localcon_layer=False, normalization=None):
+    """unet_pin -- sp_preups.py:192-315 (the bottleneck block is never normalised, :266-268)."""
     x = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
     n_blocks = check_nblocks((x.shape[2], x.shape[3]), n_blocks)
     init_n_filters = n_filters
     skips, flist = [], []
     for i in range(n_blocks):
-        y = conv_block(p, 'EncoderBlock%d' % (i + 1), x, n_filters, activation, attention)
+        y = conv_block(p, 'EncoderBlock%d' % (i + 1), x, n_filters, activation, attention,
+                       normalization=normalization)
         skips.append(y)
         x = maxpool2(y)
         flist.append(n_filters)
@@ -413,9 +472,10 @@ def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu'
         elif decoder_upsampling == 'dc':
             x = deconv_block(p, 'Deconvolution%d' % (j + 1), x, 2, n_filters, activation)
         x = pad_concat(x, skip)
-        x = conv_block(p, 'DecoderConvBlock%d' % (j + 1), x, n_filters, activation, attention)
+        x = conv_block(p, 'DecoderConvBlock%d' % (j + 1), x, n_filters, activation, attention,
+                       normalization=normalization)
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
-              output_activation, localcon_layer)
+              output_activation, localcon_layer, normalization=normalization)
     return _nhwc(x)
 
 
@@ -474,19 +534,21 @@ def recnet_pin(p, inputs, backbone_block, time_window, n_channels_out=1, n_filte
 
 
 def residual_discriminator(p, inputs, upsampling, scale, lr_size, n_filters=8, n_res_blocks=4,
-                           attention=False, dropout_mask=None):
+                           attention=False, dropout_mask=None, normalization=None):
     """residual_discriminator (spatial) -- discriminator.py:11-81.  ResidualBlocks always relu
     (App. B #10).  ``dropout_mask``: (B, 2*n_filters) keep-mask already scaled by 1/(1-0.4)
     (Dropout(0.4) with training=True, cgan.py:599-600); None = inference (identity)."""
     x_in, x_ref = _nchw(inputs[0]), _nchw(inputs[1])
     x1 = b = _conv(p, 'branch1_stem', x_in, n_filters)
     for i in range(n_res_blocks):
-        b = residual_block(p, 'ResidualBlock%d_branch1' % (i + 1), b, n_filters, 'relu', attention)
+        b = residual_block(p, 'ResidualBlock%d_branch1' % (i + 1), b, n_filters, 'relu', attention,
+                           normalization=normalization)
     b = _conv(p, 'branch1_last', b, n_filters)
     x1 = x1 + b
     x2 = c = _conv(p, 'branch2_stem', x_ref, n_filters)
     for i in range(n_res_blocks):
-        c = residual_block(p, 'ResidualBlock%d_branch2' % (i + 1), c, n_filters, 'relu', attention)
+        c = residual_block(p, 'ResidualBlock%d_branch2' % (i + 1), c, n_filters, 'relu', attention,
+                           normalization=normalization)
     if upsampling in POSTUPSAMPLING_METHODS:
         if scale == 5:
             c = _conv(p, 'branch2_down1', c, n_filters, stride=2, padding='valid')
@@ -501,7 +563,7 @@ def residual_discriminator(p, inputs, upsampling, scale, lr_size, n_filters=8, n
         c = _conv(p, 'branch2_last', c, n_filters)
         x2 = x2 + c
     x = torch.cat([x1, x2], dim=1)
-    x = residual_block(p, 'ResidualBlock_merged', x, x.shape[1], 'relu', attention)
+    x = residual_block(p, 'ResidualBlock_merged', x, x.shape[1], 'relu', attention, normalization=normalization)
     x = x.mean(dim=(2, 3))
     if dropout_mask is not None:
         x = x * dropout_mask
@@ -693,7 +755,8 @@ def supervised_step(forward_fn, weights, opt, inputs, target, loss='mae'):
     y = forward_fn(Params(weights), inputs)
     lossv = LOSSES[loss](target, y)
     lossv.backward()
-    grads = {n: w.grad.detach().clone() for n, w in weights.items()}
+    # (variables without a gradient -- BN moving statistics, DenseBlock's unused norm1 -- are skipped by Keras)
+    grads = {n: (w.grad.detach().clone() if w.grad is not None else torch.zeros_like(w)) for n, w in weights.items()}
     for w in weights.values():
         w.requires_grad_(False)
     if opt is not None:
@@ -751,7 +814,14 @@ def init_weights(spec, seed=0, bias_scale=0.0):
     rng = np.random.default_rng(seed)
     out = OrderedDict()
     for name, shape in spec.items():
-        if name.endswith('/bias'):
+        if name.endswith(('/gamma', '/moving_variance')):
+            # Keras: ones; with bias_scale > 0 perturbed so that the scale paths are exercised
+            a = 1.0 + (bias_scale * rng.uniform(-1, 1, size=shape) if bias_scale > 0 else np.zeros(shape))
+            out[name] = torch.from_numpy(a.astype(np.float32))
+        elif name.endswith(('/beta', '/moving_mean')):
+            a = bias_scale * rng.standard_normal(shape) if bias_scale > 0 else np.zeros(shape)
+            out[name] = torch.from_numpy(a.astype(np.float32))
+        elif name.endswith('/bias'):
             if bias_scale > 0:
                 out[name] = torch.from_numpy((bias_scale * rng.standard_normal(shape)).astype(np.float32))
             else:

@@ -186,8 +186,10 @@ def test_recnet_structure_cfg4():
 def test_model_names_and_unsupported():
     assert nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8)).name == 'resnet_spc'
     assert nets.unet_pin('unet', 1, 0, (16, 16), 1, 8, 2).name == 'unet_pin'
+    with pytest.raises(ValueError):
+        nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), normalization='gn')
     with pytest.raises(NotImplementedError):
-        nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), normalization='bn')
+        nets.recnet_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), 3, normalization='bn')
     with pytest.raises(NotImplementedError):
         nets.net_postupsampling('convnext', 'spc', 4, 1, 0, (8, 8))
     with pytest.raises(NotImplementedError):
