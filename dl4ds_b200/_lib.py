@@ -45,6 +45,12 @@ SIGNATURES = {
     'dl4ds_batchnorm_bwd': ('i', 'pipipipppfpipppliip'),
     'dl4ds_layernorm_fwd': ('i', 'pippfpiliip'),
     'dl4ds_layernorm_bwd': ('i', 'pipipipfpippliip'),
+    'dl4ds_depthwise_conv_fwd': ('i', 'pipppiiiiiiiip'),
+    'dl4ds_depthwise_conv_wgrad': ('i', 'pipipiiiiip'),
+    'dl4ds_gelu_fwd': ('i', 'pplp'),
+    'dl4ds_gelu_bwd': ('i', 'ppplp'),
+    'dl4ds_dropout': ('i', 'pipillifipip'),
+    'dl4ds_rng_advance': ('i', 'pp'),
     'dl4ds_adam_step': ('i', 'pppplffffifp'),
     'dl4ds_adam_step_dev': ('i', 'pppplpffffp'),
     'dl4ds_convt_rearrange': ('i', 'ppiiiiiiiip'),

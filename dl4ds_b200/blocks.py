@@ -7,7 +7,7 @@ Where the reference fuses nothing, the CUDA path fuses bias + activation (+ resi
 (+ depth_to_space) into the convolution epilogue.
 """
 
-SUPPORTED_ACTIVATIONS = (None, 'linear', 'relu', 'sigmoid', 'tanh')
+SUPPORTED_ACTIVATIONS = (None, 'linear', 'relu', 'sigmoid', 'tanh', 'gelu')
 
 
 def conv_block(c, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3, normalization=None):
@@ -62,6 +62,22 @@ def dense_block(c, name, x, filters, activation='relu', attention=False, normali
     if attention:
         y = c.channel_attention(y, name + '/att')
     return c.concat([y, x])
+
+
+def convnext_block(c, name, x, filters, activation='gelu', normalization='ln', use_1x1conv=False):
+    """ConvNextBlock.call -- blocks.py:170-184 with drop_path=0 and layer_scale_init_value=0 (the values every
+    builder passes / the default: no DropPath, no layer-scale gamma): 7x7 depthwise conv -> norm (LN with
+    epsilon 1e-6, or BN) -> Dense(4F) -> activation -> Dense(F), added to the ([1x1-projected]) input."""
+    if normalization not in ('bn', 'ln'):
+        # the reference only creates `self.norm` for 'bn' / 'ln' (:158-164) and calls it unconditionally (:173)
+        raise ValueError("ConvNextBlock needs normalization 'bn' or 'ln' (the reference fails in call() with "
+                         "%r: blocks.py:158-164,173)" % (normalization,))
+    y = c.depthwise_conv(x, name + '/dwconv', 7)
+    y = c.norm(y, name + '/norm', normalization, eps=1e-6 if normalization == 'ln' else 1e-3)
+    y = c.dense(y, name + '/pwconv1', 4 * filters, act=activation)
+    y = c.dense(y, name + '/pwconv2', filters)
+    skip = c.conv(x, name + '/conv1x1', filters, k=1) if use_1x1conv else x
+    return c.add(skip, y)
 
 
 def transition_block(c, name, x, filters, activation='relu'):

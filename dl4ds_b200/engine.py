@@ -331,6 +331,9 @@ class Ctx:
              d2s=1, out=None, dense=False):
         """Keras Conv2D (+bias +activation [+residual add before the activation] [+depth_to_space])
         -- blocks.py:49-61,91,97,208,299,427; sp_postups.py:134,156."""
+        if act == 'gelu':       # not expressible through its output: linear epilogue, then the standalone kernel
+            return self.gelu(self.conv(x, name, cout, k=k, act=None, bias=bias, stride=stride, padding=padding,
+                                       res=res, d2s=d2s, out=out, dense=dense))
         w = self._p(name + '/kernel')
         wshape = (x.C, cout) if dense else (k, k, x.C, cout)
         assert tuple(w.shape) == wshape, (name, tuple(w.shape), wshape)
@@ -407,6 +410,8 @@ class Ctx:
         differentiates the composed layer and maps (dW_eff, db_eff) back onto the four original parameter
         gradients with the exact chain rule (``dl4ds_spc_pointwise_chain``).  Results equal the unfused
         graph up to fp32 re-association."""
+        if act == 'gelu':
+            return self.gelu(self.conv_d2s_pointwise(x, name1, cm, name2, co, act=None, r=r, k=k))
         w1, b1 = self._p(name1 + '/kernel'), self._p(name1 + '/bias')
         w2, b2 = self._p(name2 + '/kernel'), self._p(name2 + '/bias')
         R2 = r * r
@@ -468,6 +473,8 @@ class Ctx:
     def conv_transpose(self, x, name, cout, k, stride, act=None):
         """Keras Conv2DTranspose(cout, k, strides=stride, padding='same', use_bias=False)
         -- blocks.py:508-516.  out = stride * in; kernel layout (kh,kw,Cout,Cin)."""
+        if act == 'gelu':
+            return self.gelu(self.conv_transpose(x, name, cout, k, stride, act=None))
         w = self._p(name + '/kernel')
         assert tuple(w.shape) == (k, k, cout, x.C), (name, tuple(w.shape))
         Ho, Wo = x.H * stride, x.W * stride
@@ -550,14 +557,17 @@ class Ctx:
         return out
 
     def dense(self, x, name, cout, act=None):
-        """Keras Dense on (B,1,1,Cin) -- discriminator.py:78-79 (a 1x1 convolution on a 1x1 map)."""
-        assert x.H == 1 and x.W == 1
+        """Keras Dense acts on the last axis: a 1x1 convolution with a (Cin, Cout) kernel -- on the pooled
+        (B,1,1,Cin) vector in the discriminator (discriminator.py:78-79), on every pixel in ConvNextBlock
+        (blocks.py:150,155)."""
         return self.conv(x, name, cout, k=1, act=act, dense=True)
 
     # ---------------------------------------------------------------- element-wise / structural
     def add(self, a, b, act=None):
         """Add (+ optional activation) -- sp_postups.py:164, blocks.py:228-229."""
         assert (a.N, a.H, a.W, a.C) == (b.N, b.H, b.W, b.C)
+        if act == 'gelu':
+            return self.gelu(self.add(a, b))
         out = a.like()
         code = ACT[act]
         self._call('dl4ds_add', a.ptr, a.ld, b.ptr, b.ld, out.ptr, out.ld, a.npix, a.C, code, _stream())
@@ -600,6 +610,8 @@ class Ctx:
 
     def act(self, x, act):
         """Standalone activation -- blocks.py:391,397."""
+        if act == 'gelu':
+            return self.gelu(x)
         code = ACT[act]
         if code == 0:
             return x
@@ -625,6 +637,8 @@ class Ctx:
         it uses the moving ones."""
         if kind not in ('bn', 'ln'):
             raise ValueError('Normalization not supported, got %s' % (kind,))           # blocks.py:64-65
+        if act == 'gelu':
+            return self.gelu(self.norm(x, name, kind, act=None, eps=eps))
         code, C, n_pix = ACT[act], x.C, x.npix
         gamma, beta = self._p(name + '/gamma'), self._p(name + '/beta')
         out = x.like()
@@ -672,6 +686,51 @@ class Ctx:
                     self._acc_via_tmp(x, wr)
                 elif pg:
                     wr(x.like())
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def depthwise_conv(self, x, name, k=7):
+        """DepthwiseConv2D(kernel_size=k, padding='same', depth_multiplier=1) with bias -- blocks.py:147-148."""
+        wt, bias = self._p(name + '/depthwise_kernel'), self._p(name + '/bias')
+        out = x.like()
+        self._call('dl4ds_depthwise_conv_fwd', x.ptr, x.ld, wt.data_ptr(), bias.data_ptr(), out.ptr, out.ld,
+                   x.N, x.H, x.W, x.C, k, 0, 0, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            if self.param_grads:
+                self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, None, 0, None, 0, self._g(name + '/bias').data_ptr(),
+                           x.N, x.H, x.W, x.C, 0, 1, _stream())
+                self._call('dl4ds_depthwise_conv_wgrad', x.ptr, x.ld, dy.ptr, dy.ld,
+                           self._g(name + '/depthwise_kernel').data_ptr(), x.N, x.H, x.W, x.C, k, _stream())
+            if x.requires_grad:
+                def wr(dst, beta):
+                    self._call('dl4ds_depthwise_conv_fwd', dy.ptr, dy.ld, wt.data_ptr(), None, dst.ptr, dst.ld,
+                               x.N, x.H, x.W, x.C, k, 1, beta, _stream())
+                self._acc(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def gelu(self, x):
+        """Activation('gelu'), exact erf form -- ConvNextBlock's default activation, blocks.py:143,153."""
+        xd = self._dense(x)
+        out = xd.like()
+        n = xd.npix * xd.C
+        self._call('dl4ds_gelu_fwd', xd.ptr, out.ptr, n, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dy = self._dense(dy)
+
+            def wr(dst):
+                self._call('dl4ds_gelu_bwd', xd.ptr, dy.ptr, dst.ptr, n, _stream())
+            self._acc_via_tmp(x, wr)
             out.grad = None
         self._record(bwd)
         return out

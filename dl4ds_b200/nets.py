@@ -20,7 +20,7 @@ from . import blocks as B
 from .engine import Arena, Ctx
 from .spec import SpecCtx
 
-BACKBONES = ('convnet', 'resnet', 'densenet', 'unet')
+BACKBONES = ('convnet', 'resnet', 'densenet', 'unet', 'convnext')
 POSTUPSAMPLING_METHODS = ('spc', 'rc', 'dc')
 
 
@@ -297,6 +297,14 @@ class Model:
 def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization=None):
     """Stem + N blocks + last conv + long skip -- sp_postups.py:132-168, sp_preups.py:116-151."""
     init_n_filters = n_filters
+    if backbone_block == 'convnext':      # sp_postups.py:120-131, sp_preups.py:104-115: 7x7 stem, no last conv
+        x = b = c.conv(x_in, 'stem', n_filters, k=7)
+        for i in range(n_blocks):
+            n_filters = init_n_filters * (i + 1)
+            b = B.convnext_block(c, 'ConvNextBlock%d' % (i + 1), b, n_filters, activation, normalization,
+                                 use_1x1conv=(i != 0))
+        x = B.transition_block(c, 'TransitionSkip', x, n_filters, activation)
+        return c.add(x, b), n_filters
     x = b = c.conv(x_in, 'stem', n_filters)
     for i in range(n_blocks):
         n_filters = init_n_filters * (i + 1)
@@ -323,23 +331,31 @@ def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activatio
 
 
 def _tail(c, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation, output_activation,
-          localcon_layer, transition_done=False, normalization=None):
+          localcon_layer, transition_done=False, normalization=None, convnext=False):
     """LCB, HR aux branch, TransitionLast, ConvBlock(att), ConvBlock(out)
     -- sp_postups.py:184-212, sp_preups.py:155-183,291-309.  ``transition_done``: TransitionLast was already
     applied by the caller (composed with the last sub-pixel stage)."""
     nz = normalization
+    ks = 7 if convnext else 3             # sp_postups.py:121,133,207-212: the tail ConvBlocks use the backbone's `ks`
     if transition_done:
-        x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz)
-        return B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz)
+        x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz,
+                         ks1=ks, ks2=ks)
+        return B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz,
+                            ks1=ks, ks2=ks)
     if localcon_layer:
         lws = B.localized_conv_block(c, 'LocalizedConvBlock', x, 2)
         x = c.concat([x, lws])
     if s_in is not None:
-        s = B.conv_block(c, 'ConvBlock_aux', s_in, n_filters_aux, activation=activation, normalization=nz)
+        if convnext:                      # sp_postups.py:191-195
+            s = B.convnext_block(c, 'ConvNextBlock_aux', s_in, n_filters_aux, activation, nz, use_1x1conv=True)
+        else:
+            s = B.conv_block(c, 'ConvBlock_aux', s_in, n_filters_aux, activation=activation, normalization=nz)
         x = c.concat([x, s])
     x = B.transition_block(c, 'TransitionLast', x, init_n_filters)      # default relu
-    x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz)
-    x = B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz)
+    x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz,
+                     ks1=ks, ks2=ks)
+    x = B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz,
+                     ks1=ks, ks2=ks)
     return x
 
 
@@ -378,7 +394,8 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
             x = B.transition_block(c, 'TransitionDC', x, n_filters, activation)
             x = B.deconv_block(c, 'Deconvolution', x, scale, nf, activation)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
-                     output_activation, localcon_layer, transition_done=fused, normalization=normalization)
+                     output_activation, localcon_layer, transition_done=fused, normalization=normalization,
+                     convnext=(backbone_block == 'convnext'))
 
     ups_total = scale
     if upsampling == 'dc' and scale == 4:
@@ -399,7 +416,8 @@ def net_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out=
     def fn(c, inputs):
         x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation, normalization)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
-                     output_activation, localcon_layer, normalization=normalization)
+                     output_activation, localcon_layer, normalization=normalization,
+                     convnext=(backbone_block == 'convnext'))
 
     shapes = [(hr_size[0], hr_size[1], n_channels)]
     if aux:

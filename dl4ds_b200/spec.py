@@ -108,6 +108,15 @@ class SpecCtx:
             self._reg(name + '/moving_variance', (x.C,))
         return SVar(*x.shape)
 
+    def depthwise_conv(self, x, name, k=7):
+        self._reg(name + '/depthwise_kernel', (k, k, x.C, 1))
+        self._reg(name + '/bias', (x.C,))
+        self._count(name, x, x.N * x.H * x.W * k * k * x.C)
+        return SVar(*x.shape)
+
+    def gelu(self, x):
+        return x
+
     def channel_attention(self, x, name, r=4, groups=None):
         cr = int(x.C / r)
         self._reg(name + '/conv1/kernel', (1, 1, x.C, cr))

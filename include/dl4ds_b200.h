@@ -220,6 +220,34 @@ int dl4ds_layernorm_bwd(const float* dy, int dy_ld, const float* x, int x_ld, co
                         int64_t n_pix, int C, int act, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ConvNextBlock pieces -- blocks.py:131-184.  DepthwiseConv2D(kernel_size=7, padding='same', depth_multiplier=1)
+ * (:147-148): w is the Keras depthwise kernel (k, k, C, 1) = [k][k][C], stride 1, odd k <= 7.
+ *   fwd:   y (+)= bias + sum_ij w[i][j][c] x[h+i-r, w+j-r, c];  flip = 1 uses w[k-1-i][k-1-j]: the input gradient
+ *          (call it with x := dy, bias := NULL).
+ *   wgrad: dw[i][j][c] += sum dy[p, c] x[p + (i-r, j-r), c]   (the bias gradient is dl4ds_bias_act_bwd's dbias).
+ * GELU, the block's default activation (:143,153), exact erf form: y = x Phi(x); dx = dy (Phi(x) + x phi(x)).
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_depthwise_conv_fwd(const float* x, int x_ld, const float* w, const float* bias, float* y, int y_ld,
+                             int N, int H, int W, int C, int k, int flip, int accumulate, void* stream);
+int dl4ds_depthwise_conv_wgrad(const float* x, int x_ld, const float* dy, int dy_ld, float* dw, int N, int H, int W,
+                               int C, int k, void* stream);
+int dl4ds_gelu_fwd(const float* x, float* y, int64_t n, void* stream);
+int dl4ds_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dropout variants -- blocks.py:659-706 (`get_dropout_layer`) applied at blocks.py:89,95-96,211-214,219-220,
+ * 265-266,271-272 and sp_postups.py:158.  variant 0 = Dropout (keep where u >= rate, scale 1/(1-rate)),
+ * 1 = GaussianDropout (x * N(1, sqrt(rate/(1-rate)))), 2 = SpatialDropout2D (one draw per sample and channel).
+ * y = x * mask(seed, step, layer_id, element): Philox4x32-10, `rng_state` = DEVICE uint64[2] {seed, step}.  The
+ * mask is a pure function of its arguments: the backward pass is the same call on dy.  dl4ds_rng_advance bumps
+ * `step` (one kernel, captured with the step graph, so every replay draws new masks).  TensorFlow's own random
+ * streams are not reproducible; parity tests obtain the mask by applying the call to a tensor of ones.
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_dropout(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, int64_t pix_per_sample, int C,
+                  float rate, int variant, const uint64_t* rng_state, int layer_id, void* stream);
+int dl4ds_rng_advance(uint64_t* rng_state, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * tf.keras.optimizers.Adam step on a flat arena -- supervised.py:353, cgan.py:277-278.
  *   g = grad * grad_scale (grad_scale = 1/world_size folds Horovod's allreduce-average,
  *   supervised.py:365);  m,v updated;  theta -= lr_t * m / (sqrt(v) + eps)

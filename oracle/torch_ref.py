@@ -251,6 +251,37 @@ def dense_block(p, name, x, filters, activation='relu', attention=False, normali
     return torch.cat([y, x], dim=1)
 
 
+def depthwise_conv2d(x, w, b):
+    """tf.keras.layers.DepthwiseConv2D(k, padding='same', depth_multiplier=1): w (k,k,C,1), NCHW x."""
+    k, c = w.shape[0], w.shape[2]
+    pt, pb = same_pads(x.shape[2], k, 1)
+    pl, pr = same_pads(x.shape[3], k, 1)
+    wt = w.permute(2, 3, 0, 1)                          # (C,1,k,k)
+    return F.conv2d(F.pad(x, (pl, pr, pt, pb)), wt, b, groups=c)
+
+
+def convnext_block(p, name, x, filters, activation='gelu', normalization='ln', use_1x1conv=False):
+    """ConvNextBlock.call -- blocks.py:170-184 (drop_path=0: identity, :117-118; layer_scale_init_value=0: no
+    gamma, :166-168).  LayerNormalization(epsilon=1e-6) / BatchNormalization() -- :161-164; any other value of
+    ``normalization`` leaves the layer without ``self.norm`` and the reference's call() fails."""
+    if normalization not in ('bn', 'ln'):
+        raise ValueError('ConvNextBlock needs normalization bn or ln')
+    c = x.shape[1]
+    wd = p.get(name + '/dwconv/depthwise_kernel', (7, 7, c, 1))
+    bd = p.get(name + '/dwconv/bias', (c,))
+    y = depthwise_conv2d(x, wd, bd)
+    y = normalize(p, name + '/norm', y, normalization, eps=1e-6 if normalization == 'ln' else 1e-3)
+    w1 = p.get(name + '/pwconv1/kernel', (c, 4 * filters))
+    b1 = p.get(name + '/pwconv1/bias', (4 * filters,))
+    y = act(torch.einsum('nchw,cd->ndhw', y, w1) + b1.view(1, -1, 1, 1), activation)
+    w2 = p.get(name + '/pwconv2/kernel', (4 * filters, filters))
+    b2 = p.get(name + '/pwconv2/bias', (filters,))
+    y = torch.einsum('nchw,cd->ndhw', y, w2) + b2.view(1, -1, 1, 1)
+    if use_1x1conv:
+        x = _conv(p, name + '/conv1x1', x, filters, k=1)
+    return x + y
+
+
 def transition_block(p, name, x, filters, activation='relu'):
     """TransitionBlock.call without BN: conv1x1 then activation -- blocks.py:306-308."""
     return act(_conv(p, name + '/conv', x, filters, k=1), activation)
@@ -357,20 +388,25 @@ def _nhwc(x):
 
 
 def _tail(p, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation,
-          output_activation, localcon_layer, aux_name='ConvBlock_aux', normalization=None):
+          output_activation, localcon_layer, aux_name='ConvBlock_aux', normalization=None, convnext=False):
     """Shared output module: LCB, aux branch, TransitionLast, two ConvBlocks
     -- sp_postups.py:184-212, sp_preups.py:155-183,291-309."""
     if localcon_layer:
         lws = localized_conv_block(p, 'LocalizedConvBlock', x, 2)
         x = torch.cat([x, lws], dim=1)
     if s_in is not None:
-        s = conv_block(p, aux_name, s_in, n_filters_aux, activation=activation, normalization=normalization)
+        if convnext:                            # sp_postups.py:191-195
+            s = convnext_block(p, 'ConvNextBlock_aux', s_in, n_filters_aux, activation, normalization,
+                               use_1x1conv=True)
+        else:
+            s = conv_block(p, aux_name, s_in, n_filters_aux, activation=activation, normalization=normalization)
         x = torch.cat([x, s], dim=1)
+    ks = 7 if convnext else 3                   # sp_postups.py:121,133: `ks` of the backbone branch
     x = transition_block(p, 'TransitionLast', x, init_n_filters)   # default relu (App. B #9)
     x = conv_block(p, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True,
-                   normalization=normalization)
+                   normalization=normalization, ks1=ks, ks2=ks)
     x = conv_block(p, 'ConvBlock_out', x, n_channels_out, activation=output_activation,
-                   normalization=normalization)
+                   normalization=normalization, ks1=ks, ks2=ks)
     return x
 
 
@@ -378,6 +414,14 @@ def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activatio
     """Backbone section shared by net_postupsampling / net_pin -- sp_postups.py:132-168,
     sp_preups.py:116-151."""
     init_n_filters = n_filters
+    if backbone_block == 'convnext':        # sp_postups.py:120-131, sp_preups.py:104-115
+        x = b = _conv(p, 'stem', x_in, n_filters, k=7)
+        for i in range(n_blocks):
+            n_filters = init_n_filters * (i + 1)
+            b = convnext_block(p, 'ConvNextBlock' + str(i + 1), b, n_filters, activation, normalization,
+                               use_1x1conv=(i != 0))
+        x = transition_block(p, 'TransitionSkip', x, n_filters, activation)
+        return x + b, n_filters
     x = b = _conv(p, 'stem', x_in, n_filters)
     for i in range(n_blocks):
         n_filters = init_n_filters * (i + 1)
@@ -421,7 +465,8 @@ def net_postupsampling(p, inputs, backbone_block, upsampling, scale, n_channels_
         x = transition_block(p, 'TransitionDC', x, init_n_filters, activation)
         x = deconv_block(p, 'Deconvolution', x, scale, n_filters, activation)
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
-              output_activation, localcon_layer, normalization=normalization)
+              output_activation, localcon_layer, normalization=normalization,
+              convnext=(backbone_block == 'convnext'))
     return _nhwc(x)
 
 
@@ -434,7 +479,8 @@ def net_pin(p, inputs, backbone_block, n_channels_out=1, n_filters=8, n_blocks=6
     init_n_filters = n_filters
     x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization)
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
-              output_activation, localcon_layer, normalization=normalization)
+              output_activation, localcon_layer, normalization=normalization,
+              convnext=(backbone_block == 'convnext'))
     return _nhwc(x)
 
 

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_convnext.py tests/test_gpu_norm.py -m gpu -q -rf --no-header > gpurun_out/next_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/next_pytest.log
+grep -E "^FAILED|^ERROR|passed|failed|rc=" gpurun_out/next_pytest.log | cut -c1-300 | tail -40

@@ -190,10 +190,12 @@ def test_model_names_and_unsupported():
         nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), normalization='gn')
     with pytest.raises(NotImplementedError):
         nets.recnet_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), 3, normalization='bn')
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):           # ConvNextBlock without a normalisation fails in the reference too
         nets.net_postupsampling('convnext', 'spc', 4, 1, 0, (8, 8))
     with pytest.raises(NotImplementedError):
-        nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), activation='gelu')
+        nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), activation='elu')
+    with pytest.raises(NotImplementedError):
+        nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), dropout_rate=0.2)
 
 
 def test_recnet_pin_structure():
