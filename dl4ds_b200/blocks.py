@@ -1,8 +1,8 @@
 """Graph blocks of the DL4DS hot path as functions over an engine context (``Ctx`` or ``SpecCtx``).
 
 Mirrors the layer classes of the reference's ``dl4ds/models/blocks.py`` (cited per function) for the
-configurations on the north-star path (``dropout_rate=0``, the model default, sp_postups.py:26-28;
-``normalization`` None, 'bn' or 'ln').  Parameter names follow ``<layer>/<sublayer>/{kernel,bias}``.
+configurations on the north-star path and its "next" rows (``normalization`` None, 'bn' or 'ln'; every
+``dropout_variant``; model defaults are None / 0, sp_postups.py:26-28).  Parameter names follow ``<layer>/<sublayer>/{kernel,bias}``.
 Where the reference fuses nothing, the CUDA path fuses bias + activation (+ residual add)
 (+ depth_to_space) into the convolution epilogue.
 """
@@ -10,15 +10,20 @@ Where the reference fuses nothing, the CUDA path fuses bias + activation (+ resi
 SUPPORTED_ACTIVATIONS = (None, 'linear', 'relu', 'sigmoid', 'tanh', 'gelu')
 
 
-def conv_block(c, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3, normalization=None):
+def conv_block(c, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3, normalization=None,
+               dropout_rate=0, dropout_variant=None):
     """ConvBlock.call -- blocks.py:87-103.  With ``normalization`` ('bn' | 'ln') the convolutions carry no bias
-    (:37,44,52,58) and each is followed by the normalisation with the activation fused into it."""
+    (:37,44,52,58) and each is followed by the normalisation with the activation fused into it; with
+    ``dropout_rate`` > 0 a dropout layer sits in front of each convolution (:89,95-96)."""
+    x = c.dropout(x, dropout_rate, dropout_variant)
     if normalization is None:
         y = c.conv(x, name + '/conv1', filters, k=ks1, act=activation)
+        y = c.dropout(y, dropout_rate, dropout_variant)
         y = c.conv(y, name + '/conv2', filters, k=ks2, act=activation)
     else:
         y = c.conv(x, name + '/conv1', filters, k=ks1, bias=False)
         y = c.norm(y, name + '/norm1', normalization, act=activation)
+        y = c.dropout(y, dropout_rate, dropout_variant)
         y = c.conv(y, name + '/conv2', filters, k=ks2, bias=False)
         y = c.norm(y, name + '/norm2', normalization, act=activation)
     if attention:
@@ -26,18 +31,23 @@ def conv_block(c, name, x, filters, activation='relu', attention=False, ks1=3, k
     return y
 
 
-def residual_block(c, name, x, filters, activation='relu', attention=False, use_1x1conv=False, normalization=None):
-    """ResidualBlock.call -- blocks.py:210-230: act([norm2](conv2(act([norm1](conv1(X))))) [*att] + [conv1x1](X))."""
+def residual_block(c, name, x, filters, activation='relu', attention=False, use_1x1conv=False, normalization=None,
+                   dropout_rate=0, dropout_variant=None):
+    """ResidualBlock.call -- blocks.py:210-230: act([norm2](conv2([drop](act([norm1](conv1([drop](X))))))) [*att]
+    + [conv1x1](X)); the skip takes the un-dropped X."""
+    xd = c.dropout(x, dropout_rate, dropout_variant)
     if normalization is not None:
-        y = c.conv(x, name + '/conv1', filters, bias=False)
+        y = c.conv(xd, name + '/conv1', filters, bias=False)
         y = c.norm(y, name + '/norm1', normalization, act=activation)
+        y = c.dropout(y, dropout_rate, dropout_variant)
         y = c.conv(y, name + '/conv2', filters, bias=False)
         y = c.norm(y, name + '/norm2', normalization)
         if attention:
             y = c.channel_attention(y, name + '/att')
         skip = c.conv(x, name + '/conv1x1', filters, k=1) if use_1x1conv else x
         return c.add(y, skip, act=activation)
-    y = c.conv(x, name + '/conv1', filters, act=activation)
+    y = c.conv(xd, name + '/conv1', filters, act=activation)
+    y = c.dropout(y, dropout_rate, dropout_variant)
     skip = c.conv(x, name + '/conv1x1', filters, k=1) if use_1x1conv else x
     if attention:
         y = c.conv(y, name + '/conv2', filters)
@@ -47,17 +57,19 @@ def residual_block(c, name, x, filters, activation='relu', attention=False, use_
     return c.conv(y, name + '/conv2', filters, act=activation, res=skip)
 
 
-def dense_block(c, name, x, filters, activation='relu', attention=False, normalization=None):
+def dense_block(c, name, x, filters, activation='relu', attention=False, normalization=None, dropout_rate=0,
+                dropout_variant=None):
     """DenseBlock.call -- blocks.py:262-277.  The pre-activation of X is computed and discarded by
-    the reference (:263-267): Y = conv3x3(act([norm2](conv1x1(X)))) [*att]; out = concat([Y, X]).  With a
+    the reference (:263-267): Y = conv3x3([drop](act([norm2](conv1x1(X))))) [*att]; out = concat([Y, X]).  With a
     normalisation, norm1 still runs on X (its parameters exist, BN moving statistics follow X) and its output is
-    dropped; DenseBlock's own conv1 / conv2 keep their bias (:249-259)."""
+    dropped -- as is dropout1's; DenseBlock's own conv1 / conv2 keep their bias (:249-259)."""
     if normalization is None:
         y = c.conv(x, name + '/conv1', 4 * filters, k=1, act=activation)
     else:
         c.norm(x, name + '/norm1', normalization, act=activation)
         y = c.conv(x, name + '/conv1', 4 * filters, k=1)
         y = c.norm(y, name + '/norm2', normalization, act=activation)
+    y = c.dropout(y, dropout_rate, dropout_variant)
     y = c.conv(y, name + '/conv2', filters, k=3)
     if attention:
         y = c.channel_attention(y, name + '/att')

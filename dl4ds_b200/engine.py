@@ -35,6 +35,8 @@ LOSS_TERMS = {
     'msdssim_mae_mse': (('mae', 0.2), ('mse', 0.2), ('msdssim', 0.6)),
 }
 MSSSIM_POWER_FACTORS = (0.0448, 0.2856, 0.3001, 0.2363)      # losses.py:128
+DROPOUT_KIND = {None: 0, 'vanilla': 0, 'mcdrop': 0, 'gaussian': 1, 'mcgaussiandrop': 1, 'spatial': 2,
+                'mcspatialdrop': 2}                          # blocks.py:680-706 -> dl4ds_dropout variant
 LOSS_ACCUMULATE = 16                                          # DL4DS_LOSS_ACCUMULATE, OR-ed into `kind`
 _PF_HOST = (ctypes.c_float * len(MSSSIM_POWER_FACTORS))(*MSSSIM_POWER_FACTORS)
 
@@ -99,6 +101,24 @@ class Arena:
 
     def zero_grad(self):
         self.grad.zero_()
+
+    # dropout masks: DEVICE uint64[2] {seed, step} read by dl4ds_dropout, bumped by dl4ds_rng_advance
+    RNG_SEED = 0x5DEECE66D
+
+    def rng_state(self):
+        if getattr(self, '_rng', None) is None:
+            rank = 0
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank = dist.get_rank()          # independent masks per replica, as with Horovod
+            except Exception:
+                rank = 0
+            self._rng = torch.tensor([self.RNG_SEED + 7919 * rank, 0], dtype=torch.int64, device=self.device)
+        return self._rng
+
+    def seed_rng(self, seed, step=0):
+        self._rng = torch.tensor([int(seed), int(step)], dtype=torch.int64, device=self.device)
 
 
 class Var:
@@ -176,6 +196,8 @@ class Ctx:
         self.pack_stream = None
         self._packed = set()
         self._pack_forked = False
+        self._rng_advanced = False  # dropout: the arena's RNG step is bumped once per Ctx, before the first mask
+        self._dropout_calls = 0     # ... and every dropout application gets its own layer id
 
     # ---------------------------------------------------------------- helpers
     def _call(self, name, *args):
@@ -730,6 +752,39 @@ class Ctx:
 
             def wr(dst):
                 self._call('dl4ds_gelu_bwd', xd.ptr, dy.ptr, dst.ptr, n, _stream())
+            self._acc_via_tmp(x, wr)
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def dropout(self, x, rate, variant=None):
+        """get_dropout_layer(rate, variant)(x) -- blocks.py:680-706: Dropout / GaussianDropout / SpatialDropout2D,
+        active in training mode; the 'mc*' variants also in inference (blocks.py:662-677).  Masks: dl4ds_dropout
+        (Philox, seed and step in device memory); the backward pass regenerates the same mask."""
+        if variant is not None and variant not in DROPOUT_KIND:
+            raise ValueError('`dropout_variant` must be None or one of %s, got %s' % (sorted(k for k in DROPOUT_KIND if k), variant))
+        if not rate or rate <= 0:
+            return x
+        if not (self.training or (variant or '').startswith('mc')):
+            return x
+        state = self.arena.rng_state()
+        if not self._rng_advanced:
+            self._call('dl4ds_rng_advance', state.data_ptr(), _stream())
+            self._rng_advanced = True
+        self._dropout_calls += 1
+        lid, kind = self._dropout_calls, DROPOUT_KIND[variant]
+        out = x.like()
+        self._call('dl4ds_dropout', x.ptr, x.ld, out.ptr, out.ld, x.npix, x.H * x.W, x.C, float(rate), kind,
+                   state.data_ptr(), lid, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+
+            def wr(dst):
+                self._call('dl4ds_dropout', dy.ptr, dy.ld, dst.ptr, dst.ld, x.npix, x.H * x.W, x.C, float(rate), kind,
+                           state.data_ptr(), lid, _stream())
             self._acc_via_tmp(x, wr)
             out.grad = None
         self._record(bwd)

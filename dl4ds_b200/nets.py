@@ -19,19 +19,22 @@ import torch
 from . import blocks as B
 from .engine import Arena, Ctx
 from .spec import SpecCtx
+from .utils import checkarg_dropout_variant
 
 BACKBONES = ('convnet', 'resnet', 'densenet', 'unet', 'convnext')
 POSTUPSAMPLING_METHODS = ('spc', 'rc', 'dc')
 
 
-def _check_common(activation, output_activation, normalization, dropout_rate, backbone_block=None):
+def _check_common(activation, output_activation, normalization, dropout_rate, backbone_block=None,
+                  dropout_variant=None, dropout_built=True):
     for a in (activation, output_activation):
         if a not in B.SUPPORTED_ACTIVATIONS:
             raise NotImplementedError('activation %r is outside the B200 hot path' % (a,))
     if normalization not in (None, 'bn', 'ln'):
         raise ValueError('Normalization not supported, got %s' % (normalization,))      # blocks.py:64-65
-    if dropout_rate:
-        raise NotImplementedError('dropout_rate>0 is outside the B200 hot path (model default is 0)')
+    checkarg_dropout_variant(dropout_variant)
+    if dropout_rate and not dropout_built:
+        raise NotImplementedError('dropout_rate>0 in the recurrent (ConvLSTM) networks is not built')
     if backbone_block is not None and backbone_block not in BACKBONES:
         raise NotImplementedError('backbone %r is outside the B200 hot path' % (backbone_block,))
 
@@ -294,7 +297,8 @@ class Model:
 # ---------------------------------------------------------------------------------------------
 # shared sections
 # ---------------------------------------------------------------------------------------------
-def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization=None):
+def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization=None,
+              dropout_rate=0, dropout_variant=None):
     """Stem + N blocks + last conv + long skip -- sp_postups.py:132-168, sp_preups.py:116-151."""
     init_n_filters = n_filters
     if backbone_block == 'convnext':      # sp_postups.py:120-131, sp_preups.py:104-115: 7x7 stem, no last conv
@@ -310,15 +314,17 @@ def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activatio
         n_filters = init_n_filters * (i + 1)
         if backbone_block == 'convnet':
             b = B.conv_block(c, 'ConvBlock%d' % (i + 1), b, n_filters, activation, attention,
-                             normalization=normalization)
+                             normalization=normalization, dropout_rate=dropout_rate, dropout_variant=dropout_variant)
         elif backbone_block == 'resnet':
             b = B.residual_block(c, 'ResidualBlock%d' % (i + 1), b, n_filters, activation, attention,
-                                 use_1x1conv=(i != 0), normalization=normalization)
+                                 use_1x1conv=(i != 0), normalization=normalization, dropout_rate=dropout_rate,
+                                 dropout_variant=dropout_variant)
         elif backbone_block == 'densenet':
             b = B.dense_block(c, 'DenseBlock%d' % (i + 1), b, n_filters, activation, attention,
-                              normalization=normalization)
+                              normalization=normalization, dropout_rate=dropout_rate, dropout_variant=dropout_variant)
             b = B.transition_block(c, 'Transition%d' % (i + 1), b, b.C // 2)
     b = c.conv(b, 'backbone_last', n_filters, act=activation)
+    b = c.dropout(b, dropout_rate, dropout_variant)                     # sp_postups.py:158
     if backbone_block == 'convnet':
         x = b
     elif backbone_block == 'resnet':
@@ -331,7 +337,7 @@ def _backbone(c, x_in, backbone_block, n_filters, n_blocks, attention, activatio
 
 
 def _tail(c, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation, output_activation,
-          localcon_layer, transition_done=False, normalization=None, convnext=False):
+          localcon_layer, transition_done=False, normalization=None, convnext=False, dropout_rate=0):
     """LCB, HR aux branch, TransitionLast, ConvBlock(att), ConvBlock(out)
     -- sp_postups.py:184-212, sp_preups.py:155-183,291-309.  ``transition_done``: TransitionLast was already
     applied by the caller (composed with the last sub-pixel stage)."""
@@ -339,7 +345,7 @@ def _tail(c, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation,
     ks = 7 if convnext else 3             # sp_postups.py:121,133,207-212: the tail ConvBlocks use the backbone's `ks`
     if transition_done:
         x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz,
-                         ks1=ks, ks2=ks)
+                         ks1=ks, ks2=ks, dropout_rate=dropout_rate)
         return B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz,
                             ks1=ks, ks2=ks)
     if localcon_layer:
@@ -352,8 +358,9 @@ def _tail(c, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation,
             s = B.conv_block(c, 'ConvBlock_aux', s_in, n_filters_aux, activation=activation, normalization=nz)
         x = c.concat([x, s])
     x = B.transition_block(c, 'TransitionLast', x, init_n_filters)      # default relu
+    # (the reference passes the rate but not the variant here: plain Dropout, sp_postups.py:206-208)
     x = B.conv_block(c, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True, normalization=nz,
-                     ks1=ks, ks2=ks)
+                     ks1=ks, ks2=ks, dropout_rate=dropout_rate)
     x = B.conv_block(c, 'ConvBlock_out', x, n_channels_out, activation=output_activation, normalization=nz,
                      ks1=ks, ks2=ks)
     return x
@@ -369,7 +376,7 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
                        math='fp32', fuse_spc_transition=True):
     """net_postupsampling -- sp_postups.py:14-217.  ``fuse_spc_transition`` (an addition): compose the last
     sub-pixel stage with TransitionLast when nothing sits between them (same function, same parameters)."""
-    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant)
     if upsampling not in POSTUPSAMPLING_METHODS:
         raise ValueError('`upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
     if upsampling == 'rc' and rc_interpolation != 'bilinear':
@@ -378,7 +385,8 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
     aux = n_aux_channels > 0
 
     def fn(c, inputs):
-        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation, normalization)
+        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation, normalization,
+                          dropout_rate, dropout_variant)
         fused = False
         if upsampling == 'spc':
             if fuse_spc_transition and not aux and not localcon_layer:
@@ -395,7 +403,7 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
             x = B.deconv_block(c, 'Deconvolution', x, scale, nf, activation)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
                      output_activation, localcon_layer, transition_done=fused, normalization=normalization,
-                     convnext=(backbone_block == 'convnext'))
+                     convnext=(backbone_block == 'convnext'), dropout_rate=dropout_rate)
 
     ups_total = scale
     if upsampling == 'dc' and scale == 4:
@@ -410,14 +418,15 @@ def net_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out=
             n_blocks=6, dropout_rate=0, dropout_variant=None, normalization=None, attention=False,
             activation='relu', output_activation=None, localcon_layer=False, math='fp32'):
     """net_pin -- sp_preups.py:13-189."""
-    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant)
     aux = n_aux_channels > 0
 
     def fn(c, inputs):
-        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation, normalization)
+        x, nf = _backbone(c, inputs[0], backbone_block, n_filters, n_blocks, attention, activation, normalization,
+                          dropout_rate, dropout_variant)
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
                      output_activation, localcon_layer, normalization=normalization,
-                     convnext=(backbone_block == 'convnext'))
+                     convnext=(backbone_block == 'convnext'), dropout_rate=dropout_rate)
 
     shapes = [(hr_size[0], hr_size[1], n_channels)]
     if aux:
@@ -439,7 +448,7 @@ def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out
              attention=False, decoder_upsampling='rc', rc_interpolation='bilinear',
              output_activation=None, width_cap=256, localcon_layer=False, math='fp32'):
     """unet_pin -- sp_preups.py:192-315."""
-    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant)
     if decoder_upsampling not in POSTUPSAMPLING_METHODS:
         raise ValueError('`decoder_upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
     if decoder_upsampling == 'rc' and rc_interpolation != 'bilinear':
@@ -457,7 +466,8 @@ def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out
             x = c.maxpool2(y)
             flist.append(nf)
             nf = min(width_cap, nf * 2)
-        x = B.conv_block(c, 'Bottleneck', x, nf, activation)
+        x = B.conv_block(c, 'Bottleneck', x, nf, activation, dropout_rate=dropout_rate,
+                         dropout_variant=dropout_variant)       # sp_preups.py:265-268 (encoder blocks: rate 0, :255)
         for j, skip in enumerate(reversed(skips)):
             nf = flist[::-1][j]
             if decoder_upsampling == 'spc':
@@ -469,8 +479,9 @@ def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out
             x = B.pad_concat(c, x, skip)
             x = B.conv_block(c, 'DecoderConvBlock%d' % (j + 1), x, nf, activation, attention,
                              normalization=normalization)
+        x = c.dropout(x, dropout_rate, dropout_variant)                 # sp_preups.py:287
         return _tail(c, x, inputs[1] if aux else None, n_filters, nf, n_channels_out, activation,
-                     output_activation, localcon_layer, normalization=normalization)
+                     output_activation, localcon_layer, normalization=normalization, dropout_rate=dropout_rate)
 
     shapes = [(hr_size[0], hr_size[1], n_channels)]
     if aux:
@@ -485,7 +496,8 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
                           localcon_layer=False, math='fp32'):
     """recnet_postupsampling -- spt_postups.py:12-163.  Inputs (B,T,h,w,C) [+ (B,H,W,n_aux)];
     output (B,T,H,W,n_channels_out).  Internally frames are time-major (T*B,H,W,C)."""
-    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block)
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant,
+                  dropout_built=False)
     if normalization is not None:
         raise NotImplementedError('normalization in the recurrent (ConvLSTM) networks is not built')
     if backbone_block == 'unet':

@@ -29,6 +29,7 @@ class SpecCtx:
         self.layer_macs = {}     # '<layer>@HxW' -> MACs of that convolution application (as executed)
         self.macs_saved = 0      # reference-graph MACs (fwd) that operator composition does not execute
         self.training = False
+        self.n_dropout = 0
 
     def _reg(self, name, shape):
         shape = tuple(int(s) for s in shape)
@@ -115,6 +116,11 @@ class SpecCtx:
         return SVar(*x.shape)
 
     def gelu(self, x):
+        return x
+
+    def dropout(self, x, rate, variant=None):
+        if rate and rate > 0:
+            self.n_dropout += 1        # applications in graph order = the layer ids of the mask generator
         return x
 
     def channel_attention(self, x, name, r=4, groups=None):

@@ -36,6 +36,8 @@ class Params:
         self.weights = weights
         self.dtype = dtype
         self.training = training        # Keras `training` flag: BatchNormalization batch vs moving statistics
+        self.dropout_mask = None        # callable(call_index, NCHW shape, rate, variant) -> mask tensor (see dropout)
+        self.n_dropout = 0
 
     def get(self, name, shape):
         shape = tuple(int(s) for s in shape)
@@ -169,6 +171,25 @@ def channel_attention_5d(p, name, x5, nf, r=4):
     return x5 * y.unsqueeze(1)              # broadcast over T and H
 
 
+MC_DROPOUT = ('mcdrop', 'mcgaussiandrop', 'mcspatialdrop')
+
+
+def dropout(p, x, rate, variant=None):
+    """get_dropout_layer(rate, variant)(x) -- blocks.py:680-706: identity at rate 0; Dropout / GaussianDropout /
+    SpatialDropout2D act in training mode only, their MC twins always (blocks.py:662-677).  All are ``x * mask``.
+    TensorFlow's random stream cannot be restated, so the mask is SUPPLIED: ``p.dropout_mask(i, shape, rate,
+    variant)`` returns the mask of the i-th dropout application (the parity tests hand over the masks the CUDA
+    generator produced); without a supplier the op only counts itself (spec mode)."""
+    if not rate or rate <= 0:
+        return x
+    if not (p.training or variant in MC_DROPOUT):
+        return x
+    p.n_dropout += 1
+    if p.dropout_mask is None:
+        return x
+    return x * p.dropout_mask(p.n_dropout, tuple(x.shape), rate, variant)
+
+
 def normalize(p, name, x, kind, eps=1e-3):
     """tf.keras.layers.BatchNormalization() / LayerNormalization() on NCHW ``x`` -- blocks.py:63-71.
     Keras defaults: axis=-1 (channels), epsilon=1e-3, BN momentum 0.99, gamma ones / beta zeros.
@@ -199,14 +220,17 @@ def normalize(p, name, x, kind, eps=1e-3):
     return (x - mu.view(1, c, 1, 1)) / torch.sqrt(var.view(1, c, 1, 1) + eps) * gamma + beta
 
 
-def conv_block(p, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3, normalization=None):
-    """ConvBlock.call -- blocks.py:87-103 (dropout_rate=0).  With a normalisation the convolutions carry no
+def conv_block(p, name, x, filters, activation='relu', attention=False, ks1=3, ks2=3, normalization=None,
+               dropout_rate=0, dropout_variant=None):
+    """ConvBlock.call -- blocks.py:87-103.  With a normalisation the convolutions carry no
     bias (blocks.py:37,44,52,58)."""
     nb = normalization is None
-    y = _conv(p, name + '/conv1', x, filters, k=ks1, bias=nb)
+    y = dropout(p, x, dropout_rate, dropout_variant)
+    y = _conv(p, name + '/conv1', y, filters, k=ks1, bias=nb)
     if not nb:
         y = normalize(p, name + '/norm1', y, normalization)
     y = act(y, activation)
+    y = dropout(p, y, dropout_rate, dropout_variant)
     y = _conv(p, name + '/conv2', y, filters, k=ks2, bias=nb)
     if not nb:
         y = normalize(p, name + '/norm2', y, normalization)
@@ -217,13 +241,15 @@ def conv_block(p, name, x, filters, activation='relu', attention=False, ks1=3, k
 
 
 def residual_block(p, name, x, filters, activation='relu', attention=False, use_1x1conv=False,
-                   normalization=None):
+                   normalization=None, dropout_rate=0, dropout_variant=None):
     """ResidualBlock.call -- blocks.py:210-230."""
     nb = normalization is None
-    y = _conv(p, name + '/conv1', x, filters, bias=nb)
+    y = dropout(p, x, dropout_rate, dropout_variant)
+    y = _conv(p, name + '/conv1', y, filters, bias=nb)
     if not nb:
         y = normalize(p, name + '/norm1', y, normalization)
     y = act(y, activation)
+    y = dropout(p, y, dropout_rate, dropout_variant)
     y = _conv(p, name + '/conv2', y, filters, bias=nb)
     if not nb:
         y = normalize(p, name + '/norm2', y, normalization)
@@ -234,7 +260,8 @@ def residual_block(p, name, x, filters, activation='relu', attention=False, use_
     return act(y + x, activation)
 
 
-def dense_block(p, name, x, filters, activation='relu', attention=False, normalization=None):
+def dense_block(p, name, x, filters, activation='relu', attention=False, normalization=None, dropout_rate=0,
+                dropout_variant=None):
     """DenseBlock.call -- blocks.py:262-277.  The pre-activation of X is discarded (:263-267,
     App. B #5): Y = conv3x3(act([norm2](conv1x1(X)))); out = concat([Y, X]).  DenseBlock re-creates conv1 / conv2
     WITH bias (:249-259); norm1 is applied to X and its result dropped, so its gamma / beta exist without a
@@ -245,6 +272,7 @@ def dense_block(p, name, x, filters, activation='relu', attention=False, normali
     if normalization is not None:
         y = normalize(p, name + '/norm2', y, normalization)
     y = act(y, activation)
+    y = dropout(p, y, dropout_rate, dropout_variant)     # dropout2 (:271-272); dropout1's output is dropped (:265-267)
     y = _conv(p, name + '/conv2', y, filters, k=3)
     if attention:
         y = channel_attention(p, name + '/att', y, filters)
@@ -388,7 +416,8 @@ def _nhwc(x):
 
 
 def _tail(p, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation,
-          output_activation, localcon_layer, aux_name='ConvBlock_aux', normalization=None, convnext=False):
+          output_activation, localcon_layer, aux_name='ConvBlock_aux', normalization=None, convnext=False,
+          dropout_rate=0):
     """Shared output module: LCB, aux branch, TransitionLast, two ConvBlocks
     -- sp_postups.py:184-212, sp_preups.py:155-183,291-309."""
     if localcon_layer:
@@ -404,13 +433,14 @@ def _tail(p, x, s_in, init_n_filters, n_filters_aux, n_channels_out, activation,
     ks = 7 if convnext else 3                   # sp_postups.py:121,133: `ks` of the backbone branch
     x = transition_block(p, 'TransitionLast', x, init_n_filters)   # default relu (App. B #9)
     x = conv_block(p, 'ConvBlock_tail', x, init_n_filters, activation=None, attention=True,
-                   normalization=normalization, ks1=ks, ks2=ks)
+                   normalization=normalization, ks1=ks, ks2=ks, dropout_rate=dropout_rate)   # no variant: :206-208
     x = conv_block(p, 'ConvBlock_out', x, n_channels_out, activation=output_activation,
                    normalization=normalization, ks1=ks, ks2=ks)
     return x
 
 
-def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization=None):
+def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization=None,
+              dropout_rate=0, dropout_variant=None):
     """Backbone section shared by net_postupsampling / net_pin -- sp_postups.py:132-168,
     sp_preups.py:116-151."""
     init_n_filters = n_filters
@@ -427,17 +457,19 @@ def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activatio
         n_filters = init_n_filters * (i + 1)
         if backbone_block == 'convnet':
             b = conv_block(p, 'ConvBlock' + str(i + 1), b, n_filters, activation, attention,
-                           normalization=normalization)
+                           normalization=normalization, dropout_rate=dropout_rate, dropout_variant=dropout_variant)
         elif backbone_block == 'resnet':
             b = residual_block(p, 'ResidualBlock' + str(i + 1), b, n_filters, activation,
-                               attention, use_1x1conv=(i != 0), normalization=normalization)
+                               attention, use_1x1conv=(i != 0), normalization=normalization,
+                               dropout_rate=dropout_rate, dropout_variant=dropout_variant)
         elif backbone_block == 'densenet':
             b = dense_block(p, 'DenseBlock' + str(i + 1), b, n_filters, activation, attention,
-                            normalization=normalization)
+                            normalization=normalization, dropout_rate=dropout_rate, dropout_variant=dropout_variant)
             b = transition_block(p, 'Transition' + str(i + 1), b, b.shape[1] // 2)
         else:
             raise NotImplementedError(backbone_block)
     b = act(_conv(p, 'backbone_last', b, n_filters), activation)
+    b = dropout(p, b, dropout_rate, dropout_variant)                # sp_postups.py:158
     if backbone_block == 'convnet':
         x = b
     elif backbone_block == 'resnet':
@@ -451,12 +483,14 @@ def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activatio
 
 def net_postupsampling(p, inputs, backbone_block, upsampling, scale, n_channels_out=1,
                        n_filters=8, n_blocks=6, attention=False, activation='relu',
-                       output_activation=None, localcon_layer=False, normalization=None):
+                       output_activation=None, localcon_layer=False, normalization=None, dropout_rate=0,
+                       dropout_variant=None):
     """net_postupsampling -- sp_postups.py:14-217.  inputs: [x_lr NHWC] or [x_lr, s_hr]."""
     x_in = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
     init_n_filters = n_filters
-    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization)
+    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization,
+                             dropout_rate, dropout_variant)
     if upsampling == 'spc':
         x = subpixel_block(p, 'SubpixelConvolution', x, scale, n_filters)
     elif upsampling == 'rc':
@@ -466,21 +500,22 @@ def net_postupsampling(p, inputs, backbone_block, upsampling, scale, n_channels_
         x = deconv_block(p, 'Deconvolution', x, scale, n_filters, activation)
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
               output_activation, localcon_layer, normalization=normalization,
-              convnext=(backbone_block == 'convnext'))
+              convnext=(backbone_block == 'convnext'), dropout_rate=dropout_rate)
     return _nhwc(x)
 
 
 def net_pin(p, inputs, backbone_block, n_channels_out=1, n_filters=8, n_blocks=6,
             attention=False, activation='relu', output_activation=None, localcon_layer=False,
-            normalization=None):
+            normalization=None, dropout_rate=0, dropout_variant=None):
     """net_pin -- sp_preups.py:13-189."""
     x_in = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
     init_n_filters = n_filters
-    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization)
+    x, n_filters = _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activation, normalization,
+                             dropout_rate, dropout_variant)
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
               output_activation, localcon_layer, normalization=normalization,
-              convnext=(backbone_block == 'convnext'))
+              convnext=(backbone_block == 'convnext'), dropout_rate=dropout_rate)
     return _nhwc(x)
 
 
@@ -493,7 +528,7 @@ def check_nblocks(shape, power):
 
 def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu',
              attention=False, decoder_upsampling='rc', output_activation=None, width_cap=256,
-             localcon_layer=False, normalization=None):
+             localcon_layer=False, normalization=None, dropout_rate=0, dropout_variant=None):
     """unet_pin -- sp_preups.py:192-315 (the bottleneck block is never normalised, :266-268)."""
     x = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
@@ -507,7 +542,8 @@ def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu'
         x = maxpool2(y)
         flist.append(n_filters)
         n_filters = min(width_cap, n_filters * 2)
-    x = conv_block(p, 'Bottleneck', x, n_filters, activation)
+    x = conv_block(p, 'Bottleneck', x, n_filters, activation, dropout_rate=dropout_rate,
+                   dropout_variant=dropout_variant)       # encoder blocks get rate 0 (sp_preups.py:255)
     flist = flist[::-1]
     for j, skip in enumerate(reversed(skips)):
         n_filters = flist[j]
@@ -520,8 +556,9 @@ def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu'
         x = pad_concat(x, skip)
         x = conv_block(p, 'DecoderConvBlock%d' % (j + 1), x, n_filters, activation, attention,
                        normalization=normalization)
+    x = dropout(p, x, dropout_rate, dropout_variant)          # sp_preups.py:287
     x = _tail(p, x, s_in, init_n_filters, n_filters, n_channels_out, activation,
-              output_activation, localcon_layer, normalization=normalization)
+              output_activation, localcon_layer, normalization=normalization, dropout_rate=dropout_rate)
     return _nhwc(x)
 
 

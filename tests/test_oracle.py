@@ -194,8 +194,10 @@ def test_model_names_and_unsupported():
         nets.net_postupsampling('convnext', 'spc', 4, 1, 0, (8, 8))
     with pytest.raises(NotImplementedError):
         nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), activation='elu')
+    with pytest.raises(ValueError):
+        nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), dropout_rate=0.2, dropout_variant='alpha')
     with pytest.raises(NotImplementedError):
-        nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), dropout_rate=0.2)
+        nets.recnet_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), 3, dropout_rate=0.2)
 
 
 def test_recnet_pin_structure():
