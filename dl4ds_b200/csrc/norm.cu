@@ -7,6 +7,7 @@
 // layer norm reads x once per pass; batch norm needs the batch statistics first (two passes: mean, then centred
 // second moment) and, backward, two per-channel sums before the element-wise pass.
 #include <algorithm>
+#include <initializer_list>
 
 #include "common.cuh"
 
@@ -314,6 +315,245 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// float4 variants (C % 4 == 0, pitches % 4 == 0, 16-byte aligned pointers): one lane = four consecutive channels.
+// Batch norm: Q = C/4 lanes per pixel, 256/Q pixels per block step (per-channel constants in registers).
+// Layer norm: G = next power of two >= Q lanes per pixel (C <= 128) so the per-pixel sums are xor-shuffles.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 act4(float4 v, int act) {
+    return make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act), apply_act(v.w, act));
+}
+__device__ __forceinline__ float4 actgrad4(float4 dy, float4 y, int act) {
+    return make_float4(dy.x * act_grad_from_out(y.x, act), dy.y * act_grad_from_out(y.y, act),
+                       dy.z * act_grad_from_out(y.z, act), dy.w * act_grad_from_out(y.w, act));
+}
+
+template <int NACC>
+__device__ __forceinline__ void flush_quad_sums(const float4 (&acc)[NACC], int q, bool on, int C, float* sh,
+                                                float* const (&dst)[NACC]) {
+    for (int i = threadIdx.x; i < NACC * 256; i += kThreads) sh[i] = 0.0f;
+    __syncthreads();
+    if (on) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            atomicAdd(sh + a * 256 + 4 * q + 0, acc[a].x);
+            atomicAdd(sh + a * 256 + 4 * q + 1, acc[a].y);
+            atomicAdd(sh + a * 256 + 4 * q + 2, acc[a].z);
+            atomicAdd(sh + a * 256 + 4 * q + 3, acc[a].w);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NACC * 256; i += kThreads) {
+        const int a = i / 256, c = i % 256;
+        if (c < C) atomicAdd(dst[a] + c, sh[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bn_stats_v4_kernel(const float* __restrict__ x, int x_ld, int64_t n_pix,
+                                                               int C, float* __restrict__ sums, int pass) {
+    __shared__ float sh[256];
+    const int Q = C >> 2, rows = kThreads / Q, q = threadIdx.x % Q, row = threadIdx.x / Q;
+    const bool on = row < rows;
+    float4 acc[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pass == 1) {
+        const float inv = 1.0f / (float)n_pix;
+        mu = make_float4(sums[4 * q] * inv, sums[4 * q + 1] * inv, sums[4 * q + 2] * inv, sums[4 * q + 3] * inv);
+    }
+    if (on) {
+        for (int64_t p = (int64_t)blockIdx.x * rows + row; p < n_pix; p += (int64_t)gridDim.x * rows) {
+            const float4 v = ld4(x + p * x_ld + 4 * q);
+            const float dx = v.x - mu.x, dy = v.y - mu.y, dz = v.z - mu.z, dw = v.w - mu.w;
+            if (pass == 0) { acc[0].x += dx; acc[0].y += dy; acc[0].z += dz; acc[0].w += dw; }
+            else { acc[0].x = fmaf(dx, dx, acc[0].x); acc[0].y = fmaf(dy, dy, acc[0].y);
+                   acc[0].z = fmaf(dz, dz, acc[0].z); acc[0].w = fmaf(dw, dw, acc[0].w); }
+        }
+    }
+    float* const dst[1] = {sums + (pass == 0 ? 0 : C)};
+    flush_quad_sums<1>(acc, q, on, C, sh, dst);
+}
+
+__global__ void __launch_bounds__(kThreads) norm_apply_v4_kernel(const float* __restrict__ x, int x_ld,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ var,
+                                                                 const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps,
+                                                                 float* __restrict__ y, int y_ld, int64_t n_pix,
+                                                                 int C, int act) {
+    const int Q = C >> 2, rows = kThreads / Q, q = threadIdx.x % Q, row = threadIdx.x / Q;
+    if (row >= rows) return;
+    float a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = 4 * q + k;
+        a[k] = gamma[c] * rsqrtf(var[c] + eps);
+        b[k] = beta[c] - mean[c] * a[k];
+    }
+    for (int64_t p = (int64_t)blockIdx.x * rows + row; p < n_pix; p += (int64_t)gridDim.x * rows) {
+        const float4 v = ld4(x + p * x_ld + 4 * q);
+        st4(y + p * y_ld + 4 * q, act4(make_float4(fmaf(v.x, a[0], b[0]), fmaf(v.y, a[1], b[1]), fmaf(v.z, a[2], b[2]),
+                                                   fmaf(v.w, a[3], b[3])), act));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_v4_kernel(const float* __restrict__ dy, int dy_ld,
+                                                                    const float* __restrict__ x, int x_ld,
+                                                                    const float* __restrict__ y, int y_ld,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ var, float eps,
+                                                                    int64_t n_pix, int C, int act,
+                                                                    float* __restrict__ sums) {
+    __shared__ float sh[2 * 256];
+    const int Q = C >> 2, rows = kThreads / Q, q = threadIdx.x % Q, row = threadIdx.x / Q;
+    const bool on = row < rows;
+    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    const float4 mu = ld4(mean + 4 * q);
+    const float4 vr = ld4(var + 4 * q);
+    const float4 rs = make_float4(rsqrtf(vr.x + eps), rsqrtf(vr.y + eps), rsqrtf(vr.z + eps), rsqrtf(vr.w + eps));
+    if (on) {
+        for (int64_t p = (int64_t)blockIdx.x * rows + row; p < n_pix; p += (int64_t)gridDim.x * rows) {
+            float4 dz = ld4(dy + p * dy_ld + 4 * q);
+            if (act != DL4DS_ACT_NONE) dz = actgrad4(dz, ld4(y + p * y_ld + 4 * q), act);
+            const float4 v = ld4(x + p * x_ld + 4 * q);
+            acc[0].x += dz.x; acc[0].y += dz.y; acc[0].z += dz.z; acc[0].w += dz.w;
+            acc[1].x = fmaf(dz.x, (v.x - mu.x) * rs.x, acc[1].x);
+            acc[1].y = fmaf(dz.y, (v.y - mu.y) * rs.y, acc[1].y);
+            acc[1].z = fmaf(dz.z, (v.z - mu.z) * rs.z, acc[1].z);
+            acc[1].w = fmaf(dz.w, (v.w - mu.w) * rs.w, acc[1].w);
+        }
+    }
+    float* const dst[2] = {sums, sums + C};
+    flush_quad_sums<2>(acc, q, on, C, sh, dst);
+}
+
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_v4_kernel(const float* __restrict__ dy, int dy_ld,
+                                                                   const float* __restrict__ x, int x_ld,
+                                                                   const float* __restrict__ y, int y_ld,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ var,
+                                                                   const float* __restrict__ gamma, float eps,
+                                                                   float* __restrict__ dx, int dx_ld, int64_t n_pix,
+                                                                   int C, int act, const float* __restrict__ sums,
+                                                                   float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta) {
+    const int Q = C >> 2, rows = kThreads / Q, q = threadIdx.x % Q, row = threadIdx.x / Q;
+    if (blockIdx.x == 0 && dgamma) {
+        for (int c = threadIdx.x; c < C; c += kThreads) {
+            dbeta[c] += sums[c];
+            dgamma[c] += sums[C + c];
+        }
+    }
+    if (row >= rows) return;
+    const float invM = 1.0f / (float)n_pix;
+    float mu[4], rs[4], ga[4], m1[4], m2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = 4 * q + k;
+        mu[k] = mean[c];
+        rs[k] = rsqrtf(var[c] + eps);
+        ga[k] = gamma[c] * rs[k];
+        m1[k] = sums[c] * invM;
+        m2[k] = sums[C + c] * invM;
+    }
+    for (int64_t p = (int64_t)blockIdx.x * rows + row; p < n_pix; p += (int64_t)gridDim.x * rows) {
+        float4 dz = ld4(dy + p * dy_ld + 4 * q);
+        if (act != DL4DS_ACT_NONE) dz = actgrad4(dz, ld4(y + p * y_ld + 4 * q), act);
+        const float4 v = ld4(x + p * x_ld + 4 * q);
+        st4(dx + p * dx_ld + 4 * q,
+            make_float4(ga[0] * (dz.x - m1[0] - (v.x - mu[0]) * rs[0] * m2[0]),
+                        ga[1] * (dz.y - m1[1] - (v.y - mu[1]) * rs[1] * m2[1]),
+                        ga[2] * (dz.z - m1[2] - (v.z - mu[2]) * rs[2] * m2[2]),
+                        ga[3] * (dz.w - m1[3] - (v.w - mu[3]) * rs[3] * m2[3])));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) ln_fwd_v4_kernel(const float* __restrict__ x, int x_ld,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             float* __restrict__ y, int y_ld, int64_t n_pix, int C,
+                                                             int G, int act) {
+    const int lane = threadIdx.x % G, row = threadIdx.x / G, rows = kThreads / G;
+    const bool has = 4 * lane < C;
+    const float invC = 1.0f / (float)C;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 ga = has ? ld4(gamma + 4 * lane) : z, be = has ? ld4(beta + 4 * lane) : z;
+    for (int64_t base = (int64_t)blockIdx.x * rows; base < n_pix; base += (int64_t)gridDim.x * rows) {
+        const int64_t p = base + row;
+        const bool live = has && p < n_pix;
+        const float4 v = live ? ld4(x + p * x_ld + 4 * lane) : z;
+        const float mu = group_sum(v.x + v.y + v.z + v.w, G) * invC;
+        const float4 d = has ? make_float4(v.x - mu, v.y - mu, v.z - mu, v.w - mu) : z;
+        const float rstd = rsqrtf(group_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w, G) * invC + eps);
+        if (live)
+            st4(y + p * y_ld + 4 * lane, act4(make_float4(fmaf(d.x * rstd, ga.x, be.x), fmaf(d.y * rstd, ga.y, be.y),
+                                                          fmaf(d.z * rstd, ga.z, be.z), fmaf(d.w * rstd, ga.w, be.w)),
+                                              act));
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) ln_bwd_v4_kernel(const float* __restrict__ dy, int dy_ld,
+                                                             const float* __restrict__ x, int x_ld,
+                                                             const float* __restrict__ y, int y_ld,
+                                                             const float* __restrict__ gamma, float eps,
+                                                             float* __restrict__ dx, int dx_ld,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             int64_t n_pix, int C, int G, int act) {
+    __shared__ float sh[2 * 256];
+    const int lane = threadIdx.x % G, row = threadIdx.x / G, rows = kThreads / G;
+    const bool has = 4 * lane < C;
+    const float invC = 1.0f / (float)C;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 ga = has ? ld4(gamma + 4 * lane) : z;
+    float4 acc[2] = {z, z};
+    for (int64_t base = (int64_t)blockIdx.x * rows; base < n_pix; base += (int64_t)gridDim.x * rows) {
+        const int64_t p = base + row;
+        const bool live = has && p < n_pix;
+        const float4 v = live ? ld4(x + p * x_ld + 4 * lane) : z;
+        float4 dz = live ? ld4(dy + p * dy_ld + 4 * lane) : z;
+        if (live && act != DL4DS_ACT_NONE) dz = actgrad4(dz, ld4(y + p * y_ld + 4 * lane), act);
+        const float mu = group_sum(v.x + v.y + v.z + v.w, G) * invC;
+        const float4 d = has ? make_float4(v.x - mu, v.y - mu, v.z - mu, v.w - mu) : z;
+        const float rstd = rsqrtf(group_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w, G) * invC + eps);
+        const float4 xh = make_float4(d.x * rstd, d.y * rstd, d.z * rstd, d.w * rstd);
+        acc[0].x += dz.x; acc[0].y += dz.y; acc[0].z += dz.z; acc[0].w += dz.w;
+        acc[1].x = fmaf(dz.x, xh.x, acc[1].x); acc[1].y = fmaf(dz.y, xh.y, acc[1].y);
+        acc[1].z = fmaf(dz.z, xh.z, acc[1].z); acc[1].w = fmaf(dz.w, xh.w, acc[1].w);
+        const float4 g = make_float4(dz.x * ga.x, dz.y * ga.y, dz.z * ga.z, dz.w * ga.w);
+        const float m1 = group_sum(g.x + g.y + g.z + g.w, G) * invC;
+        const float m2 = group_sum(g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w, G) * invC;
+        if (live && dx)
+            st4(dx + p * dx_ld + 4 * lane, make_float4(rstd * (g.x - m1 - xh.x * m2), rstd * (g.y - m1 - xh.y * m2),
+                                                       rstd * (g.z - m1 - xh.z * m2), rstd * (g.w - m1 - xh.w * m2)));
+    }
+    if (dgamma) {
+        float* const dst[2] = {dbeta, dgamma};
+        flush_quad_sums<2>(acc, lane, has, C, sh, dst);
+    }
+}
+
+bool vec4_ok(int C, std::initializer_list<int> lds, std::initializer_list<const void*> ptrs) {
+    if (C % 4) return false;
+    for (int ld : lds)
+        if (ld % 4) return false;
+    for (const void* p : ptrs)
+        if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+    return true;
+}
+
+int grid_quads(int64_t n_pix, int lanes_per_pixel, int max_blocks) {
+    const int rows = kThreads / lanes_per_pixel;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n_pix, (int64_t)rows * 2), max_blocks));
+}
+
+int ln_group(int C) {      // lanes per pixel for the float4 layer norm, 0 if it does not apply
+    if (C % 4 || C > 128) return 0;
+    int g = 1;
+    while (4 * g < C) g <<= 1;
+    return g;
+}
+
 int grid_rows(int64_t n_pix, int G) {
     const int rows = kThreads / G;
     const int64_t blocks = cdiv(n_pix, (int64_t)rows * 4);
@@ -342,8 +582,14 @@ int dl4ds_batchnorm_stats(const float* x, int x_ld, int64_t n_pix, int C, float*
     cudaStream_t st = as_stream(stream);
     const int G = group_width(C), grid = grid_rows(n_pix, G);
     cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), st);
-    bn_stats_kernel<<<grid, kThreads, 0, st>>>(x, x_ld, n_pix, C, G, ws, 0);
-    bn_stats_kernel<<<grid, kThreads, 0, st>>>(x, x_ld, n_pix, C, G, ws, 1);
+    if (vec4_ok(C, {x_ld}, {x})) {
+        const int g4 = grid_quads(n_pix, C / 4, 4 * kNumSMs);
+        bn_stats_v4_kernel<<<g4, kThreads, 0, st>>>(x, x_ld, n_pix, C, ws, 0);
+        bn_stats_v4_kernel<<<g4, kThreads, 0, st>>>(x, x_ld, n_pix, C, ws, 1);
+    } else {
+        bn_stats_kernel<<<grid, kThreads, 0, st>>>(x, x_ld, n_pix, C, G, ws, 0);
+        bn_stats_kernel<<<grid, kThreads, 0, st>>>(x, x_ld, n_pix, C, G, ws, 1);
+    }
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, (float)n_pix, mean, var, moving_mean, moving_var,
                                                         momentum);
     return check_launch("batchnorm_stats");
@@ -355,8 +601,12 @@ int dl4ds_norm_apply(const float* x, int x_ld, const float* mean, const float* v
     NORM_CHECK("norm_apply");
     DL4DS_REQUIRE(x && mean && var && gamma && beta && y, DL4DS_E_BADARG, "norm_apply: null pointer");
     const int G = group_width(C);
-    norm_apply_kernel<<<grid_rows(n_pix, G), kThreads, 0, as_stream(stream)>>>(x, x_ld, mean, var, gamma, beta, eps,
-                                                                                y, y_ld, n_pix, C, G, act);
+    if (vec4_ok(C, {x_ld, y_ld}, {x, y}))
+        norm_apply_v4_kernel<<<grid_quads(n_pix, C / 4, 16 * kNumSMs), kThreads, 0, as_stream(stream)>>>(
+            x, x_ld, mean, var, gamma, beta, eps, y, y_ld, n_pix, C, act);
+    else
+        norm_apply_kernel<<<grid_rows(n_pix, G), kThreads, 0, as_stream(stream)>>>(x, x_ld, mean, var, gamma, beta,
+                                                                                    eps, y, y_ld, n_pix, C, G, act);
     return check_launch("norm_apply");
 }
 
@@ -371,6 +621,13 @@ int dl4ds_batchnorm_bwd(const float* dy, int dy_ld, const float* x, int x_ld, co
     cudaStream_t st = as_stream(stream);
     const int G = group_width(C), grid = grid_rows(n_pix, G);
     cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(float), st);
+    if (vec4_ok(C, {dy_ld, x_ld, y_ld, dx_ld}, {dy, x, y, dx, mean, var})) {
+        bn_bwd_reduce_v4_kernel<<<grid_quads(n_pix, C / 4, 4 * kNumSMs), kThreads, 0, st>>>(
+            dy, dy_ld, x, x_ld, y, y_ld, mean, var, eps, n_pix, C, act, ws);
+        bn_bwd_apply_v4_kernel<<<grid_quads(n_pix, C / 4, 16 * kNumSMs), kThreads, 0, st>>>(
+            dy, dy_ld, x, x_ld, y, y_ld, mean, var, gamma, eps, dx, dx_ld, n_pix, C, act, ws, dgamma, dbeta);
+        return check_launch("batchnorm_bwd");
+    }
     bn_bwd_reduce_kernel<<<grid, kThreads, 0, st>>>(dy, dy_ld, x, x_ld, y, y_ld, mean, var, eps, n_pix, C, G, act, ws);
     bn_bwd_apply_kernel<<<grid, kThreads, 0, st>>>(dy, dy_ld, x, x_ld, y, y_ld, mean, var, gamma, eps, dx, dx_ld,
                                                    n_pix, C, G, act, ws, dgamma, dbeta);
@@ -382,8 +639,13 @@ int dl4ds_layernorm_fwd(const float* x, int x_ld, const float* gamma, const floa
     NORM_CHECK("layernorm_fwd");
     DL4DS_REQUIRE(x && gamma && beta && y, DL4DS_E_BADARG, "layernorm_fwd: null pointer");
     const int G = group_width(C);
-    ln_fwd_kernel<<<grid_rows(n_pix, G), kThreads, 0, as_stream(stream)>>>(x, x_ld, gamma, beta, eps, y, y_ld, n_pix,
-                                                                            C, G, act);
+    const int g4 = ln_group(C);
+    if (g4 && vec4_ok(C, {x_ld, y_ld}, {x, y, gamma, beta}))
+        ln_fwd_v4_kernel<<<grid_quads(n_pix, g4, 16 * kNumSMs), kThreads, 0, as_stream(stream)>>>(
+            x, x_ld, gamma, beta, eps, y, y_ld, n_pix, C, g4, act);
+    else
+        ln_fwd_kernel<<<grid_rows(n_pix, G), kThreads, 0, as_stream(stream)>>>(x, x_ld, gamma, beta, eps, y, y_ld,
+                                                                                n_pix, C, G, act);
     return check_launch("layernorm_fwd");
 }
 
@@ -396,8 +658,14 @@ int dl4ds_layernorm_bwd(const float* dy, int dy_ld, const float* x, int x_ld, co
     DL4DS_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), DL4DS_E_BADARG,
                   "layernorm_bwd: dgamma / dbeta must come together");
     const int G = group_width(C);
-    ln_bwd_kernel<<<grid_rows(n_pix, G), kThreads, 0, as_stream(stream)>>>(dy, dy_ld, x, x_ld, y, y_ld, gamma, eps, dx,
-                                                                            dx_ld, dgamma, dbeta, n_pix, C, G, act);
+    const int g4 = ln_group(C);
+    if (g4 && vec4_ok(C, {dy_ld, x_ld, y_ld, dx_ld}, {dy, x, y, dx, gamma}))
+        ln_bwd_v4_kernel<<<grid_quads(n_pix, g4, 4 * kNumSMs), kThreads, 0, as_stream(stream)>>>(
+            dy, dy_ld, x, x_ld, y, y_ld, gamma, eps, dx, dx_ld, dgamma, dbeta, n_pix, C, g4, act);
+    else
+        ln_bwd_kernel<<<grid_rows(n_pix, G), kThreads, 0, as_stream(stream)>>>(dy, dy_ld, x, x_ld, y, y_ld, gamma, eps,
+                                                                                dx, dx_ld, dgamma, dbeta, n_pix, C, G,
+                                                                                act);
     return check_launch("layernorm_bwd");
 }
 
