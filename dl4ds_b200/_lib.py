@@ -49,7 +49,7 @@ SIGNATURES = {
     'dl4ds_depthwise_conv_wgrad': ('i', 'pipipiiiiip'),
     'dl4ds_gelu_fwd': ('i', 'pplp'),
     'dl4ds_gelu_bwd': ('i', 'ppplp'),
-    'dl4ds_dropout': ('i', 'pipillifipip'),
+    'dl4ds_dropout': ('i', 'pipilliifipip'),
     'dl4ds_rng_advance': ('i', 'pp'),
     'dl4ds_adam_step': ('i', 'pppplffffifp'),
     'dl4ds_adam_step_dev': ('i', 'pppplpffffp'),

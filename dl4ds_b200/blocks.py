@@ -151,11 +151,19 @@ def deconv_block(c, name, x, scale, n_filters, output_activation=None):
     return x
 
 
-def recurrent_conv_block(c, name, x, filters, T, activation='relu'):
-    """RecurrentConvBlock.call -- blocks.py:380-398: ConvLSTM2D 5x5 -> act -> ConvLSTM2D 3x3 -> act.
-    ``x`` holds time-major frames (T*B, H, W, C)."""
-    y = c.act(c.convlstm(x, name + '/convlstm1', filters, 5, T), activation)
-    y = c.act(c.convlstm(y, name + '/convlstm2', filters, 3, T), activation)
+def recurrent_conv_block(c, name, x, filters, T, activation='relu', normalization=None, dropout_rate=0,
+                         dropout_variant=None):
+    """RecurrentConvBlock.call -- blocks.py:380-398: [drop] -> ConvLSTM2D 5x5 -> [norm1] -> act -> [drop] ->
+    ConvLSTM2D 3x3 -> [norm2] -> act.  ``x`` holds time-major frames (T*B, H, W, C): batch norm over (B,T,H,W) and
+    layer norm over C are the same reductions on the folded tensor; the dropout layers are the ``dim=3`` ones
+    (:371-374: the spatial variant draws per sample and channel over (T,H,W))."""
+    bsz = x.N // T
+    y = c.dropout(x, dropout_rate, dropout_variant, n_samples=bsz)
+    y = c.convlstm(y, name + '/convlstm1', filters, 5, T)
+    y = c.norm(y, name + '/norm1', normalization, act=activation) if normalization else c.act(y, activation)
+    y = c.dropout(y, dropout_rate, dropout_variant, n_samples=bsz)
+    y = c.convlstm(y, name + '/convlstm2', filters, 3, T)
+    y = c.norm(y, name + '/norm2', normalization, act=activation) if normalization else c.act(y, activation)
     return y
 
 

@@ -27,10 +27,11 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0
 
 // variant 0: Dropout -- keep where u >= rate, scale 1/(1-rate)
 //         1: GaussianDropout -- multiply by N(1, sqrt(rate / (1 - rate)))
-//         2: SpatialDropout2D -- as 0 with one draw per (sample, channel)
+//         2: SpatialDropout2D / 3D -- as 0 with one draw per (sample, channel); sample = (pixel / pix_per_sample) %
+//            n_samples, so time-major frame stacks (T*B, H, W, C) share the draw over T as SpatialDropout3D does
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
-                                                      int y_ld, int64_t n_pix, int64_t pix_per_sample, int C,
-                                                      float rate, int variant,
+                                                      int y_ld, int64_t n_pix, int64_t pix_per_sample, int n_samples,
+                                                      int C, float rate, int variant,
                                                       const unsigned long long* __restrict__ state, int layer_id) {
     const unsigned long long seed = state[0], step = state[1];
     const float scale = 1.0f / (1.0f - rate);
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = i / C;
         const int c = (int)(i - p * C);
-        const unsigned long long idx = variant == 2 ? (unsigned long long)(p / pix_per_sample) * C + c
+        const unsigned long long idx = variant == 2 ? (unsigned long long)((p / pix_per_sample) % n_samples) * C + c
                                                     : (unsigned long long)i;
         uint32_t ctr[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)layer_id, (uint32_t)step};
         philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
@@ -65,16 +66,17 @@ using namespace dl4ds;
 
 extern "C" {
 
-int dl4ds_dropout(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, int64_t pix_per_sample, int C,
-                  float rate, int variant, const uint64_t* rng_state, int layer_id, void* stream) {
+int dl4ds_dropout(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, int64_t pix_per_sample, int n_samples,
+                  int C, float rate, int variant, const uint64_t* rng_state, int layer_id, void* stream) {
     DL4DS_REQUIRE(x && y && rng_state, DL4DS_E_BADARG, "dropout: null pointer");
-    DL4DS_REQUIRE(n_pix > 0 && C > 0 && pix_per_sample > 0 && n_pix % pix_per_sample == 0, DL4DS_E_SHAPE,
-                  "dropout: bad shape");
+    DL4DS_REQUIRE(n_pix > 0 && C > 0 && pix_per_sample > 0 && n_pix % pix_per_sample == 0 && n_samples > 0,
+                  DL4DS_E_SHAPE, "dropout: bad shape");
     DL4DS_REQUIRE(rate > 0.0f && rate < 1.0f, DL4DS_E_BADARG, "dropout: rate must be in (0, 1)");
     DL4DS_REQUIRE(variant >= 0 && variant <= 2, DL4DS_E_BADARG, "dropout: variant must be 0, 1 or 2");
     const int64_t n = n_pix * C;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256 * 4), 8 * kNumSMs));
-    dropout_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_ld, y, y_ld, n_pix, pix_per_sample, C, rate, variant,
+    dropout_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_ld, y, y_ld, n_pix, pix_per_sample, n_samples, C, rate,
+                                                        variant,
                                                         reinterpret_cast<const unsigned long long*>(rng_state),
                                                         layer_id);
     return check_launch("dropout");

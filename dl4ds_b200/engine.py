@@ -757,10 +757,12 @@ class Ctx:
         self._record(bwd)
         return out
 
-    def dropout(self, x, rate, variant=None):
+    def dropout(self, x, rate, variant=None, n_samples=None):
         """get_dropout_layer(rate, variant)(x) -- blocks.py:680-706: Dropout / GaussianDropout / SpatialDropout2D,
         active in training mode; the 'mc*' variants also in inference (blocks.py:662-677).  Masks: dl4ds_dropout
-        (Philox, seed and step in device memory); the backward pass regenerates the same mask."""
+        (Philox, seed and step in device memory); the backward pass regenerates the same mask.  ``n_samples``: batch
+        size B when ``x`` holds time-major frames (T*B,H,W,C), so that the spatial variant draws once per sample and
+        channel over (T,H,W) like SpatialDropout3D (``dim=3``, blocks.py:692-693,701-702)."""
         if variant is not None and variant not in DROPOUT_KIND:
             raise ValueError('`dropout_variant` must be None or one of %s, got %s' % (sorted(k for k in DROPOUT_KIND if k), variant))
         if not rate or rate <= 0:
@@ -773,8 +775,9 @@ class Ctx:
             self._rng_advanced = True
         self._dropout_calls += 1
         lid, kind = self._dropout_calls, DROPOUT_KIND[variant]
+        ns = int(n_samples) if n_samples else x.N
         out = x.like()
-        self._call('dl4ds_dropout', x.ptr, x.ld, out.ptr, out.ld, x.npix, x.H * x.W, x.C, float(rate), kind,
+        self._call('dl4ds_dropout', x.ptr, x.ld, out.ptr, out.ld, x.npix, x.H * x.W, ns, x.C, float(rate), kind,
                    state.data_ptr(), lid, _stream())
 
         def bwd():
@@ -783,8 +786,8 @@ class Ctx:
                 return
 
             def wr(dst):
-                self._call('dl4ds_dropout', dy.ptr, dy.ld, dst.ptr, dst.ld, x.npix, x.H * x.W, x.C, float(rate), kind,
-                           state.data_ptr(), lid, _stream())
+                self._call('dl4ds_dropout', dy.ptr, dy.ld, dst.ptr, dst.ld, x.npix, x.H * x.W, ns, x.C, float(rate),
+                           kind, state.data_ptr(), lid, _stream())
             self._acc_via_tmp(x, wr)
             out.grad = None
         self._record(bwd)

@@ -496,10 +496,7 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
                           localcon_layer=False, math='fp32'):
     """recnet_postupsampling -- spt_postups.py:12-163.  Inputs (B,T,h,w,C) [+ (B,H,W,n_aux)];
     output (B,T,H,W,n_channels_out).  Internally frames are time-major (T*B,H,W,C)."""
-    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant,
-                  dropout_built=False)
-    if normalization is not None:
-        raise NotImplementedError('normalization in the recurrent (ConvLSTM) networks is not built')
+    _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant)
     if backbone_block == 'unet':
         raise ValueError('unet backbone is not compatible with post-upsampling')
     if upsampling not in POSTUPSAMPLING_METHODS + ('pin',):
@@ -511,9 +508,12 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
     def fn(c, inputs):
         x_in = inputs[0]
         bsz = x_in.N // T
-        x = b = B.recurrent_conv_block(c, 'RecurrentConvBlock1', x_in, n_filters, T, activation)
+        nz = normalization
+        x = b = B.recurrent_conv_block(c, 'RecurrentConvBlock1', x_in, n_filters, T, activation, nz)
         for i in range(n_blocks):
-            b = B.recurrent_conv_block(c, 'RecurrentConvBlock%d' % (i + 2), b, n_filters, T, activation)
+            b = B.recurrent_conv_block(c, 'RecurrentConvBlock%d' % (i + 2), b, n_filters, T, activation, nz,
+                                       dropout_rate, dropout_variant)
+        b = c.dropout(b, dropout_rate, dropout_variant, n_samples=bsz)      # dim=3 layer, spt_postups.py:113
         if backbone_block == 'convnet':
             x = b
         elif backbone_block == 'resnet':
@@ -542,12 +542,20 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
         x = B.transition_block(c, 'TransitionLast', x, n_filters if upsampling == 'pin' else x.C // 2)
         # ConvBlock(n_filters, activation=None, attention=True) on the 5-D tensor: the attention's
         # reduce_mean over axes [1,2] pools (T,H) and keeps W (blocks.py:587)
-        y = c.conv(x, 'ConvBlock_tail/conv1', n_filters)
-        y = c.conv(y, 'ConvBlock_tail/conv2', n_filters)
+        # (with dropout_rate > 0: plain Dropout in front of each convolution -- the variant is not passed, :152-153;
+        #  with a normalisation: bias-free convolutions, each followed by the normalisation)
+        y = c.dropout(x, dropout_rate)
+        y = c.conv(y, 'ConvBlock_tail/conv1', n_filters, bias=nz is None)
+        if nz:
+            y = c.norm(y, 'ConvBlock_tail/norm1', nz)
+        y = c.dropout(y, dropout_rate)
+        y = c.conv(y, 'ConvBlock_tail/conv2', n_filters, bias=nz is None)
+        if nz:
+            y = c.norm(y, 'ConvBlock_tail/norm2', nz)
         yb = c.permute_frames(y, T, bsz)                       # batch-major (B*T,H,W,C)
         yb = c.channel_attention(yb, 'ConvBlock_tail/att', groups=(bsz * y.W, T * y.H, y.W))
         y = c.permute_frames(yb, bsz, T)                       # back to time-major
-        return B.conv_block(c, 'ConvBlock_out', y, n_channels_out, activation=output_activation)
+        return B.conv_block(c, 'ConvBlock_out', y, n_channels_out, activation=output_activation, normalization=nz)
 
     shapes = [(T, h_lr, w_lr, n_channels)]
     if aux:

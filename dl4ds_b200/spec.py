@@ -118,7 +118,7 @@ class SpecCtx:
     def gelu(self, x):
         return x
 
-    def dropout(self, x, rate, variant=None):
+    def dropout(self, x, rate, variant=None, n_samples=None):
         if rate and rate > 0:
             self.n_dropout += 1        # applications in graph order = the layer ids of the mask generator
         return x

@@ -237,14 +237,15 @@ int dl4ds_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* 
 /* ---------------------------------------------------------------------------------------------
  * Dropout variants -- blocks.py:659-706 (`get_dropout_layer`) applied at blocks.py:89,95-96,211-214,219-220,
  * 265-266,271-272 and sp_postups.py:158.  variant 0 = Dropout (keep where u >= rate, scale 1/(1-rate)),
- * 1 = GaussianDropout (x * N(1, sqrt(rate/(1-rate)))), 2 = SpatialDropout2D (one draw per sample and channel).
+ * 1 = GaussianDropout (x * N(1, sqrt(rate/(1-rate)))), 2 = SpatialDropout2D / 3D (one draw per sample and channel;
+ * sample = (pixel / pix_per_sample) % n_samples: n_samples = N for (N,H,W,C), = B for time-major frames (T*B,H,W,C)).
  * y = x * mask(seed, step, layer_id, element): Philox4x32-10, `rng_state` = DEVICE uint64[2] {seed, step}.  The
  * mask is a pure function of its arguments: the backward pass is the same call on dy.  dl4ds_rng_advance bumps
  * `step` (one kernel, captured with the step graph, so every replay draws new masks).  TensorFlow's own random
  * streams are not reproducible; parity tests obtain the mask by applying the call to a tensor of ones.
  * ------------------------------------------------------------------------------------------- */
-int dl4ds_dropout(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, int64_t pix_per_sample, int C,
-                  float rate, int variant, const uint64_t* rng_state, int layer_id, void* stream);
+int dl4ds_dropout(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, int64_t pix_per_sample, int n_samples,
+                  int C, float rate, int variant, const uint64_t* rng_state, int layer_id, void* stream);
 int dl4ds_rng_advance(uint64_t* rng_state, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

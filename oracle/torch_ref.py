@@ -383,11 +383,26 @@ def convlstm2d(p, name, x5, filters, k):
     return torch.stack(outs, dim=1)
 
 
-def recurrent_conv_block(p, name, x5, filters, activation='relu'):
-    """RecurrentConvBlock.call -- blocks.py:380-398 (no normalization / dropout)."""
-    y = act(convlstm2d(p, name + '/convlstm1', x5, filters, 5), activation)
-    y = act(convlstm2d(p, name + '/convlstm2', y, filters, 3), activation)
-    return y
+def normalize_5d(p, name, x5, kind):
+    """BatchNormalization / LayerNormalization on (B,T,C,H,W) [NTHWC in the reference], axis -1: batch statistics
+    over (B,T,H,W), layer statistics over C -- the 4-D op on the tensor folded to (B*T,C,H,W)."""
+    b, t = x5.shape[:2]
+    return normalize(p, name, x5.reshape(b * t, *x5.shape[2:]), kind).reshape(x5.shape)
+
+
+def recurrent_conv_block(p, name, x5, filters, activation='relu', normalization=None, dropout_rate=0,
+                         dropout_variant=None):
+    """RecurrentConvBlock.call -- blocks.py:380-398; dropout layers with dim=3 (:371-374)."""
+    y = dropout(p, x5, dropout_rate, dropout_variant)
+    y = convlstm2d(p, name + '/convlstm1', y, filters, 5)
+    if normalization is not None:
+        y = normalize_5d(p, name + '/norm1', y, normalization)
+    y = act(y, activation)
+    y = dropout(p, y, dropout_rate, dropout_variant)
+    y = convlstm2d(p, name + '/convlstm2', y, filters, 3)
+    if normalization is not None:
+        y = normalize_5d(p, name + '/norm2', y, normalization)
+    return act(y, activation)
 
 
 def pad_concat(t1, t2):
@@ -564,14 +579,18 @@ def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu'
 
 def recnet_postupsampling(p, inputs, backbone_block, upsampling, scale, time_window,
                           n_channels_out=1, n_filters=8, n_blocks=4, attention=False,
-                          activation='relu', output_activation=None, localcon_layer=False):
+                          activation='relu', output_activation=None, localcon_layer=False, normalization=None,
+                          dropout_rate=0, dropout_variant=None):
     """recnet_postupsampling -- spt_postups.py:12-163.  inputs[0]: (B,T,h,w,C) NTHWC;
     optional inputs[1]: (B,H,W,n_aux).  Output (B,T,H,W,n_channels_out)."""
     x5 = inputs[0].permute(0, 1, 4, 2, 3).contiguous()   # (B,T,C,h,w)
     bsz, t = x5.shape[0], x5.shape[1]
-    x = b = recurrent_conv_block(p, 'RecurrentConvBlock1', x5, n_filters, activation)
+    nz = normalization
+    x = b = recurrent_conv_block(p, 'RecurrentConvBlock1', x5, n_filters, activation, nz)
     for i in range(n_blocks):
-        b = recurrent_conv_block(p, 'RecurrentConvBlock' + str(i + 2), b, n_filters, activation)
+        b = recurrent_conv_block(p, 'RecurrentConvBlock' + str(i + 2), b, n_filters, activation, nz, dropout_rate,
+                                 dropout_variant)
+    b = dropout(p, b, dropout_rate, dropout_variant)              # spt_postups.py:113
     if backbone_block == 'convnet':
         x = b
     elif backbone_block == 'resnet':
@@ -597,23 +616,34 @@ def recnet_postupsampling(p, inputs, backbone_block, upsampling, scale, time_win
     # spt_postups.py:150 halves the channel count; spt_preups.py:133 maps to n_filters
     xf = transition_block(p, 'TransitionLast', xf, n_filters if upsampling == 'pin' else xf.shape[1] // 2)
     # ConvBlock(n_filters, activation=None, attention=True) on a 5-D tensor (App. B #6)
-    y = _conv(p, 'ConvBlock_tail/conv1', xf, n_filters)
-    y = _conv(p, 'ConvBlock_tail/conv2', y, n_filters)
+    # (plain Dropout in front of each convolution when dropout_rate > 0 -- no variant passed, :152-153; the masks
+    #  are handed over on the 5-D view so that the supplier sees (B,T,C,H,W) everywhere in this network)
+    def drop5(v):
+        return dropout(p, v.reshape(bsz, t, *v.shape[1:]), dropout_rate).reshape(v.shape)
+    y = _conv(p, 'ConvBlock_tail/conv1', drop5(xf), n_filters, bias=nz is None)
+    if nz is not None:
+        y = normalize(p, 'ConvBlock_tail/norm1', y, nz)
+    y = _conv(p, 'ConvBlock_tail/conv2', drop5(y), n_filters, bias=nz is None)
+    if nz is not None:
+        y = normalize(p, 'ConvBlock_tail/norm2', y, nz)
     y5 = y.reshape(bsz, t, *y.shape[1:])
     y5 = channel_attention_5d(p, 'ConvBlock_tail/att', y5, n_filters)
     y = y5.reshape(bsz * t, *y5.shape[2:])
-    y = conv_block(p, 'ConvBlock_out', y, n_channels_out, activation=output_activation)
+    y = conv_block(p, 'ConvBlock_out', y, n_channels_out, activation=output_activation, normalization=nz)
     y5 = y.reshape(bsz, t, *y.shape[1:])
     return y5.permute(0, 1, 3, 4, 2).contiguous()
 
 
 def recnet_pin(p, inputs, backbone_block, time_window, n_channels_out=1, n_filters=8, n_blocks=6, attention=False,
-               activation='relu', output_activation=None, localcon_layer=False):
+               activation='relu', output_activation=None, localcon_layer=False, normalization=None, dropout_rate=0,
+               dropout_variant=None):
     """recnet_pin -- spt_preups.py:12-163: recnet_postupsampling's graph without the upsampler (inputs already on
     the HR grid) and with TransitionLast -> n_filters (:133)."""
     return recnet_postupsampling(p, inputs, backbone_block, 'pin', 1, time_window, n_channels_out=n_channels_out,
                                  n_filters=n_filters, n_blocks=n_blocks, attention=attention, activation=activation,
-                                 output_activation=output_activation, localcon_layer=localcon_layer)
+                                 output_activation=output_activation, localcon_layer=localcon_layer,
+                                 normalization=normalization, dropout_rate=dropout_rate,
+                                 dropout_variant=dropout_variant)
 
 
 def residual_discriminator(p, inputs, upsampling, scale, lr_size, n_filters=8, n_res_blocks=4,

@@ -14,12 +14,12 @@ from tests.util import compare, rel_err, trace_spec
 pytestmark = pytest.mark.gpu
 
 
-def gpu_mask(shape_nhwc, rate, variant, seed, step, layer_id):
+def gpu_mask(shape_nhwc, rate, variant, seed, step, layer_id, n_samples=None):
     n, h, w, c = shape_nhwc
     ones = torch.ones(shape_nhwc, dtype=torch.float32, device='cuda')
     out = torch.empty_like(ones)
     state = torch.tensor([seed, step], dtype=torch.int64, device='cuda')
-    _lib.call('dl4ds_dropout', ones.data_ptr(), c, out.data_ptr(), c, n * h * w, h * w, c, float(rate),
+    _lib.call('dl4ds_dropout', ones.data_ptr(), c, out.data_ptr(), c, n * h * w, h * w, n_samples or n, c, float(rate),
               DROPOUT_KIND[variant], state.data_ptr(), int(layer_id), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return out.cpu()
@@ -27,8 +27,12 @@ def gpu_mask(shape_nhwc, rate, variant, seed, step, layer_id):
 
 def supplier(seed=Arena.RNG_SEED, step=1):
     """Oracle-side mask source: the i-th dropout application of the graph <-> layer id i."""
-    def f(i, shape_nchw, rate, variant):
-        n, c, h, w = shape_nchw
+    def f(i, shape, rate, variant):
+        if len(shape) == 5:       # oracle (B,T,C,H,W) <-> engine time-major frames (T*B,H,W,C), one sample = one b
+            b, t, c, h, w = shape
+            m = gpu_mask((t * b, h, w, c), rate, variant, seed, step, i, n_samples=b)
+            return m.reshape(t, b, h, w, c).permute(1, 0, 4, 2, 3)
+        n, c, h, w = shape
         return gpu_mask((n, h, w, c), rate, variant, seed, step, i).permute(0, 3, 1, 2)
     return f
 
@@ -151,3 +155,27 @@ def test_supervised_steps_with_dropout_in_the_captured_graph(cuda):
     from tests.util import assert_adam_weights_close
     assert_adam_weights_close(tr.model.get_weights(), {k: v.numpy() for k, v in w.items()}, lr=1e-3, steps=3,
                               tight=5e-5, frac=5e-3)
+
+
+@pytest.mark.parametrize('nz,variant', [('ln', 'spatial'), ('bn', None), (None, 'gaussian')])
+def test_recurrent_net_with_normalization_and_dropout(cuda, nz, variant):
+    """recnet_postupsampling with RecurrentConvBlock(normalization, dropout) and the 5-D tail; the spatial variant
+    is SpatialDropout3D: one draw per sample and channel over (T,H,W) of the time-major frame stack."""
+    T, Bz = 3, 2
+    kw = dict(n_blocks=1, normalization=nz, dropout_rate=0.2, dropout_variant=variant)
+    m = nets.recnet_postupsampling('resnet', 'rc', 4, 1, 1, (8, 8), T, **kw)
+
+    def ofn(p, xs):
+        p.dropout_mask = supplier()
+        x = xs[0]
+        x5 = x.reshape(T, Bz, *x.shape[1:]).permute(1, 0, 2, 3, 4)      # (B,T,h,w,C)
+        y5 = R.recnet_postupsampling(p, [x5, xs[1]], 'resnet', 'rc', 4, T, **kw)
+        return y5.permute(1, 0, 2, 3, 4).reshape(T * Bz, *y5.shape[2:])
+    compare(m.fn, ofn, [(T * Bz, 8, 8, 1), (Bz, 32, 32, 1)], cuda, tol=5e-5, gtol=3e-3, input_grads=False)
+
+
+def test_spatial_dropout_over_time_major_frames(cuda):
+    T, Bz = 4, 3
+    m = gpu_mask((T * Bz, 6, 5, 8), 0.4, 'spatial', 5, 1, 1, n_samples=Bz).numpy().reshape(T, Bz, 6, 5, 8)
+    assert np.array_equal(m, np.broadcast_to(m[:1, :, :1, :1, :], m.shape))     # shared over T, H, W
+    assert len(np.unique(m[0, :, 0, 0, :])) == 2                                # but not over samples / channels

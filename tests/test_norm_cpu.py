@@ -96,3 +96,19 @@ def test_resnet_bn_parameter_count_by_hand():
     blk0 = sum(int(np.prod(s)) for k, s in m0.spec.items() if k.startswith('ResidualBlock1/'))
     blk1 = sum(int(np.prod(s)) for k, s in m1.spec.items() if k.startswith('ResidualBlock1/'))
     assert blk0 == 2 * (9 * 64 + 8) and blk1 == 2 * (9 * 64) + 2 * 32
+
+
+@pytest.mark.parametrize('nz', ['bn', 'ln'])
+def test_recurrent_networks_with_normalization_and_dropout(nz):
+    """RecurrentConvBlock(normalization, dropout) and the 5-D tail -- blocks.py:339-398, spt_postups.py:104-157:
+    same parameter table and the same number of dropout applications in the builder and in the oracle."""
+    from dl4ds_b200.spec import SpecCtx
+    kw = dict(n_blocks=1, normalization=nz, dropout_rate=0.2, dropout_variant='spatial')
+    m = nets.recnet_postupsampling('resnet', 'rc', 4, 1, 1, (8, 8), 3, **kw)
+    p = R.Params()
+    y = R.recnet_postupsampling(p, [torch.zeros(2, 3, 8, 8, 1), torch.zeros(2, 32, 32, 1)], 'resnet', 'rc', 4, 3, **kw)
+    assert dict(m.spec) == dict(p.spec) and tuple(y.shape) == (2, 3, 32, 32, 1)
+    sc = SpecCtx()
+    m.fn(sc, [sc.input((6, 8, 8, 1)), sc.input((2, 32, 32, 1))])
+    assert sc.n_dropout == p.n_dropout == 2 + 1 + 2          # block 2, after the blocks, the tail ConvBlock
+    assert 'RecurrentConvBlock1/norm1/gamma' in m.spec and 'ConvBlock_tail/conv1/bias' not in m.spec

@@ -188,16 +188,16 @@ def test_model_names_and_unsupported():
     assert nets.unet_pin('unet', 1, 0, (16, 16), 1, 8, 2).name == 'unet_pin'
     with pytest.raises(ValueError):
         nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), normalization='gn')
-    with pytest.raises(NotImplementedError):
-        nets.recnet_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), 3, normalization='bn')
+    with pytest.raises(ValueError):
+        nets.recnet_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), 3, normalization='gn')
     with pytest.raises(ValueError):           # ConvNextBlock without a normalisation fails in the reference too
         nets.net_postupsampling('convnext', 'spc', 4, 1, 0, (8, 8))
     with pytest.raises(NotImplementedError):
         nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), activation='elu')
     with pytest.raises(ValueError):
         nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), dropout_rate=0.2, dropout_variant='alpha')
-    with pytest.raises(NotImplementedError):
-        nets.recnet_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), 3, dropout_rate=0.2)
+    with pytest.raises(ValueError):
+        nets.recnet_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), 3, dropout_rate=0.2, dropout_variant='alpha')
 
 
 def test_recnet_pin_structure():
