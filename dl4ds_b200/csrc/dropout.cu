@@ -29,29 +29,82 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0
 //         1: GaussianDropout -- multiply by N(1, sqrt(rate / (1 - rate)))
 //         2: SpatialDropout2D / 3D -- as 0 with one draw per (sample, channel); sample = (pixel / pix_per_sample) %
 //            n_samples, so time-major frame stacks (T*B, H, W, C) share the draw over T as SpatialDropout3D does
-__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
-                                                      int y_ld, int64_t n_pix, int64_t pix_per_sample, int n_samples,
-                                                      int C, float rate, int variant,
-                                                      const unsigned long long* __restrict__ state, int layer_id) {
+// The mask of logical element idx (= flat NHWC index, or sample*C + c for the spatial variant) is a pure function:
+//   variants 0 / 2: word (idx & 3) of Philox(counter idx >> 2);  variant 1: words 2*(idx & 1), +1 of Philox(idx >> 1).
+// One thread owns four consecutive elements; with C % 4 == 0 they share one Philox call (two for the gaussian).
+struct DropArgs {
+    const float* x; float* y;
+    int x_ld, y_ld;
+    int64_t n_pix, pix_per_sample;
+    int n_samples, C;
+    float rate;
+    int variant, layer_id, vec;
+};
+
+__device__ __forceinline__ float gauss_from(uint32_t a, uint32_t b, float sd) {
+    const float u1 = 1.0f - u01(a), u2 = u01(b);                       // u1 in (0, 1]
+    return 1.0f + sd * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);    // Box-Muller
+}
+
+__global__ void __launch_bounds__(256) dropout_kernel(DropArgs a, const unsigned long long* __restrict__ state) {
     const unsigned long long seed = state[0], step = state[1];
-    const float scale = 1.0f / (1.0f - rate);
-    const float sd = sqrtf(rate / (1.0f - rate));
-    const int64_t n = n_pix * C;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p = i / C;
-        const int c = (int)(i - p * C);
-        const unsigned long long idx = variant == 2 ? (unsigned long long)((p / pix_per_sample) % n_samples) * C + c
-                                                    : (unsigned long long)i;
-        uint32_t ctr[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)layer_id, (uint32_t)step};
-        philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
-        float m;
-        if (variant == 1) {
-            const float u1 = 1.0f - u01(ctr[0]), u2 = u01(ctr[1]);          // u1 in (0, 1]
-            m = 1.0f + sd * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);   // Box-Muller
-        } else {
-            m = u01(ctr[0]) >= rate ? scale : 0.0f;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32);
+    const float scale = 1.0f / (1.0f - a.rate);
+    const float sd = sqrtf(a.rate / (1.0f - a.rate));
+    const int64_t n = a.n_pix * a.C;
+    const int64_t groups = (n + 3) >> 2;
+    const bool shared_call = (a.C & 3) == 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g << 2;
+        float m[4];
+        int64_t p0 = i0 / a.C;
+        int c0 = (int)(i0 - p0 * a.C);
+        if (shared_call) {
+            const unsigned long long idx0 = a.variant == 2
+                ? (unsigned long long)((p0 / a.pix_per_sample) % a.n_samples) * a.C + c0 : (unsigned long long)i0;
+            if (a.variant == 1) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned long long q = (idx0 >> 1) + h;
+                    uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)a.layer_id, (uint32_t)step};
+                    philox4x32_10(ctr, k0, k1);
+                    m[2 * h] = gauss_from(ctr[0], ctr[1], sd);
+                    m[2 * h + 1] = gauss_from(ctr[2], ctr[3], sd);
+                }
+            } else {
+                const unsigned long long q = idx0 >> 2;
+                uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)a.layer_id, (uint32_t)step};
+                philox4x32_10(ctr, k0, k1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[k] = u01(ctr[k]) >= a.rate ? scale : 0.0f;
+            }
+            if (a.vec) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + p0 * a.x_ld + c0));
+                *reinterpret_cast<float4*>(a.y + p0 * a.y_ld + c0) = make_float4(v.x * m[0], v.y * m[1], v.z * m[2], v.w * m[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a.y[p0 * a.y_ld + c0 + k] = __ldg(a.x + p0 * a.x_ld + c0 + k) * m[k];
+            }
+            continue;
         }
-        y[p * y_ld + c] = __ldg(x + p * x_ld + c) * m;
+        for (int k = 0; k < 4 && i0 + k < n; ++k) {     // any C: one call per element, same mask function
+            const int64_t i = i0 + k, p = i / a.C;
+            const int c = (int)(i - p * a.C);
+            const unsigned long long idx = a.variant == 2
+                ? (unsigned long long)((p / a.pix_per_sample) % a.n_samples) * a.C + c : (unsigned long long)i;
+            const unsigned long long q = a.variant == 1 ? idx >> 1 : idx >> 2;
+            uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)a.layer_id, (uint32_t)step};
+            philox4x32_10(ctr, k0, k1);
+            float mk;
+            if (a.variant == 1) {
+                const int w = 2 * (int)(idx & 1);
+                mk = gauss_from(w ? ctr[2] : ctr[0], w ? ctr[3] : ctr[1], sd);
+            } else {
+                const int w = (int)(idx & 3);
+                mk = u01(w == 0 ? ctr[0] : w == 1 ? ctr[1] : w == 2 ? ctr[2] : ctr[3]) >= a.rate ? scale : 0.0f;
+            }
+            a.y[p * a.y_ld + c] = __ldg(a.x + p * a.x_ld + c) * mk;
+        }
     }
 }
 
@@ -74,11 +127,10 @@ int dl4ds_dropout(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, i
     DL4DS_REQUIRE(rate > 0.0f && rate < 1.0f, DL4DS_E_BADARG, "dropout: rate must be in (0, 1)");
     DL4DS_REQUIRE(variant >= 0 && variant <= 2, DL4DS_E_BADARG, "dropout: variant must be 0, 1 or 2");
     const int64_t n = n_pix * C;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256 * 4), 8 * kNumSMs));
-    dropout_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_ld, y, y_ld, n_pix, pix_per_sample, n_samples, C, rate,
-                                                        variant,
-                                                        reinterpret_cast<const unsigned long long*>(rng_state),
-                                                        layer_id);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256 * 4 * 2), 16 * kNumSMs));
+    DropArgs a{x, y, x_ld, y_ld, n_pix, pix_per_sample, n_samples, C, rate, variant, layer_id, 0};
+    a.vec = (C % 4 == 0 && x_ld % 4 == 0 && y_ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) ? 1 : 0;
+    dropout_kernel<<<grid, 256, 0, as_stream(stream)>>>(a, reinterpret_cast<const unsigned long long*>(rng_state));
     return check_launch("dropout");
 }
 

@@ -100,7 +100,8 @@ class SupervisedTrainer(Trainer):
         if self.data_on_device and DeviceDataGenerator.supported(
                 getattr(self.data_train, 'values', self.data_train), self.data_train_lr, self.upsampling, self.scale,
                 self.patch_size, self.time_window, self.static_vars, self.predictors_train, self.interpolation):
-            self.ds_train = DeviceDataGenerator(self.data_train, None, device=self.dp.torch_device, **p)
+            self.ds_train = DeviceDataGenerator(self.data_train, None, device=self.dp.torch_device,
+                                                predictors=self.predictors_train, **p)
         else:
             self.ds_train = DataGenerator(self.data_train, self.data_train_lr, predictors=self.predictors_train, **p)
         self.ds_val = DataGenerator(self.data_val, self.data_val_lr, predictors=self.predictors_val, **p)
@@ -296,7 +297,7 @@ class SupervisedTrainer(Trainer):
         evs = [torch.cuda.Event() for _ in range(2)]
         pending = None
         for i, idx in enumerate(order):
-            gen.fill(int(idx), st.inputs[0], st.target)
+            gen.fill(int(idx), st.inputs[0], st.target, st.inputs[1] if len(st.inputs) > 1 else None)
             loss = st.run()
             slots[i & 1].copy_(loss, non_blocking=True)
             evs[i & 1].record()

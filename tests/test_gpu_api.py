@@ -127,6 +127,64 @@ def test_device_data_generator_matches_host(cuda, patch):
         assert np.abs(lr_d - lr_h).max() <= 1e-6 * max(1.0, np.abs(lr_h).max())
 
 
+@pytest.mark.parametrize('case', ['pred_hr+static', 'pred_lr', 'static+patch'])
+def test_device_data_generator_with_predictors_and_static(cuda, case):
+    """Predictors (on the HR or the LR grid) and static variables assembled on the GPU into their channel slices
+    of the LR batch (+ the static HR planes as the aux input) == the host generator (BASELINE config 3's data path:
+    3 predictors + 1 static field)."""
+    from dl4ds_b200.dataloader import DataGenerator, DeviceDataGenerator
+    rng = np.random.default_rng(6)
+    hr = rng.standard_normal((14, 32, 48, 1)).astype(np.float32)
+    kw = dict(backbone='densenet', upsampling='dc', scale=4, batch_size=4)
+    if case == 'pred_hr+static':
+        kw.update(predictors=[rng.standard_normal((14, 32, 48, 1)).astype(np.float32) for _ in range(3)],
+                  static_vars=[rng.standard_normal((32, 48)).astype(np.float32)])
+    elif case == 'pred_lr':
+        kw.update(predictors=[rng.standard_normal((14, 8, 12, 2)).astype(np.float32)])
+    else:
+        kw.update(static_vars=[rng.standard_normal((32, 48)).astype(np.float32),
+                               rng.standard_normal((32, 48, 1)).astype(np.float32)], patch_size=16)
+    assert DeviceDataGenerator.supported(hr, None, 'dc', 4, kw.get('patch_size'), None, kw.get('static_vars'),
+                                         kw.get('predictors'), 'inter_area')
+    np.random.seed(12)
+    host = DataGenerator(hr, None, **kw)
+    hb = [host[i] for i in range(len(host))]
+    np.random.seed(12)
+    dev = DeviceDataGenerator(hr, None, device=cuda, **kw)
+    for i in range(len(dev)):
+        xd, (hr_d,) = dev[i]
+        xh, (hr_h,) = hb[i]
+        assert len(xd) == len(xh) and np.array_equal(hr_d, hr_h)
+        for a, b in zip(xd, xh):
+            assert a.shape == b.shape, (a.shape, b.shape)
+            assert np.abs(a - b).max() <= 1e-6 * max(1.0, np.abs(b).max())
+    # outside the device domain: the reference's patch + predictors branch
+    assert not DeviceDataGenerator.supported(hr, None, 'dc', 4, 16, None, None, kw.get('predictors') or [hr],
+                                             'inter_area')
+
+
+def test_supervised_run_cfg3_data_on_device(cuda):
+    """BASELINE config 3 shape (densenet + attention + LCB, 8x deconvolution, 3 predictors + 1 static) trained from
+    the device-resident data path: the same loss history as from the host generator."""
+    rng = np.random.default_rng(8)
+    hr = rng.standard_normal((24, 64, 64, 1)).astype(np.float32)
+    preds = [rng.standard_normal((24, 64, 64, 1)).astype(np.float32) for _ in range(3)]
+    static = rng.standard_normal((64, 64)).astype(np.float32)
+    hist = []
+    for on_dev in (False, True):
+        np.random.seed(4)
+        tr = SupervisedTrainer('densenet', 'dc', hr[:16], hr[16:], hr[16:], predictors_train=[p[:16] for p in preds],
+                               predictors_val=[p[16:] for p in preds], predictors_test=[p[16:] for p in preds],
+                               static_vars=[static.copy()], scale=8, batch_size=4, epochs=2, learning_rate=1e-3,
+                               verbose=False, seed=3, n_blocks=2, attention=True, localcon_layer=True, math='fp32',
+                               data_on_device=on_dev)
+        tr.run()
+        from dl4ds_b200.dataloader import DeviceDataGenerator
+        assert isinstance(tr.ds_train, DeviceDataGenerator) == on_dev
+        hist.append(tr.fithist.history['loss'])
+    assert np.allclose(hist[0], hist[1], rtol=2e-4), hist
+
+
 def test_supervised_run_data_on_device(cuda):
     """SupervisedTrainer(data_on_device=True): the same losses as the host data path, epoch by epoch."""
     hr = _data(40, 32, 2)
