@@ -11,3 +11,5 @@ timeout 600 python bench.py --steps 30 --warmup 5 --math tf32 --no-cpu > gpurun_
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_tc|thin_" -c 18 -o gpurun_out/${TAG}_layers -f python scratch/prof_layers.py tf32x3 > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json
+timeout 300 python scratch/bench_next_ops.py > gpurun_out/${TAG}_next_ops.json 2> gpurun_out/${TAG}_next_ops.err
+timeout 600 python scratch/next_configs.py > gpurun_out/${TAG}_next_configs.json 2> gpurun_out/${TAG}_next_configs.err; tail -3 gpurun_out/${TAG}_next_configs.err

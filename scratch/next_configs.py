@@ -53,5 +53,45 @@ for label, backbone, kw in CASES:
     print(label, out[label], file=sys.stderr, flush=True)
     del tr
     torch.cuda.empty_cache()
+# ---- BASELINE config 3 inputs (3 predictors + 1 static field, densenet + attention + LCB, 8x deconvolution, batch 16
+#      per GPU): one epoch through SupervisedTrainer.run() from the host generator (per-sample numpy / cv2 loop, as
+#      the reference) and from the device-resident generator
+B3, N3 = 16, 16 * 12
+hr3 = rng.standard_normal((N3 + 2 * B3, 128, 128, 1), dtype=np.float32)
+preds = [rng.standard_normal((N3 + 2 * B3, 128, 128, 1), dtype=np.float32) for _ in range(3)]
+static = rng.standard_normal((128, 128)).astype(np.float32)
+data = {}
+for on_dev in (False, True):
+    np.random.seed(0)
+    tr = SupervisedTrainer('densenet', 'dc', hr3[:N3], hr3[N3:N3 + B3], hr3[N3 + B3:],
+                           predictors_train=[p[:N3] for p in preds], predictors_val=[p[N3:N3 + B3] for p in preds],
+                           predictors_test=[p[N3 + B3:] for p in preds], static_vars=[static.copy()], scale=8,
+                           batch_size=B3, epochs=2, learning_rate=1e-3, verbose=False, math=math, seed=1,
+                           attention=True, localcon_layer=True, data_on_device=on_dev)
+    tr.setup_datagen()
+    tr.setup_model()
+    gen = tr.ds_train
+    st = tr.train_step
+
+    def epoch():
+        if on_dev:
+            for _ in tr.train_on_device_batches(gen, list(range(len(gen)))):
+                pass
+        else:
+            for _ in tr.train_on_batches(((gen[i][0], gen[i][1][0]) for i in range(len(gen)))):
+                pass
+    epoch()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    epoch()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / len(gen) * 1e3
+    data['device generator' if on_dev else 'host generator'] = dict(
+        ms_per_step=round(ms, 3), hr_px_per_s=round(B3 * 128 * 128 / ms * 1e3), steps=len(gen))
+    print('cfg3 data path', on_dev, data, file=sys.stderr, flush=True)
+    del tr
+    torch.cuda.empty_cache()
+out['cfg3 (densenet+att+LCB dc x8, 3 predictors + 1 static, batch 16): epoch incl. batch creation'] = data
+
 print(json.dumps({'math': math, 'batch': B, 'timing': 'wall clock around train_on_batch (host batch -> loss float), '
                   '10 steps after 3 warm-up', 'rows': out}, indent=1))
