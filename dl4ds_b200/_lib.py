@@ -58,6 +58,8 @@ SIGNATURES = {
     'dl4ds_avgpool_coarsen': ('i', 'ppiiiiip'),
     'dl4ds_resize_bilinear_fwd': ('i', 'pipiiiiiiip'),
     'dl4ds_resize_bilinear_bwd': ('i', 'pipiiiiiiip'),
+    'dl4ds_resize_fwd': ('i', 'pipiiiiiiiip'),
+    'dl4ds_resize_bwd': ('i', 'pipiiiiiiiip'),
     'dl4ds_maxpool2_fwd': ('i', 'pipiiiiip'),
     'dl4ds_maxpool2_bwd': ('i', 'pipipiiiiip'),
     'dl4ds_local_conv1x1_fwd': ('i', 'pipppiiiiiip'),

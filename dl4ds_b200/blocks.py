@@ -127,9 +127,9 @@ def subpixel_transition(c, name, x, scale, n_filters, tname, t_filters, activati
     return c.conv_d2s_pointwise(x, name + '/conv2x', n_filters, tname + '/conv', t_filters, act=activation, r=2)
 
 
-def resize_conv_block(c, name, x, scale, n_filters):
-    """ResizeConvolutionBlock.call (bilinear) -- blocks.py:485-491."""
-    y = c.resize_bilinear(x, int(x.H * scale), int(x.W * scale))
+def resize_conv_block(c, name, x, scale, n_filters, interpolation='bilinear'):
+    """ResizeConvolutionBlock.call -- blocks.py:485-491 (interpolation: bilinear, nearest or bicubic)."""
+    y = c.resize(x, int(x.H * scale), int(x.W * scale), interpolation)
     return c.conv(y, name + '/conv', n_filters)
 
 

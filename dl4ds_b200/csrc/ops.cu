@@ -507,6 +507,90 @@ __device__ __forceinline__ void bilinear_coords(int o, int in, int out, int& i0,
     i1 = min(max(b + 1, 0), in - 1);
 }
 
+// -------------------------------------------------------------------------------------------------
+// nearest / bicubic resize as Keras Resizing(interpolation=...) = tf.image.resize(method, antialias=False) runs them
+// (TF kernels ResizeNearestNeighbor / ResizeBicubic with half_pixel_centers=True; restated from the published source):
+//   nearest: in = min(floor((out + 0.5) * scale), in - 1)
+//   bicubic: Keys cubic, A = -0.5; in_loc = floor((out + 0.5) * scale - 0.5); the fractional offset is quantised to
+//            1/1024 (TF's coefficient table); taps whose index leaves the image get weight 0 and the remaining
+//            weights are renormalised to sum 1
+// Both are separable: up to 4 taps per axis.
+// -------------------------------------------------------------------------------------------------
+struct Taps { int idx[4]; float w[4]; int n; };
+
+__device__ __forceinline__ Taps resize_taps(int o, int in, int out, int method) {
+    Taps t;
+    const float scale = (float)in / (float)out;
+    if (method == 1) {
+        t.n = 1;
+        t.idx[0] = min((int)floorf(((float)o + 0.5f) * scale), in - 1);
+        t.w[0] = 1.0f;
+        return t;
+    }
+    const float A = -0.5f;
+    const float loc = ((float)o + 0.5f) * scale - 0.5f;
+    const float fl = floorf(loc);
+    const int b = (int)fl;
+    const int off = (int)lrintf((loc - fl) * 1024.0f);
+    const float x0 = (float)off / 1024.0f, x1 = (float)(1024 - off) / 1024.0f;
+    // coefficient table: [2i] = ((A+2) x - (A+3)) x^2 + 1 at x = i/1024; [2i+1] = ((A x - 5A) x + 8A) x - 4A at x + 1
+    const float near0 = ((A + 2.0f) * x0 - (A + 3.0f)) * x0 * x0 + 1.0f;
+    const float far0 = ((A * (x0 + 1.0f) - 5.0f * A) * (x0 + 1.0f) + 8.0f * A) * (x0 + 1.0f) - 4.0f * A;
+    const float near1 = ((A + 2.0f) * x1 - (A + 3.0f)) * x1 * x1 + 1.0f;
+    const float far1 = ((A * (x1 + 1.0f) - 5.0f * A) * (x1 + 1.0f) + 8.0f * A) * (x1 + 1.0f) - 4.0f * A;
+    const float wraw[4] = {far0, near0, near1, far1};
+    float sum = 0.0f;
+    t.n = 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int want = b - 1 + k;
+        const int got = min(max(want, 0), in - 1);
+        t.idx[k] = got;
+        t.w[k] = got == want ? wraw[k] : 0.0f;
+        sum += t.w[k];
+    }
+    if (fabsf(sum) >= 1000.0f * 1.17549435e-38f) {
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t.w[k] *= inv;
+    }
+    return t;
+}
+
+// fwd: y[o] = sum w x[taps];  bwd (transpose = 1): scatter g * w onto dx with atomics
+__global__ void resize_taps_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_ld,
+                                   int N, int H, int W, int C, int Ho, int Wo, int method, int transpose) {
+    const int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        int64_t t = i / C;
+        const int ox = (int)(t % Wo); t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const Taps ty = resize_taps(oy, H, Ho, method), tx = resize_taps(ox, W, Wo, method);
+        const int64_t o_hi = (((int64_t)n * Ho + oy) * Wo + ox);
+        if (!transpose) {
+            const float* b = src + (int64_t)n * H * W * src_ld + c;
+            float acc = 0.0f;
+            for (int a = 0; a < ty.n; ++a) {
+                float row = 0.0f;
+                for (int k = 0; k < tx.n; ++k) row = fmaf(tx.w[k], __ldg(b + ((int64_t)ty.idx[a] * W + tx.idx[k]) * src_ld), row);
+                acc = fmaf(ty.w[a], row, acc);
+            }
+            dst[o_hi * dst_ld + c] = acc;
+        } else {
+            const float g = __ldg(src + o_hi * src_ld + c);
+            float* b = dst + (int64_t)n * H * W * dst_ld + c;
+            for (int a = 0; a < ty.n; ++a)
+                for (int k = 0; k < tx.n; ++k) {
+                    const float wgt = ty.w[a] * tx.w[k];
+                    if (wgt != 0.0f) atomicAdd(b + ((int64_t)ty.idx[a] * W + tx.idx[k]) * dst_ld, g * wgt);
+                }
+        }
+    }
+}
+
 __global__ void resize_bilinear_fwd_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
                                            int y_ld, int N, int H, int W, int C, int Ho, int Wo) {
     const int64_t total = (int64_t)N * Ho * Wo * C;
@@ -1222,6 +1306,29 @@ int dl4ds_resize_bilinear_bwd(const float* dy, int dy_ld, float* dx, int dx_ld,
     return launch1d("resize_bilinear_bwd", resize_bilinear_bwd_kernel, (int64_t)N * Ho * Wo * C,
                     as_stream(stream), dy, dy_ld, dx, dx_ld, N, H, W, C, Ho, Wo);
 }
+
+int dl4ds_resize_fwd(const float* x, int x_ld, float* y, int y_ld, int N, int H, int W, int C, int Ho, int Wo,
+                     int method, void* stream) {
+    DL4DS_REQUIRE(x && y, DL4DS_E_BADARG, "resize_fwd: null pointer");
+    DL4DS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, DL4DS_E_SHAPE, "resize_fwd: bad shape");
+    if (method == DL4DS_RESIZE_BILINEAR) return dl4ds_resize_bilinear_fwd(x, x_ld, y, y_ld, N, H, W, C, Ho, Wo, stream);
+    DL4DS_REQUIRE(method == DL4DS_RESIZE_NEAREST || method == DL4DS_RESIZE_BICUBIC, DL4DS_E_UNSUPPORTED,
+                  "resize_fwd: method %d not built (bilinear 0, nearest 1, bicubic 2)", method);
+    return launch1d("resize_fwd", resize_taps_kernel, (int64_t)N * Ho * Wo * C, as_stream(stream), x, x_ld, y, y_ld, N,
+                    H, W, C, Ho, Wo, method, 0);
+}
+
+int dl4ds_resize_bwd(const float* dy, int dy_ld, float* dx, int dx_ld, int N, int H, int W, int C, int Ho, int Wo,
+                     int method, void* stream) {
+    DL4DS_REQUIRE(dy && dx, DL4DS_E_BADARG, "resize_bwd: null pointer");
+    DL4DS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0, DL4DS_E_SHAPE, "resize_bwd: bad shape");
+    if (method == DL4DS_RESIZE_BILINEAR) return dl4ds_resize_bilinear_bwd(dy, dy_ld, dx, dx_ld, N, H, W, C, Ho, Wo, stream);
+    DL4DS_REQUIRE(method == DL4DS_RESIZE_NEAREST || method == DL4DS_RESIZE_BICUBIC, DL4DS_E_UNSUPPORTED,
+                  "resize_bwd: method %d not built (bilinear 0, nearest 1, bicubic 2)", method);
+    return launch1d("resize_bwd", resize_taps_kernel, (int64_t)N * Ho * Wo * C, as_stream(stream), dy, dy_ld, dx, dx_ld,
+                    N, H, W, C, Ho, Wo, method, 1);
+}
+
 
 int dl4ds_maxpool2_fwd(const float* x, int x_ld, float* y, int y_ld, int N, int H, int W, int C,
                        void* stream) {

@@ -37,6 +37,7 @@ LOSS_TERMS = {
 MSSSIM_POWER_FACTORS = (0.0448, 0.2856, 0.3001, 0.2363)      # losses.py:128
 DROPOUT_KIND = {None: 0, 'vanilla': 0, 'mcdrop': 0, 'gaussian': 1, 'mcgaussiandrop': 1, 'spatial': 2,
                 'mcspatialdrop': 2}                          # blocks.py:680-706 -> dl4ds_dropout variant
+RESIZE_METHOD = {'bilinear': 0, 'nearest': 1, 'bicubic': 2}     # DL4DS_RESIZE_*
 LOSS_ACCUMULATE = 16                                          # DL4DS_LOSS_ACCUMULATE, OR-ed into `kind`
 _PF_HOST = (ctypes.c_float * len(MSSSIM_POWER_FACTORS))(*MSSSIM_POWER_FACTORS)
 
@@ -875,6 +876,29 @@ class Ctx:
                 x.grad = Var(torch.zeros((x.N, x.H, x.W, x.C), dtype=torch.float32, device=self.device))
             self._call('dl4ds_resize_bilinear_bwd', dy.ptr, dy.ld, x.grad.ptr, x.grad.ld, x.N, x.H, x.W,
                        x.C, Ho, Wo, _stream())
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def resize(self, x, Ho, Wo, method='bilinear'):
+        """keras Resizing(Ho, Wo, interpolation=method) -- blocks.py:457-491 (`rc_interpolation`): bilinear, nearest,
+        bicubic (tf.image.resize without antialiasing, half-pixel centres)."""
+        if method == 'bilinear':
+            return self.resize_bilinear(x, Ho, Wo)
+        if method not in RESIZE_METHOD:
+            raise NotImplementedError('interpolation=%r is not built (bilinear, nearest, bicubic are)' % (method,))
+        code = RESIZE_METHOD[method]
+        out = new_var(x.N, Ho, Wo, x.C, self.device)
+        self._call('dl4ds_resize_fwd', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, x.C, Ho, Wo, code, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None or not x.requires_grad:
+                return
+            if x.grad is None:
+                x.grad = Var(torch.zeros((x.N, x.H, x.W, x.C), dtype=torch.float32, device=self.device))
+            self._call('dl4ds_resize_bwd', dy.ptr, dy.ld, x.grad.ptr, x.grad.ld, x.N, x.H, x.W, x.C, Ho, Wo, code,
+                       _stream())
             out.grad = None
         self._record(bwd)
         return out

@@ -23,6 +23,7 @@ from .utils import checkarg_dropout_variant
 
 BACKBONES = ('convnet', 'resnet', 'densenet', 'unet', 'convnext')
 POSTUPSAMPLING_METHODS = ('spc', 'rc', 'dc')
+RC_INTERPOLATIONS = ('bilinear', 'nearest', 'bicubic')     # of Keras Resizing's eight (blocks.py:463-465)
 
 
 def _check_common(activation, output_activation, normalization, dropout_rate, backbone_block=None,
@@ -379,8 +380,8 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
     _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant)
     if upsampling not in POSTUPSAMPLING_METHODS:
         raise ValueError('`upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
-    if upsampling == 'rc' and rc_interpolation != 'bilinear':
-        raise NotImplementedError('rc_interpolation=%r is outside the B200 hot path' % rc_interpolation)
+    if upsampling == 'rc' and rc_interpolation not in RC_INTERPOLATIONS:
+        raise NotImplementedError('rc_interpolation=%r is not built (%s are)' % (rc_interpolation, RC_INTERPOLATIONS))
     h_lr, w_lr = lr_size
     aux = n_aux_channels > 0
 
@@ -397,7 +398,7 @@ def net_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_chan
             else:
                 x = B.subpixel_block(c, 'SubpixelConvolution', x, scale, nf)
         elif upsampling == 'rc':
-            x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf)
+            x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf, rc_interpolation)
         else:
             x = B.transition_block(c, 'TransitionDC', x, n_filters, activation)
             x = B.deconv_block(c, 'Deconvolution', x, scale, nf, activation)
@@ -451,8 +452,8 @@ def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out
     _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant)
     if decoder_upsampling not in POSTUPSAMPLING_METHODS:
         raise ValueError('`decoder_upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
-    if decoder_upsampling == 'rc' and rc_interpolation != 'bilinear':
-        raise NotImplementedError('rc_interpolation=%r is outside the B200 hot path' % rc_interpolation)
+    if decoder_upsampling == 'rc' and rc_interpolation not in RC_INTERPOLATIONS:
+        raise NotImplementedError('rc_interpolation=%r is not built (%s are)' % (rc_interpolation, RC_INTERPOLATIONS))
     n_blocks = _check_nblocks(hr_size, n_blocks)
     aux = n_aux_channels > 0
 
@@ -473,7 +474,7 @@ def unet_pin(backbone_block, n_channels, n_aux_channels, hr_size, n_channels_out
             if decoder_upsampling == 'spc':
                 x = B.subpixel_block(c, 'SubpixelConvolution%d' % (j + 1), x, 2, nf)
             elif decoder_upsampling == 'rc':
-                x = B.resize_conv_block(c, 'ResizeConvolution%d' % (j + 1), x, 2, nf)
+                x = B.resize_conv_block(c, 'ResizeConvolution%d' % (j + 1), x, 2, nf, rc_interpolation)
             else:
                 x = B.deconv_block(c, 'Deconvolution%d' % (j + 1), x, 2, nf, activation)
             x = B.pad_concat(c, x, skip)
@@ -499,6 +500,8 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
     _check_common(activation, output_activation, normalization, dropout_rate, backbone_block, dropout_variant)
     if backbone_block == 'unet':
         raise ValueError('unet backbone is not compatible with post-upsampling')
+    if upsampling == 'rc' and rc_interpolation not in RC_INTERPOLATIONS:
+        raise NotImplementedError('rc_interpolation=%r is not built (%s are)' % (rc_interpolation, RC_INTERPOLATIONS))
     if upsampling not in POSTUPSAMPLING_METHODS + ('pin',):
         raise ValueError('`upsampling` must be one of %s' % (POSTUPSAMPLING_METHODS,))
     T = int(time_window)
@@ -525,7 +528,7 @@ def recnet_postupsampling(backbone_block, upsampling, scale, n_channels, n_aux_c
         if upsampling == 'spc':
             x = B.subpixel_block(c, 'SubpixelConvolution', x, scale, nf_ups)
         elif upsampling == 'rc':
-            x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf_ups)
+            x = B.resize_conv_block(c, 'ResizeConvolution', x, scale, nf_ups, rc_interpolation)
         elif upsampling == 'dc':
             x = B.deconv_block(c, 'Deconvolution', x, scale, nf_ups, None)    # no activation passed
         # ('pin': the samples already live on the HR grid, spt_preups.py:100-118)

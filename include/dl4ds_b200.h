@@ -294,6 +294,18 @@ int dl4ds_resize_bilinear_fwd(const float* x, int x_ld, float* y, int y_ld,
                               int N, int H, int W, int C, int Ho, int Wo, void* stream);
 int dl4ds_resize_bilinear_bwd(const float* dy, int dy_ld, float* dx, int dx_ld,
                               int N, int H, int W, int C, int Ho, int Wo, void* stream);
+/* Keras Resizing(interpolation=...) of ResizeConvolutionBlock -- blocks.py:457-491 (`rc_interpolation` of the
+ * builders): tf.image.resize(method, antialias=False), half-pixel centres.  method 0 = bilinear (the two calls above),
+ * 1 = nearest (in = min(floor((out+0.5)*scale), in-1)), 2 = bicubic (Keys cubic A = -0.5, offsets quantised to
+ * 1/1024 as TF's coefficient table does, out-of-image taps zeroed and the weights renormalised).
+ * bwd ACCUMULATES into dx (caller zeroes it), as dl4ds_resize_bilinear_bwd does. */
+#define DL4DS_RESIZE_BILINEAR 0
+#define DL4DS_RESIZE_NEAREST  1
+#define DL4DS_RESIZE_BICUBIC  2
+int dl4ds_resize_fwd(const float* x, int x_ld, float* y, int y_ld, int N, int H, int W, int C, int Ho, int Wo,
+                     int method, void* stream);
+int dl4ds_resize_bwd(const float* dy, int dy_ld, float* dx, int dx_ld, int N, int H, int W, int C, int Ho, int Wo,
+                     int method, void* stream);
 /* MaxPooling2D((2,2)) -- blocks.py:613.  bwd routes dy to the first max of each window and
  * WRITES dx fully (zeros elsewhere, including odd trailing rows/cols). */
 int dl4ds_maxpool2_fwd(const float* x, int x_ld, float* y, int y_ld,

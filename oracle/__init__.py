@@ -13,5 +13,12 @@ known-answer fixtures for the network arithmetic, and its arithmetic lives in Te
     (``oracle/ref_datapath.py``) -> committed fixtures ``tests/golden/datapath_*.npz``.
 Everything else is a restatement of the published TF/Keras 2.x op definitions,
 cross-checked between two independent statements: numpy-fp64 direct loops (``oracle/ops_np.py``)
-and torch-CPU fp32 functional code (``oracle/torch_ref.py``).
+and torch-CPU fp32 functional code (``oracle/torch_ref.py``).  Restatements added for SURVEY 8f row 3 carry
+their own independent checks (none of them is the reference itself, so the header stays "unpinned"):
+  * tf.image.ssim / ssim_multiscale -> window-by-window numpy fp64 evaluation of the SSIM definition, and the
+    closed-form gradient against torch autograd (``tests/ssim_np.py``, ``tests/test_ssim_losses.py``);
+  * BatchNormalization / LayerNormalization, DepthwiseConv2D, GELU -> direct numpy / scipy formulas
+    (``tests/test_norm_cpu.py``, ``tests/test_convnext_cpu.py``);
+  * tf.image.resize 'nearest' / 'bicubic' -> Pillow's float-image resize, an independent implementation of the
+    same definitions (``tests/test_resize_cpu.py``).
 """

@@ -123,6 +123,58 @@ def resize_bilinear(x, ho, wo):
     return F.interpolate(x, size=(ho, wo), mode='bilinear', align_corners=False, antialias=False)
 
 
+def _resize_matrix(n_in, n_out, method):
+    """(n_out, n_in) resampling matrix of one axis for tf.image.resize(method, antialias=False) -- the TF kernels
+    ResizeNearestNeighbor / ResizeBicubic with half_pixel_centers=True (tensorflow/core/kernels/image/
+    resize_nearest_neighbor_op.cc, resize_bicubic_op.cc; third-party, restated from the published source):
+    index arithmetic in float32 as TF does it."""
+    m = np.zeros((n_out, n_in), np.float64)
+    scale = np.float32(n_in) / np.float32(n_out)
+    for o in range(n_out):
+        if method == 'nearest':
+            i = min(int(np.floor((np.float32(o) + np.float32(0.5)) * scale)), n_in - 1)
+            m[o, i] = 1.0
+            continue
+        # bicubic: Keys kernel A=-0.5 through the 1024-entry coefficient table; taps outside the image get weight 0
+        # and the rest is renormalised (GetWeightsAndIndices<HalfPixelScaler, true>)
+        A = -0.5
+        loc = (np.float32(o) + np.float32(0.5)) * scale - np.float32(0.5)
+        fl = np.floor(loc)
+        off = int(np.rint(np.float32(loc - fl) * np.float32(1024.0)))
+
+        def near(t):
+            x = np.float32(t) / np.float32(1024.0)
+            return float(((A + 2) * x - (A + 3)) * x * x + 1)
+
+        def far(t):
+            x = np.float32(t) / np.float32(1024.0) + 1.0
+            return float(((A * x - 5 * A) * x + 8 * A) * x - 4 * A)
+        raw = [far(off), near(off), near(1024 - off), far(1024 - off)]
+        w, idx = [], []
+        for k in range(4):
+            want = int(fl) - 1 + k
+            got = min(max(want, 0), n_in - 1)
+            idx.append(got)
+            w.append(raw[k] if got == want else 0.0)
+        tot = sum(w)
+        if abs(tot) >= 1000.0 * np.finfo(np.float32).tiny:
+            w = [v / tot for v in w]
+        for i, v in zip(idx, w):
+            m[o, i] += v
+    return m
+
+
+def resize(x, ho, wo, method='bilinear'):
+    """keras Resizing(ho, wo, interpolation=method) on NCHW ``x`` -- blocks.py:457-491."""
+    if method == 'bilinear':
+        return resize_bilinear(x, ho, wo)
+    if method not in ('nearest', 'bicubic'):
+        raise NotImplementedError(method)
+    rh = torch.as_tensor(_resize_matrix(x.shape[2], ho, method), dtype=x.dtype)
+    rw = torch.as_tensor(_resize_matrix(x.shape[3], wo, method), dtype=x.dtype)
+    return torch.einsum('oh,nchw,pw->ncop', rh, x, rw)
+
+
 def maxpool2(x):
     """MaxPooling2D((2,2)) stride 2 'valid' -- blocks.py:613."""
     return F.max_pool2d(x, 2, 2)
@@ -336,10 +388,10 @@ def subpixel_block(p, name, x, scale, n_filters):
     return x
 
 
-def resize_conv_block(p, name, x, scale, n_filters):
-    """ResizeConvolutionBlock.call (bilinear) -- blocks.py:485-491."""
+def resize_conv_block(p, name, x, scale, n_filters, interpolation='bilinear'):
+    """ResizeConvolutionBlock.call -- blocks.py:485-491."""
     ho, wo = int(x.shape[2] * scale), int(x.shape[3] * scale)
-    return _conv(p, name + '/conv', resize_bilinear(x, ho, wo), n_filters)
+    return _conv(p, name + '/conv', resize(x, ho, wo, interpolation), n_filters)
 
 
 def deconv_block(p, name, x, scale, n_filters, output_activation=None):
@@ -499,7 +551,7 @@ def _backbone(p, x_in, backbone_block, n_filters, n_blocks, attention, activatio
 def net_postupsampling(p, inputs, backbone_block, upsampling, scale, n_channels_out=1,
                        n_filters=8, n_blocks=6, attention=False, activation='relu',
                        output_activation=None, localcon_layer=False, normalization=None, dropout_rate=0,
-                       dropout_variant=None):
+                       dropout_variant=None, rc_interpolation='bilinear'):
     """net_postupsampling -- sp_postups.py:14-217.  inputs: [x_lr NHWC] or [x_lr, s_hr]."""
     x_in = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
@@ -509,7 +561,7 @@ def net_postupsampling(p, inputs, backbone_block, upsampling, scale, n_channels_
     if upsampling == 'spc':
         x = subpixel_block(p, 'SubpixelConvolution', x, scale, n_filters)
     elif upsampling == 'rc':
-        x = resize_conv_block(p, 'ResizeConvolution', x, scale, n_filters)
+        x = resize_conv_block(p, 'ResizeConvolution', x, scale, n_filters, rc_interpolation)
     elif upsampling == 'dc':
         x = transition_block(p, 'TransitionDC', x, init_n_filters, activation)
         x = deconv_block(p, 'Deconvolution', x, scale, n_filters, activation)
@@ -543,7 +595,8 @@ def check_nblocks(shape, power):
 
 def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu',
              attention=False, decoder_upsampling='rc', output_activation=None, width_cap=256,
-             localcon_layer=False, normalization=None, dropout_rate=0, dropout_variant=None):
+             localcon_layer=False, normalization=None, dropout_rate=0, dropout_variant=None,
+             rc_interpolation='bilinear'):
     """unet_pin -- sp_preups.py:192-315 (the bottleneck block is never normalised, :266-268)."""
     x = _nchw(inputs[0])
     s_in = _nchw(inputs[1]) if len(inputs) > 1 else None
@@ -565,7 +618,7 @@ def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu'
         if decoder_upsampling == 'spc':
             x = subpixel_block(p, 'SubpixelConvolution%d' % (j + 1), x, 2, n_filters)
         elif decoder_upsampling == 'rc':
-            x = resize_conv_block(p, 'ResizeConvolution%d' % (j + 1), x, 2, n_filters)
+            x = resize_conv_block(p, 'ResizeConvolution%d' % (j + 1), x, 2, n_filters, rc_interpolation)
         elif decoder_upsampling == 'dc':
             x = deconv_block(p, 'Deconvolution%d' % (j + 1), x, 2, n_filters, activation)
         x = pad_concat(x, skip)
@@ -580,7 +633,7 @@ def unet_pin(p, inputs, n_filters, n_blocks, n_channels_out=1, activation='relu'
 def recnet_postupsampling(p, inputs, backbone_block, upsampling, scale, time_window,
                           n_channels_out=1, n_filters=8, n_blocks=4, attention=False,
                           activation='relu', output_activation=None, localcon_layer=False, normalization=None,
-                          dropout_rate=0, dropout_variant=None):
+                          dropout_rate=0, dropout_variant=None, rc_interpolation='bilinear'):
     """recnet_postupsampling -- spt_postups.py:12-163.  inputs[0]: (B,T,h,w,C) NTHWC;
     optional inputs[1]: (B,H,W,n_aux).  Output (B,T,H,W,n_channels_out)."""
     x5 = inputs[0].permute(0, 1, 4, 2, 3).contiguous()   # (B,T,C,h,w)
@@ -602,7 +655,7 @@ def recnet_postupsampling(p, inputs, backbone_block, upsampling, scale, time_win
     if upsampling == 'spc':
         xf = subpixel_block(p, 'SubpixelConvolution', xf, scale, n_filters_ups)
     elif upsampling == 'rc':
-        xf = resize_conv_block(p, 'ResizeConvolution', xf, scale, n_filters_ups)
+        xf = resize_conv_block(p, 'ResizeConvolution', xf, scale, n_filters_ups, rc_interpolation)
     elif upsampling == 'dc':
         xf = deconv_block(p, 'Deconvolution', xf, scale, n_filters_ups, None)   # App. B #8
     # upsampling == 'pin' (recnet_pin, spt_preups.py:100-118): no upsampler
