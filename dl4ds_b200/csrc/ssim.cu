@@ -216,6 +216,23 @@ __global__ void __launch_bounds__(256) ssim_maps_kernel(const float* __restrict_
     }
 }
 
+// ssim_multiscale's downsampling: pad odd sizes by one (mode SYMMETRIC = repeat the edge), avg_pool 2x2 stride 2
+__global__ void ssim_pool_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+    const int Hc = (H + 1) / 2, Wc = (W + 1) / 2;
+    const int64_t total = (int64_t)B * Hc * Wc * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        int64_t t = i / C;
+        const int j = (int)(t % Wc); t /= Wc;
+        const int r = (int)(t % Hc);
+        const int b = (int)(t / Hc);
+        const int r0 = 2 * r, r1 = min(2 * r + 1, H - 1), c0 = 2 * j, c1 = min(2 * j + 1, W - 1);
+        const float* p = x + (int64_t)b * H * W * C + c;
+        y[i] = 0.25f * ((__ldg(p + ((int64_t)r0 * W + c0) * C) + __ldg(p + ((int64_t)r0 * W + c1) * C)) +
+                        (__ldg(p + ((int64_t)r1 * W + c0) * C) + __ldg(p + ((int64_t)r1 * W + c1) * C)));
+    }
+}
+
 struct CombineArgs {
     int n_scales, n_planes, B, C;
     float pf[kMaxScales];
@@ -299,7 +316,7 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const float* __restrict__
     __syncthreads();
     const float cf = __ldg(coef + plane);
     float sum = 0.0f;
-    const int Hc = H / 2, Wc = W / 2;
+    const int Hc = (H + 1) / 2, Wc = (W + 1) / 2;     // pooled size; an odd edge row / column was mirrored: it counts twice
     for (int i = threadIdx.x; i < kTile * kTile; i += 256) {
         const int r = i / kTile, q = i % kTile;
         const int yy = qy0 + r, xx = qx0 + q;
@@ -315,7 +332,10 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const float* __restrict__
         const int64_t o = (((int64_t)b * H + yy) * W + xx) * C + c;
         const float x = __ldg(yp + o) - shp, y = __ldg(yt + o) - sht;
         float gq = cf * (t1 + 2.0f * x * t2 + y * t3);
-        if (up) gq += 0.25f * __ldg(up + (((int64_t)b * Hc + (yy >> 1)) * Wc + (xx >> 1)) * C + c);
+        if (up) {
+            const float mult = (((H & 1) && yy == H - 1) ? 2.0f : 1.0f) * (((W & 1) && xx == W - 1) ? 2.0f : 1.0f);
+            gq += 0.25f * mult * __ldg(up + (((int64_t)b * Hc + (yy >> 1)) * Wc + (xx >> 1)) * C + c);
+        }
         sum += gq;
         dy[o] = accumulate ? dy[o] + gq : gq;
     }
@@ -365,7 +385,7 @@ Layout make_layout(int B, int H, int W, int C, int nS) {
             l.grad[j] = o; o = align(o + (int64_t)B * h * w * C);
         }
         l.maps[j] = o; o = align(o + 3 * (int64_t)B * (h - kHalo) * (w - kHalo) * C);
-        h /= 2; w /= 2;
+        h = (h + 1) / 2; w = (w + 1) / 2;
     }
     l.total = o;
     return l;
@@ -380,10 +400,7 @@ int check_shape(int B, int H, int W, int C, int nS) {
         // tf.image.ssim asserts every image is at least filter_size wide at every scale
         DL4DS_REQUIRE(h >= kWin && w >= kWin, DL4DS_E_SHAPE,
                       "ssim_loss: %dx%d at scale %d is smaller than the 11x11 window", h, w, j);
-        if (j + 1 < nS)
-            DL4DS_REQUIRE(h % 2 == 0 && w % 2 == 0, DL4DS_E_UNSUPPORTED,
-                          "ssim_loss: odd size %dx%d at scale %d (SYMMETRIC padding not built)", h, w, j);
-        h /= 2; w /= 2;
+        h = (h + 1) / 2; w = (w + 1) / 2;       // odd sizes are SYMMETRIC-padded by one before the 2x2 pooling
     }
     return DL4DS_OK;
 }
@@ -440,10 +457,10 @@ int dl4ds_ssim_loss(const float* y_pred, const float* y_true, int B, int H, int 
     for (int j = 0; j < n_scales; ++j) {
         const int h = l.Hs[j], w = l.Ws[j];
         if (j > 0) {   // ssim_multiscale: avg_pool(ksize 2, stride 2) between scales
-            int r1 = dl4ds_avgpool_coarsen(xp, ws + l.img_p[j], B, l.Hs[j - 1], l.Ws[j - 1], C, 2, stream);
-            if (r1 != DL4DS_OK) return r1;
-            r1 = dl4ds_avgpool_coarsen(xt, ws + l.img_t[j], B, l.Hs[j - 1], l.Ws[j - 1], C, 2, stream);
-            if (r1 != DL4DS_OK) return r1;
+            const int64_t np_ = (int64_t)B * h * w * C;
+            const int pg = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(np_, 256), 8 * kNumSMs));
+            ssim_pool_kernel<<<pg, 256, 0, st>>>(xp, ws + l.img_p[j], B, l.Hs[j - 1], l.Ws[j - 1], C);
+            ssim_pool_kernel<<<pg, 256, 0, st>>>(xt, ws + l.img_t[j], B, l.Hs[j - 1], l.Ws[j - 1], C);
             xp = ws + l.img_p[j];
             xt = ws + l.img_t[j];
         }

@@ -179,8 +179,8 @@ int dl4ds_pixel_loss(const float* y_pred, const float* y_true, float* loss_out, 
  * :62-93,134-151, which add dl4ds_pixel_loss terms).  tf.image.ssim / tf.image.ssim_multiscale semantics:
  * 11x11 gaussian (sigma 1.5), k1 0.01, k2 0.03, VALID filtering, max_val = max(both) - min(both), each tensor
  * shifted by its own minimum when negative.  n_scales 1 = SSIM; > 1 = MS-SSIM with `power_factors` (HOST
- * array, n_scales entries; the reference passes 4: losses.py:128), 2x2 average pooling between scales (even
- * sizes only).  loss_out[0] += scale * mean_b((1 - ssim_b) / 2); if dy != NULL, dy (+)= scale * d/d y_pred,
+ * array, n_scales entries; the reference passes 4: losses.py:128), 2x2 average pooling between scales (odd
+ * sizes SYMMETRIC-padded by one first, as tf.image.ssim_multiscale does).  loss_out[0] += scale * mean_b((1 - ssim_b) / 2); if dy != NULL, dy (+)= scale * d/d y_pred,
  * including the gradient through the dynamic range and the shift (arg-max / arg-min elements of y_pred).
  * `ws`: dl4ds_ssim_loss_workspace_floats(...) floats of device scratch, 16-byte aligned (no allocation inside).
  * ------------------------------------------------------------------------------------------- */

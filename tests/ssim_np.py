@@ -58,7 +58,23 @@ def _maps(x, y, C1, C2, cs_only):
 
 
 def _pool(a):
+    """ssim_multiscale's downsampling: SYMMETRIC pad of odd sizes by one (= repeat the edge), 2x2 mean."""
+    a = np.pad(a, ((0, a.shape[0] % 2), (0, a.shape[1] % 2)), mode='edge')
     return a.reshape(a.shape[0] // 2, 2, a.shape[1] // 2, 2).mean(axis=(1, 3))
+
+
+def _unpool(g, shape):
+    """adjoint of _pool: a quarter of the coarse gradient to each of the four sources; a mirrored edge row / column
+    is its own neighbour and collects twice."""
+    up = np.repeat(np.repeat(g, 2, 0), 2, 1) / 4.0
+    out = up[:shape[0], :shape[1]].copy()
+    if shape[0] % 2:
+        out[-1, :] += up[shape[0], :shape[1]]
+    if shape[1] % 2:
+        out[:, -1] += up[:shape[0], shape[1]]
+    if shape[0] % 2 and shape[1] % 2:
+        out[-1, -1] += up[shape[0], shape[1]]
+    return out
 
 
 def loss_and_grad(y_true, y_pred, multiscale):
@@ -89,7 +105,7 @@ def loss_and_grad(y_true, y_pred, multiscale):
             coef = (-0.5 / B) * dms / maps[j][0].size
             gj = coef * (_filt_t(maps[j][1]) + 2 * xs[j] * _filt_t(maps[j][2]) + ys[j] * _filt_t(maps[j][3]))
             if g is not None:
-                gj = gj + np.repeat(np.repeat(g, 2, 0), 2, 1) / 4.0
+                gj = gj + _unpool(g, gj.shape)
             g = gj
             dL += coef * (maps[j][4].sum() * 2 * K1 * K1 * L + maps[j][5].sum() * 2 * K2 * K2 * L)
         dy[b] = g
