@@ -19,6 +19,8 @@ their own independent checks (none of them is the reference itself, so the heade
     closed-form gradient against torch autograd (``tests/ssim_np.py``, ``tests/test_ssim_losses.py``);
   * BatchNormalization / LayerNormalization, DepthwiseConv2D, GELU -> direct numpy / scipy formulas
     (``tests/test_norm_cpu.py``, ``tests/test_convnext_cpu.py``);
-  * tf.image.resize 'nearest' / 'bicubic' -> Pillow's float-image resize, an independent implementation of the
-    same definitions (``tests/test_resize_cpu.py``).
+  * tf.image.resize 'nearest' / 'bicubic' / 'bilinear' -> Pillow's float-image resize (and OpenCV for bilinear),
+    independent implementations of the same definitions (``tests/test_resize_cpu.py``);
+  * Conv2D 'same' -> scipy.signal.correlate2d; depth_to_space -> einops.rearrange; INTER_AREA coarsening -> OpenCV
+    (``tests/test_oracle_independent.py``).
 """
