@@ -5,10 +5,10 @@ Each builder keeps the signature and the model naming (``<backbone>_<upsampling>
 ``dl4ds/models/`` and returns a :class:`Model` whose graph function runs over the CUDA engine
 (``engine.Ctx``) or, for shape/parameter inference, over ``spec.SpecCtx``.
 
-Scope: ``normalization=None``, ``dropout_rate=0`` (model defaults),
-activations in {None, relu, sigmoid, tanh}, bilinear resize-convolution; backbones
-convnet / resnet / densenet / unet.  Anything else raises ``NotImplementedError`` -- there is no
-fallback path.
+Scope (SURVEY.md sections 8a and 8f row 3): backbones convnet / resnet / densenet / unet / convnext (and the
+recurrent ConvLSTM networks), ``normalization`` None / 'bn' / 'ln', every ``dropout_variant``, activations in
+{None, relu, sigmoid, tanh, gelu}, bilinear / nearest / bicubic resize-convolution.  Anything else raises
+``NotImplementedError`` (or the reference's own ``ValueError``) -- there is no fallback path.
 """
 import math
 from collections import OrderedDict
