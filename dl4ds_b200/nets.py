@@ -96,12 +96,33 @@ class Model:
             print_fn('  %-40s %12d' % (g, n))
         print_fn('Total params: %d' % self.count_params())
 
+    @staticmethod
+    def _resolve_device(device):
+        """torch.device with an explicit index: 'cuda' means the current device ('cuda' != 'cuda:0' for torch)."""
+        d = torch.device(device)
+        if d.type == 'cuda' and d.index is None:
+            d = torch.device('cuda', torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        return d
+
     def to(self, device='cuda'):
-        if self.arena is None or self.arena.device != torch.device(device):
+        """Place the parameter arena on ``device``.  A no-op when it already lives on that physical device; a real
+        move carries the whole optimizer state (theta, Adam m / v, iteration count, dropout RNG state) and drops
+        every captured CUDA graph / packed weight image, which hold raw pointers into the old arena."""
+        dev = self._resolve_device(device)
+        if self.arena is None:
+            self.arena = Arena(self.spec, dev)
+        elif self._resolve_device(self.arena.device) != dev:
             old = self.arena
-            self.arena = Arena(self.spec, device)
-            if old is not None:
-                self.arena.theta.copy_(old.theta)
+            new = Arena(self.spec, dev)
+            for name in ('theta', 'm', 'v'):
+                getattr(new, name).copy_(getattr(old, name))
+            new.t = old.t
+            if getattr(old, '_rng', None) is not None:
+                new._rng = old._rng.to(dev)
+            self.arena = new
+            self._predict_graphs = {}
+            self._pack_cache = {}
+            self.arena_generation = getattr(self, 'arena_generation', 0) + 1   # captured steps re-capture on a change
         return self
 
     def init_weights(self, seed=0):
@@ -155,6 +176,8 @@ class Model:
         (cgan.py:288-292,375): resuming from it continues the Adam trajectory exactly."""
         a = self.arena
         out = {'__iterations__': np.asarray(a.t, np.int64), '__model_name__': np.asarray(self.name)}
+        if getattr(a, '_rng', None) is not None:
+            out['__rng__'] = a._rng.detach().cpu().numpy()          # dropout Philox {seed, step}
         for n in a.spec:
             key = n.replace('/', '|')
             out[key] = a.param(n).detach().cpu().numpy()
@@ -171,6 +194,8 @@ class Model:
             a = self.arena
             full = '__iterations__' in files
             a.t = int(z['__iterations__']) if full else 0
+            if '__rng__' in files:
+                a.seed_rng(int(z['__rng__'][0]), int(z['__rng__'][1]))
             for n in a.spec:
                 key = n.replace('/', '|')
                 for flat, tag in ((a.m, '__adam_m__'), (a.v, '__adam_v__')):

@@ -75,7 +75,11 @@ class SupervisedStep:
         self.target = torch.zeros(target_shape, dtype=torch.float32, device=dev)
         self.loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
         self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else None
+        # lr_t staging: a small ring of pinned scalars, each guarded by an event recorded after its H2D copy, so a
+        # host that runs a step ahead (the pipelined fit loops) never overwrites a value still waiting to be copied
+        self._lr_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(4)] if dev.type == 'cuda' else None
+        self._lr_events = [None] * 4
+        self._lr_slot = 0
         self.use_graph = use_graph
         self.graph_fb = None        # zero-grad + forward + loss + backward
         self.graph_opt = None       # adam
@@ -112,8 +116,15 @@ class SupervisedStep:
         lr = self.schedule(t - 1)     # Keras evaluates the schedule at `iterations` before increment
         lr_t = lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
         if self._lr_host is not None:
-            self._lr_host[0] = lr_t
-            self.lr_t_dev.copy_(self._lr_host, non_blocking=True)
+            k = self._lr_slot
+            self._lr_slot = (k + 1) % len(self._lr_host)
+            if self._lr_events[k] is not None:
+                self._lr_events[k].synchronize()
+            self._lr_host[k][0] = lr_t
+            self.lr_t_dev.copy_(self._lr_host[k], non_blocking=True)
+            if self._lr_events[k] is None:
+                self._lr_events[k] = torch.cuda.Event()
+            self._lr_events[k].record()
         else:
             self.lr_t_dev.fill_(lr_t)
 
@@ -154,6 +165,9 @@ class SupervisedStep:
     def run(self):
         """One optimizer step on the batch in the static buffers.  Returns the device loss scalar
         (valid after the stream is synchronised / ``.item()``)."""
+        if self.model.arena is not self.arena:
+            raise RuntimeError('the model arena was replaced (Model.to() onto another device) after this step was '
+                               'built: its captured graphs point into the old arena -- build a new SupervisedStep')
         self._set_lr_t()
         if self.graph_fb is not None:
             self.graph_fb.replay()

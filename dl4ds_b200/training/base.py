@@ -43,6 +43,15 @@ class DataParallel:
             raise ValueError("device not recognized" if device != 'CPU' else
                              "device='CPU' is not available: dl4ds_b200 runs the hot path on CUDA only")
 
+    def allreduce_mean_scalar(self, value):
+        """Mean of a host scalar over the ranks (hvd.callbacks.MetricAverageCallback's role for val_loss)."""
+        if self.dist is None or self.size == 1:
+            return float(value)
+        import torch
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self.torch_device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item()) / self.size
+
 
 class Trainer(ABC):
     """Trainer -- training/base.py:24-152 (same arguments, checks and exception types)."""

@@ -165,6 +165,11 @@ class SupervisedTrainer(Trainer):
             self.model = self.trained_model
             self.model.to(self.dp.torch_device)
             print('Loading pre-trained model')
+        if getattr(self.model.arena, '_rng', None) is None:
+            # dropout masks: seeded from the trainer seed (OS entropy when unseeded) + the rank, so replicas and
+            # unseeded runs draw independent masks; a resumed model keeps the RNG state its checkpoint carried
+            base = self.seed if self.seed is not None else int.from_bytes(os.urandom(6), 'little')
+            self.model.arena.seed_rng((int(base) * 2654435761 + 7919 * self.dp.rank) & 0x7FFFFFFFFFFFFFFF)
         self._compile()
 
     def _batch_shapes(self):
@@ -357,6 +362,11 @@ class SupervisedTrainer(Trainer):
                 tot += lval
             loss = tot / max(n_train, 1)
             val = self.evaluate(self.ds_val, self.validation_steps)
+            if self.dp.size > 1:
+                # every rank draws its own validation batches: average val_loss over the ranks so that the
+                # early-stopping / best-model decisions below are identical everywhere (a rank that left the epoch
+                # loop alone would leave the others waiting in the next gradient all-reduce)
+                val = self.dp.allreduce_mean_scalar(val)
             self.fithist.history['loss'].append(loss)
             self.fithist.history['val_loss'].append(val)
             self.fithist.epoch.append(epoch)

@@ -243,3 +243,32 @@ def test_predict_graphed_equals_eager(cuda):
         assert out.shape == (22, 64, 64, 1)
         assert np.abs(out - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
         m.arena.theta.mul_(1.5)                           # change the parameters, predict again
+
+
+def test_resume_from_checkpoint_continues_the_adam_trajectory(cuda, tmp_path):
+    """train k steps, save_checkpoint, load into a fresh model, resume through
+    ``trained_model`` -- the resumed losses equal uninterrupted training (Adam m / v / t survive ``Model.to``)."""
+    hr = _data(32, 32, 21)
+    lr = hr.reshape(32, 8, 4, 8, 4, 1).mean(axis=(2, 4)).astype(np.float32)
+    kw = dict(scale=4, batch_size=8, epochs=1, learning_rate=(1e-3, 1e-4), lr_decay_after=4, verbose=False,
+              math='tf32x3', n_blocks=2)
+    tr = SupervisedTrainer('resnet', 'spc', hr, hr[:8], hr[:8], seed=5, **kw)
+    tr.setup_model()
+    for i in range(3):
+        tr.train_on_batch([lr[8 * i:8 * i + 8]], hr[8 * i:8 * i + 8])
+    path = str(tmp_path / 'ck.npz')
+    tr.model.save_checkpoint(path)
+    ref = [tr.train_on_batch([lr[8 * (i % 4):8 * (i % 4) + 8]], hr[8 * (i % 4):8 * (i % 4) + 8]) for i in range(3, 6)]
+    m2 = nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (8, 8), n_blocks=2, math='tf32x3')
+    m2.to('cuda').load_checkpoint(path)            # index-less 'cuda', as load_checkpoint / set_weights do
+    assert m2.arena.t == 3
+    tr2 = SupervisedTrainer('resnet', 'spc', hr, hr[:8], hr[:8], trained_model=m2, trained_epochs=0, seed=99, **kw)
+    tr2.setup_model()
+    assert tr2.model.arena.t == 3 and float(tr2.model.arena.m.abs().max()) > 0     # slots survived to(cuda:0)
+    got = [tr2.train_on_batch([lr[8 * (i % 4):8 * (i % 4) + 8]], hr[8 * (i % 4):8 * (i % 4) + 8]) for i in range(3, 6)]
+    assert np.allclose(got, ref, rtol=2e-4), (got, ref)
+    # Predictor on the trained model must not replace the arena the trainer's captured step updates
+    arena = tr2.model.arena
+    Predictor(tr2, hr[:8], scale=4, array_in_hr=True, batch_size=8).run()
+    assert tr2.model.arena is arena
+    tr2.train_on_batch([lr[:8]], hr[:8])
