@@ -125,7 +125,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 h[j] = tf32_rna(v[j]);
-                l[j] = v[j] - h[j];
+                l[j] = tf32_rna(v[j] - h[j]);      // on the tf32 grid: the tensor core's truncation is then exact
             }
             *reinterpret_cast<float4*>(hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
@@ -435,7 +435,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                             const float vv[8] = {v0[o].x, v0[o].y, v0[o].z, v0[o].w, v1[o].x, v1[o].y, v1[o].z, v1[o].w};
                             float l[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) l[e] = vv[e] - tf32_trunc(vv[e]);
+                            for (int e = 0; e < 8; ++e) l[e] = tf32_lo_of_trunc(vv[e]);
                             tmem_st8(trow + (uint32_t)((s * p.group + j) * p.kc + c), l);
                         }
                     }
@@ -495,8 +495,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcFwdParams
                 for (int u = et; u < units; u += 128) {
                     const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 16);
                     float4 l;
-                    l.x = v.x - tf32_trunc(v.x); l.y = v.y - tf32_trunc(v.y);
-                    l.z = v.z - tf32_trunc(v.z); l.w = v.w - tf32_trunc(v.w);
+                    l.x = tf32_lo_of_trunc(v.x); l.y = tf32_lo_of_trunc(v.y);
+                    l.z = tf32_lo_of_trunc(v.z); l.w = tf32_lo_of_trunc(v.w);
                     *reinterpret_cast<float4*>(a_lo + u * 16) = l;
                 }
                 fence_proxy_async_smem();
@@ -551,7 +551,7 @@ static bool fwd_shape_supported(const ConvArgs& a, int math_mode) {
     if (a.d2s_r != 1 && (a.d2s_r != 2 || (a.Cout / 4) % 4)) return false;
     if (a.KH * a.KW > 81) return false;
     int bw, bh;
-    return tile_geometry(a.H, a.W, 128, &bw, &bh);
+    return tile_geometry(a.H, a.W, 128, &bw, &bh) || conv2d_fwd_halo_supported(a, math_mode);
 }
 
 static bool fwd_supported(const ConvArgs& a, int math_mode) {
@@ -609,6 +609,12 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     const int64_t n = pack_floats(a.KH * a.KW, a.Cin, a.Cout);
     p.wp_hi = reinterpret_cast<const float*>(ws);
     p.wp_lo = p.wp_hi + n;
+    {   // halo-tile kernel (conv_tc_halo.cu) first; the per-tap kernel below keeps the shapes outside its domain
+        const int rc = conv2d_fwd_tc_halo(a, math_mode, p.wp_hi, p.wp_lo, st);
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+        int bw_, bh_;
+        if (!tile_geometry(a.H, a.W, 128, &bw_, &bh_)) return DL4DS_E_UNSUPPORTED;
+    }
     p.bias = a.bias; p.res = a.res; p.y = a.y; p.res_ld = a.res_ld; p.y_ld = a.y_ld;
     p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout;
     p.KW = a.KW; p.ntaps = a.KH * a.KW; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
@@ -910,7 +916,7 @@ __global__ void __launch_bounds__(kWgThreads) conv_tc_wgrad_kernel(const __grid_
                     if (X3) {
                         const float h = tf32_rna(vv[r]);
                         *reinterpret_cast<float*>(dst + off) = h;
-                        *reinterpret_cast<float*>(dst + p.op_bytes + off) = vv[r] - h;
+                        *reinterpret_cast<float*>(dst + p.op_bytes + off) = tf32_rna(vv[r] - h);
                     } else {
                         *reinterpret_cast<float*>(dst + off) = vv[r];
                     }

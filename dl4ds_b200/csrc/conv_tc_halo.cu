@@ -1,0 +1,423 @@
+// Second-generation tcgen05 forward / input-gradient convolution kernel: ONE halo tile per channel chunk.
+//
+// conv_tc.cu's first kernel loads one TMA box per (kernel tap, channel chunk) and re-splits it per tap: a 3x3 layer
+// writes every activation element to shared memory 9 times and splits it 9 times, and its MMA issue loop rebuilt both
+// descriptors per instruction.  Round-2 measurements (scratch/umma_rate3.cu, profiles/r02a_umma_rate3.log) showed the
+// tensor pipe takes a kind::tf32 M=128 K=8 MMA every max(44, 32 + N/4, N/2) cycles -- the "95-119 cycle floor" of round 1
+// was the issuing thread's own scalar work -- so the old kernel was bound by shared-memory staging traffic and by its
+// issue loop, not by the tensor core.  Here:
+//   * tile = 16 rows x 8 pixels of one image (M = 128); per channel chunk (KC = 8/16/32 channels) ONE TMA box
+//     {KC, 8+KW-1, 16+KH-1, 1} lands the halo tile (out-of-bounds = the zero padding), K-major, hardware swizzle;
+//   * 3xTF32: the four splitter warps write lo = rna(v - trunc(v)) ONCE per halo tile (the raw tile is the hi operand);
+//   * every kernel tap reads the SAME halo tile through a shifted UMMA descriptor: an 8-row core-matrix group is 8
+//     consecutive pixels of one image row, so tap (kh, kw) is start address + (kh*HWp + kw)*span with the group stride
+//     (SBO) = HWp*span -- the swizzle of both TMA and the tensor core is a function of the shared-memory address bits,
+//     which keeps a row-shifted view consistent;
+//   * weights stream through their own ring (items = a few taps of one chunk: [W_hi ; W_lo] per tap), fed by a second
+//     producer warp, so the next halo tile is prefetched independently of the weight traffic;
+//   * the issuing thread keeps descriptor templates in registers and only adds byte offsets.
+// Shared-memory bytes per 128 pixels, tap and K = 8 (48 -> 48 layer): 27.6 KB before (4 TMA + 8 split + 3 weights + 12.6
+// operand reads), 16.5 KB now (0.9 + 1.3 + 3 + 12.6... the operand reads of the two MMAs dominate).
+//
+// Same epilogue as conv_tc.cu (bias, residual, activation, beta accumulate, depth_to_space store), accumulator
+// double-buffered in TMEM, persistent CTAs (one per SM).
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "tc_common.cuh"
+
+namespace dl4ds {
+
+using namespace tc;
+
+struct HaloParams {
+    const float* wp_hi;
+    const float* wp_lo;
+    const float* bias;
+    const float* res;
+    float* y;
+    int res_ld, y_ld;
+    int H, W, Cin, Cout, Npad;
+    int KH, KW, ntaps, pad_t, pad_l;
+    int tiles_x, tiles_per_img, ntiles;
+    int kc, span, nchunks, ksteps;
+    uint32_t layout;
+    int act, d2s_r, beta;
+    int HWp, HHp;            // halo tile: pixels per row (pitch), rows
+    int a_box_bytes;         // bytes one TMA box delivers (HWp*HHp*span)
+    int a_bytes;             // the same rounded up to 1024
+    int a_stage_bytes;       // a_bytes * (x3 ? 2 : 1)
+    int a_stages;
+    int b_bytes;             // one weight tile: Npad*span
+    int b_tap_bytes;         // b_bytes * (x3 ? 2 : 1): [hi ; lo] of one tap
+    int tg, ngroups;         // taps per weight stage, stages per chunk
+    int b_stage_bytes, b_stages;
+    int b_base;              // byte offset of the weight ring
+    int acc_stride, tmem_cols;
+    int base_off_mode;       // probe switch: 1 = put (start address >> 7) & 7 into the descriptor's base-offset field
+};
+
+constexpr int kHaloThreads = 480;   // warp 0 A producer, 1 MMA, 2-9 epilogue, 10-13 splitter, 14 B producer
+constexpr int kHaloMaxStages = 8;
+constexpr int BWt = 8, BHt = 16;    // tile: 8 pixels x 16 rows
+
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off, int base_off_mode, uint32_t start_addr) {
+    uint64_t r = d + (uint64_t)(byte_off >> 4);
+    if (base_off_mode) r |= (uint64_t)(((start_addr + byte_off) >> 7) & 7u) << 49;
+    return r;
+}
+
+template <bool X3, bool STACKN>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[kHaloMaxStages];
+    __shared__ __align__(8) uint64_t a_conv[kHaloMaxStages];
+    __shared__ __align__(8) uint64_t a_empty[kHaloMaxStages];
+    __shared__ __align__(8) uint64_t b_full[kHaloMaxStages];
+    __shared__ __align__(8) uint64_t b_empty[kHaloMaxStages];
+    __shared__ __align__(8) uint64_t bar_tfull[2];
+    __shared__ __align__(8) uint64_t bar_tempty[2];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[256];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.a_stages; ++s) {
+            mbar_init(smem_u32(&a_full[s]), 1);
+            mbar_init(smem_u32(&a_conv[s]), 4);
+            mbar_init(smem_u32(&a_empty[s]), 1);
+        }
+        for (int s = 0; s < p.b_stages; ++s) {
+            mbar_init(smem_u32(&b_full[s]), 1);
+            mbar_init(smem_u32(&b_empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bar_tfull[b]), 1);
+            mbar_init(smem_u32(&bar_tempty[b]), 8);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_x);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== halo-tile producer (TMA) =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int img = tile / p.tiles_per_img;
+                const int trem = tile - img * p.tiles_per_img;
+                const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+                const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
+                for (int c = 0; c < p.nchunks; ++c) {
+                    mbar_wait(smem_u32(&a_empty[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&a_full[s]);
+                    mbar_arrive_expect_tx(full, (uint32_t)p.a_box_bytes);
+                    tma_load_4d(smem_base + (uint32_t)(s * p.a_stage_bytes), &tmap_x, full, c * p.kc, x0, y0, img);
+                    if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 14) {
+        // ===================== weight producer (bulk copies) =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const size_t tile_floats = (size_t)p.Npad * p.kc;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                for (int c = 0; c < p.nchunks; ++c) {
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        const int t0 = g * p.tg;
+                        const int n = min(p.tg, p.ntaps - t0);
+                        mbar_wait(smem_u32(&b_empty[s]), ph ^ 1u);
+                        const uint32_t full = smem_u32(&b_full[s]);
+                        mbar_arrive_expect_tx(full, (uint32_t)(n * p.b_tap_bytes));
+                        const uint32_t sb = smem_base + (uint32_t)(p.b_base + s * p.b_stage_bytes);
+                        for (int j = 0; j < n; ++j) {
+                            // packed images are [tap][chunk][Npad][kc]
+                            const size_t woff = ((size_t)(t0 + j) * p.nchunks + c) * tile_floats;
+                            bulk_load(sb + (uint32_t)(j * p.b_tap_bytes), p.wp_hi + woff, (uint32_t)p.b_bytes, full);
+                            if (X3)
+                                bulk_load(sb + (uint32_t)(j * p.b_tap_bytes + p.b_bytes), p.wp_lo + woff, (uint32_t)p.b_bytes, full);
+                        }
+                        if (++s == p.b_stages) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, p.Npad, 0, 0);
+            const uint32_t idesc2 = make_idesc_tf32(128, 2 * p.Npad, 0, 0);
+            const uint32_t sbo_a = (uint32_t)(p.HWp * p.span);
+            const uint32_t sbo_b = 8u * (uint32_t)p.span;
+            // descriptor templates (address field zero): add (byte address >> 4)
+            const uint64_t tmpl_a = make_smem_desc(0, 16, sbo_a, p.layout);
+            const uint64_t tmpl_b = make_smem_desc(0, 16, sbo_b, p.layout);
+            const uint32_t row_bytes = (uint32_t)(p.HWp * p.span);
+            const uint32_t lo_off = (uint32_t)p.a_bytes;
+            const int bom = p.base_off_mode;
+            int as = 0, bs = 0;
+            uint32_t aph = 0, bph = 0;
+            int tcount = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+                const int ab = tcount & 1;
+                mbar_wait(smem_u32(&bar_tempty[ab]), (uint32_t)(((tcount >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t td = tmem_d + (uint32_t)(ab * p.acc_stride);
+                uint32_t accumulate = 0;
+                for (int c = 0; c < p.nchunks; ++c) {
+                    mbar_wait(smem_u32(X3 ? &a_conv[as] : &a_full[as]), aph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + (uint32_t)(as * p.a_stage_bytes);
+                    const uint64_t da_base = tmpl_a + (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                    int kh = 0, kw = 0;
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        const int n = min(p.tg, p.ntaps - g * p.tg);
+                        mbar_wait(smem_u32(&b_full[bs]), bph);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_base + (uint32_t)(p.b_base + bs * p.b_stage_bytes);
+                        const uint64_t db_base = tmpl_b + (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+                        for (int j = 0; j < n; ++j) {
+                            const uint32_t a_off = (uint32_t)kh * row_bytes + (uint32_t)(kw * p.span);
+                            const uint32_t b_off = (uint32_t)(j * p.b_tap_bytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < p.ksteps) {
+                                    const uint32_t ko = (uint32_t)k * 32u;
+                                    const uint64_t da = desc_add(da_base, a_off + ko, bom, a_addr);
+                                    const uint64_t db = desc_add(db_base, b_off + ko, 0, 0);
+                                    if (X3 && STACKN) {
+                                        // A_hi x [W_hi ; W_lo] -> columns [0, 2 Npad); A_lo x W_hi -> columns [0, Npad)
+                                        const uint64_t dal = desc_add(da_base, a_off + ko + lo_off, bom, a_addr);
+                                        umma_tf32(td, da, db, idesc2, accumulate);
+                                        umma_tf32(td, dal, db, idesc, 1u);
+                                    } else if (X3) {
+                                        const uint64_t dal = desc_add(da_base, a_off + ko + lo_off, bom, a_addr);
+                                        const uint64_t dbl = desc_add(db_base, b_off + ko + (uint32_t)p.b_bytes, 0, 0);
+                                        umma_tf32(td, dal, db, idesc, accumulate);
+                                        umma_tf32(td, da, dbl, idesc, 1u);
+                                        umma_tf32(td, da, db, idesc, 1u);
+                                    } else {
+                                        umma_tf32(td, da, db, idesc, accumulate);
+                                    }
+                                    accumulate = 1u;
+                                }
+                            }
+                            if (++kw == p.KW) { kw = 0; ++kh; }
+                        }
+                        umma_commit(smem_u32(&b_empty[bs]));
+                        if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+                    }
+                    umma_commit(smem_u32(&a_empty[as]));
+                    if (++as == p.a_stages) { as = 0; aph ^= 1u; }
+                }
+                umma_commit(smem_u32(&bar_tfull[ab]));
+            }
+        }
+    } else if (warp < 10) {
+        // ===================== epilogue (warps 2-9) =====================
+        // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant take alternate 16-column
+        // blocks.  Thread = one output pixel (TMEM lane), 16 consecutive channels per block.
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const int ry = row / BWt, rx = row - ry * BWt;
+        const int r = p.d2s_r;
+        const int Cd = p.Cout / (r * r);
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+            const int ab = tcount & 1;
+            const int img = tile / p.tiles_per_img;
+            const int trem = tile - img * p.tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int oy = ty * BHt + ry, ox = tx * BWt + rx;
+            const int64_t pix = ((int64_t)img * p.H + oy) * p.W + ox;
+            const float* __restrict__ resp = p.res ? p.res + pix * p.res_ld : nullptr;
+            float* __restrict__ yp = p.y + pix * p.y_ld;
+            const int64_t hr_row0 = ((int64_t)img * p.H * r + (int64_t)oy * r) * ((int64_t)p.W * r) + (int64_t)ox * r;
+            mbar_wait(smem_u32(&bar_tfull[ab]), (uint32_t)((tcount >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.acc_stride);
+            for (int c0 = half * 16; c0 < p.Npad; c0 += 32) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                if (X3 && STACKN) {
+                    float v2[16];
+                    tmem_ld16(taddr + (uint32_t)(p.Npad + c0), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                }
+                if (c0 >= p.Cout) continue;
+                float4 rs[4];
+                if (resp) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        rs[j] = (c0 + 4 * j < p.Cout) ? __ldg(reinterpret_cast<const float4*>(resp + c0) + j)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                int g = 0, cg = c0;
+                if (r > 1) { g = c0 / Cd; cg = c0 - g * Cd; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int co = c0 + 4 * j;
+                    if (co >= p.Cout) break;
+                    const float4 b = *reinterpret_cast<const float4*>(&bias_s[co]);
+                    float4 o = make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w);
+                    if (resp) { o.x += rs[j].x; o.y += rs[j].y; o.z += rs[j].z; o.w += rs[j].w; }
+                    o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
+                    o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
+                    if (r == 1) {
+                        float4* dst = reinterpret_cast<float4*>(yp + co);
+                        if (p.beta) {
+                            const float4 old = *dst;
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *dst = o;
+                    } else {
+                        if (cg >= Cd) { cg -= Cd; ++g; }
+                        const int di = g / r, dj = g - di * r;
+                        const int64_t hp = hr_row0 + (int64_t)di * p.W * r + dj;
+                        *reinterpret_cast<float4*>(p.y + hp * p.y_ld + cg) = o;
+                        cg += 4;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_warp(smem_u32(&bar_tempty[ab]));
+        }
+    } else if (warp < 14) {
+        // ===================== operand splitter (warps 10-13, x3 mode): once per halo tile =====================
+        if (X3) {
+            const int et = threadIdx.x - 320;          // 0..127
+            uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+            const int units = p.a_box_bytes >> 4;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                for (int c = 0; c < p.nchunks; ++c) {
+                    mbar_wait(smem_u32(&a_full[s]), ph);
+                    const uint8_t* a_hi = smem_al + (size_t)s * p.a_stage_bytes;
+                    uint8_t* a_lo = smem_al + (size_t)s * p.a_stage_bytes + p.a_bytes;
+                    // the raw tile is the hi operand (kind::tf32 reads the top 19 bits); lo is rounded onto the tf32 grid
+#pragma unroll 4
+                    for (int u = et; u < units; u += 128) {
+                        const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 16);
+                        float4 l;
+                        l.x = tf32_lo_of_trunc(v.x); l.y = tf32_lo_of_trunc(v.y);
+                        l.z = tf32_lo_of_trunc(v.z); l.w = tf32_lo_of_trunc(v.w);
+                        *reinterpret_cast<float4*>(a_lo + u * 16) = l;
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive_warp(smem_u32(&a_conv[s]));
+                    if (++s == p.a_stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+}
+
+extern std::atomic<long long> g_tc_launches;
+std::atomic<long long> g_halo_launches{0};
+
+// shape part of the eligibility test
+bool conv2d_fwd_halo_supported(const ConvArgs& a, int math_mode) {
+    static const bool disabled = [] { const char* e = getenv("DL4DS_TC_NO_HALO"); return e && e[0] == '1'; }();
+    if (disabled) return false;
+    if (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3) return false;
+    if (a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W) return false;
+    if (a.Cin % 8 || a.Cout % 8 || a.Cout > 256) return false;
+    if (a.W % BWt || a.H % BHt) return false;
+    if (BWt + a.KW - 1 > 256 || BHt + a.KH - 1 > 256) return false;
+    return true;
+}
+
+// weights already packed ([tap][chunk][Npad][kc], hi then lo) by conv2d_pack_tc
+int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, const float* wp_lo, cudaStream_t st) {
+    if (!conv2d_fwd_halo_supported(a, math_mode)) return DL4DS_E_UNSUPPORTED;
+    const bool x3 = math_mode == DL4DS_MATH_TF32X3;
+    const Chunk c = pick_chunk(a.Cin);
+    HaloParams p;
+    p.wp_hi = wp_hi; p.wp_lo = wp_lo;
+    p.bias = a.bias; p.res = a.res; p.y = a.y; p.res_ld = a.res_ld; p.y_ld = a.y_ld;
+    p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout;
+    p.Npad = (a.Cout + 15) / 16 * 16;
+    p.KH = a.KH; p.KW = a.KW; p.ntaps = a.KH * a.KW; p.pad_t = a.pad_t; p.pad_l = a.pad_l;
+    p.tiles_x = a.W / BWt;
+    p.tiles_per_img = p.tiles_x * (a.H / BHt);
+    p.ntiles = a.N * p.tiles_per_img;
+    p.kc = c.kc; p.span = c.span; p.layout = c.layout;
+    p.nchunks = a.Cin / c.kc;
+    p.ksteps = c.kc / 8;
+    p.act = a.act; p.d2s_r = a.d2s_r; p.beta = a.beta;
+    static const int pitch_align = [] { const char* e = getenv("DL4DS_HALO_PITCH_ALIGN"); return e ? atoi(e) : 1; }();
+    static const int base_off_mode = [] { const char* e = getenv("DL4DS_HALO_BASEOFF"); return e ? atoi(e) : 0; }();
+    p.base_off_mode = base_off_mode;
+    p.HWp = BWt + a.KW - 1;
+    if (pitch_align > 1) p.HWp = (p.HWp + pitch_align - 1) / pitch_align * pitch_align;
+    p.HHp = BHt + a.KH - 1;
+    if (p.HWp > 256) return DL4DS_E_UNSUPPORTED;
+    p.a_box_bytes = p.HWp * p.HHp * c.span;
+    p.a_bytes = (p.a_box_bytes + 1023) & ~1023;
+    p.a_stage_bytes = p.a_bytes * (x3 ? 2 : 1);
+    p.b_bytes = p.Npad * c.span;
+    p.b_tap_bytes = p.b_bytes * (x3 ? 2 : 1);
+    const bool stackn = x3 && p.Npad <= 64;
+    p.acc_stride = stackn ? 2 * p.Npad : p.Npad;
+    int cols = 32;
+    while (cols < 2 * p.acc_stride) cols *= 2;
+    if (cols > 512) return DL4DS_E_UNSUPPORTED;
+    p.tmem_cols = cols;
+    // weight ring: ~24 KB stages, 3 deep; the rest (up to 4 stages) holds halo tiles
+    int tg = (24 * 1024) / p.b_tap_bytes;
+    if (tg < 1) tg = 1;
+    if (tg > p.ntaps) tg = p.ntaps;
+    p.tg = tg;
+    p.ngroups = (p.ntaps + tg - 1) / tg;
+    p.b_stage_bytes = tg * p.b_tap_bytes;
+    const int budget = 216 * 1024;
+    int b_stages = 3;
+    while (b_stages > 2 && b_stages * p.b_stage_bytes + 2 * p.a_stage_bytes > budget) --b_stages;
+    if (b_stages * p.b_stage_bytes + 2 * p.a_stage_bytes > budget) return DL4DS_E_UNSUPPORTED;
+    int a_stages = (budget - b_stages * p.b_stage_bytes) / p.a_stage_bytes;
+    if (a_stages > 4) a_stages = 4;
+    p.a_stages = a_stages;
+    p.b_stages = b_stages;
+    p.b_base = a_stages * p.a_stage_bytes;
+    const size_t smem = (size_t)p.b_base + (size_t)b_stages * p.b_stage_bytes + 1024;
+    const CUtensorMap* tm = get_tensor_map_nhwc(a.x, a.x_ld, a.N, a.H, a.W, a.Cin, c.kc, p.HWp, p.HHp, c.swz);
+    if (!tm) return DL4DS_E_CUDA;
+    const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv_tc_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        cudaFuncSetAttribute(conv_tc_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        cudaFuncSetAttribute(conv_tc_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
+        attr_done = true;
+    }
+    if (x3 && stackn)
+        conv_tc_halo_kernel<true, true><<<grid, kHaloThreads, smem, st>>>(*tm, p);
+    else if (x3)
+        conv_tc_halo_kernel<true, false><<<grid, kHaloThreads, smem, st>>>(*tm, p);
+    else
+        conv_tc_halo_kernel<false, false><<<grid, kHaloThreads, smem, st>>>(*tm, p);
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    g_halo_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch("conv_tc_halo_kernel");
+}
+
+}  // namespace dl4ds

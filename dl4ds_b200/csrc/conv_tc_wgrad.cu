@@ -110,7 +110,7 @@ __device__ __forceinline__ void transpose_unit(const uint8_t* box, int span, int
         if (X3) {
             const float h = tf32_rna(vv[r]);
             *reinterpret_cast<float*>(tile + off) = h;
-            *reinterpret_cast<float*>(tile + lo_off + off) = vv[r] - h;
+            *reinterpret_cast<float*>(tile + lo_off + off) = tf32_rna(vv[r] - h);
         } else {
             *reinterpret_cast<float*>(tile + off) = vv[r];
         }
@@ -144,7 +144,7 @@ __device__ __forceinline__ void transpose_units(const int4* tab, int u_begin, in
                     if (X3) {
                         // hi = the raw value (kind::tf32 reads its top 19 bits), lo = v - trunc(v): exact, 2 ALU ops
                         *reinterpret_cast<float*>(tile + off) = vv[r];
-                        *reinterpret_cast<float*>(tile + lo_off + off) = vv[r] - tf32_trunc(vv[r]);
+                        *reinterpret_cast<float*>(tile + lo_off + off) = tf32_lo_of_trunc(vv[r]);
                     } else {
                         *reinterpret_cast<float*>(tile + off) = vv[r];
                     }

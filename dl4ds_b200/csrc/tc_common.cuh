@@ -177,6 +177,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
 __device__ __forceinline__ float tf32_trunc(float x) {
     return __uint_as_float(__float_as_uint(x) & 0xffffe000u);
 }
+// lo operand of the raw-tile-as-hi scheme: v - trunc(v) is exact but carries up to 13 significant bits, of which the
+// tensor core would TRUNCATE the last two (a one-signed error of up to 2^-21 |v| per element that accumulates coherently
+// over a reduction); rounding it onto the tf32 grid here makes the residual error half as large and unbiased.
+__device__ __forceinline__ float tf32_lo_of_trunc(float v) {
+    return tf32_rna(v - tf32_trunc(v));
+}
 // hi/lo split for the 3xTF32 scheme: x = hi + lo exactly; the tensor core truncates lo to tf32
 // (|lo| <= 2^-12 |x|, so the truncation error is <= 2^-22 |x|).
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
