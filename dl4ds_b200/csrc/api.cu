@@ -38,6 +38,7 @@ int64_t dl4ds_tc_launch_count(void) { return g_tc_launches.load(); }
 
 int dl4ds_debug_set_buffer(void* dev_i64) {
     wgrad2_set_debug_buffer(reinterpret_cast<long long*>(dev_i64));
+    halo_set_debug_buffer(reinterpret_cast<long long*>(dev_i64));
     return DL4DS_OK;
 }
 

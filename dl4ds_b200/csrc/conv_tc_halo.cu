@@ -54,21 +54,47 @@ struct HaloParams {
     int tg, ngroups;         // taps per weight stage, stages per chunk
     int b_stage_bytes, b_stages;
     int b_base;              // byte offset of the weight ring
+    int w_resident;          // the whole packed weight set [chunk][tap][hi ; lo] stays in shared memory (loaded once per CTA)
     int acc_stride, tmem_cols;
-    int base_off_mode;       // probe switch: 1 = put (start address >> 7) & 7 into the descriptor's base-offset field
+    const float* x;          // LDG producer mode: activations (NHWC, pitch x_ld)
+    int x_ld, ldg, upp_shift;
+    long long* stamps;       // optional clock64 stamps of CTA 0 (dl4ds_debug_set_buffer): [item < 64][16]
+    int dbg;                 // timing experiments (DL4DS_HALO_DBG): 1 no MMAs, 2 no splitter work, 4 no epilogue stores, 8 no weight copies
 };
 
-constexpr int kHaloThreads = 480;   // warp 0 A producer, 1 MMA, 2-9 epilogue, 10-13 splitter, 14 B producer
+constexpr int kHaloThreads = 608;   // warp 0 TMA A producer, 1 MMA, 2-9 epilogue, 10-17 A producers (LDG mode; 10-13 splitter in TMA mode), 18 B producer
 constexpr int kHaloMaxStages = 8;
 constexpr int BWt = 8, BHt = 16;    // tile: 8 pixels x 16 rows
 
-__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t byte_off, int base_off_mode, uint32_t start_addr) {
-    uint64_t r = d + (uint64_t)(byte_off >> 4);
-    if (base_off_mode) r |= (uint64_t)(((start_addr + byte_off) >> 7) & 7u) << 49;
-    return r;
+// tcgen05.mma kind::tf32 with the accumulate predicate hard-wired to true (no setp on a runtime value per instruction)
+__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+        : "memory");
 }
 
-template <bool X3, bool STACKN>
+#define HSTAMP(it, id)                                                                         \
+    do {                                                                                       \
+        if (p.stamps != nullptr && blockIdx.x == 0 && (it) < 64 && lane == 0)                  \
+            p.stamps[(it) * 16 + (id)] = clock64();                                            \
+    } while (0)
+
+// one lane of a converged warp (the same lane every time).  The single-thread roles below run their loops with the
+// WHOLE warp and guard only the issuing instructions with this predicate: every address / descriptor is then a
+// warp-uniform value, which ptxas keeps in uniform registers -- UTCHMMA / UTMALDG / UBLKCP issue back to back.  With
+// `if (lane == 0)` around the loop the same code compiles to per-thread registers + R2UR moves + an ELECT loop around
+// every issue (~45 instructions per K-step, measured ~320 clk per 2 MMAs; the tensor pipe needs ~100).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+template <bool X3, bool STACKN, int KSTEPS>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -81,10 +107,19 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     __shared__ __align__(8) uint64_t bar_tempty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[256];
+    __shared__ int2 pix_tab[512];        // LDG mode, per halo pixel: {float offset from the tile origin, hy << 16 | hx}
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: tells ptxas the value is warp-uniform, so the role branches below are uniform branches
+    // and the single-thread roles keep their addresses / descriptors in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
+    if (p.ldg)
+        for (int i = threadIdx.x; i < p.HWp * p.HHp; i += blockDim.x) {
+            const int hy = i / p.HWp, hx = i - hy * p.HWp;
+            pix_tab[i] = make_int2((hy * p.W + hx) * p.x_ld, (hy << 16) | hx);
+        }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.a_stages; ++s) {
@@ -110,121 +145,163 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     const uint32_t tmem_d = tmem_base_smem;
 
     if (warp == 0) {
-        // ===================== halo-tile producer (TMA) =====================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const int img = tile / p.tiles_per_img;
-                const int trem = tile - img * p.tiles_per_img;
-                const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-                const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
-                for (int c = 0; c < p.nchunks; ++c) {
-                    mbar_wait(smem_u32(&a_empty[s]), ph ^ 1u);
-                    const uint32_t full = smem_u32(&a_full[s]);
+        // ===================== halo-tile producer (TMA mode) =====================
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < (p.ldg ? 0 : p.ntiles); tile += gridDim.x) {
+            const int img = tile / p.tiles_per_img;
+            const int trem = tile - img * p.tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(smem_u32(&a_empty[s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&a_full[s]);
+                if (leader) {
                     mbar_arrive_expect_tx(full, (uint32_t)p.a_box_bytes);
                     tma_load_4d(smem_base + (uint32_t)(s * p.a_stage_bytes), &tmap_x, full, c * p.kc, x0, y0, img);
-                    if (++s == p.a_stages) { s = 0; ph ^= 1u; }
                 }
+                if (++s == p.a_stages) { s = 0; ph ^= 1u; }
             }
         }
-    } else if (warp == 14) {
+    } else if (warp == 18) {
         // ===================== weight producer (bulk copies) =====================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            const size_t tile_floats = (size_t)p.Npad * p.kc;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                for (int c = 0; c < p.nchunks; ++c) {
-                    for (int g = 0; g < p.ngroups; ++g) {
-                        const int t0 = g * p.tg;
-                        const int n = min(p.tg, p.ntaps - t0);
-                        mbar_wait(smem_u32(&b_empty[s]), ph ^ 1u);
-                        const uint32_t full = smem_u32(&b_full[s]);
-                        mbar_arrive_expect_tx(full, (uint32_t)(n * p.b_tap_bytes));
-                        const uint32_t sb = smem_base + (uint32_t)(p.b_base + s * p.b_stage_bytes);
-                        for (int j = 0; j < n; ++j) {
-                            // packed images are [tap][chunk][Npad][kc]
-                            const size_t woff = ((size_t)(t0 + j) * p.nchunks + c) * tile_floats;
-                            bulk_load(sb + (uint32_t)(j * p.b_tap_bytes), p.wp_hi + woff, (uint32_t)p.b_bytes, full);
-                            if (X3)
-                                bulk_load(sb + (uint32_t)(j * p.b_tap_bytes + p.b_bytes), p.wp_lo + woff, (uint32_t)p.b_bytes, full);
-                        }
-                        if (++s == p.b_stages) { s = 0; ph ^= 1u; }
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t tile_floats = (uint32_t)(p.Npad * p.kc);
+        if (p.w_resident) {
+            // every (chunk, tap) weight tile once: the ring round trip (bulk-copy latency + tcgen05.commit latency, ~1 us
+            // each, 3 stages in flight) was what bounded the streaming version at ~5 us per tile
+            if (leader) {
+                const uint32_t full = smem_u32(&b_full[0]);
+                mbar_arrive_expect_tx(full, (uint32_t)(p.nchunks * p.ntaps * p.b_tap_bytes));
+                for (int c = 0; c < p.nchunks; ++c)
+                    for (int t = 0; t < p.ntaps; ++t) {
+                        const uint32_t woff = (uint32_t)(t * p.nchunks + c) * tile_floats;
+                        const uint32_t sb = smem_base + (uint32_t)(p.b_base + (c * p.ntaps + t) * p.b_tap_bytes);
+                        bulk_load(sb, p.wp_hi + woff, (uint32_t)p.b_bytes, full);
+                        if (X3) bulk_load(sb + (uint32_t)p.b_bytes, p.wp_lo + woff, (uint32_t)p.b_bytes, full);
                     }
+            }
+        }
+        for (int tile = blockIdx.x; tile < (p.w_resident ? 0 : p.ntiles); tile += gridDim.x) {
+            for (int c = 0; c < p.nchunks; ++c) {
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const int t0 = g * p.tg;
+                    const int n = min(p.tg, p.ntaps - t0);
+                    mbar_wait(smem_u32(&b_empty[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&b_full[s]);
+                    const uint32_t sb = smem_base + (uint32_t)(p.b_base + s * p.b_stage_bytes);
+                    if (leader) {
+                        mbar_arrive_expect_tx(full, (p.dbg & 8) ? 0u : (uint32_t)(n * p.b_tap_bytes));
+                        if (!(p.dbg & 8)) {
+                            for (int j = 0; j < n; ++j) {
+                                // packed images are [tap][chunk][Npad][kc]
+                                const uint32_t woff = (uint32_t)((t0 + j) * p.nchunks + c) * tile_floats;
+                                bulk_load(sb + (uint32_t)(j * p.b_tap_bytes), p.wp_hi + woff, (uint32_t)p.b_bytes, full);
+                                if (X3)
+                                    bulk_load(sb + (uint32_t)(j * p.b_tap_bytes + p.b_bytes), p.wp_lo + woff, (uint32_t)p.b_bytes, full);
+                            }
+                        }
+                    }
+                    if (++s == p.b_stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(128, p.Npad, 0, 0);
-            const uint32_t idesc2 = make_idesc_tf32(128, 2 * p.Npad, 0, 0);
-            const uint32_t sbo_a = (uint32_t)(p.HWp * p.span);
-            const uint32_t sbo_b = 8u * (uint32_t)p.span;
-            // descriptor templates (address field zero): add (byte address >> 4)
-            const uint64_t tmpl_a = make_smem_desc(0, 16, sbo_a, p.layout);
-            const uint64_t tmpl_b = make_smem_desc(0, 16, sbo_b, p.layout);
-            const uint32_t row_bytes = (uint32_t)(p.HWp * p.span);
-            const uint32_t lo_off = (uint32_t)p.a_bytes;
-            const int bom = p.base_off_mode;
-            int as = 0, bs = 0;
-            uint32_t aph = 0, bph = 0;
-            int tcount = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
-                const int ab = tcount & 1;
-                mbar_wait(smem_u32(&bar_tempty[ab]), (uint32_t)(((tcount >> 1) & 1) ^ 1));
+        // whole warp runs the loops (uniform registers); only `leader` issues tcgen05.mma / tcgen05.commit.  One thread's
+        // dependent instruction chain is what paces the issue (measured: 139 clk per K-step for ~20 uniform-datapath
+        // instructions + a reconvergence block per K-step, against 44-56 clk per MMA in the tensor pipe), so per kernel tap
+        // there is ONE guarded straight-line block of 2 * KSTEPS MMAs whose descriptors differ from two running 64-bit
+        // values (da_tap, db_tap) by compile-time constants, and the tap walk itself is incremental (no multiplies).
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_tf32(128, p.Npad, 0, 0);
+        const uint32_t idesc2 = make_idesc_tf32(128, 2 * p.Npad, 0, 0);
+        const uint64_t tmpl_a = make_smem_desc(0, 16, (uint32_t)(p.HWp * p.span), p.layout);
+        const uint64_t tmpl_b = make_smem_desc(0, 16, 8u * (uint32_t)p.span, p.layout);
+        const uint64_t a_step = (uint64_t)(p.span >> 4);                                       // next tap in the kernel row
+        const uint64_t a_jump = (uint64_t)((p.HWp * p.span - (p.KW - 1) * p.span) >> 4);       // last tap of a row -> first of the next
+        const uint64_t b_step = (uint64_t)(p.b_tap_bytes >> 4);
+        const uint64_t lo16 = (uint64_t)(p.a_bytes >> 4);
+        const uint64_t blo16 = (uint64_t)(p.b_bytes >> 4);
+        const bool skip = (p.dbg & 1) != 0;
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        int tcount = 0;
+        const bool res = p.w_resident != 0;
+        if (res) {
+            mbar_wait(smem_u32(&b_full[0]), 0);
+            tc_fence_after();
+        }
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
+            const int ab = tcount & 1;
+            mbar_wait(smem_u32(&bar_tempty[ab]), (uint32_t)(((tcount >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t td = tmem_d + (uint32_t)(ab * p.acc_stride);
+            uint32_t accumulate = 0;
+            HSTAMP(tcount * p.nchunks, 8);
+            for (int c = 0; c < p.nchunks; ++c) {
+                mbar_wait(smem_u32((X3 || p.ldg) ? &a_conv[as] : &a_full[as]), aph);
                 tc_fence_after();
-                const uint32_t td = tmem_d + (uint32_t)(ab * p.acc_stride);
-                uint32_t accumulate = 0;
-                for (int c = 0; c < p.nchunks; ++c) {
-                    mbar_wait(smem_u32(X3 ? &a_conv[as] : &a_full[as]), aph);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + (uint32_t)(as * p.a_stage_bytes);
-                    const uint64_t da_base = tmpl_a + (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-                    int kh = 0, kw = 0;
-                    for (int g = 0; g < p.ngroups; ++g) {
-                        const int n = min(p.tg, p.ntaps - g * p.tg);
+                HSTAMP(tcount * p.nchunks + c, 4);
+                const uint32_t a_addr = smem_base + (uint32_t)(as * p.a_stage_bytes);
+                uint64_t da_tap = tmpl_a + (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                int kw = 0;
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const int n = min(p.tg, p.ntaps - g * p.tg);
+                    if (!res) {
                         mbar_wait(smem_u32(&b_full[bs]), bph);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_base + (uint32_t)(p.b_base + bs * p.b_stage_bytes);
-                        const uint64_t db_base = tmpl_b + (uint64_t)((b_addr & 0x3FFFFu) >> 4);
-                        for (int j = 0; j < n; ++j) {
-                            const uint32_t a_off = (uint32_t)kh * row_bytes + (uint32_t)(kw * p.span);
-                            const uint32_t b_off = (uint32_t)(j * p.b_tap_bytes);
+                    }
+                    const uint32_t b_addr = smem_base + (uint32_t)(p.b_base + (res ? c * p.ntaps * p.b_tap_bytes : bs * p.b_stage_bytes));
+                    uint64_t db_tap = tmpl_b + (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+                    for (int j = 0; j < n; ++j) {
+                        if (leader && !skip) {
+                            if (X3 && STACKN) {
+                                // A_hi x [W_hi ; W_lo] -> columns [0, 2 Npad); A_lo x W_hi -> columns [0, Npad)
+                                umma_tf32(td, da_tap, db_tap, idesc2, accumulate);
+                                umma_tf32_acc(td, da_tap + lo16, db_tap, idesc);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k < p.ksteps) {
-                                    const uint32_t ko = (uint32_t)k * 32u;
-                                    const uint64_t da = desc_add(da_base, a_off + ko, bom, a_addr);
-                                    const uint64_t db = desc_add(db_base, b_off + ko, 0, 0);
-                                    if (X3 && STACKN) {
-                                        // A_hi x [W_hi ; W_lo] -> columns [0, 2 Npad); A_lo x W_hi -> columns [0, Npad)
-                                        const uint64_t dal = desc_add(da_base, a_off + ko + lo_off, bom, a_addr);
-                                        umma_tf32(td, da, db, idesc2, accumulate);
-                                        umma_tf32(td, dal, db, idesc, 1u);
-                                    } else if (X3) {
-                                        const uint64_t dal = desc_add(da_base, a_off + ko + lo_off, bom, a_addr);
-                                        const uint64_t dbl = desc_add(db_base, b_off + ko + (uint32_t)p.b_bytes, 0, 0);
-                                        umma_tf32(td, dal, db, idesc, accumulate);
-                                        umma_tf32(td, da, dbl, idesc, 1u);
-                                        umma_tf32(td, da, db, idesc, 1u);
-                                    } else {
-                                        umma_tf32(td, da, db, idesc, accumulate);
-                                    }
-                                    accumulate = 1u;
+                                for (int k = 1; k < KSTEPS; ++k) {
+                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc2);
+                                    umma_tf32_acc(td, da_tap + lo16 + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
                                 }
+                            } else if (X3) {
+                                umma_tf32(td, da_tap + lo16, db_tap, idesc, accumulate);
+                                umma_tf32_acc(td, da_tap, db_tap + blo16, idesc);
+                                umma_tf32_acc(td, da_tap, db_tap, idesc);
+#pragma unroll
+                                for (int k = 1; k < KSTEPS; ++k) {
+                                    umma_tf32_acc(td, da_tap + lo16 + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
+                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + blo16 + (uint64_t)(2 * k), idesc);
+                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
+                                }
+                            } else {
+                                umma_tf32(td, da_tap, db_tap, idesc, accumulate);
+#pragma unroll
+                                for (int k = 1; k < KSTEPS; ++k)
+                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
                             }
-                            if (++kw == p.KW) { kw = 0; ++kh; }
                         }
-                        umma_commit(smem_u32(&b_empty[bs]));
+                        accumulate = 1u;
+                        db_tap += b_step;
+                        if (++kw == p.KW) { kw = 0; da_tap += a_jump; } else { da_tap += a_step; }
+                    }
+                    if (!res) {
+                        if (leader) umma_commit(smem_u32(&b_empty[bs]));
                         if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
                     }
-                    umma_commit(smem_u32(&a_empty[as]));
-                    if (++as == p.a_stages) { as = 0; aph ^= 1u; }
                 }
-                umma_commit(smem_u32(&bar_tfull[ab]));
+                HSTAMP(tcount * p.nchunks + c, 5);
+                if (leader) umma_commit(smem_u32(&a_empty[as]));
+                HSTAMP(tcount * p.nchunks + c, 6);
+                if (++as == p.a_stages) { as = 0; aph ^= 1u; }
             }
+            if (leader) umma_commit(smem_u32(&bar_tfull[ab]));
+            HSTAMP(tcount * p.nchunks, 9);
+            __syncwarp();
         }
     } else if (warp < 10) {
         // ===================== epilogue (warps 2-9) =====================
@@ -249,6 +326,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             const int64_t hr_row0 = ((int64_t)img * p.H * r + (int64_t)oy * r) * ((int64_t)p.W * r) + (int64_t)ox * r;
             mbar_wait(smem_u32(&bar_tfull[ab]), (uint32_t)((tcount >> 1) & 1));
             tc_fence_after();
+            if (warp == 2) HSTAMP(tcount * p.nchunks, 10);
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.acc_stride);
             for (int c0 = half * 16; c0 < p.Npad; c0 += 32) {
                 float v[16];
@@ -259,7 +337,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += v2[j];
                 }
-                if (c0 >= p.Cout) continue;
+                if (c0 >= p.Cout || (p.dbg & 4)) continue;
                 float4 rs[4];
                 if (resp) {
 #pragma unroll
@@ -295,10 +373,74 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                 }
             }
             tc_fence_before();
+            if (warp == 2) HSTAMP(tcount * p.nchunks, 11);
             mbar_arrive_warp(smem_u32(&bar_tempty[ab]));
         }
+    } else if (p.ldg) {
+        // ===================== A producers, LDG mode (warps 10-17: two groups of four warps) =====================
+        // global -> registers -> swizzled K-major hi (raw) and lo tiles of one (tile, channel chunk) item; the two
+        // groups take alternate items, so two items' loads are in flight.  (A TMA box of this shape -- 180 rows of
+        // 64 bytes -- costs ~2 us per box and at most a_stages of them overlap: measured 69 us for the composed layer
+        // with every other role switched off.)
+        const int pt = threadIdx.x - 320, grp = pt >> 7, gt = pt & 127;
+        const int upp = 1 << p.upp_shift;                 // 16-byte units per pixel and chunk: kc / 4
+        const int sub = gt & (upp - 1);
+        const int pl0 = gt >> p.upp_shift;
+        const int PS = 128 >> p.upp_shift;                // pixels covered by the group per step
+        const int npix = p.HWp * p.HHp;
+        uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+        int item = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            const int img = tile / p.tiles_per_img;
+            const int trem = tile - img * p.tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
+            const float* tbase = p.x + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld + sub * 4;
+            for (int c = 0; c < p.nchunks; ++c, ++item) {
+                if ((item & 1) != grp) continue;
+                const int s = item % p.a_stages;
+                const uint32_t ph = (uint32_t)((item / p.a_stages) & 1);
+                mbar_wait(smem_u32(&a_empty[s]), ph ^ 1u);
+                if (warp == 10 || warp == 14) HSTAMP(item, 0);
+                uint8_t* a_hi = smem_al + (size_t)s * p.a_stage_bytes;
+                uint8_t* a_lo = a_hi + p.a_bytes;
+                const float* cbase = tbase + c * p.kc;
+                for (int pb = pl0; pb < npix; pb += 8 * PS) {
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int pix = pb + j * PS;
+                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pix < npix) {
+                            const int2 e = pix_tab[pix];
+                            const int hy = e.y >> 16, hx = e.y & 0xffff;
+                            if ((unsigned)(y0 + hy) < (unsigned)p.H && (unsigned)(x0 + hx) < (unsigned)p.W && !(p.dbg & 2))
+                                v[j] = __ldg(reinterpret_cast<const float4*>(cbase + e.x));
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int pix = pb + j * PS;
+                        if (pix < npix) {
+                            const uint32_t so = (uint32_t)(pix * p.span + (swizzle_unit(sub, pix, p.span) << 4));
+                            *reinterpret_cast<float4*>(a_hi + so) = v[j];
+                            if (X3) {
+                                float4 l;
+                                l.x = tf32_lo_of_trunc(v[j].x); l.y = tf32_lo_of_trunc(v[j].y);
+                                l.z = tf32_lo_of_trunc(v[j].z); l.w = tf32_lo_of_trunc(v[j].w);
+                                *reinterpret_cast<float4*>(a_lo + so) = l;
+                            }
+                        }
+                    }
+                }
+                if (warp == 10 || warp == 14) HSTAMP(item, 1);
+                fence_proxy_async_smem();
+                if (warp == 10 || warp == 14) HSTAMP(item, 2);
+                mbar_arrive_warp(smem_u32(&a_conv[s]));
+            }
+        }
     } else if (warp < 14) {
-        // ===================== operand splitter (warps 10-13, x3 mode): once per halo tile =====================
+        // ===================== operand splitter (TMA mode, warps 10-13, x3): once per halo tile =====================
         if (X3) {
             const int et = threadIdx.x - 320;          // 0..127
             uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -312,7 +454,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                     uint8_t* a_lo = smem_al + (size_t)s * p.a_stage_bytes + p.a_bytes;
                     // the raw tile is the hi operand (kind::tf32 reads the top 19 bits); lo is rounded onto the tf32 grid
 #pragma unroll 4
-                    for (int u = et; u < units; u += 128) {
+                    for (int u = et; u < ((p.dbg & 2) ? 0 : units); u += 128) {
                         const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 16);
                         float4 l;
                         l.x = tf32_lo_of_trunc(v.x); l.y = tf32_lo_of_trunc(v.y);
@@ -332,6 +474,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
 }
 
 extern std::atomic<long long> g_tc_launches;
+static long long* g_halo_stamps = nullptr;
+void halo_set_debug_buffer(long long* p) { g_halo_stamps = p; }
 std::atomic<long long> g_halo_launches{0};
 
 // shape part of the eligibility test
@@ -352,6 +496,7 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
     const bool x3 = math_mode == DL4DS_MATH_TF32X3;
     const Chunk c = pick_chunk(a.Cin);
     HaloParams p;
+    int tg_override = 0;
     p.wp_hi = wp_hi; p.wp_lo = wp_lo;
     p.bias = a.bias; p.res = a.res; p.y = a.y; p.res_ld = a.res_ld; p.y_ld = a.y_ld;
     p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout;
@@ -365,12 +510,17 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
     p.ksteps = c.kc / 8;
     p.act = a.act; p.d2s_r = a.d2s_r; p.beta = a.beta;
     static const int pitch_align = [] { const char* e = getenv("DL4DS_HALO_PITCH_ALIGN"); return e ? atoi(e) : 1; }();
-    static const int base_off_mode = [] { const char* e = getenv("DL4DS_HALO_BASEOFF"); return e ? atoi(e) : 0; }();
-    p.base_off_mode = base_off_mode;
+    { const char* e = getenv("DL4DS_HALO_DBG"); p.dbg = e ? atoi(e) : 0; }
+    static const int use_ldg = [] { const char* e = getenv("DL4DS_HALO_TMA"); return (e && e[0] == '1') ? 0 : 1; }();
+    p.ldg = use_ldg;
+    p.x = a.x; p.x_ld = a.x_ld;
+    p.stamps = g_halo_stamps;
+    p.upp_shift = c.kc == 32 ? 3 : (c.kc == 16 ? 2 : 1);
+    { const char* e = getenv("DL4DS_HALO_TG"); if (e) tg_override = atoi(e); }
     p.HWp = BWt + a.KW - 1;
     if (pitch_align > 1) p.HWp = (p.HWp + pitch_align - 1) / pitch_align * pitch_align;
     p.HHp = BHt + a.KH - 1;
-    if (p.HWp > 256) return DL4DS_E_UNSUPPORTED;
+    if (p.HWp > 256 || p.HWp * p.HHp > 512) return DL4DS_E_UNSUPPORTED;
     p.a_box_bytes = p.HWp * p.HHp * c.span;
     p.a_bytes = (p.a_box_bytes + 1023) & ~1023;
     p.a_stage_bytes = p.a_bytes * (x3 ? 2 : 1);
@@ -385,36 +535,55 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
     // weight ring: ~24 KB stages, 3 deep; the rest (up to 4 stages) holds halo tiles
     int tg = (24 * 1024) / p.b_tap_bytes;
     if (tg < 1) tg = 1;
+    if (tg_override > 0) tg = tg_override;
     if (tg > p.ntaps) tg = p.ntaps;
     p.tg = tg;
     p.ngroups = (p.ntaps + tg - 1) / tg;
     p.b_stage_bytes = tg * p.b_tap_bytes;
     const int budget = 216 * 1024;
-    int b_stages = 3;
-    while (b_stages > 2 && b_stages * p.b_stage_bytes + 2 * p.a_stage_bytes > budget) --b_stages;
-    if (b_stages * p.b_stage_bytes + 2 * p.a_stage_bytes > budget) return DL4DS_E_UNSUPPORTED;
-    int a_stages = (budget - b_stages * p.b_stage_bytes) / p.a_stage_bytes;
-    if (a_stages > 4) a_stages = 4;
-    p.a_stages = a_stages;
-    p.b_stages = b_stages;
-    p.b_base = a_stages * p.a_stage_bytes;
-    const size_t smem = (size_t)p.b_base + (size_t)b_stages * p.b_stage_bytes + 1024;
+    static const bool no_res = [] { const char* e = getenv("DL4DS_HALO_NO_RESIDENT"); return e && e[0] == '1'; }();
+    const int w_total = p.ntaps * p.nchunks * p.b_tap_bytes;
+    p.w_resident = (!no_res && w_total + 2 * p.a_stage_bytes <= budget && w_total < (1 << 20)) ? 1 : 0;
+    if (p.w_resident) {
+        p.tg = p.ntaps; p.ngroups = 1; p.b_stage_bytes = w_total;
+        int a_st = (budget - w_total) / p.a_stage_bytes;
+        if (a_st > 6) a_st = 6;
+        p.a_stages = a_st; p.b_stages = 1;
+        p.b_base = a_st * p.a_stage_bytes;
+    }
+    if (!p.w_resident) {
+        int b_stages = 3;
+        while (b_stages > 2 && b_stages * p.b_stage_bytes + 2 * p.a_stage_bytes > budget) --b_stages;
+        if (b_stages * p.b_stage_bytes + 2 * p.a_stage_bytes > budget) return DL4DS_E_UNSUPPORTED;
+        int a_stages = (budget - b_stages * p.b_stage_bytes) / p.a_stage_bytes;
+        if (a_stages > 4) a_stages = 4;
+        p.a_stages = a_stages;
+        p.b_stages = b_stages;
+        p.b_base = a_stages * p.a_stage_bytes;
+    }
+    const size_t smem = (size_t)p.b_base + (size_t)p.b_stages * p.b_stage_bytes + 1024;
     const CUtensorMap* tm = get_tensor_map_nhwc(a.x, a.x_ld, a.N, a.H, a.W, a.Cin, c.kc, p.HWp, p.HHp, c.swz);
     if (!tm) return DL4DS_E_CUDA;
     const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(conv_tc_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
-        cudaFuncSetAttribute(conv_tc_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
-        cudaFuncSetAttribute(conv_tc_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(221 * 1024));
-        attr_done = true;
-    }
-    if (x3 && stackn)
-        conv_tc_halo_kernel<true, true><<<grid, kHaloThreads, smem, st>>>(*tm, p);
-    else if (x3)
-        conv_tc_halo_kernel<true, false><<<grid, kHaloThreads, smem, st>>>(*tm, p);
-    else
-        conv_tc_halo_kernel<false, false><<<grid, kHaloThreads, smem, st>>>(*tm, p);
+#define HALO_LAUNCH(X3_, ST_, KS_)                                                                                   \
+    do {                                                                                                             \
+        static bool attr_done_ = false;                                                                              \
+        if (!attr_done_) {                                                                                           \
+            cudaFuncSetAttribute(conv_tc_halo_kernel<X3_, ST_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 (int)(221 * 1024));                                                                 \
+            attr_done_ = true;                                                                                       \
+        }                                                                                                            \
+        conv_tc_halo_kernel<X3_, ST_, KS_><<<grid, kHaloThreads, smem, st>>>(*tm, p);                                \
+    } while (0)
+#define HALO_LAUNCH_K(X3_, ST_)                                                                                      \
+    do {                                                                                                             \
+        if (p.ksteps == 4) HALO_LAUNCH(X3_, ST_, 4);                                                                 \
+        else if (p.ksteps == 2) HALO_LAUNCH(X3_, ST_, 2);                                                            \
+        else HALO_LAUNCH(X3_, ST_, 1);                                                                               \
+    } while (0)
+    if (x3 && stackn) HALO_LAUNCH_K(true, true);
+    else if (x3) HALO_LAUNCH_K(true, false);
+    else HALO_LAUNCH_K(false, false);
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     g_halo_launches.fetch_add(1, std::memory_order_relaxed);
     return check_launch("conv_tc_halo_kernel");

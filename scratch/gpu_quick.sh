@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/q_pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/q_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/q_pytest.log
 tail -4 gpurun_out/q_pytest.log
 timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu > gpurun_out/q_bench.json 2> gpurun_out/q_bench.err; tail -2 gpurun_out/q_bench.err
 python -c "
