@@ -28,6 +28,8 @@ SIGNATURES = {
     'dl4ds_conv2d_fwd_workspace_bytes': ('l', 'iiiiiiiiiiiii'),
     'dl4ds_conv2d_pack': ('i', 'piiiiiipp'),
     'dl4ds_conv2d_fwd': ('i', 'pipppipiiiiiiiiiiiiiiiiiiipp'),
+    'dl4ds_conv2d_dgrad_fused_supported': ('i', 'iiiiiiii'),
+    'dl4ds_conv2d_dgrad_fused': ('i', 'pippipiipiiiiiiiiiiiipp'),
     'dl4ds_conv2d_wgrad_workspace_bytes': ('l', 'iiiiiiii'),
     'dl4ds_conv2d_wgrad': ('i', 'pipipiiiiiiiiiiiipip'),
     'dl4ds_spc_pointwise_compose': ('i', 'ppppppiiiip'),

@@ -2,6 +2,7 @@
 // family (include/dl4ds_b200.h).  Kernels live in conv_simt.cu (CUDA-core fp32) and conv_tc.cu
 // (tcgen05 tf32 / 3xtf32).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -96,6 +97,46 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
     }
     return conv2d_fwd_simt(a, st);
+}
+
+int dl4ds_conv2d_dgrad_fused_supported(int N, int H, int W, int Cq, int Cp, int KH, int KW, int math_mode) {
+    static const bool disabled = [] { const char* e = getenv("DL4DS_NO_FUSED_DGRAD"); return e && e[0] == '1'; }();
+    if (disabled || dl4ds_device_is_sm100() != 1) return 0;
+    ConvArgs a = {};
+    a.N = N; a.H = H; a.W = W; a.Cin = Cq; a.Ho = H; a.Wo = W; a.Cout = Cp;
+    a.KH = KH; a.KW = KW; a.stride = 1; a.up = 1; a.d2s_r = 1;
+    return conv2d_fwd_halo_supported(a, math_mode) ? 1 : 0;
+}
+
+int dl4ds_conv2d_dgrad_fused(const float* dq, int dq_ld, const float* w, float* dz, int dz_ld,
+                             const float* y_prod, int y_ld, int act, float* dbias,
+                             int N, int H, int W, int Cq, int Cp, int KH, int KW, int pad_t, int pad_l,
+                             int wmode, int beta, int math_mode, void* ws, void* stream) {
+    DL4DS_REQUIRE(dq && w && dz, DL4DS_E_BADARG, "conv2d_dgrad_fused: null pointer");
+    DL4DS_REQUIRE(act >= 0 && act <= 3, DL4DS_E_BADARG, "conv2d_dgrad_fused: act");
+    DL4DS_REQUIRE(dq_ld >= Cq && dz_ld >= Cp && (!y_prod || y_ld >= Cp), DL4DS_E_SHAPE, "conv2d_dgrad_fused: pitch < channels");
+    const int prepacked = (wmode & DL4DS_W_PREPACKED) ? 1 : 0;
+    wmode &= ~DL4DS_W_PREPACKED;
+    DL4DS_REQUIRE(wmode == DL4DS_W_FLIP_T, DL4DS_E_BADARG, "conv2d_dgrad_fused: wmode must be DL4DS_W_FLIP_T");
+    if (!dl4ds_conv2d_dgrad_fused_supported(N, H, W, Cq, Cp, KH, KW, math_mode)) {
+        set_error("conv2d_dgrad_fused: shape outside the halo-tile kernel's domain");
+        return DL4DS_E_UNSUPPORTED;
+    }
+    DL4DS_REQUIRE((!y_prod || (y_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(y_prod) & 15) == 0)) &&
+                  (!dbias || (reinterpret_cast<uintptr_t>(dbias) & 3) == 0), DL4DS_E_BADARG,
+                  "conv2d_dgrad_fused: y_prod must be 16-byte aligned with a pitch multiple of 4");
+    ConvArgs a;
+    a.x = dq; a.w = w; a.bias = nullptr; a.res = nullptr; a.y = dz;
+    a.x_ld = dq_ld; a.res_ld = 0; a.y_ld = dz_ld;
+    a.N = N; a.H = H; a.W = W; a.Cin = Cq; a.Ho = H; a.Wo = W; a.Cout = Cp;
+    a.KH = KH; a.KW = KW; a.stride = 1; a.up = 1; a.pad_t = pad_t; a.pad_l = pad_l;
+    a.wmode = wmode; a.act = DL4DS_ACT_NONE; a.d2s_r = 1; a.beta = beta;
+    a.M = N * H * W; a.HoWo = H * W;
+    a.vec = 1;
+    a.mask_y = y_prod; a.mask_ld = y_ld; a.mask_act = act; a.dbias = dbias;
+    const int rc = conv2d_fwd_tc(a, math_mode, ws, prepacked, reinterpret_cast<cudaStream_t>(stream));
+    if (rc == DL4DS_E_UNSUPPORTED) set_error("conv2d_dgrad_fused: tensors not aligned for the tensor-core kernel");
+    return rc;
 }
 
 int64_t dl4ds_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Ho, int Wo, int Cout,

@@ -31,6 +31,8 @@ struct ConvArgs {
     int x_ld, res_ld, y_ld;
     int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, up, pad_t, pad_l, wmode, act, d2s_r, beta;
     int M, HoWo, vec;
+    // dgrad launches only (dl4ds_conv2d_dgrad_fused): epilogue-backward of the layer that produced the output tensor
+    const float* mask_y = nullptr; int mask_ld = 0, mask_act = 0; float* dbias = nullptr;
 };
 struct WgradArgs {
     const float* P; const float* Q; float* dw;

@@ -614,6 +614,7 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
         int bw_, bh_;
         if (!tile_geometry(a.H, a.W, 128, &bw_, &bh_)) return DL4DS_E_UNSUPPORTED;
+        if (a.mask_y != nullptr || a.dbias != nullptr) return DL4DS_E_UNSUPPORTED;      // fused epilogue: halo kernel only
     }
     p.bias = a.bias; p.res = a.res; p.y = a.y; p.res_ld = a.res_ld; p.y_ld = a.y_ld;
     p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout;

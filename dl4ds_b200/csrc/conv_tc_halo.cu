@@ -56,6 +56,9 @@ struct HaloParams {
     int b_base;              // byte offset of the weight ring
     int w_resident;          // the whole packed weight set [chunk][tap][hi ; lo] stays in shared memory (loaded once per CTA)
     int acc_stride, tmem_cols;
+    // fused epilogue-backward of the layer that PRODUCED this launch's output tensor (dgrad launches): out *= act'(mask_y)
+    // and dbias[c] += sum over pixels of out[., c]
+    const float* mask_y; int mask_ld, mask_act; float* dbias;
     const float* x;          // LDG producer mode: activations (NHWC, pitch x_ld)
     int x_ld, ldg, upp_shift;
     long long* stamps;       // optional clock64 stamps of CTA 0 (dl4ds_debug_set_buffer): [item < 64][16]
@@ -107,6 +110,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     __shared__ __align__(8) uint64_t bar_tempty[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[256];
+    __shared__ float colsum_s[256];      // fused bias gradient: column sums of this CTA's output rows
     __shared__ int2 pix_tab[512];        // LDG mode, per halo pixel: {float offset from the tile origin, hy << 16 | hx}
 
     // warp index through a shuffle: tells ptxas the value is warp-uniform, so the role branches below are uniform branches
@@ -114,7 +118,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
+        colsum_s[i] = 0.0f;
+    }
     if (p.ldg)
         for (int i = threadIdx.x; i < p.HWp * p.HHp; i += blockDim.x) {
             const int hy = i / p.HWp, hx = i - hy * p.HWp;
@@ -313,6 +320,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
         const int ry = row / BWt, rx = row - ry * BWt;
         const int r = p.d2s_r;
         const int Cd = p.Cout / (r * r);
+        float bsum[8];                                  // fused bias gradient: this lane's column of each of its blocks
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bsum[i] = 0.0f;
+        const float* __restrict__ mask_y = p.mask_y;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
             const int ab = tcount & 1;
@@ -328,7 +339,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             tc_fence_after();
             if (warp == 2) HSTAMP(tcount * p.nchunks, 10);
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.acc_stride);
-            for (int c0 = half * 16; c0 < p.Npad; c0 += 32) {
+            int blk = 0;
+            for (int c0 = half * 16; c0 < p.Npad; c0 += 32, ++blk) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)c0, v);
                 if (X3 && STACKN) {
@@ -338,6 +350,74 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                     for (int j = 0; j < 16; ++j) v[j] += v2[j];
                 }
                 if (c0 >= p.Cout || (p.dbg & 4)) continue;
+                if (mask_y != nullptr || p.dbias != nullptr) {
+                    // ---- dgrad with the producer's epilogue-backward fused (r == 1, no bias / residual / activation here):
+                    // dz = (acc [+ old]) * act'(y_producer); dbias += column sums of dz
+                    float* dstp = yp + c0;
+                    const float* myp = mask_y ? mask_y + pix * p.mask_ld + c0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (c0 + 4 * j < p.Cout) {
+                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (p.beta) {
+                                const float4 old = *(reinterpret_cast<const float4*>(dstp) + j);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            if (myp) {
+                                const float4 m = __ldg(reinterpret_cast<const float4*>(myp) + j);
+                                o.x *= act_grad_from_out(m.x, p.mask_act); o.y *= act_grad_from_out(m.y, p.mask_act);
+                                o.z *= act_grad_from_out(m.z, p.mask_act); o.w *= act_grad_from_out(m.w, p.mask_act);
+                            }
+                            *(reinterpret_cast<float4*>(dstp) + j) = o;
+                            v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;
+                        } else {
+                            v[4 * j] = v[4 * j + 1] = v[4 * j + 2] = v[4 * j + 3] = 0.0f;
+                        }
+                    }
+                    if (p.dbias != nullptr) {
+                        // transpose-reduce over the warp's 32 pixels: 16 -> 8 -> 4 -> 2 -> 1 values per lane (8 + 4 + 2 + 1
+                        // shuffles), then the two lanes that hold the same column add up
+                        {
+                            const bool up = (lane & 16) != 0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float send = up ? v[j] : v[j + 8];
+                                const float keep = up ? v[j + 8] : v[j];
+                                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
+                        }
+                        {
+                            const bool up = (lane & 8) != 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float send = up ? v[j] : v[j + 4];
+                                const float keep = up ? v[j + 4] : v[j];
+                                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            }
+                        }
+                        {
+                            const bool up = (lane & 4) != 0;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const float send = up ? v[j] : v[j + 2];
+                                const float keep = up ? v[j + 2] : v[j];
+                                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                            }
+                        }
+                        {
+                            const bool up = (lane & 2) != 0;
+                            const float send = up ? v[0] : v[1];
+                            const float keep = up ? v[1] : v[0];
+                            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+                        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+                        // lane holds column c0 + 8*bit4 + 4*bit3 + 2*bit2 + bit1
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (i == blk) bsum[i] += v[0];
+                    }
+                    continue;
+                }
                 float4 rs[4];
                 if (resp) {
 #pragma unroll
@@ -375,6 +455,20 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             tc_fence_before();
             if (warp == 2) HSTAMP(tcount * p.nchunks, 11);
             mbar_arrive_warp(smem_u32(&bar_tempty[ab]));
+        }
+        if (p.dbias != nullptr) {
+            // the four lane quadrants meet in shared memory, then one global reduction per column and CTA
+            const int cl = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = half * 16 + 32 * i + cl;
+                    if (c < p.Cout) atomicAdd(&colsum_s[c], bsum[i]);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int et = threadIdx.x - 64;            // 0..255 over the eight epilogue warps
+            if (et < p.Cout) atomicAdd(p.dbias + et, colsum_s[et]);
         }
     } else if (p.ldg) {
         // ===================== A producers, LDG mode (warps 10-17: two groups of four warps) =====================
@@ -514,6 +608,7 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
     static const int use_ldg = [] { const char* e = getenv("DL4DS_HALO_TMA"); return (e && e[0] == '1') ? 0 : 1; }();
     p.ldg = use_ldg;
     p.x = a.x; p.x_ld = a.x_ld;
+    p.mask_y = a.mask_y; p.mask_ld = a.mask_ld; p.mask_act = a.mask_act; p.dbias = a.dbias;
     p.stamps = g_halo_stamps;
     p.upp_shift = c.kc == 32 ? 3 : (c.kc == 16 ? 2 : 1);
     { const char* e = getenv("DL4DS_HALO_TG"); if (e) tg_override = atoi(e); }
@@ -540,7 +635,7 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
     p.tg = tg;
     p.ngroups = (p.ntaps + tg - 1) / tg;
     p.b_stage_bytes = tg * p.b_tap_bytes;
-    const int budget = 216 * 1024;
+    const int budget = 208 * 1024;      // + ~7 KB of static shared memory (barriers, bias, column sums, pixel table) <= 227 KB
     static const bool no_res = [] { const char* e = getenv("DL4DS_HALO_NO_RESIDENT"); return e && e[0] == '1'; }();
     const int w_total = p.ntaps * p.nchunks * p.b_tap_bytes;
     p.w_resident = (!no_res && w_total + 2 * p.a_stage_bytes <= budget && w_total < (1 << 20)) ? 1 : 0;
@@ -570,7 +665,7 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
         static bool attr_done_ = false;                                                                              \
         if (!attr_done_) {                                                                                           \
             cudaFuncSetAttribute(conv_tc_halo_kernel<X3_, ST_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                 (int)(221 * 1024));                                                                 \
+                                 (int)(210 * 1024));                                                                 \
             attr_done_ = true;                                                                                       \
         }                                                                                                            \
         conv_tc_halo_kernel<X3_, ST_, KS_><<<grid, kHaloThreads, smem, st>>>(*tm, p);                                \

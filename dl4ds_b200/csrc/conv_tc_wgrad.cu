@@ -171,7 +171,9 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
     __shared__ int4 a_tab[kWg2MaxAUnits];
     __shared__ int4 q_tab[kWg2MaxQUnits];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: ptxas then treats it (and the role branches) as warp-uniform, see conv_tc_halo.cu
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     WG2_KSTAMP(0);
@@ -239,21 +241,24 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            const uint32_t tx_bytes = (uint32_t)(nbox_p * p.tx_p + nbox_q * p.tx_q);
-            const uint32_t rawq = (uint32_t)(p.nbox_p_max * p.box_p);
-            for (int it = 0; it < my_tiles; ++it) {
-                const int s = it % p.rstages;
-                mbar_wait(smem_u32(&bar_rfree[s]), (uint32_t)(((it / p.rstages) & 1) ^ 1));
-                WG2_STAMP(0);
-                const uint32_t full = smem_u32(&bar_rfull[s]);
+        uint32_t elected;
+        asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(elected));
+        const bool leader = elected != 0;
+        const uint32_t tx_bytes = (uint32_t)(nbox_p * p.tx_p + nbox_q * p.tx_q);
+        const uint32_t rawq = (uint32_t)(p.nbox_p_max * p.box_p);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int s = it % p.rstages;
+            mbar_wait(smem_u32(&bar_rfree[s]), (uint32_t)(((it / p.rstages) & 1) ^ 1));
+            WG2_STAMP(0);
+            const uint32_t full = smem_u32(&bar_rfull[s]);
+            const int tile = t_begin + it;
+            const int img = tile / p.tiles_per_img;
+            const int trem = tile - img * p.tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * p.BH, x0 = tx * p.BW;
+            const uint32_t sp = smem_base + (uint32_t)p.raw_base + (uint32_t)s * (uint32_t)p.raw_bytes;
+            if (leader) {
                 mbar_arrive_expect_tx(full, tx_bytes);
-                const int tile = t_begin + it;
-                const int img = tile / p.tiles_per_img;
-                const int trem = tile - img * p.tiles_per_img;
-                const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-                const int y0 = ty * p.BH, x0 = tx * p.BW;
-                const uint32_t sp = smem_base + (uint32_t)p.raw_base + (uint32_t)s * (uint32_t)p.raw_bytes;
                 for (int b = 0; b < nbox_p; ++b)
                     tma_load_4d(sp + (uint32_t)(b * p.box_p), &tmap_p, full, ca0 + b * p.kc_p, x0 - p.pad_l,
                                 y0 - p.pad_t, img);
@@ -263,55 +268,68 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int item = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int qs = it % p.qstages;
-                mbar_wait(smem_u32(&bar_qfull[qs]), (uint32_t)((it / p.qstages) & 1));
-                WG2_STAMP(1);
-                const uint32_t qb = smem_base + (uint32_t)p.q_base + (uint32_t)(qs * p.q_slot);
-                for (int b = 0; b < nblk; ++b, ++item) {
-                    const int as = item % p.astages;
-                    mbar_wait(smem_u32(&bar_afull[as]), (uint32_t)((item / p.astages) & 1));
-                    if (b == 0) WG2_STAMP(2);
-                    tc_fence_after();
-                    const uint32_t ab = smem_base + (uint32_t)p.a_base + (uint32_t)(as * p.a_slot);
-                    // swap: D[cb][stacked row] with N = rows of this block; else D[stacked row][cb] with N = Nmma
-                    const int nb_rows = min(p.BR, rows - (blk0 + b) * p.BR);
-                    const uint32_t idesc = make_idesc_tf32(128, p.swap ? ((nb_rows + 15) & ~15) : Nmma, 0, 0);
-                    const uint32_t td = tmem_d + (uint32_t)(b * (p.swap ? p.BR : Nmma));
-                    const uint32_t sa = p.swap ? qb : ab, sb = p.swap ? ab : qb;
-                    const uint32_t la = (uint32_t)(p.swap ? p.q_half : p.a_half), lb = (uint32_t)(p.swap ? p.a_half : p.q_half);
+        // the whole warp walks the loops (uniform registers), one elected lane issues; descriptors are two running 64-bit
+        // values + compile-time K offsets (conv_tc_halo.cu has the measurements behind this shape)
+        uint32_t elected;
+        asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(elected));
+        const bool leader = elected != 0;
+        const uint64_t tmpl = make_smem_desc(0, 16, 1024, kLayoutSw128);
+        const uint64_t la16 = (uint64_t)((p.swap ? p.q_half : p.a_half) >> 4), lb16 = (uint64_t)((p.swap ? p.a_half : p.q_half) >> 4);
+        int item = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int qs = it % p.qstages;
+            mbar_wait(smem_u32(&bar_qfull[qs]), (uint32_t)((it / p.qstages) & 1));
+            WG2_STAMP(1);
+            const uint32_t qb = smem_base + (uint32_t)p.q_base + (uint32_t)(qs * p.q_slot);
+            for (int b = 0; b < nblk; ++b, ++item) {
+                const int as = item % p.astages;
+                mbar_wait(smem_u32(&bar_afull[as]), (uint32_t)((item / p.astages) & 1));
+                if (b == 0) WG2_STAMP(2);
+                tc_fence_after();
+                const uint32_t ab = smem_base + (uint32_t)p.a_base + (uint32_t)(as * p.a_slot);
+                // swap: D[cb][stacked row] with N = rows of this block; else D[stacked row][cb] with N = Nmma
+                const int nb_rows = min(p.BR, rows - (blk0 + b) * p.BR);
+                const uint32_t idesc = make_idesc_tf32(128, p.swap ? ((nb_rows + 15) & ~15) : Nmma, 0, 0);
+                const uint32_t td = tmem_d + (uint32_t)(b * (p.swap ? p.BR : Nmma));
+                const uint32_t sa = p.swap ? qb : ab, sb = p.swap ? ab : qb;
+                const uint64_t da = tmpl + (uint64_t)((sa & 0x3FFFFu) >> 4);
+                const uint64_t db = tmpl + (uint64_t)((sb & 0x3FFFFu) >> 4);
+                const uint32_t acc0 = it > 0 ? 1u : 0u;
+                if (leader) {
+                    if (X3 && p.stackm) {
+                        // the 128 A rows starting at the slot hold [Q_hi ; Q_lo]: rows [0,q_rows) of D collect
+                        // hi*hi + hi*lo, rows [q_rows, 2 q_rows) lo*hi + lo*lo; the epilogue adds both row groups
+                        // to the same dw element.  2 MMAs instead of 3 per K-step.
+                        umma_tf32(td, da, db, idesc, acc0);
+                        umma_tf32(td, da, db + lb16, idesc, 1u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-                        const uint32_t ko = (uint32_t)k * 32u;
-                        const uint64_t da = make_smem_desc(sa + ko, 16, 1024, kLayoutSw128);
-                        const uint64_t db = make_smem_desc(sb + ko, 16, 1024, kLayoutSw128);
-                        if (X3 && p.stackm) {
-                            // the 128 A rows starting at the slot hold [Q_hi ; Q_lo]: rows [0,q_rows) of D collect
-                            // hi*hi + hi*lo, rows [q_rows, 2 q_rows) lo*hi + lo*lo; the epilogue adds both row groups
-                            // to the same dw element.  2 MMAs (~137 cycles each) instead of 3 per K-step.
-                            const uint64_t dbl = make_smem_desc(sb + lb + ko, 16, 1024, kLayoutSw128);
-                            umma_tf32(td, da, db, idesc, acc);
-                            umma_tf32(td, da, dbl, idesc, 1u);
-                        } else if (X3) {
-                            const uint64_t dal = make_smem_desc(sa + la + ko, 16, 1024, kLayoutSw128);
-                            const uint64_t dbl = make_smem_desc(sb + lb + ko, 16, 1024, kLayoutSw128);
-                            umma_tf32(td, dal, db, idesc, acc);
-                            umma_tf32(td, da, dbl, idesc, 1u);
-                            umma_tf32(td, da, db, idesc, 1u);
-                        } else {
-                            umma_tf32(td, da, db, idesc, acc);
+                        for (int k = 1; k < 4; ++k) {
+                            umma_tf32(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+                            umma_tf32(td, da + (uint64_t)(2 * k), db + lb16 + (uint64_t)(2 * k), idesc, 1u);
                         }
+                    } else if (X3) {
+                        umma_tf32(td, da + la16, db, idesc, acc0);
+                        umma_tf32(td, da, db + lb16, idesc, 1u);
+                        umma_tf32(td, da, db, idesc, 1u);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) {
+                            umma_tf32(td, da + la16 + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+                            umma_tf32(td, da + (uint64_t)(2 * k), db + lb16 + (uint64_t)(2 * k), idesc, 1u);
+                            umma_tf32(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+                        }
+                    } else {
+                        umma_tf32(td, da, db, idesc, acc0);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) umma_tf32(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
                     }
                     umma_commit(smem_u32(&bar_aempty[as]));
                 }
-                umma_commit(smem_u32(&bar_qempty[qs]));
-                WG2_STAMP(3);
             }
-            umma_commit(smem_u32(&bar_accum));
+            if (leader) umma_commit(smem_u32(&bar_qempty[qs]));
+            WG2_STAMP(3);
         }
+        if (leader) umma_commit(smem_u32(&bar_accum));
+        __syncwarp();
     } else {
         // ===================== transposers (+ tf32 split), then the epilogue =====================
         const int tw = warp - 2;

@@ -124,7 +124,7 @@ class Arena:
 
 class Var:
     """fp32 NHWC activation: channels [off, off+C) of ``buf`` (N,H,W,ld)."""
-    __slots__ = ('buf', 'off', 'C', 'grad', 'requires_grad')
+    __slots__ = ('buf', 'off', 'C', 'grad', 'requires_grad', 'n_uses', 'n_contrib', 'act_src', 'premasked')
 
     def __init__(self, buf, off=0, C=None, requires_grad=True):
         assert buf.dim() == 4 and buf.is_contiguous() and buf.dtype == torch.float32
@@ -133,6 +133,13 @@ class Var:
         self.C = buf.shape[3] - off if C is None else C
         self.grad = None
         self.requires_grad = requires_grad
+        # bookkeeping for the fused epilogue-backward (Ctx.conv): consumers registered in the forward pass, gradient
+        # contributions received in the backward pass, the producing convolution's (activation, bias-gradient name), and
+        # whether .grad already holds d(pre-activation) (the last consumer's dgrad applied act' and summed the bias grad)
+        self.n_uses = 0
+        self.n_contrib = 0
+        self.act_src = None
+        self.premasked = False
 
     @property
     def N(self):
@@ -295,11 +302,26 @@ class Ctx:
         if self.training:
             self.tape.append(fn)
 
+    def _use(self, *vs):
+        """Register the calling op as a consumer of each Var (forward pass).  Every op does this for its
+        differentiable inputs: a convolution may fuse the producer's epilogue-backward into its dgrad only when it is
+        the LAST of ``n_uses`` contributors to the input's gradient (``_contrib`` raises if the counts disagree)."""
+        for v in vs:
+            if v is not None:
+                v.n_uses += 1
+
+    def _contrib(self, var):
+        var.n_contrib += 1
+        if var.premasked or (var.act_src is not None and var.n_contrib > var.n_uses):
+            raise RuntimeError('gradient bookkeeping: a contribution arrived after the fused epilogue-backward was '
+                               'applied (an op consumed the tensor without Ctx._use)')
+
     def _acc(self, var, writer):
         """Accumulate a gradient into ``var``.  writer(dst_var, beta) must write (beta=0) or
         add (beta=1) the gradient; ops that cannot accumulate are wrapped by ``_acc_via_tmp``."""
         if not var.requires_grad:
             return
+        self._contrib(var)
         if var.grad is None:
             var.grad = var.like()
             writer(var.grad, 0)
@@ -310,6 +332,7 @@ class Ctx:
         """writer(dst_var) writes the full gradient; summed into var.grad if one exists."""
         if not var.requires_grad:
             return
+        self._contrib(var)
         if var.grad is None:
             var.grad = var.like()
             writer(var.grad)
@@ -339,6 +362,7 @@ class Ctx:
         buffer was adopted."""
         if not var.requires_grad:
             return False
+        self._contrib(var)
         if var.grad is None:
             if adopt:
                 var.grad = gvar
@@ -376,6 +400,9 @@ class Ctx:
             assert (res.N, res.H, res.W, res.C) == (x.N, Ho, Wo, cout)
         a = ACT[act]
         lib = _lib.load()
+        self._use(x, res)
+        if r == 1 and out.off == 0 and out.ld == out.C and (a != 0 or bias):
+            out.act_src = (a, (name + '/bias') if bias else None)     # what a consumer's fused dgrad needs
         ws, wm = self._packed_ws(name + '/kernel', w, W_HWIO, k, x.C, cout,
                                  lambda: lib.dl4ds_conv2d_fwd_workspace_bytes(x.N, x.H, x.W, x.C, Ho, Wo, cout, k, k,
                                                                               stride, 1, r, self.math))
@@ -391,7 +418,9 @@ class Ctx:
                 return
             # epilogue backward: dz = dy * act'(y) (un-shuffled if d2s), dbias += sum dz
             pg = self.param_grads
-            if a == 0 and r == 1:
+            if out.premasked:
+                dz = dy         # the last consumer's dgrad already stored d(pre-activation) and summed the bias gradient
+            elif a == 0 and r == 1:
                 dz = dy
                 if bias and pg:
                     self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, None, 0, None, 0,
@@ -407,20 +436,43 @@ class Ctx:
                             label='%s:wgrad@%dx%d' % (name, x.H, x.W))
             # input gradient
             if x.requires_grad:
-                def wr(dst, beta):
-                    ws2, wm2 = self._packed_ws(
-                        name + '/kernel', w, W_FLIP_T, k, cout, x.C,
-                        lambda: lib.dl4ds_conv2d_fwd_workspace_bytes(x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1,
-                                                                     stride, 1, self.math))
+                ws_q = lambda: lib.dl4ds_conv2d_fwd_workspace_bytes(x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1, stride, 1,
+                                                                    self.math)
+                # fused epilogue-backward of x's producer: this dgrad is the last of x's gradient contributions
+                fuse = (x.act_src is not None and x.n_contrib == x.n_uses - 1 and stride == 1 and self.math != 0 and
+                        (Ho, Wo) == (x.H, x.W) and x.off == 0 and x.ld == x.C and not (x.C == 8 and cout == 8) and
+                        dz.ptr % 16 == 0 and dz.ld % 4 == 0 and
+                        (x.grad is None or (x.grad.ptr % 16 == 0 and x.grad.ld % 4 == 0)) and
+                        lib.dl4ds_conv2d_dgrad_fused_supported(x.N, x.H, x.W, cout, x.C, k, k, self.math) == 1)
+                if fuse:
+                    ws2, wm2 = self._packed_ws(name + '/kernel', w, W_FLIP_T, k, cout, x.C, ws_q)
+                    fuse = ws2 is not None
+                if fuse:
+                    pa, pbias = x.act_src
+                    self._contrib(x)
+                    beta = 1
+                    if x.grad is None:
+                        x.grad, beta = x.like(), 0
+                    dbp = self._g(pbias).data_ptr() if (pbias is not None and pg) else None
                     self._timed('%s:dgrad@%dx%d' % (name, x.H, x.W),
-                               'dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
-                               dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1, stride,
-                               k - 1 - pt, k - 1 - pl, wm2, 0, 1, beta, self.math,
-                               ws2.data_ptr() if ws2 is not None else None, _stream())
-                self._acc(x, wr)
+                                'dl4ds_conv2d_dgrad_fused', dz.ptr, dz.ld, w.data_ptr(), x.grad.ptr, x.grad.ld,
+                                x.ptr if pa != 0 else None, x.ld, pa, dbp, x.N, x.H, x.W, cout, x.C, k, k,
+                                k - 1 - pt, k - 1 - pl, wm2, beta, self.math, ws2.data_ptr(), _stream())
+                    x.premasked = True
+                else:
+                    def wr(dst, beta):
+                        ws2, wm2 = self._packed_ws(name + '/kernel', w, W_FLIP_T, k, cout, x.C, ws_q)
+                        self._timed('%s:dgrad@%dx%d' % (name, x.H, x.W),
+                                   'dl4ds_conv2d_fwd', dz.ptr, dz.ld, w.data_ptr(), None, None, 0,
+                                   dst.ptr, dst.ld, x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1, stride,
+                                   k - 1 - pt, k - 1 - pl, wm2, 0, 1, beta, self.math,
+                                   ws2.data_ptr() if ws2 is not None else None, _stream())
+                    self._acc(x, wr)
             if res is not None:     # d(res) = dz; handed over last (stream order keeps reads before
                 self._give_grad(res, dz)   # any later in-place update by the new owner)
             out.grad = None
+            out.n_contrib = 0
+            out.premasked = False
         self._record(bwd)
         return out
 
@@ -435,6 +487,7 @@ class Ctx:
         graph up to fp32 re-association."""
         if act == 'gelu':
             return self.gelu(self.conv_d2s_pointwise(x, name1, cm, name2, co, act=None, r=r, k=k))
+        self._use(x)
         w1, b1 = self._p(name1 + '/kernel'), self._p(name1 + '/bias')
         w2, b2 = self._p(name2 + '/kernel'), self._p(name2 + '/bias')
         R2 = r * r
@@ -500,6 +553,7 @@ class Ctx:
             return self.gelu(self.conv_transpose(x, name, cout, k, stride, act=None))
         w = self._p(name + '/kernel')
         assert tuple(w.shape) == (k, k, cout, x.C), (name, tuple(w.shape))
+        self._use(x)
         Ho, Wo = x.H * stride, x.W * stride
         _, pt = same_pads(Ho, k, stride)
         _, pl = same_pads(Wo, k, stride)
@@ -591,6 +645,7 @@ class Ctx:
         assert (a.N, a.H, a.W, a.C) == (b.N, b.H, b.W, b.C)
         if act == 'gelu':
             return self.gelu(self.add(a, b))
+        self._use(a, b)
         out = a.like()
         code = ACT[act]
         self._call('dl4ds_add', a.ptr, a.ld, b.ptr, b.ld, out.ptr, out.ld, a.npix, a.C, code, _stream())
@@ -611,6 +666,7 @@ class Ctx:
     def concat(self, parts):
         """Concatenate along channels -- blocks.py:276, sp_postups.py:186,201."""
         p0 = parts[0]
+        self._use(*parts)
         ctot = sum(p.C for p in parts)
         out = new_var(p0.N, p0.H, p0.W, ctot, self.device)
         offs = []
@@ -638,6 +694,7 @@ class Ctx:
         code = ACT[act]
         if code == 0:
             return x
+        self._use(x)
         out = x.like()
         self._call('dl4ds_act_fwd', x.ptr, x.ld, out.ptr, out.ld, x.npix, x.C, code, _stream())
 
@@ -662,6 +719,7 @@ class Ctx:
             raise ValueError('Normalization not supported, got %s' % (kind,))           # blocks.py:64-65
         if act == 'gelu':
             return self.gelu(self.norm(x, name, kind, act=None, eps=eps))
+        self._use(x)
         code, C, n_pix = ACT[act], x.C, x.npix
         gamma, beta = self._p(name + '/gamma'), self._p(name + '/beta')
         out = x.like()
@@ -715,6 +773,7 @@ class Ctx:
 
     def depthwise_conv(self, x, name, k=7):
         """DepthwiseConv2D(kernel_size=k, padding='same', depth_multiplier=1) with bias -- blocks.py:147-148."""
+        self._use(x)
         wt, bias = self._p(name + '/depthwise_kernel'), self._p(name + '/bias')
         out = x.like()
         self._call('dl4ds_depthwise_conv_fwd', x.ptr, x.ld, wt.data_ptr(), bias.data_ptr(), out.ptr, out.ld,
@@ -740,6 +799,7 @@ class Ctx:
 
     def gelu(self, x):
         """Activation('gelu'), exact erf form -- ConvNextBlock's default activation, blocks.py:143,153."""
+        self._use(x)
         xd = self._dense(x)
         out = xd.like()
         n = xd.npix * xd.C
@@ -770,6 +830,7 @@ class Ctx:
             return x
         if not (self.training or (variant or '').startswith('mc')):
             return x
+        self._use(x)
         state = self.arena.rng_state()
         if not self._rng_advanced:
             self._call('dl4ds_rng_advance', state.data_ptr(), _stream())
@@ -797,6 +858,7 @@ class Ctx:
     def channel_attention(self, x, name, r=4, groups=None):
         """ChannelAttention2D -- blocks.py:537-593.  ``groups`` = (n_groups, pix_per_group, inner)
         overrides the default per-image pooling (used for the 5-D (T,H) pooling quirk)."""
+        self._use(x)
         C = x.C
         Cr = int(C / r)
         w1, b1 = self._p(name + '/conv1/kernel'), self._p(name + '/conv1/bias')
@@ -837,6 +899,7 @@ class Ctx:
 
     def local_conv(self, x, name, filters):
         """LocallyConnected2D(filters, (1,1), implementation=3) -- blocks.py:322-328."""
+        self._use(x)
         w, b = self._p(name + '/kernel'), self._p(name + '/bias')
         assert tuple(w.shape) == (x.H, x.W, x.C, filters)
         out = x.like(filters)
@@ -864,6 +927,7 @@ class Ctx:
 
     def resize_bilinear(self, x, Ho, Wo):
         """keras Resizing(Ho, Wo, 'bilinear') -- blocks.py:489, discriminator.py:62."""
+        self._use(x)
         out = new_var(x.N, Ho, Wo, x.C, self.device)
         self._call('dl4ds_resize_bilinear_fwd', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, x.C, Ho, Wo,
                    _stream())
@@ -872,6 +936,7 @@ class Ctx:
             dy = out.grad
             if dy is None or not x.requires_grad:
                 return
+            self._contrib(x)
             if x.grad is None:
                 x.grad = Var(torch.zeros((x.N, x.H, x.W, x.C), dtype=torch.float32, device=self.device))
             self._call('dl4ds_resize_bilinear_bwd', dy.ptr, dy.ld, x.grad.ptr, x.grad.ld, x.N, x.H, x.W,
@@ -888,6 +953,7 @@ class Ctx:
         if method not in RESIZE_METHOD:
             raise NotImplementedError('interpolation=%r is not built (bilinear, nearest, bicubic are)' % (method,))
         code = RESIZE_METHOD[method]
+        self._use(x)
         out = new_var(x.N, Ho, Wo, x.C, self.device)
         self._call('dl4ds_resize_fwd', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, x.C, Ho, Wo, code, _stream())
 
@@ -895,6 +961,7 @@ class Ctx:
             dy = out.grad
             if dy is None or not x.requires_grad:
                 return
+            self._contrib(x)
             if x.grad is None:
                 x.grad = Var(torch.zeros((x.N, x.H, x.W, x.C), dtype=torch.float32, device=self.device))
             self._call('dl4ds_resize_bwd', dy.ptr, dy.ld, x.grad.ptr, x.grad.ld, x.N, x.H, x.W, x.C, Ho, Wo, code,
@@ -905,6 +972,7 @@ class Ctx:
 
     def maxpool2(self, x):
         """MaxPooling2D((2,2)) -- blocks.py:613."""
+        self._use(x)
         out = new_var(x.N, x.H // 2, x.W // 2, x.C, self.device)
         self._call('dl4ds_maxpool2_fwd', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, x.C, _stream())
 
@@ -925,6 +993,7 @@ class Ctx:
         """ZeroPadding2D bottom/right to (H, W) -- PadConcat, blocks.py:639-655."""
         if (x.H, x.W) == (H, W):
             return x
+        self._use(x)
         out = new_var(x.N, H, W, x.C, self.device)
         self._call('dl4ds_pad_bottom_right', x.ptr, x.ld, out.ptr, out.ld, x.N, x.H, x.W, H, W, x.C,
                    _stream())
@@ -945,6 +1014,7 @@ class Ctx:
     def permute_frames(self, x, A, B):
         """(A,B,frame) -> (B,A,frame) over the leading (frame) dimension of a (A*B,H,W,C) Var."""
         assert x.N == A * B and x.ld == x.C
+        self._use(x)
         out = x.like()
         fe = x.H * x.W * x.C
         self._call('dl4ds_permute_frames', x.ptr, out.ptr, A, B, fe, _stream())
@@ -964,6 +1034,7 @@ class Ctx:
 
     def group_mean(self, x):
         """GlobalAveragePooling2D -- discriminator.py:76.  (N,H,W,C) -> (N,1,1,C)."""
+        self._use(x)
         out = new_var(x.N, 1, 1, x.C, self.device)
         self.launches += 1
         self._call('dl4ds_group_mean_fwd', x.ptr, x.ld, out.ptr, x.N, x.H * x.W, x.C, _stream())
@@ -985,6 +1056,8 @@ class Ctx:
         """tf.repeat(tf.expand_dims(s, 1), T, axis=1) (spt_postups.py:139-140) in the time-major
         frame layout: (B,H,W,C) -> (T*B,H,W,C), T stacked copies."""
         B_ = x.N
+        for _ in range(T):
+            self._use(x)            # T gradient contributions come back
         out = new_var(T * B_, x.H, x.W, x.C, self.device)
         for t in range(T):
             self._copy(x, Var(out.buf[t * B_:(t + 1) * B_]))
@@ -1005,6 +1078,7 @@ class Ctx:
             assert mask.off == 0 and mask.ld == mask.C
             mask = mask.buf
         assert x.ld == x.C and mask.numel() == x.npix * x.C
+        self._use(x)
         out = x.like()
         self._call('dl4ds_mul', x.ptr, mask.data_ptr(), out.ptr, x.npix * x.C, _stream())
 
@@ -1025,6 +1099,7 @@ class Ctx:
         """ConvLSTM2D(filters, k, return_sequences=True, padding='same') -- blocks.py:350-355
         (Keras 2.x: tanh / hard_sigmoid, gates i,f,c,o, zero initial state, recurrent conv 'same'
         without bias).  ``x``: TIME-MAJOR frames (T*B, H, W, C); returns (T*B, H, W, filters)."""
+        self._use(x)
         TB, H, W, C = x.N, x.H, x.W, x.C
         B = TB // T
         F4 = 4 * filters
@@ -1101,6 +1176,7 @@ class Ctx:
         The weighted mixes (losses.py:62-93,134-151) run their pixel terms first, then the SSIM term accumulates
         into the same gradient buffer."""
         assert y_pred.ld == y_pred.C and y_true.ld == y_true.C
+        self._use(y_pred)
         if name not in LOSS_TERMS:
             raise ValueError('unknown loss %r' % (name,))
         n = y_pred.npix * y_pred.C

@@ -101,6 +101,7 @@ def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function):
     cf.bce_loss(p_fake, 1.0, loss_buf=losses[0:1])
     cf.backward()
     if gen_in.grad is not None:
+        cg._use(gen)                        # the discriminator is a second consumer of the generated field
         cg._give_grad(gen, gen_in.grad)
     cg.pixel_loss(gen, cg.input(hr_t), gen_pxloss_function or 'mae', scale=LAMBDA, loss_buf=losses[1:2])
     cg.backward()

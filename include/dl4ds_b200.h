@@ -97,6 +97,23 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
                      int KH, int KW, int stride, int up, int pad_t, int pad_l,
                      int wmode, int act, int d2s_r, int beta, int math_mode, void* ws, void* stream);
 
+/* Input gradient of a stride-1 'same' Conv2D with the epilogue-backward of the layer that PRODUCED the
+ * convolution's input fused into the store (what GradientTape does between two Keras layers,
+ * blocks.py:87-103,210-230: d(pre-activation) = d(activation) * act'(.), d(bias) = its sum over pixels):
+ *   dz[n,y,x,c] = ( dgrad(dq, w)[n,y,x,c] (+ dz[n,y,x,c] if beta) ) * act'(y_prod[n,y,x,c])
+ *   dbias[c]   += sum_{n,y,x} dz[n,y,x,c]
+ * dq: (N,H,W,Cq) gradient w.r.t. this convolution's output; w: its HWIO kernel (KH,KW,Cp,Cq) read with
+ * DL4DS_W_FLIP_T (or its packed image with DL4DS_W_PREPACKED); dz: (N,H,W,Cp).  y_prod (may be NULL: no
+ * activation) is the producer's forward OUTPUT, act its activation code; dbias may be NULL.  Valid only when
+ * this launch is the LAST contribution to dz.  Tensor-core math modes only, shapes in the halo-tile kernel's
+ * domain (dl4ds_conv2d_dgrad_fused_supported() == 1: W % 8 == 0, H % 16 == 0, Cp and Cq multiples of 8,
+ * Cp <= 256); otherwise DL4DS_E_UNSUPPORTED -- the caller then runs dl4ds_conv2d_fwd + dl4ds_bias_act_bwd. */
+int dl4ds_conv2d_dgrad_fused_supported(int N, int H, int W, int Cq, int Cp, int KH, int KW, int math_mode);
+int dl4ds_conv2d_dgrad_fused(const float* dq, int dq_ld, const float* w, float* dz, int dz_ld,
+                             const float* y_prod, int y_ld, int act, float* dbias,
+                             int N, int H, int W, int Cq, int Cp, int KH, int KW, int pad_t, int pad_l,
+                             int wmode, int beta, int math_mode, void* ws, void* stream);
+
 /* Weight gradient of the same family (accumulating):
  *   dw[kh][kw][a][b] += sum_{n,oy,ox} P[n,oy*stride+kh-pad_t,ox*stride+kw-pad_l,a] * Q[n,oy,ox,b]
  * Conv2D: P = layer input (Ca=Cin), Q = dZ (Cb=Cout).  Conv2DTranspose (kernel (kh,kw,Cout,Cin)):
