@@ -27,6 +27,8 @@ SIGNATURES = {
     'dl4ds_debug_set_buffer': ('i', 'p'),
     'dl4ds_conv2d_fwd_workspace_bytes': ('l', 'iiiiiiiiiiiii'),
     'dl4ds_conv2d_pack': ('i', 'piiiiiipp'),
+    'dl4ds_conv2d_pack_desc': ('l', 'piiiiiipp'),
+    'dl4ds_conv2d_pack_multi': ('i', 'pilp'),
     'dl4ds_conv2d_fwd': ('i', 'pipppipiiiiiiiiiiiiiiiiiiipp'),
     'dl4ds_conv2d_dgrad_fused_supported': ('i', 'iiiiiiii'),
     'dl4ds_conv2d_dgrad_fused': ('i', 'pippipiipiiiiiiiiiiiipp'),

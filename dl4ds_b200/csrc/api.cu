@@ -158,6 +158,21 @@ int dl4ds_conv2d_pack(const float* w, int wmode, int KH, int KW, int Cin, int Co
                           reinterpret_cast<cudaStream_t>(stream));
 }
 
+int64_t dl4ds_conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode,
+                               void* ws, void* desc_out_host) {
+    if (!w || !ws || !desc_out_host || (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3) || Cin % 8 ||
+        Cout % 8) {
+        set_error("conv2d_pack_desc: bad argument");
+        return DL4DS_E_BADARG;
+    }
+    return conv2d_pack_desc(w, wmode & ~DL4DS_W_PREPACKED, KH, KW, Cin, Cout, math_mode, ws, desc_out_host);
+}
+
+int dl4ds_conv2d_pack_multi(const void* descs_dev, int n, int64_t total_units, void* stream) {
+    DL4DS_REQUIRE(descs_dev || n == 0, DL4DS_E_BADARG, "conv2d_pack_multi: null descriptor table");
+    return conv2d_pack_multi(descs_dev, n, total_units, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int64_t dl4ds_conv2d_wgrad_workspace_bytes(int N, int Hq, int Wq, int Ca, int Cb, int KH, int KW,
                                            int math_mode) {
     if (math_mode == DL4DS_MATH_FP32) return 0;

@@ -62,6 +62,8 @@ bool conv2d_fwd_halo_supported(const ConvArgs& a, int math_mode);
 int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, const float* wp_lo, cudaStream_t st);
 int conv2d_pack_tc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws,
                    cudaStream_t st);
+int64_t conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws, void* desc_out);
+int conv2d_pack_multi(const void* descs_dev, int n, int64_t total_units, cudaStream_t st);
 int conv2d_wgrad_tc(const WgradArgs& a, void* ws, int math_mode, cudaStream_t st);
 // conv_tc_wgrad.cu: stacked-taps M=128 kernel (tried first; conv2d_wgrad_tc is the fallback for shapes outside it)
 int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st);

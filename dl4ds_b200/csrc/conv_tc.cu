@@ -19,6 +19,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = operand splitter (x3 mode) during the main loop, then epilogue.
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <map>
@@ -131,6 +132,61 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
             *reinterpret_cast<float4*>(lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
         } else {
             *reinterpret_cast<float4*>(hi + dst) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// Every (layer, pass) weight image of a model in ONE launch: a table of descriptors in device memory, a flat unit
+// index space (16-byte units of all images), each unit located by a binary search over the descriptors' first units.
+// Replaces ~40 three-microsecond pack launches per optimizer step (and the side-stream fork / join around them).
+struct PackDesc {
+    const float* w; float* hi; float* lo;
+    int taps, Cin, Cout, Npad, kc, nchunks, wmode, x3;
+    long long unit_begin;
+};
+static_assert(sizeof(PackDesc) == 64, "PackDesc is a 64-byte record (dl4ds_conv2d_pack_desc writes it, Python fills unit_begin)");
+
+__global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int n, long long total_units) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_units;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int lo_i = 0, hi_i = n - 1;
+        while (lo_i < hi_i) {                         // last descriptor whose unit_begin <= idx
+            const int mid = (lo_i + hi_i + 1) >> 1;
+            if (descs[mid].unit_begin <= idx) lo_i = mid; else hi_i = mid - 1;
+        }
+        const PackDesc d = descs[lo_i];
+        const long long li = idx - d.unit_begin;
+        const int upr = d.kc / 4;
+        const int u = (int)(li % upr);
+        const int nn = (int)((li / upr) % d.Npad);
+        const int blk = (int)(li / ((long long)upr * d.Npad));
+        const int tap = blk / d.nchunks, ch = blk - tap * d.nchunks;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = ch * d.kc + u * 4 + j;
+            float x = 0.0f;
+            if (nn < d.Cout && c < d.Cin) {
+                if (d.wmode == DL4DS_W_HWIO)
+                    x = __ldg(d.w + ((int64_t)tap * d.Cin + c) * d.Cout + nn);
+                else
+                    x = __ldg(d.w + ((int64_t)(d.taps - 1 - tap) * d.Cout + nn) * d.Cin + c);
+            }
+            v[j] = x;
+        }
+        const int us = swizzle_unit(u, nn, d.kc * 4);
+        const int64_t dst = ((int64_t)blk * d.Npad + nn) * d.kc + us * 4;
+        if (d.x3) {
+            float h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[j] = tf32_rna(v[j]);
+                l[j] = tf32_rna(v[j] - h[j]);
+            }
+            *reinterpret_cast<float4*>(d.hi + dst) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(d.lo + dst) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+            *reinterpret_cast<float4*>(d.hi + dst) = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
@@ -589,6 +645,33 @@ int conv2d_pack_tc(const float* w, int wmode, int KH, int KW, int Cin, int Cout,
     pack_weights_kernel<<<blocks, 256, 0, st>>>(w, hi, lo, KH * KW, Cin, Cout, npad, c.kc, nchunks, wmode,
                                                 math_mode == DL4DS_MATH_TF32X3 ? 1 : 0);
     return check_launch("pack_weights_kernel");
+}
+
+// fills one 64-byte PackDesc (host memory) for conv2d_pack_multi; returns its number of 16-byte units
+int64_t conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws, void* desc_out) {
+    const Chunk c = pick_chunk(Cin);
+    PackDesc d;
+    d.w = w;
+    d.taps = KH * KW; d.Cin = Cin; d.Cout = Cout;
+    d.Npad = (Cout + 15) / 16 * 16;
+    d.kc = c.kc;
+    d.nchunks = (Cin + c.kc - 1) / c.kc;
+    d.wmode = wmode;
+    d.x3 = math_mode == DL4DS_MATH_TF32X3 ? 1 : 0;
+    const int64_t n = pack_floats(d.taps, Cin, Cout);
+    d.hi = reinterpret_cast<float*>(ws);
+    d.lo = d.hi + n;
+    d.unit_begin = 0;
+    memcpy(desc_out, &d, sizeof(d));
+    return n / 4;
+}
+
+int conv2d_pack_multi(const void* descs_dev, int n, int64_t total_units, cudaStream_t st) {
+    if (n <= 0 || total_units <= 0) return DL4DS_OK;
+    int64_t blocks = (total_units + 255) / 256;
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    pack_weights_multi_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const PackDesc*>(descs_dev), n, total_units);
+    return check_launch("pack_weights_multi_kernel");
 }
 
 int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cudaStream_t st) {

@@ -134,7 +134,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             mbar_init(smem_u32(&a_conv[s]), 4);
             mbar_init(smem_u32(&a_empty[s]), 1);
         }
-        for (int s = 0; s < p.b_stages; ++s) {
+        for (int s = 0; s < kHaloMaxStages; ++s) {
             mbar_init(smem_u32(&b_full[s]), 1);
             mbar_init(smem_u32(&b_empty[s]), 1);
         }
@@ -181,15 +181,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             // every (chunk, tap) weight tile once: the ring round trip (bulk-copy latency + tcgen05.commit latency, ~1 us
             // each, 3 stages in flight) was what bounded the streaming version at ~5 us per tile
             if (leader) {
-                const uint32_t full = smem_u32(&b_full[0]);
-                mbar_arrive_expect_tx(full, (uint32_t)(p.nchunks * p.ntaps * p.b_tap_bytes));
-                for (int c = 0; c < p.nchunks; ++c)
+                for (int c = 0; c < p.nchunks; ++c) {
+                    // one barrier per channel chunk: the first tile's MMAs start when chunk 0 has landed
+                    const uint32_t full = smem_u32(&b_full[c]);
+                    mbar_arrive_expect_tx(full, (uint32_t)(p.ntaps * p.b_tap_bytes));
                     for (int t = 0; t < p.ntaps; ++t) {
                         const uint32_t woff = (uint32_t)(t * p.nchunks + c) * tile_floats;
                         const uint32_t sb = smem_base + (uint32_t)(p.b_base + (c * p.ntaps + t) * p.b_tap_bytes);
                         bulk_load(sb, p.wp_hi + woff, (uint32_t)p.b_bytes, full);
                         if (X3) bulk_load(sb + (uint32_t)p.b_bytes, p.wp_lo + woff, (uint32_t)p.b_bytes, full);
                     }
+                }
             }
         }
         for (int tile = blockIdx.x; tile < (p.w_resident ? 0 : p.ntiles); tile += gridDim.x) {
@@ -238,10 +240,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
         uint32_t aph = 0, bph = 0;
         int tcount = 0;
         const bool res = p.w_resident != 0;
-        if (res) {
-            mbar_wait(smem_u32(&b_full[0]), 0);
-            tc_fence_after();
-        }
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
             const int ab = tcount & 1;
             mbar_wait(smem_u32(&bar_tempty[ab]), (uint32_t)(((tcount >> 1) & 1) ^ 1));
@@ -253,6 +251,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                 mbar_wait(smem_u32((X3 || p.ldg) ? &a_conv[as] : &a_full[as]), aph);
                 tc_fence_after();
                 HSTAMP(tcount * p.nchunks + c, 4);
+                if (res && tcount == 0) {           // resident weights: chunk c landed (phase 0 stays complete afterwards)
+                    mbar_wait(smem_u32(&b_full[c]), 0);
+                    tc_fence_after();
+                }
                 const uint32_t a_addr = smem_base + (uint32_t)(as * p.a_stage_bytes);
                 uint64_t da_tap = tmpl_a + (uint64_t)((a_addr & 0x3FFFFu) >> 4);
                 int kw = 0;
@@ -638,7 +640,7 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
     const int budget = 208 * 1024;      // + ~7 KB of static shared memory (barriers, bias, column sums, pixel table) <= 227 KB
     static const bool no_res = [] { const char* e = getenv("DL4DS_HALO_NO_RESIDENT"); return e && e[0] == '1'; }();
     const int w_total = p.ntaps * p.nchunks * p.b_tap_bytes;
-    p.w_resident = (!no_res && w_total + 2 * p.a_stage_bytes <= budget && w_total < (1 << 20)) ? 1 : 0;
+    p.w_resident = (!no_res && w_total + 2 * p.a_stage_bytes <= budget && p.nchunks <= kHaloMaxStages) ? 1 : 0;
     if (p.w_resident) {
         p.tg = p.ntaps; p.ngroups = 1; p.b_stage_bytes = w_total;
         int a_st = (budget - w_total) / p.a_stage_bytes;

@@ -182,6 +182,41 @@ def new_var(N, H, W, C, device, zero=False):
     return Var(f((N, H, W, C), dtype=torch.float32, device=device))
 
 
+class PackPlan:
+    """Every tensor-core weight image of a model packed by ONE kernel (``dl4ds_conv2d_pack_multi``): built from the
+    model's pack cache after an eager pass has discovered which (parameter, pass, shape) images the graph uses.  A
+    captured step launches it first; the convolutions then find their images prepacked."""
+
+    def __init__(self, arena, pack_cache):
+        import numpy as np
+        lib = _lib.load()
+        self.keys = set()
+        recs = np.zeros((max(len(pack_cache), 1), 64), dtype=np.uint8)
+        total = 0
+        n = 0
+        self._keep = []
+        for key, ws in pack_cache.items():
+            wname, wmode, k, cin, cout, math = key
+            w = arena.param(wname)
+            row = recs[n]
+            units = lib.dl4ds_conv2d_pack_desc(w.data_ptr(), wmode, k, k, cin, cout, math, ws.data_ptr(),
+                                               row.ctypes.data)
+            if units < 0:
+                raise _lib.Dl4dsError('conv2d_pack_desc: %s' % _lib.last_error())
+            row[56:64].view(np.int64)[0] = total
+            total += int(units)
+            n += 1
+            self.keys.add(key)
+            self._keep.append(ws)
+        self.n, self.total = n, total
+        self.descs = torch.from_numpy(recs[:max(n, 1)].copy()).to(arena.device)
+
+    def run(self):
+        if self.n:
+            call('dl4ds_conv2d_pack_multi', self.descs.data_ptr(), self.n, self.total, _stream())
+        return 1 if self.n else 0
+
+
 class Ctx:
     """One recorded forward pass (and its backward)."""
     TIMER_REPS = 4
@@ -202,6 +237,7 @@ class Ctx:
         # the step, so the ~30 small pack kernels leave the critical path of the captured graph.
         self.pack_cache = None
         self.pack_stream = None
+        self.prepacked = None       # keys of a PackPlan that already ran on this stream: their images are up to date
         self._packed = set()
         self._pack_forked = False
         self._rng_advanced = False  # dropout: the arena's RNG step is bumped once per Ctx, before the first mask
@@ -257,8 +293,11 @@ class Ctx:
             return torch.empty(nb, dtype=torch.uint8, device=self.device), wmode
         key = (wname, wmode, k, Cin, Cout, self.math)
         ws = self.pack_cache.get(key)
-        if ws is None or ws.numel() < nb:
+        fresh = ws is None or ws.numel() < nb
+        if fresh:
             ws = self.pack_cache[key] = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        if not fresh and self.prepacked is not None and key in self.prepacked:
+            return ws, wmode | W_PREPACKED
         if key not in self._packed:
             self._packed.add(key)
             main = torch.cuda.current_stream()

@@ -227,14 +227,16 @@ class Model:
             out.append(x.contiguous())
         return out, bsz, T
 
-    def forward(self, inputs, training=False, math=None, timers=None, pack_stream=None):
-        """Run the graph on CUDA tensors prepared by ``_prep_inputs``.  Returns (ctx, out Var)."""
+    def forward(self, inputs, training=False, math=None, timers=None, pack_stream=None, prepacked=None):
+        """Run the graph on CUDA tensors prepared by ``_prep_inputs``.  Returns (ctx, out Var).  ``prepacked``: keys
+        of a :class:`engine.PackPlan` that has just run on this stream."""
         ctx = Ctx(self.arena, math or self.math, training=training)
         ctx.timers = timers
         if not hasattr(self, '_pack_cache'):
             self._pack_cache = {}
         ctx.pack_cache = self._pack_cache
         ctx.pack_stream = pack_stream
+        ctx.prepacked = prepacked
         vs = [ctx.input(x) for x in inputs]
         out = self.fn(ctx, vs)
         return ctx, out

@@ -90,15 +90,17 @@ class SupervisedStep:
             self.world = d.get_world_size()
 
     # the recorded work -------------------------------------------------------------------------
-    def _fwd_bwd(self, timers=None, pack_stream=None):
+    def _fwd_bwd(self, timers=None, plan=None):
+        """``plan``: a PackPlan -- all tensor-core weight images in one launch at the head of the step (the captured
+        graph); without it every convolution packs its own image on first use (eager passes)."""
         self.arena.grad.zero_()
         self.loss_buf.zero_()
+        n_pack = plan.run() if plan is not None else 0
         ctx, out = self.model.forward(self.inputs, training=True, math=self.math, timers=timers,
-                                      pack_stream=pack_stream)
+                                      prepacked=plan.keys if plan is not None else None)
         ctx.pixel_loss(out, ctx.input(self.target), self.loss_kind, loss_buf=self.loss_buf)
         ctx.backward()
-        ctx.join_pack_stream()
-        return ctx.launches + 2     # + the two memsets
+        return ctx.launches + 2 + n_pack     # + the two memsets
 
     def _opt(self):
         _lib.call('dl4ds_adam_step_dev', self.arena.theta.data_ptr(), self.arena.grad.data_ptr(),
@@ -141,13 +143,14 @@ class SupervisedStep:
         a.theta.copy_(snap[0]); a.m.copy_(snap[1]); a.v.copy_(snap[2]); a.t = snap[3]
         if not self.use_graph:
             return self
+        from .engine import PackPlan
+        self.pack_plan = PackPlan(a, getattr(self.model, '_pack_cache', {}))      # images the eager pass above used
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self.graph_fb = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()          # weight-image packs: a parallel branch of the captured graph
             with torch.cuda.graph(self.graph_fb, stream=s):
-                self._fwd_bwd(pack_stream=side)
+                self.launches_per_step = self._fwd_bwd(plan=self.pack_plan) + n2
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, stream=s):
                 self._opt()

@@ -91,6 +91,13 @@ int64_t dl4ds_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Ho, i
                                          int KH, int KW, int stride, int up, int d2s_r, int math_mode);
 int dl4ds_conv2d_pack(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode,
                       void* ws, void* stream);
+/* All weight images of a model in one launch: dl4ds_conv2d_pack_desc() writes one 64-byte descriptor (host memory)
+ * for what dl4ds_conv2d_pack() would pack and returns its number of 16-byte units (< 0: error); the caller stores
+ * the running sum of the units of the preceding descriptors into bytes [56, 64) of each record (int64), copies the
+ * table to the device and calls dl4ds_conv2d_pack_multi(table, n, total units) once per optimizer step. */
+int64_t dl4ds_conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode,
+                               void* ws, void* desc_out_host);
+int dl4ds_conv2d_pack_multi(const void* descs_dev, int n, int64_t total_units, void* stream);
 int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias,
                      const float* res, int res_ld, float* y, int y_ld,
                      int N, int H, int W, int Cin, int Ho, int Wo, int Cout,
