@@ -78,6 +78,15 @@ SIGNATURES = {
     'dl4ds_permute_frames': ('i', 'ppiilp'),
     'dl4ds_pad_bottom_right': ('i', 'pipiiiiiiip'),
     'dl4ds_axpby': ('i', 'fpfplp'),
+    'dl4ds_comm_unique_id_bytes': ('i', ''),
+    'dl4ds_comm_nccl_version': ('i', ''),
+    'dl4ds_comm_get_unique_id': ('i', 'p'),
+    'dl4ds_comm_init_rank': ('i', 'pii'),
+    'dl4ds_comm_size': ('i', ''),
+    'dl4ds_comm_rank': ('i', ''),
+    'dl4ds_comm_allreduce_sum': ('i', 'plp'),
+    'dl4ds_comm_broadcast': ('i', 'plip'),
+    'dl4ds_comm_destroy': ('i', ''),
 }
 
 _lib = None

@@ -32,7 +32,11 @@ def allreduce_sum_(flat, dist=None):
     (``world_grad_scale``).  NCCL for CUDA buffers, gloo for the CPU tests."""
     d = dist if dist is not None else _dist()
     if d is not None and d.get_world_size() > 1:
-        d.all_reduce(flat, op=d.ReduceOp.SUM)
+        from . import comm
+        if flat.is_cuda and comm.ensure(d):
+            comm.allreduce_sum_(flat)              # dl4ds_comm_allreduce_sum on the current stream (capturable)
+        else:
+            d.all_reduce(flat, op=d.ReduceOp.SUM)
     return flat
 
 
@@ -81,8 +85,8 @@ class SupervisedStep:
         self._lr_events = [None] * 4
         self._lr_slot = 0
         self.use_graph = use_graph
-        self.graph_fb = None        # zero-grad + forward + loss + backward
-        self.graph_opt = None       # adam
+        self.graph_fb = None        # the whole step: zero-grad + forward + loss + backward + all-reduce + Adam
+        self.graph_opt = None       # (kept for callers that test for it: aliases graph_fb)
         self.launches_per_step = 0
         self.world = 1
         d = _dist()
@@ -150,10 +154,12 @@ class SupervisedStep:
         with torch.cuda.stream(s):
             self.graph_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_fb, stream=s):
+                # ONE graph: the NCCL all-reduce (dl4ds_comm_allreduce_sum on this stream) is captured between the
+                # backward pass and Adam, so a replay has no host gap and no second graph launch
                 self.launches_per_step = self._fwd_bwd(plan=self.pack_plan) + n2
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, stream=s):
+                self._allreduce()
                 self._opt()
+            self.graph_opt = self.graph_fb
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         return self
@@ -174,8 +180,6 @@ class SupervisedStep:
         self._set_lr_t()
         if self.graph_fb is not None:
             self.graph_fb.replay()
-            self._allreduce()
-            self.graph_opt.replay()
         else:
             self._fwd_bwd()
             self._allreduce()
@@ -195,8 +199,12 @@ class SupervisedStep:
         """hvd BroadcastGlobalVariablesCallback(0) (supervised.py:369) + optimizer slots."""
         d = _dist()
         if d is not None:
+            from . import comm
             for t in (self.arena.theta, self.arena.m, self.arena.v):
-                d.broadcast(t, src=0)
+                if t.is_cuda and comm.ensure(d):
+                    comm.broadcast_(t, 0)
+                else:
+                    d.broadcast(t, src=0)
 
 
 class EvalStep:

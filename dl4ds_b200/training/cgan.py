@@ -143,10 +143,18 @@ class CGANStep:
             _lib.call('dl4ds_adam_step_dev', a.theta.data_ptr(), a.grad.data_ptr(), a.m.data_ptr(), a.v.data_ptr(), a.n,
                       lr_t.data_ptr(), float(self.b1), float(self.b2), float(self.eps), 1.0 / self.world, st)
 
+    def _exchange(self):
+        """hvd.DistributedGradientTape (cgan.py:608-611): both gradient arenas summed over the ranks on this stream."""
+        if self.dist is not None and self.world > 1:
+            from ..step import allreduce_sum_
+            allreduce_sum_(self.G.arena.grad, self.dist)
+            allreduce_sum_(self.D.arena.grad, self.dist)
+
     def capture(self):
         import torch
         snap = [(m.arena.theta.clone(), m.arena.m.clone(), m.arena.v.clone(), m.arena.t) for m in (self.G, self.D)]
         _fwd_bwd(self.G, self.D, self.lr, self.hr, self.st, self.masks, self.losses, self.pxloss)   # warm-up (eager)
+        self._exchange()
         self._opt()
         torch.cuda.synchronize()
         for m, (th, mm, vv, t) in zip((self.G, self.D), snap):
@@ -156,10 +164,11 @@ class CGANStep:
         with torch.cuda.stream(s):
             self.graph_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_fb, stream=s):
+                # one graph: both backward passes, the two NCCL all-reduces (dl4ds_comm_*, captured), both Adam updates
                 _fwd_bwd(self.G, self.D, self.lr, self.hr, self.st, self.masks, self.losses, self.pxloss)
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, stream=s):
+                self._exchange()
                 self._opt()
+            self.graph_opt = self.graph_fb
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         return self
@@ -187,10 +196,6 @@ class CGANStep:
         self.lr_t[1].copy_(self._lr_host[1:2], non_blocking=True)
         self.graph_fb.replay()
         d = self.dist
-        if d is not None and self.world > 1:
-            d.all_reduce(self.G.arena.grad, op=d.ReduceOp.SUM)
-            d.all_reduce(self.D.arena.grad, op=d.ReduceOp.SUM)
-        self.graph_opt.replay()
         if d is not None and self.world > 1 and first_batch:
             for mdl in (self.G, self.D):
                 for t in (mdl.arena.theta, mdl.arena.m, mdl.arena.v):

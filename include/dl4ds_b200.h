@@ -379,6 +379,25 @@ int dl4ds_pad_bottom_right(const float* src, int src_ld, float* dst, int dst_ld,
 /* y = a*x + b*y element-wise (gradient combination for the two-seed cGAN backward). */
 int dl4ds_axpby(float a, const float* x, float b, float* y, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel exchange (one process per GPU; replaces Horovod: hvd.DistributedOptimizer /
+ * DistributedGradientTape average, training/supervised.py:363-365, training/cgan.py:608-611, and
+ * hvd.broadcast_variables / BroadcastGlobalVariablesCallback(0), supervised.py:369, cgan.py:626-637).
+ * NCCL over NVLink / NVSwitch, resolved with dlopen at the first call (libnccl.so.2; DL4DS_NCCL_LIB
+ * overrides).  Rank 0 creates the 128-byte id, the caller's launcher distributes it (any channel), every
+ * rank calls init_rank.  Collectives are asynchronous on `stream` and may be captured into a CUDA graph.
+ * The gradient AVERAGE of Horovod is allreduce_sum here + grad_scale = 1/world in dl4ds_adam_step*.
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_comm_unique_id_bytes(void);                       /* 128 */
+int dl4ds_comm_nccl_version(void);                          /* e.g. 22809; -1 if NCCL cannot be loaded */
+int dl4ds_comm_get_unique_id(void* id_out_128);
+int dl4ds_comm_init_rank(const void* id_128, int nranks, int rank);
+int dl4ds_comm_size(void);                                  /* 0 without a communicator */
+int dl4ds_comm_rank(void);                                  /* -1 without a communicator */
+int dl4ds_comm_allreduce_sum(float* buf, int64_t n, void* stream);             /* in place */
+int dl4ds_comm_broadcast(void* buf, int64_t nbytes, int root, void* stream);   /* in place */
+int dl4ds_comm_destroy(void);
+
 #ifdef __cplusplus
 }
 #endif
