@@ -54,7 +54,12 @@ def _config(n_gpus, extra=None):
 # --------------------------------------------------------------------------------------------
 # CPU leg (oracle): used for cpu_baseline and for --impl reference
 # --------------------------------------------------------------------------------------------
-def cpu_oracle_rate(batch, steps, warmup, threads):
+def cpu_oracle_rate(batch, steps, warmup, threads, with_batch_creation=False):
+    """HR-px/s and seconds per step of the oracle's training step on the host cores.  ``with_batch_creation``: every
+    timed step also builds its (LR, HR) batch from the HR array the way the reference does per step on the host
+    (``create_batch_hr_lr``: per-sample slicing + cv2 INTER_AREA coarsening, dataloader.py:297-360) -- through
+    dl4ds_b200.dataloader's restatement, which tests/test_datapath.py pins bit-for-bit to the reference's own output
+    (/root/reference is not present on the GPU box)."""
     import numpy as np
     import torch
     from oracle import torch_ref as R
@@ -68,12 +73,22 @@ def cpu_oracle_rate(batch, steps, warmup, threads):
     hr = rng.standard_normal((batch, HR_HW, HR_HW, 1), dtype=np.float32)
     lr = hr.reshape(batch, LR_HW, SCALE, LR_HW, SCALE, 1).mean(axis=(2, 4)).astype(np.float32)
     hr_t, lr_t = torch.from_numpy(hr), torch.from_numpy(lr)
+
+    def one():
+        if with_batch_creation:
+            from dl4ds_b200.dataloader import create_batch_hr_lr
+            (lr_b,), (hr_b,) = create_batch_hr_lr(np.arange(batch), 0, hr, None, upsampling='spc', scale=SCALE,
+                                                  batch_size=batch)
+            R.supervised_step(fwd, w, opt, [torch.from_numpy(np.ascontiguousarray(lr_b))],
+                              torch.from_numpy(np.ascontiguousarray(hr_b)))
+        else:
+            R.supervised_step(fwd, w, opt, [lr_t], hr_t)
     for _ in range(warmup):
-        R.supervised_step(fwd, w, opt, [lr_t], hr_t)
+        one()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        R.supervised_step(fwd, w, opt, [lr_t], hr_t)
+        one()
         times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return batch * HR_HW * HR_HW / sec, sec
@@ -86,6 +101,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     sample_b = 16
     rate, sec = cpu_oracle_rate(sample_b, args.steps, args.warmup, threads)
+    rate_e2e, sec_e2e = cpu_oracle_rate(sample_b, max(2, args.steps // 2), 1, threads, with_batch_creation=True)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
@@ -96,6 +112,9 @@ def run_reference(args):
                                    'batch-64 workload per step; torch-CPU fp32 restatement of the '
                                    'reference graph (TF/Keras not installable offline)' % sample_b},
         'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'cpu_end_to_end': {'value': rate_e2e, 'unit': UNIT, 'ms_per_step': sec_e2e * 1e3,
+                           'what': 'the same step including the per-step host batch creation (create_batch_hr_lr: slicing + '
+                                   'cv2 INTER_AREA), BASELINE.md section 3 "end-to-end" row'},
         'gpu_launches': 0,
     }
     _emit(line)
@@ -277,18 +296,30 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
-    if rank == 0:
-        peaks = {}
-        peaks_src = 'fallback'
+    peaks = {}
+    peaks_src = 'fallback'
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+        peaks_src = 'measured'
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    bf16_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
+    tf32_peak = bf16_peak / 2.0         # kind::tf32 issues at half the kind::f16 rate
+
+    # ---------------- BASELINE configs 3 / 4 / 5 (after the headline's timed regions; every rank takes part) ----------------
+    n_launch_headline = int(step.launches_per_step)
+    extra = {}
+    if args.configs:
+        del trainer.train_step, step
+        torch.cuda.empty_cache()
         try:
-            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-                peaks = json.load(f)
-            peaks_src = 'measured'
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-        bf16_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
-        tf32_peak = bf16_peak / 2.0         # kind::tf32 issues at half the kind::f16 rate
+            extra = run_extra_configs(args, dev, rank, world, tf32_peak)
+        except Exception as e:      # the headline line must survive a failure of an extra configuration
+            extra = {'error': '%s: %s' % (type(e).__name__, e)}
+
+    if rank == 0:
 
         px_per_step = BATCH * HR_HW * HR_HW * world
         value = px_per_step * args.steps / (ms * 1e-3)
@@ -329,10 +360,26 @@ def run_native(args):
             'conv_family_ms_per_step_eager': conv_ms,
             'hbm_peak_gbs': hbm_peak,
         }
+        # per-FUNCTION view next to the per-layer one: every launch of a pass type summed (the tensor-core layers of the
+        # forward / input-gradient passes run conv_tc_halo_kernel, those of the weight-gradient pass conv_tc_wgrad2_kernel;
+        # the 1- and 8-channel layers of the same passes run the thin / pointwise kernels and are included in the sums)
+        groups = {}
+        for k, (ms_k, n_k) in per_label.items():
+            pas = k.rsplit(':', 1)[1].split('@')[0]
+            g = 'wgrad (conv_tc_wgrad2_kernel + thin)' if pas == 'wgrad' else 'fwd+dgrad (conv_tc_halo_kernel + thin)'
+            a_ = groups.setdefault(g, [0.0, 0.0, 0])
+            a_[0] += ms_k
+            a_[1] += 2.0 * macs.get(k, 0) * n_k
+            a_[2] += n_k
+        roofline['per_function'] = {
+            g: {'ms_per_step': v[0], 'launches_per_step': v[2], 'achieved': v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0,
+                'frac': (v[1] / (v[0] * 1e-3) / 1e12) / tf32_peak if v[0] > 0 else 0.0, 'share_of_conv_family': v[0] / max(conv_ms, 1e-9)}
+            for g, v in groups.items()}
 
         # bounded CPU sample: 10-30 s of host work
         threads = os.cpu_count() or 1
         cpu_rate, cpu_sec = cpu_oracle_rate(4, 8, 2, threads) if not args.no_cpu else (None, None)
+        cpu_e2e, _ = cpu_oracle_rate(4, 4, 1, threads, with_batch_creation=True) if not args.no_cpu else (None, None)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True,
@@ -346,22 +393,200 @@ def run_native(args):
             'predict': {'value': pred_px * world / pred_s, 'unit': UNIT, 'ms_per_batch': pred_s / n_pool * 1e3,
                         'api': 'Model.predict(host LR array, batch_size=64) -> host HR array (forward only, captured '
                                'graph per chunk, H2D + D2H included; what Predictor.run calls, inference.py:238)'},
-            'gpu_launches': int(step.launches_per_step * args.steps),
-            'launches_per_step': int(step.launches_per_step),
+            'gpu_launches': int(n_launch_headline * args.steps),
+            'launches_per_step': n_launch_headline,
             'roofline': roofline,
             'cpu_baseline': None if cpu_rate is None else {
                 'value': cpu_rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                 'sample': '8 timed training steps at batch 4 (configs[0]) of the torch-CPU fp32 '
-                          'restatement of the reference graph; TF/Keras not installable offline'},
+                          'restatement of the reference graph; TF/Keras not installable offline',
+                'end_to_end_value': cpu_e2e,
+                'end_to_end_what': 'the same step including the per-step host batch creation (create_batch_hr_lr)'},
             'clocks': sampler.summary(t_wall0, t_wall2) if sampler is not None else None,
             'final_loss': final_loss,
             'top_kernels_ms_per_step': dict(sorted(((k, round(v[0], 4)) for k, v in per_label.items()),
                                                    key=lambda kv: -kv[1])[:8]),
+            'kernels_ms_per_step': dict(sorted(((k, round(v[0], 4)) for k, v in per_label.items()), key=lambda kv: -kv[1])),
+            'configs': extra,
         }
         _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE.json configs[2..4] at their per-GPU sizes (weak scaling: the stated global batches 128 / 32 / 32 are
+# 16 / 8 / 4 per GPU at the stated 8 / 4 / 8 GPUs).  Run after the headline's timed region; the headline keys of the
+# JSON line are unaffected.  Every entry: device-resident captured-graph step time (CUDA events, max over ranks),
+# the same through the trainer API with host batches (e2e), algorithmic FLOPs (2 * MACs of the reference graph:
+# fwd + dgrad + wgrad) and its fraction of the kind::tf32 tensor peak.
+# --------------------------------------------------------------------------------------------
+def _max_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def _time_steps(fn, n, warm, dev, world):
+    """ms per step of fn(i): warm-up, barrier, CUDA events around n calls, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    for i in range(warm):
+        fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        dist.barrier()
+    ms = max(e0.elapsed_time(e1), 0.0)
+    ms, wall = _max_over_ranks([ms, wall], dev, world)
+    return ms / n, max(ms, wall) / n
+
+
+def _supervised_config(tag, workload, trainer, hr_px_per_sample, batch, args, dev, world, tf32_peak, stated_gpus):
+    import numpy as np
+    import torch
+    trainer.setup_datagen()
+    trainer.setup_model()
+    st = trainer.train_step
+    batches = [trainer.ds_train[i % len(trainer.ds_train)] for i in range(2)]
+    fold = trainer.model_is_spatiotemporal
+
+    def fix(x):          # App. B #2: spatio-temporal LR batches without predictors come out without a channel axis
+        x = [np.asarray(a, np.float32) for a in x]
+        if fold and x[0].ndim == 4:
+            x[0] = x[0][..., None]
+        return x
+    batches = [(fix(x), np.asarray(y[0], np.float32)) for x, y in batches]
+    # device-resident pool: stage both batches once in the layout of the static buffers
+    pool = []
+    for x, y in batches:
+        trainer._stage(x, y)
+        torch.cuda.synchronize()
+        pool.append(([t.clone() for t in st.inputs], st.target.clone()))
+
+    def dev_step(i):
+        ins, tgt = pool[i % len(pool)]
+        st.load_batch(ins, tgt)
+        return st.run()
+    n, warm = max(10, args.steps // 2), max(3, args.warmup)
+    ms_dev, _ = _time_steps(dev_step, n, warm, dev, world)
+
+    def host_epoch(k):
+        for _ in trainer.train_on_batches((batches[i % len(batches)] for i in range(k))):
+            pass
+    host_epoch(warm)
+    _, ms_e2e = _time_steps(lambda i: None if i else host_epoch(n), 1, 0, dev, world)
+    ms_e2e /= n
+    px = batch * hr_px_per_sample * world
+    flops = 2.0 * trainer.train_macs_per_sample() * batch
+    h2d = sum(int(np.prod(t.shape)) for t in st.inputs) * 4 + int(np.prod(st.target.shape)) * 4
+    return {
+        'workload': workload, 'per_gpu_batch': batch, 'n_gpus': world, 'stated_gpus': stated_gpus,
+        'ms_per_step': ms_dev, 'value': px / (ms_dev * 1e-3), 'unit': UNIT,
+        'e2e': {'value': px / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 4, 'api': 'SupervisedTrainer.train_on_batches(host numpy batches)'},
+        'params': trainer.model.count_params(), 'launches_per_step': int(st.launches_per_step),
+        'roofline': {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': tf32_peak,
+                     'achieved': flops / (ms_dev * 1e-3) / 1e12, 'frac': flops / (ms_dev * 1e-3) / 1e12 / tf32_peak,
+                     'algorithmic_gflop_per_step': flops / 1e9,
+                     'note': 'whole-step algorithmic FLOPs (2 * MACs of the reference graph, fwd + dgrad + wgrad) / step time'},
+    }
+
+
+def run_extra_configs(args, dev, rank, world, tf32_peak):
+    import numpy as np
+    import torch
+    from dl4ds_b200 import nets, training
+    from dl4ds_b200.training import cgan
+    out = {}
+    rng = np.random.default_rng(4321 + rank)
+    math = args.math
+    want = set(args.configs.split(','))
+    # ---- cfg3: densenet + channel attention + LCB, 8x deconvolution, 3 predictors + 1 static, LR 16 -> HR 128
+    if 'cfg3' in want:
+        B = 16
+        hr = rng.standard_normal((2 * B, 128, 128, 1), dtype=np.float32)
+        preds = [rng.standard_normal((2 * B, 128, 128, 1), dtype=np.float32) for _ in range(3)]
+        static = rng.standard_normal((128, 128)).astype(np.float32)
+        tr = training.SupervisedTrainer('densenet', 'dc', hr, hr[:B], hr[:B], predictors_train=preds,
+                                        predictors_val=[q[:B] for q in preds], predictors_test=[q[:B] for q in preds],
+                                        static_vars=[static], scale=8, batch_size=B, epochs=1, learning_rate=1e-3,
+                                        verbose=False, save=False, math=math, seed=1, attention=True, localcon_layer=True)
+        out['cfg3'] = _supervised_config(
+            'cfg3', 'SupervisedTrainer step: densenet + ChannelAttention + LCB, 8x deconv, 3 predictors + 1 static, '
+                    'LR 16 -> HR 128, batch 16 per GPU (128 over 8 GPUs), MAE, Adam', tr, 128 * 128, B, args, dev, world,
+            tf32_peak, 8)
+        del tr
+        torch.cuda.empty_cache()
+    # ---- cfg4: recurrent (ConvLSTM) resnet, 4x resize-convolution, T = 6, 32 -> 128
+    if 'cfg4' in want:
+        B, T = 8, 6
+        hr = rng.standard_normal((2 * B + T, 128, 128, 1), dtype=np.float32)
+        tr = training.SupervisedTrainer('resnet', 'rc', hr, hr[:B + T], hr[:B + T], scale=4, time_window=T, batch_size=B,
+                                        epochs=1, learning_rate=1e-3, verbose=False, save=False, math=math, seed=1)
+        out['cfg4'] = _supervised_config(
+            'cfg4', 'SupervisedTrainer step: recurrent ConvLSTM resnet, 4x resize-conv, seq_len 6, 32 -> 128, '
+                    'batch 8 per GPU (32 over 4 GPUs), MAE, Adam', tr, T * 128 * 128, B, args, dev, world, tf32_peak, 4)
+        del tr
+        torch.cuda.empty_cache()
+    # ---- cfg5: CGANTrainer step, U-Net generator (pin) + residual discriminator, 256 x 256
+    if 'cfg5' in want:
+        import torch.distributed as dist
+        B, hw = 4, 256
+        hr = rng.standard_normal((2 * B, hw, hw, 1), dtype=np.float32)
+        static = rng.standard_normal((hw, hw)).astype(np.float32)
+        G = nets.unet_pin('unet', 2, 1, (hw, hw), 1, 8, 6, math=math).to(dev).init_weights(seed=1)
+        D = nets.residual_discriminator(2, 'pin', False, 4, (hw, hw), n_filters=8, n_res_blocks=4, math=math).to(dev).init_weights(seed=2)
+        st_b = np.broadcast_to(static[None, :, :, None], (B, hw, hw, 1)).astype(np.float32).copy()
+        lrs = [np.concatenate([hr[i * B:(i + 1) * B], st_b], axis=-1).astype(np.float32) for i in range(2)]
+        hrs = [hr[i * B:(i + 1) * B] for i in range(2)]
+        d = dist if world > 1 else None
+        step = cgan.CGANStep(G, D, lrs[0].shape, hrs[0].shape, st_b.shape, dist=d).capture()
+        step.run(lrs[0], hrs[0], st_b, first_batch=True)
+        lrd = [torch.from_numpy(a).to(dev) for a in lrs]
+        hrd = [torch.from_numpy(a).to(dev) for a in hrs]
+        std = torch.from_numpy(st_b).to(dev)
+        n, warm = max(10, args.steps // 2), max(3, args.warmup)
+
+        def dev_step(i):        # device-resident arrays; the loss read (D2H of 4 floats) stays, as train_step returns floats
+            step.run(lrd[i % 2], hrd[i % 2], std)
+        ms_dev, _ = _time_steps(dev_step, n, warm, dev, world)
+        _, ms_e2e = _time_steps(lambda i: step.run(lrs[i % 2], hrs[i % 2], st_b), n, warm, dev, world)
+        FG, FGd = G.macs_per_sample, G.macs_dgrad_per_sample
+        FD, FDd = D.macs_per_sample, D.macs_dgrad_per_sample
+        # G: fwd + dgrad + wgrad; D: two forward passes, weight + input gradients through both, one more input-gradient
+        # pass through D(fake) for the generator loss (the reference's two tapes, cgan.py:587-611)
+        macs = (2 * FG + FGd) + (2 * FD + 2 * (FD + FDd) + FDd)
+        flops = 2.0 * macs * B
+        px = B * hw * hw * world
+        out['cfg5'] = {
+            'workload': 'CGANTrainer train_step: U-Net generator (pin, n_filters 8, n_blocks 6) + residual discriminator, '
+                        '256 x 256, 1 static variable, batch 4 per GPU (32 over 8 GPUs), MAE + BCE, two Adam(beta_1 0.5)',
+            'per_gpu_batch': B, 'n_gpus': world, 'stated_gpus': 8,
+            'ms_per_step': ms_dev, 'value': px / (ms_dev * 1e-3), 'unit': UNIT,
+            'e2e': {'value': px / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+                    'h2d_bytes_per_step': int(lrs[0].nbytes + hrs[0].nbytes + st_b.nbytes), 'd2h_bytes_per_step': 16,
+                    'api': 'CGANStep.run(host numpy LR / HR / static arrays) -> 4 float losses (what CGANTrainer.run loops over)'},
+            'params': G.count_params() + D.count_params(),
+            'roofline': {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': tf32_peak,
+                         'achieved': flops / (ms_dev * 1e-3) / 1e12, 'frac': flops / (ms_dev * 1e-3) / 1e12 / tf32_peak,
+                         'algorithmic_gflop_per_step': flops / 1e9,
+                         'note': 'whole-step algorithmic FLOPs (generator fwd+bwd, discriminator 2 fwd + 2 bwd + 1 dgrad) / step time'},
+        }
+    return out
 
 
 _REAL_STDOUT = None
@@ -391,6 +616,8 @@ def main():
     ap.add_argument('--math', default=os.environ.get('DL4DS_MATH', 'auto'),
                     choices=['auto', 'fp32', 'tf32x3', 'tf32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline sample')
+    ap.add_argument('--configs', default='cfg3,cfg4,cfg5',
+                    help="BASELINE configs measured after the headline ('' = none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     _stdout_to_stderr()
