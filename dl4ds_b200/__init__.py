@@ -11,3 +11,4 @@ from .nets import (net_pin, net_postupsampling, recnet_pin, recnet_postupsamplin
 from .training import CGANTrainer, SupervisedTrainer, Trainer  # noqa: F401
 from .inference import Predictor, predict  # noqa: F401
 from . import losses  # noqa: F401
+from .metrics import compute_correlation, compute_metrics, compute_rmse  # noqa: F401

@@ -44,6 +44,8 @@ SIGNATURES = {
     'dl4ds_pixel_loss': ('i', 'pppplifp'),
     'dl4ds_ssim_loss_workspace_floats': ('l', 'iiiii'),
     'dl4ds_ssim_loss': ('i', 'ppiiiiipfppipp'),
+    'dl4ds_ssim_index': ('i', 'ppiiiifppp'),
+    'dl4ds_metrics_moments': ('i', 'ppilppp'),
     'dl4ds_batchnorm_stats': ('i', 'pilippppfpp'),
     'dl4ds_norm_apply': ('i', 'pippppfpiliip'),
     'dl4ds_batchnorm_bwd': ('i', 'pipipipppfpipppliip'),
@@ -60,6 +62,7 @@ SIGNATURES = {
     'dl4ds_convt_rearrange': ('i', 'ppiiiiiiiip'),
     'dl4ds_gather_crop': ('i', 'pppppiiiiiiiip'),
     'dl4ds_avgpool_coarsen': ('i', 'ppiiiiip'),
+    'dl4ds_resample_taps': ('i', 'ppiiiiiippippiiip'),
     'dl4ds_resize_bilinear_fwd': ('i', 'pipiiiiiiip'),
     'dl4ds_resize_bilinear_bwd': ('i', 'pipiiiiiiip'),
     'dl4ds_resize_fwd': ('i', 'pipiiiiiiiip'),

@@ -456,6 +456,41 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
 }
 
 // -------------------------------------------------------------------------------------------------
+// data path: separable resampling with per-output tap tables -- cv2.resize (utils.py:341-401) for every
+// interpolation the reference offers (inter_area up/down, nearest, bilinear, bicubic, lanczos4).  The tables hold, per
+// output row (column), K source indices and float32 weights taken from cv2 itself (dataloader.DeviceDataGenerator
+// resizes an identity matrix), so the arithmetic is cv2's: horizontal pass first, then the vertical one.
+// -------------------------------------------------------------------------------------------------
+__global__ void resample_taps_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C,
+                                     int Ho, int Wo, const int* __restrict__ iy, const float* __restrict__ wy, int Ky,
+                                     const int* __restrict__ ix, const float* __restrict__ wx, int Kx, int y_ld,
+                                     int y_coff) {
+    const int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        int64_t t = i / C;
+        const int ox = (int)(t % Wo); t /= Wo;
+        const int oy = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const float* base = x + (int64_t)n * H * W * C + c;
+        float acc = 0.0f;
+        for (int j = 0; j < Ky; ++j) {
+            const float wj = __ldg(wy + oy * Ky + j);
+            if (wj == 0.0f) continue;
+            const float* row = base + (int64_t)__ldg(iy + oy * Ky + j) * W * C;
+            float h = 0.0f;
+            for (int k = 0; k < Kx; ++k) {
+                const float wk = __ldg(wx + ox * Kx + k);
+                if (wk != 0.0f) h = fmaf(wk, __ldg(row + (int64_t)__ldg(ix + ox * Kx + k) * C), h);
+            }
+            acc = fmaf(wj, h, acc);
+        }
+        y[(((int64_t)n * Ho + oy) * Wo + ox) * y_ld + y_coff + c] = acc;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // data path: s x s block mean, summation order of cv2's resizeAreaFast (utils.py:376-384):
 // k runs row-major over the s*s window, accumulated as sum += ((v0+v1)+v2)+v3 per group of four,
 // remainder one by one, then multiplied by 1/(s*s).
@@ -1289,6 +1324,17 @@ int dl4ds_avgpool_coarsen(const float* x, float* y, int N, int H, int W, int C, 
                   "avgpool_coarsen: H, W must be multiples of s");
     return launch1d("avgpool_coarsen", avgpool_coarsen_kernel, (int64_t)N * (H / s) * (W / s) * C,
                     as_stream(stream), x, y, N, H, W, C, s);
+}
+
+int dl4ds_resample_taps(const float* x, float* y, int N, int H, int W, int C, int Ho, int Wo, const int* iy,
+                        const float* wy, int Ky, const int* ix, const float* wx, int Kx, int y_ld, int y_coff,
+                        void* stream) {
+    DL4DS_REQUIRE(x && y && iy && wy && ix && wx, DL4DS_E_BADARG, "resample_taps: null pointer");
+    DL4DS_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && Ho > 0 && Wo > 0 && Ky > 0 && Kx > 0, DL4DS_E_SHAPE,
+                  "resample_taps: bad shape");
+    DL4DS_REQUIRE(y_coff >= 0 && y_ld >= y_coff + C, DL4DS_E_SHAPE, "resample_taps: channel slice outside y_ld");
+    return launch1d("resample_taps", resample_taps_kernel, (int64_t)N * Ho * Wo * C, as_stream(stream), x, y, N, H, W, C,
+                    Ho, Wo, iy, wy, Ky, ix, wx, Kx, y_ld, y_coff);
 }
 
 int dl4ds_resize_bilinear_fwd(const float* x, int x_ld, float* y, int y_ld,

@@ -362,6 +362,27 @@ __global__ void ssim_fixup_kernel(const float* __restrict__ stats, float* __rest
     }
 }
 
+// tf.image.ssim(img1, img2, max_val) per image (metrics.py:172-176): no shift, C1 / C2 from the given dynamic range
+__global__ void ssim_index_setup_kernel(float max_val, float* __restrict__ stats, float* __restrict__ plane_acc, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) plane_acc[i] = 0.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[S_SHIFT_P] = 0.0f;
+        stats[S_SHIFT_T] = 0.0f;
+        stats[S_C1] = (kK1 * max_val) * (kK1 * max_val);
+        stats[S_C2] = (kK2 * max_val) * (kK2 * max_val);
+        stats[S_L] = max_val;
+    }
+}
+
+__global__ void ssim_index_final_kernel(const float* __restrict__ plane_acc, float inv_count, int B, int C,
+                                        float* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.0f;
+    for (int c = 0; c < C; ++c) s += plane_acc[b * C + c] * inv_count;
+    out[b] = s / (float)C;
+}
+
 struct Layout {
     int64_t stats, plane_acc, coef, partial, total;
     int64_t img_p[kMaxScales], img_t[kMaxScales], grad[kMaxScales], maps[kMaxScales];
@@ -488,6 +509,27 @@ int dl4ds_ssim_loss(const float* y_pred, const float* y_true, int B, int H, int 
         ssim_fixup_kernel<<<1, 32, 0, st>>>(stats, dy);
     }
     return check_launch("ssim_loss");
+}
+
+int dl4ds_ssim_index(const float* img1, const float* img2, int B, int H, int W, int C, float max_val, float* out,
+                     float* ws, void* stream) {
+    DL4DS_REQUIRE(img1 && img2 && out && ws, DL4DS_E_BADARG, "ssim_index: null pointer");
+    DL4DS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, DL4DS_E_BADARG, "ssim_index: ws not 16-byte aligned");
+    const int rc = check_shape(B, H, W, C, 1);
+    if (rc != DL4DS_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const Layout l = make_layout(B, H, W, C, 1);
+    const Gauss g = make_gauss();
+    const int n_planes = B * C;
+    float* stats = ws + l.stats;
+    ssim_index_setup_kernel<<<(unsigned)cdiv(3 * n_planes, 256), 256, 0, st>>>(max_val, stats, ws + l.plane_acc,
+                                                                               3 * n_planes);
+    const int Ho = H - kHalo, Wo = W - kHalo;
+    dim3 grid((unsigned)cdiv(Wo, kTile), (unsigned)cdiv(Ho, kTile), (unsigned)n_planes);
+    ssim_maps_kernel<<<grid, 256, 0, st>>>(img1, img2, stats, H, W, C, 0, g, ws + l.maps[0], ws + l.plane_acc, n_planes);
+    ssim_index_final_kernel<<<(unsigned)cdiv(B, 128), 128, 0, st>>>(ws + l.plane_acc, 1.0f / ((float)Ho * (float)Wo), B, C,
+                                                                    out);
+    return check_launch("ssim_index");
 }
 
 }  // extern "C"

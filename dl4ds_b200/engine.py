@@ -1071,12 +1071,17 @@ class Ctx:
         self._record(bwd)
         return out
 
-    def group_mean(self, x):
-        """GlobalAveragePooling2D -- discriminator.py:76.  (N,H,W,C) -> (N,1,1,C)."""
+    def group_mean(self, x, n_groups=None):
+        """GlobalAveragePooling2D -- discriminator.py:76.  (N,H,W,C) -> (N,1,1,C).  ``n_groups`` = B on BATCH-major
+        frames (B*T,H,W,C) pools every sample's T consecutive frames together: GlobalAveragePooling3D over (T,H,W),
+        discriminator.py:74 -> (B,1,1,C)."""
         self._use(x)
-        out = new_var(x.N, 1, 1, x.C, self.device)
+        ng = x.N if n_groups is None else int(n_groups)
+        assert x.N % ng == 0
+        ppg = (x.N // ng) * x.H * x.W
+        out = new_var(ng, 1, 1, x.C, self.device)
         self.launches += 1
-        self._call('dl4ds_group_mean_fwd', x.ptr, x.ld, out.ptr, x.N, x.H * x.W, x.C, _stream())
+        self._call('dl4ds_group_mean_fwd', x.ptr, x.ld, out.ptr, ng, ppg, x.C, _stream())
 
         def bwd():
             dy = out.grad
@@ -1085,7 +1090,7 @@ class Ctx:
             dy = self._dense(dy)
 
             def wr(dst):
-                self._call('dl4ds_group_mean_bwd', dy.ptr, dst.ptr, dst.ld, x.N, x.H * x.W, x.C, _stream())
+                self._call('dl4ds_group_mean_bwd', dy.ptr, dst.ptr, dst.ld, ng, ppg, x.C, _stream())
             self._acc_via_tmp(x, wr)
             out.grad = None
         self._record(bwd)
@@ -1172,6 +1177,10 @@ class Ctx:
             dy = out.grad
             if dy is None:
                 return
+            pg = self.param_grads
+            if not pg and not x.requires_grad:      # cGAN generator pass through D: nothing to compute here
+                out.grad = None
+                return
             dy = self._dense(dy)
             dh = dy.buf      # owned; dh_{t-1} is accumulated in place
             dz = new_var(TB, H, W, F4, dev)
@@ -1189,11 +1198,13 @@ class Ctx:
                     self._conv_raw(dzt.data_ptr(), F4, wh.data_ptr(), None, None, 0,
                                    step(dh, t - 1).data_ptr(), filters, B, H, W, F4, H, W, filters, k, 1, 1,
                                    k - 1 - pad, k - 1 - pad, W_FLIP_T, 0, 1, 1)
-                    self._wgrad(Var(step(out.buf, t - 1)), Var(dzt), gwh, k, 1, pad, pad)
+                    if pg:
+                        self._wgrad(Var(step(out.buf, t - 1)), Var(dzt), gwh, k, 1, pad, pad)
             # the input convolution's bias / weight / input gradients, all T in one shot
-            self._call('dl4ds_bias_act_bwd', dz.ptr, dz.ld, None, 0, None, 0,
-                       self._g(name + '/bias').data_ptr(), TB, H, W, F4, 0, 1, _stream())
-            self._wgrad(x, dz, self._g(name + '/kernel'), k, 1, pad, pad)
+            if pg:
+                self._call('dl4ds_bias_act_bwd', dz.ptr, dz.ld, None, 0, None, 0,
+                           self._g(name + '/bias').data_ptr(), TB, H, W, F4, 0, 1, _stream())
+                self._wgrad(x, dz, self._g(name + '/kernel'), k, 1, pad, pad)
             if x.requires_grad:
                 def wr(dst, beta):
                     self._conv_raw(dz.ptr, dz.ld, wx.data_ptr(), None, None, 0, dst.ptr,

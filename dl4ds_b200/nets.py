@@ -170,6 +170,13 @@ class Model:
 
     save = save_weights
 
+    def load_keras_weights(self, source):
+        """Weights of a reference-trained Keras model, exported on the reference side with
+        ``keras_import.REFERENCE_EXPORT_SNIPPET`` (structural variable names); see keras_import.py."""
+        from .keras_import import load_keras_weights
+        load_keras_weights(self, source)
+        return self
+
     def save_checkpoint(self, path):
         """Weights AND optimizer state of the flat arena (theta, Adam m / v per parameter, iteration count) in one
         ``.npz`` -- what ``tf.train.Checkpoint(generator=..., generator_optimizer=...)`` stores in the reference
@@ -609,21 +616,33 @@ def recnet_pin(backbone_block, n_channels, n_aux_channels, hr_size, time_window,
 
 def residual_discriminator(n_channels, upsampling, is_spatiotemporal, scale, lr_size, n_filters=8,
                            n_res_blocks=4, normalization=None, activation='relu', attention=False,
-                           math='fp32'):
-    """residual_discriminator -- discriminator.py:11-81 (spatial variant).  ResidualBlocks always
-    use relu (the ``activation`` argument is ignored there, :36-38).  Dropout(0.4) on the pooled
-    features is applied with a caller-supplied keep mask as third input (training) or skipped."""
-    if is_spatiotemporal:
-        raise NotImplementedError('spatio-temporal discriminator is outside the B200 hot path')
+                           math='fp32', time_window=None):
+    """residual_discriminator -- discriminator.py:11-81.  ResidualBlocks always use relu (the ``activation``
+    argument only reaches the recurrent stem, :31-33,36-38).  Dropout(0.4) on the pooled features is applied with a
+    caller-supplied keep mask as third input (training) or skipped.
+
+    Spatio-temporal variant (``is_spatiotemporal``, discriminator.py:25-33,42-47,73-74): inputs (B,T,h,w,C) and
+    (B,T,H,W,1), held as time-major frames; the LR branch starts with RecurrentConvBlock(normalization='ln'), every
+    Conv2D / ResidualBlock acts per frame (Keras Conv2D on a 5-D tensor folds the leading axes), and
+    GlobalAveragePooling3D pools (T,H,W).  ``time_window`` (an addition) fixes T for shape inference; the reference's
+    Input has T = None."""
     if normalization not in (None, 'bn', 'ln'):
         raise ValueError('Normalization not supported, got %s' % (normalization,))
-    if normalization is not None and is_spatiotemporal:
-        raise NotImplementedError('normalization in the spatio-temporal discriminator is not built')
+    if is_spatiotemporal and attention:
+        raise NotImplementedError('ChannelAttention2D on the 5-D tensors of the spatio-temporal discriminator is not built')
+    if is_spatiotemporal and activation not in B.SUPPORTED_ACTIVATIONS:
+        raise NotImplementedError('activation %r is outside the B200 hot path' % (activation,))
+    T = int(time_window) if (is_spatiotemporal and time_window) else None
+    if is_spatiotemporal and not T:
+        raise ValueError('the spatio-temporal discriminator needs `time_window`')
 
     def fn(c, inputs):
         x_in, x_ref = inputs[0], inputs[1]
         mask = inputs[2] if len(inputs) > 2 else None
-        x1 = b = c.conv(x_in, 'branch1_stem', n_filters)
+        if is_spatiotemporal:
+            x1 = b = B.recurrent_conv_block(c, 'branch1_recurrent', x_in, n_filters, T, activation, 'ln')
+        else:
+            x1 = b = c.conv(x_in, 'branch1_stem', n_filters)
         for i in range(n_res_blocks):
             b = B.residual_block(c, 'ResidualBlock%d_branch1' % (i + 1), b, n_filters, 'relu', attention,
                                  normalization=normalization)
@@ -646,7 +665,11 @@ def residual_discriminator(n_channels, upsampling, is_spatiotemporal, scale, lr_
             x2 = c.conv(cc, 'branch2_last', n_filters, res=x2)
         x = c.concat([x1, x2])
         x = B.residual_block(c, 'ResidualBlock_merged', x, x.C, 'relu', attention, normalization=normalization)
-        x = c.group_mean(x)
+        if is_spatiotemporal:
+            bsz = x.N // T
+            x = c.group_mean(c.permute_frames(x, T, bsz), n_groups=bsz)     # GlobalAveragePooling3D over (T,H,W)
+        else:
+            x = c.group_mean(x)
         if mask is not None:
             x = c.mul_mask(x, mask)
         x = c.dense(x, 'dense1', 32, act='sigmoid')
@@ -657,4 +680,7 @@ def residual_discriminator(n_channels, upsampling, is_spatiotemporal, scale, lr_
         ref_hw = (int(lr_size[0] * scale), int(lr_size[1] * scale))
     else:
         in_hw = ref_hw = (lr_size[0], lr_size[1])
+    if is_spatiotemporal:
+        return Model('discriminator', fn, [(T,) + in_hw + (n_channels,), (T,) + ref_hw + (1,)], time_window=T,
+                     math=math)
     return Model('discriminator', fn, [in_hw + (n_channels,), ref_hw + (1,)], math=math)

@@ -157,8 +157,8 @@ class SpecCtx:
     def repeat_frames(self, x, T):
         return SVar(x.N * T, x.H, x.W, x.C)
 
-    def group_mean(self, x):
-        return SVar(x.N, 1, 1, x.C)
+    def group_mean(self, x, n_groups=None):
+        return SVar(x.N if n_groups is None else n_groups, 1, 1, x.C)
 
     def mul_mask(self, x, mask):
         return x

@@ -67,6 +67,25 @@ def discriminator_loss(disc_real_output, disc_generated_output):
     return _bce_np(1.0, disc_real_output) + _bce_np(0.0, disc_generated_output)
 
 
+def _draw_keep_masks(D, masks):
+    """Fill ``masks`` (CUDA tensors (B,1,1,F)) with fresh inverted-dropout keep masks of rate DROPOUT_RATE
+    (discriminator.py:77 under ``training=True``: an independent mask per D call): ``dl4ds_dropout`` (Philox keyed by
+    the discriminator arena's device-resident {seed, step}) applied to a tensor of ones; no torch operator."""
+    import torch
+    from .. import _lib
+    state = D.arena.rng_state()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call('dl4ds_rng_advance', state.data_ptr(), st)
+    for i, m in enumerate(masks):
+        ones = getattr(D, '_mask_ones', None)
+        if ones is None or ones.shape != m.shape or ones.device != m.device:
+            ones = D._mask_ones = torch.ones_like(m)
+        B, F = m.shape[0], m.shape[-1]
+        _lib.call('dl4ds_dropout', ones.data_ptr(), F, m.data_ptr(), F, B, 1, B, F, float(DROPOUT_RATE), 0,
+                  state.data_ptr(), 1000 + i, st)
+    return masks
+
+
 def _dev_inputs(model, arrays, dev):
     ins, _, _ = model._prep_inputs(arrays, dev)
     return ins
@@ -122,6 +141,12 @@ class CGANStep:
         z = lambda shp: torch.zeros(tuple(shp), dtype=torch.float32, device=dev)
         self.lr, self.hr = z(lr_shape), z(hr_shape)
         self.st = z(static_shape) if static_shape is not None else None
+        # spatio-temporal step (5-D arrays, cgan.py:575-639 with recnet generators): the (B,T,H,W,C) staging buffers
+        # are re-ordered into the engine's time-major frames (T*B,H,W,C) by dl4ds_permute_frames inside the graph
+        self.frames = None
+        if len(lr_shape) == 5:
+            fr = lambda shp: z((shp[0] * shp[1],) + tuple(shp[2:]))
+            self.frames = (fr(lr_shape), fr(hr_shape))
         nfeat = self.D.spec['dense1/kernel'][0]
         self.masks = [z((lr_shape[0], 1, 1, nfeat)) for _ in range(2)]
         self.losses = z((4,))
@@ -143,6 +168,19 @@ class CGANStep:
             _lib.call('dl4ds_adam_step_dev', a.theta.data_ptr(), a.grad.data_ptr(), a.m.data_ptr(), a.v.data_ptr(), a.n,
                       lr_t.data_ptr(), float(self.b1), float(self.b2), float(self.eps), 1.0 / self.world, st)
 
+    def _device_step(self):
+        """Everything the captured graph holds up to the gradients."""
+        import torch
+        from .. import _lib
+        lr, hr = self.lr, self.hr
+        if self.frames is not None:
+            st = torch.cuda.current_stream().cuda_stream
+            for src, dst in zip((self.lr, self.hr), self.frames):
+                b, t = src.shape[0], src.shape[1]
+                _lib.call('dl4ds_permute_frames', src.data_ptr(), dst.data_ptr(), b, t, src[0, 0].numel(), st)
+            lr, hr = self.frames
+        _fwd_bwd(self.G, self.D, lr, hr, self.st, self.masks, self.losses, self.pxloss)
+
     def _exchange(self):
         """hvd.DistributedGradientTape (cgan.py:608-611): both gradient arenas summed over the ranks on this stream."""
         if self.dist is not None and self.world > 1:
@@ -153,7 +191,7 @@ class CGANStep:
     def capture(self):
         import torch
         snap = [(m.arena.theta.clone(), m.arena.m.clone(), m.arena.v.clone(), m.arena.t) for m in (self.G, self.D)]
-        _fwd_bwd(self.G, self.D, self.lr, self.hr, self.st, self.masks, self.losses, self.pxloss)   # warm-up (eager)
+        self._device_step()                                                                         # warm-up (eager)
         self._exchange()
         self._opt()
         torch.cuda.synchronize()
@@ -165,7 +203,7 @@ class CGANStep:
             self.graph_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_fb, stream=s):
                 # one graph: both backward passes, the two NCCL all-reduces (dl4ds_comm_*, captured), both Adam updates
-                _fwd_bwd(self.G, self.D, self.lr, self.hr, self.st, self.masks, self.losses, self.pxloss)
+                self._device_step()
                 self._exchange()
                 self._opt()
             self.graph_opt = self.graph_fb
@@ -183,11 +221,11 @@ class CGANStep:
         if self.st is not None:
             self.st.copy_(f32(static_array), non_blocking=True)
         keep = 1.0 - DROPOUT_RATE
-        for i, m in enumerate(self.masks):
-            if dropout_masks is not None:
+        if dropout_masks is not None:
+            for i, m in enumerate(self.masks):
                 m.copy_(f32(dropout_masks[i]).reshape(m.shape))
-            else:
-                m.copy_((torch.rand(m.shape, device=m.device) < keep).to(torch.float32) / keep)
+        else:
+            _draw_keep_masks(self.D, self.masks)
         for i, mdl in enumerate((self.G, self.D)):
             mdl.arena.t += 1
             t = mdl.arena.t
@@ -217,14 +255,14 @@ def train_step(lr_array, hr_array, generator, discriminator, generator_optimizer
     dev = G.arena.device
     f32 = lambda a: torch.as_tensor(np.asarray(a, np.float32) if not torch.is_tensor(a) else a).to(dev, torch.float32).contiguous()
     lr_t, hr_t = f32(lr_array), f32(hr_array)
-    if lr_t.dim() != 4:
-        raise NotImplementedError('the spatio-temporal cGAN step is outside the B200 hot path')
-    st_t = f32(static_array) if static_array is not None else None
     B = lr_t.shape[0]
+    if lr_t.dim() == 5:         # spatio-temporal models: (B,T,H,W,C) -> the engine's time-major frames (T*B,H,W,C)
+        tm = lambda x: x.transpose(0, 1).reshape(x.shape[0] * x.shape[1], *x.shape[2:]).contiguous()
+        lr_t, hr_t = tm(lr_t), tm(hr_t)
+    st_t = f32(static_array) if static_array is not None else None
     nfeat = D.spec['dense1/kernel'][0]
     if dropout_masks is None:
-        keep = 1.0 - DROPOUT_RATE
-        mk = [(torch.rand((B, 1, 1, nfeat), device=dev) < keep).to(torch.float32) / keep for _ in range(2)]
+        mk = _draw_keep_masks(D, [torch.empty((B, 1, 1, nfeat), dtype=torch.float32, device=dev) for _ in range(2)])
     else:
         mk = [f32(m) for m in dropout_masks]
     world = dist.get_world_size() if dist is not None else 1
@@ -298,13 +336,18 @@ class CGANTrainer(Trainer):
         """cgan.py:173-262."""
         n_channels = self.data_train.shape[-1]
         n_aux_channels = 0
-        if self.model_is_spatiotemporal:
-            raise NotImplementedError('the spatio-temporal cGAN is outside the B200 hot path')
-        if self.static_vars is not None:
-            n_channels += len(self.static_vars)
-            n_aux_channels = len(self.static_vars)
-        if self.predictors_train is not None:
-            n_channels += len(self.predictors_train)
+        st = self.model_is_spatiotemporal
+        if st:                      # cgan.py:179-185: static variables only feed the HR aux branch
+            if self.predictors_train is not None:
+                n_channels += len(self.predictors_train)
+            if self.static_vars is not None:
+                n_aux_channels += len(self.static_vars)
+        else:
+            if self.static_vars is not None:
+                n_channels += len(self.static_vars)
+                n_aux_channels = len(self.static_vars)
+            if self.predictors_train is not None:
+                n_channels += len(self.predictors_train)
         if self.patch_size is None:
             lr_h, lr_w = int(self.data_train.shape[1] / self.scale), int(self.data_train.shape[2] / self.scale)
             hr_h, hr_w = int(self.data_train.shape[1]), int(self.data_train.shape[2])
@@ -312,11 +355,21 @@ class CGANTrainer(Trainer):
             lr_h = lr_w = int(self.patch_size / self.scale)
             hr_h = hr_w = int(self.patch_size)
         gp = self.generator_params
-        if self.upsampling in POSTUPSAMPLING_METHODS:
+        if self.upsampling in POSTUPSAMPLING_METHODS and st:
+            self.generator = nets.recnet_postupsampling(
+                backbone_block=self.backbone, upsampling=self.upsampling, scale=self.scale, n_channels=n_channels,
+                n_aux_channels=n_aux_channels, lr_size=(lr_h, lr_w), time_window=self.time_window, math=self.math, **gp)
+            d_size = (lr_h, lr_w)
+        elif self.upsampling in POSTUPSAMPLING_METHODS:
             self.generator = nets.net_postupsampling(
                 backbone_block=self.backbone, upsampling=self.upsampling, scale=self.scale,
                 n_channels=n_channels, n_aux_channels=n_aux_channels, lr_size=(lr_h, lr_w), math=self.math, **gp)
             d_size = (lr_h, lr_w)
+        elif st:
+            self.generator = nets.recnet_pin(backbone_block=self.backbone, n_channels=n_channels,
+                                             n_aux_channels=n_aux_channels, hr_size=(hr_h, hr_w),
+                                             time_window=self.time_window, math=self.math, **gp)
+            d_size = (hr_h, hr_w)
         elif self.backbone == 'unet':
             self.generator = nets.unet_pin(backbone_block=self.backbone, n_channels=n_channels,
                                            n_aux_channels=n_aux_channels, hr_size=(hr_h, hr_w),
@@ -332,8 +385,8 @@ class CGANTrainer(Trainer):
         # the tensors really have is passed so that shape inference is exact
         self.discriminator = nets.residual_discriminator(
             n_channels=n_channels, scale=self.scale, upsampling=self.upsampling,
-            is_spatiotemporal=self.model_is_spatiotemporal, lr_size=d_size, math=self.math,
-            **self.discriminator_params)
+            is_spatiotemporal=st, lr_size=d_size, math=self.math,
+            time_window=self.time_window if st else None, **self.discriminator_params)
         seed = self.seed if self.seed is not None else int(np.random.randint(0, 2 ** 31 - 2))
         dev = self.dp.torch_device
         self.generator.to(dev).init_weights(seed)
@@ -376,6 +429,8 @@ class CGANTrainer(Trainer):
                 else:
                     [lr_array], [hr_array] = res
                     aux_hr = None
+                if self.model_is_spatiotemporal and np.ndim(lr_array) == 4:
+                    lr_array = lr_array[..., None]      # the single-variable LR batch lost its channel axis
                 if self._step is None and self.use_graph:
                     # static shapes (fixed batch / patch size): capture the step once, replay it per batch
                     self._step = CGANStep(
@@ -427,6 +482,8 @@ class CGANTrainer(Trainer):
             else:
                 [lr_array], [hr_array] = res
                 input_test = [lr_array]
+            if self.model_is_spatiotemporal and np.ndim(input_test[0]) == 4:
+                input_test[0] = input_test[0][..., None]
             y_pred = self.generator.predict(input_test, batch_size=self.batch_size)
             self.test_loss = _host_loss(self.lossf, hr_array, y_pred)
             if self.verbose:
@@ -475,7 +532,8 @@ def load_checkpoint(checkpoint_dir, checkpoint_number, backbone, upsampling, sca
         raise ValueError('`upsampling` not recognized')
     discriminator = nets.residual_discriminator(
         n_channels=n_channels, upsampling=upsampling, is_spatiotemporal=st, scale=scale, lr_size=input_height_width,
-        n_filters=n_filters[1], n_res_blocks=n_blocks[1], attention=attention, math=math)
+        n_filters=n_filters[1], n_res_blocks=n_blocks[1], attention=attention, math=math,
+        time_window=time_window if st else None)
     ck = os.path.join(checkpoint_dir, 'checkpoints')
     if not os.path.isdir(ck):
         ck = checkpoint_dir

@@ -213,6 +213,21 @@ int dl4ds_ssim_loss(const float* y_pred, const float* y_true, int B, int H, int 
                     const float* power_factors, float scale, float* loss_out, float* dy, int accumulate,
                     float* ws, void* stream);
 
+/* tf.image.ssim(img1, img2, max_val) per image as compute_metrics calls it (metrics.py:172-176): no shift, the given
+ * dynamic range; out[b] = mean over channels and windows.  `ws`: dl4ds_ssim_loss_workspace_floats(B,H,W,C,1) floats. */
+int dl4ds_ssim_index(const float* img1, const float* img2, int B, int H, int W, int C, float max_val, float* out,
+                     float* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Verification metrics -- metrics.py:15-97,166-186 (compute_rmse / compute_correlation 'time' and 'space', PSNR,
+ * MAE, dynamic range): raw fp64 moments of the (N, P) fp32 pair y / y_hat.
+ *   pair_out  [N][11]: sum d^2, sum |d|, sum y, sum yh, sum y^2, sum yh^2, sum y*yh over the P values of sample n,
+ *                      then min y, max y, min yh, max yh                                  (NULL: skipped)
+ *   point_out [P][7] : the same seven sums over the N samples for every grid value        (NULL: skipped)
+ * ------------------------------------------------------------------------------------------- */
+int dl4ds_metrics_moments(const float* y, const float* y_hat, int N, int64_t P, double* pair_out, double* point_out,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Normalisation layers of the conv blocks (`normalization='bn' | 'ln'`) with the following activation fused --
  * blocks.py:63-71 (construction), :94-101 ConvBlock, :216-224 ResidualBlock, :263-272 DenseBlock, :298-305
@@ -308,6 +323,16 @@ int dl4ds_gather_crop(const float* src, const int* idx, const int* y0, const int
  * factor -- utils.py:376-384 as called from dataloader.py:204,208.  (N,H,W,C) -> (N,H/s,W/s,C).
  * ------------------------------------------------------------------------------------------- */
 int dl4ds_avgpool_coarsen(const float* x, float* y, int N, int H, int W, int C, int s, void* stream);
+
+/* Data path: cv2.resize for every `interpolation` of utils.resize_array (utils.py:341-401: inter_area, nearest,
+ * bilinear, bicubic, lanczos) as a separable resampling with tap tables: y[n, oy, ox, y_coff + c] =
+ * sum_j wy[oy*Ky + j] * sum_k wx[ox*Kx + k] * x[n, iy[oy*Ky + j], ix[ox*Kx + k], c].  Tables are DEVICE arrays
+ * (int32 indices, fp32 weights; zero weights are skipped); x dense (N,H,W,C), y a channel slice of pitch y_ld.
+ * Used by the device-resident data path for `pin` pairs (coarsen + re-interpolate, dataloader.py:108-150) and for
+ * the non-`inter_area` coarsenings (dataloader.py:157-222). */
+int dl4ds_resample_taps(const float* x, float* y, int N, int H, int W, int C, int Ho, int Wo, const int* iy,
+                        const float* wy, int Ky, const int* ix, const float* wx, int Kx, int y_ld, int y_coff,
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Remaining graph ops for the dense / U-Net / recurrent / cGAN configurations.

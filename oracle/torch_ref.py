@@ -700,12 +700,24 @@ def recnet_pin(p, inputs, backbone_block, time_window, n_channels_out=1, n_filte
 
 
 def residual_discriminator(p, inputs, upsampling, scale, lr_size, n_filters=8, n_res_blocks=4,
-                           attention=False, dropout_mask=None, normalization=None):
-    """residual_discriminator (spatial) -- discriminator.py:11-81.  ResidualBlocks always relu
+                           attention=False, dropout_mask=None, normalization=None, is_spatiotemporal=False,
+                           activation='relu'):
+    """residual_discriminator -- discriminator.py:11-81.  ResidualBlocks always relu
     (App. B #10).  ``dropout_mask``: (B, 2*n_filters) keep-mask already scaled by 1/(1-0.4)
-    (Dropout(0.4) with training=True, cgan.py:599-600); None = inference (identity)."""
-    x_in, x_ref = _nchw(inputs[0]), _nchw(inputs[1])
-    x1 = b = _conv(p, 'branch1_stem', x_in, n_filters)
+    (Dropout(0.4) with training=True, cgan.py:599-600); None = inference (identity).
+    ``is_spatiotemporal`` (:25-33,42-47,73-74): inputs (B,T,h,w,C) / (B,T,H,W,1) NTHWC; the LR branch opens with
+    RecurrentConvBlock(n_filters, activation, normalization='ln'); Keras Conv2D on a 5-D tensor treats the leading
+    axes as batch, so every later layer acts per frame on (B*T,C,H,W); GlobalAveragePooling3D pools (T,H,W)."""
+    if is_spatiotemporal:
+        x5 = inputs[0].permute(0, 1, 4, 2, 3).contiguous()          # (B,T,C,h,w)
+        bsz, t = x5.shape[0], x5.shape[1]
+        r5 = inputs[1].permute(0, 1, 4, 2, 3).contiguous()
+        x_ref = r5.reshape(bsz * t, *r5.shape[2:])
+        b5 = recurrent_conv_block(p, 'branch1_recurrent', x5, n_filters, activation, 'ln')
+        x1 = b = b5.reshape(bsz * t, *b5.shape[2:])
+    else:
+        x_in, x_ref = _nchw(inputs[0]), _nchw(inputs[1])
+        x1 = b = _conv(p, 'branch1_stem', x_in, n_filters)
     for i in range(n_res_blocks):
         b = residual_block(p, 'ResidualBlock%d_branch1' % (i + 1), b, n_filters, 'relu', attention,
                            normalization=normalization)
@@ -730,7 +742,10 @@ def residual_discriminator(p, inputs, upsampling, scale, lr_size, n_filters=8, n
         x2 = x2 + c
     x = torch.cat([x1, x2], dim=1)
     x = residual_block(p, 'ResidualBlock_merged', x, x.shape[1], 'relu', attention, normalization=normalization)
-    x = x.mean(dim=(2, 3))
+    if is_spatiotemporal:
+        x = x.reshape(bsz, t, *x.shape[1:]).mean(dim=(1, 3, 4))     # GlobalAveragePooling3D
+    else:
+        x = x.mean(dim=(2, 3))
     if dropout_mask is not None:
         x = x * dropout_mask
     w1 = p.get('dense1/kernel', (x.shape[1], 32))

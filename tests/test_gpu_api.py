@@ -92,6 +92,58 @@ def test_cgan_step_matches_oracle(cuda):
                                   tight=2e-5)
 
 
+@pytest.mark.parametrize('graph', [False, True])
+def test_cgan_step_spatiotemporal_matches_oracle(cuda, graph):
+    """train_step on 5-D arrays (cgan.py:575-639 with a recurrent generator and the spatio-temporal discriminator):
+    losses and both weight updates after one step == oracle; eagerly and as the captured CGANStep."""
+    rng = np.random.default_rng(12)
+    B, T, hw = 2, 3, 8
+    G = nets.recnet_postupsampling('resnet', 'rc', 4, 1, 1, (hw, hw), T, n_filters=4, n_blocks=1, math='fp32').to(cuda)
+    D = nets.residual_discriminator(1, 'rc', True, 4, (hw, hw), n_filters=4, n_res_blocks=1, math='fp32',
+                                    time_window=T).to(cuda)
+    gw = R.init_weights(G.spec, seed=1, bias_scale=0.05)
+    dw = R.init_weights(D.spec, seed=2, bias_scale=0.05)
+    G.set_weights({k: v.numpy() for k, v in gw.items()})
+    D.set_weights({k: v.numpy() for k, v in dw.items()})
+    lr = rng.standard_normal((B, T, hw, hw, 1)).astype(np.float32)
+    hr = rng.standard_normal((B, T, 4 * hw, 4 * hw, 1)).astype(np.float32)
+    st = rng.standard_normal((B, 4 * hw, 4 * hw, 1)).astype(np.float32)
+    nfeat = D.spec['dense1/kernel'][0]
+    masks = [(rng.random((B, 1, 1, nfeat)) < 0.6).astype(np.float32) / 0.6 for _ in range(2)]
+    if graph:
+        step = cgan.CGANStep(G, D, lr.shape, hr.shape, st.shape, learning_rates=(2e-4, 2e-4)).capture()
+        losses = step.run(lr, hr, st, dropout_masks=masks)
+    else:
+        losses = cgan.train_step(lr, hr, G, D, cgan.Adam(2e-4, beta_1=0.5), cgan.Adam(2e-4, beta_1=0.5),
+                                 gen_pxloss_function='mae', static_array=st, dropout_masks=masks)
+    gen_fn = lambda p, xs: R.recnet_postupsampling(p, xs, 'resnet', 'rc', 4, T, n_filters=4, n_blocks=1)
+    disc_fn = lambda p, xs, m: R.residual_discriminator(p, xs, 'rc', 4, (hw, hw), n_filters=4, n_res_blocks=1,
+                                                        dropout_mask=m, is_spatiotemporal=True)
+    gopt, dopt = R.TFAdam(list(gw), lr=2e-4, beta_1=0.5), R.TFAdam(list(dw), lr=2e-4, beta_1=0.5)
+    ref, _, _ = R.cgan_step(gen_fn, disc_fn, gw, dw, gopt, dopt, torch.from_numpy(lr), torch.from_numpy(hr),
+                            torch.from_numpy(st), mask_real=torch.from_numpy(masks[0].reshape(B, nfeat)),
+                            mask_fake=torch.from_numpy(masks[1].reshape(B, nfeat)))
+    for a, b in zip(losses, ref):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (losses, ref)
+    from tests.util import assert_adam_weights_close
+    for model, w in ((G, gw), (D, dw)):
+        assert_adam_weights_close(model.get_weights(), {k: v.numpy() for k, v in w.items()}, lr=2e-4, steps=1,
+                                  tight=2e-5)
+
+
+def test_cgan_trainer_spatiotemporal_runs(cuda, tmp_path):
+    """CGANTrainer with time_window > 1 (cgan.py:179-185,208-231): recurrent generator + 5-D discriminator."""
+    hr = _data(14, 32, 5)
+    static = np.random.default_rng(6).standard_normal((32, 32)).astype(np.float32)
+    tr = CGANTrainer('resnet', 'rc', hr[:10], hr[10:], scale=4, batch_size=2, epochs=2, static_vars=[static],
+                     generator_params=dict(n_filters=4, n_blocks=1),
+                     discriminator_params=dict(n_filters=4, n_res_blocks=1), verbose=False, seed=2, time_window=2,
+                     save_loss_history=False, save_path=str(tmp_path))
+    tr.run()
+    assert len(tr.gentotal) == 2 and all(np.isfinite(v) for v in tr.gentotal + tr.disc)
+    assert np.isfinite(tr.test_loss) and tr.generator.name == 'recresnet_rc'
+
+
 def test_cgan_trainer_runs(cuda, tmp_path):
     hr = _data(12, 32, 5)
     static = np.random.default_rng(6).standard_normal((32, 32)).astype(np.float32)
@@ -272,3 +324,82 @@ def test_resume_from_checkpoint_continues_the_adam_trajectory(cuda, tmp_path):
     Predictor(tr2, hr[:8], scale=4, array_in_hr=True, batch_size=8).run()
     assert tr2.model.arena is arena
     tr2.train_on_batch([lr[:8]], hr[:8])
+
+
+_DDG_CASES = [
+    # upsampling, scale, patch, time_window, interpolation, C, predictors ('hr' | 'lr' | None), static, exact
+    ('pin', 4, None, None, 'inter_area', 1, None, True, True),          # BASELINE config 5's data path
+    ('pin', 4, 24, None, 'inter_area', 2, 'hr', True, True),
+    ('pin', 4, None, None, 'bicubic', 1, 'lr', False, False),
+    ('pin', 2, 16, None, 'bilinear', 2, None, True, False),
+    ('pin', 4, None, 3, 'inter_area', 1, None, True, True),             # recnet_pin
+    ('pin', 4, None, 3, 'bicubic', 2, 'hr', False, False),
+    ('rc', 4, None, 3, 'inter_area', 1, None, True, True),              # BASELINE config 4's data path
+    ('spc', 4, 16, 2, 'inter_area', 2, None, False, True),
+    ('spc', 4, None, 3, 'inter_area', 1, 'hr', True, True),
+    ('spc', 4, None, None, 'bilinear', 2, 'hr', True, False),
+    ('spc', 4, 16, None, 'bicubic', 1, None, False, False),
+    ('spc', 5, None, None, 'inter_area', 1, None, False, False),        # 48/5, 64/5: cv2's non-integer area path
+    ('dc', 2, None, None, 'lanczos', 1, 'lr', False, False),
+    ('spc', 4, None, None, 'nearest', 1, None, True, True),
+]
+
+
+@pytest.mark.parametrize('case', _DDG_CASES, ids=lambda c: '-'.join(str(v) for v in c))
+def test_device_data_generator_pin_time_window_interpolations(cuda, case):
+    """DeviceDataGenerator for `pin` pairs, `time_window` windows and every interpolation (SURVEY 8f row 1,
+    dataloader.py:108-222, utils.py:341-401) against the host DataGenerator (bit-exact vs the reference's own
+    outputs, tests/test_datapath.py) under the same numpy RNG state.  `exact`: bit-for-bit (block means, pure
+    gathers / replication); otherwise the same cv2 coefficients in another summation order: 2e-6 of max|x|."""
+    from dl4ds_b200.dataloader import DataGenerator, DeviceDataGenerator
+    ups, scale, patch, tw, interp, C, pred, static, exact = case
+    rng = np.random.default_rng(5)
+    n, H, W = 14, 48, 64
+    hr = rng.standard_normal((n, H, W, C)).astype(np.float32)
+    preds = None
+    if pred == 'hr':
+        preds = [rng.standard_normal((n, H, W, 1)).astype(np.float32) for _ in range(2)]
+    elif pred == 'lr':
+        preds = [rng.standard_normal((n, int(H / scale), int(W / scale), 1)).astype(np.float32) for _ in range(2)]
+    st = [rng.standard_normal((H, W)).astype(np.float32)] if static else None
+    kw = dict(backbone='resnet', upsampling=ups, scale=scale, batch_size=4, patch_size=patch, time_window=tw,
+              static_vars=st, predictors=preds, interpolation=interp)
+    assert DeviceDataGenerator.supported(hr, None, ups, scale, patch, tw, st, preds, interp)
+    np.random.seed(11)
+    host = DataGenerator(hr, None, **kw)
+    hb = [host[i] for i in range(len(host))]
+    np.random.seed(11)
+    dev = DeviceDataGenerator(hr, None, device=cuda, **kw)
+    assert len(dev) == len(host) and len(dev) >= 2
+    for i in range(len(dev)):
+        din, (hr_d,) = dev[i]
+        hin, (hr_h,) = hb[i]
+        np.testing.assert_array_equal(hr_d, hr_h)
+        assert len(din) == len(hin)
+        for a, b in zip(din, hin):
+            b = np.asarray(b, np.float32).reshape(a.shape)      # App. B #2: a single-channel 5-D LR batch lost its axis
+            if exact:
+                np.testing.assert_array_equal(a, b)
+            else:
+                assert np.abs(a - b).max() <= 2e-6 * np.abs(b).max(), np.abs(a - b).max()
+
+
+def test_device_data_generator_trains_cfg4_cfg5_shapes(cuda):
+    """SupervisedTrainer(data_on_device=True) for a recurrent post-upsampling model (time_window) and a U-Net `pin`
+    model: same loss history as the host generator under the same numpy RNG state."""
+    hr = _data(22, 32, 5)
+    static = np.random.default_rng(6).standard_normal((32, 32)).astype(np.float32)
+    for backbone, ups, tw, extra in (('resnet', 'rc', 3, dict(n_filters=4, n_blocks=1)),
+                                     ('unet', 'pin', None, dict(n_filters=4, n_blocks=2, n_channels_out=1))):
+        hist = []
+        for on_dev in (False, True):
+            np.random.seed(3)
+            tr = SupervisedTrainer(backbone, ups, hr[:14], hr[14:18], hr[18:], scale=4, batch_size=4, epochs=2,
+                                   time_window=tw, static_vars=[static], verbose=False, show_plot=False, seed=4,
+                                   data_on_device=on_dev, math='fp32', **extra)
+            tr.run()
+            from dl4ds_b200.dataloader import DeviceDataGenerator
+            assert isinstance(tr.ds_train, DeviceDataGenerator) == on_dev
+            hist.append(tr.fithist.history['loss'])
+        np.testing.assert_allclose(hist[0], hist[1], rtol=2e-5)
+

@@ -242,6 +242,31 @@ def test_discriminator(cuda, ups, scale):
     compare(fn, ofn, shapes, cuda, tol=5e-5, gtol=1e-3)
 
 
+@pytest.mark.parametrize('ups,scale,math', [('pin', 4, 'fp32'), ('spc', 4, 'fp32'), ('pin', 4, 'tf32x3')])
+def test_discriminator_spatiotemporal(cuda, ups, scale, math):
+    """Spatio-temporal residual_discriminator (discriminator.py:25-33,42-47,73-74): RecurrentConvBlock('ln') stem on
+    the LR branch, per-frame Conv2D / ResidualBlocks, GlobalAveragePooling3D, against the oracle's 5-D statement."""
+    T, Bz = 3, 2
+    lr = (16, 16) if ups == 'pin' else (8, 8)
+    m = nets.residual_discriminator(2, ups, True, scale, lr, n_res_blocks=1, time_window=T)
+    nfeat = m.spec['dense1/kernel'][0]
+    mask = (np.random.default_rng(5).random((Bz, 1, 1, nfeat)) > 0.4).astype(np.float32) / 0.6
+
+    def fn(c, xs):
+        mk = c.input((Bz, 1, 1, nfeat)) if isinstance(c, SpecCtx) else c.input(torch.as_tensor(mask).cuda())
+        return m.fn(c, [xs[0], xs[1], mk])
+
+    def five(x):
+        return x.reshape(T, Bz, *x.shape[1:]).permute(1, 0, 2, 3, 4)          # time-major frames -> (B,T,H,W,C)
+
+    def ofn(p, xs):
+        y = R.residual_discriminator(p, [five(xs[0]), five(xs[1])], ups, scale, lr, n_res_blocks=1,
+                                     dropout_mask=torch.as_tensor(mask.reshape(Bz, nfeat)), is_spatiotemporal=True)
+        return y.reshape(Bz, 1, 1, 1)
+    shapes = [(T * Bz,) + tuple(s[1:]) for s in m.input_shapes]
+    compare(fn, ofn, shapes, cuda, math=math, tol=5e-5, gtol=3e-3)
+
+
 # ------------------------------------------------------------------------------------------ tcgen05
 TC_TOL = {'tf32x3': dict(tol=2e-5, gtol=2e-4), 'tf32': dict(tol=5e-3, gtol=2e-2)}
 
