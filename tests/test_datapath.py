@@ -91,11 +91,21 @@ def test_argument_checks():
         utils.resize_array(np.zeros((4, 4), np.float32), (2, 2), 'cubic')
 
 
-def test_device_data_generator_rejects_out_of_domain():
+def test_device_data_generator_domain():
+    """What the device-resident data path takes over and what stays with the host generator."""
     from dl4ds_b200.dataloader import DeviceDataGenerator
     a = np.zeros((4, 30, 30, 1), np.float32)
-    assert not DeviceDataGenerator.supported(a, None, 'spc', 4, None, None, None, None, 'inter_area')   # 30 % 4
-    assert not DeviceDataGenerator.supported(a, a, 'spc', 2, None, None, None, None, 'inter_area')      # explicit LR
-    assert not DeviceDataGenerator.supported(a, None, 'pin', 2, None, None, None, None, 'inter_area')
-    assert not DeviceDataGenerator.supported(a, None, 'spc', 2, None, None, None, None, 'bicubic')
-    assert DeviceDataGenerator.supported(a, None, 'spc', 2, None, None, None, None, 'inter_area')
+    p_hr = [np.zeros((4, 30, 30, 1), np.float32)]
+    ok = DeviceDataGenerator.supported
+    assert not ok(a, a, 'spc', 2, None, None, None, None, 'inter_area')         # explicit LR arrays
+    assert not ok(a, None, 'spc', 2, 16, None, None, p_hr, 'inter_area')        # post-upsampling patches + predictors (App. B #3)
+    assert not ok(a, None, 'spc', 4, 18, None, None, None, 'inter_area')        # patch not divisible by the scale
+    assert not ok(a, None, 'spc', 2, 30, None, None, None, 'inter_area')        # crop_array needs patch < grid
+    assert not ok(a, None, 'pin', 2, 16, 3, None, None, 'inter_area')           # the reference's own (T,y) crop of squeezed 1-channel windows
+    assert not ok(a, None, 'spc', 2, None, None, [np.zeros((31, 30))], None, 'inter_area')
+    assert not ok(a, None, 'spc', 2, None, None, None, None, 'spline')
+    assert ok(a, None, 'spc', 4, None, None, None, None, 'inter_area')          # 30 / 4: cv2's non-integer area path (tap tables)
+    assert ok(a, None, 'pin', 2, None, None, None, None, 'inter_area')
+    assert ok(a, None, 'spc', 2, None, None, None, None, 'bicubic')
+    assert ok(a, None, 'rc', 2, None, 3, None, p_hr, 'inter_area')
+    assert ok(a, None, 'spc', 2, None, None, None, None, 'inter_area')
