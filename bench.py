@@ -614,7 +614,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--math', default=os.environ.get('DL4DS_MATH', 'auto'),
-                    choices=['auto', 'fp32', 'tf32x3', 'tf32'])
+                    choices=['auto', 'fp32', 'tf32x3', 'tf32', 'f16x3'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline sample')
     ap.add_argument('--configs', default='cfg3,cfg4,cfg5',
                     help="BASELINE configs measured after the headline ('' = none)")

@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libdl4ds_b200.so')
 
 ACT = {None: 0, 'linear': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
 MATH_FP32, MATH_TF32X3, MATH_TF32 = 0, 1, 2
-MATH = {'fp32': MATH_FP32, 'tf32x3': MATH_TF32X3, 'tf32': MATH_TF32}
+MATH_F16X3 = 3
+MATH = {'fp32': MATH_FP32, 'tf32x3': MATH_TF32X3, 'tf32': MATH_TF32, 'f16x3': MATH_F16X3}
 W_HWIO, W_FLIP_T, W_PREPACKED = 0, 1, 4
 
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
@@ -99,6 +100,9 @@ class Dl4dsError(RuntimeError):
     pass
 
 
+_TRACE = os.environ.get("DL4DS_TRACE", "0") == "1"
+
+
 def load():
     """Load the shared library (once) and declare every prototype."""
     global _lib
@@ -126,4 +130,11 @@ def call(name, *args):
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise Dl4dsError('%s failed (%d): %s' % (name, rc, last_error()))
+    if _TRACE:          # DL4DS_TRACE=1: name every launch and wait for it (locating a kernel that never returns)
+        import sys
+        import torch
+        print('[dl4ds] %s %s' % (name, ' '.join(str(a) for a in args if isinstance(a, (int, float)) and abs(a) < 1 << 20)),
+              file=sys.stderr, flush=True)
+        if not torch.cuda.is_current_stream_capturing():
+            torch.cuda.synchronize()
     return rc

@@ -105,7 +105,8 @@ int dl4ds_conv2d_dgrad_fused_supported(int N, int H, int W, int Cq, int Cp, int 
     ConvArgs a = {};
     a.N = N; a.H = H; a.W = W; a.Cin = Cq; a.Ho = H; a.Wo = W; a.Cout = Cp;
     a.KH = KH; a.KW = KW; a.stride = 1; a.up = 1; a.d2s_r = 1;
-    return conv2d_fwd_halo_supported(a, math_mode) ? 1 : 0;
+    return (conv2d_fwd_halo_supported(a, math_mode) ||
+            (math_mode == DL4DS_MATH_F16X3 && conv2d_fwd_halo_supported(a, DL4DS_MATH_TF32X3))) ? 1 : 0;
 }
 
 int dl4ds_conv2d_dgrad_fused(const float* dq, int dq_ld, const float* w, float* dz, int dz_ld,
@@ -151,8 +152,8 @@ int64_t dl4ds_conv2d_fwd_workspace_bytes(int N, int H, int W, int Cin, int Ho, i
 int dl4ds_conv2d_pack(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode,
                       void* ws, void* stream) {
     DL4DS_REQUIRE(w && ws, DL4DS_E_BADARG, "conv2d_pack: null pointer");
-    DL4DS_REQUIRE(math_mode == DL4DS_MATH_TF32 || math_mode == DL4DS_MATH_TF32X3, DL4DS_E_BADARG,
-                  "conv2d_pack: math_mode must be a tensor-core mode");
+    DL4DS_REQUIRE(math_mode == DL4DS_MATH_TF32 || math_mode == DL4DS_MATH_TF32X3 || math_mode == DL4DS_MATH_F16X3,
+                  DL4DS_E_BADARG, "conv2d_pack: math_mode must be a tensor-core mode");
     DL4DS_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, DL4DS_E_SHAPE, "conv2d_pack: channels must be multiples of 8");
     return conv2d_pack_tc(w, wmode & ~DL4DS_W_PREPACKED, KH, KW, Cin, Cout, math_mode, ws,
                           reinterpret_cast<cudaStream_t>(stream));
@@ -160,7 +161,8 @@ int dl4ds_conv2d_pack(const float* w, int wmode, int KH, int KW, int Cin, int Co
 
 int64_t dl4ds_conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode,
                                void* ws, void* desc_out_host) {
-    if (!w || !ws || !desc_out_host || (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3) || Cin % 8 ||
+    if (!w || !ws || !desc_out_host ||
+        (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3 && math_mode != DL4DS_MATH_F16X3) || Cin % 8 ||
         Cout % 8) {
         set_error("conv2d_pack_desc: bad argument");
         return DL4DS_E_BADARG;
@@ -191,6 +193,7 @@ int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float
     a.P = P; a.Q = Q; a.dw = dw; a.p_ld = p_ld; a.q_ld = q_ld;
     a.N = N; a.Hp = Hp; a.Wp = Wp; a.Ca = Ca; a.Hq = Hq; a.Wq = Wq; a.Cb = Cb;
     a.KH = KH; a.KW = KW; a.stride = stride; a.pad_t = pad_t; a.pad_l = pad_l;
+    if (math_mode == DL4DS_MATH_F16X3) math_mode = DL4DS_MATH_TF32X3;       // weight gradients: the 3xTF32 kernels
     a.Mw = KH * KW * Ca;
     a.NQ = (int64_t)N * Hq * Wq;
     a.chunks_per_split = 0;

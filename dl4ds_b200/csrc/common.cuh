@@ -59,7 +59,8 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
 int64_t conv2d_fwd_tc_workspace(const ConvArgs& a, int math_mode);
 // conv_tc_halo.cu: one halo tile per channel chunk, taps through shifted descriptors (tried first by conv2d_fwd_tc)
 bool conv2d_fwd_halo_supported(const ConvArgs& a, int math_mode);
-int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, const float* wp_lo, cudaStream_t st);
+int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, const float* wp_lo, const float* w_scale,
+                       cudaStream_t st);
 int conv2d_pack_tc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws,
                    cudaStream_t st);
 int64_t conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws, void* desc_out);

@@ -26,6 +26,8 @@
 #include <mutex>
 #include <tuple>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace dl4ds {
@@ -136,6 +138,85 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// 3-term fp16 mode (DL4DS_MATH_F16X3): the weight image [tap][chunk][Npad][KC16] as fp16 hi / lo halves of w * s_w,
+// s_w = the power of two that brings max |w| of the layer into [2^13, 2^14) (fp16 keeps 11 significant bits like tf32
+// but a 5-bit exponent).  The scale pair {s_w, 1 / s_w} sits behind the two images; the convolution's epilogue
+// multiplies the accumulator by 1 / (s_w * s_tile).  Geometry: tc::pick_chunk16.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) weight_absmax_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ scale_out) {
+    __shared__ float red[8];
+    float m = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(__ldg(w + i)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 1; j < 8; ++j) m = fmaxf(m, red[j]);
+        const float s = pow2_scale_for(m);
+        scale_out[0] = s;
+        scale_out[1] = 1.0f / s;
+    }
+}
+
+// one 16-byte unit (8 halfs) of the hi and lo fp16 images; li = unit index inside the layer's fp16 image
+__device__ __forceinline__ void pack_f16_unit(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo,
+                                              const float* __restrict__ scale, int64_t li, int taps, int Cin, int Cout,
+                                              int Npad, int kc16, int nchunks16, int wmode) {
+    const int upr = kc16 / 8;
+    const int u = (int)(li % upr);
+    const int nn = (int)((li / upr) % Npad);
+    const int blk = (int)(li / ((int64_t)upr * Npad));
+    const int tap = blk / nchunks16, ch = blk - tap * nchunks16;
+    const float s = __ldg(scale);
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch * kc16 + u * 8 + j;
+        float x = 0.0f;
+        if (nn < Cout && c < Cin) {
+            if (wmode == DL4DS_W_HWIO)
+                x = __ldg(w + ((int64_t)tap * Cin + c) * Cout + nn);
+            else
+                x = __ldg(w + ((int64_t)(taps - 1 - tap) * Cout + nn) * Cin + c);
+        }
+        x *= s;
+        h[j] = __float2half_rn(x);
+        l[j] = __float2half_rn(x - __half2float(h[j]));
+    }
+    const int us = swizzle_unit(u, nn, kc16 * 2);
+    const int64_t dst = ((int64_t)blk * Npad + nn) * kc16 + us * 8;
+    *reinterpret_cast<uint4*>(hi + dst) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + dst) = *reinterpret_cast<const uint4*>(l);
+}
+
+struct F16Image {       // where the fp16 part of a DL4DS_MATH_F16X3 workspace lives (behind the two tf32 images)
+    int kc16, nchunks16;
+    int64_t n16;        // halfs per image
+    __half* hi; __half* lo; float* scale;
+};
+__host__ __device__ inline F16Image f16_image(float* tf32_hi, int64_t n_tf32, int taps, int Cin, int Npad) {
+    F16Image f;
+    const int cp = (Cin + 15) / 16 * 16;
+    f.kc16 = (cp % 64 == 0) ? 64 : ((cp % 32 == 0) ? 32 : 16);
+    f.nchunks16 = cp / f.kc16;
+    f.n16 = (int64_t)taps * f.nchunks16 * Npad * f.kc16;
+    f.hi = reinterpret_cast<__half*>(tf32_hi + 2 * n_tf32);
+    f.lo = f.hi + f.n16;
+    f.scale = reinterpret_cast<float*>(f.lo + f.n16);
+    return f;
+}
+
+__global__ void pack_weights_f16_kernel(const float* __restrict__ w, float* __restrict__ tf32_hi, int64_t n_tf32, int taps,
+                                        int Cin, int Cout, int Npad, int wmode) {
+    const F16Image f = f16_image(tf32_hi, n_tf32, taps, Cin, Npad);
+    const int64_t total = f.n16 / 8;
+    for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li < total; li += (int64_t)gridDim.x * blockDim.x)
+        pack_f16_unit(w, f.hi, f.lo, f.scale, li, taps, Cin, Cout, Npad, f.kc16, f.nchunks16, wmode);
+}
+
 // Every (layer, pass) weight image of a model in ONE launch: a table of descriptors in device memory, a flat unit
 // index space (16-byte units of all images), each unit located by a binary search over the descriptors' first units.
 // Replaces ~40 three-microsecond pack launches per optimizer step (and the side-stream fork / join around them).
@@ -146,6 +227,27 @@ struct PackDesc {
 };
 static_assert(sizeof(PackDesc) == 64, "PackDesc is a 64-byte record (dl4ds_conv2d_pack_desc writes it, Python fills unit_begin)");
 
+// one block per descriptor of a DL4DS_MATH_F16X3 pack table (x3 == 2): the layer's weight scale
+__global__ void __launch_bounds__(256) weight_absmax_multi_kernel(const PackDesc* __restrict__ descs) {
+    __shared__ float red[8];
+    const PackDesc d = descs[blockIdx.x];
+    if (d.x3 != 2) return;
+    const int64_t n = (int64_t)d.taps * d.Cin * d.Cout;
+    float m = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(__ldg(d.w + i)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 1; j < 8; ++j) m = fmaxf(m, red[j]);
+        const F16Image f = f16_image(d.hi, (int64_t)d.taps * d.nchunks * d.Npad * d.kc, d.taps, d.Cin, d.Npad);
+        const float s = pow2_scale_for(m);
+        f.scale[0] = s;
+        f.scale[1] = 1.0f / s;
+    }
+}
+
 __global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int n, long long total_units) {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_units;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -155,7 +257,14 @@ __global__ void pack_weights_multi_kernel(const PackDesc* __restrict__ descs, in
             if (descs[mid].unit_begin <= idx) lo_i = mid; else hi_i = mid - 1;
         }
         const PackDesc d = descs[lo_i];
-        const long long li = idx - d.unit_begin;
+        long long li = idx - d.unit_begin;
+        const long long n_tf32 = (long long)d.taps * d.nchunks * d.Npad * d.kc;
+        if (li >= n_tf32 / 4) {          // x3 == 2: the fp16 images follow the two tf32 ones
+            const F16Image f = f16_image(d.hi, n_tf32, d.taps, d.Cin, d.Npad);
+            pack_f16_unit(d.w, f.hi, f.lo, f.scale, li - n_tf32 / 4, d.taps, d.Cin, d.Cout, d.Npad, f.kc16, f.nchunks16,
+                          d.wmode);
+            continue;
+        }
         const int upr = d.kc / 4;
         const int u = (int)(li % upr);
         const int nn = (int)((li / upr) % d.Npad);
@@ -627,8 +736,12 @@ static int64_t pack_floats(int taps, int Cin, int Cout) {
 }
 
 int64_t conv2d_fwd_tc_workspace(const ConvArgs& a, int math_mode) {
-    if (!fwd_shape_supported(a, math_mode)) return 0;
+    if (!fwd_shape_supported(a, math_mode == DL4DS_MATH_F16X3 ? DL4DS_MATH_TF32X3 : math_mode)) return 0;
     const int64_t n = pack_floats(a.KH * a.KW, a.Cin, a.Cout);
+    if (math_mode == DL4DS_MATH_F16X3) {
+        const F16Image f = f16_image(nullptr, n, a.KH * a.KW, a.Cin, (a.Cout + 15) / 16 * 16);
+        return n * 4 * 2 + f.n16 * 2 * 2 + 128;
+    }
     return n * 4 * (math_mode == DL4DS_MATH_TF32X3 ? 2 : 1);
 }
 
@@ -643,9 +756,18 @@ int conv2d_pack_tc(const float* w, int wmode, int KH, int KW, int Cin, int Cout,
     const int64_t units = n / 4;
     const int blocks = (int)((units + 255) / 256 > 1184 ? 1184 : (units + 255) / 256);
     pack_weights_kernel<<<blocks, 256, 0, st>>>(w, hi, lo, KH * KW, Cin, Cout, npad, c.kc, nchunks, wmode,
-                                                math_mode == DL4DS_MATH_TF32X3 ? 1 : 0);
+                                                math_mode != DL4DS_MATH_TF32 ? 1 : 0);
+    if (math_mode == DL4DS_MATH_F16X3) {
+        const F16Image f = f16_image(hi, n, KH * KW, Cin, npad);
+        weight_absmax_kernel<<<1, 256, 0, st>>>(w, (int64_t)KH * KW * Cin * Cout, f.scale);
+        const int64_t u16 = f.n16 / 8;
+        const int b16 = (int)((u16 + 255) / 256 > 1184 ? 1184 : (u16 + 255) / 256);
+        pack_weights_f16_kernel<<<b16, 256, 0, st>>>(w, hi, n, KH * KW, Cin, Cout, npad, wmode);
+    }
     return check_launch("pack_weights_kernel");
 }
+
+static std::atomic<bool> g_pack_has_f16{false};
 
 // fills one 64-byte PackDesc (host memory) for conv2d_pack_multi; returns its number of 16-byte units
 int64_t conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int Cout, int math_mode, void* ws, void* desc_out) {
@@ -657,12 +779,16 @@ int64_t conv2d_pack_desc(const float* w, int wmode, int KH, int KW, int Cin, int
     d.kc = c.kc;
     d.nchunks = (Cin + c.kc - 1) / c.kc;
     d.wmode = wmode;
-    d.x3 = math_mode == DL4DS_MATH_TF32X3 ? 1 : 0;
+    d.x3 = math_mode == DL4DS_MATH_F16X3 ? 2 : (math_mode == DL4DS_MATH_TF32X3 ? 1 : 0);
     const int64_t n = pack_floats(d.taps, Cin, Cout);
     d.hi = reinterpret_cast<float*>(ws);
     d.lo = d.hi + n;
     d.unit_begin = 0;
     memcpy(desc_out, &d, sizeof(d));
+    if (d.x3 == 2) {
+        g_pack_has_f16.store(true, std::memory_order_relaxed);
+        return n / 4 + f16_image(d.hi, n, d.taps, Cin, d.Npad).n16 / 8;
+    }
     return n / 4;
 }
 
@@ -670,11 +796,17 @@ int conv2d_pack_multi(const void* descs_dev, int n, int64_t total_units, cudaStr
     if (n <= 0 || total_units <= 0) return DL4DS_OK;
     int64_t blocks = (total_units + 255) / 256;
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    // the weight scales of the fp16 images (DL4DS_MATH_F16X3) first; skipped while no such descriptor was ever built
+    if (g_pack_has_f16.load(std::memory_order_relaxed))
+        weight_absmax_multi_kernel<<<n, 256, 0, st>>>(reinterpret_cast<const PackDesc*>(descs_dev));
     pack_weights_multi_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const PackDesc*>(descs_dev), n, total_units);
     return check_launch("pack_weights_multi_kernel");
 }
 
-int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cudaStream_t st) {
+int conv2d_fwd_tc(const ConvArgs& a, int math_mode_in, void* ws, int prepacked, cudaStream_t st) {
+    // DL4DS_MATH_F16X3: the halo-tile kernel runs on fp16 operands; every other kernel of this file as TF32X3
+    const bool f16 = math_mode_in == DL4DS_MATH_F16X3;
+    const int math_mode = f16 ? DL4DS_MATH_TF32X3 : math_mode_in;
     if (!fwd_supported(a, math_mode)) return DL4DS_E_UNSUPPORTED;
     DL4DS_REQUIRE(ws != nullptr, DL4DS_E_BADARG,
                   "conv2d_fwd: tensor-core math needs the packed-weight workspace "
@@ -682,7 +814,7 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     DL4DS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 127) == 0, DL4DS_E_BADARG, "conv2d_fwd: ws must be 128-byte aligned");
     const bool x3 = math_mode == DL4DS_MATH_TF32X3;
     if (!prepacked) {
-        int rc = conv2d_pack_tc(a.w, a.wmode, a.KH, a.KW, a.Cin, a.Cout, math_mode, ws, st);
+        int rc = conv2d_pack_tc(a.w, a.wmode, a.KH, a.KW, a.Cin, a.Cout, math_mode_in, ws, st);
         if (rc) return rc;
     }
     const Chunk c = pick_chunk(a.Cin);
@@ -693,7 +825,13 @@ int conv2d_fwd_tc(const ConvArgs& a, int math_mode, void* ws, int prepacked, cud
     p.wp_hi = reinterpret_cast<const float*>(ws);
     p.wp_lo = p.wp_hi + n;
     {   // halo-tile kernel (conv_tc_halo.cu) first; the per-tap kernel below keeps the shapes outside its domain
-        const int rc = conv2d_fwd_tc_halo(a, math_mode, p.wp_hi, p.wp_lo, st);
+        if (f16) {
+            const F16Image fi = f16_image(reinterpret_cast<float*>(ws), n, a.KH * a.KW, a.Cin, p.Npad);
+            const int rc16 = conv2d_fwd_tc_halo(a, DL4DS_MATH_F16X3, reinterpret_cast<const float*>(fi.hi),
+                                                reinterpret_cast<const float*>(fi.lo), fi.scale, st);
+            if (rc16 != DL4DS_E_UNSUPPORTED) return rc16;
+        }
+        const int rc = conv2d_fwd_tc_halo(a, math_mode, p.wp_hi, p.wp_lo, nullptr, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
         int bw_, bh_;
         if (!tile_geometry(a.H, a.W, 128, &bw_, &bh_)) return DL4DS_E_UNSUPPORTED;

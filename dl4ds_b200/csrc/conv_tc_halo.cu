@@ -25,6 +25,8 @@
 
 #include <atomic>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace dl4ds {
@@ -61,6 +63,8 @@ struct HaloParams {
     const float* mask_y; int mask_ld, mask_act; float* dbias;
     const float* x;          // LDG producer mode: activations (NHWC, pitch x_ld)
     int x_ld, ldg, upp_shift;
+    const float* w_scale;    // 3-term fp16 mode: {s_w, 1 / s_w} of the packed weight image (device memory)
+    int f16_regs;            // ... units (8 channels of one halo pixel) per producer thread when a tile fits in registers, else 0
     long long* stamps;       // optional clock64 stamps of CTA 0 (dl4ds_debug_set_buffer): [item < 64][16]
     int dbg;                 // timing experiments (DL4DS_HALO_DBG): 1 no MMAs, 2 no splitter work, 4 no epilogue stores, 8 no weight copies
 };
@@ -80,6 +84,26 @@ __device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t desc_a, 
         : "memory");
 }
 
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_x(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    if (F16) umma_f16(tmem_d, desc_a, desc_b, idesc, acc);
+    else umma_tf32(tmem_d, desc_a, desc_b, idesc, acc);
+}
+template <bool F16>
+__device__ __forceinline__ void umma_x_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    if (F16) umma_f16_acc(tmem_d, desc_a, desc_b, idesc);
+    else umma_tf32_acc(tmem_d, desc_a, desc_b, idesc);
+}
+
 #define HSTAMP(it, id)                                                                         \
     do {                                                                                       \
         if (p.stamps != nullptr && blockIdx.x == 0 && (it) < 64 && lane == 0)                  \
@@ -97,7 +121,11 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-template <bool X3, bool STACKN, int KSTEPS>
+// F16 (DL4DS_MATH_F16X3): fp16 operands (K = 16 per MMA: half the instructions and half the operand bytes of 3xTF32).
+// The A producers take whole tiles: pass 1 reads the tile's halo box for its absolute maximum, which fixes a power-of-two
+// scale s_tile (max -> [2^13, 2^14)); pass 2 re-reads it chunk by chunk (L2) and writes hi = fp16(v s), lo = fp16(v s - hi).
+// The epilogue multiplies the accumulator by 1 / (s_tile s_w).  Error per operand element <= 2^-22 |v| + 2^-38 max|tile|.
+template <bool X3, bool STACKN, int KSTEPS, bool F16>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -112,16 +140,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     __shared__ __align__(16) float bias_s[256];
     __shared__ float colsum_s[256];      // fused bias gradient: column sums of this CTA's output rows
     __shared__ int2 pix_tab[512];        // LDG mode, per halo pixel: {float offset from the tile origin, hy << 16 | hx}
+    __shared__ float tile_inv_s[16];     // F16: 1 / s_tile of the tiles in flight (slot = tile count & 15)
+    __shared__ float amax_red[2][2][4];  // F16: [producer group][parity][warp] partial maxima
+    __shared__ int a_uses[kHaloMaxStages];   // F16: uses of each A stage whose producer has passed its a_empty wait
 
     // warp index through a shuffle: tells ptxas the value is warp-uniform, so the role branches below are uniform branches
     // and the single-thread roles keep their addresses / descriptors in uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    if (p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.stamps[12] = clock64();      // kernel entry
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
         colsum_s[i] = 0.0f;
     }
+    if (threadIdx.x < kHaloMaxStages) a_uses[threadIdx.x] = 0;
     if (p.ldg)
         for (int i = threadIdx.x; i < p.HWp * p.HHp; i += blockDim.x) {
             const int hy = i / p.HWp, hx = i - hy * p.HWp;
@@ -150,6 +183,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
+    if (p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.stamps[13] = clock64();      // prologue done
 
     if (warp == 0) {
         // ===================== halo-tile producer (TMA mode) =====================
@@ -176,7 +210,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
         const bool leader = elect_one();
         int s = 0;
         uint32_t ph = 0;
-        const uint32_t tile_floats = (uint32_t)(p.Npad * p.kc);
+        const uint8_t* const w_hi = reinterpret_cast<const uint8_t*>(p.wp_hi);
+        const uint8_t* const w_lo = reinterpret_cast<const uint8_t*>(p.wp_lo);
         if (p.w_resident) {
             // every (chunk, tap) weight tile once: the ring round trip (bulk-copy latency + tcgen05.commit latency, ~1 us
             // each, 3 stages in flight) was what bounded the streaming version at ~5 us per tile
@@ -186,10 +221,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                     const uint32_t full = smem_u32(&b_full[c]);
                     mbar_arrive_expect_tx(full, (uint32_t)(p.ntaps * p.b_tap_bytes));
                     for (int t = 0; t < p.ntaps; ++t) {
-                        const uint32_t woff = (uint32_t)(t * p.nchunks + c) * tile_floats;
+                        const size_t woff = (size_t)(t * p.nchunks + c) * (size_t)p.b_bytes;
                         const uint32_t sb = smem_base + (uint32_t)(p.b_base + (c * p.ntaps + t) * p.b_tap_bytes);
-                        bulk_load(sb, p.wp_hi + woff, (uint32_t)p.b_bytes, full);
-                        if (X3) bulk_load(sb + (uint32_t)p.b_bytes, p.wp_lo + woff, (uint32_t)p.b_bytes, full);
+                        bulk_load(sb, w_hi + woff, (uint32_t)p.b_bytes, full);
+                        if (X3) bulk_load(sb + (uint32_t)p.b_bytes, w_lo + woff, (uint32_t)p.b_bytes, full);
                     }
                 }
             }
@@ -207,10 +242,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                         if (!(p.dbg & 8)) {
                             for (int j = 0; j < n; ++j) {
                                 // packed images are [tap][chunk][Npad][kc]
-                                const uint32_t woff = (uint32_t)((t0 + j) * p.nchunks + c) * tile_floats;
-                                bulk_load(sb + (uint32_t)(j * p.b_tap_bytes), p.wp_hi + woff, (uint32_t)p.b_bytes, full);
+                                const size_t woff = (size_t)((t0 + j) * p.nchunks + c) * (size_t)p.b_bytes;
+                                bulk_load(sb + (uint32_t)(j * p.b_tap_bytes), w_hi + woff, (uint32_t)p.b_bytes, full);
                                 if (X3)
-                                    bulk_load(sb + (uint32_t)(j * p.b_tap_bytes + p.b_bytes), p.wp_lo + woff, (uint32_t)p.b_bytes, full);
+                                    bulk_load(sb + (uint32_t)(j * p.b_tap_bytes + p.b_bytes), w_lo + woff, (uint32_t)p.b_bytes, full);
                             }
                         }
                     }
@@ -226,8 +261,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
         // there is ONE guarded straight-line block of 2 * KSTEPS MMAs whose descriptors differ from two running 64-bit
         // values (da_tap, db_tap) by compile-time constants, and the tap walk itself is incremental (no multiplies).
         const bool leader = elect_one();
-        const uint32_t idesc = make_idesc_tf32(128, p.Npad, 0, 0);
-        const uint32_t idesc2 = make_idesc_tf32(128, 2 * p.Npad, 0, 0);
+        const uint32_t idesc = F16 ? make_idesc_f16(128, p.Npad) : make_idesc_tf32(128, p.Npad, 0, 0);
+        const uint32_t idesc2 = F16 ? make_idesc_f16(128, 2 * p.Npad) : make_idesc_tf32(128, 2 * p.Npad, 0, 0);
         const uint64_t tmpl_a = make_smem_desc(0, 16, (uint32_t)(p.HWp * p.span), p.layout);
         const uint64_t tmpl_b = make_smem_desc(0, 16, 8u * (uint32_t)p.span, p.layout);
         const uint64_t a_step = (uint64_t)(p.span >> 4);                                       // next tap in the kernel row
@@ -270,28 +305,28 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                         if (leader && !skip) {
                             if (X3 && STACKN) {
                                 // A_hi x [W_hi ; W_lo] -> columns [0, 2 Npad); A_lo x W_hi -> columns [0, Npad)
-                                umma_tf32(td, da_tap, db_tap, idesc2, accumulate);
-                                umma_tf32_acc(td, da_tap + lo16, db_tap, idesc);
+                                umma_x<F16>(td, da_tap, db_tap, idesc2, accumulate);
+                                umma_x_acc<F16>(td, da_tap + lo16, db_tap, idesc);
 #pragma unroll
                                 for (int k = 1; k < KSTEPS; ++k) {
-                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc2);
-                                    umma_tf32_acc(td, da_tap + lo16 + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
+                                    umma_x_acc<F16>(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc2);
+                                    umma_x_acc<F16>(td, da_tap + lo16 + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
                                 }
                             } else if (X3) {
-                                umma_tf32(td, da_tap + lo16, db_tap, idesc, accumulate);
-                                umma_tf32_acc(td, da_tap, db_tap + blo16, idesc);
-                                umma_tf32_acc(td, da_tap, db_tap, idesc);
+                                umma_x<F16>(td, da_tap + lo16, db_tap, idesc, accumulate);
+                                umma_x_acc<F16>(td, da_tap, db_tap + blo16, idesc);
+                                umma_x_acc<F16>(td, da_tap, db_tap, idesc);
 #pragma unroll
                                 for (int k = 1; k < KSTEPS; ++k) {
-                                    umma_tf32_acc(td, da_tap + lo16 + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
-                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + blo16 + (uint64_t)(2 * k), idesc);
-                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
+                                    umma_x_acc<F16>(td, da_tap + lo16 + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
+                                    umma_x_acc<F16>(td, da_tap + (uint64_t)(2 * k), db_tap + blo16 + (uint64_t)(2 * k), idesc);
+                                    umma_x_acc<F16>(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
                                 }
                             } else {
-                                umma_tf32(td, da_tap, db_tap, idesc, accumulate);
+                                umma_x<F16>(td, da_tap, db_tap, idesc, accumulate);
 #pragma unroll
                                 for (int k = 1; k < KSTEPS; ++k)
-                                    umma_tf32_acc(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
+                                    umma_x_acc<F16>(td, da_tap + (uint64_t)(2 * k), db_tap + (uint64_t)(2 * k), idesc);
                             }
                         }
                         accumulate = 1u;
@@ -341,6 +376,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             tc_fence_after();
             if (warp == 2) HSTAMP(tcount * p.nchunks, 10);
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.acc_stride);
+            float unscale = 1.0f;
+            if (F16) unscale = tile_inv_s[tcount & 15] * __ldg(p.w_scale + 1);
             int blk = 0;
             for (int c0 = half * 16; c0 < p.Npad; c0 += 32, ++blk) {
                 float v[16];
@@ -350,6 +387,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
                     tmem_ld16(taddr + (uint32_t)(p.Npad + c0), v2);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                }
+                if (F16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= unscale;
                 }
                 if (c0 >= p.Cout || (p.dbg & 4)) continue;
                 if (mask_y != nullptr || p.dbias != nullptr) {
@@ -472,6 +513,254 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             const int et = threadIdx.x - 64;            // 0..255 over the eight epilogue warps
             if (et < p.Cout) atomicAdd(p.dbias + et, colsum_s[et]);
         }
+    } else if (F16) {
+        // ===================== A producers, fp16 mode (warps 10-17: two groups of four warps, alternate TILES) =====
+        const int pt = threadIdx.x - 320, grp = pt >> 7, gt = pt & 127, gw = gt >> 5;
+        const int upt = p.Cin >> 3;                       // 8-channel units per pixel that exist in memory
+        const int upc = p.kc >> 3;                        // 16-byte fp16 units per pixel and chunk
+        const int npix = p.HWp * p.HHp;
+        const int units_tile = npix * upt, units_item = npix * upc;
+        uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+        int tcount = 0;
+        constexpr int kRegUnits = 9;
+        // unit u = gt + 128 j of a tile is (pixel u / upt, 8-channel group u % upt): walked incrementally (integer
+        // divisions by run-time values are ~50-instruction dependent chains; with two producer warps per scheduler
+        // they -- not the loads -- set the pace: measured 1000 clk per unit before, profiles/r02s_stamps.log)
+        const int pix_first = gt / upt, cg_first = gt - pix_first * upt;
+        const int pix_step = 128 / upt, cg_step = 128 - pix_step * upt;
+        const int upc_shift = p.kc == 64 ? 3 : (p.kc == 32 ? 2 : 1);
+        const int sw_shift = p.span == 128 ? 0 : (p.span == 64 ? 1 : 2), sw_mask = p.span == 128 ? 7 : (p.span == 64 ? 3 : 1);
+        // (stage, use) of the first item of this group's current tile, advanced by two tiles per iteration
+        int st_tile = (grp * p.nchunks) % p.a_stages, use_tile = (grp * p.nchunks) / p.a_stages;
+        for (int tile = blockIdx.x; tile < (p.f16_regs ? p.ntiles : 0); tile += gridDim.x, ++tcount) {
+            // ---- register-resident variant (halo box <= 9 units per thread): ONE read of the tile.  All loads of the
+            // tile are in flight at once, the maximum comes from the registers, then every chunk's stage is acquired
+            // and the scaled hi / lo halves are written.
+            if ((tcount & 1) != grp) continue;
+            const int img = tile / p.tiles_per_img;
+            const int trem = tile - img * p.tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
+            const float* tbase = p.x + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld;
+            float4 a[kRegUnits][2];
+            if (gw == 0) HSTAMP(tcount * p.nchunks, 0);
+            int pix = pix_first, cu = cg_first;
+#pragma unroll
+            for (int j = 0; j < kRegUnits; ++j) {
+                const int u = gt + j * 128;
+                a[j][0] = a[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j > 0) {
+                    pix += pix_step; cu += cg_step;
+                    if (cu >= upt) { cu -= upt; ++pix; }
+                }
+                if (j < p.f16_regs && u < units_tile) {
+                    const int2 e = pix_tab[pix];
+                    const int hy = e.y >> 16, hx = e.y & 0xffff;
+                    if ((unsigned)(y0 + hy) < (unsigned)p.H && (unsigned)(x0 + hx) < (unsigned)p.W && !(p.dbg & 2)) {
+                        const float4* src = reinterpret_cast<const float4*>(tbase + e.x + cu * 8);
+                        a[j][0] = __ldg(src);
+                        a[j][1] = __ldg(src + 1);
+                    }
+                }
+            }
+            float m = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kRegUnits; ++j) {
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(a[j][0].x), fabsf(a[j][0].y)), fmaxf(fabsf(a[j][0].z), fabsf(a[j][0].w))));
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(a[j][1].x), fabsf(a[j][1].y)), fmaxf(fabsf(a[j][1].z), fabsf(a[j][1].w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const int par = (tcount >> 1) & 1;
+            if (lane == 0) amax_red[grp][par][gw] = m;
+            if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+            else asm volatile("bar.sync 3, 128;" ::: "memory");
+            m = fmaxf(fmaxf(amax_red[grp][par][0], amax_red[grp][par][1]), fmaxf(amax_red[grp][par][2], amax_red[grp][par][3]));
+            const float sc = pow2_scale_for(m);
+            if (gt == 0) tile_inv_s[tcount & 15] = 1.0f / sc;
+            if (gw == 0) HSTAMP(tcount * p.nchunks, 1);             // loads landed, maximum known
+            {
+                int st = st_tile, use = use_tile;
+                for (int c = 0; c < p.nchunks; ++c) {       // acquire the tile's stages in item order
+                    {
+                        volatile int* uses = a_uses;
+                        while (uses[st] < use) {}
+                    }
+                    mbar_wait(smem_u32(&a_empty[st]), (uint32_t)(use & 1) ^ 1u);
+                    if (gt == 0) {
+                        volatile int* uses = a_uses;
+                        uses[st] = use + 1;
+                    }
+                    if (++st == p.a_stages) { st = 0; ++use; }
+                }
+            }
+            if (gw == 0) HSTAMP(tcount * p.nchunks, 3);             // stages acquired
+            const int st0 = st_tile;
+            pix = pix_first;
+            int cg = cg_first;
+#pragma unroll
+            for (int j = 0; j < kRegUnits; ++j) {
+                // straight-line body (only the two stores are predicated), so the scheduler overlaps the units
+                if (j > 0) {
+                    pix += pix_step; cg += cg_step;
+                    const bool wrap = cg >= upt;
+                    cg -= wrap ? upt : 0;
+                    pix += wrap ? 1 : 0;
+                }
+                const bool active = j < p.f16_regs && gt + j * 128 < units_tile;
+                const int c = cg >> upc_shift, cu = cg & (upc - 1);
+                int st = st0 + c;
+                st -= st >= p.a_stages ? p.a_stages : 0;
+                const float v[8] = {a[j][0].x * sc, a[j][0].y * sc, a[j][0].z * sc, a[j][0].w * sc,
+                                    a[j][1].x * sc, a[j][1].y * sc, a[j][1].z * sc, a[j][1].w * sc};
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) {
+                    const __half2 h2 = __floats2half2_rn(v[2 * q2], v[2 * q2 + 1]);
+                    const float2 hf = __half22float2(h2);
+                    const __half2 l2 = __floats2half2_rn(v[2 * q2] - hf.x, v[2 * q2 + 1] - hf.y);
+                    hw[q2] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lw[q2] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                const uint32_t so = (uint32_t)(st * p.a_stage_bytes + pix * p.span + ((cu ^ ((pix >> sw_shift) & sw_mask)) << 4));
+                if (active) {
+                    *reinterpret_cast<uint4*>(smem_al + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(smem_al + so + p.a_bytes) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+            if (gw == 0) HSTAMP(tcount * p.nchunks, 7);             // converted + stored
+            // channel padding (Cin % 16 == 8): the upper half of the last chunk's rows stays zero -- written once per stage use
+            if (upt < p.nchunks * upc) {
+                int st = st0 + p.nchunks - 1;
+                st -= st >= p.a_stages ? p.a_stages : 0;
+                uint8_t* a_hi = smem_al + (size_t)st * p.a_stage_bytes;
+                const int cu = upc - 1;
+                for (int pix = gt; pix < npix; pix += 128) {
+                    const uint32_t so = (uint32_t)(pix * p.span + (swizzle_unit(cu, pix, p.span) << 4));
+                    *reinterpret_cast<uint4*>(a_hi + so) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(a_hi + p.a_bytes + so) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            fence_proxy_async_smem();
+            if (gw == 0) HSTAMP(tcount * p.nchunks, 2);             // written + fenced
+            {
+                int st = st0;
+                __syncwarp();
+                for (int c = 0; c < p.nchunks; ++c) {
+                    if (lane == 0) mbar_arrive(smem_u32(&a_conv[st]));
+                    if (++st == p.a_stages) st = 0;
+                }
+            }
+            st_tile += 2 * p.nchunks;                        // this group's next tile is two tiles on
+            while (st_tile >= p.a_stages) { st_tile -= p.a_stages; ++use_tile; }
+        }
+        tcount = 0;
+        for (int tile = blockIdx.x; tile < (p.f16_regs ? 0 : p.ntiles); tile += gridDim.x, ++tcount) {
+            if ((tcount & 1) != grp) continue;
+            const int img = tile / p.tiles_per_img;
+            const int trem = tile - img * p.tiles_per_img;
+            const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+            const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
+            const float* tbase = p.x + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld;
+            // ---- pass 1: absolute maximum of the halo box
+            float m = 0.0f;
+            for (int u0 = gt; u0 < units_tile; u0 += 512) {
+                float4 a[4][2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int u = u0 + j * 128;
+                    a[j][0] = a[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (u < units_tile) {
+                        const int pix = u / upt, cu = u - pix * upt;
+                        const int2 e = pix_tab[pix];
+                        const int hy = e.y >> 16, hx = e.y & 0xffff;
+                        if ((unsigned)(y0 + hy) < (unsigned)p.H && (unsigned)(x0 + hx) < (unsigned)p.W) {
+                            const float4* src = reinterpret_cast<const float4*>(tbase + e.x + cu * 8);
+                            a[j][0] = __ldg(src);
+                            a[j][1] = __ldg(src + 1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    m = fmaxf(m, fmaxf(fmaxf(fabsf(a[j][0].x), fabsf(a[j][0].y)), fmaxf(fabsf(a[j][0].z), fabsf(a[j][0].w))));
+                    m = fmaxf(m, fmaxf(fmaxf(fabsf(a[j][1].x), fabsf(a[j][1].y)), fmaxf(fabsf(a[j][1].z), fabsf(a[j][1].w))));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const int par = (tcount >> 1) & 1;
+            if (lane == 0) amax_red[grp][par][gw] = m;
+            if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+            else asm volatile("bar.sync 3, 128;" ::: "memory");
+            m = fmaxf(fmaxf(amax_red[grp][par][0], amax_red[grp][par][1]), fmaxf(amax_red[grp][par][2], amax_red[grp][par][3]));
+            const float sc = pow2_scale_for(m);
+            if (gt == 0) tile_inv_s[tcount & 15] = 1.0f / sc;
+            // ---- pass 2: chunk by chunk, scaled hi / lo halves into the swizzled K-major tiles
+            for (int c = 0; c < p.nchunks; ++c) {
+                const int item = tcount * p.nchunks + c;
+                const int st = item % p.a_stages;
+                const int use = item / p.a_stages;
+                const uint32_t ph = (uint32_t)(use & 1);
+                // The two groups work on different TILES, so one may reach a stage's use u while the other has not
+                // even started use u - 1: a parity wait only tells two consecutive phases apart, so wait until the
+                // previous use's producer is past its own wait (the barrier is then at most one phase behind).
+                {
+                    volatile int* uses = a_uses;
+                    while (uses[st] < use) {}
+                }
+                mbar_wait(smem_u32(&a_empty[st]), ph ^ 1u);
+                if (gt == 0) {
+                    volatile int* uses = a_uses;
+                    uses[st] = use + 1;
+                }
+                uint8_t* a_hi = smem_al + (size_t)st * p.a_stage_bytes;
+                uint8_t* a_lo = a_hi + p.a_bytes;
+                for (int u0 = gt; u0 < units_item; u0 += 512) {
+                    float4 a[4][2];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int u = u0 + j * 128;
+                        a[j][0] = a[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (u < units_item) {
+                            const int pix = u / upc, cu = u - pix * upc;
+                            const int cg = c * upc + cu;                  // unit among the pixel's real channels
+                            const int2 e = pix_tab[pix];
+                            const int hy = e.y >> 16, hx = e.y & 0xffff;
+                            if (cg < upt && (unsigned)(y0 + hy) < (unsigned)p.H && (unsigned)(x0 + hx) < (unsigned)p.W &&
+                                !(p.dbg & 2)) {
+                                const float4* src = reinterpret_cast<const float4*>(tbase + e.x + cg * 8);
+                                a[j][0] = __ldg(src);
+                                a[j][1] = __ldg(src + 1);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int u = u0 + j * 128;
+                        if (u < units_item) {
+                            const int pix = u / upc, cu = u - pix * upc;
+                            const float v[8] = {a[j][0].x * sc, a[j][0].y * sc, a[j][0].z * sc, a[j][0].w * sc,
+                                                a[j][1].x * sc, a[j][1].y * sc, a[j][1].z * sc, a[j][1].w * sc};
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int q2 = 0; q2 < 4; ++q2) {
+                                const __half2 h2 = __floats2half2_rn(v[2 * q2], v[2 * q2 + 1]);
+                                const float2 hf = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn(v[2 * q2] - hf.x, v[2 * q2 + 1] - hf.y);
+                                hw[q2] = *reinterpret_cast<const uint32_t*>(&h2);
+                                lw[q2] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                            const uint32_t so = (uint32_t)(pix * p.span + (swizzle_unit(cu, pix, p.span) << 4));
+                            *reinterpret_cast<uint4*>(a_hi + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4*>(a_lo + so) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive_warp(smem_u32(&a_conv[st]));
+            }
+        }
     } else if (p.ldg) {
         // ===================== A producers, LDG mode (warps 10-17: two groups of four warps) =====================
         // global -> registers -> swizzled K-major hi (raw) and lo tiles of one (tile, channel chunk) item; the two
@@ -567,6 +856,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_d, (uint32_t)p.tmem_cols);
+    if (p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.stamps[14] = clock64();      // CTA done
 }
 
 extern std::atomic<long long> g_tc_launches;
@@ -578,20 +868,38 @@ std::atomic<long long> g_halo_launches{0};
 bool conv2d_fwd_halo_supported(const ConvArgs& a, int math_mode) {
     static const bool disabled = [] { const char* e = getenv("DL4DS_TC_NO_HALO"); return e && e[0] == '1'; }();
     if (disabled) return false;
-    if (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3) return false;
+    if (math_mode != DL4DS_MATH_TF32 && math_mode != DL4DS_MATH_TF32X3 && math_mode != DL4DS_MATH_F16X3) return false;
     if (a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W) return false;
     if (a.Cin % 8 || a.Cout % 8 || a.Cout > 256) return false;
     if (a.W % BWt || a.H % BHt) return false;
+    if (math_mode == DL4DS_MATH_F16X3) {
+        static const bool no_f16 = [] { const char* e = getenv("DL4DS_NO_F16X3"); return e && e[0] == '1'; }();
+        // narrow layers stay on 3xTF32: their launches are latency chains of 3-4 tiles per CTA, and the fp16 producer's
+        // extra steps (tile maximum, conversion) cost more start-up than the halved MMA count returns
+        // (profiles/r02v_stamps.log: 16 -> 16 @ 32x32 20.7k clk against 18.3k; 48 -> 48 35.4k against 52.8k)
+        static const int min_cin = [] { const char* e = getenv("DL4DS_F16_MIN_CIN"); return e ? atoi(e) : 32; }();
+        if (no_f16 || a.Cin > 256 || a.Cin < min_cin) return false;        // (Cin / 8 units per pixel index the halo box)
+    }
     if (BWt + a.KW - 1 > 256 || BHt + a.KH - 1 > 256) return false;
     return true;
 }
 
 // weights already packed ([tap][chunk][Npad][kc], hi then lo) by conv2d_pack_tc
-int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, const float* wp_lo, cudaStream_t st) {
+// (DL4DS_MATH_F16X3: wp_hi / wp_lo are the fp16 images, w_scale their {s_w, 1 / s_w} pair)
+int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, const float* wp_lo, const float* w_scale,
+                       cudaStream_t st) {
     if (!conv2d_fwd_halo_supported(a, math_mode)) return DL4DS_E_UNSUPPORTED;
-    const bool x3 = math_mode == DL4DS_MATH_TF32X3;
-    const Chunk c = pick_chunk(a.Cin);
+    const bool f16 = math_mode == DL4DS_MATH_F16X3;
+    const bool x3 = math_mode == DL4DS_MATH_TF32X3 || f16;
+    Chunk c = pick_chunk(a.Cin);
+    int nchunks = a.Cin / c.kc;
+    if (f16) {
+        const Chunk16 c16 = pick_chunk16(a.Cin);
+        c.kc = c16.kc; c.span = c16.span; c.layout = c16.layout; c.swz = 0;
+        nchunks = c16.nchunks;
+    }
     HaloParams p;
+    p.w_scale = w_scale;
     int tg_override = 0;
     p.wp_hi = wp_hi; p.wp_lo = wp_lo;
     p.bias = a.bias; p.res = a.res; p.y = a.y; p.res_ld = a.res_ld; p.y_ld = a.y_ld;
@@ -602,13 +910,13 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
     p.tiles_per_img = p.tiles_x * (a.H / BHt);
     p.ntiles = a.N * p.tiles_per_img;
     p.kc = c.kc; p.span = c.span; p.layout = c.layout;
-    p.nchunks = a.Cin / c.kc;
-    p.ksteps = c.kc / 8;
+    p.nchunks = nchunks;
+    p.ksteps = f16 ? c.kc / 16 : c.kc / 8;
     p.act = a.act; p.d2s_r = a.d2s_r; p.beta = a.beta;
     static const int pitch_align = [] { const char* e = getenv("DL4DS_HALO_PITCH_ALIGN"); return e ? atoi(e) : 1; }();
     { const char* e = getenv("DL4DS_HALO_DBG"); p.dbg = e ? atoi(e) : 0; }
     static const int use_ldg = [] { const char* e = getenv("DL4DS_HALO_TMA"); return (e && e[0] == '1') ? 0 : 1; }();
-    p.ldg = use_ldg;
+    p.ldg = f16 ? 1 : use_ldg;
     p.x = a.x; p.x_ld = a.x_ld;
     p.mask_y = a.mask_y; p.mask_ld = a.mask_ld; p.mask_act = a.mask_act; p.dbias = a.dbias;
     p.stamps = g_halo_stamps;
@@ -658,29 +966,41 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
         p.b_stages = b_stages;
         p.b_base = a_stages * p.a_stage_bytes;
     }
+    p.f16_regs = 0;
+    if (f16) {
+        static const bool no_regs = [] { const char* e = getenv("DL4DS_F16_TWO_PASS"); return e && e[0] == '1'; }();
+        const int units = p.HWp * p.HHp * (a.Cin / 8);
+        const int per_thread = (units + 127) / 128;
+        if (!no_regs && per_thread <= 9 && p.nchunks <= p.a_stages) p.f16_regs = per_thread;
+    }
     const size_t smem = (size_t)p.b_base + (size_t)p.b_stages * p.b_stage_bytes + 1024;
-    const CUtensorMap* tm = get_tensor_map_nhwc(a.x, a.x_ld, a.N, a.H, a.W, a.Cin, c.kc, p.HWp, p.HHp, c.swz);
+    // (the fp16 mode has no TMA path: any valid map serves as the unused kernel argument)
+    const Chunk ct = pick_chunk(a.Cin);
+    const CUtensorMap* tm = get_tensor_map_nhwc(a.x, a.x_ld, a.N, a.H, a.W, a.Cin, f16 ? ct.kc : c.kc, p.HWp, p.HHp,
+                                                f16 ? ct.swz : c.swz);
     if (!tm) return DL4DS_E_CUDA;
     const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-#define HALO_LAUNCH(X3_, ST_, KS_)                                                                                   \
+#define HALO_LAUNCH(X3_, ST_, KS_, F16_)                                                                             \
     do {                                                                                                             \
         static bool attr_done_ = false;                                                                              \
         if (!attr_done_) {                                                                                           \
-            cudaFuncSetAttribute(conv_tc_halo_kernel<X3_, ST_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+            cudaFuncSetAttribute(conv_tc_halo_kernel<X3_, ST_, KS_, F16_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)(210 * 1024));                                                                 \
             attr_done_ = true;                                                                                       \
         }                                                                                                            \
-        conv_tc_halo_kernel<X3_, ST_, KS_><<<grid, kHaloThreads, smem, st>>>(*tm, p);                                \
+        conv_tc_halo_kernel<X3_, ST_, KS_, F16_><<<grid, kHaloThreads, smem, st>>>(*tm, p);                          \
     } while (0)
-#define HALO_LAUNCH_K(X3_, ST_)                                                                                      \
+#define HALO_LAUNCH_K(X3_, ST_, F16_)                                                                                \
     do {                                                                                                             \
-        if (p.ksteps == 4) HALO_LAUNCH(X3_, ST_, 4);                                                                 \
-        else if (p.ksteps == 2) HALO_LAUNCH(X3_, ST_, 2);                                                            \
-        else HALO_LAUNCH(X3_, ST_, 1);                                                                               \
+        if (p.ksteps == 4) HALO_LAUNCH(X3_, ST_, 4, F16_);                                                           \
+        else if (p.ksteps == 2) HALO_LAUNCH(X3_, ST_, 2, F16_);                                                      \
+        else HALO_LAUNCH(X3_, ST_, 1, F16_);                                                                         \
     } while (0)
-    if (x3 && stackn) HALO_LAUNCH_K(true, true);
-    else if (x3) HALO_LAUNCH_K(true, false);
-    else HALO_LAUNCH_K(false, false);
+    if (f16 && stackn) HALO_LAUNCH_K(true, true, true);
+    else if (f16) HALO_LAUNCH_K(true, false, true);
+    else if (x3 && stackn) HALO_LAUNCH_K(true, true, false);
+    else if (x3) HALO_LAUNCH_K(true, false, false);
+    else HALO_LAUNCH_K(false, false, false);
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     g_halo_launches.fetch_add(1, std::memory_order_relaxed);
     return check_launch("conv_tc_halo_kernel");

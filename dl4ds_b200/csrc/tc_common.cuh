@@ -166,6 +166,26 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a
     return d;
 }
 
+// instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate (a_format = b_format = 0 = F16)
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // c_format = F32
+    d |= static_cast<uint32_t>(N >> 3) << 17;
+    d |= static_cast<uint32_t>(M >> 4) << 24;
+    return d;
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (K = 16 per instruction: 32-byte K-major rows)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // round-to-nearest (ties away from zero in magnitude) onto the tf32 grid with two integer ops: add half
 // an ulp of the 10-bit mantissa, clear the 13 low bits.  (cvt.rna.tf32.f32 expands to ~8 SASS
 // instructions with Inf/NaN handling; the operand splitters run this per element.)  Inf/NaN inputs
@@ -202,6 +222,28 @@ static inline Chunk pick_chunk(int C) {
     if (C % 32 == 0) return {32, 128, kLayoutSw128, (int)CU_TENSOR_MAP_SWIZZLE_128B};
     if (C % 16 == 0) return {16, 64, kLayoutSw64, (int)CU_TENSOR_MAP_SWIZZLE_64B};
     return {8, 32, kLayoutSw32, (int)CU_TENSOR_MAP_SWIZZLE_32B};
+}
+// 2^(13 - floor(log2(amax))): amax * s lands in [2^13, 2^14); 1 for zero / denormal / non-finite maxima.  The scale of
+// the 3-term fp16 mode: a power of two, so scaling and un-scaling are exact.
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+    if (e == 0 || e == 255) return 1.0f;
+    int se = 127 + 13 - (e - 127);
+    se = se < 1 ? 1 : (se > 254 ? 254 : se);
+    return __uint_as_float((uint32_t)se << 23);
+}
+
+// the same for fp16 operands (3-term fp16 mode): channels are padded to a multiple of 16 (K = 16 per MMA), KC halfs =
+// one 32 / 64 / 128-byte span
+struct Chunk16 {
+    int kc, span, nchunks, cpad;
+    uint32_t layout;
+};
+static inline Chunk16 pick_chunk16(int C) {
+    const int cp = (C + 15) / 16 * 16;
+    if (cp % 64 == 0) return {64, 128, cp / 64, cp, kLayoutSw128};
+    if (cp % 32 == 0) return {32, 64, cp / 32, cp, kLayoutSw64};
+    return {16, 32, cp / 16, cp, kLayoutSw32};
 }
 // 16-byte-unit XOR of the hardware swizzle for row r of a tile whose rows are `span` bytes
 __host__ __device__ __forceinline__ int swizzle_unit(int unit, int row, int span) {

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256, 3) thin_conv_mma_kernel(const ConvArgs p,
 // DL4DS_E_UNSUPPORTED outside the domain (then thin.cu's CUDA-core kernel runs)
 int conv2d_fwd_thin_mma(const ConvArgs& a, int math_mode, cudaStream_t st) {
     static const bool disabled = [] { const char* e = getenv("DL4DS_THIN_NO_MMA"); return e && e[0] == '1'; }();
+    if (math_mode == DL4DS_MATH_F16X3) math_mode = DL4DS_MATH_TF32X3;
     if (disabled || (math_mode != DL4DS_MATH_TF32X3 && math_mode != DL4DS_MATH_TF32)) return DL4DS_E_UNSUPPORTED;
     if (a.KH != 3 || a.KW != 3 || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
         return DL4DS_E_UNSUPPORTED;
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(256, 2) thin_wgrad_mma_kernel(const float* __r
 // DL4DS_E_UNSUPPORTED outside the domain (then thin.cu's CUDA-core kernel runs)
 int conv2d_wgrad_thin_mma(const WgradArgs& w, int math_mode, cudaStream_t st) {
     static const bool disabled = [] { const char* e = getenv("DL4DS_THIN_NO_MMA"); return e && e[0] == '1'; }();
+    if (math_mode == DL4DS_MATH_F16X3) math_mode = DL4DS_MATH_TF32X3;
     if (disabled || (math_mode != DL4DS_MATH_TF32X3 && math_mode != DL4DS_MATH_TF32)) return DL4DS_E_UNSUPPORTED;
     if (w.KH != 3 || w.KW != 3 || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
     if (w.Ca != 8 || w.Cb != 8) return DL4DS_E_UNSUPPORTED;

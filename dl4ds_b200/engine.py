@@ -240,6 +240,15 @@ class Ctx:
         self.prepacked = None       # keys of a PackPlan that already ran on this stream: their images are up to date
         self._packed = set()
         self._pack_forked = False
+        # weight-gradient kernels on a side stream (the captured optimizer step): a wgrad only feeds the gradient arena,
+        # so it can overlap the dgrad chain that the rest of the backward pass waits on.  Both kernel families are
+        # persistent one-CTA-per-SM grids with 3-5 tiles per CTA on the 32x32 layers: run alone, a quarter of every
+        # launch is ramp and tail; two streams let the block scheduler fill one kernel's tail with the other's CTAs.
+        # Only convolutions whose dz buffer has no later in-place writer qualify (no residual hand-over); the buffers a
+        # side-stream kernel reads are kept alive until the join in backward().
+        self.wgrad_stream = None
+        self._side_keep = []
+        self._side_used = False
         self._rng_advanced = False  # dropout: the arena's RNG step is bumped once per Ctx, before the first mask
         self._dropout_calls = 0     # ... and every dropout application gets its own layer id
 
@@ -472,7 +481,7 @@ class Ctx:
             # weight gradient (accumulating)
             if pg:
                 self._wgrad(x, dz, self._g(name + '/kernel'), k, stride, pt, pl,
-                            label='%s:wgrad@%dx%d' % (name, x.H, x.W))
+                            label='%s:wgrad@%dx%d' % (name, x.H, x.W), side=res is None)
             # input gradient
             if x.requires_grad:
                 ws_q = lambda: lib.dl4ds_conv2d_fwd_workspace_bytes(x.N, Ho, Wo, cout, x.H, x.W, x.C, k, k, 1, stride, 1,
@@ -559,12 +568,15 @@ class Ctx:
                        dbeff.data_ptr() if pg else None, x.N, Ho, Wo, ce, a, r, _stream())
             if pg:
                 dweff = torch.zeros_like(weff)
-                self._wgrad(x, dz, dweff, k, 1, pt, pl, label='%s:wgrad@%dx%d' % (label, x.H, x.W))
                 self.launches += 1
-                self._call('dl4ds_spc_pointwise_chain', w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                           dweff.data_ptr(), dbeff.data_ptr(), self._g(name1 + '/kernel').data_ptr(),
-                           self._g(name1 + '/bias').data_ptr(), self._g(name2 + '/kernel').data_ptr(),
-                           self._g(name2 + '/bias').data_ptr(), rows, cm, co, r, _stream())
+
+                def chain():
+                    self._call('dl4ds_spc_pointwise_chain', w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                               dweff.data_ptr(), dbeff.data_ptr(), self._g(name1 + '/kernel').data_ptr(),
+                               self._g(name1 + '/bias').data_ptr(), self._g(name2 + '/kernel').data_ptr(),
+                               self._g(name2 + '/bias').data_ptr(), rows, cm, co, r, _stream())
+                self._wgrad(x, dz, dweff, k, 1, pt, pl, label='%s:wgrad@%dx%d' % (label, x.H, x.W), side=True,
+                            then=chain, keep=(dbeff, weff))
             if x.requires_grad:
                 def wr(dst, beta):
                     ws2 = self._conv_ws(x.N, Ho, Wo, ce, x.H, x.W, x.C, k, 1, 1, 1)
@@ -578,12 +590,43 @@ class Ctx:
         self._record(bwd)
         return out
 
-    def _wgrad(self, P, Q, dw, k, stride, pt, pl, label='wgrad'):
+    def _on_side(self, keep):
+        """Context manager: the weight-gradient side stream, forked after everything queued on the current stream so
+        far; ``keep`` lists the tensors the side-stream kernels read or write (held until the join)."""
+        import contextlib
+        side = self.wgrad_stream
+        if side is None or self.timers is not None:
+            return contextlib.nullcontext()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        side.wait_event(ev)
+        self._side_keep.extend(keep)
+        self._side_used = True
+        return torch.cuda.stream(side)
+
+    def _join_side(self):
+        if self._side_used:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+            self._side_used = False
+        self._side_keep = []
+
+    def _wgrad(self, P, Q, dw, k, stride, pt, pl, label='wgrad', side=False, then=None, keep=()):
+        """``side``: launch on the weight-gradient side stream when one is set (see __init__); ``then``: a callable
+        issued right after the wgrad on the same stream (the chain-rule kernels of composed layers)."""
         ws_bytes = _lib.load().dl4ds_conv2d_wgrad_workspace_bytes(P.N, Q.H, Q.W, P.C, Q.C, k, k, self.math)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device) if ws_bytes > 0 else None
-        self._timed(label, 'dl4ds_conv2d_wgrad', P.ptr, P.ld, Q.ptr, Q.ld, dw.data_ptr(),
-                   P.N, P.H, P.W, P.C, Q.H, Q.W, Q.C, k, k, stride, pt, pl,
-                   ws.data_ptr() if ws is not None else None, self.math, _stream())
+
+        def go():
+            self._timed(label, 'dl4ds_conv2d_wgrad', P.ptr, P.ld, Q.ptr, Q.ld, dw.data_ptr(),
+                        P.N, P.H, P.W, P.C, Q.H, Q.W, Q.C, k, k, stride, pt, pl,
+                        ws.data_ptr() if ws is not None else None, self.math, _stream())
+            if then is not None:
+                then()
+        if side:
+            with self._on_side([P.buf, Q.buf, ws, dw] + list(keep)):
+                go()
+        else:
+            go()
 
     def conv_transpose(self, x, name, cout, k, stride, act=None):
         """Keras Conv2DTranspose(cout, k, strides=stride, padding='same', use_bias=False)
@@ -657,9 +700,12 @@ class Ctx:
                        x.N, x.H, x.W, ce, a, s, _stream())
             if self.param_grads:
                 dwp = torch.zeros_like(wp)
-                self._wgrad(x, dz, dwp, Kp, 1, pp, pp, label='%s:wgrad@%dx%d' % (name, x.H, x.W))
-                self._call('dl4ds_convt_rearrange', self._g(name + '/kernel').data_ptr(), dwp.data_ptr(), k, s, pad,
-                           off_min, Kp, cout, x.C, 1, _stream())
+
+                def scatter():
+                    self._call('dl4ds_convt_rearrange', self._g(name + '/kernel').data_ptr(), dwp.data_ptr(), k, s,
+                               pad, off_min, Kp, cout, x.C, 1, _stream())
+                self._wgrad(x, dz, dwp, Kp, 1, pp, pp, label='%s:wgrad@%dx%d' % (name, x.H, x.W), side=True,
+                            then=scatter)
             if x.requires_grad:
                 def wr(dst, beta):
                     ws2 = self._conv_ws(x.N, x.H, x.W, ce, x.H, x.W, x.C, Kp, 1, 1, 1)
@@ -1281,6 +1327,7 @@ class Ctx:
         (cGAN: D(fake) is differentiated once for the discriminator weights, once for the generator)."""
         for fn in reversed(self.tape):
             fn()
+        self._join_side()
         if not keep_tape:
             self.tape = []
 

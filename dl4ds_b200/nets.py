@@ -234,7 +234,8 @@ class Model:
             out.append(x.contiguous())
         return out, bsz, T
 
-    def forward(self, inputs, training=False, math=None, timers=None, pack_stream=None, prepacked=None):
+    def forward(self, inputs, training=False, math=None, timers=None, pack_stream=None, prepacked=None,
+                wgrad_stream=None):
         """Run the graph on CUDA tensors prepared by ``_prep_inputs``.  Returns (ctx, out Var).  ``prepacked``: keys
         of a :class:`engine.PackPlan` that has just run on this stream."""
         ctx = Ctx(self.arena, math or self.math, training=training)
@@ -244,6 +245,7 @@ class Model:
         ctx.pack_cache = self._pack_cache
         ctx.pack_stream = pack_stream
         ctx.prepacked = prepacked
+        ctx.wgrad_stream = wgrad_stream
         vs = [ctx.input(x) for x in inputs]
         out = self.fn(ctx, vs)
         return ctx, out

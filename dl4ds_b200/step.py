@@ -84,6 +84,10 @@ class SupervisedStep:
         self._lr_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(4)] if dev.type == 'cuda' else None
         self._lr_events = [None] * 4
         self._lr_slot = 0
+        import os
+        # weight gradients on a side stream (engine.Ctx.wgrad_stream); DL4DS_WGRAD_STREAM=0 keeps one stream
+        self.wgrad_stream = (torch.cuda.Stream(device=dev) if dev.type == 'cuda' and
+                             os.environ.get('DL4DS_WGRAD_STREAM', '1') != '0' else None)
         self.use_graph = use_graph
         self.graph_fb = None        # the whole step: zero-grad + forward + loss + backward + all-reduce + Adam
         self.graph_opt = None       # (kept for callers that test for it: aliases graph_fb)
@@ -101,7 +105,8 @@ class SupervisedStep:
         self.loss_buf.zero_()
         n_pack = plan.run() if plan is not None else 0
         ctx, out = self.model.forward(self.inputs, training=True, math=self.math, timers=timers,
-                                      prepacked=plan.keys if plan is not None else None)
+                                      prepacked=plan.keys if plan is not None else None,
+                                      wgrad_stream=self.wgrad_stream)
         ctx.pixel_loss(out, ctx.input(self.target), self.loss_kind, loss_buf=self.loss_buf)
         ctx.backward()
         return ctx.launches + 2 + n_pack     # + the two memsets

@@ -47,6 +47,9 @@ extern "C" {
 #define DL4DS_MATH_FP32    0   /* CUDA-core fp32 FMA (exact fp32 semantics)                     */
 #define DL4DS_MATH_TF32X3  1   /* tcgen05 kind::tf32, 3-term split (hi*hi+hi*lo+lo*hi), ~fp32   */
 #define DL4DS_MATH_TF32    2   /* tcgen05 kind::tf32, single pass (10-bit mantissa operands)    */
+#define DL4DS_MATH_F16X3   3   /* forward / dgrad: tcgen05 kind::f16, 3-term fp16 split with    */
+                               /* power-of-two scales per tile and per weight tensor (~fp32,    */
+                               /* half the MMAs of TF32X3); every other kernel as TF32X3        */
 
 /* weight indexing modes of dl4ds_conv2d_fwd */
 #define DL4DS_W_HWIO        0  /* B[(tap,c),n] = w[tap][c][n]            (Conv2D forward)          */

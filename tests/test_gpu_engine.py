@@ -268,7 +268,8 @@ def test_discriminator_spatiotemporal(cuda, ups, scale, math):
 
 
 # ------------------------------------------------------------------------------------------ tcgen05
-TC_TOL = {'tf32x3': dict(tol=2e-5, gtol=2e-4), 'tf32': dict(tol=5e-3, gtol=2e-2)}
+TC_TOL = {'tf32x3': dict(tol=2e-5, gtol=2e-4), 'tf32': dict(tol=5e-3, gtol=2e-2),
+          'f16x3': dict(tol=2e-5, gtol=2e-4)}     # 3-term fp16 (power-of-two scales): the fp32-level bound of tf32x3
 
 
 def _tc_count():
@@ -276,7 +277,7 @@ def _tc_count():
     return _lib.load().dl4ds_tc_launch_count()
 
 
-@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32', 'f16x3'])
 @pytest.mark.parametrize('shape,cout,k,act', [
     ((2, 16, 16, 8), 16, 3, 'relu'),        # SW32 chunks, BW=16 BH=8
     ((2, 8, 16, 24), 40, 3, None),          # Cin 24 -> three 8-channel chunks; Cout 40 -> Npad 48
@@ -297,9 +298,9 @@ def test_conv_tc(cuda, math, shape, cout, k, act):
     assert _tc_count() >= n0 + 2, 'tensor-core path did not run (fwd + dgrad expected)'
 
 
-@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32', 'f16x3'])
 def test_conv_tc_residual_and_d2s(cuda, math):
-    a = 'relu' if math == 'tf32x3' else 'tanh'
+    a = 'relu' if math != 'tf32' else 'tanh'
 
     def fn(c, xs):
         y = c.conv(xs[0], 'cv', 16, act=a, res=xs[1])
@@ -310,7 +311,7 @@ def test_conv_tc_residual_and_d2s(cuda, math):
     assert _tc_count() >= n0 + 4
 
 
-@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32', 'f16x3'])
 def test_spc_block_tc(cuda, math):
     """The headline layer: shared 48 -> 192 3x3 conv + depth_to_space applied at 32^2 and 64^2."""
     fn = lambda c, xs: B.subpixel_block(c, 'spc', xs[0], 4, 48)
@@ -318,7 +319,7 @@ def test_spc_block_tc(cuda, math):
     compare(fn, ofn, [(1, 32, 32, 48)], cuda, math=math, **TC_TOL[math])
 
 
-@pytest.mark.parametrize('math', ['tf32x3'])
+@pytest.mark.parametrize('math', ['tf32x3', 'f16x3'])
 def test_net_resnet_spc_tc(cuda, math):
     m = nets.net_postupsampling('resnet', 'spc', 4, 1, 0, (32, 32), n_blocks=3)
     ofn = lambda p, xs: R.net_postupsampling(p, xs, 'resnet', 'spc', 4, n_blocks=3)
@@ -363,7 +364,7 @@ def test_pointwise_conv(cuda, cin, cout):
 
 
 # ------------------------------------------------------------------------------------------ stacked-taps wgrad
-@pytest.mark.parametrize('math', ['tf32x3', 'tf32'])
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32', 'f16x3'])
 @pytest.mark.parametrize('shape,cout,k', [
     ((3, 32, 32, 48), 48, 3),       # backbone layer: 432 stacked rows -> 4 M-blocks, one role
     ((2, 64, 64, 48), 192, 3),      # SPC layer: two output-channel roles of 96, two chunks per image row
@@ -397,7 +398,7 @@ def test_wgrad_stacked_taps_on_concat_slices(cuda):
 
 
 # ------------------------------------------------------------------------------------------ composed SPC stage + 1x1
-@pytest.mark.parametrize('math', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('math', ['fp32', 'tf32x3', 'f16x3'])
 @pytest.mark.parametrize('scale,cin,hw', [(4, 48, 16), (2, 16, 32), (4, 8, 32)])
 def test_subpixel_transition_composed(cuda, math, scale, cin, hw):
     """SubpixelConvolutionBlock + TransitionLast with the last x2 stage composed with the 1x1 convolution
@@ -417,7 +418,7 @@ def test_subpixel_transition_fallback_x5(cuda):
 
 
 # ------------------------------------------------------------------------------------------ Conv2DTranspose on tensor cores
-@pytest.mark.parametrize('math', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('math', ['fp32', 'tf32x3', 'f16x3'])
 @pytest.mark.parametrize('shape,cout,k,stride,act', [
     ((2, 16, 16, 8), 48, 9, 2, None),        # DeconvolutionBlock T1 (blocks.py:508-516): 8 -> 48, 9x9, s=2
     ((2, 32, 32, 48), 48, 9, 2, 'tanh'),     # T2: 48 -> 48 with the block's activation
