@@ -307,6 +307,9 @@ def run_native(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     bf16_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
     tf32_peak = bf16_peak / 2.0         # kind::tf32 issues at half the kind::f16 rate
+    # --math f16x3: the forward / input-gradient launches issue kind::f16 MMAs (the full bf16-class rate); the weight
+    # gradients stay on kind::tf32
+    fwd_peak = bf16_peak if args.math == 'f16x3' else tf32_peak
 
     # ---------------- BASELINE configs 3 / 4 / 5 (after the headline's timed regions; every rank takes part) ----------------
     n_launch_headline = int(step.launches_per_step)
@@ -344,12 +347,14 @@ def run_native(args):
                 traffic = json.load(f).get(label)
         except Exception:
             pass
+        lab_peak = tf32_peak if ':wgrad@' in label else fwd_peak
         roofline = {
-            'bound': 'tensor', 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-            'frac': achieved / tf32_peak, 'traffic': traffic,
+            'bound': 'tensor', 'achieved': achieved, 'peak': lab_peak, 'unit': 'TFLOP/s',
+            'frac': achieved / lab_peak, 'traffic': traffic,
             'kernel': label, 'avg_launch_ms': avg_ms, 'launches_per_step': n_launch,
             'share_of_step': ms_lab / max(sum(v[0] for v in per_label.values()), 1e-9),
-            'peak_source': '%s: bf16_tflops_sustained/2 (tcgen05 kind::tf32 issue rate)' % peaks_src,
+            'peak_source': '%s: bf16_tflops_sustained%s' % (peaks_src, '/2 (tcgen05 kind::tf32 issue rate)'
+                                                            if lab_peak == tf32_peak else ' (tcgen05 kind::f16 issue rate)'),
             'math': args.math,
             'step_conv_roofline_frac': (algo_flops_step / (step_ms * 1e-3) / 1e12) / tf32_peak,
             'step_algorithmic_tflops': algo_flops_step / (step_ms * 1e-3) / 1e12,
@@ -373,7 +378,8 @@ def run_native(args):
             a_[2] += n_k
         roofline['per_function'] = {
             g: {'ms_per_step': v[0], 'launches_per_step': v[2], 'achieved': v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0,
-                'frac': (v[1] / (v[0] * 1e-3) / 1e12) / tf32_peak if v[0] > 0 else 0.0, 'share_of_conv_family': v[0] / max(conv_ms, 1e-9)}
+                'frac': (v[1] / (v[0] * 1e-3) / 1e12) / (tf32_peak if g.startswith('wgrad') else fwd_peak) if v[0] > 0 else 0.0,
+                'share_of_conv_family': v[0] / max(conv_ms, 1e-9)}
             for g, v in groups.items()}
 
         # bounded CPU sample: 10-30 s of host work

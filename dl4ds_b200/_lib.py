@@ -56,6 +56,8 @@ SIGNATURES = {
     'dl4ds_depthwise_conv_wgrad': ('i', 'pipipiiiiip'),
     'dl4ds_gelu_fwd': ('i', 'pplp'),
     'dl4ds_gelu_bwd': ('i', 'ppplp'),
+    'dl4ds_channel_scale_fwd': ('i', 'pippilip'),
+    'dl4ds_channel_scale_bwd': ('i', 'pipippiplip'),
     'dl4ds_dropout': ('i', 'pipilliifipip'),
     'dl4ds_rng_advance': ('i', 'pp'),
     'dl4ds_adam_step': ('i', 'pppplffffifp'),

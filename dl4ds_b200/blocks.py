@@ -76,10 +76,12 @@ def dense_block(c, name, x, filters, activation='relu', attention=False, normali
     return c.concat([y, x])
 
 
-def convnext_block(c, name, x, filters, activation='gelu', normalization='ln', use_1x1conv=False):
-    """ConvNextBlock.call -- blocks.py:170-184 with drop_path=0 and layer_scale_init_value=0 (the values every
-    builder passes / the default: no DropPath, no layer-scale gamma): 7x7 depthwise conv -> norm (LN with
-    epsilon 1e-6, or BN) -> Dense(4F) -> activation -> Dense(F), added to the ([1x1-projected]) input."""
+def convnext_block(c, name, x, filters, activation='gelu', normalization='ln', use_1x1conv=False, drop_path=0.,
+                   layer_scale_init_value=0):
+    """ConvNextBlock.call -- blocks.py:170-184: 7x7 depthwise conv -> norm (LN with epsilon 1e-6, or BN) -> Dense(4F)
+    -> activation -> Dense(F) [-> * gamma, the layer scale, when ``layer_scale_init_value`` > 0 (:166-169,178-179)]
+    [-> DropPath(drop_path): whole samples of the branch dropped in training, :106-129,183], added to the
+    ([1x1-projected]) input.  The builders pass neither option (sp_postups.py:125-129): defaults 0."""
     if normalization not in ('bn', 'ln'):
         # the reference only creates `self.norm` for 'bn' / 'ln' (:158-164) and calls it unconditionally (:173)
         raise ValueError("ConvNextBlock needs normalization 'bn' or 'ln' (the reference fails in call() with "
@@ -88,7 +90,11 @@ def convnext_block(c, name, x, filters, activation='gelu', normalization='ln', u
     y = c.norm(y, name + '/norm', normalization, eps=1e-6 if normalization == 'ln' else 1e-3)
     y = c.dense(y, name + '/pwconv1', 4 * filters, act=activation)
     y = c.dense(y, name + '/pwconv2', filters)
+    if layer_scale_init_value > 0:
+        y = c.channel_scale(y, name + '/gamma', layer_scale_init_value)
     skip = c.conv(x, name + '/conv1x1', filters, k=1) if use_1x1conv else x
+    if drop_path and drop_path > 0:
+        y = c.dropout(y, drop_path, 'droppath')
     return c.add(skip, y)
 
 

@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(DropArgs a, const unsigned
         int64_t p0 = i0 / a.C;
         int c0 = (int)(i0 - p0 * a.C);
         if (shared_call) {
-            const unsigned long long idx0 = a.variant == 2
-                ? (unsigned long long)((p0 / a.pix_per_sample) % a.n_samples) * a.C + c0 : (unsigned long long)i0;
+            const unsigned long long smp = (unsigned long long)((p0 / a.pix_per_sample) % a.n_samples);
+            const unsigned long long idx0 = a.variant == 2 ? smp * a.C + c0 : (a.variant == 3 ? smp : (unsigned long long)i0);
             if (a.variant == 1) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(256) dropout_kernel(DropArgs a, const unsigned
                 philox4x32_10(ctr, k0, k1);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) m[k] = u01(ctr[k]) >= a.rate ? scale : 0.0f;
+                if (a.variant == 3) {       // DropPath: one draw per sample, shared by every element of the sample
+                    const int w = (int)(idx0 & 3);
+                    m[0] = m[1] = m[2] = m[3] = w == 0 ? m[0] : w == 1 ? m[1] : w == 2 ? m[2] : m[3];
+                }
             }
             if (a.vec) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(a.x + p0 * a.x_ld + c0));
@@ -90,8 +94,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(DropArgs a, const unsigned
         for (int k = 0; k < 4 && i0 + k < n; ++k) {     // any C: one call per element, same mask function
             const int64_t i = i0 + k, p = i / a.C;
             const int c = (int)(i - p * a.C);
-            const unsigned long long idx = a.variant == 2
-                ? (unsigned long long)((p / a.pix_per_sample) % a.n_samples) * a.C + c : (unsigned long long)i;
+            const unsigned long long smp = (unsigned long long)((p / a.pix_per_sample) % a.n_samples);
+            const unsigned long long idx = a.variant == 2 ? smp * a.C + c : (a.variant == 3 ? smp : (unsigned long long)i);
             const unsigned long long q = a.variant == 1 ? idx >> 1 : idx >> 2;
             uint32_t ctr[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)a.layer_id, (uint32_t)step};
             philox4x32_10(ctr, k0, k1);
@@ -125,7 +129,7 @@ int dl4ds_dropout(const float* x, int x_ld, float* y, int y_ld, int64_t n_pix, i
     DL4DS_REQUIRE(n_pix > 0 && C > 0 && pix_per_sample > 0 && n_pix % pix_per_sample == 0 && n_samples > 0,
                   DL4DS_E_SHAPE, "dropout: bad shape");
     DL4DS_REQUIRE(rate > 0.0f && rate < 1.0f, DL4DS_E_BADARG, "dropout: rate must be in (0, 1)");
-    DL4DS_REQUIRE(variant >= 0 && variant <= 2, DL4DS_E_BADARG, "dropout: variant must be 0, 1 or 2");
+    DL4DS_REQUIRE(variant >= 0 && variant <= 3, DL4DS_E_BADARG, "dropout: variant must be 0, 1, 2 or 3");
     const int64_t n = n_pix * C;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(n, 256 * 4 * 2), 16 * kNumSMs));
     DropArgs a{x, y, x_ld, y_ld, n_pix, pix_per_sample, n_samples, C, rate, variant, layer_id, 0};

@@ -456,6 +456,45 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
 }
 
 // -------------------------------------------------------------------------------------------------
+// ConvNextBlock's layer scale (blocks.py:166-179): y = gamma[c] * x with a trainable per-channel gamma.
+// bwd: dx = gamma[c] * dy, dgamma[c] += sum over pixels of dy * x.
+// -------------------------------------------------------------------------------------------------
+__global__ void channel_scale_fwd_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ gamma,
+                                         float* __restrict__ y, int y_ld, int64_t n_pix, int C) {
+    const int64_t total = n_pix * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        y[p * y_ld + c] = __ldg(gamma + c) * __ldg(x + p * x_ld + c);
+    }
+}
+
+// block = 256 threads = (256 / C') pixel lanes x C' channel lanes, C' = C rounded up to a power of two <= 256
+__global__ void __launch_bounds__(256) channel_scale_bwd_kernel(const float* __restrict__ dy, int dy_ld,
+                                                                const float* __restrict__ x, int x_ld,
+                                                                const float* __restrict__ gamma, float* __restrict__ dx,
+                                                                int dx_ld, float* __restrict__ dgamma, int64_t n_pix,
+                                                                int C, int cp) {
+    __shared__ float red[256];
+    const int c = threadIdx.x % cp, lane = threadIdx.x / cp, lanes = 256 / cp;
+    float acc = 0.0f;
+    if (c < C) {
+        const float g = __ldg(gamma + c);
+        for (int64_t p = (int64_t)blockIdx.x * lanes + lane; p < n_pix; p += (int64_t)gridDim.x * lanes) {
+            const float d = __ldg(dy + p * dy_ld + c);
+            acc = fmaf(d, __ldg(x + p * x_ld + c), acc);
+            if (dx) dx[p * dx_ld + c] = g * d;
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (lane == 0 && c < C && dgamma) {
+        for (int l = 1; l < lanes; ++l) acc += red[l * cp + c];
+        atomicAdd(dgamma + c, acc);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // data path: separable resampling with per-output tap tables -- cv2.resize (utils.py:341-401) for every
 // interpolation the reference offers (inter_area up/down, nearest, bilinear, bicubic, lanczos4).  The tables hold, per
 // output row (column), K source indices and float32 weights taken from cv2 itself (dataloader.DeviceDataGenerator
@@ -1324,6 +1363,27 @@ int dl4ds_avgpool_coarsen(const float* x, float* y, int N, int H, int W, int C, 
                   "avgpool_coarsen: H, W must be multiples of s");
     return launch1d("avgpool_coarsen", avgpool_coarsen_kernel, (int64_t)N * (H / s) * (W / s) * C,
                     as_stream(stream), x, y, N, H, W, C, s);
+}
+
+int dl4ds_channel_scale_fwd(const float* x, int x_ld, const float* gamma, float* y, int y_ld, int64_t n_pix, int C,
+                            void* stream) {
+    DL4DS_REQUIRE(x && gamma && y, DL4DS_E_BADARG, "channel_scale_fwd: null pointer");
+    DL4DS_REQUIRE(n_pix > 0 && C > 0 && x_ld >= C && y_ld >= C, DL4DS_E_SHAPE, "channel_scale_fwd: bad shape");
+    return launch1d("channel_scale_fwd", channel_scale_fwd_kernel, n_pix * C, as_stream(stream), x, x_ld, gamma, y, y_ld,
+                    n_pix, C);
+}
+
+int dl4ds_channel_scale_bwd(const float* dy, int dy_ld, const float* x, int x_ld, const float* gamma, float* dx,
+                            int dx_ld, float* dgamma, int64_t n_pix, int C, void* stream) {
+    DL4DS_REQUIRE(dy && x && gamma && (dx || dgamma), DL4DS_E_BADARG, "channel_scale_bwd: null pointer");
+    DL4DS_REQUIRE(n_pix > 0 && C > 0 && C <= 256 && dy_ld >= C && x_ld >= C && (!dx || dx_ld >= C), DL4DS_E_SHAPE,
+                  "channel_scale_bwd: bad shape (C <= 256)");
+    int cp = 1;
+    while (cp < C) cp *= 2;
+    const int lanes = 256 / cp;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_pix + lanes - 1) / lanes, 8 * kNumSMs));
+    channel_scale_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(dy, dy_ld, x, x_ld, gamma, dx, dx_ld, dgamma, n_pix, C, cp);
+    return check_launch("channel_scale_bwd");
 }
 
 int dl4ds_resample_taps(const float* x, float* y, int N, int H, int W, int C, int Ho, int Wo, const int* iy,

@@ -36,7 +36,7 @@ LOSS_TERMS = {
 }
 MSSSIM_POWER_FACTORS = (0.0448, 0.2856, 0.3001, 0.2363)      # losses.py:128
 DROPOUT_KIND = {None: 0, 'vanilla': 0, 'mcdrop': 0, 'gaussian': 1, 'mcgaussiandrop': 1, 'spatial': 2,
-                'mcspatialdrop': 2}                          # blocks.py:680-706 -> dl4ds_dropout variant
+                'mcspatialdrop': 2, 'droppath': 3}           # blocks.py:680-706 (+ DropPath, :106-129) -> dl4ds_dropout variant
 RESIZE_METHOD = {'bilinear': 0, 'nearest': 1, 'bicubic': 2}     # DL4DS_RESIZE_*
 LOSS_ACCUMULATE = 16                                          # DL4DS_LOSS_ACCUMULATE, OR-ed into `kind`
 _PF_HOST = (ctypes.c_float * len(MSSSIM_POWER_FACTORS))(*MSSSIM_POWER_FACTORS)
@@ -903,6 +903,33 @@ class Ctx:
         self._record(bwd)
         return out
 
+    def channel_scale(self, x, name, init_value):
+        """ConvNextBlock's layer scale (blocks.py:166-169,178-179): y = gamma * x with a trainable per-channel ``gamma``
+        (initialised to ``layer_scale_init_value``; parameter ``<name>`` of shape (C,))."""
+        self._use(x)
+        gamma = self._p(name)
+        assert tuple(gamma.shape) == (x.C,)
+        out = x.like()
+        self._call('dl4ds_channel_scale_fwd', x.ptr, x.ld, gamma.data_ptr(), out.ptr, out.ld, x.npix, x.C, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None:
+                return
+            dg = self._g(name).data_ptr() if self.param_grads else None
+
+            def wr(dst):
+                self._call('dl4ds_channel_scale_bwd', dy.ptr, dy.ld, x.ptr, x.ld, gamma.data_ptr(),
+                           dst.ptr if dst is not None else None, dst.ld if dst is not None else 0, dg, x.npix, x.C,
+                           _stream())
+            if x.requires_grad:
+                self._acc_via_tmp(x, wr)
+            elif dg is not None:
+                wr(None)
+            out.grad = None
+        self._record(bwd)
+        return out
+
     def dropout(self, x, rate, variant=None, n_samples=None):
         """get_dropout_layer(rate, variant)(x) -- blocks.py:680-706: Dropout / GaussianDropout / SpatialDropout2D,
         active in training mode; the 'mc*' variants also in inference (blocks.py:662-677).  Masks: dl4ds_dropout
@@ -1035,8 +1062,11 @@ class Ctx:
         bicubic (tf.image.resize without antialiasing, half-pixel centres)."""
         if method == 'bilinear':
             return self.resize_bilinear(x, Ho, Wo)
+        from .resize_tables import TAP_METHODS
+        if method in TAP_METHODS:
+            return self._resize_taps(x, Ho, Wo, method)
         if method not in RESIZE_METHOD:
-            raise NotImplementedError('interpolation=%r is not built (bilinear, nearest, bicubic are)' % (method,))
+            raise NotImplementedError('interpolation=%r is not one of keras Resizing\'s methods' % (method,))
         code = RESIZE_METHOD[method]
         self._use(x)
         out = new_var(x.N, Ho, Wo, x.C, self.device)
@@ -1051,6 +1081,46 @@ class Ctx:
                 x.grad = Var(torch.zeros((x.N, x.H, x.W, x.C), dtype=torch.float32, device=self.device))
             self._call('dl4ds_resize_bwd', dy.ptr, dy.ld, x.grad.ptr, x.grad.ld, x.N, x.H, x.W, x.C, Ho, Wo, code,
                        _stream())
+            out.grad = None
+        self._record(bwd)
+        return out
+
+    def _tap_tables(self, n_in, n_out, method, transposed):
+        """Device (indices, weights, K) of tf.image.resize's 1-D operator n_in -> n_out (or of its transpose),
+        cached on the arena."""
+        from .resize_tables import matrix_to_taps, tf_resize_matrix
+        cache = self.arena.__dict__.setdefault('_resize_taps', {})
+        key = (n_in, n_out, method, transposed)
+        if key not in cache:
+            r = tf_resize_matrix(n_in, n_out, method)
+            idx, w = matrix_to_taps(r.T.copy() if transposed else r)
+            cache[key] = (torch.as_tensor(idx).to(self.device), torch.as_tensor(w).to(self.device), idx.shape[1])
+        return cache[key]
+
+    def _resize_taps(self, x, Ho, Wo, method):
+        """keras Resizing with interpolation in area / lanczos3 / lanczos5 / gaussian / mitchellcubic
+        (blocks.py:457-491): a separable linear map, run as tap tables by ``dl4ds_resample_taps``; the backward pass
+        is the same kernel with the transposed tables."""
+        self._use(x)
+        xd = self._dense(x)
+        out = new_var(x.N, Ho, Wo, x.C, self.device)
+        iy, wy, ky = self._tap_tables(x.H, Ho, method, False)
+        ix, wx, kx = self._tap_tables(x.W, Wo, method, False)
+        self._call('dl4ds_resample_taps', xd.ptr, out.ptr, x.N, x.H, x.W, x.C, Ho, Wo, iy.data_ptr(), wy.data_ptr(), ky,
+                   ix.data_ptr(), wx.data_ptr(), kx, out.ld, 0, _stream())
+
+        def bwd():
+            dy = out.grad
+            if dy is None or not x.requires_grad:
+                return
+            dyd = self._dense(dy)
+            ty, tw, tk = self._tap_tables(x.H, Ho, method, True)
+            sx, sw, sk = self._tap_tables(x.W, Wo, method, True)
+
+            def wr(dst):
+                self._call('dl4ds_resample_taps', dyd.ptr, dst.ptr, x.N, Ho, Wo, x.C, x.H, x.W, ty.data_ptr(),
+                           tw.data_ptr(), tk, sx.data_ptr(), sw.data_ptr(), sk, dst.ld, 0, _stream())
+            self._acc_via_tmp(x, wr)
             out.grad = None
         self._record(bwd)
         return out

@@ -7,7 +7,7 @@ Each builder keeps the signature and the model naming (``<backbone>_<upsampling>
 
 Scope (SURVEY.md sections 8a and 8f row 3): backbones convnet / resnet / densenet / unet / convnext (and the
 recurrent ConvLSTM networks), ``normalization`` None / 'bn' / 'ln', every ``dropout_variant``, activations in
-{None, relu, sigmoid, tanh, gelu}, bilinear / nearest / bicubic resize-convolution.  Anything else raises
+{None, relu, sigmoid, tanh, gelu}, every ``rc_interpolation`` of Keras ``Resizing``.  Anything else raises
 ``NotImplementedError`` (or the reference's own ``ValueError``) -- there is no fallback path.
 """
 import math
@@ -23,7 +23,8 @@ from .utils import checkarg_dropout_variant
 
 BACKBONES = ('convnet', 'resnet', 'densenet', 'unet', 'convnext')
 POSTUPSAMPLING_METHODS = ('spc', 'rc', 'dc')
-RC_INTERPOLATIONS = ('bilinear', 'nearest', 'bicubic')     # of Keras Resizing's eight (blocks.py:463-465)
+RC_INTERPOLATIONS = ('bilinear', 'nearest', 'bicubic', 'area', 'lanczos3', 'lanczos5', 'gaussian',
+                     'mitchellcubic')                          # Keras Resizing's eight (blocks.py:463-465)
 
 
 def _check_common(activation, output_activation, normalization, dropout_rate, backbone_block=None,
@@ -66,6 +67,7 @@ class Model:
         ins = [sc.input(self._spec_shape(s)) for s in self.input_shapes]
         out = fn(sc, ins)
         self.spec = sc.spec
+        self.const_init = dict(getattr(sc, 'const_init', {}))     # parameters with a constant initial value (layer scale)
         n0 = ins[0].N if len(self.input_shapes[0]) == 3 else 1    # traced batch (T folded into N)
         self.macs_per_sample = sc.macs // n0 if len(self.input_shapes[0]) == 3 else sc.macs
         self.macs_dgrad_per_sample = sc.macs_dgrad
@@ -133,7 +135,9 @@ class Model:
         rng = np.random.default_rng(seed)
         w = OrderedDict()
         for name, shape in self.spec.items():
-            if name.endswith(('/gamma', '/moving_variance')):        # BatchNormalization / LayerNormalization: ones
+            if name in self.const_init:                              # ConvNextBlock layer scale: layer_scale_init_value
+                w[name] = np.full(shape, self.const_init[name], np.float32)
+            elif name.endswith(('/gamma', '/moving_variance')):      # BatchNormalization / LayerNormalization: ones
                 w[name] = np.ones(shape, np.float32)
             elif name.endswith(('/beta', '/moving_mean')):
                 w[name] = np.zeros(shape, np.float32)

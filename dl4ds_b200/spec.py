@@ -118,6 +118,12 @@ class SpecCtx:
     def gelu(self, x):
         return x
 
+    def channel_scale(self, x, name, init_value):
+        self._reg(name, (x.C,))
+        self.const_init = getattr(self, 'const_init', {})
+        self.const_init[name] = float(init_value)
+        return SVar(*x.shape)
+
     def dropout(self, x, rate, variant=None, n_samples=None):
         if rate and rate > 0:
             self.n_dropout += 1        # applications in graph order = the layer ids of the mask generator

@@ -273,6 +273,12 @@ int dl4ds_depthwise_conv_fwd(const float* x, int x_ld, const float* w, const flo
                              int N, int H, int W, int C, int k, int flip, int accumulate, void* stream);
 int dl4ds_depthwise_conv_wgrad(const float* x, int x_ld, const float* dy, int dy_ld, float* dw, int N, int H, int W,
                                int C, int k, void* stream);
+/* ConvNextBlock's layer scale (blocks.py:166-179): y = gamma[c] * x; bwd: dx = gamma[c] * dy (dx may be NULL),
+ * dgamma[c] += sum_pixels dy * x (dgamma may be NULL).  C <= 256 for the backward. */
+int dl4ds_channel_scale_fwd(const float* x, int x_ld, const float* gamma, float* y, int y_ld, int64_t n_pix, int C,
+                            void* stream);
+int dl4ds_channel_scale_bwd(const float* dy, int dy_ld, const float* x, int x_ld, const float* gamma, float* dx,
+                            int dx_ld, float* dgamma, int64_t n_pix, int C, void* stream);
 int dl4ds_gelu_fwd(const float* x, float* y, int64_t n, void* stream);
 int dl4ds_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
 
@@ -281,6 +287,7 @@ int dl4ds_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* 
  * 265-266,271-272 and sp_postups.py:158.  variant 0 = Dropout (keep where u >= rate, scale 1/(1-rate)),
  * 1 = GaussianDropout (x * N(1, sqrt(rate/(1-rate)))), 2 = SpatialDropout2D / 3D (one draw per sample and channel;
  * sample = (pixel / pix_per_sample) % n_samples: n_samples = N for (N,H,W,C), = B for time-major frames (T*B,H,W,C)).
+ * 3 = DropPath (blocks.py:106-129: one keep / drop draw per SAMPLE, kept samples scaled by 1/(1-rate)).
  * y = x * mask(seed, step, layer_id, element): Philox4x32-10, `rng_state` = DEVICE uint64[2] {seed, step}.  The
  * mask is a pure function of its arguments: the backward pass is the same call on dy.  dl4ds_rng_advance bumps
  * `step` (one kernel, captured with the step graph, so every replay draws new masks).  TensorFlow's own random

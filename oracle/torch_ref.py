@@ -164,10 +164,56 @@ def _resize_matrix(n_in, n_out, method):
     return m
 
 
+def _scale_and_translate_matrix(n_in, n_out, method):
+    """tf.image.resize(method in lanczos3 / lanczos5 / gaussian / mitchellcubic, antialias=False) = the ScaleAndTranslate
+    op (tensorflow/core/kernels/image/scale_and_translate_op.cc ComputeSpansCore + sampling_kernels.h; third-party,
+    restated): per output sample the kernel is evaluated at the source centres inside [sample - radius, sample +
+    radius] (clamped to the image) and the weights are normalised to sum 1.  'area' = the ResizeArea op
+    (resize_area_op.cc): the box [x * s, (x + 1) * s) of source cells, partial cells weighted by their overlap."""
+    m = np.zeros((n_out, n_in), np.float64)
+    if method == 'area':
+        s = n_in / n_out
+        for o in range(n_out):
+            a, b = o * s, (o + 1) * s
+            i = int(np.floor(a))
+            while i < np.ceil(b):
+                overlap = min(i + 1, b) - max(i, a)
+                m[o, min(max(i, 0), n_in - 1)] += overlap / s
+                i += 1
+        return m
+    pi = 3.14159265359
+
+    def lanczos(r):
+        return lambda t: 0.0 if t > r else (1.0 if t <= 1e-3 else r * np.sin(pi * t) * np.sin(pi * t / r) / (pi * pi * t * t))
+    kernels = {
+        'lanczos3': (3.0, lanczos(3.0)),
+        'lanczos5': (5.0, lanczos(5.0)),
+        'gaussian': (1.5, lambda t: 0.0 if t >= 1.5 else np.exp(-t * t / (2.0 * 0.5 * 0.5))),
+        'mitchellcubic': (2.0, lambda t: 0.0 if t >= 2.0 else (
+            (((-7.0 / 18.0) * t + 2.0) * t - 10.0 / 3.0) * t + 16.0 / 9.0 if t >= 1.0 else
+            (((7.0 / 6.0) * t - 2.0) * t) * t + 8.0 / 9.0)),
+    }
+    radius, k = kernels[method]
+    for o in range(n_out):
+        centre = (o + 0.5) * (n_in / n_out)
+        if centre < 0 or centre > n_in:
+            continue
+        first = int(min(max(np.ceil(centre - radius - 0.5), 0), n_in - 1))
+        last = int(min(max(np.floor(centre + radius - 0.5), 0), n_in - 1))
+        w = np.array([k(abs(i + 0.5 - centre)) for i in range(first, last + 1)])
+        if abs(w.sum()) >= 1000.0 * np.finfo(np.float32).tiny:
+            m[o, first:last + 1] = w / w.sum()
+    return m
+
+
 def resize(x, ho, wo, method='bilinear'):
     """keras Resizing(ho, wo, interpolation=method) on NCHW ``x`` -- blocks.py:457-491."""
     if method == 'bilinear':
         return resize_bilinear(x, ho, wo)
+    if method in ('area', 'lanczos3', 'lanczos5', 'gaussian', 'mitchellcubic'):
+        rh = torch.as_tensor(_scale_and_translate_matrix(x.shape[2], ho, method), dtype=x.dtype)
+        rw = torch.as_tensor(_scale_and_translate_matrix(x.shape[3], wo, method), dtype=x.dtype)
+        return torch.einsum('oh,nchw,pw->ncop', rh, x, rw)
     if method not in ('nearest', 'bicubic'):
         raise NotImplementedError(method)
     rh = torch.as_tensor(_resize_matrix(x.shape[2], ho, method), dtype=x.dtype)
@@ -340,10 +386,13 @@ def depthwise_conv2d(x, w, b):
     return F.conv2d(F.pad(x, (pl, pr, pt, pb)), wt, b, groups=c)
 
 
-def convnext_block(p, name, x, filters, activation='gelu', normalization='ln', use_1x1conv=False):
-    """ConvNextBlock.call -- blocks.py:170-184 (drop_path=0: identity, :117-118; layer_scale_init_value=0: no
-    gamma, :166-168).  LayerNormalization(epsilon=1e-6) / BatchNormalization() -- :161-164; any other value of
-    ``normalization`` leaves the layer without ``self.norm`` and the reference's call() fails."""
+def convnext_block(p, name, x, filters, activation='gelu', normalization='ln', use_1x1conv=False, drop_path=0.,
+                   layer_scale_init_value=0):
+    """ConvNextBlock.call -- blocks.py:170-184.  ``layer_scale_init_value`` > 0: trainable per-channel ``gamma``
+    multiplying the branch (:166-169,178-179); ``drop_path`` > 0: DropPath on the branch in training mode
+    (:106-129,183: x / keep_prob * floor(keep_prob + U[0,1)) with one draw per sample -- the mask is supplied like
+    the dropout masks, shape (N,1,1,1)).  LayerNormalization(epsilon=1e-6) / BatchNormalization() -- :161-164; any
+    other value of ``normalization`` leaves the layer without ``self.norm`` and the reference's call() fails."""
     if normalization not in ('bn', 'ln'):
         raise ValueError('ConvNextBlock needs normalization bn or ln')
     c = x.shape[1]
@@ -357,8 +406,12 @@ def convnext_block(p, name, x, filters, activation='gelu', normalization='ln', u
     w2 = p.get(name + '/pwconv2/kernel', (4 * filters, filters))
     b2 = p.get(name + '/pwconv2/bias', (filters,))
     y = torch.einsum('nchw,cd->ndhw', y, w2) + b2.view(1, -1, 1, 1)
+    if layer_scale_init_value > 0:
+        y = p.get(name + '/gamma', (filters,)).view(1, -1, 1, 1) * y
     if use_1x1conv:
         x = _conv(p, name + '/conv1x1', x, filters, k=1)
+    if drop_path and drop_path > 0:
+        y = dropout(p, y, drop_path, 'droppath')
     return x + y
 
 

@@ -71,3 +71,31 @@ def test_net_convnext_pin_bn(cuda):
     m = nets.net_pin('convnext', 2, 0, (24, 24), n_blocks=2, normalization='bn')
     _net_case(cuda, m, lambda p, xs: R.net_pin(p, xs, 'convnext', n_blocks=2, normalization='bn'), 2,
               skip_grads=_zero_bias)
+
+
+def test_convnext_block_layer_scale_and_drop_path(cuda):
+    """ConvNextBlock(drop_path > 0, layer_scale_init_value > 0) -- blocks.py:106-129,166-169,178-183: the trainable
+    per-channel gamma (forward, input gradient and d gamma) and DropPath (one draw per sample, from the Philox
+    generator: the oracle multiplies by the mask the CUDA call produced)."""
+    import numpy as np
+    import torch
+    from dl4ds_b200 import _lib
+    from dl4ds_b200.engine import DROPOUT_KIND, Arena
+    from tests.test_gpu_dropout import gpu_mask, supplier
+
+    fn = lambda c, xs: B.convnext_block(c, 'cnb', xs[0], 16, 'gelu', 'ln', use_1x1conv=True, drop_path=0.3,
+                                        layer_scale_init_value=1e-2)
+
+    def ofn(p, xs):
+        p.dropout_mask = supplier()
+        return R._nhwc(R.convnext_block(p, 'cnb', R._nchw(xs[0]), 16, 'gelu', 'ln', use_1x1conv=True, drop_path=0.3,
+                                        layer_scale_init_value=1e-2))
+    compare(fn, ofn, [(6, 12, 12, 8)], cuda, tol=2e-5, gtol=3e-4)
+    m = gpu_mask((64, 4, 4, 8), 0.3, 'droppath', 5, 1, 1).numpy()
+    assert np.array_equal(m, np.broadcast_to(m[:, :1, :1, :1], m.shape))          # one draw per sample
+    assert set(np.unique(m)).issubset({0.0, np.float32(1 / 0.7)}) and 0.5 < (m[:, 0, 0, 0] > 0).mean() < 0.9
+    # Keras initialises gamma to layer_scale_init_value * ones
+    from dl4ds_b200 import nets
+    from dl4ds_b200.nets import Model
+    mdl = Model('cnb', lambda c, xs: fn(c, xs), [(12, 12, 8)]).to(cuda).init_weights(0)
+    assert np.allclose(mdl.get_weights()['cnb/gamma'], 1e-2)

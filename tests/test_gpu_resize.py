@@ -15,7 +15,8 @@ def _o(fn):
     return w
 
 
-@pytest.mark.parametrize('method', ['nearest', 'bicubic', 'bilinear'])
+@pytest.mark.parametrize('method', ['nearest', 'bicubic', 'bilinear', 'area', 'lanczos3', 'lanczos5', 'gaussian',
+                                    'mitchellcubic'])
 @pytest.mark.parametrize('shape,out', [((2, 8, 8, 3), (16, 16)), ((1, 6, 10, 8), (24, 40)), ((2, 7, 5, 1), (11, 13)),
                                        ((1, 16, 12, 4), (8, 6))])
 def test_resize_op(cuda, method, shape, out):
@@ -23,7 +24,7 @@ def test_resize_op(cuda, method, shape, out):
             _o(lambda p, xs: R.resize(xs[0], out[0], out[1], method)), [shape], cuda)
 
 
-@pytest.mark.parametrize('method', ['nearest', 'bicubic'])
+@pytest.mark.parametrize('method', ['nearest', 'bicubic', 'lanczos3', 'mitchellcubic'])
 def test_resize_conv_block_and_nets(cuda, method):
     compare(lambda c, xs: B.resize_conv_block(c, 'rc', xs[0], 4, 8, method),
             _o(lambda p, xs: R.resize_conv_block(p, 'rc', xs[0], 4, 8, method)), [(2, 8, 8, 8)], cuda)

@@ -28,7 +28,7 @@ def test_nearest_is_replication_at_integer_factors():
     assert np.array_equal(m, np.repeat(np.eye(5), 4, axis=0))
 
 
-@pytest.mark.parametrize('method,pil', [('bicubic', Image.BICUBIC), ('nearest', Image.NEAREST)])
+@pytest.mark.parametrize('method,pil', [('bicubic', Image.BICUBIC), ('nearest', Image.NEAREST), ('lanczos3', Image.LANCZOS)])
 @pytest.mark.parametrize('scale', [2, 4])
 def test_against_pillow(method, pil, scale):
     rng = np.random.default_rng(scale)
@@ -45,7 +45,27 @@ def test_builders_accept_the_methods():
         y = R.net_postupsampling(p, [torch.zeros(1, 8, 8, 1)], 'resnet', 'rc', 2, n_blocks=1, rc_interpolation=method)
         assert dict(m.spec) == dict(p.spec) and tuple(y.shape) == (1, 16, 16, 1)
     with pytest.raises(NotImplementedError):
-        nets.net_postupsampling('resnet', 'rc', 2, 1, 0, (8, 8), rc_interpolation='lanczos3')
+        nets.net_postupsampling('resnet', 'rc', 2, 1, 0, (8, 8), rc_interpolation='spline')
+
+
+def test_scale_and_translate_methods():
+    """area / lanczos3 / lanczos5 / gaussian / mitchellcubic (tf.image.resize without antialiasing): the product's
+    tables (dl4ds_b200/resize_tables.py, float32 like the TF op) against the oracle's float64 statement; rows sum to
+    one; area = replication and OpenCV's INTER_AREA at integer upsampling factors; the reference Mitchell-Netravali
+    values (B = C = 1/3: k(0) = 8/9, k(1) = 1/18)."""
+    import cv2
+    from dl4ds_b200.resize_tables import TAP_METHODS, tf_resize_matrix
+    for method in TAP_METHODS:
+        for n_in, n_out in ((8, 16), (9, 36), (13, 65), (7, 10)):
+            a, b = tf_resize_matrix(n_in, n_out, method), R._scale_and_translate_matrix(n_in, n_out, method)
+            assert np.abs(a - b).max() <= 2e-6, (method, n_in, n_out)
+            assert np.allclose(b.sum(axis=1), 1.0, atol=1e-12)
+    assert np.array_equal(tf_resize_matrix(5, 20, 'area'), np.repeat(np.eye(5, dtype=np.float32), 4, axis=0))
+    x = np.random.default_rng(1).standard_normal((6, 7)).astype(np.float32)
+    got = R.resize(torch.tensor(x)[None, None], 18, 21, 'area')[0, 0].numpy()
+    assert np.array_equal(got, cv2.resize(x, (21, 18), interpolation=cv2.INTER_AREA))
+    m = R._scale_and_translate_matrix(8, 8, 'mitchellcubic')      # identity scale: samples sit on the source centres
+    assert abs(m[4, 4] / m[4, 3] - (8.0 / 9.0) / (1.0 / 18.0)) < 1e-9
 
 
 def test_bilinear_against_opencv_and_pillow():
