@@ -150,10 +150,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     const int lane = threadIdx.x & 31;
     if (p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.stamps[12] = clock64();      // kernel entry
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
-        colsum_s[i] = 0.0f;
-    }
+    pdl_launch_dependents();        // the next kernel of the stream may start its own prologue (common.cuh, PDL)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) colsum_s[i] = 0.0f;
     if (threadIdx.x < kHaloMaxStages) a_uses[threadIdx.x] = 0;
     if (p.ldg)
         for (int i = threadIdx.x; i < p.HWp * p.HHp; i += blockDim.x) {
@@ -183,6 +181,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
+    // ---- everything above touched only shared memory / TMEM; from here on the predecessor's results are needed
+    pdl_wait();
+    const float* const x_g = pdl_after_wait(p.x);               // tensors other kernels of the step produce
+    const float* const res_g = pdl_after_wait(p.res);
+    const float* const mask_g = pdl_after_wait(p.mask_y);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) bias_s[i] = (p.bias && i < p.Cout) ? __ldg(p.bias + i) : 0.0f;
+    __syncthreads();
     if (p.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.stamps[13] = clock64();      // prologue done
 
     if (warp == 0) {
@@ -360,7 +365,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
         float bsum[8];                                  // fused bias gradient: this lane's column of each of its blocks
 #pragma unroll
         for (int i = 0; i < 8; ++i) bsum[i] = 0.0f;
-        const float* __restrict__ mask_y = p.mask_y;
+        const float* __restrict__ mask_y = mask_g;
         int tcount = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tcount) {
             const int ab = tcount & 1;
@@ -369,7 +374,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int oy = ty * BHt + ry, ox = tx * BWt + rx;
             const int64_t pix = ((int64_t)img * p.H + oy) * p.W + ox;
-            const float* __restrict__ resp = p.res ? p.res + pix * p.res_ld : nullptr;
+            const float* __restrict__ resp = res_g ? res_g + pix * p.res_ld : nullptr;
             float* __restrict__ yp = p.y + pix * p.y_ld;
             const int64_t hr_row0 = ((int64_t)img * p.H * r + (int64_t)oy * r) * ((int64_t)p.W * r) + (int64_t)ox * r;
             mbar_wait(smem_u32(&bar_tfull[ab]), (uint32_t)((tcount >> 1) & 1));
@@ -541,7 +546,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             const int trem = tile - img * p.tiles_per_img;
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
-            const float* tbase = p.x + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld;
+            const float* tbase = x_g + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld;
             float4 a[kRegUnits][2];
             if (gw == 0) HSTAMP(tcount * p.nchunks, 0);
             int pix = pix_first, cu = cg_first;
@@ -661,7 +666,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             const int trem = tile - img * p.tiles_per_img;
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
-            const float* tbase = p.x + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld;
+            const float* tbase = x_g + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld;
             // ---- pass 1: absolute maximum of the halo box
             float m = 0.0f;
             for (int u0 = gt; u0 < units_tile; u0 += 512) {
@@ -780,7 +785,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const HaloParams
             const int trem = tile - img * p.tiles_per_img;
             const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
             const int y0 = ty * BHt - p.pad_t, x0 = tx * BWt - p.pad_l;
-            const float* tbase = p.x + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld + sub * 4;
+            const float* tbase = x_g + (((int64_t)img * p.H + y0) * p.W + x0) * p.x_ld + sub * 4;
             for (int c = 0; c < p.nchunks; ++c, ++item) {
                 if ((item & 1) != grp) continue;
                 const int s = item % p.a_stages;
@@ -988,7 +993,7 @@ int conv2d_fwd_tc_halo(const ConvArgs& a, int math_mode, const float* wp_hi, con
                                  (int)(210 * 1024));                                                                 \
             attr_done_ = true;                                                                                       \
         }                                                                                                            \
-        conv_tc_halo_kernel<X3_, ST_, KS_, F16_><<<grid, kHaloThreads, smem, st>>>(*tm, p);                          \
+        launch_pdl(1, conv_tc_halo_kernel<X3_, ST_, KS_, F16_>, dim3(grid), dim3(kHaloThreads), smem, st, *tm, p);      \
     } while (0)
 #define HALO_LAUNCH_K(X3_, ST_, F16_)                                                                                \
     do {                                                                                                             \

@@ -177,6 +177,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     WG2_KSTAMP(0);
+    pdl_launch_dependents();        // programmatic dependent launch: see common.cuh
 
     // role: input-channel group x output-channel block x row group
     const int rg = blockIdx.y % p.nrg;
@@ -237,6 +238,7 @@ conv_tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_smem;
+    pdl_wait();                     // the prologue above used shared memory / TMEM only
     WG2_KSTAMP(1);
 
     if (warp == 0) {
@@ -593,9 +595,9 @@ int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st) {
     }
     dim3 grid((unsigned)splits, (unsigned)nroles);
     if (x3)
-        conv_tc_wgrad2_kernel<true><<<grid, kWg2Threads, smem, st>>>(*tp, *tq, p);
+        launch_pdl(2, conv_tc_wgrad2_kernel<true>, grid, dim3(kWg2Threads), smem, st, *tp, *tq, p);
     else
-        conv_tc_wgrad2_kernel<false><<<grid, kWg2Threads, smem, st>>>(*tp, *tq, p);
+        launch_pdl(2, conv_tc_wgrad2_kernel<false>, grid, dim3(kWg2Threads), smem, st, *tp, *tq, p);
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     return check_launch("conv_tc_wgrad2_kernel");
 }

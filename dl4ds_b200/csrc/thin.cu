@@ -34,7 +34,11 @@ struct ThinWgradArgs {
 };
 
 template <int CA, int CB>
-__global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWgradArgs a) {
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    a.P = pdl_after_wait(a.P);
+    a.Q = pdl_after_wait(a.Q);
     using C = ThinCfg<CA, CB>;
     constexpr int TA = C::TA, TB = C::TB, TPS = C::TPS, SEG = C::SEG;
     extern __shared__ float sm[];
@@ -208,7 +212,7 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
     if (blocks_per_sm > 4) blocks_per_sm = 4;
     int grid = kNumSMs * blocks_per_sm;
     if (grid > a.ntiles) grid = a.ntiles;
-    thin_wgrad_kernel<CA, CB><<<grid, 256, smem, st>>>(a);
+    launch_pdl(8, thin_wgrad_kernel<CA, CB>, dim3(grid), dim3(256), smem, st, a);
     return check_launch("thin_wgrad_kernel");
 }
 
@@ -237,7 +241,11 @@ int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
 // registers; the weights sit in shared memory and are read as warp-uniform broadcasts.
 // -------------------------------------------------------------------------------------------------
 template <int CI, int CO>
-__global__ void __launch_bounds__(256) thin_conv_kernel(const ConvArgs p, int TW, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(256) thin_conv_kernel(ConvArgs p, int TW, int tiles_x, int tiles_y) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    p.x = pdl_after_wait(p.x);
+    p.res = pdl_after_wait(p.res);
     constexpr int TH = 8;
     extern __shared__ float sm[];
     __shared__ __align__(16) float ws[9 * CI * CO];
@@ -387,7 +395,7 @@ static int launch_thin_conv(const ConvArgs& a, cudaStream_t st) {
     const int tiles_x = a.W / TW, tiles_y = (a.H + 7) / 8;
     const int pitch = (TW + 2) * CI + (CI == 8 ? 8 : 1);
     const size_t smem = (size_t)10 * pitch * 4;
-    thin_conv_kernel<CI, CO><<<a.N * tiles_x * tiles_y, 256, smem, st>>>(a, TW, tiles_x, tiles_y);
+    launch_pdl(8, thin_conv_kernel<CI, CO>, dim3(a.N * tiles_x * tiles_y), dim3(256), smem, st, a, TW, tiles_x, tiles_y);
     return check_launch("thin_conv_kernel");
 }
 
@@ -414,7 +422,11 @@ int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
 // loop.  Measured (round 1): 69 us for 48 -> 8 and 103 us for 8 -> 48 over 2^20 pixels (a warp-tile variant
 // staging 32 pixels per warp through shared memory was slower: 181 / 119 us).
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pointwise_conv_kernel(const ConvArgs p, int n_items, int G) {
+__global__ void __launch_bounds__(256) pointwise_conv_kernel(ConvArgs p, int n_items, int G) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    p.x = pdl_after_wait(p.x);
+    p.res = pdl_after_wait(p.res);
     extern __shared__ __align__(16) float psm[];
     const int Cin = p.Cin, Cout = p.Cout;
     float* wsm = psm;                                        // Cin x Cout
@@ -467,7 +479,7 @@ static int launch_pointwise(const ConvArgs& a, cudaStream_t st) {
     if (smem > 48 * 1024) return DL4DS_E_UNSUPPORTED;
     int64_t blocks = (n_items + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
-    pointwise_conv_kernel<<<(int)blocks, 256, smem, st>>>(a, (int)n_items, G);
+    launch_pdl(8, pointwise_conv_kernel, dim3((unsigned)blocks), dim3(256), smem, st, a, (int)n_items, G);
     return check_launch("pointwise_conv_kernel");
 }
 
@@ -497,6 +509,10 @@ constexpr int kPwgTile = 128;
 __global__ void __launch_bounds__(256) pointwise_wgrad_kernel(const float* __restrict__ P, int p_ld,
                                                               const float* __restrict__ Q, int q_ld,
                                                               float* __restrict__ dw, int64_t n_pix, int Ca, int Cb) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    P = pdl_after_wait(P);
+    Q = pdl_after_wait(Q);
     extern __shared__ __align__(16) float wsm[];
     float* ps = wsm;                                         // kPwgTile x Ca
     float* qs = ps + kPwgTile * Ca;                          // kPwgTile x Cb
@@ -558,7 +574,7 @@ int conv2d_wgrad_pointwise(const WgradArgs& w, cudaStream_t st) {
     if (blocks_per_sm > 8) blocks_per_sm = 8;
     int64_t grid = (int64_t)kNumSMs * blocks_per_sm;
     if (grid > ntiles) grid = ntiles;
-    pointwise_wgrad_kernel<<<(int)grid, 256, smem, st>>>(w.P, w.p_ld, w.Q, w.q_ld, w.dw, w.NQ, w.Ca, w.Cb);
+    launch_pdl(8, pointwise_wgrad_kernel, dim3((unsigned)grid), dim3(256), smem, st, w.P, w.p_ld, w.Q, w.q_ld, w.dw, w.NQ, w.Ca, w.Cb);
     return check_launch("pointwise_wgrad_kernel");
 }
 
@@ -571,6 +587,10 @@ __global__ void __launch_bounds__(256) bias_act_bwd_vec4_kernel(
     const float* __restrict__ dy, int dy_ld, const float* __restrict__ y, int y_ld,
     float* __restrict__ dz, int dz_ld, float* __restrict__ dbias,
     int64_t n_pix, int Ho, int Wo, int C, int act, int r) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    dy = pdl_after_wait(dy);
+    y = pdl_after_wait(y);
     __shared__ float4 red[256];
     const int TX = blockDim.x, PY = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -721,7 +741,7 @@ int bias_act_bwd_vec4(const float* dy, int dy_ld, const float* y, int y_ld, floa
     dim3 block(TX, PY);
     int64_t want = (n_pix + PY * 4 - 1) / (PY * 4);
     int grid = (int)(want > 8 * kNumSMs ? 8 * kNumSMs : (want < 1 ? 1 : want));
-#define LAUNCH_V4(K) bias_act_bwd_vec4_kernel<K><<<grid, block, 0, st>>>(dy, dy_ld, y, y_ld, dz, dz_ld, dbias, n_pix, Ho, Wo, C, act, r)
+#define LAUNCH_V4(K) launch_pdl(8, bias_act_bwd_vec4_kernel<K>, dim3(grid), dim3(block), 0, st, dy, dy_ld, y, y_ld, dz, dz_ld, dbias, n_pix, Ho, Wo, C, act, r)
     if (KS == 1) LAUNCH_V4(1);
     else if (KS == 2) LAUNCH_V4(2);
     else LAUNCH_V4(4);

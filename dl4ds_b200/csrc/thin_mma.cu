@@ -37,7 +37,11 @@ __device__ __forceinline__ int px_word(int px, int c) { return px * 8 + ((((c >>
 // TW-pixel-wide tile; warp = one row, 16 pixels per MMA tile.
 // -------------------------------------------------------------------------------------------------
 template <bool X3>
-__global__ void __launch_bounds__(256, 3) thin_conv_mma_kernel(const ConvArgs p, int TW, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(256, 3) thin_conv_mma_kernel(ConvArgs p, int TW, int tiles_x, int tiles_y) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    p.x = pdl_after_wait(p.x);
+    p.res = pdl_after_wait(p.res);
     constexpr int TH = 8;
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -144,9 +148,9 @@ int conv2d_fwd_thin_mma(const ConvArgs& a, int math_mode, cudaStream_t st) {
     const int tiles_x = a.W / TW, tiles_y = (a.H + 7) / 8;
     const size_t smem = (size_t)10 * ((TW + 2) * 8 + 8) * 4;
     if (math_mode == DL4DS_MATH_TF32X3)
-        thin_conv_mma_kernel<true><<<a.N * tiles_x * tiles_y, 256, smem, st>>>(a, TW, tiles_x, tiles_y);
+        launch_pdl(4, thin_conv_mma_kernel<true>, dim3(a.N * tiles_x * tiles_y), dim3(256), smem, st, a, TW, tiles_x, tiles_y);
     else
-        thin_conv_mma_kernel<false><<<a.N * tiles_x * tiles_y, 256, smem, st>>>(a, TW, tiles_x, tiles_y);
+        launch_pdl(4, thin_conv_mma_kernel<false>, dim3(a.N * tiles_x * tiles_y), dim3(256), smem, st, a, TW, tiles_x, tiles_y);
     return check_launch("thin_conv_mma_kernel");
 }
 
@@ -161,6 +165,10 @@ template <bool X3>
 __global__ void __launch_bounds__(256, 2) thin_wgrad_mma_kernel(const float* __restrict__ P, int p_ld, const float* __restrict__ Q,
                                                              int q_ld, float* __restrict__ dw, int N, int H, int W, int pad_t,
                                                              int pad_l, int TW, int tiles_x, int tiles_y) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    P = pdl_after_wait(P);
+    Q = pdl_after_wait(Q);
     constexpr int TH = 8;
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[576];
@@ -297,11 +305,11 @@ int conv2d_wgrad_thin_mma(const WgradArgs& w, int math_mode, cudaStream_t st) {
     const int ntiles = w.N * tiles_x * tiles_y;
     if (grid > ntiles) grid = ntiles;
     if (math_mode == DL4DS_MATH_TF32X3)
-        thin_wgrad_mma_kernel<true><<<grid, 256, smem, st>>>(w.P, w.p_ld, w.Q, w.q_ld, w.dw, w.N, w.Hq, w.Wq, w.pad_t, w.pad_l,
-                                                             TW, tiles_x, tiles_y);
+        launch_pdl(4, thin_wgrad_mma_kernel<true>, dim3(grid), dim3(256), smem, st, w.P, w.p_ld, w.Q, w.q_ld, w.dw, w.N, w.Hq,
+                   w.Wq, w.pad_t, w.pad_l, TW, tiles_x, tiles_y);
     else
-        thin_wgrad_mma_kernel<false><<<grid, 256, smem, st>>>(w.P, w.p_ld, w.Q, w.q_ld, w.dw, w.N, w.Hq, w.Wq, w.pad_t, w.pad_l,
-                                                              TW, tiles_x, tiles_y);
+        launch_pdl(4, thin_wgrad_mma_kernel<false>, dim3(grid), dim3(256), smem, st, w.P, w.p_ld, w.Q, w.q_ld, w.dw, w.N, w.Hq,
+                   w.Wq, w.pad_t, w.pad_l, TW, tiles_x, tiles_y);
     return check_launch("thin_wgrad_mma_kernel");
 }
 
