@@ -247,6 +247,8 @@ class Ctx:
         # Only convolutions whose dz buffer has no later in-place writer qualify (no residual hand-over); the buffers a
         # side-stream kernel reads are kept alive until the join in backward().
         self.wgrad_stream = None
+        self.first_use = {}
+        self.bwd_hooks = {}         # {tape index: callable}: run once backward has executed every entry >= that index
         self._side_keep = []
         self._side_used = False
         self._rng_advanced = False  # dropout: the arena's RNG step is bumped once per Ctx, before the first mask
@@ -341,6 +343,7 @@ class Ctx:
 
     def _p(self, name):
         self.names_used.append(name)
+        self.first_use.setdefault(name, len(self.tape))     # tape position of the op that first reads the parameter
         return self.arena.param(name)
 
     def _g(self, name):
@@ -1395,8 +1398,11 @@ class Ctx:
     def backward(self, keep_tape=False):
         """Run the recorded backward closures.  ``keep_tape`` allows a second pass with other seeds
         (cGAN: D(fake) is differentiated once for the discriminator weights, once for the generator)."""
-        for fn in reversed(self.tape):
-            fn()
+        for i in range(len(self.tape) - 1, -1, -1):
+            self.tape[i]()
+            hook = self.bwd_hooks.get(i)
+            if hook is not None:
+                hook()
         self._join_side()
         if not keep_tape:
             self.tape = []

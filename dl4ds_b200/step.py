@@ -96,6 +96,13 @@ class SupervisedStep:
         d = _dist()
         if d is not None:
             self.world = d.get_world_size()
+        # DL4DS_COMM_BUCKETS=1: two gradient buckets, the upper one all-reduced on a communication stream under the rest
+        # of the backward pass.  Measured on 2 B200 (round 2): 2.119-2.125 ms against 2.126-2.130 ms per step with the
+        # single all-reduce -- what stays exposed is the latency of the LAST collective, not its size -- so the single
+        # all-reduce remains the default.
+        self.comm_stream = (torch.cuda.Stream(device=dev) if self.world > 1 and dev.type == 'cuda' and
+                            os.environ.get('DL4DS_COMM_BUCKETS', '0') == '1' else None)
+        self._early_off = 0
 
     # the recorded work -------------------------------------------------------------------------
     def _fwd_bwd(self, timers=None, plan=None):
@@ -108,8 +115,37 @@ class SupervisedStep:
                                       prepacked=plan.keys if plan is not None else None,
                                       wgrad_stream=self.wgrad_stream)
         ctx.pixel_loss(out, ctx.input(self.target), self.loss_kind, loss_buf=self.loss_buf)
+        self._early_off = 0
+        if self.comm_stream is not None and timers is None:
+            self._arm_early_allreduce(ctx)
         ctx.backward()
         return ctx.launches + 2 + n_pack     # + the two memsets
+
+    def _arm_early_allreduce(self, ctx):
+        """Two gradient buckets: the upper half of the arena (parameters first used late in the forward pass: their
+        gradients are final early in the backward pass) is all-reduced on a communication stream while the backward
+        pass of the lower half still runs; ``_allreduce`` then only has the lower half left."""
+        a = self.arena
+        names = [n for n in a.spec if n in ctx.first_use]
+        split = next((n for n in names if a.offsets[n] >= a.n // 2), None)
+        if split is None or a.offsets[split] == 0:
+            return
+        upper = [n for n in names if a.offsets[n] >= a.offsets[split]]
+        lower = [n for n in names if a.offsets[n] < a.offsets[split]]
+        mark = min(ctx.first_use[n] for n in upper)
+        if lower and max(ctx.first_use[n] for n in lower) >= mark:
+            return          # creation order and first-use order disagree (not the case for the builders): one bucket
+        off = a.offsets[split]
+
+        def hook():
+            main = torch.cuda.current_stream()
+            self.comm_stream.wait_stream(main)
+            if ctx._side_used:
+                self.comm_stream.wait_stream(ctx.wgrad_stream)
+            with torch.cuda.stream(self.comm_stream):
+                allreduce_sum_(a.grad[off:])
+            self._early_off = off
+        ctx.bwd_hooks[mark] = hook
 
     def _opt(self):
         _lib.call('dl4ds_adam_step_dev', self.arena.theta.data_ptr(), self.arena.grad.data_ptr(),
@@ -119,7 +155,14 @@ class SupervisedStep:
         return 1
 
     def _allreduce(self):
-        allreduce_sum_(self.arena.grad)
+        if self.comm_stream is not None and getattr(self, '_early_off', 0) > 0:
+            main = torch.cuda.current_stream()
+            self.comm_stream.wait_stream(main)
+            with torch.cuda.stream(self.comm_stream):
+                allreduce_sum_(self.arena.grad[:self._early_off])
+            main.wait_stream(self.comm_stream)
+        else:
+            allreduce_sum_(self.arena.grad)
 
     def _set_lr_t(self):
         self.arena.t += 1
