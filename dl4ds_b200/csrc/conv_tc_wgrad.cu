@@ -516,7 +516,14 @@ int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st) {
         p.Nb = a.Cb; p.ncob = 1;
         cb_first = a.Cb;
         nmma_max = (a.Cb + 15) & ~15;
-        const int nnb = (rows_g + 255) / 256;
+        // block height (DL4DS_WG2_BR_MAX, default 256).  Smaller blocks would let the A-slot ring turn over inside a
+        // chunk, but every block re-reads the Q^T operand: measured (round 2, 48 -> 48 @ 32x32) 4050 clk per chunk with
+        // two 216-row blocks against 5100 / 6000 clk with four 112-row / five 96-row blocks -- the kernel is bound by
+        // shared-memory operand bandwidth, not by the MMA count
+        static const int br_max = [] { const char* e = getenv("DL4DS_WG2_BR_MAX"); int v = e ? atoi(e) : 256; return v < 64 ? 64 : (v > 256 ? 256 : v); }();
+        int nnb = (rows_g + br_max - 1) / br_max;
+        while (nnb * ((((rows_g + nnb - 1) / nnb) + 15) & ~15) > 512) --nnb;      // accumulators: nnb * BR TMEM columns
+        if (nnb < (rows_g + 255) / 256) nnb = (rows_g + 255) / 256;
         p.BR = ((rows_g + nnb - 1) / nnb + 15) & ~15;
         p.bpr = nnb; p.nrg = 1;
         tmem_need = nnb * p.BR;
@@ -568,6 +575,7 @@ int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st) {
     if (need(2, rst, ast) <= budget) qst = 2;
     if (need(qst, 3, ast) <= budget) rst = 3;
     if (need(qst, rst, 3) <= budget) ast = 3;
+    while (ast < kWg2MaxStages && ast < 2 * p.bpr && need(qst, rst, ast + 1) <= budget) ++ast;     // up to two chunks of blocks
     while (rst < 6 && need(qst, rst + 1, ast) <= budget) ++rst;
     p.qstages = qst; p.rstages = rst; p.astages = ast;
     p.q_base = 0;

@@ -40,6 +40,8 @@ DROPOUT_KIND = {None: 0, 'vanilla': 0, 'mcdrop': 0, 'gaussian': 1, 'mcgaussiandr
 RESIZE_METHOD = {'bilinear': 0, 'nearest': 1, 'bicubic': 2}     # DL4DS_RESIZE_*
 LOSS_ACCUMULATE = 16                                          # DL4DS_LOSS_ACCUMULATE, OR-ed into `kind`
 _PF_HOST = (ctypes.c_float * len(MSSSIM_POWER_FACTORS))(*MSSSIM_POWER_FACTORS)
+_SKIP_WGRAD = os.environ.get('DL4DS_SKIP_WGRAD', '0') == '1'
+
 
 
 def _stream():
@@ -616,6 +618,8 @@ class Ctx:
     def _wgrad(self, P, Q, dw, k, stride, pt, pl, label='wgrad', side=False, then=None, keep=()):
         """``side``: launch on the weight-gradient side stream when one is set (see __init__); ``then``: a callable
         issued right after the wgrad on the same stream (the chain-rule kernels of composed layers)."""
+        if _SKIP_WGRAD:     # timing experiment only (DL4DS_SKIP_WGRAD=1): how long is the step without weight gradients
+            return
         ws_bytes = _lib.load().dl4ds_conv2d_wgrad_workspace_bytes(P.N, Q.H, Q.W, P.C, Q.C, k, k, self.math)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device) if ws_bytes > 0 else None
 
