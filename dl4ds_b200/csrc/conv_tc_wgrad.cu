@@ -526,7 +526,12 @@ int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st) {
         if (nnb < (rows_g + 255) / 256) nnb = (rows_g + 255) / 256;
         p.BR = ((rows_g + nnb - 1) / nnb + 15) & ~15;
         p.bpr = nnb; p.nrg = 1;
-        tmem_need = nnb * p.BR;
+        // one block per CTA role (DL4DS_WG2_SPLIT_ROLES=1): each role then keeps several CHUNKS of its block in the
+        // A-slot ring, so the transposer of chunk i + 1 overlaps the MMAs of chunk i (with all blocks in one role the
+        // slots that fit hold exactly one chunk and the two phases alternate)
+        static const int split_roles = [] { const char* e = getenv("DL4DS_WG2_SPLIT_ROLES"); return e ? atoi(e) : 0; }();
+        if (split_roles && nnb > 1) { p.bpr = 1; p.nrg = nnb; }
+        tmem_need = p.bpr * p.BR;
     } else {
         // A = 128-row blocks of stacked rows, B = Q^T with N = Cb (<= 256 per output-channel role); as many blocks
         // per role as accumulators fit TMEM, the rest goes to further row-group roles
@@ -575,7 +580,7 @@ int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st) {
     if (need(2, rst, ast) <= budget) qst = 2;
     if (need(qst, 3, ast) <= budget) rst = 3;
     if (need(qst, rst, 3) <= budget) ast = 3;
-    while (ast < kWg2MaxStages && ast < 2 * p.bpr && need(qst, rst, ast + 1) <= budget) ++ast;     // up to two chunks of blocks
+    while (ast < kWg2MaxStages && ast < (p.bpr == 1 ? 4 : 2 * p.bpr) && need(qst, rst, ast + 1) <= budget) ++ast;
     while (rst < 6 && need(qst, rst + 1, ast) <= budget) ++rst;
     p.qstages = qst; p.rstages = rst; p.astages = ast;
     p.q_base = 0;

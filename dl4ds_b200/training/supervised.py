@@ -100,7 +100,7 @@ class SupervisedTrainer(Trainer):
         if self.data_on_device and DeviceDataGenerator.supported(
                 getattr(self.data_train, 'values', self.data_train), self.data_train_lr, self.upsampling, self.scale,
                 self.patch_size, self.time_window, self.static_vars, self.predictors_train, self.interpolation):
-            self.ds_train = DeviceDataGenerator(self.data_train, None, device=self.dp.torch_device,
+            self.ds_train = DeviceDataGenerator(self.data_train, self.data_train_lr, device=self.dp.torch_device,
                                                 predictors=self.predictors_train, **p)
         else:
             self.ds_train = DataGenerator(self.data_train, self.data_train_lr, predictors=self.predictors_train, **p)

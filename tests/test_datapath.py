@@ -97,7 +97,8 @@ def test_device_data_generator_domain():
     a = np.zeros((4, 30, 30, 1), np.float32)
     p_hr = [np.zeros((4, 30, 30, 1), np.float32)]
     ok = DeviceDataGenerator.supported
-    assert not ok(a, a, 'spc', 2, None, None, None, None, 'inter_area')         # explicit LR arrays
+    assert not ok(a, a[:, :15, :15], 'spc', 2, 8, None, None, None, 'inter_area')      # explicit LR + post-upsampling patches
+    assert ok(a, a[:, :15, :15], 'spc', 2, None, None, None, None, 'inter_area')      # explicit pairs (MOS)
     assert not ok(a, None, 'spc', 2, 16, None, None, p_hr, 'inter_area')        # post-upsampling patches + predictors (App. B #3)
     assert not ok(a, None, 'spc', 4, 18, None, None, None, 'inter_area')        # patch not divisible by the scale
     assert not ok(a, None, 'spc', 2, 30, None, None, None, 'inter_area')        # crop_array needs patch < grid

@@ -403,3 +403,33 @@ def test_device_data_generator_trains_cfg4_cfg5_shapes(cuda):
             hist.append(tr.fithist.history['loss'])
         np.testing.assert_allclose(hist[0], hist[1], rtol=2e-5)
 
+
+
+@pytest.mark.parametrize('case', [('spc', 4, None, None, 'inter_area', True), ('pin', 4, None, None, 'bicubic', True),
+                                  ('pin', 4, 24, None, 'inter_area', False), ('rc', 4, None, 3, 'inter_area', True)],
+                         ids=lambda c: '-'.join(str(v) for v in c))
+def test_device_data_generator_explicit_lr(cuda, case):
+    """Explicit pairs (`array_lr` given, the MOS case of dataloader.py:108-116,157-222): the LR member is gathered as
+    is (post-upsampling) or interpolated onto the HR grid once (`pin`), against the host DataGenerator."""
+    from dl4ds_b200.dataloader import DataGenerator, DeviceDataGenerator
+    ups, scale, patch, tw, interp, static = case
+    rng = np.random.default_rng(8)
+    n, H, W, C = 12, 48, 64, 2
+    hr = rng.standard_normal((n, H, W, C)).astype(np.float32)
+    lr = rng.standard_normal((n, H // scale, W // scale, C)).astype(np.float32)
+    st = [rng.standard_normal((H, W)).astype(np.float32)] if static else None
+    kw = dict(backbone='resnet', upsampling=ups, scale=scale, batch_size=4, patch_size=patch, time_window=tw,
+              static_vars=st, interpolation=interp)
+    assert DeviceDataGenerator.supported(hr, lr, ups, scale, patch, tw, st, None, interp)
+    np.random.seed(5)
+    host = DataGenerator(hr, lr, **kw)
+    hb = [host[i] for i in range(len(host))]
+    np.random.seed(5)
+    dev = DeviceDataGenerator(hr, lr, device=cuda, **kw)
+    for i in range(len(dev)):
+        din, (hr_d,) = dev[i]
+        hin, (hr_h,) = hb[i]
+        np.testing.assert_array_equal(hr_d, hr_h)
+        for a, b in zip(din, hin):
+            b = np.asarray(b, np.float32).reshape(a.shape)
+            assert np.abs(a - b).max() <= 2e-6 * np.abs(b).max(), np.abs(a - b).max()
