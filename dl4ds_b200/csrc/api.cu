@@ -39,6 +39,7 @@ int64_t dl4ds_tc_launch_count(void) { return g_tc_launches.load(); }
 
 int dl4ds_debug_set_buffer(void* dev_i64) {
     wgrad2_set_debug_buffer(reinterpret_cast<long long*>(dev_i64));
+    wgrad3_set_debug_buffer(reinterpret_cast<long long*>(dev_i64));
     halo_set_debug_buffer(reinterpret_cast<long long*>(dev_i64));
     return DL4DS_OK;
 }
@@ -207,7 +208,9 @@ int dl4ds_conv2d_wgrad(const float* P, int p_ld, const float* Q, int q_ld, float
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
     }
     if (math_mode != DL4DS_MATH_FP32) {
-        int rc = conv2d_wgrad_tc2(a, math_mode, st);
+        int rc = conv2d_wgrad_tc3(a, math_mode, st);
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+        rc = conv2d_wgrad_tc2(a, math_mode, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;
         rc = conv2d_wgrad_tc(a, ws, math_mode, st);
         if (rc != DL4DS_E_UNSUPPORTED) return rc;

@@ -69,7 +69,10 @@ int conv2d_pack_multi(const void* descs_dev, int n, int64_t total_units, cudaStr
 int conv2d_wgrad_tc(const WgradArgs& a, void* ws, int math_mode, cudaStream_t st);
 // conv_tc_wgrad.cu: stacked-taps M=128 kernel (tried first; conv2d_wgrad_tc is the fallback for shapes outside it)
 int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st);
+// conv_tc_wgrad3.cu: kind::f16, MN-major operands straight from the NHWC tiles (tried before conv2d_wgrad_tc2)
+int conv2d_wgrad_tc3(const WgradArgs& a, int math_mode, cudaStream_t st);
 void wgrad2_set_debug_buffer(long long* p);
+void wgrad3_set_debug_buffer(long long* p);
 void halo_set_debug_buffer(long long* p);
 int64_t conv2d_wgrad_tc_workspace(int N, int Hq, int Wq, int Ca, int Cb, int KH, int KW);
 

@@ -382,6 +382,29 @@ def test_wgrad_stacked_taps(cuda, math, shape, cout, k):
     compare(fn, ofn, [shape], cuda, math=math, **TC_TOL[math])
 
 
+@pytest.mark.parametrize('shape,cout,k', [
+    ((3, 32, 32, 48), 48, 3),       # backbone layer: one chunk per image row
+    ((2, 32, 64, 32), 32, 3),       # two chunks per row: the halo columns come from the neighbouring chunk
+    ((1, 64, 128, 40), 32, 3),      # four chunks per row, 24 padding channels per panel
+    ((2, 32, 32, 64), 48, 3),       # full 64-channel panels
+    ((2, 32, 32, 16), 16, 3),       # narrow layer: below the width threshold, conv_tc_wgrad2 serves it
+    ((70, 32, 32, 40), 56, 3),      # 2240 chunks: 16 per CTA, the stage ring wraps; Cb 56 -> 64 columns x 9 taps > 512: wgrad2
+    ((70, 32, 32, 48), 40, 3),      # the same through this kernel: range maxima over many images
+])
+def test_wgrad_mn_major_f16(cuda, shape, cout, k):
+    """conv_tc_wgrad3_kernel (kind::f16, MN-major operands read from the NHWC tiles, per-CTA power-of-two scales)
+    through Ctx.conv's backward against the oracle, at the 3xTF32 bounds; asserts the kernel's domain covers the case."""
+    from dl4ds_b200 import _lib
+    fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=k, act='tanh')
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=k), 'tanh'))
+    compare(fn, ofn, [shape], cuda, math='tf32x3', **TC_TOL['tf32x3'])
+    # activations far outside fp16's comfortable range (what the scales are for); linear layer: no tanh saturation
+    fn2 = lambda c, xs: c.conv(xs[0], 'cv', cout, k=k)
+    ofn2 = _o(lambda p, xs: R._conv(p, 'cv', xs[0], cout, k=k))
+    compare(fn2, ofn2, [shape], cuda, math='tf32x3', scale_inputs=3000.0, **TC_TOL['tf32x3'])
+    compare(fn2, ofn2, [shape], cuda, math='tf32x3', scale_inputs=1e-6, **TC_TOL['tf32x3'])
+
+
 def test_wgrad_stacked_taps_on_concat_slices(cuda):
     """Q (dz) as a channel slice of a wider gradient buffer (pitch 24, 16 channels): the gradient of a
     Concatenate input is a slice of the concat's gradient (dense-block wiring, blocks.py:276)."""
