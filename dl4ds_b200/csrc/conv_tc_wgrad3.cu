@@ -362,6 +362,9 @@ int conv2d_wgrad_tc3(const WgradArgs& a, int math_mode, cudaStream_t st) {
         return DL4DS_E_UNSUPPORTED;
     const int taps = a.KH * a.KW;
     if (taps == 1 || a.KH > 5 || a.KW > 5) return DL4DS_E_UNSUPPORTED;
+    // (Wider layers could be split into channel-group roles -- <= 64 input channels, taps x N <= 512 accumulator columns
+    //  per role; tried in round 2: every role converts the P box again and issues its own taps x 4 MMAs per chunk, the
+    //  48 -> 192 sub-pixel layer took 100 us against 92 us on conv_tc_wgrad2.  Not kept.)
     Wg3Params p;
     p.Npad = (a.Cb + 15) & ~15;
     if (taps * p.Npad > 512) return DL4DS_E_UNSUPPORTED;
