@@ -347,7 +347,29 @@ def run_native(args):
                 traffic = json.load(f).get(label)
         except Exception:
             pass
-        lab_peak = tf32_peak if ':wgrad@' in label else fwd_peak
+        def label_peak(lab):
+            """Dense peak of the MMA kind that serves a launch: kind::f16 for the weight gradients conv_tc_wgrad3 takes
+            (3x3 / 5x5, 32 <= Cin, Cout <= 64, W % 32 == 0, taps * pad16(Cout) <= 512: conv_tc_wgrad3.cu) and, with
+            --math f16x3, for the forward / input-gradient launches; kind::tf32 (half that rate) otherwise."""
+            lay, rest = lab.rsplit(':', 1)
+            pas, hw = rest.split('@')
+            if pas != 'wgrad':
+                return fwd_peak
+            try:
+                w_ = int(hw.split('x')[1])
+                if '*' in lay:
+                    a_, b_ = lay.split('*')
+                    k_, _, cin, _ = model.spec[a_ + '/kernel']
+                    cout = 4 * model.spec[b_ + '/kernel'][3]
+                else:
+                    k_, _, cin, cout = model.spec[lay + '/kernel']
+                taps = k_ * k_
+                if k_ in (3, 5) and 32 <= cin <= 64 and 32 <= cout <= 64 and w_ % 32 == 0 and taps * ((cout + 15) // 16 * 16) <= 512:
+                    return bf16_peak
+            except Exception:
+                pass
+            return tf32_peak
+        lab_peak = label_peak(label)
         roofline = {
             'bound': 'tensor', 'achieved': achieved, 'peak': lab_peak, 'unit': 'TFLOP/s',
             'frac': achieved / lab_peak, 'traffic': traffic,
@@ -361,7 +383,9 @@ def run_native(args):
             'step_executed_tflops': exec_flops_step / (step_ms * 1e-3) / 1e12,
             'note': 'achieved = executed FLOPs of the named launch (2*MACs; tf32x3 issues 2-3 MMAs per MAC on top); '
                     'step_algorithmic_* counts the reference graph (220 GFLOP/step), step_executed_* what the '
-                    'composed sub-pixel x TransitionLast kernels really run',
+                    'composed sub-pixel x TransitionLast kernels really run; `peak` is the dense peak of the MMA kind of the named '
+                    'launch (conv_tc_wgrad3: kind::f16 = the bf16 figure; kind::tf32 = half of it), step_conv_roofline_frac is '
+                    'quoted against the kind::tf32 peak',
             'conv_family_ms_per_step_eager': conv_ms,
             'hbm_peak_gbs': hbm_peak,
         }
@@ -371,14 +395,15 @@ def run_native(args):
         groups = {}
         for k, (ms_k, n_k) in per_label.items():
             pas = k.rsplit(':', 1)[1].split('@')[0]
-            g = 'wgrad (conv_tc_wgrad2_kernel + thin)' if pas == 'wgrad' else 'fwd+dgrad (conv_tc_halo_kernel + thin)'
-            a_ = groups.setdefault(g, [0.0, 0.0, 0])
+            g = 'wgrad (conv_tc_wgrad3 / wgrad2 kernels + thin)' if pas == 'wgrad' else 'fwd+dgrad (conv_tc_halo_kernel + thin)'
+            a_ = groups.setdefault(g, [0.0, 0.0, 0, 0.0])
             a_[0] += ms_k
             a_[1] += 2.0 * macs.get(k, 0) * n_k
             a_[2] += n_k
+            a_[3] += 2.0 * macs.get(k, 0) * n_k / (label_peak(k) * 1e12)      # seconds at the peak of each launch's MMA kind
         roofline['per_function'] = {
             g: {'ms_per_step': v[0], 'launches_per_step': v[2], 'achieved': v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0,
-                'frac': (v[1] / (v[0] * 1e-3) / 1e12) / (tf32_peak if g.startswith('wgrad') else fwd_peak) if v[0] > 0 else 0.0,
+                'frac': v[3] / (v[0] * 1e-3) if v[0] > 0 else 0.0,
                 'share_of_conv_family': v[0] / max(conv_ms, 1e-9)}
             for g, v in groups.items()}
 
