@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(
     const float* __restrict__ dy, int dy_ld, const float* __restrict__ y, int y_ld,
     float* __restrict__ dz, int dz_ld, float* __restrict__ dbias,
     int64_t n_pix, int Ho, int Wo, int C, int act, int r) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     __shared__ float red[256];
     const int TX = blockDim.x, PY = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(
 // -------------------------------------------------------------------------------------------------
 __global__ void add_kernel(const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
                            float* __restrict__ out, int out_ld, int64_t n_pix, int C, int act) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -94,6 +96,7 @@ __global__ void add_kernel(const float* __restrict__ a, int a_ld, const float* _
 
 __global__ void add_vec4_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                 float4* __restrict__ out, int64_t n4, int act) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float4 u = __ldg(a + i), v = __ldg(b + i);
@@ -106,6 +109,7 @@ __global__ void add_vec4_kernel(const float4* __restrict__ a, const float4* __re
 
 __global__ void copy_channels_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst,
                                      int dst_ld, int64_t n_pix, int C, int accumulate) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -120,6 +124,7 @@ __global__ void copy_channels_kernel(const float* __restrict__ src, int src_ld, 
 __global__ void copy_channels_vec4_kernel(const float* __restrict__ src, int src_ld,
                                           float* __restrict__ dst, int dst_ld, int64_t n_pix, int C4,
                                           int accumulate) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * C4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -137,6 +142,7 @@ __global__ void copy_channels_vec4_kernel(const float* __restrict__ src, int src
 
 __global__ void act_fwd_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y, int y_ld,
                                int64_t n_pix, int C, int act) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -148,6 +154,7 @@ __global__ void act_fwd_kernel(const float* __restrict__ x, int x_ld, float* __r
 
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b,
                            float* __restrict__ out, int64_t n) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
         out[i] = a[i] * b[i];
@@ -155,6 +162,7 @@ __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict_
 
 __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y,
                              int64_t n) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
         y[i] = a * x[i] + (b == 0.0f ? 0.0f : b * y[i]);
@@ -170,6 +178,7 @@ template <int KS, bool kMulB>
 __global__ void __launch_bounds__(256) group_sum_kernel(
     const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
     float* __restrict__ out, int64_t ppg, int inner, int C) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     __shared__ float red[256];
     const int TX = blockDim.x, PY = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -210,6 +219,7 @@ __global__ void __launch_bounds__(256) group_sum_kernel(
 __global__ void group_scale_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
                                    int y_ld, const float* __restrict__ s, const float* __restrict__ dm,
                                    float inv, int64_t n_pix, int64_t ppg, int inner, int C, int mode) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * C;
     const int64_t span = ppg * inner;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -231,6 +241,7 @@ __global__ void group_scale_kernel(const float* __restrict__ x, int x_ld, float*
 __global__ void __launch_bounds__(256) group_scale_vec4_kernel(
     const float* __restrict__ x, int x_ld, float* __restrict__ y, int y_ld, const float* __restrict__ s,
     const float* __restrict__ dm, float inv, int n_items, int ppg, int inner, int C, int mode) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int G = C >> 2;
     const int span = ppg * inner;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n_items; i += gridDim.x * 256) {
@@ -255,6 +266,7 @@ template <bool kMulB>
 __global__ void __launch_bounds__(256) group_sum_vec4_kernel(
     const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
     float* __restrict__ out, int ppg, int C) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     __shared__ float4 red[256];
     const int TX = blockDim.x, PY = blockDim.y;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -308,6 +320,7 @@ __global__ void attention_mlp_fwd_kernel(const float* __restrict__ pooled, float
                                          const float* __restrict__ w2, const float* __restrict__ b2,
                                          float* __restrict__ hidden, float* __restrict__ scale,
                                          int n_groups, int C, int Cr) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int g = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x % 32;
     if (g >= n_groups) return;
@@ -332,6 +345,7 @@ __global__ void attention_mlp_bwd_kernel(const float* __restrict__ pooled, float
                                          float* __restrict__ dsum, float* __restrict__ dw1,
                                          float* __restrict__ db1, float* __restrict__ dw2,
                                          float* __restrict__ db2, int n_groups, int C, int Cr) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     extern __shared__ float sm[];   // per warp: dsig[C] + dhid[Cr]
     const int wib = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int g = blockIdx.x * (blockDim.x / 32) + wib;
@@ -379,6 +393,7 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const float* __restrict
                                                          float* __restrict__ loss_out,
                                                          float* __restrict__ dy, int64_t n, int kind,
                                                          float scale, int accumulate) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     __shared__ float red[8];
     const float invn = 1.0f / (float)n;
     float acc = 0.0f;
@@ -413,6 +428,7 @@ __global__ void __launch_bounds__(256) pixel_loss_kernel(const float* __restrict
 // -mean(t*log(p+eps) + (1-t)*log(1-p+eps)), eps = 1e-7
 __global__ void bce_loss_kernel(const float* __restrict__ p, float target, float* __restrict__ loss_out,
                                 float* __restrict__ dp, int64_t n, float scale, int accumulate) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const float eps = 1e-7f;
     const float invn = 1.0f / (float)n;
     float acc = 0.0f;
@@ -445,6 +461,7 @@ __global__ void bce_loss_kernel(const float* __restrict__ p, float target, float
 __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ grad,
                             float* __restrict__ m, float* __restrict__ v, int64_t n, float lr_t,
                             float b1, float b2, float eps, float gscale) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float g = grad[i] * gscale;
@@ -461,6 +478,7 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
 // -------------------------------------------------------------------------------------------------
 __global__ void channel_scale_fwd_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ gamma,
                                          float* __restrict__ y, int y_ld, int64_t n_pix, int C) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = i / C;
@@ -475,6 +493,7 @@ __global__ void __launch_bounds__(256) channel_scale_bwd_kernel(const float* __r
                                                                 const float* __restrict__ gamma, float* __restrict__ dx,
                                                                 int dx_ld, float* __restrict__ dgamma, int64_t n_pix,
                                                                 int C, int cp) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     __shared__ float red[256];
     const int c = threadIdx.x % cp, lane = threadIdx.x / cp, lanes = 256 / cp;
     float acc = 0.0f;
@@ -504,6 +523,7 @@ __global__ void resample_taps_kernel(const float* __restrict__ x, float* __restr
                                      int Ho, int Wo, const int* __restrict__ iy, const float* __restrict__ wy, int Ky,
                                      const int* __restrict__ ix, const float* __restrict__ wx, int Kx, int y_ld,
                                      int y_coff) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)N * Ho * Wo * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -536,6 +556,7 @@ __global__ void resample_taps_kernel(const float* __restrict__ x, float* __restr
 // -------------------------------------------------------------------------------------------------
 __global__ void avgpool_coarsen_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H,
                                        int W, int C, int s) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int Ho = H / s, Wo = W / s;
     const int64_t total = (int64_t)N * Ho * Wo * C;
     const int area = s * s;
@@ -634,6 +655,7 @@ __device__ __forceinline__ Taps resize_taps(int o, int in, int out, int method) 
 // fwd: y[o] = sum w x[taps];  bwd (transpose = 1): scatter g * w onto dx with atomics
 __global__ void resize_taps_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_ld,
                                    int N, int H, int W, int C, int Ho, int Wo, int method, int transpose) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)N * Ho * Wo * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -667,6 +689,7 @@ __global__ void resize_taps_kernel(const float* __restrict__ src, int src_ld, fl
 
 __global__ void resize_bilinear_fwd_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y,
                                            int y_ld, int N, int H, int W, int C, int Ho, int Wo) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)N * Ho * Wo * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -688,6 +711,7 @@ __global__ void resize_bilinear_fwd_kernel(const float* __restrict__ x, int x_ld
 
 __global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dy, int dy_ld, float* __restrict__ dx,
                                            int dx_ld, int N, int H, int W, int C, int Ho, int Wo) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)N * Ho * Wo * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -713,6 +737,7 @@ __global__ void resize_bilinear_bwd_kernel(const float* __restrict__ dy, int dy_
 // -------------------------------------------------------------------------------------------------
 __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y, int y_ld,
                                     int N, int H, int W, int C) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int Ho = H / 2, Wo = W / 2;
     const int64_t total = (int64_t)N * Ho * Wo * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -733,6 +758,7 @@ __global__ void maxpool2_fwd_kernel(const float* __restrict__ x, int x_ld, float
 __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ dy,
                                     int dy_ld, float* __restrict__ dx, int dx_ld, int N, int H, int W,
                                     int C) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int Ho = H / 2, Wo = W / 2;
     const int64_t total = (int64_t)N * H * W * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -766,6 +792,7 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, int x_ld, const
 __global__ void local_conv_fwd_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ w,
                                       const float* __restrict__ b, float* __restrict__ y, int y_ld,
                                       int N, int64_t HW, int Cin, int F) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)N * HW * F;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -783,6 +810,7 @@ __global__ void local_conv_bwd_kernel(const float* __restrict__ x, int x_ld, con
                                       int dy_ld, const float* __restrict__ w, float* __restrict__ dx,
                                       int dx_ld, float* __restrict__ dw, float* __restrict__ db, int N,
                                       int64_t HW, int Cin, int F) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = HW * Cin;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -824,6 +852,7 @@ __device__ __forceinline__ float hard_sigmoid_grad(float x) {
 __global__ void convlstm_gates_fwd_kernel(const float* __restrict__ z, const float* __restrict__ c_prev,
                                           float* __restrict__ c, float* __restrict__ h, int h_ld,
                                           float* __restrict__ gates, int64_t n_pix, int F) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * F;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -847,6 +876,7 @@ __global__ void convlstm_gates_bwd_kernel(const float* __restrict__ gates, const
                                           int dh_ld, const float* __restrict__ dc_next,
                                           float* __restrict__ dz, float* __restrict__ dc_prev,
                                           int64_t n_pix, int F) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = n_pix * F;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -876,6 +906,7 @@ __global__ void adam_dev_kernel(float* __restrict__ theta, const float* __restri
                                 float* __restrict__ m, float* __restrict__ v, int64_t n,
                                 const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
                                 float gscale) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const float lr_t = __ldg(lr_t_dev);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -890,6 +921,7 @@ __global__ void adam_dev_kernel(float* __restrict__ theta, const float* __restri
 // dst[b][a][:] = src[a][b][:]  (frame = contiguous run of `fe` floats, fe % 4 == 0 -> float4 path)
 __global__ void permute_frames_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int B,
                                       int64_t fe) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)A * B * fe;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -903,6 +935,7 @@ __global__ void permute_frames_kernel(const float* __restrict__ src, float* __re
 // zero-pad bottom/right: dst (N,Hd,Wd,C) <- src (N,Hs,Ws,C);  crop=1 is the adjoint (dst <- src window)
 __global__ void pad_br_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_ld,
                               int N, int Hs, int Ws, int Hd, int Wd, int C) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)N * Hd * Wd * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -944,6 +977,7 @@ static void pick_xy(int C, int& TX, int& KS) {
 __global__ void spc_compose_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
                                    const float* __restrict__ w2, const float* __restrict__ b2,
                                    float* __restrict__ weff, float* __restrict__ beff, int rows, int Cm, int Co, int R2) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int ne = R2 * Co;
     const int total = (rows + 1) * ne;                       // row == rows: the bias row
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -961,6 +995,7 @@ __global__ void spc_compose_kernel(const float* __restrict__ w1, const float* __
 __global__ void spc_chain_w1_kernel(const float* __restrict__ dweff, const float* __restrict__ dbeff,
                                     const float* __restrict__ w2, float* __restrict__ gw1, float* __restrict__ gb1,
                                     int rows, int Cm, int Co, int R2) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int n1 = R2 * Cm, ne = R2 * Co;
     const int total = (rows + 1) * n1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -980,6 +1015,7 @@ __global__ void __launch_bounds__(256) spc_chain_w2_kernel(const float* __restri
                                                            const float* __restrict__ dweff, const float* __restrict__ dbeff,
                                                            float* __restrict__ gw2, float* __restrict__ gb2,
                                                            int rows, int Cm, int Co, int R2) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     __shared__ float red[8];
     const int c = blockIdx.x / Co, co = blockIdx.x - c * Co;
     const int n1 = R2 * Cm, ne = R2 * Co;
@@ -1014,6 +1050,7 @@ __global__ void __launch_bounds__(256) spc_chain_w2_kernel(const float* __restri
 __global__ void gather_crop_kernel(const float* __restrict__ src, const int* __restrict__ idx,
                                    const int* __restrict__ y0, const int* __restrict__ x0, float* __restrict__ dst,
                                    int n, int H, int W, int C, int ph, int pw, int dst_ld, int dst_coff) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int64_t total = (int64_t)n * ph * pw * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -1038,6 +1075,7 @@ __global__ void gather_crop_kernel(const float* __restrict__ src, const int* __r
 // -------------------------------------------------------------------------------------------------
 __global__ void convt_rearrange_kernel(float* __restrict__ w, float* __restrict__ wp, int k, int s, int pad, int off_min,
                                        int Kp, int Co, int Ci, int backward) {
+    pdl_launch_dependents();    // lets a PDL-launched successor start its prologue (common.cuh); this kernel itself is launched normally
     const int ne = s * s * Co;
     const int64_t total = (int64_t)Kp * Kp * Ci * ne;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
