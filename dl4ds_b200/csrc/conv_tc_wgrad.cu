@@ -482,7 +482,7 @@ int conv2d_wgrad_tc2(const WgradArgs& a, int math_mode, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(a.P) & 15) || (reinterpret_cast<uintptr_t>(a.Q) & 15) ||
         (reinterpret_cast<uintptr_t>(a.dw) & 15))
         return DL4DS_E_UNSUPPORTED;
-    if (a.KH > 5 || a.KW > 5) return DL4DS_E_UNSUPPORTED;
+    if (a.KH > 7 || a.KW > 7) return DL4DS_E_UNSUPPORTED;      // (7x7: the ConvNeXt stem / tail, validated in round 2)
     if (a.KH * a.KW == 1) return DL4DS_E_UNSUPPORTED;     // 1x1: a handful of stacked rows -- the first-generation kernel is faster (measured)
     const bool x3 = math_mode == DL4DS_MATH_TF32X3;
     Wg2Params p;

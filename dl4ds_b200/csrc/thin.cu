@@ -3,7 +3,7 @@
 // cannot feed a 128 x N tensor-core tile (Cout 1 / 8) and are bandwidth-bound anyway, so they get
 // CUDA-core kernels built around data reuse in shared memory and registers:
 //
-//   thin_wgrad_kernel<CA,CB>  3x3 stride-1 weight gradient for Ca, Cb in {1, 8}: an (rows x cols)
+//   thin_wgrad_kernel<CA,CB,KS>  3x3 (and 7x7: one kernel row per thread) stride-1 weight gradient for Ca, Cb in {1, 8}: an (rows x cols)
 //       tile of P (with halo) and Q lives in shared memory; a thread owns a TA x TB block of
 //       (ca, cb) pairs for ALL nine taps (9*TA*TB accumulators) and walks 32 pixels of one row with
 //       a 3x3 sliding register window, i.e. 4 shared loads per 72 FMAs for Ca = Cb = 8.
@@ -16,11 +16,16 @@ namespace dl4ds {
 // -------------------------------------------------------------------------------------------------
 // thin 3x3 wgrad
 // -------------------------------------------------------------------------------------------------
-template <int CA, int CB>
+template <int CA, int CB, int KS>
 struct ThinCfg {
-    static constexpr int TA = CA >= 2 ? 2 : 1;
-    static constexpr int TB = CB >= 4 ? 4 : 1;
-    static constexpr int TPS = (CA / TA) * (CB / TB);      // threads per pixel stream
+    // 3x3: a thread owns a 2 x 4 block of (ca, cb) pairs for all nine taps.  7x7 (the ConvNeXt stem / tail, never
+    // 8 x 8 channels): a thread owns ONE kernel row, all seven taps of it and every (ca, cb) pair.
+    static constexpr int TA = KS == 3 ? (CA >= 2 ? 2 : 1) : CA;
+    static constexpr int TB = KS == 3 ? (CB >= 4 ? 4 : 1) : CB;
+    static constexpr int KHT = KS == 3 ? 3 : 1;             // kernel rows per thread
+    static constexpr int KG = KS / KHT;                     // kernel-row groups
+    static constexpr int CPS = (CA / TA) * (CB / TB);       // channel-block threads per kernel-row group
+    static constexpr int TPS = CPS * KG;                    // threads per pixel stream
     static constexpr int STREAMS = 256 / TPS;
     static constexpr int SEG = 32;                          // pixels per stream per tile (16 measured slower for 8x8)
 };
@@ -33,37 +38,55 @@ struct ThinWgradArgs {
     int p_pitch, q_pitch;       // shared-memory row pitches in floats
 };
 
-template <int CA, int CB>
+template <int N>
+__device__ __forceinline__ void lds_vec(const float* src, float (&out)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(src + i);
+            out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; out[i + 3] = v.w;
+        }
+    } else if constexpr (N == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(src);
+        out[0] = v.x; out[1] = v.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = src[i];
+    }
+}
+
+template <int CA, int CB, int KS>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
     pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
     pdl_wait();
     a.P = pdl_after_wait(a.P);
     a.Q = pdl_after_wait(a.Q);
-    using C = ThinCfg<CA, CB>;
-    constexpr int TA = C::TA, TB = C::TB, TPS = C::TPS, SEG = C::SEG;
+    using C = ThinCfg<CA, CB, KS>;
+    constexpr int TA = C::TA, TB = C::TB, TPS = C::TPS, SEG = C::SEG, KHT = C::KHT, HALO = KS - 1;
     extern __shared__ float sm[];
-    float* Ps = sm;                                          // (TH+2) rows x p_pitch
-    float* Qs = sm + (((size_t)(a.TH + 2) * a.p_pitch + 3) & ~(size_t)3);   // TH rows x q_pitch (16-byte aligned)
-    __shared__ float red[9 * CA * CB];
+    float* Ps = sm;                                          // (TH+HALO) rows x p_pitch
+    float* Qs = sm + (((size_t)(a.TH + HALO) * a.p_pitch + 3) & ~(size_t)3);   // TH rows x q_pitch (16-byte aligned)
+    __shared__ float red[KS * KS * CA * CB];
 
     const int tid = threadIdx.x;
     const int stream = tid / TPS, sub = tid % TPS;
-    const int ca0 = (sub / (CB / TB)) * TA, cb0 = (sub % (CB / TB)) * TB;
+    const int kh0 = (sub / C::CPS) * KHT, csub = sub % C::CPS;
+    const int ca0 = (csub / (CB / TB)) * TA, cb0 = (csub % (CB / TB)) * TB;
     const int segs = a.TW / SEG;
     // consecutive streams = consecutive rows (row pitches are chosen so that they hit distinct banks)
     const int srow = stream % a.TH, sseg = stream / a.TH;
     const bool active = sseg < segs;
 
-    float acc[3][3][TA][TB];
+    float acc[KHT][KS][TA][TB];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < KHT; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < KS; ++j)
 #pragma unroll
             for (int u = 0; u < TA; ++u)
 #pragma unroll
                 for (int v = 0; v < TB; ++v) acc[i][j][u][v] = 0.0f;
-    for (int i = tid; i < 9 * CA * CB; i += 256) red[i] = 0.0f;
+    for (int i = tid; i < KS * KS * CA * CB; i += 256) red[i] = 0.0f;
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int img = tile / (a.tiles_x * a.tiles_y);
@@ -71,9 +94,9 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
         const int ty = trem / a.tiles_x, tx = trem - ty * a.tiles_x;
         const int y0 = ty * a.TH, x0 = tx * a.TW;
         __syncthreads();       // previous tile fully consumed
-        // ---- P tile with halo: rows y0-pad_t .. +TH+2, cols x0-pad_l .. +TW+2, CA channels
+        // ---- P tile with halo: rows y0-pad_t .. +TH+HALO, cols x0-pad_l .. +TW+HALO, CA channels
         {
-            const int cols = a.TW + 2, rows = a.TH + 2;
+            const int cols = a.TW + HALO, rows = a.TH + HALO;
             if constexpr (CA % 4 == 0) {
                 const int v4 = CA / 4, total = rows * cols * v4;
                 for (int i = tid; i < total; i += 256) {
@@ -115,48 +138,34 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
         }
         __syncthreads();
         if (active) {
-            // window win[kh][kw][ta] = P at (row srow+kh, col x+kw) in halo coordinates
-            float win[3][3][TA];
+            // window win[kh][kw][ta] = P at (row srow+kh0+kh, col x+kw) in halo coordinates
+            float win[KHT][KS][TA];
             const int xs = sseg * SEG;
-            const float* prow[3];
+            const float* prow[KHT];
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) prow[kh] = Ps + (size_t)(srow + kh) * a.p_pitch + ca0;
+            for (int kh = 0; kh < KHT; ++kh) prow[kh] = Ps + (size_t)(srow + kh0 + kh) * a.p_pitch + ca0;
             const float* qrow = Qs + (size_t)srow * a.q_pitch + cb0;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+            for (int kh = 0; kh < KHT; ++kh)
 #pragma unroll
-                for (int kw = 1; kw < 3; ++kw)
-#pragma unroll
-                    for (int u = 0; u < TA; ++u) win[kh][kw][u] = prow[kh][(xs + kw - 1) * CA + u];
+                for (int kw = 1; kw < KS; ++kw) lds_vec<TA>(prow[kh] + (xs + kw - 1) * CA, win[kh][kw]);
 #pragma unroll 4
             for (int x = xs; x < xs + SEG; ++x) {
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
+                for (int kh = 0; kh < KHT; ++kh) {
 #pragma unroll
-                    for (int u = 0; u < TA; ++u) {
-                        win[kh][0][u] = win[kh][1][u];
-                        win[kh][1][u] = win[kh][2][u];
-                    }
-                    if (TA == 2) {
-                        const float2 v = *reinterpret_cast<const float2*>(prow[kh] + (x + 2) * CA);
-                        win[kh][2][0] = v.x;
-                        win[kh][2][TA - 1] = v.y;
-                    } else {
-                        win[kh][2][0] = prow[kh][(x + 2) * CA];
-                    }
+                    for (int kw = 0; kw < KS - 1; ++kw)
+#pragma unroll
+                        for (int u = 0; u < TA; ++u) win[kh][kw][u] = win[kh][kw + 1][u];
+                    lds_vec<TA>(prow[kh] + (x + KS - 1) * CA, win[kh][KS - 1]);
                 }
                 float q[TB];
-                if (TB == 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(qrow + x * CB);
-                    q[0] = v.x; q[TB > 1 ? 1 : 0] = v.y; q[TB > 2 ? 2 : 0] = v.z; q[TB > 3 ? 3 : 0] = v.w;
-                } else {
-                    q[0] = qrow[x * CB];
-                }
+                lds_vec<TB>(qrow + x * CB, q);
                 // (packed FFMA2 was tried here: 74 -> 102 us, the register pairs cost more moves than they save)
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
+                for (int kh = 0; kh < KHT; ++kh)
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw)
+                    for (int kw = 0; kw < KS; ++kw)
 #pragma unroll
                         for (int u = 0; u < TA; ++u)
 #pragma unroll
@@ -167,22 +176,25 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
     }
     // ---- block reduction (shared atomics) then one global atomic per weight
     __syncthreads();
+    if (stream < C::STREAMS) {
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+        for (int kh = 0; kh < KHT; ++kh)
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
+            for (int kw = 0; kw < KS; ++kw)
 #pragma unroll
-            for (int u = 0; u < TA; ++u)
+                for (int u = 0; u < TA; ++u)
 #pragma unroll
-                for (int v = 0; v < TB; ++v)
-                    atomicAdd(&red[((kh * 3 + kw) * CA + ca0 + u) * CB + cb0 + v], acc[kh][kw][u][v]);
+                    for (int v = 0; v < TB; ++v)
+                        atomicAdd(&red[(((kh0 + kh) * KS + kw) * CA + ca0 + u) * CB + cb0 + v], acc[kh][kw][u][v]);
+    }
     __syncthreads();
-    for (int i = tid; i < 9 * CA * CB; i += 256) atomicAdd(a.dw + i, red[i]);
+    for (int i = tid; i < KS * KS * CA * CB; i += 256) atomicAdd(a.dw + i, red[i]);
 }
 
-template <int CA, int CB>
+template <int CA, int CB, int KS>
 static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
-    using C = ThinCfg<CA, CB>;
+    using C = ThinCfg<CA, CB, KS>;
+    constexpr int HALO = KS - 1;
     const int segs = a.TW / C::SEG;
     int th = C::STREAMS / segs;
     if (th > 16) th = 16;          // >= 512 tiles for the 1-channel cases (r01b: 128 blocks of 64-row tiles, 74 us)
@@ -190,8 +202,8 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
     while (th > 1 && a.H % th) --th;
     // shared-memory budget: shrink the tile height until both tiles fit in ~96 KB
     auto bytes = [&](int t) {
-        const int pp = ((a.TW + 2) * CA + 31) / 32 * 32 + CA, qp = (a.TW * CB + 31) / 32 * 32 + CB;
-        return (size_t)((((t + 2) * pp + 3) & ~3) + t * qp) * 4;
+        const int pp = ((a.TW + HALO) * CA + 31) / 32 * 32 + CA, qp = (a.TW * CB + 31) / 32 * 32 + CB;
+        return (size_t)((((t + HALO) * pp + 3) & ~3) + t * qp) * 4;
     };
     while (th > 1 && bytes(th) > 96 * 1024) { --th; while (th > 1 && a.H % th) --th; }
     a.TH = th;
@@ -199,12 +211,12 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
     a.tiles_y = a.H / th;
     a.ntiles = a.N * a.tiles_x * a.tiles_y;
     // row pitch = CA (mod 32) floats: consecutive rows land on consecutive bank groups
-    a.p_pitch = ((a.TW + 2) * CA + 31) / 32 * 32 + CA;
+    a.p_pitch = ((a.TW + HALO) * CA + 31) / 32 * 32 + CA;
     a.q_pitch = (a.TW * CB + 31) / 32 * 32 + CB;
     const size_t smem = bytes(th);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(thin_wgrad_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(thin_wgrad_kernel<CA, CB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         attr = true;
     }
     int blocks_per_sm = (int)((200 * 1024) / (smem + 4096));
@@ -212,14 +224,16 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
     if (blocks_per_sm > 4) blocks_per_sm = 4;
     int grid = kNumSMs * blocks_per_sm;
     if (grid > a.ntiles) grid = a.ntiles;
-    launch_pdl(8, thin_wgrad_kernel<CA, CB>, dim3(grid), dim3(256), smem, st, a);
+    launch_pdl(8, thin_wgrad_kernel<CA, CB, KS>, dim3(grid), dim3(256), smem, st, a);
     return check_launch("thin_wgrad_kernel");
 }
 
 // DL4DS_E_UNSUPPORTED when the shape is outside this kernel's domain
 int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
-    if (w.KH != 3 || w.KW != 3 || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
+    const bool k3 = w.KH == 3 && w.KW == 3, k7 = w.KH == 7 && w.KW == 7;
+    if (!(k3 || k7) || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
     if (!((w.Ca == 1 || w.Ca == 8) && (w.Cb == 1 || w.Cb == 8))) return DL4DS_E_UNSUPPORTED;
+    if (k7 && w.Ca == 8 && w.Cb == 8) return DL4DS_E_UNSUPPORTED;       // tensor-core kernels (conv_tc_wgrad2)
     if (w.Wq % 32 || (w.Wq > 128 && w.Wq % 128)) return DL4DS_E_UNSUPPORTED;
     if (w.Ca == 8 && (w.p_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15))) return DL4DS_E_UNSUPPORTED;
     if (w.Cb == 8 && (w.q_ld % 4 || (reinterpret_cast<uintptr_t>(w.Q) & 15))) return DL4DS_E_UNSUPPORTED;
@@ -228,10 +242,15 @@ int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
     a.P = w.P; a.Q = w.Q; a.dw = w.dw; a.p_ld = w.p_ld; a.q_ld = w.q_ld;
     a.N = w.N; a.H = w.Hq; a.W = w.Wq; a.pad_t = w.pad_t; a.pad_l = w.pad_l;
     a.TW = w.Wq > 128 ? 128 : w.Wq;
-    if (w.Ca == 8 && w.Cb == 8) return launch_thin<8, 8>(a, st);
-    if (w.Ca == 8 && w.Cb == 1) return launch_thin<8, 1>(a, st);
-    if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8>(a, st);
-    return launch_thin<1, 1>(a, st);
+    if (k7) {
+        if (w.Ca == 8 && w.Cb == 1) return launch_thin<8, 1, 7>(a, st);
+        if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8, 7>(a, st);
+        return launch_thin<1, 1, 7>(a, st);
+    }
+    if (w.Ca == 8 && w.Cb == 8) return launch_thin<8, 8, 3>(a, st);
+    if (w.Ca == 8 && w.Cb == 1) return launch_thin<8, 1, 3>(a, st);
+    if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8, 3>(a, st);
+    return launch_thin<1, 1, 3>(a, st);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -240,21 +259,21 @@ int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
 // shared-memory access of a warp touches 32 consecutive pixels: conflict-free), all Cout outputs in
 // registers; the weights sit in shared memory and are read as warp-uniform broadcasts.
 // -------------------------------------------------------------------------------------------------
-template <int CI, int CO>
+template <int CI, int CO, int KS>
 __global__ void __launch_bounds__(256) thin_conv_kernel(ConvArgs p, int TW, int tiles_x, int tiles_y) {
     pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
     pdl_wait();
     p.x = pdl_after_wait(p.x);
     p.res = pdl_after_wait(p.res);
-    constexpr int TH = 8;
+    constexpr int TH = 8, HALO = KS - 1, TAPS = KS * KS;
     extern __shared__ float sm[];
-    __shared__ __align__(16) float ws[9 * CI * CO];
+    __shared__ __align__(16) float ws[TAPS * CI * CO];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pitch = (TW + 2) * CI + (CI == 8 ? 8 : 1);      // row pitch (floats), rows land on distinct banks
-    for (int i = tid; i < 9 * CI * CO; i += 256) {
+    const int pitch = (TW + HALO) * CI + (CI == 8 ? 8 : 1);   // row pitch (floats), rows land on distinct banks
+    for (int i = tid; i < TAPS * CI * CO; i += 256) {
         const int co = i % CO, ci = (i / CO) % CI, tap = i / (CO * CI);
         ws[i] = (p.wmode == DL4DS_W_HWIO) ? __ldg(p.w + (tap * CI + ci) * CO + co)
-                                           : __ldg(p.w + ((8 - tap) * CO + co) * CI + ci);
+                                           : __ldg(p.w + ((TAPS - 1 - tap) * CO + co) * CI + ci);
     }
     const int tile = blockIdx.x;
     const int img = tile / (tiles_x * tiles_y);
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(256) thin_conv_kernel(ConvArgs p, int TW, int 
     const int y0 = ty * TH, x0 = tx * TW;
     // ---- input tile with halo
     {
-        const int cols = TW + 2, rows = TH + 2;
+        const int cols = TW + HALO, rows = TH + HALO;
         if constexpr (CI % 4 == 0) {
             const int v4 = CI / 4, total = rows * cols * v4;
             for (int i = tid; i < total; i += 256) {
@@ -298,11 +317,11 @@ __global__ void __launch_bounds__(256) thin_conv_kernel(ConvArgs p, int TW, int 
 #pragma unroll
         for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
+    for (int kh = 0; kh < KS; ++kh) {
         const float* row = sm + (size_t)(warp + kh) * pitch + lane * CI;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const float* wt = ws + (kh * 3 + kw) * CI * CO;
+        for (int kw = 0; kw < KS; ++kw) {
+            const float* wt = ws + (kh * KS + kw) * CI * CO;
             if constexpr (CI == 8) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {                 // 4 input channels at a time
@@ -389,28 +408,42 @@ __global__ void __launch_bounds__(256) thin_conv_kernel(ConvArgs p, int TW, int 
     }
 }
 
-template <int CI, int CO>
+template <int CI, int CO, int KS>
 static int launch_thin_conv(const ConvArgs& a, cudaStream_t st) {
     const int TW = a.W > 128 ? 128 : a.W;
     const int tiles_x = a.W / TW, tiles_y = (a.H + 7) / 8;
-    const int pitch = (TW + 2) * CI + (CI == 8 ? 8 : 1);
-    const size_t smem = (size_t)10 * pitch * 4;
-    launch_pdl(8, thin_conv_kernel<CI, CO>, dim3(a.N * tiles_x * tiles_y), dim3(256), smem, st, a, TW, tiles_x, tiles_y);
+    const int pitch = (TW + KS - 1) * CI + (CI == 8 ? 8 : 1);
+    const size_t smem = (size_t)(8 + KS - 1) * pitch * 4;
+    if (smem > 48 * 1024) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(thin_conv_kernel<CI, CO, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            attr = true;
+        }
+    }
+    launch_pdl(8, thin_conv_kernel<CI, CO, KS>, dim3(a.N * tiles_x * tiles_y), dim3(256), smem, st, a, TW, tiles_x, tiles_y);
     return check_launch("thin_conv_kernel");
 }
 
 // DL4DS_E_UNSUPPORTED when the shape is outside this kernel's domain
 int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
-    if (a.KH != 3 || a.KW != 3 || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
+    const bool k3 = a.KH == 3 && a.KW == 3, k7 = a.KH == 7 && a.KW == 7;      // 7x7: the ConvNeXt stem / tail
+    if (!(k3 || k7) || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
         return DL4DS_E_UNSUPPORTED;
     if (!((a.Cin == 1 || a.Cin == 8) && (a.Cout == 1 || a.Cout == 8))) return DL4DS_E_UNSUPPORTED;
     if (a.W % 32 || (a.W > 128 && a.W % 128)) return DL4DS_E_UNSUPPORTED;
     if (a.Cin == 8 && !a.vec) return DL4DS_E_UNSUPPORTED;
     if ((int64_t)a.N * a.H * a.W < 16384) return DL4DS_E_UNSUPPORTED;
-    if (a.Cin == 8 && a.Cout == 8) return launch_thin_conv<8, 8>(a, st);
-    if (a.Cin == 8 && a.Cout == 1) return launch_thin_conv<8, 1>(a, st);
-    if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8>(a, st);
-    return launch_thin_conv<1, 1>(a, st);
+    if (k7) {
+        if (a.Cin == 8 && a.Cout == 8) return DL4DS_E_UNSUPPORTED;      // the tensor-core halo kernel
+        if (a.Cin == 8 && a.Cout == 1) return launch_thin_conv<8, 1, 7>(a, st);
+        if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8, 7>(a, st);
+        return launch_thin_conv<1, 1, 7>(a, st);
+    }
+    if (a.Cin == 8 && a.Cout == 8) return launch_thin_conv<8, 8, 3>(a, st);
+    if (a.Cin == 8 && a.Cout == 1) return launch_thin_conv<8, 1, 3>(a, st);
+    if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8, 3>(a, st);
+    return launch_thin_conv<1, 1, 3>(a, st);
 }
 
 // -------------------------------------------------------------------------------------------------

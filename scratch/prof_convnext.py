@@ -20,3 +20,11 @@ for _ in range(4):
     tr.train_on_batch(x, y[0])
 torch.cuda.synchronize()
 print('launches per step', tr.train_step.launches_per_step)
+import time
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+st = tr.train_step
+e0.record()
+for _ in range(20):
+    st.run()
+e1.record(); torch.cuda.synchronize()
+print('convnext + ln + gelu, 4x SPC, batch 64: %.3f ms per captured step' % (e0.elapsed_time(e1) / 20))

@@ -331,12 +331,13 @@ def test_net_resnet_spc_tc(cuda, math):
 
 
 # ------------------------------------------------------------------------------------------ narrow layers
-@pytest.mark.parametrize('cin,cout', [(8, 8), (8, 1), (1, 8), (1, 1)])
+@pytest.mark.parametrize('cin,cout,k', [(8, 8, 3), (8, 1, 3), (1, 8, 3), (1, 1, 3),
+                                        (8, 1, 7), (1, 8, 7), (1, 1, 7)])      # 7x7: the ConvNeXt stem / tail
 @pytest.mark.parametrize('hw', [(128, 128), (64, 32), (16, 256)])
-def test_thin_wgrad(cuda, cin, cout, hw):
+def test_thin_wgrad(cuda, cin, cout, k, hw):
     """Direct conv (fwd + dgrad) and sliding-window wgrad of the HR-tail / stem layers (thin.cu)."""
-    fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=3, act='tanh')
-    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=3), 'tanh'))
+    fn = lambda c, xs: c.conv(xs[0], 'cv', cout, k=k, act='tanh')
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=k), 'tanh'))
     n = max(1, 16384 // (hw[0] * hw[1])) + 1
     compare(fn, ofn, [(n, hw[0], hw[1], cin)], cuda)
 
@@ -374,6 +375,8 @@ def test_pointwise_conv(cuda, cin, cout):
     ((2, 32, 32, 8), 48, 1),        # 1x1 projection, 8 stacked rows
     ((2, 16, 32, 16), 40, 5),       # 5x5: 400 stacked rows, halo 36 x 5
     ((5, 32, 32, 40), 56, 3),       # 360 rows (3 blocks, last one partial), Cb 56 -> Nmma 64
+    ((2, 32, 32, 8), 8, 7),         # 7x7 (ConvNeXt stem / tail): 392 stacked rows, halo 38 x 7
+    ((1, 64, 128, 8), 16, 7),
 ])
 def test_wgrad_stacked_taps(cuda, math, shape, cout, k):
     """conv_tc_wgrad2_kernel (conv_tc_wgrad.cu) through Ctx.conv's backward, against the oracle."""
