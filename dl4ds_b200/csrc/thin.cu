@@ -232,7 +232,8 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
 int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
     const bool k3 = w.KH == 3 && w.KW == 3, k7 = w.KH == 7 && w.KW == 7;
     if (!(k3 || k7) || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
-    if (!((w.Ca == 1 || w.Ca == 8) && (w.Cb == 1 || w.Cb == 8))) return DL4DS_E_UNSUPPORTED;
+    const bool c28 = k3 && w.Ca == 2 && w.Cb == 8;          // the first layer of the 'pin' networks with one static variable (cfg5)
+    if (!c28 && !((w.Ca == 1 || w.Ca == 8) && (w.Cb == 1 || w.Cb == 8))) return DL4DS_E_UNSUPPORTED;
     if (k7 && w.Ca == 8 && w.Cb == 8) return DL4DS_E_UNSUPPORTED;       // tensor-core kernels (conv_tc_wgrad2)
     if (w.Wq % 32 || (w.Wq > 128 && w.Wq % 128)) return DL4DS_E_UNSUPPORTED;
     if (w.Ca == 8 && (w.p_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15))) return DL4DS_E_UNSUPPORTED;
@@ -247,6 +248,7 @@ int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
         if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8, 7>(a, st);
         return launch_thin<1, 1, 7>(a, st);
     }
+    if (c28) return launch_thin<2, 8, 3>(a, st);
     if (w.Ca == 8 && w.Cb == 8) return launch_thin<8, 8, 3>(a, st);
     if (w.Ca == 8 && w.Cb == 1) return launch_thin<8, 1, 3>(a, st);
     if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8, 3>(a, st);
@@ -430,7 +432,8 @@ int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
     const bool k3 = a.KH == 3 && a.KW == 3, k7 = a.KH == 7 && a.KW == 7;      // 7x7: the ConvNeXt stem / tail
     if (!(k3 || k7) || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
         return DL4DS_E_UNSUPPORTED;
-    if (!((a.Cin == 1 || a.Cin == 8) && (a.Cout == 1 || a.Cout == 8))) return DL4DS_E_UNSUPPORTED;
+    const bool c28 = k3 && a.Cin == 2 && a.Cout == 8;      // first layer of the pin networks with one static variable (cfg5)
+    if (!c28 && !((a.Cin == 1 || a.Cin == 8) && (a.Cout == 1 || a.Cout == 8))) return DL4DS_E_UNSUPPORTED;
     if (a.W % 32 || (a.W > 128 && a.W % 128)) return DL4DS_E_UNSUPPORTED;
     if (a.Cin == 8 && !a.vec) return DL4DS_E_UNSUPPORTED;
     if ((int64_t)a.N * a.H * a.W < 16384) return DL4DS_E_UNSUPPORTED;
@@ -440,6 +443,7 @@ int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
         if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8, 7>(a, st);
         return launch_thin_conv<1, 1, 7>(a, st);
     }
+    if (c28) return launch_thin_conv<2, 8, 3>(a, st);
     if (a.Cin == 8 && a.Cout == 8) return launch_thin_conv<8, 8, 3>(a, st);
     if (a.Cin == 8 && a.Cout == 1) return launch_thin_conv<8, 1, 3>(a, st);
     if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8, 3>(a, st);

@@ -17,3 +17,8 @@ go, do = cgan.Adam(2e-4, beta_1=0.5), cgan.Adam(2e-4, beta_1=0.5)
 for _ in range(2):
     cgan.train_step(lr, hr, G, D, go, do, gen_pxloss_function='mae', static_array=st)
 torch.cuda.synchronize()
+# one whole step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+torch.cuda.profiler.start()
+cgan.train_step(lr, hr, G, D, go, do, gen_pxloss_function='mae', static_array=st)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()

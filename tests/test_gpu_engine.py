@@ -332,7 +332,8 @@ def test_net_resnet_spc_tc(cuda, math):
 
 # ------------------------------------------------------------------------------------------ narrow layers
 @pytest.mark.parametrize('cin,cout,k', [(8, 8, 3), (8, 1, 3), (1, 8, 3), (1, 1, 3),
-                                        (8, 1, 7), (1, 8, 7), (1, 1, 7)])      # 7x7: the ConvNeXt stem / tail
+                                        (8, 1, 7), (1, 8, 7), (1, 1, 7),       # 7x7: the ConvNeXt stem / tail
+                                        (2, 8, 3)])                            # cfg5's first layer (HR field + one static variable)
 @pytest.mark.parametrize('hw', [(128, 128), (64, 32), (16, 256)])
 def test_thin_wgrad(cuda, cin, cout, k, hw):
     """Direct conv (fwd + dgrad) and sliding-window wgrad of the HR-tail / stem layers (thin.cu)."""
@@ -340,6 +341,26 @@ def test_thin_wgrad(cuda, cin, cout, k, hw):
     ofn = _o(lambda p, xs: R.act(R._conv(p, 'cv', xs[0], cout, k=k), 'tanh'))
     n = max(1, 16384 // (hw[0] * hw[1])) + 1
     compare(fn, ofn, [(n, hw[0], hw[1], cin)], cuda)
+
+
+@pytest.mark.parametrize('math', ['tf32x3', 'tf32', 'f16x3'])
+@pytest.mark.parametrize('hw', [(128, 128), (64, 32), (16, 256), (72, 64)])
+def test_thin_mma_8x8(cuda, math, hw):
+    """The 8 -> 8 3x3 layers of the HR tail in the tensor-core math modes (thin_mma.cu: mma.sync kernels; the 3-term
+    mode splits into fp16 hi / lo halves under per-tile power-of-two scales): forward, dgrad, wgrad, a residual +
+    relu epilogue, and inputs far from fp16's range."""
+    n = max(1, 16384 // (hw[0] * hw[1])) + 1
+    fn = lambda c, xs: c.conv(c.conv(xs[0], 'a', 8, k=3, act='tanh'), 'b', 8, k=3, act='relu', res=xs[1])
+    ofn = _o(lambda p, xs: R.act(R._conv(p, 'b', R.act(R._conv(p, 'a', xs[0], 8, k=3), 'tanh'), 8, k=3) + xs[1], 'relu'))
+    if math == 'tf32':      # single-pass mode: the smooth layer only (a relu mask flip moves the small bias gradients by percents)
+        fn = lambda c, xs: c.conv(xs[0], 'a', 8, k=3, act='tanh')
+        ofn = _o(lambda p, xs: R.act(R._conv(p, 'a', xs[0], 8, k=3), 'tanh'))
+    compare(fn, ofn, [(n, hw[0], hw[1], 8), (n, hw[0], hw[1], 8)][:1 if math == 'tf32' else 2], cuda, math=math, **TC_TOL[math])
+    if math != 'tf32':
+        fn2 = lambda c, xs: c.conv(xs[0], 'cv', 8, k=3)
+        ofn2 = _o(lambda p, xs: R._conv(p, 'cv', xs[0], 8, k=3))
+        for sc in (3000.0, 1e-6):
+            compare(fn2, ofn2, [(n, hw[0], hw[1], 8)], cuda, math=math, scale_inputs=sc, **TC_TOL[math])
 
 
 def test_bias_act_bwd_vec4_d2s(cuda):
