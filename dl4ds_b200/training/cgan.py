@@ -91,27 +91,65 @@ def _dev_inputs(model, arrays, dev):
     return ins
 
 
-def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function):
+def _ctx(model, plan):
+    """A training Ctx on ``model``'s arena that shares the model's tensor-core weight-image cache (``plan``: the
+    engine.PackPlan that has just refreshed those images on this stream, or None: first use packs)."""
+    from ..engine import Ctx
+    c = Ctx(model.arena, model.math, training=True)
+    if not hasattr(model, '_pack_cache'):
+        model._pack_cache = {}
+    c.pack_cache = model._pack_cache
+    c.prepacked = plan.keys if plan is not None else None
+    return c
+
+
+def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function, plans=None, side=None, shadow_grad=None):
     """Device work of one cGAN step up to the gradients (cgan.py:587-611): zero both gradient arenas, generator
     forward, D(real), D(fake), the four loss terms into ``losses`` (gan, lambda*px, d_real, d_fake) and the two
-    backward passes.  Pure kernel launches on the current stream: ``train_step`` runs it eagerly, ``CGANStep``
-    captures it into a CUDA graph."""
-    from ..engine import Ctx, Var
+    backward passes.  Pure kernel launches: ``train_step`` runs it eagerly on the current stream, ``CGANStep``
+    captures it into a CUDA graph with ``plans`` = (generator, discriminator) PackPlans (every tensor-core weight
+    image packed by one launch per model) and ``side`` = a second stream for the D(real) branch: its forward and
+    backward depend on nothing the generator produces, and at the small per-GPU batches of the cGAN configurations
+    (BASELINE config 5: 4 samples) no kernel of either branch fills the GPU.  The branch accumulates its weight
+    gradients into ``shadow_grad`` (same layout as the discriminator's gradient arena), added at the join."""
+    import copy
+    import torch
+    from .. import _lib
+    from ..engine import Var
     G.arena.zero_grad(); D.arena.zero_grad()
     losses.zero_()
+    pg, pd = plans if plans is not None else (None, None)
+    for pl in (pg, pd):
+        if pl is not None:
+            pl.run()
+    main = torch.cuda.current_stream()
+
+    def d_real(arena):
+        cr = _ctx(D, pd)
+        cr.arena = arena
+        p_real = D.fn(cr, [cr.input(lr_t), cr.input(hr_t), cr.input(mk[0])])
+        cr.bce_loss(p_real, 1.0, loss_buf=losses[2:3])
+        cr.backward()
+
+    two_streams = side is not None and shadow_grad is not None and plans is not None
+    if two_streams:
+        shadow = copy.copy(D.arena)
+        shadow.grad = shadow_grad
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            shadow_grad.zero_()
+            d_real(shadow)
     # ---- forward: generator, D(real), D(fake)
-    cg = Ctx(G.arena, G.math, training=True)
+    cg = _ctx(G, pg)
     gin = [cg.input(lr_t)] + ([cg.input(st_t)] if st_t is not None else [])
     gen = G.fn(cg, gin)
-    cr = Ctx(D.arena, D.math, training=True)
-    p_real = D.fn(cr, [cr.input(lr_t), cr.input(hr_t), cr.input(mk[0])])
-    cf = Ctx(D.arena, D.math, training=True)
+    if not two_streams:
+        d_real(D.arena)
+    cf = _ctx(D, pd)
     gen_in = Var(gen.buf, gen.off, gen.C, requires_grad=True)
     p_fake = D.fn(cf, [cf.input(lr_t), gen_in, cf.input(mk[1])])
 
     # ---- discriminator loss and weight gradients
-    cr.bce_loss(p_real, 1.0, loss_buf=losses[2:3])
-    cr.backward()
     cf.bce_loss(p_fake, 0.0, loss_buf=losses[3:4])
     cf.backward(keep_tape=True)
     gen_in.grad = None                      # d(D loss)/d(gen) is not used by either optimizer
@@ -124,6 +162,10 @@ def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function):
         cg._give_grad(gen, gen_in.grad)
     cg.pixel_loss(gen, cg.input(hr_t), gen_pxloss_function or 'mae', scale=LAMBDA, loss_buf=losses[1:2])
     cg.backward()
+    if two_streams:
+        main.wait_stream(side)
+        g = D.arena.grad
+        _lib.call('dl4ds_axpby', 1.0, shadow_grad.data_ptr(), 1.0, g.data_ptr(), g.numel(), main.cuda_stream)
 
 
 class CGANStep:
@@ -158,6 +200,12 @@ class CGANStep:
         self.lr_t = [z((1,)), z((1,))]
         self._lr_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.graph_fb = self.graph_opt = None
+        # captured step only: one pack launch per model and the D(real) branch on a second stream (see _fwd_bwd);
+        # a discriminator with batch normalisation updates its moving statistics in both passes, in program order
+        self.plans = None
+        two = os.environ.get('DL4DS_CGAN_STREAMS', '2') != '1' and not any('moving_mean' in k for k in self.D.spec)
+        self.side = torch.cuda.Stream(device=dev) if two and dev.type == 'cuda' else None
+        self.shadow_grad = torch.zeros_like(self.D.arena.grad) if self.side is not None else None
 
     def _opt(self):
         import torch
@@ -179,7 +227,8 @@ class CGANStep:
                 b, t = src.shape[0], src.shape[1]
                 _lib.call('dl4ds_permute_frames', src.data_ptr(), dst.data_ptr(), b, t, src[0, 0].numel(), st)
             lr, hr = self.frames
-        _fwd_bwd(self.G, self.D, lr, hr, self.st, self.masks, self.losses, self.pxloss)
+        _fwd_bwd(self.G, self.D, lr, hr, self.st, self.masks, self.losses, self.pxloss, plans=self.plans,
+                 side=self.side, shadow_grad=self.shadow_grad)
 
     def _exchange(self):
         """hvd.DistributedGradientTape (cgan.py:608-611): both gradient arenas summed over the ranks on this stream."""
@@ -197,6 +246,8 @@ class CGANStep:
         torch.cuda.synchronize()
         for m, (th, mm, vv, t) in zip((self.G, self.D), snap):
             m.arena.theta.copy_(th); m.arena.m.copy_(mm); m.arena.v.copy_(vv); m.arena.t = t
+        from ..engine import PackPlan
+        self.plans = tuple(PackPlan(m.arena, getattr(m, '_pack_cache', {})) for m in (self.G, self.D))   # images the eager pass used
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
