@@ -103,7 +103,8 @@ def _ctx(model, plan):
     return c
 
 
-def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function, plans=None, side=None, shadow_grad=None):
+def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function, plans=None, side=None, shadow_grad=None,
+             wgrad_stream=None):
     """Device work of one cGAN step up to the gradients (cgan.py:587-611): zero both gradient arenas, generator
     forward, D(real), D(fake), the four loss terms into ``losses`` (gan, lambda*px, d_real, d_fake) and the two
     backward passes.  Pure kernel launches: ``train_step`` runs it eagerly on the current stream, ``CGANStep``
@@ -111,7 +112,9 @@ def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function, plans=None
     image packed by one launch per model) and ``side`` = a second stream for the D(real) branch: its forward and
     backward depend on nothing the generator produces, and at the small per-GPU batches of the cGAN configurations
     (BASELINE config 5: 4 samples) no kernel of either branch fills the GPU.  The branch accumulates its weight
-    gradients into ``shadow_grad`` (same layout as the discriminator's gradient arena), added at the join."""
+    gradients into ``shadow_grad`` (same layout as the discriminator's gradient arena), added at the join.
+    ``wgrad_stream``: the weight-gradient kernels of the other two backward passes leave the dgrad chain for a third
+    stream (engine.Ctx.wgrad_stream)."""
     import copy
     import torch
     from .. import _lib
@@ -141,11 +144,13 @@ def _fwd_bwd(G, D, lr_t, hr_t, st_t, mk, losses, gen_pxloss_function, plans=None
             d_real(shadow)
     # ---- forward: generator, D(real), D(fake)
     cg = _ctx(G, pg)
+    cg.wgrad_stream = wgrad_stream if two_streams else None
     gin = [cg.input(lr_t)] + ([cg.input(st_t)] if st_t is not None else [])
     gen = G.fn(cg, gin)
     if not two_streams:
         d_real(D.arena)
     cf = _ctx(D, pd)
+    cf.wgrad_stream = wgrad_stream if two_streams else None
     gen_in = Var(gen.buf, gen.off, gen.C, requires_grad=True)
     p_fake = D.fn(cf, [cf.input(lr_t), gen_in, cf.input(mk[1])])
 
@@ -203,8 +208,10 @@ class CGANStep:
         # captured step only: one pack launch per model and the D(real) branch on a second stream (see _fwd_bwd);
         # a discriminator with batch normalisation updates its moving statistics in both passes, in program order
         self.plans = None
-        two = os.environ.get('DL4DS_CGAN_STREAMS', '2') != '1' and not any('moving_mean' in k for k in self.D.spec)
+        n_streams = int(os.environ.get('DL4DS_CGAN_STREAMS', '3'))
+        two = n_streams > 1 and not any('moving_mean' in k for k in self.D.spec)
         self.side = torch.cuda.Stream(device=dev) if two and dev.type == 'cuda' else None
+        self.wside = torch.cuda.Stream(device=dev) if self.side is not None and n_streams > 2 else None
         self.shadow_grad = torch.zeros_like(self.D.arena.grad) if self.side is not None else None
 
     def _opt(self):
@@ -228,7 +235,7 @@ class CGANStep:
                 _lib.call('dl4ds_permute_frames', src.data_ptr(), dst.data_ptr(), b, t, src[0, 0].numel(), st)
             lr, hr = self.frames
         _fwd_bwd(self.G, self.D, lr, hr, self.st, self.masks, self.losses, self.pxloss, plans=self.plans,
-                 side=self.side, shadow_grad=self.shadow_grad)
+                 side=self.side, shadow_grad=self.shadow_grad, wgrad_stream=self.wside)
 
     def _exchange(self):
         """hvd.DistributedGradientTape (cgan.py:608-611): both gradient arenas summed over the ranks on this stream."""
