@@ -103,6 +103,8 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
 int dl4ds_conv2d_dgrad_fused_supported(int N, int H, int W, int Cq, int Cp, int KH, int KW, int math_mode) {
     static const bool disabled = [] { const char* e = getenv("DL4DS_NO_FUSED_DGRAD"); return e && e[0] == '1'; }();
     if (disabled || dl4ds_device_is_sm100() != 1) return 0;
+    if (Cq == 8 && Cp == 8)      // the 8-channel HR tail: the warp-level fp16 kernel (thin_mma.cu) or not fused at all
+        return conv2d_thin_fused_dgrad_supported(N, H, W, KH, KW, math_mode) ? 1 : 0;
     ConvArgs a = {};
     a.N = N; a.H = H; a.W = W; a.Cin = Cq; a.Ho = H; a.Wo = W; a.Cout = Cp;
     a.KH = KH; a.KW = KW; a.stride = 1; a.up = 1; a.d2s_r = 1;
@@ -136,7 +138,8 @@ int dl4ds_conv2d_dgrad_fused(const float* dq, int dq_ld, const float* w, float* 
     a.M = N * H * W; a.HoWo = H * W;
     a.vec = 1;
     a.mask_y = y_prod; a.mask_ld = y_ld; a.mask_act = act; a.dbias = dbias;
-    const int rc = conv2d_fwd_tc(a, math_mode, ws, prepacked, reinterpret_cast<cudaStream_t>(stream));
+    const int rc = (Cq == 8 && Cp == 8) ? conv2d_fwd_thin_mma(a, math_mode, reinterpret_cast<cudaStream_t>(stream))
+                                        : conv2d_fwd_tc(a, math_mode, ws, prepacked, reinterpret_cast<cudaStream_t>(stream));
     if (rc == DL4DS_E_UNSUPPORTED) set_error("conv2d_dgrad_fused: tensors not aligned for the tensor-core kernel");
     return rc;
 }

@@ -50,6 +50,7 @@ int conv2d_wgrad_thin(const WgradArgs& a, cudaStream_t st);
 int conv2d_wgrad_pointwise(const WgradArgs& a, cudaStream_t st);
 int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st);
 // thin_mma.cu: mma.sync (register-operand) kernels of the 8-channel HR tail, tensor-core math modes only
+bool conv2d_thin_fused_dgrad_supported(int N, int H, int W, int KH, int KW, int math_mode);
 int conv2d_fwd_thin_mma(const ConvArgs& a, int math_mode, cudaStream_t st);
 int conv2d_wgrad_thin_mma(const WgradArgs& a, int math_mode, cudaStream_t st);
 int conv2d_fwd_pointwise(const ConvArgs& a, cudaStream_t st);

@@ -164,6 +164,13 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void ld_nc_f2(const float* p, float2& v) {
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+}
+__device__ __forceinline__ void ld_f2(const float* p, float2& v) {
+    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+}
+
 __device__ __forceinline__ float block_amax_256(float m, float* red8) {     // red8: 8 floats of shared memory
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -181,9 +188,15 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
     pdl_wait();
     p.x = pdl_after_wait(p.x);
     p.res = pdl_after_wait(p.res);
+    p.mask_y = pdl_after_wait(p.mask_y);
     constexpr int TH = 8;
     extern __shared__ __align__(16) uint32_t smw[];          // [hi | lo] planes, (TH+2) rows x pitch words, 4 words = one pixel
     __shared__ float red8[8];
+    __shared__ float dbs[8];
+    // dgrad launches with the producer's epilogue-backward fused (dl4ds_conv2d_dgrad_fused): dz = (acc [+ old]) *
+    // act'(y_producer), dbias += column sums of dz; no bias / residual / activation of its own
+    const bool fusedbw = p.mask_y != nullptr || p.dbias != nullptr;
+    if (threadIdx.x < 8) dbs[threadIdx.x] = 0.f;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int pitch = (TW + 2) * 4;
@@ -248,11 +261,25 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
     }
     __syncthreads();
     const int oy = y0 + warp;
-    if (oy >= p.H) return;
+    if (oy >= p.H && !fusedbw) return;
     const float inv = (1.0f / sx) * (1.0f / sw);
     const float bias0 = p.bias ? __ldg(p.bias + 2 * t) : 0.f, bias1 = p.bias ? __ldg(p.bias + 2 * t + 1) : 0.f;
-    for (int m0 = 0; m0 < TW; m0 += 16) {
+    float bs0 = 0.f, bs1 = 0.f;
+    for (int m0 = 0; m0 < TW && oy < p.H; m0 += 16) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, accx[4] = {0.f, 0.f, 0.f, 0.f};
+        // the epilogue's global operands (residual / producer output / old value) are requested BEFORE the MMAs of this
+        // pixel tile (asm volatile keeps them there): loaded at the point of use they cost a memory round trip per tile
+        // and per warp -- r02cfg5f: 11 us without, 17 us with a residual, 26 us with mask + old at 4 x 256 x 256
+        float2 e_a[2], e_b[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t pix = ((int64_t)img * p.H + oy) * p.W + x0 + m0 + g + 8 * h;
+            e_a[h] = e_b[h] = make_float2(0.f, 0.f);
+            const float* pa = fusedbw ? p.mask_y : p.res;
+            const int lda = fusedbw ? p.mask_ld : p.res_ld;
+            if (pa) ld_nc_f2(pa + pix * lda + 2 * t, e_a[h]);
+            if (p.beta) ld_f2(p.y + pix * p.y_ld + 2 * t, e_b[h]);
+        }
 #pragma unroll
         for (int pr = 0; pr < 5; ++pr) {
             const int ta = 2 * pr, tb = 2 * pr + 1;
@@ -276,14 +303,39 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
         for (int h = 0; h < 2; ++h) {
             const int64_t pix = ((int64_t)img * p.H + oy) * p.W + x0 + m0 + g + 8 * h;
             float2 o = make_float2((acc[2 * h] + accx[2 * h]) * inv + bias0, (acc[2 * h + 1] + accx[2 * h + 1]) * inv + bias1);
-            if (p.res) {
-                const float2 r = __ldg(reinterpret_cast<const float2*>(p.res + pix * p.res_ld + 2 * t));
-                o.x += r.x; o.y += r.y;
+            if (fusedbw) {
+                float2* dstf = reinterpret_cast<float2*>(p.y + pix * p.y_ld + 2 * t);
+                o.x += e_b[h].x; o.y += e_b[h].y;
+                if (p.mask_y) {
+                    o.x *= act_grad_from_out(e_a[h].x, p.mask_act); o.y *= act_grad_from_out(e_a[h].y, p.mask_act);
+                }
+                *dstf = o;
+                bs0 += o.x; bs1 += o.y;
+                continue;
             }
+            o.x += e_a[h].x; o.y += e_a[h].y;
             o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
             float2* dst = reinterpret_cast<float2*>(p.y + pix * p.y_ld + 2 * t);
-            if (p.beta) { const float2 old = *dst; o.x += old.x; o.y += old.y; }
+            o.x += e_b[h].x; o.y += e_b[h].y;
             *dst = o;
+        }
+    }
+    if (p.dbias != nullptr) {           // (uniform per launch; every warp of the block arrives here in this mode)
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            bs0 += __shfl_xor_sync(0xffffffffu, bs0, o);
+            bs1 += __shfl_xor_sync(0xffffffffu, bs1, o);
+        }
+        if (lane < 4) { atomicAdd(&dbs[2 * lane], bs0); atomicAdd(&dbs[2 * lane + 1], bs1); }
+        __syncthreads();
+        // two 16-byte reductions per block (the arena keeps every tensor 16-byte aligned): at batch 4 every block of the
+        // launch lands on the same 32 bytes within a few microseconds, and same-address atomics serialise in L2
+        if ((reinterpret_cast<uintptr_t>(p.dbias) & 15) == 0) {
+            if (tid < 2)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dbias + 4 * tid), "f"(dbs[4 * tid]),
+                             "f"(dbs[4 * tid + 1]), "f"(dbs[4 * tid + 2]), "f"(dbs[4 * tid + 3]) : "memory");
+        } else if (tid < 8) {
+            atomicAdd(p.dbias + tid, dbs[tid]);
         }
     }
 }
@@ -305,6 +357,8 @@ int conv2d_fwd_thin_mma(const ConvArgs& a, int math_mode, cudaStream_t st) {
     if (a.y_ld % 2 || (reinterpret_cast<uintptr_t>(a.y) & 7)) return DL4DS_E_UNSUPPORTED;
     if (a.res && (a.res_ld % 2 || (reinterpret_cast<uintptr_t>(a.res) & 7))) return DL4DS_E_UNSUPPORTED;
     if ((int64_t)a.N * a.H * a.W < 16384) return DL4DS_E_UNSUPPORTED;
+    if ((a.mask_y || a.dbias) && !(math_mode == DL4DS_MATH_TF32X3 && thin_f16_enabled())) return DL4DS_E_UNSUPPORTED;
+    if (a.mask_y && (a.mask_ld % 2 || (reinterpret_cast<uintptr_t>(a.mask_y) & 7))) return DL4DS_E_UNSUPPORTED;
     const int TW = a.W > 128 ? 128 : a.W;
     const int tiles_x = a.W / TW, tiles_y = (a.H + 7) / 8;
     const size_t smem = (size_t)10 * ((TW + 2) * 8 + 8) * 4;
@@ -322,6 +376,16 @@ int conv2d_fwd_thin_mma(const ConvArgs& a, int math_mode, cudaStream_t st) {
     else
         launch_pdl(4, thin_conv_mma_kernel<false>, dim3(a.N * tiles_x * tiles_y), dim3(256), smem, st, a, TW, tiles_x, tiles_y);
     return check_launch("thin_conv_mma_kernel");
+}
+
+// the shapes whose dgrad can carry the producer's epilogue-backward (the fp16 3-term kernel only)
+bool conv2d_thin_fused_dgrad_supported(int N, int H, int W, int KH, int KW, int math_mode) {
+    static const bool disabled = [] { const char* e = getenv("DL4DS_THIN_NO_MMA"); return e && e[0] == '1'; }();
+    if (math_mode == DL4DS_MATH_F16X3) math_mode = DL4DS_MATH_TF32X3;
+    static const bool off = [] { const char* e = getenv("DL4DS_THIN_FUSED"); return e && e[0] == '0'; }();
+    if (off || disabled || math_mode != DL4DS_MATH_TF32X3 || !thin_f16_enabled()) return false;
+    if (KH != 3 || KW != 3 || W % 32 || (W > 128 && W % 128)) return false;
+    return (int64_t)N * H * W >= 16384;
 }
 
 // -------------------------------------------------------------------------------------------------

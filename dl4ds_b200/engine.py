@@ -493,13 +493,13 @@ class Ctx:
                                                                     self.math)
                 # fused epilogue-backward of x's producer: this dgrad is the last of x's gradient contributions
                 fuse = (x.act_src is not None and x.n_contrib == x.n_uses - 1 and stride == 1 and self.math != 0 and
-                        (Ho, Wo) == (x.H, x.W) and x.off == 0 and x.ld == x.C and not (x.C == 8 and cout == 8) and
+                        (Ho, Wo) == (x.H, x.W) and x.off == 0 and x.ld == x.C and
                         dz.ptr % 16 == 0 and dz.ld % 4 == 0 and
                         (x.grad is None or (x.grad.ptr % 16 == 0 and x.grad.ld % 4 == 0)) and
                         lib.dl4ds_conv2d_dgrad_fused_supported(x.N, x.H, x.W, cout, x.C, k, k, self.math) == 1)
                 if fuse:
                     ws2, wm2 = self._packed_ws(name + '/kernel', w, W_FLIP_T, k, cout, x.C, ws_q)
-                    fuse = ws2 is not None
+                    fuse = ws2 is not None or (x.C == 8 and cout == 8)      # (the 8-channel warp-level kernel packs nothing)
                 if fuse:
                     pa, pbias = x.act_src
                     self._contrib(x)
@@ -510,7 +510,8 @@ class Ctx:
                     self._timed('%s:dgrad@%dx%d' % (name, x.H, x.W),
                                 'dl4ds_conv2d_dgrad_fused', dz.ptr, dz.ld, w.data_ptr(), x.grad.ptr, x.grad.ld,
                                 x.ptr if pa != 0 else None, x.ld, pa, dbp, x.N, x.H, x.W, cout, x.C, k, k,
-                                k - 1 - pt, k - 1 - pl, wm2, beta, self.math, ws2.data_ptr(), _stream())
+                                k - 1 - pt, k - 1 - pl, wm2, beta, self.math,
+                                ws2.data_ptr() if ws2 is not None else None, _stream())
                     x.premasked = True
                 else:
                     def wr(dst, beta):
