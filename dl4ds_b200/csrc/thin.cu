@@ -27,7 +27,7 @@ struct ThinCfg {
     static constexpr int CPS = (CA / TA) * (CB / TB);       // channel-block threads per kernel-row group
     static constexpr int TPS = CPS * KG;                    // threads per pixel stream
     static constexpr int STREAMS = 256 / TPS;
-    static constexpr int SEG = 32;                          // pixels per stream per tile (16 measured slower for 8x8)
+    static constexpr int SEG = 32;                          // pixels per stream per tile: the largest choice (the launcher may pick 16 / 8)
 };
 
 struct ThinWgradArgs {
@@ -36,6 +36,7 @@ struct ThinWgradArgs {
     int N, H, W, pad_t, pad_l;
     int TW, TH, tiles_x, tiles_y, ntiles;
     int p_pitch, q_pitch;       // shared-memory row pitches in floats
+    int seg;                    // pixels a stream walks per tile
 };
 
 template <int N>
@@ -62,11 +63,11 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
     a.P = pdl_after_wait(a.P);
     a.Q = pdl_after_wait(a.Q);
     using C = ThinCfg<CA, CB, KS>;
-    constexpr int TA = C::TA, TB = C::TB, TPS = C::TPS, SEG = C::SEG, KHT = C::KHT, HALO = KS - 1;
+    constexpr int TA = C::TA, TB = C::TB, TPS = C::TPS, KHT = C::KHT, HALO = KS - 1;
+    const int SEG = a.seg;
     extern __shared__ float sm[];
     float* Ps = sm;                                          // (TH+HALO) rows x p_pitch
     float* Qs = sm + (((size_t)(a.TH + HALO) * a.p_pitch + 3) & ~(size_t)3);   // TH rows x q_pitch (16-byte aligned)
-    __shared__ float red[KS * KS * CA * CB];
 
     const int tid = threadIdx.x;
     const int stream = tid / TPS, sub = tid % TPS;
@@ -86,7 +87,6 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
             for (int u = 0; u < TA; ++u)
 #pragma unroll
                 for (int v = 0; v < TB; ++v) acc[i][j][u][v] = 0.0f;
-    for (int i = tid; i < KS * KS * CA * CB; i += 256) red[i] = 0.0f;
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int img = tile / (a.tiles_x * a.tiles_y);
@@ -174,9 +174,15 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
             }
         }
     }
-    // ---- block reduction (shared atomics) then one global atomic per weight
+    // ---- block reduction, then one global atomic per weight.  Every thread parks its accumulators in shared memory
+    // ([element][stream]; the tiles are dead by now) and a warp per element sums the streams.  (Shared-memory atomics
+    // here cost more than the whole main loop: all streams hit the same few addresses, 16- to 32-way conflicts per
+    // instruction -- r02cfg5h: the kernel got SLOWER with more threads active.)
+    constexpr int NACC = KHT * KS * TA * TB, NEL = KS * KS * CA * CB, SP = C::STREAMS;
+    static_assert(NEL == TPS * NACC, "every weight element is owned by exactly one (sub, accumulator) pair");
     __syncthreads();
     if (stream < C::STREAMS) {
+        float* dst = sm + (size_t)sub * NACC * SP + stream;
 #pragma unroll
         for (int kh = 0; kh < KHT; ++kh)
 #pragma unroll
@@ -184,28 +190,55 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(ThinWgradArgs a) {
 #pragma unroll
                 for (int u = 0; u < TA; ++u)
 #pragma unroll
-                    for (int v = 0; v < TB; ++v)
-                        atomicAdd(&red[(((kh0 + kh) * KS + kw) * CA + ca0 + u) * CB + cb0 + v], acc[kh][kw][u][v]);
+                    for (int v = 0; v < TB; ++v) dst[(size_t)(((kh * KS + kw) * TA + u) * TB + v) * SP] = acc[kh][kw][u][v];
     }
     __syncthreads();
-    for (int i = tid; i < KS * KS * CA * CB; i += 256) atomicAdd(a.dw + i, red[i]);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int e = warp; e < NEL; e += 8) {
+        float v = 0.f;
+        for (int st = lane; st < SP; st += 32) v += sm[(size_t)e * SP + st];
+        v = warp_sum(v);
+        if (lane == 0) {
+            const int esub = e / NACC, j = e - esub * NACC;
+            const int ekh0 = (esub / C::CPS) * KHT, ecs = esub % C::CPS;
+            const int eca0 = (ecs / (CB / TB)) * TA, ecb0 = (ecs % (CB / TB)) * TB;
+            const int vv = j % TB, uu = (j / TB) % TA, kw = (j / (TB * TA)) % KS, kh = j / (TB * TA * KS);
+            atomicAdd(a.dw + (((ekh0 + kh) * KS + kw) * CA + eca0 + uu) * CB + ecb0 + vv, v);
+        }
+    }
 }
 
 template <int CA, int CB, int KS>
 static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
     using C = ThinCfg<CA, CB, KS>;
     constexpr int HALO = KS - 1;
-    const int segs = a.TW / C::SEG;
-    int th = C::STREAMS / segs;
-    if (th > 16) th = 16;          // >= 512 tiles for the 1-channel cases (r01b: 128 blocks of 64-row tiles, 74 us)
-    if (th > a.H) th = a.H;
-    while (th > 1 && a.H % th) --th;
     // shared-memory budget: shrink the tile height until both tiles fit in ~96 KB
     auto bytes = [&](int t) {
         const int pp = ((a.TW + HALO) * CA + 31) / 32 * 32 + CA, qp = (a.TW * CB + 31) / 32 * 32 + CB;
         return (size_t)((((t + HALO) * pp + 3) & ~3) + t * qp) * 4;
     };
-    while (th > 1 && bytes(th) > 96 * 1024) { --th; while (th > 1 && a.H % th) --th; }
+    // Pixels per stream (32 / 16 / 8) and tile height: a stream is a serial walk along a row segment (shared-memory
+    // latency per pixel), so what matters is how many streams run at once -- every thread of the block busy (tile
+    // rows x segments = streams) and at least two blocks per SM.  ncu (r02_thinw): 32-pixel segments of 16-row tiles
+    // left half of the <1,8> block idle (three quarters of <1,1>) on a 128-block grid at 4 x 256 x 256 -- 65 us at 12 %
+    // issue utilisation.  Of the choices that fill the block the longest segment wins (least window warm-up).
+    int th = 1, best_seg = C::SEG;
+    long best_score = -1;
+    for (int seg = C::SEG; seg >= 8; seg >>= 1) {
+        if (a.TW % seg) continue;
+        const int segs = a.TW / seg;
+        int t = C::STREAMS / segs;
+        if (t < 1) continue;
+        if (t > 16) t = 16;        // >= 512 tiles for the 1-channel cases (r01b: 128 blocks of 64-row tiles, 74 us)
+        if (t > a.H) t = a.H;
+        while (t > 1 && a.H % t) --t;
+        while (t > 1 && bytes(t) > 96 * 1024) { --t; while (t > 1 && a.H % t) --t; }
+        const long ntl = (long)a.N * (a.W / a.TW) * (a.H / t);
+        const long blocks = ntl < 4L * kNumSMs ? ntl : 4L * kNumSMs;
+        const long score = blocks * t * segs;             // streams in flight across the grid
+        if (best_score < 0 || score * 5 > best_score * 6) { best_score = score; best_seg = seg; th = t; }    // shorter only for > 20 % more
+    }
+    a.seg = best_seg;
     a.TH = th;
     a.tiles_x = a.W / a.TW;
     a.tiles_y = a.H / th;
@@ -213,7 +246,9 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
     // row pitch = CA (mod 32) floats: consecutive rows land on consecutive bank groups
     a.p_pitch = ((a.TW + HALO) * CA + 31) / 32 * 32 + CA;
     a.q_pitch = (a.TW * CB + 31) / 32 * 32 + CB;
-    const size_t smem = bytes(th);
+    size_t smem = bytes(th);
+    const size_t red_bytes = (size_t)KS * KS * CA * CB * C::STREAMS * 4;      // the final [element][stream] reduction buffer
+    if (smem < red_bytes) smem = red_bytes;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(thin_wgrad_kernel<CA, CB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
