@@ -476,8 +476,12 @@ class Ctx:
             elif a == 0 and r == 1:
                 dz = dy
                 if bias and pg:
-                    self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, None, 0, None, 0,
-                               self._g(name + '/bias').data_ptr(), x.N, Ho, Wo, cout, 0, 1, _stream())
+                    # a pure column sum that only feeds the gradient arena: like the weight gradient it leaves the
+                    # dgrad chain for the side stream (same condition: dz is not handed on to a residual input)
+                    import contextlib
+                    with (self._on_side([dy.buf]) if res is None else contextlib.nullcontext()):
+                        self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, None, 0, None, 0,
+                                   self._g(name + '/bias').data_ptr(), x.N, Ho, Wo, cout, 0, 1, _stream())
             else:
                 dz = new_var(x.N, Ho, Wo, cout, self.device) if r > 1 else dy
                 self._call('dl4ds_bias_act_bwd', dy.ptr, dy.ld, out.ptr, out.ld, dz.ptr, dz.ld,
