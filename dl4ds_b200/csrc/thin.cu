@@ -267,11 +267,11 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
 int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
     const bool k3 = w.KH == 3 && w.KW == 3, k7 = w.KH == 7 && w.KW == 7;
     if (!(k3 || k7) || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
-    const bool c28 = k3 && w.Ca == 2 && w.Cb == 8;          // the first layer of the 'pin' networks with one static variable (cfg5)
+    const bool c28 = k3 && (w.Ca == 2 || w.Ca == 4) && w.Cb == 8;   // first layer of the 'pin' networks with one static variable (cfg5); cfg4's 4-channel tail
     if (!c28 && !((w.Ca == 1 || w.Ca == 8) && (w.Cb == 1 || w.Cb == 8))) return DL4DS_E_UNSUPPORTED;
     if (k7 && w.Ca == 8 && w.Cb == 8) return DL4DS_E_UNSUPPORTED;       // tensor-core kernels (conv_tc_wgrad2)
     if (w.Wq % 32 || (w.Wq > 128 && w.Wq % 128)) return DL4DS_E_UNSUPPORTED;
-    if (w.Ca == 8 && (w.p_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15))) return DL4DS_E_UNSUPPORTED;
+    if (w.Ca % 4 == 0 && (w.p_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15))) return DL4DS_E_UNSUPPORTED;
     if (w.Cb == 8 && (w.q_ld % 4 || (reinterpret_cast<uintptr_t>(w.Q) & 15))) return DL4DS_E_UNSUPPORTED;
     if (w.NQ < 16384) return DL4DS_E_UNSUPPORTED;          // tiny problems: the generic kernel is fine
     ThinWgradArgs a;
@@ -283,7 +283,7 @@ int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
         if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8, 7>(a, st);
         return launch_thin<1, 1, 7>(a, st);
     }
-    if (c28) return launch_thin<2, 8, 3>(a, st);
+    if (c28) return w.Ca == 2 ? launch_thin<2, 8, 3>(a, st) : launch_thin<4, 8, 3>(a, st);
     if (w.Ca == 8 && w.Cb == 8) return launch_thin<8, 8, 3>(a, st);
     if (w.Ca == 8 && w.Cb == 1) return launch_thin<8, 1, 3>(a, st);
     if (w.Ca == 1 && w.Cb == 8) return launch_thin<1, 8, 3>(a, st);
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) thin_conv_kernel(ConvArgs p, int TW, int 
     extern __shared__ float sm[];
     __shared__ __align__(16) float ws[TAPS * CI * CO];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pitch = (TW + HALO) * CI + (CI == 8 ? 8 : 1);   // row pitch (floats), rows land on distinct banks
+    const int pitch = (TW + HALO) * CI + (CI == 8 ? 8 : (CI == 4 ? 4 : 1));   // row pitch (floats), rows land on distinct banks
     for (int i = tid; i < TAPS * CI * CO; i += 256) {
         const int co = i % CO, ci = (i / CO) % CI, tap = i / (CO * CI);
         ws[i] = (p.wmode == DL4DS_W_HWIO) ? __ldg(p.w + (tap * CI + ci) * CO + co)
@@ -449,7 +449,7 @@ template <int CI, int CO, int KS>
 static int launch_thin_conv(const ConvArgs& a, cudaStream_t st) {
     const int TW = a.W > 128 ? 128 : a.W;
     const int tiles_x = a.W / TW, tiles_y = (a.H + 7) / 8;
-    const int pitch = (TW + KS - 1) * CI + (CI == 8 ? 8 : 1);
+    const int pitch = (TW + KS - 1) * CI + (CI == 8 ? 8 : (CI == 4 ? 4 : 1));
     const size_t smem = (size_t)(8 + KS - 1) * pitch * 4;
     if (smem > 48 * 1024) {
         static bool attr = false;
@@ -467,10 +467,10 @@ int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
     const bool k3 = a.KH == 3 && a.KW == 3, k7 = a.KH == 7 && a.KW == 7;      // 7x7: the ConvNeXt stem / tail
     if (!(k3 || k7) || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
         return DL4DS_E_UNSUPPORTED;
-    const bool c28 = k3 && a.Cin == 2 && a.Cout == 8;      // first layer of the pin networks with one static variable (cfg5)
+    const bool c28 = k3 && ((a.Cin == 2 && a.Cout == 8) || (a.Cin == 4 && a.Cout == 8) || (a.Cin == 8 && a.Cout == 4));      // first layer of the pin networks with one static variable (cfg5)
     if (!c28 && !((a.Cin == 1 || a.Cin == 8) && (a.Cout == 1 || a.Cout == 8))) return DL4DS_E_UNSUPPORTED;
     if (a.W % 32 || (a.W > 128 && a.W % 128)) return DL4DS_E_UNSUPPORTED;
-    if (a.Cin == 8 && !a.vec) return DL4DS_E_UNSUPPORTED;
+    if (a.Cin % 4 == 0 && !a.vec) return DL4DS_E_UNSUPPORTED;
     if ((int64_t)a.N * a.H * a.W < 16384) return DL4DS_E_UNSUPPORTED;
     if (k7) {
         if (a.Cin == 8 && a.Cout == 8) return DL4DS_E_UNSUPPORTED;      // the tensor-core halo kernel
@@ -478,7 +478,11 @@ int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
         if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8, 7>(a, st);
         return launch_thin_conv<1, 1, 7>(a, st);
     }
-    if (c28) return launch_thin_conv<2, 8, 3>(a, st);
+    if (c28) {
+        if (a.Cin == 2) return launch_thin_conv<2, 8, 3>(a, st);
+        if (a.Cin == 4) return launch_thin_conv<4, 8, 3>(a, st);
+        return launch_thin_conv<8, 4, 3>(a, st);
+    }
     if (a.Cin == 8 && a.Cout == 8) return launch_thin_conv<8, 8, 3>(a, st);
     if (a.Cin == 8 && a.Cout == 1) return launch_thin_conv<8, 1, 3>(a, st);
     if (a.Cin == 1 && a.Cout == 8) return launch_thin_conv<1, 8, 3>(a, st);
@@ -501,31 +505,57 @@ __global__ void __launch_bounds__(256) pointwise_conv_kernel(ConvArgs p, int n_i
     p.res = pdl_after_wait(p.res);
     extern __shared__ __align__(16) float psm[];
     const int Cin = p.Cin, Cout = p.Cout;
-    float* wsm = psm;                                        // Cin x Cout
-    float* bsm = wsm + Cin * Cout;                           // Cout
-    for (int i = threadIdx.x; i < Cin * Cout; i += 256) {
-        const int co = i % Cout, ci = i / Cout;
-        wsm[i] = (p.wmode == DL4DS_W_HWIO) ? __ldg(p.w + ci * Cout + co) : __ldg(p.w + co * Cin + ci);
+    // channel counts that are no multiple of 4 (98 = 48 + 48 + 2 of cfg3's concatenation): the weight image is padded
+    // with zeros to Cinp x Coutp, the last input group is masked, the last output group is stored lane by lane
+    const int Coutp = G * 4, v4in = (Cin + 3) >> 2, Cinp = v4in * 4;
+    const int in_tail = Cin & 3, out_tail = Cout & 3;
+    float* wsm = psm;                                        // Cinp x Coutp
+    float* bsm = wsm + Cinp * Coutp;                         // Coutp
+    for (int i = threadIdx.x; i < Cinp * Coutp; i += 256) {
+        const int co = i % Coutp, ci = i / Coutp;
+        float w = 0.f;
+        if (ci < Cin && co < Cout) w = (p.wmode == DL4DS_W_HWIO) ? __ldg(p.w + ci * Cout + co) : __ldg(p.w + co * Cin + ci);
+        wsm[i] = w;
     }
-    for (int i = threadIdx.x; i < Cout; i += 256) bsm[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
+    for (int i = threadIdx.x; i < Coutp; i += 256) bsm[i] = (p.bias && i < Cout) ? __ldg(p.bias + i) : 0.0f;
     __syncthreads();
-    const int v4in = Cin >> 2;
     for (int idx = blockIdx.x * 256 + threadIdx.x; idx < n_items; idx += gridDim.x * 256) {
         const int px = idx / G, g = idx - px * G;
-        const float4* xr = reinterpret_cast<const float4*>(p.x + (int64_t)px * p.x_ld);
+        const float* xrow = p.x + (int64_t)px * p.x_ld;
+        const float4* xr = reinterpret_cast<const float4*>(xrow);
         const float* wg = wsm + g * 4;
         float4 acc = *reinterpret_cast<const float4*>(bsm + g * 4);
 #pragma unroll 4
         for (int c4 = 0; c4 < v4in; ++c4) {
-            const float4 xv = __ldg(xr + c4);
-            const float4 w0 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 0) * Cout);
-            const float4 w1 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 1) * Cout);
-            const float4 w2 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 2) * Cout);
-            const float4 w3 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 3) * Cout);
+            float4 xv;
+            if (in_tail && c4 == v4in - 1) {                 // (never reads past the row's Cin channels)
+                xv.x = __ldg(xrow + c4 * 4);
+                xv.y = in_tail > 1 ? __ldg(xrow + c4 * 4 + 1) : 0.f;
+                xv.z = in_tail > 2 ? __ldg(xrow + c4 * 4 + 2) : 0.f;
+                xv.w = 0.f;
+            } else {
+                xv = __ldg(xr + c4);
+            }
+            const float4 w0 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 0) * Coutp);
+            const float4 w1 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 1) * Coutp);
+            const float4 w2 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 2) * Coutp);
+            const float4 w3 = *reinterpret_cast<const float4*>(wg + (c4 * 4 + 3) * Coutp);
             acc.x = fmaf(xv.x, w0.x, acc.x); acc.y = fmaf(xv.x, w0.y, acc.y); acc.z = fmaf(xv.x, w0.z, acc.z); acc.w = fmaf(xv.x, w0.w, acc.w);
             acc.x = fmaf(xv.y, w1.x, acc.x); acc.y = fmaf(xv.y, w1.y, acc.y); acc.z = fmaf(xv.y, w1.z, acc.z); acc.w = fmaf(xv.y, w1.w, acc.w);
             acc.x = fmaf(xv.z, w2.x, acc.x); acc.y = fmaf(xv.z, w2.y, acc.y); acc.z = fmaf(xv.z, w2.z, acc.z); acc.w = fmaf(xv.z, w2.w, acc.w);
             acc.x = fmaf(xv.w, w3.x, acc.x); acc.y = fmaf(xv.w, w3.y, acc.y); acc.z = fmaf(xv.w, w3.z, acc.z); acc.w = fmaf(xv.w, w3.w, acc.w);
+        }
+        if (out_tail && g == G - 1) {                        // partial last group: lane by lane
+            float v[4] = {acc.x, acc.y, acc.z, acc.w};
+            for (int l = 0; l < out_tail; ++l) {
+                float o = v[l];
+                if (p.res) o += __ldg(p.res + (int64_t)px * p.res_ld + g * 4 + l);
+                o = apply_act(o, p.act);
+                float* d = p.y + (int64_t)px * p.y_ld + g * 4 + l;
+                if (p.beta) o += *d;
+                *d = o;
+            }
+            continue;
         }
         if (p.res) {
             const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + (int64_t)px * p.res_ld) + g);
@@ -544,10 +574,10 @@ __global__ void __launch_bounds__(256) pointwise_conv_kernel(ConvArgs p, int n_i
 
 static int launch_pointwise(const ConvArgs& a, cudaStream_t st) {
     const int64_t n_pix = (int64_t)a.N * a.H * a.W;
-    const int G = a.Cout / 4;
+    const int G = (a.Cout + 3) / 4;
     const int64_t n_items = n_pix * G;
     if (n_items >= (1ll << 31)) return DL4DS_E_UNSUPPORTED;
-    const size_t smem = (size_t)(a.Cin * a.Cout + a.Cout) * 4;
+    const size_t smem = (size_t)(((a.Cin + 3) / 4 * 4) * G * 4 + G * 4) * 4;
     if (smem > 48 * 1024) return DL4DS_E_UNSUPPORTED;
     int64_t blocks = (n_items + 255) / 256;
     if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
@@ -559,12 +589,13 @@ static int launch_pointwise(const ConvArgs& a, cudaStream_t st) {
 int conv2d_fwd_pointwise(const ConvArgs& a, cudaStream_t st) {
     if (a.KH != 1 || a.KW != 1 || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
         return DL4DS_E_UNSUPPORTED;
-    if (a.Cin % 4 || a.Cin > 64 || !a.vec) return DL4DS_E_UNSUPPORTED;
+    // rows must be 16-byte aligned (pitch % 4); the channel COUNTS may have a tail (round 2)
+    if (a.x_ld % 4 || (reinterpret_cast<uintptr_t>(a.x) & 15) || a.Cin > 128) return DL4DS_E_UNSUPPORTED;
     if (a.Cin > 8 && a.Cout > 8) return DL4DS_E_UNSUPPORTED;          // wide x wide goes to the tensor cores
     if (a.y_ld % 4 || (reinterpret_cast<uintptr_t>(a.y) & 15)) return DL4DS_E_UNSUPPORTED;
     if (a.res && (a.res_ld % 4 || (reinterpret_cast<uintptr_t>(a.res) & 15))) return DL4DS_E_UNSUPPORTED;
     if ((int64_t)a.N * a.H * a.W < 65536) return DL4DS_E_UNSUPPORTED;
-    if (a.Cout % 4 || a.Cout > 64) return DL4DS_E_UNSUPPORTED;
+    if (a.Cout > 128 || a.Cin < 2 || a.Cout < 2) return DL4DS_E_UNSUPPORTED;
     return launch_pointwise(a, st);
 }
 
@@ -586,19 +617,21 @@ __global__ void __launch_bounds__(256) pointwise_wgrad_kernel(const float* __res
     P = pdl_after_wait(P);
     Q = pdl_after_wait(Q);
     extern __shared__ __align__(16) float wsm[];
-    float* ps = wsm;                                         // kPwgTile x Ca
-    float* qs = ps + kPwgTile * Ca;                          // kPwgTile x Cb
-    float* red = qs + kPwgTile * Cb;                         // Ca x Cb
+    // channel counts with a tail (Ca = 98, Cb = 2 in cfg3): shared rows are padded to multiples of 4, the tail group is
+    // loaded lane by lane (zeros beyond the tensor's channels), lanes beyond Cb are dropped at the end
+    const int va = (Ca + 3) >> 2, G = (Cb + 3) >> 2, Cap = va * 4, Cbp = G * 4;
+    const int a_tail = Ca & 3, b_tail = Cb & 3;
+    float* ps = wsm;                                         // kPwgTile x Cap
+    float* qs = ps + kPwgTile * Cap;                         // kPwgTile x Cbp
+    float* red = qs + kPwgTile * Cbp;                        // Ca x Cbp
     const int tid = threadIdx.x;
-    const int G = Cb >> 2;
     const int tps = Ca * G;                                  // threads per pixel stream
     const int streams = 256 / tps;
     const int stream = tid / tps, sub = tid - stream * tps;
     const int ca = sub / G, g = sub - ca * G;
     const bool active = stream < streams;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < Ca * Cb; i += 256) red[i] = 0.0f;
-    const int va = Ca >> 2;
+    for (int i = tid; i < Ca * Cbp; i += 256) red[i] = 0.0f;
     const int64_t ntiles = (n_pix + kPwgTile - 1) / kPwgTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * kPwgTile;
@@ -606,18 +639,32 @@ __global__ void __launch_bounds__(256) pointwise_wgrad_kernel(const float* __res
         __syncthreads();
         for (int i = tid; i < npx * va; i += 256) {
             const int px = i / va, c4 = i - px * va;
-            *reinterpret_cast<float4*>(ps + px * Ca + c4 * 4) = __ldg(reinterpret_cast<const float4*>(P + (base + px) * p_ld) + c4);
+            const float* src = P + (base + px) * p_ld + c4 * 4;
+            float4 v;
+            if (a_tail && c4 == va - 1) {
+                v.x = __ldg(src); v.y = a_tail > 1 ? __ldg(src + 1) : 0.f; v.z = a_tail > 2 ? __ldg(src + 2) : 0.f; v.w = 0.f;
+            } else {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+            }
+            *reinterpret_cast<float4*>(ps + px * Cap + c4 * 4) = v;
         }
         for (int i = tid; i < npx * G; i += 256) {
             const int px = i / G, c4 = i - px * G;
-            *reinterpret_cast<float4*>(qs + px * Cb + c4 * 4) = __ldg(reinterpret_cast<const float4*>(Q + (base + px) * q_ld) + c4);
+            const float* src = Q + (base + px) * q_ld + c4 * 4;
+            float4 v;
+            if (b_tail && c4 == G - 1) {
+                v.x = __ldg(src); v.y = b_tail > 1 ? __ldg(src + 1) : 0.f; v.z = b_tail > 2 ? __ldg(src + 2) : 0.f; v.w = 0.f;
+            } else {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+            }
+            *reinterpret_cast<float4*>(qs + px * Cbp + c4 * 4) = v;
         }
         __syncthreads();
         if (active) {
 #pragma unroll 4
             for (int px = stream; px < npx; px += streams) {
-                const float x = ps[px * Ca + ca];
-                const float4 q = *reinterpret_cast<const float4*>(qs + px * Cb + g * 4);
+                const float x = ps[px * Cap + ca];
+                const float4 q = *reinterpret_cast<const float4*>(qs + px * Cbp + g * 4);
                 acc.x = fmaf(x, q.x, acc.x); acc.y = fmaf(x, q.y, acc.y);
                 acc.z = fmaf(x, q.z, acc.z); acc.w = fmaf(x, q.w, acc.w);
             }
@@ -625,22 +672,31 @@ __global__ void __launch_bounds__(256) pointwise_wgrad_kernel(const float* __res
     }
     __syncthreads();
     if (active) {
-        float* r = red + ca * Cb + g * 4;
+        float* r = red + ca * Cbp + g * 4;
         atomicAdd(r + 0, acc.x); atomicAdd(r + 1, acc.y); atomicAdd(r + 2, acc.z); atomicAdd(r + 3, acc.w);
     }
     __syncthreads();
-    for (int i = tid; i < Ca * Cb; i += 256) atomicAdd(dw + i, red[i]);
+    for (int i = tid; i < Ca * Cbp; i += 256) {
+        const int a_ = i / Cbp, b_ = i - a_ * Cbp;
+        if (b_ < Cb) atomicAdd(dw + a_ * Cb + b_, red[i]);
+    }
 }
 
 // DL4DS_E_UNSUPPORTED when the shape is outside this kernel's domain
 int conv2d_wgrad_pointwise(const WgradArgs& w, cudaStream_t st) {
     if (w.KH != 1 || w.KW != 1 || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
-    if (w.Ca % 4 || w.Cb % 4 || w.Ca * (w.Cb / 4) > 256) return DL4DS_E_UNSUPPORTED;
+    if (w.Ca < 2 || w.Ca * ((w.Cb + 3) / 4) > 256) return DL4DS_E_UNSUPPORTED;
     if (w.p_ld % 4 || w.q_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15) || (reinterpret_cast<uintptr_t>(w.Q) & 15))
         return DL4DS_E_UNSUPPORTED;
     if (w.NQ < 16384) return DL4DS_E_UNSUPPORTED;
-    const size_t smem = (size_t)(kPwgTile * (w.Ca + w.Cb) + w.Ca * w.Cb) * 4;
-    if (smem > 48 * 1024) return DL4DS_E_UNSUPPORTED;
+    const int Cap = (w.Ca + 3) / 4 * 4, Cbp = (w.Cb + 3) / 4 * 4;
+    const size_t smem = (size_t)(kPwgTile * (Cap + Cbp) + w.Ca * Cbp) * 4;
+    if (smem > 96 * 1024) return DL4DS_E_UNSUPPORTED;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(pointwise_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+    }
     const int64_t ntiles = (w.NQ + kPwgTile - 1) / kPwgTile;
     int blocks_per_sm = (int)((200 * 1024) / (smem + 1024));   // measured: 6 per SM beats 3 (94 vs 115 us)
     if (blocks_per_sm > 8) blocks_per_sm = 8;

@@ -174,9 +174,17 @@ class Var:
     def slice(self, off, C):
         return Var(self.buf, self.off + off, C, self.requires_grad)
 
-    def like(self, C=None):
+    def like(self, C=None, pad=False):
+        """A new tensor of this shape.  ``pad``: a channel count that is no multiple of 4 (98 = 48 + 48 + 2 after a
+        concatenation with static / localized channels) gets a pitch rounded up to 4 floats, so rows and 4-channel
+        aligned slices stay 16-byte aligned and the vector / TMA kernels apply (the Var is then a slice of its buffer)."""
         C = self.C if C is None else C
-        return Var(torch.empty((self.N, self.H, self.W, C), dtype=torch.float32, device=self.buf.device))
+        ld = padded_channels(C) if pad else C
+        return Var(torch.empty((self.N, self.H, self.W, ld), dtype=torch.float32, device=self.buf.device), 0, C)
+
+
+def padded_channels(C):
+    return (C + 3) // 4 * 4 if (C % 4 and C > 4) else C
 
 
 def new_var(N, H, W, C, device, zero=False):
@@ -376,7 +384,7 @@ class Ctx:
             return
         self._contrib(var)
         if var.grad is None:
-            var.grad = var.like()
+            var.grad = var.like(pad=True)
             writer(var.grad, 0)
         else:
             writer(var.grad, 1)
@@ -765,7 +773,7 @@ class Ctx:
         p0 = parts[0]
         self._use(*parts)
         ctot = sum(p.C for p in parts)
-        out = new_var(p0.N, p0.H, p0.W, ctot, self.device)
+        out = Var(torch.empty((p0.N, p0.H, p0.W, padded_channels(ctot)), dtype=torch.float32, device=self.device), 0, ctot)
         offs = []
         o = 0
         for p in parts:
