@@ -590,10 +590,12 @@ int conv2d_fwd_pointwise(const ConvArgs& a, cudaStream_t st) {
     if (a.KH != 1 || a.KW != 1 || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
         return DL4DS_E_UNSUPPORTED;
     // rows must be 16-byte aligned (pitch % 4); the channel COUNTS may have a tail (round 2)
-    if (a.x_ld % 4 || (reinterpret_cast<uintptr_t>(a.x) & 15) || a.Cin > 128) return DL4DS_E_UNSUPPORTED;
+    // (a tensor with fewer than 4 channels has no full group: it is read / written lane by lane, no alignment needed)
+    if (a.Cin > 128) return DL4DS_E_UNSUPPORTED;
+    if (a.Cin >= 4 && (a.x_ld % 4 || (reinterpret_cast<uintptr_t>(a.x) & 15))) return DL4DS_E_UNSUPPORTED;
     if (a.Cin > 8 && a.Cout > 8) return DL4DS_E_UNSUPPORTED;          // wide x wide goes to the tensor cores
-    if (a.y_ld % 4 || (reinterpret_cast<uintptr_t>(a.y) & 15)) return DL4DS_E_UNSUPPORTED;
-    if (a.res && (a.res_ld % 4 || (reinterpret_cast<uintptr_t>(a.res) & 15))) return DL4DS_E_UNSUPPORTED;
+    if (a.Cout >= 4 && (a.y_ld % 4 || (reinterpret_cast<uintptr_t>(a.y) & 15))) return DL4DS_E_UNSUPPORTED;
+    if (a.Cout >= 4 && a.res && (a.res_ld % 4 || (reinterpret_cast<uintptr_t>(a.res) & 15))) return DL4DS_E_UNSUPPORTED;
     if ((int64_t)a.N * a.H * a.W < 65536) return DL4DS_E_UNSUPPORTED;
     if (a.Cout > 128 || a.Cin < 2 || a.Cout < 2) return DL4DS_E_UNSUPPORTED;
     return launch_pointwise(a, st);
@@ -686,8 +688,8 @@ __global__ void __launch_bounds__(256) pointwise_wgrad_kernel(const float* __res
 int conv2d_wgrad_pointwise(const WgradArgs& w, cudaStream_t st) {
     if (w.KH != 1 || w.KW != 1 || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
     if (w.Ca < 2 || w.Ca * ((w.Cb + 3) / 4) > 256) return DL4DS_E_UNSUPPORTED;
-    if (w.p_ld % 4 || w.q_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15) || (reinterpret_cast<uintptr_t>(w.Q) & 15))
-        return DL4DS_E_UNSUPPORTED;
+    if (w.Ca >= 4 && (w.p_ld % 4 || (reinterpret_cast<uintptr_t>(w.P) & 15))) return DL4DS_E_UNSUPPORTED;
+    if (w.Cb >= 4 && (w.q_ld % 4 || (reinterpret_cast<uintptr_t>(w.Q) & 15))) return DL4DS_E_UNSUPPORTED;
     if (w.NQ < 16384) return DL4DS_E_UNSUPPORTED;
     const int Cap = (w.Ca + 3) / 4 * 4, Cbp = (w.Cb + 3) / 4 * 4;
     const size_t smem = (size_t)(kPwgTile * (Cap + Cbp) + w.Ca * Cbp) * 4;

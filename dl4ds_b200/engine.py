@@ -787,7 +787,15 @@ class Ctx:
             if dy is None:
                 return
             for p, o in zip(parts, offs):
-                self._give_grad(p, dy.slice(o, p.C))
+                g = dy.slice(o, p.C)
+                if (g.off % 4 or g.ld % 4) and p.C % 8 == 0 and p.C >= 16:
+                    # a wide part that starts at an odd channel (48 channels behind 48 + 2 in cfg3's tail): every kernel
+                    # downstream of a 16-byte-misaligned gradient is the generic CUDA-core one (r02c3b: 846 us weight
+                    # gradient + 505 us dgrad against ~130 + 100 us on the tensor cores); one re-aligning copy instead
+                    d = p.like()
+                    self._copy(g, d)
+                    g = d
+                self._give_grad(p, g)
             out.grad = None
         self._record(bwd)
         return out

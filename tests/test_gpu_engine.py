@@ -385,6 +385,26 @@ def test_pointwise_conv(cuda, cin, cout):
     compare(fn, ofn, [(5, 128, 128, cin), (5, 128, 128, cout)], cuda)
 
 
+def test_pointwise_conv_channel_tails(cuda):
+    """cfg3's tail wiring: a 48 -> 2 1x1 convolution (LocalizedConvBlock transition), the nested concatenation
+    [[48 | 2] | 48] = 98 channels (padded pitch 100, the last part starts at channel 50: its gradient slice is
+    re-aligned) and the 98 -> 8 1x1 convolution (TransitionLast) -- the streaming 1x1 kernels with channel tails."""
+    def fn(c, xs):
+        lc = c.conv(xs[0], 'lc', 2, k=1, act='tanh')
+        aux = c.conv(xs[1], 'aux', 48, k=3, act='tanh')
+        cat = c.concat([c.concat([xs[0], lc]), aux])
+        return c.conv(cat, 'tl', 8, k=1, act='tanh')
+
+    def ofn(p, xs):
+        x0, x1 = R._nchw(xs[0]), R._nchw(xs[1])
+        lc = R.act(R._conv(p, 'lc', x0, 2, k=1), 'tanh')
+        aux = R.act(R._conv(p, 'aux', x1, 48, k=3), 'tanh')
+        cat = torch.cat([torch.cat([x0, lc], 1), aux], 1)
+        return R._nhwc(R.act(R._conv(p, 'tl', cat, 8, k=1), 'tanh'))
+    for math in ('fp32', 'tf32x3'):
+        compare(fn, ofn, [(5, 128, 128, 48), (5, 128, 128, 8)], cuda, math=math, **TC_TOL['tf32x3'])
+
+
 # ------------------------------------------------------------------------------------------ stacked-taps wgrad
 @pytest.mark.parametrize('math', ['tf32x3', 'tf32', 'f16x3'])
 @pytest.mark.parametrize('shape,cout,k', [
