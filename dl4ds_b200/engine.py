@@ -1342,13 +1342,14 @@ class Ctx:
                     self._conv_raw(dzt.data_ptr(), F4, wh.data_ptr(), None, None, 0,
                                    step(dh, t - 1).data_ptr(), filters, B, H, W, F4, H, W, filters, k, 1, 1,
                                    k - 1 - pad, k - 1 - pad, W_FLIP_T, 0, 1, 1)
-                    if pg:
-                        self._wgrad(Var(step(out.buf, t - 1)), Var(dzt), gwh, k, 1, pad, pad)
+                    if pg:      # (side stream: dz_t and h_{t-1} have no later writer)
+                        self._wgrad(Var(step(out.buf, t - 1)), Var(dzt), gwh, k, 1, pad, pad, side=True,
+                                    keep=[out.buf, dz.buf])
             # the input convolution's bias / weight / input gradients, all T in one shot
             if pg:
                 self._call('dl4ds_bias_act_bwd', dz.ptr, dz.ld, None, 0, None, 0,
                            self._g(name + '/bias').data_ptr(), TB, H, W, F4, 0, 1, _stream())
-                self._wgrad(x, dz, self._g(name + '/kernel'), k, 1, pad, pad)
+                self._wgrad(x, dz, self._g(name + '/kernel'), k, 1, pad, pad, side=True)
             if x.requires_grad:
                 def wr(dst, beta):
                     self._conv_raw(dz.ptr, dz.ld, wx.data_ptr(), None, None, 0, dst.ptr,
