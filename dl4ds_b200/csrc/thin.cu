@@ -267,6 +267,22 @@ static int launch_thin(ThinWgradArgs a, cudaStream_t st) {
 int conv2d_wgrad_thin(const WgradArgs& w, cudaStream_t st) {
     const bool k3 = w.KH == 3 && w.KW == 3, k7 = w.KH == 7 && w.KW == 7;
     if (!(k3 || k7) || w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq) return DL4DS_E_UNSUPPORTED;
+    const bool c1w = k3 && w.Ca == 1 && (w.Cb == 16 || w.Cb == 32 || w.Cb == 48 || w.Cb == 64);     // ConvBlock_aux/conv1 (cfg3: 1 -> 48)
+    if (c1w) {
+        if (w.stride != 1 || w.Hp != w.Hq || w.Wp != w.Wq || w.Wq % 32 || (w.Wq > 128 && w.Wq % 128) || w.NQ < 16384 ||
+            w.q_ld % 4 || (reinterpret_cast<uintptr_t>(w.Q) & 15))
+            return DL4DS_E_UNSUPPORTED;
+        ThinWgradArgs a;
+        a.P = w.P; a.Q = w.Q; a.dw = w.dw; a.p_ld = w.p_ld; a.q_ld = w.q_ld;
+        a.N = w.N; a.H = w.Hq; a.W = w.Wq; a.pad_t = w.pad_t; a.pad_l = w.pad_l;
+        a.TW = w.Wq > 128 ? 128 : w.Wq;
+        switch (w.Cb) {
+            case 16: return launch_thin<1, 16, 3>(a, st);
+            case 32: return launch_thin<1, 32, 3>(a, st);
+            case 48: return launch_thin<1, 48, 3>(a, st);
+            default: return launch_thin<1, 64, 3>(a, st);
+        }
+    }
     const bool c28 = k3 && (w.Ca == 2 || w.Ca == 4) && w.Cb == 8;   // first layer of the 'pin' networks with one static variable (cfg5); cfg4's 4-channel tail
     if (!c28 && !((w.Ca == 1 || w.Ca == 8) && (w.Cb == 1 || w.Cb == 8))) return DL4DS_E_UNSUPPORTED;
     if (k7 && w.Ca == 8 && w.Cb == 8) return DL4DS_E_UNSUPPORTED;       // tensor-core kernels (conv_tc_wgrad2)
@@ -462,8 +478,91 @@ static int launch_thin_conv(const ConvArgs& a, cudaStream_t st) {
     return check_launch("thin_conv_kernel");
 }
 
+// -------------------------------------------------------------------------------------------------
+// 3x3 convolution from ONE input channel to CO = 16 .. 64 channels (the first layer of the auxiliary / static-variable
+// branch, ConvBlock_aux/conv1 in cfg3: 1 -> 48 at 128 x 128): a thread owns one pixel and all CO outputs; the nine
+// inputs come from a shared halo tile, the weights are warp-uniform 16-byte broadcasts.  Write-bound (4*CO B/px).
+// -------------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(256) thin_conv_c1_kernel(ConvArgs p, int tiles_x, int tiles_y) {
+    pdl_launch_dependents();    // programmatic dependent launch (common.cuh): no global access before the wait
+    pdl_wait();
+    p.x = pdl_after_wait(p.x);
+    constexpr int TH = 8, TW = 32;
+    __shared__ float tile[TH + 2][TW + 4];
+    __shared__ __align__(16) float ws[9 * CO];
+    __shared__ __align__(16) float bs[CO];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 9 * CO; i += 256) {
+        const int co = i % CO, tap = i / CO;
+        ws[i] = (p.wmode == DL4DS_W_HWIO) ? __ldg(p.w + tap * CO + co) : __ldg(p.w + (8 - tap) * CO + co);
+    }
+    for (int i = tid; i < CO; i += 256) bs[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    const int blk = blockIdx.x;
+    const int img = blk / (tiles_x * tiles_y);
+    const int trem = blk - img * tiles_x * tiles_y;
+    const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    for (int i = tid; i < (TH + 2) * (TW + 2); i += 256) {
+        const int r = i / (TW + 2), c = i - r * (TW + 2);
+        const int gy = y0 + r - p.pad_t, gx = x0 + c - p.pad_l;
+        float v = 0.f;
+        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(p.x + ((int64_t)(img * p.H + gy) * p.W + gx) * p.x_ld);
+        tile[r][c] = v;
+    }
+    __syncthreads();
+    const int ry = tid >> 5, rx = tid & 31;
+    const int oy = y0 + ry;
+    if (oy >= p.H) return;
+    float xin[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) xin[kh * 3 + kw] = tile[ry + kh][rx + kw];
+    float* yp = p.y + (((int64_t)img * p.H + oy) * p.W + x0 + rx) * p.y_ld;
+#pragma unroll
+    for (int c4 = 0; c4 < CO / 4; ++c4) {
+        float4 acc = *reinterpret_cast<const float4*>(bs + c4 * 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const float4 w = *reinterpret_cast<const float4*>(ws + tap * CO + c4 * 4);
+            acc.x = fmaf(xin[tap], w.x, acc.x); acc.y = fmaf(xin[tap], w.y, acc.y);
+            acc.z = fmaf(xin[tap], w.z, acc.z); acc.w = fmaf(xin[tap], w.w, acc.w);
+        }
+        acc.x = apply_act(acc.x, p.act); acc.y = apply_act(acc.y, p.act);
+        acc.z = apply_act(acc.z, p.act); acc.w = apply_act(acc.w, p.act);
+        *reinterpret_cast<float4*>(yp + c4 * 4) = acc;
+    }
+}
+
+template <int CO>
+static int launch_thin_c1(const ConvArgs& a, cudaStream_t st) {
+    const int tiles_x = a.W / 32, tiles_y = (a.H + 7) / 8;
+    launch_pdl(8, thin_conv_c1_kernel<CO>, dim3(a.N * tiles_x * tiles_y), dim3(256), 0, st, a, tiles_x, tiles_y);
+    return check_launch("thin_conv_c1_kernel");
+}
+
+static int conv2d_fwd_thin_c1(const ConvArgs& a, cudaStream_t st) {
+    if (a.KH != 3 || a.KW != 3 || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
+        return DL4DS_E_UNSUPPORTED;
+    if (a.Cin != 1 || a.res || a.beta || a.W % 32) return DL4DS_E_UNSUPPORTED;
+    if (a.y_ld % 4 || (reinterpret_cast<uintptr_t>(a.y) & 15)) return DL4DS_E_UNSUPPORTED;
+    if ((int64_t)a.N * a.H * a.W < 16384) return DL4DS_E_UNSUPPORTED;
+    switch (a.Cout) {
+        case 16: return launch_thin_c1<16>(a, st);
+        case 32: return launch_thin_c1<32>(a, st);
+        case 48: return launch_thin_c1<48>(a, st);
+        case 64: return launch_thin_c1<64>(a, st);
+        default: return DL4DS_E_UNSUPPORTED;
+    }
+}
+
 // DL4DS_E_UNSUPPORTED when the shape is outside this kernel's domain
 int conv2d_fwd_thin(const ConvArgs& a, cudaStream_t st) {
+    {
+        const int rc = conv2d_fwd_thin_c1(a, st);       // 1 -> 16 / 32 / 48 / 64 channels
+        if (rc != DL4DS_E_UNSUPPORTED) return rc;
+    }
     const bool k3 = a.KH == 3 && a.KW == 3, k7 = a.KH == 7 && a.KW == 7;      // 7x7: the ConvNeXt stem / tail
     if (!(k3 || k7) || a.stride != 1 || a.up != 1 || a.Ho != a.H || a.Wo != a.W || a.d2s_r > 1)
         return DL4DS_E_UNSUPPORTED;

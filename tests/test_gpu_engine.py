@@ -333,7 +333,8 @@ def test_net_resnet_spc_tc(cuda, math):
 # ------------------------------------------------------------------------------------------ narrow layers
 @pytest.mark.parametrize('cin,cout,k', [(8, 8, 3), (8, 1, 3), (1, 8, 3), (1, 1, 3),
                                         (8, 1, 7), (1, 8, 7), (1, 1, 7),       # 7x7: the ConvNeXt stem / tail
-                                        (2, 8, 3), (4, 8, 3), (8, 4, 3)])      # cfg5's first layer (HR field + static variable), cfg4's 4-channel tail
+                                        (2, 8, 3), (4, 8, 3), (8, 4, 3),       # cfg5's first layer (HR field + static variable), cfg4's 4-channel tail
+                                        (1, 48, 3), (1, 16, 3), (1, 64, 3)])   # first layer of the auxiliary branch (cfg3: 1 -> 48)
 @pytest.mark.parametrize('hw', [(128, 128), (64, 32), (16, 256)])
 def test_thin_wgrad(cuda, cin, cout, k, hw):
     """Direct conv (fwd + dgrad) and sliding-window wgrad of the HR-tail / stem layers (thin.cu)."""
