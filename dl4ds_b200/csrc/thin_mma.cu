@@ -234,30 +234,42 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
         const int cols = TW + 2, total = (TH + 2) * cols * 2;
         float4 v[kMaxLoads];
         float m = 0.f;
+        // (row, pixel) of item i = tid + 256 k advance by 128 pixels per step: one division per thread, not two per load
+        // (ncu r02fin_thin16: 275 instructions per 16-pixel tile and warp, a third of them this index arithmetic)
+        const int c4 = tid & 1;
+        const int r0 = (tid >> 1) / cols, px0 = (tid >> 1) - r0 * cols;
+        const float* xin = p.x + (int64_t)img * p.H * p.W * p.x_ld + c4 * 4;
+        {
+            int r = r0, px = px0;
 #pragma unroll
-        for (int k = 0; k < kMaxLoads; ++k) {
-            const int i = tid + k * 256;
-            const int c4 = i & 1, px = (i >> 1) % cols, r = (i >> 1) / cols;
-            const int gy = y0 + r - p.pad_t, gx = x0 + px - p.pad_l;
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < total && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-                v[k] = __ldg(reinterpret_cast<const float4*>(p.x + ((int64_t)(img * p.H + gy) * p.W + gx) * p.x_ld) + c4);
-            m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
-        }
-        sx = thin_pow2_scale(block_amax_256(m, red8));
-#pragma unroll
-        for (int k = 0; k < kMaxLoads; ++k) {
-            const int i = tid + k * 256;
-            const int c4 = i & 1, px = (i >> 1) % cols, r = (i >> 1) / cols;
-            if (i < total) {
-                uint2 hi, lo;
-                split_h2(v[k].x * sx, v[k].y * sx, hi.x, lo.x);
-                split_h2(v[k].z * sx, v[k].w * sx, hi.y, lo.y);
-                uint32_t* dst = smw + r * pitch + px * 4 + c4 * 2;
-                *reinterpret_cast<uint2*>(dst) = hi;
-                *reinterpret_cast<uint2*>(dst + plane) = lo;
+            for (int k = 0; k < kMaxLoads; ++k) {
+                const int gy = y0 + r - p.pad_t, gx = x0 + px - p.pad_l;
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < TH + 2 && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+                    v[k] = __ldg(reinterpret_cast<const float4*>(xin + (int64_t)(gy * p.W + gx) * p.x_ld));
+                m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+                px += 128;
+                while (px >= cols) { px -= cols; ++r; }
             }
         }
+        sx = thin_pow2_scale(block_amax_256(m, red8));
+        {
+            int r = r0, px = px0;
+#pragma unroll
+            for (int k = 0; k < kMaxLoads; ++k) {
+                if (r < TH + 2) {
+                    uint2 hi, lo;
+                    split_h2(v[k].x * sx, v[k].y * sx, hi.x, lo.x);
+                    split_h2(v[k].z * sx, v[k].w * sx, hi.y, lo.y);
+                    uint32_t* dst = smw + r * pitch + px * 4 + c4 * 2;
+                    *reinterpret_cast<uint2*>(dst) = hi;
+                    *reinterpret_cast<uint2*>(dst + plane) = lo;
+                }
+                px += 128;
+                while (px >= cols) { px -= cols; ++r; }
+            }
+        }
+        (void)total;
     }
     __syncthreads();
     const int oy = y0 + warp;
@@ -265,6 +277,12 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
     const float inv = (1.0f / sx) * (1.0f / sw);
     const float bias0 = p.bias ? __ldg(p.bias + 2 * t) : 0.f, bias1 = p.bias ? __ldg(p.bias + 2 * t + 1) : 0.f;
     float bs0 = 0.f, bs1 = 0.f;
+    // row bases of the epilogue's tensors (64-bit once; the loop adds 32-bit pixel offsets)
+    const int64_t rowpix = ((int64_t)img * p.H + oy) * p.W + x0 + g;
+    const float* const e_src = fusedbw ? p.mask_y : p.res;
+    const int e_ld = fusedbw ? p.mask_ld : p.res_ld;
+    const float* const e_row = e_src ? e_src + rowpix * e_ld + 2 * t : nullptr;
+    float* const y_row = p.y + rowpix * p.y_ld + 2 * t;
     for (int m0 = 0; m0 < TW && oy < p.H; m0 += 16) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, accx[4] = {0.f, 0.f, 0.f, 0.f};
         // the epilogue's global operands (residual / producer output / old value) are requested BEFORE the MMAs of this
@@ -273,12 +291,9 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
         float2 e_a[2], e_b[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t pix = ((int64_t)img * p.H + oy) * p.W + x0 + m0 + g + 8 * h;
             e_a[h] = e_b[h] = make_float2(0.f, 0.f);
-            const float* pa = fusedbw ? p.mask_y : p.res;
-            const int lda = fusedbw ? p.mask_ld : p.res_ld;
-            if (pa) ld_nc_f2(pa + pix * lda + 2 * t, e_a[h]);
-            if (p.beta) ld_f2(p.y + pix * p.y_ld + 2 * t, e_b[h]);
+            if (e_row) ld_nc_f2(e_row + (m0 + 8 * h) * e_ld, e_a[h]);
+            if (p.beta) ld_f2(y_row + (m0 + 8 * h) * p.y_ld, e_b[h]);
         }
 #pragma unroll
         for (int pr = 0; pr < 5; ++pr) {
@@ -301,10 +316,9 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
         // C fragment: acc[0..1] = pixel m0+g, channels 2t, 2t+1; acc[2..3] = pixel m0+g+8
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t pix = ((int64_t)img * p.H + oy) * p.W + x0 + m0 + g + 8 * h;
             float2 o = make_float2((acc[2 * h] + accx[2 * h]) * inv + bias0, (acc[2 * h + 1] + accx[2 * h + 1]) * inv + bias1);
+            float2* const dstf = reinterpret_cast<float2*>(y_row + (m0 + 8 * h) * p.y_ld);
             if (fusedbw) {
-                float2* dstf = reinterpret_cast<float2*>(p.y + pix * p.y_ld + 2 * t);
                 o.x += e_b[h].x; o.y += e_b[h].y;
                 if (p.mask_y) {
                     o.x *= act_grad_from_out(e_a[h].x, p.mask_act); o.y *= act_grad_from_out(e_a[h].y, p.mask_act);
@@ -315,9 +329,8 @@ __global__ void __launch_bounds__(256, MINB) thin_conv_f16_kernel(ConvArgs p, in
             }
             o.x += e_a[h].x; o.y += e_a[h].y;
             o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
-            float2* dst = reinterpret_cast<float2*>(p.y + pix * p.y_ld + 2 * t);
             o.x += e_b[h].x; o.y += e_b[h].y;
-            *dst = o;
+            *dstf = o;
         }
     }
     if (p.dbias != nullptr) {           // (uniform per launch; every warp of the block arrives here in this mode)
@@ -579,46 +592,66 @@ __global__ void __launch_bounds__(256, 2) thin_wgrad_f16_kernel(const float* __r
             const int cols = TW + 2, total = (TH + 2) * cols * 2;
             float4 v[kMaxLoads];
             float m = 0.f;
+            // (row, pixel) of item tid + 256 k advance by 128 pixels per step: one division per thread and tile
+            const int c4 = tid & 1;
+            const int r0 = (tid >> 1) / cols, px0 = (tid >> 1) - r0 * cols;
+            const float* Pin = P + (int64_t)img * H * W * p_ld + c4 * 4;
+            {
+                int r = r0, px = px0;
 #pragma unroll
-            for (int k = 0; k < kMaxLoads; ++k) {
-                const int i = tid + k * 256;
-                const int c4 = i & 1, px = (i >> 1) % cols, r = (i >> 1) / cols;
-                const int gy = y0 + r - pad_t, gx = x0 + px - pad_l;
-                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < total && gy >= 0 && gy < H && gx >= 0 && gx < W)
-                    v[k] = __ldg(reinterpret_cast<const float4*>(P + ((int64_t)(img * H + gy) * W + gx) * p_ld) + c4);
-                m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+                for (int k = 0; k < kMaxLoads; ++k) {
+                    const int gy = y0 + r - pad_t, gx = x0 + px - pad_l;
+                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < TH + 2 && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                        v[k] = __ldg(reinterpret_cast<const float4*>(Pin + (int64_t)(gy * W + gx) * p_ld));
+                    m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+                    px += 128;
+                    while (px >= cols) { px -= cols; ++r; }
+                }
             }
             sp = thin_pow2_scale(block_amax_256(m, redp));
+            {
+                int r = r0, px = px0;
 #pragma unroll
-            for (int k = 0; k < kMaxLoads; ++k) {
-                const int i = tid + k * 256;
-                const int c4 = i & 1, px = (i >> 1) % cols, r = (i >> 1) / cols;
-                const bool odd = px & 1;
-                stage_pairs(v[k], sp, odd, i < total, Ph + (r * 8 + c4 * 4 + (odd ? 2 : 0)) * LP + (px >> 1), planeP, LP);
+                for (int k = 0; k < kMaxLoads; ++k) {
+                    const bool odd = px & 1;
+                    stage_pairs(v[k], sp, odd, r < TH + 2, Ph + (r * 8 + c4 * 4 + (odd ? 2 : 0)) * LP + (px >> 1), planeP, LP);
+                    px += 128;
+                    while (px >= cols) { px -= cols; ++r; }
+                }
             }
+            (void)total;
         }
         {
             const int totq = TH * TW * 2;
             float4 v[8];
             float m = 0.f;
+            const int c4 = tid & 1;
+            const int r0 = (tid >> 1) / TW, px0 = (tid >> 1) - r0 * TW;
+            const float* Qin = Q + ((int64_t)(img * H + y0) * W + x0) * q_ld + c4 * 4;
+            {
+                int r = r0, px = px0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = tid + k * 256;
-                const int c4 = i & 1, px = (i >> 1) % TW, r = (i >> 1) / TW;
-                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < totq && y0 + r < H)
-                    v[k] = __ldg(reinterpret_cast<const float4*>(Q + ((int64_t)(img * H + y0 + r) * W + x0 + px) * q_ld) + c4);
-                m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < TH && y0 + r < H) v[k] = __ldg(reinterpret_cast<const float4*>(Qin + (int64_t)(r * W + px) * q_ld));
+                    m = fmaxf(fmaxf(m, fmaxf(fabsf(v[k].x), fabsf(v[k].y))), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+                    px += 128;
+                    while (px >= TW) { px -= TW; ++r; }
+                }
             }
             sq = thin_pow2_scale(block_amax_256(m, redq));
+            {
+                int r = r0, px = px0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = tid + k * 256;
-                const int c4 = i & 1, px = (i >> 1) % TW, r = (i >> 1) / TW;
-                const bool odd = px & 1;
-                stage_pairs(v[k], sq, odd, i < totq, Qh + (r * 8 + c4 * 4 + (odd ? 2 : 0)) * LQ + (px >> 1), planeQ, LQ);
+                for (int k = 0; k < 8; ++k) {
+                    const bool odd = px & 1;
+                    stage_pairs(v[k], sq, odd, r < TH, Qh + (r * 8 + c4 * 4 + (odd ? 2 : 0)) * LQ + (px >> 1), planeQ, LQ);
+                    px += 128;
+                    while (px >= TW) { px -= TW; ++r; }
+                }
             }
+            (void)totq;
         }
         __syncthreads();
         float acc[5][4];
