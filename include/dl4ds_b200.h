@@ -117,7 +117,9 @@ int dl4ds_conv2d_fwd(const float* x, int x_ld, const float* w, const float* bias
  * activation) is the producer's forward OUTPUT, act its activation code; dbias may be NULL.  Valid only when
  * this launch is the LAST contribution to dz.  Tensor-core math modes only, shapes in the halo-tile kernel's
  * domain (dl4ds_conv2d_dgrad_fused_supported() == 1: W % 8 == 0, H % 16 == 0, Cp and Cq multiples of 8,
- * Cp <= 256); otherwise DL4DS_E_UNSUPPORTED -- the caller then runs dl4ds_conv2d_fwd + dl4ds_bias_act_bwd. */
+ * Cp <= 256); otherwise DL4DS_E_UNSUPPORTED -- the caller then runs dl4ds_conv2d_fwd + dl4ds_bias_act_bwd.
+ * Cq == Cp == 8 (the 8-channel HR tail): served by the warp-level fp16 3-term kernel instead (3x3, W % 32 == 0,
+ * W <= 128 or W % 128 == 0, N*H*W >= 16384, math TF32X3 / F16X3); that kernel packs nothing -- ws may be NULL. */
 int dl4ds_conv2d_dgrad_fused_supported(int N, int H, int W, int Cq, int Cp, int KH, int KW, int math_mode);
 int dl4ds_conv2d_dgrad_fused(const float* dq, int dq_ld, const float* w, float* dz, int dz_ld,
                              const float* y_prod, int y_ld, int act, float* dbias,
