@@ -3,8 +3,8 @@ mkdir -p gpurun_out; TAG=${TAG:-r02fin}
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
 tail -3 gpurun_out/${TAG}_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log; tail -2 gpurun_out/${TAG}_smoke.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"thin_" -c 6 -o gpurun_out/${TAG}_thin16 -f python scratch/prof_layers.py tf32x3 > gpurun_out/${TAG}_thin16_ncu.log 2>&1
-tail -2 gpurun_out/${TAG}_thin16_ncu.log
+
+
 timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/${TAG}_bench_tf32x3.json 2> gpurun_out/${TAG}_bench.err
 python -c "
 import json
